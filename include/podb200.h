@@ -1,0 +1,215 @@
+/*
+ * podb200.h -- C-ABI of libpodb200.so: the B200 (sm_100a) hot path of POD-UQNN.
+ *
+ * The reference (pierremtb/POD-UQNN) has no FFI; its seam is a set of Python
+ * signatures.  Each entry point below names the reference interface it
+ * replaces (file:line relative to the reference tree).  The Python shims in
+ * pod_uqnn_b200/ bind these with ctypes and keep the reference's names and
+ * argument meaning; INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns int: PB_OK (0) or a negative PB_ERR_*;
+ *     pb_last_error(ctx) gives the message of the last failure on that context.
+ *   - all matrices are float64, row-major, with an explicit leading dimension
+ *     (ld, in elements).  "dev" pointers are device pointers on the context's
+ *     GPU (from pb_malloc or borrowed, e.g. torch.Tensor.data_ptr()); "host"
+ *     pointers are ordinary host memory.
+ *   - one context = one GPU, one stream.  Not thread-safe per context.
+ *   - outputs are caller-allocated.  Where a size is only known after the call
+ *     (the truncation rank n_L) the call is two-phase: pb_pod() returns n_L and
+ *     keeps the factors in the context, pb_pod_basis() fills the caller buffer.
+ *   - there is no CPU fallback: without a CUDA device pb_create() fails.
+ */
+#ifndef PODB200_H
+#define PODB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_OK                      0
+#define PB_ERR_CUDA               -1
+#define PB_ERR_SHAPE              -2
+#define PB_ERR_UNSUPPORTED_FIELD  -3
+#define PB_ERR_NOT_CONVERGED      -4
+#define PB_ERR_ARG                -5
+#define PB_ERR_NOMEM              -6
+
+/* analytic fields u(X, t, mu) (reference experiments/<case>/hyperparams.py) */
+#define PB_FIELD_SHEKEL   1   /* 1d_shekel/hyperparams.py:55-67  */
+#define PB_FIELD_ACKLEY   2   /* 2d_ackley/hyperparams.py:51-57  */
+#define PB_FIELD_BURGERS  3   /* 1dt_burger/hyperparams.py:45-55 */
+
+/* POD modes */
+#define PB_POD_GRAM      0  /* method of snapshots, one Gram pass                     */
+#define PB_POD_GRAM2     1  /* + second Gram pass on the rotated numerical-rank block */
+#define PB_POD_ACCURATE  2  /* full rotate + second Gram (Jacobi-SVD accuracy class)  */
+
+/* input normalisation of the surrogate (varneuralnetwork.py:10-12,75-86) */
+#define PB_NORM_NONE     0
+#define PB_NORM_MEANSTD  1
+#define PB_NORM_CENTER   2
+
+/* timers readable with pb_last_ms() */
+#define PB_T_GRAM       0
+#define PB_T_EIG        1
+#define PB_T_BASIS      2
+#define PB_T_PROJECT    3
+#define PB_T_RECON      4
+#define PB_T_SNAPSHOTS  5
+#define PB_T_PREDICT    6
+#define PB_T_POD_TOTAL  7
+#define PB_T_PASS2      8
+#define PB_T_COUNT      9
+
+typedef struct pb_ctx pb_ctx;
+
+/* ---- lifetime ---------------------------------------------------------- */
+int  pb_create(int device, pb_ctx** out);
+int  pb_destroy(pb_ctx* ctx);
+const char* pb_last_error(const pb_ctx* ctx);       /* ctx may be NULL: global message */
+int  pb_set_stream(pb_ctx* ctx, void* cuda_stream); /* NULL = the context's own stream */
+int  pb_sync(pb_ctx* ctx);
+int  pb_device_info(pb_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* mem_bytes);
+int  pb_last_ms(pb_ctx* ctx, int which, double* ms);  /* device time of the last op of that kind */
+int64_t pb_kernel_launches(pb_ctx* ctx);              /* kernels launched by this context so far */
+
+/* ---- device memory (plain cudaMalloc / copies on the context stream) ---- */
+int  pb_malloc(pb_ctx* ctx, size_t bytes, void** dev);
+int  pb_free(pb_ctx* ctx, void* dev);
+int  pb_memset(pb_ctx* ctx, void* dev, int value, size_t bytes);
+int  pb_upload(pb_ctx* ctx, void* dev, const void* host, size_t bytes);   /* H2D + sync */
+int  pb_download(pb_ctx* ctx, void* host, const void* dev, size_t bytes); /* D2H + sync */
+int  pb_upload_async(pb_ctx* ctx, void* dev, const void* host, size_t bytes);
+int  pb_download_async(pb_ctx* ctx, void* host, const void* dev, size_t bytes);
+int  pb_host_alloc(size_t bytes, void** host);        /* pinned host memory */
+int  pb_host_free(void* host);
+
+/* ---- snapshot evaluation ------------------------------------------------
+ * replaces poduqnn/acceleration.py:13-30 (loop_u) and :34-70 (loop_u_t) for
+ * the registered fields, noise-free branch.
+ *   X_dev   (dim, n_xyz) node coordinates = x_mesh[:, 1:].T
+ *   mu_dev  (n_s, n_mu)  parameter samples
+ *   t_dev   (n_t) time grid, or NULL / n_t = 0 for steady fields
+ *   U_dev   (n_v*n_xyz, ldu >= n_s*max(n_t,1)) snapshot matrix; column of
+ *           sample i, step j is i*n_t + j; row is v*n_xyz + node
+ *   row0, n_rows: the node range [row0, row0+n_rows) this call fills (row
+ *           sharding across GPUs); U_dev points at the first LOCAL row.
+ */
+int  pb_snapshots(pb_ctx* ctx, int field, int dim, int64_t n_xyz,
+                  const double* X_dev, int64_t n_s, int n_mu, const double* mu_dev,
+                  int n_t, const double* t_dev,
+                  int64_t row0, int64_t n_rows, double* U_dev, int64_t ldu);
+
+/* Known-answer matrix U = sum_k s_k phi_k psi_k^T (DCT-II vectors, s_k = 2^(-decay k)),
+ * rows [row0, row0+n_rows) of an n_h x n_s matrix, filled in HBM. */
+int  pb_dct_lowrank(pb_ctx* ctx, int64_t n_h, int64_t n_s, int r, double decay,
+                    int64_t row0, int64_t n_rows, double* U_dev, int64_t ldu);
+
+/* ---- POD ----------------------------------------------------------------
+ * replaces poduqnn/pod.py:7-47 (perform_pod).
+ *
+ * Single-GPU:   pb_pod(ctx, U, n_h, n_st, ld, eps, n_L_in, mode, &n_L)
+ * Row-sharded:  every rank calls pb_gram() on its row slab, all-reduces the
+ *               n_st x n_st Gram (NCCL sum), calls pb_pod_from_gram() (the
+ *               small eigensolve is replicated and deterministic), and
+ *               pb_pod_basis() on its slab.  For the second-pass modes the
+ *               rank repeats with pb_pod_pass2_gram() / pb_pod_pass2_finish().
+ *
+ * pb_gram:  G (n_cols x n_cols, ld = n_cols) = A^T A over the n_rows local rows.
+ */
+int  pb_gram(pb_ctx* ctx, const double* A_dev, int64_t n_rows, int64_t n_cols, int64_t lda,
+             double* G_dev);
+/* C (ka x kb, ld = kb) = A^T B over n_rows rows (projection-shaped product). */
+int  pb_gemm_tn(pb_ctx* ctx, const double* A_dev, int64_t lda, int64_t ka,
+                const double* B_dev, int64_t ldb, int64_t kb, int64_t n_rows, double* C_dev);
+/* Y (n_rows x k, ldy) = A (n_rows x m, lda) * B (m x k, ldb). */
+int  pb_gemm_nn(pb_ctx* ctx, const double* A_dev, int64_t lda, int64_t n_rows, int64_t m,
+                const double* B_dev, int64_t ldb, int64_t k, double* Y_dev, int64_t ldy);
+
+/* Eigen-decomposition of the (all-reduced) Gram + truncation rank (pod.py:22-32).
+ * mode as above; eps / n_L_in as perform_pod(U, eps, n_L).  On return *n_L is the
+ * rank and *n_keep the number of rotated columns the second pass needs (0 for
+ * PB_POD_GRAM).  sigma_host (nullable) receives min(n_cols, capacity) singular
+ * values, zero beyond the numerical rank. */
+int  pb_pod_from_gram(pb_ctx* ctx, const double* G_dev, int64_t n_cols, double eps, int n_L_in,
+                      int mode, int* n_L, int* n_keep);
+/* Second pass (modes GRAM2 / ACCURATE): Y = A W_keep on the local slab, G2 = Y^T Y.
+ * Y_dev is caller-allocated (n_rows x n_keep, ld = n_keep), G2_dev (n_keep x n_keep). */
+int  pb_pod_pass2_gram(pb_ctx* ctx, const double* A_dev, int64_t n_rows, int64_t lda,
+                       double* Y_dev, double* G2_dev);
+int  pb_pod_pass2_finish(pb_ctx* ctx, const double* G2_dev, double eps, int n_L_in, int* n_L);
+/* V (n_rows x n_L, ldv) for the local slab.  A_dev is the slab of U (tall case).
+ * After a second pass Y_dev must be the buffer filled by pb_pod_pass2_gram (else NULL). */
+int  pb_pod_basis(pb_ctx* ctx, const double* A_dev, int64_t n_rows, int64_t lda,
+                  const double* Y_dev, double* V_dev, int64_t ldv);
+/* singular values of the last decomposition (descending; zero beyond numerical rank) */
+int  pb_pod_sigma(pb_ctx* ctx, double* sigma_host, int64_t capacity, int64_t* count);
+/* right factor of the last decomposition: Z (n_cols x n_L, ld = n_L), V = A Z diag(1/sigma) */
+int  pb_pod_right(pb_ctx* ctx, double* Z_dev, int64_t ldz);
+
+/* One-call single-GPU POD of a device matrix (tall or wide).  V via pb_pod_basis_full(). */
+int  pb_pod(pb_ctx* ctx, const double* U_dev, int64_t n_h, int64_t n_st, int64_t ldu,
+            double eps, int n_L_in, int mode, int* n_L);
+int  pb_pod_basis_full(pb_ctx* ctx, const double* U_dev, int64_t n_h, int64_t n_st, int64_t ldu,
+                       double* V_dev, int64_t ldv);
+
+/* replaces poduqnn/pod.py:51-68 (perform_fast_pod): per-sample POD with eps_init on the
+ * n_h x n_t column blocks of U (sample-major columns, as loop_u_t writes them), unweighted
+ * concatenation, global POD with eps.  ranks_host (nullable, n_s ints) gets the per-sample ranks. */
+int  pb_fast_pod(pb_ctx* ctx, const double* U_dev, int64_t n_h, int n_t, int64_t n_s, int64_t ldu,
+                 double eps, double eps_init, int mode, int* n_L, int* ranks_host);
+int  pb_fast_pod_basis(pb_ctx* ctx, double* V_dev, int64_t ldv);   /* V (n_h x n_L) of the last pb_fast_pod */
+/* (n_h, n_t, n_s) C-order U_struct  ->  (n_h, n_s*n_t) sample-major matrix (and back) */
+int  pb_struct_to_matrix(pb_ctx* ctx, const double* Us_dev, int64_t n_h, int n_t, int64_t n_s,
+                         double* U_dev, int64_t ldu);
+int  pb_matrix_to_struct(pb_ctx* ctx, const double* U_dev, int64_t ldu, int64_t n_h, int n_t,
+                         int64_t n_s, double* Us_dev);
+
+/* ---- projection / reconstruction ----------------------------------------
+ * replaces podnnmodel.py:435-437 (project_to_v), :431-433 (project_to_U), :247-253.
+ *   pb_project:      v (n x n_L, ld = n_L) = (V^T U)^T for the local slab; partial sums
+ *                    over the slab rows (all-reduce across ranks when sharded).
+ *   pb_reconstruct:  U_pod (n_rows x n, ld) = V v^T; pod_sig (n_rows, nullable) =
+ *                    mean_j |U - U_pod| / 2  (= np.stack((U,U_pod),-1).std(-1).mean(-1)).
+ *                    U_pod_dev may be NULL when only pod_sig is wanted.
+ */
+int  pb_project(pb_ctx* ctx, const double* V_dev, int64_t ldv, int n_L,
+                const double* U_dev, int64_t ldu, int64_t n_rows, int64_t n, double* v_dev);
+int  pb_reconstruct(pb_ctx* ctx, const double* V_dev, int64_t ldv, int n_L,
+                    const double* v_dev, int64_t n, int64_t n_rows,
+                    const double* U_dev, int64_t ldu,
+                    double* U_pod_dev, int64_t ldp, double* pod_sig_dev);
+
+/* ---- deep-ensemble surrogate ---------------------------------------------
+ * replaces varneuralnetwork.py:42-62,75-86,154-160 (member forward) and
+ * podnnmodel.py:314-328 (predict_v mixture moments).
+ *   dims[n_layers+1] = [n_d, h_1, ..., h_k, 2*n_L];   weights_dev = for each member,
+ *   for each layer: W (in x out, row-major) then b (out), packed back to back.
+ *   X_dev (N x n_d).  Outputs v_mean, v_sig (N x n_L).
+ */
+int  pb_ensemble_predict(pb_ctx* ctx, int n_members, int n_layers, const int* dims,
+                         const double* weights_dev, int norm_kind,
+                         const double* norm_a_dev, const double* norm_b_dev, double soft_0,
+                         const double* X_dev, int64_t N, double* v_mean_dev, double* v_sig_dev);
+/* closed-form U-level moments of PodnnModel.predict (podnnmodel.py:366-379):
+ * U_mean = V v_mean^T, U_sig = sqrt((V*V) (v_sig^2)^T); plus optional Monte-Carlo variant. */
+int  pb_predict_U(pb_ctx* ctx, const double* V_dev, int64_t ldv, int64_t n_rows, int n_L,
+                  const double* v_mean_dev, const double* v_sig_dev, int64_t N,
+                  int samples, uint64_t seed, double* U_mean_dev, double* U_sig_dev, int64_t ldo);
+
+/* ---- measurement helpers (used by bench.py; not on the product path) ------ */
+/* kind: 0 = DFMA register loop, 1 = DMMA m8n8k4 loop, 2 = both pipes mixed.  Returns TFLOP/s. */
+int  pb_probe_fp64_peak(pb_ctx* ctx, int kind, double* tflops);
+/* device-to-device copy of `bytes` (read+write counted).  Returns GB/s. */
+int  pb_probe_hbm_copy(pb_ctx* ctx, size_t bytes, double* gbs);
+/* write `bytes` of scratch to evict L2 between timed iterations */
+int  pb_flush_l2(pb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PODB200_H */

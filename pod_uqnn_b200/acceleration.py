@@ -1,0 +1,80 @@
+"""Snapshot-evaluation loops -- same names and argument order as the reference's
+poduqnn/acceleration.py (loop_u :13-30, loop_u_t :34-70), evaluated by CUDA kernels that
+write the snapshot matrix directly in HBM (csrc/fields.cu).
+
+Differences a caller can observe: `u` must be a registered field (fields.resolve), and the
+noise branches (u_noise / x_noise > 0, numba's unseeded RNG in the reference) are not built:
+they raise NotImplementedError.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .fields import resolve
+
+
+def snapshots_device(ctx, u, X, mu_lhs, n_t=0, t_min=0., t_max=0., row0=0, n_rows=None, out=None):
+    """Fill (and return) the device snapshot matrix for nodes [row0, row0+n_rows).
+
+    X is (dim, n_xyz) as the reference passes it (x_mesh[:, 1:].T).  Returns
+    (U_dev (n_rows, n_st), X_v host (n_st, n_d), t host or None).
+    """
+    f = resolve(u)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    mu = np.ascontiguousarray(mu_lhs, dtype=np.float64)
+    dim, n_xyz = X.shape
+    n_s, n_mu = mu.shape
+    has_t = n_t > 0
+    if has_t != f.has_t:
+        raise ValueError(f"field '{f.name}' is {'time-dependent' if f.has_t else 'steady'}; got n_t={n_t}")
+    n_rows = n_xyz - row0 if n_rows is None else n_rows
+    n_st = n_s * (n_t if has_t else 1)
+    t = np.linspace(t_min, t_max, n_t) if has_t else None      # acceleration.py:38
+    Xd, mud = ctx.to_device(X), ctx.to_device(mu)
+    td = ctx.to_device(t) if has_t else None
+    U = out if out is not None else ctx.alloc(n_rows, n_st)
+    ctx.check(_lib.lib().pb_snapshots(ctx.h, f.field_id, dim, n_xyz, Xd.ptr, n_s, n_mu, mud.ptr,
+                                      n_t if has_t else 0, td.ptr if has_t else None,
+                                      row0, n_rows, U.ptr, U.ld))
+    if has_t:   # X_v rows [t_j, mu_i...], acceleration.py:53
+        X_v = np.hstack((np.tile(t, n_s)[:, None], np.repeat(mu, n_t, axis=0)))
+    else:       # acceleration.py:19
+        X_v = mu.copy()
+    return U, X_v, t
+
+
+def _no_noise(u_noise, x_noise):
+    if u_noise > 0. or x_noise > 0.:
+        raise NotImplementedError("noisy snapshots (u_noise / x_noise > 0) are outside the CUDA hot path")
+
+
+def loop_u(u, n_h, X_v, U, U_no_noise, X, mu_lhs, u_noise=0., x_noise=0., *, ctx=None):
+    """Reference signature (acceleration.py:13): fills the caller's X_v, U, U_no_noise."""
+    _no_noise(u_noise, x_noise)
+    ctx = ctx or _lib.default_context()
+    Ud, Xv, _ = snapshots_device(ctx, u, X, mu_lhs)
+    if Ud.shape != (n_h, mu_lhs.shape[0]):
+        raise ValueError(f"n_h={n_h} does not match the mesh ({Ud.shape[0]} nodes, n_v=1)")
+    X_v[...] = Xv
+    U[...] = Ud.download()
+    U_no_noise[...] = U
+    return X_v, U, U, U_no_noise
+
+
+def loop_u_t(u, n_t, n_v, n_xyz, n_h, X_v, U, U_no_noise, U_struct, X, mu_lhs, t_min, t_max,
+             u_noise=0., x_noise=0., *, ctx=None):
+    """Reference signature (acceleration.py:34-35): fills X_v, U, U_no_noise, U_struct."""
+    _no_noise(u_noise, x_noise)
+    if n_v != 1:
+        raise NotImplementedError("the registered analytic fields have n_v = 1")
+    ctx = ctx or _lib.default_context()
+    Ud, Xv, _ = snapshots_device(ctx, u, X, mu_lhs, n_t, t_min, t_max)
+    n_s = mu_lhs.shape[0]
+    X_v[...] = Xv
+    U[...] = Ud.download()
+    U_no_noise[...] = U
+    Us = ctx.alloc(n_h, n_t, n_s)       # U_struct[:, :, i] = U[:, s:e], acceleration.py:69
+    ctx.check(_lib.lib().pb_matrix_to_struct(ctx.h, Ud.ptr, Ud.ld, n_h, n_t, n_s, Us.ptr))
+    U_struct[...] = Us.download()
+    return X_v, U, U_struct, U_no_noise

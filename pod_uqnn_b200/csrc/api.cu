@@ -1,0 +1,433 @@
+// C-ABI of libpodb200.so: context, memory, POD orchestration, projection / reconstruction.
+// See include/podb200.h for the contract and the reference interfaces each entry replaces.
+#include "common.cuh"
+#include <cfloat>
+#include <algorithm>
+#include <mutex>
+
+static std::string g_err;
+static std::mutex g_err_mu;
+const char* pb_set_global_error(const std::string& s) {
+    std::lock_guard<std::mutex> l(g_err_mu); g_err = s; return g_err.c_str();
+}
+
+int pb_reserve(pb_ctx* ctx, double** p, size_t* cap, size_t elems) {
+    if (*cap >= elems && *p) return PB_OK;
+    if (*p) { PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(*p); *p = nullptr; *cap = 0; }
+    cudaError_t e = cudaMalloc(p, elems * sizeof(double));
+    if (e != cudaSuccess) { cudaGetLastError(); PB_FAIL(ctx, PB_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", elems * sizeof(double), cudaGetErrorString(e)); }
+    *cap = elems;
+    return PB_OK;
+}
+int pb_reserve_int(pb_ctx* ctx, int** p, size_t* cap, size_t elems) {
+    if (*cap >= elems && *p) return PB_OK;
+    if (*p) { PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(*p); *p = nullptr; *cap = 0; }
+    cudaError_t e = cudaMalloc(p, elems * sizeof(int));
+    if (e != cudaSuccess) { cudaGetLastError(); PB_FAIL(ctx, PB_ERR_NOMEM, "cudaMalloc(%zu bytes) failed", elems * sizeof(int)); }
+    *cap = elems;
+    return PB_OK;
+}
+
+namespace {
+struct Timer {
+    pb_ctx* c; int which; cudaEvent_t a, b;
+    Timer(pb_ctx* ctx, int w, bool inner = false) : c(ctx), which(w), a(inner ? ctx->ev2 : ctx->ev0), b(inner ? ctx->ev3 : ctx->ev1) {
+        cudaEventRecord(a, c->stream);
+    }
+    void stop() {
+        cudaEventRecord(b, c->stream); cudaEventSynchronize(b);
+        float ms = 0; cudaEventElapsedTime(&ms, a, b); c->ms[which] = ms;
+    }
+};
+}  // namespace
+
+extern "C" {
+
+// ---------------------------------------------------------------- lifetime
+int pb_create(int device, pb_ctx** out) {
+    if (!out) return PB_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        pb_set_global_error(std::string("pb_create: no CUDA device (") + cudaGetErrorString(e) + "); libpodb200 has no CPU fallback");
+        return PB_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { pb_set_global_error("pb_create: bad device index"); return PB_ERR_ARG; }
+    pb_ctx* ctx = new pb_ctx();
+    ctx->device = device;
+    PB_CUDA(ctx, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PB_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        pb_set_global_error("pb_create: libpodb200 is built for sm_100a (Blackwell B200) only");
+        delete ctx; return PB_ERR_CUDA;
+    }
+    PB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    PB_CUDA(ctx, cudaEventCreate(&ctx->ev0)); PB_CUDA(ctx, cudaEventCreate(&ctx->ev1));
+    PB_CUDA(ctx, cudaEventCreate(&ctx->ev2)); PB_CUDA(ctx, cudaEventCreate(&ctx->ev3));
+    PB_CUDA(ctx, cudaMalloc(&ctx->d_int, 64 * sizeof(int)));
+    PB_CUDA(ctx, cudaMemset(ctx->d_int, 0, 64 * sizeof(int)));
+    PB_CUDA(ctx, cudaMallocHost(&ctx->h_int, 64 * sizeof(int)));
+    *out = ctx;
+    return PB_OK;
+}
+
+int pb_destroy(pb_ctx* ctx) {
+    if (!ctx) return PB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    void* bufs[] = {ctx->ws, ctx->flush, ctx->At, ctx->At2, ctx->sig, ctx->nrm, ctx->sig2, ctx->nrm2, ctx->perm,
+                    ctx->perm2, ctx->Bmat, ctx->Wk, ctx->small, ctx->Gbuf, ctx->G2buf, ctx->Ybuf, ctx->ATbuf, ctx->Uf, ctx->d_int};
+    for (void* b : bufs) if (b) cudaFree(b);
+    if (ctx->h_int) cudaFreeHost(ctx->h_int);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return PB_OK;
+}
+
+const char* pb_last_error(const pb_ctx* ctx) {
+    if (ctx) return ctx->err.c_str();
+    std::lock_guard<std::mutex> l(g_err_mu); return g_err.c_str();
+}
+int pb_set_stream(pb_ctx* ctx, void* s) { if (!ctx) return PB_ERR_ARG; ctx->stream = s ? (cudaStream_t)s : ctx->own_stream; return PB_OK; }
+int pb_sync(pb_ctx* ctx) { if (!ctx) return PB_ERR_ARG; PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return PB_OK; }
+int pb_device_info(pb_ctx* ctx, int* sm, int* maj, int* min_, size_t* mem) {
+    if (!ctx) return PB_ERR_ARG;
+    cudaDeviceProp p; PB_CUDA(ctx, cudaGetDeviceProperties(&p, ctx->device));
+    if (sm) *sm = p.multiProcessorCount; if (maj) *maj = p.major; if (min_) *min_ = p.minor; if (mem) *mem = p.totalGlobalMem;
+    return PB_OK;
+}
+int pb_last_ms(pb_ctx* ctx, int which, double* ms) {
+    if (!ctx || which < 0 || which >= PB_T_COUNT || !ms) return PB_ERR_ARG; *ms = ctx->ms[which]; return PB_OK;
+}
+int64_t pb_kernel_launches(pb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------- memory
+int pb_malloc(pb_ctx* ctx, size_t bytes, void** dev) {
+    if (!ctx || !dev) return PB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaMalloc(dev, bytes ? bytes : 8);
+    if (e != cudaSuccess) { cudaGetLastError(); PB_FAIL(ctx, PB_ERR_NOMEM, "pb_malloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
+    return PB_OK;
+}
+int pb_free(pb_ctx* ctx, void* dev) { if (!ctx) return PB_ERR_ARG; if (dev) { cudaStreamSynchronize(ctx->stream); PB_CUDA(ctx, cudaFree(dev)); } return PB_OK; }
+int pb_memset(pb_ctx* ctx, void* dev, int v, size_t bytes) { if (!ctx) return PB_ERR_ARG; PB_CUDA(ctx, cudaMemsetAsync(dev, v, bytes, ctx->stream)); return PB_OK; }
+int pb_upload_async(pb_ctx* ctx, void* dev, const void* host, size_t bytes) {
+    if (!ctx) return PB_ERR_ARG; PB_CUDA(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream)); return PB_OK;
+}
+int pb_download_async(pb_ctx* ctx, void* host, const void* dev, size_t bytes) {
+    if (!ctx) return PB_ERR_ARG; PB_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream)); return PB_OK;
+}
+int pb_upload(pb_ctx* ctx, void* dev, const void* host, size_t bytes) { PB_TRY(pb_upload_async(ctx, dev, host, bytes)); return pb_sync(ctx); }
+int pb_download(pb_ctx* ctx, void* host, const void* dev, size_t bytes) { PB_TRY(pb_download_async(ctx, host, dev, bytes)); return pb_sync(ctx); }
+int pb_host_alloc(size_t bytes, void** host) {
+    if (!host) return PB_ERR_ARG;
+    cudaError_t e = cudaMallocHost(host, bytes ? bytes : 8);
+    if (e != cudaSuccess) { cudaGetLastError(); pb_set_global_error(std::string("pb_host_alloc: ") + cudaGetErrorString(e)); return PB_ERR_NOMEM; }
+    return PB_OK;
+}
+int pb_host_free(void* host) { if (host) cudaFreeHost(host); return PB_OK; }
+
+// ---------------------------------------------------------------- products
+int pb_gram(pb_ctx* ctx, const double* A, int64_t rows, int64_t cols, int64_t lda, double* G) {
+    if (!ctx) return PB_ERR_ARG;
+    if (lda < cols) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_gram: lda %lld < n_cols %lld", (long long)lda, (long long)cols);
+    Timer t(ctx, PB_T_GRAM);
+    PB_TRY(pbi_gemm_tn(ctx, A, lda, cols, A, lda, cols, rows, G, cols, 1));
+    t.stop();
+    return PB_OK;
+}
+int pb_gemm_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const double* B, int64_t ldb, int64_t kb,
+               int64_t rows, double* C) {
+    if (!ctx) return PB_ERR_ARG;
+    return pbi_gemm_tn(ctx, A, lda, ka, B, ldb, kb, rows, C, kb, 0);
+}
+int pb_gemm_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m, const double* B, int64_t ldb,
+               int64_t k, double* Y, int64_t ldy) {
+    if (!ctx) return PB_ERR_ARG;
+    return pbi_gemm_nn(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, nullptr, 0, nullptr);
+}
+
+// ---------------------------------------------------------------- POD
+static int finish_rank(pb_ctx* ctx, const double* sig_dev, int64_t count, int avail, double eps, int n_L_in, int* n_L) {
+    int nl = 0;
+    if (n_L_in > 0) {
+        if (n_L_in > avail) PB_FAIL(ctx, PB_ERR_SHAPE, "requested n_L=%d exceeds the numerical rank %d", n_L_in, avail);
+        nl = n_L_in;
+    } else {
+        PB_TRY(pbi_rank(ctx, sig_dev, count, eps, &nl));
+        if (nl > avail) nl = avail;
+    }
+    ctx->n_L = nl; *n_L = nl;
+    return PB_OK;
+}
+
+static int fetch_sigma(pb_ctx* ctx, const double* sig_dev, int64_t count, int64_t total) {
+    ctx->sigma_host.assign((size_t)total, 0.);
+    PB_CUDA(ctx, cudaMemcpyAsync(ctx->sigma_host.data(), sig_dev, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB_OK;
+}
+
+int pb_pod_from_gram(pb_ctx* ctx, const double* G, int64_t m, double eps, int n_L_in, int mode, int* n_L, int* n_keep) {
+    if (!ctx || !n_L) return PB_ERR_ARG;
+    if (mode < PB_POD_GRAM || mode > PB_POD_ACCURATE) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod: unknown mode %d", mode);
+    if (!(eps >= 0.) || eps >= 1.) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod: eps must be in [0, 1)");
+    Timer t(ctx, PB_T_EIG);
+    ctx->m = m; ctx->mode = mode; ctx->pass2_done = false;
+    PB_TRY(pb_reserve(ctx, &ctx->sig, &ctx->sig_cap, (size_t)m + 32));
+    PB_TRY(pb_reserve(ctx, &ctx->nrm, &ctx->nrm_cap, (size_t)m + 32));
+    PB_TRY(pb_reserve_int(ctx, &ctx->perm, &ctx->perm_cap, (size_t)m + 64));
+    // eps == 0 asks for every mode (pod.py default): keep the full factor as well
+    const bool full = (mode == PB_POD_ACCURATE) || (eps == 0. && n_L_in == 0);
+    const double tol_rel = full ? 0. : 4. * DBL_EPSILON;
+    const double shift_rel = full ? 2. * (double)m * DBL_EPSILON : 0.;
+    PB_TRY(pbi_eig_psd(ctx, G, m, tol_rel, shift_rel, &ctx->At, &ctx->At_cap, ctx->sig, ctx->nrm, ctx->perm,
+                       &ctx->r, &ctx->sweeps1, 40));
+    ctx->n_keep = (mode == PB_POD_GRAM) ? 0 : ctx->r;
+    if (n_keep) *n_keep = ctx->n_keep;
+    PB_TRY(fetch_sigma(ctx, ctx->sig, m, m));
+    PB_TRY(finish_rank(ctx, ctx->sig, m, ctx->r, eps, n_L_in, n_L));
+    t.stop();
+    return PB_OK;
+}
+
+int pb_pod_pass2_gram(pb_ctx* ctx, const double* A, int64_t rows, int64_t lda, double* Y, double* G2) {
+    if (!ctx) return PB_ERR_ARG;
+    const int keep = ctx->n_keep; const int64_t m = ctx->m;
+    if (keep <= 0) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod_pass2_gram: the last decomposition has no second pass (mode GRAM)");
+    PB_TRY(pb_reserve(ctx, &ctx->Wk, &ctx->Wk_cap, (size_t)m * keep));
+    PB_TRY(pbi_factor_to_right(ctx, ctx->At, m, keep, ctx->perm, ctx->nrm, nullptr, ctx->Wk, keep));
+    PB_TRY(pbi_gemm_nn(ctx, A, lda, rows, m, ctx->Wk, keep, keep, Y, keep, nullptr, 0, nullptr));
+    PB_TRY(pbi_gemm_tn(ctx, Y, keep, keep, Y, keep, keep, rows, G2, keep, 1));
+    return PB_OK;
+}
+
+int pb_pod_pass2_finish(pb_ctx* ctx, const double* G2, double eps, int n_L_in, int* n_L) {
+    if (!ctx || !n_L) return PB_ERR_ARG;
+    const int keep = ctx->n_keep;
+    if (keep <= 0) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod_pass2_finish: no second pass pending");
+    PB_TRY(pb_reserve(ctx, &ctx->sig2, &ctx->sig2_cap, (size_t)keep + 32));
+    PB_TRY(pb_reserve(ctx, &ctx->nrm2, &ctx->nrm2_cap, (size_t)keep + 32));
+    PB_TRY(pb_reserve_int(ctx, &ctx->perm2, &ctx->perm2_cap, (size_t)keep + 64));
+    // G2 = D (I + E) D is graded and nearly diagonal: no shift, no truncation (relative accuracy)
+    PB_TRY(pbi_eig_psd(ctx, G2, keep, 0., 0., &ctx->At2, &ctx->At2_cap, ctx->sig2, ctx->nrm2, ctx->perm2,
+                       &ctx->r2, &ctx->sweeps2, 40));
+    PB_TRY(fetch_sigma(ctx, ctx->sig2, keep, ctx->m));
+    PB_TRY(finish_rank(ctx, ctx->sig2, keep, ctx->r2, eps, n_L_in, n_L));
+    ctx->pass2_done = true;
+    return PB_OK;
+}
+
+int pb_pod_basis(pb_ctx* ctx, const double* A, int64_t rows, int64_t lda, const double* Y, double* V, int64_t ldv) {
+    if (!ctx) return PB_ERR_ARG;
+    const int nl = ctx->n_L;
+    if (nl <= 0) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod_basis: no decomposition available");
+    Timer t(ctx, PB_T_BASIS);
+    if (ctx->pass2_done) {
+        if (!Y) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod_basis: second-pass modes need the rotated block Y");
+        const int keep = ctx->n_keep;
+        PB_TRY(pb_reserve(ctx, &ctx->Bmat, &ctx->B_cap, (size_t)keep * nl));
+        PB_TRY(pbi_factor_to_right(ctx, ctx->At2, keep, nl, ctx->perm2, ctx->nrm2, ctx->sig2, ctx->Bmat, nl));
+        PB_TRY(pbi_gemm_nn(ctx, Y, keep, rows, keep, ctx->Bmat, nl, nl, V, ldv, nullptr, 0, nullptr));
+    } else {
+        if (ctx->mode != PB_POD_GRAM) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod_basis: second pass not finished");
+        const int64_t m = ctx->m;
+        PB_TRY(pb_reserve(ctx, &ctx->Bmat, &ctx->B_cap, (size_t)m * nl));
+        PB_TRY(pbi_factor_to_right(ctx, ctx->At, m, nl, ctx->perm, ctx->nrm, ctx->sig, ctx->Bmat, nl));
+        PB_TRY(pbi_gemm_nn(ctx, A, lda, rows, m, ctx->Bmat, nl, nl, V, ldv, nullptr, 0, nullptr));
+    }
+    t.stop();
+    return PB_OK;
+}
+
+int pb_pod_sigma(pb_ctx* ctx, double* sigma_host, int64_t capacity, int64_t* count) {
+    if (!ctx) return PB_ERR_ARG;
+    int64_t n = std::min<int64_t>(capacity, (int64_t)ctx->sigma_host.size());
+    if (sigma_host && n > 0) memcpy(sigma_host, ctx->sigma_host.data(), sizeof(double) * (size_t)n);
+    if (count) *count = (int64_t)ctx->sigma_host.size();
+    return PB_OK;
+}
+
+int pb_pod_right(pb_ctx* ctx, double* Z, int64_t ldz) {
+    if (!ctx) return PB_ERR_ARG;
+    const int nl = ctx->n_L; const int64_t m = ctx->m;
+    if (nl <= 0) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod_right: no decomposition available");
+    if (ctx->pass2_done) {
+        const int keep = ctx->n_keep;
+        PB_TRY(pb_reserve(ctx, &ctx->Bmat, &ctx->B_cap, (size_t)keep * nl));
+        PB_TRY(pbi_factor_to_right(ctx, ctx->At2, keep, nl, ctx->perm2, ctx->nrm2, nullptr, ctx->Bmat, nl));
+        PB_TRY(pbi_gemm_nn(ctx, ctx->Wk, keep, m, keep, ctx->Bmat, nl, nl, Z, ldz, nullptr, 0, nullptr));
+    } else {
+        PB_TRY(pbi_factor_to_right(ctx, ctx->At, m, nl, ctx->perm, ctx->nrm, nullptr, Z, ldz));
+    }
+    return PB_OK;
+}
+
+int pb_pod(pb_ctx* ctx, const double* U, int64_t n_h, int64_t n_st, int64_t ldu, double eps, int n_L_in, int mode, int* n_L) {
+    if (!ctx || !n_L) return PB_ERR_ARG;
+    if (n_h <= 0 || n_st <= 0 || ldu < n_st) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod: bad shape (%lld x %lld, ld %lld)",
+                                                       (long long)n_h, (long long)n_st, (long long)ldu);
+    cudaEventRecord(ctx->ev2, ctx->stream);
+    const bool wide = n_h < n_st;
+    const double* A = U; int64_t rows = n_h, m = n_st, lda = ldu;
+    if (wide) {   // POD of U^T: its right singular vectors are the modes themselves
+        PB_TRY(pb_reserve(ctx, &ctx->ATbuf, &ctx->AT_cap, (size_t)n_st * n_h));
+        PB_TRY(pbi_transpose(ctx, U, n_h, n_st, ldu, ctx->ATbuf, n_h));
+        A = ctx->ATbuf; rows = n_st; m = n_h; lda = n_h;
+    }
+    if (m > 8192) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod: min(n_h, n_st) = %lld exceeds 8192", (long long)m);
+    PB_TRY(pb_reserve(ctx, &ctx->Gbuf, &ctx->G_cap, (size_t)m * m));
+    PB_TRY(pb_gram(ctx, A, rows, m, lda, ctx->Gbuf));
+    int keep = 0;
+    PB_TRY(pb_pod_from_gram(ctx, ctx->Gbuf, m, eps, n_L_in, mode, n_L, &keep));
+    ctx->wide = wide;
+    ctx->ms[PB_T_PASS2] = 0.;
+    if (keep > 0) {
+        Timer t2(ctx, PB_T_PASS2);
+        PB_TRY(pb_reserve(ctx, &ctx->Ybuf, &ctx->Y_cap, (size_t)rows * keep));
+        PB_TRY(pb_reserve(ctx, &ctx->G2buf, &ctx->G2_cap, (size_t)keep * keep));
+        PB_TRY(pb_pod_pass2_gram(ctx, A, rows, lda, ctx->Ybuf, ctx->G2buf));
+        PB_TRY(pb_pod_pass2_finish(ctx, ctx->G2buf, eps, n_L_in, n_L));
+        t2.stop();
+    }
+    cudaEventRecord(ctx->ev3, ctx->stream); cudaEventSynchronize(ctx->ev3);
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3); ctx->ms[PB_T_POD_TOTAL] = ms;
+    return PB_OK;
+}
+
+int pb_pod_basis_full(pb_ctx* ctx, const double* U, int64_t n_h, int64_t n_st, int64_t ldu, double* V, int64_t ldv) {
+    if (!ctx) return PB_ERR_ARG;
+    if (ldv < ctx->n_L) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod_basis_full: ldv %lld < n_L %d", (long long)ldv, ctx->n_L);
+    if (!ctx->wide) return pb_pod_basis(ctx, U, n_h, ldu, ctx->pass2_done ? ctx->Ybuf : nullptr, V, ldv);
+    (void)n_st;
+    Timer t(ctx, PB_T_BASIS);
+    PB_TRY(pb_pod_right(ctx, V, ldv));        // wide: the modes are the right factor of U^T
+    t.stop();
+    return PB_OK;
+}
+
+// ------------------------------------------------- two-step POD (pod.py:51-68)
+int pb_fast_pod(pb_ctx* ctx, const double* U, int64_t n_h, int n_t, int64_t n_s, int64_t ldu,
+                double eps, double eps_init, int mode, int* n_L, int* ranks_host) {
+    if (!ctx || !n_L) return PB_ERR_ARG;
+    if (n_t <= 0 || n_s <= 0 || ldu < n_s * n_t) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_fast_pod: bad shape");
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, ctx->stream);
+    // stage 1: per-sample bases T_k, packed side by side into U_f (n_h x sum r_k); r_k <= min(n_h, n_t)
+    const int64_t cap_per = std::min<int64_t>(n_h, n_t);
+    const int64_t ldf = cap_per * n_s;
+    int rc = pb_reserve(ctx, &ctx->Uf, &ctx->Uf_cap, (size_t)n_h * ldf);
+    int64_t off = 0;
+    for (int64_t k = 0; k < n_s && rc == PB_OK; ++k) {
+        int rk = 0;
+        const double* Uk = U + k * n_t;
+        rc = pb_pod(ctx, Uk, n_h, n_t, ldu, eps_init, 0, mode, &rk);
+        if (rc == PB_OK) rc = pb_pod_basis_full(ctx, Uk, n_h, n_t, ldu, ctx->Uf + off, ldf);
+        if (ranks_host) ranks_host[k] = rk;
+        off += rk;
+    }
+    // stage 2: global POD of the unweighted concatenation (usually wide: n_h < sum r_k)
+    if (rc == PB_OK) rc = pb_pod(ctx, ctx->Uf, n_h, off, ldf, eps, 0, mode, n_L);
+    ctx->uf_rows = n_h; ctx->uf_cols = off; ctx->uf_ld = ldf;
+    cudaEventRecord(e1, ctx->stream); cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ctx->ms[PB_T_POD_TOTAL] = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
+}
+
+int pb_fast_pod_basis(pb_ctx* ctx, double* V, int64_t ldv) {
+    if (!ctx) return PB_ERR_ARG;
+    if (!ctx->Uf || ctx->uf_cols <= 0) PB_FAIL(ctx, PB_ERR_ARG, "pb_fast_pod_basis: call pb_fast_pod first");
+    return pb_pod_basis_full(ctx, ctx->Uf, ctx->uf_rows, ctx->uf_cols, ctx->uf_ld, V, ldv);
+}
+
+namespace {
+// (n_h, n_t, n_s) C-order  <->  (n_h, n_s * n_t) with column i * n_t + j
+__global__ void struct_permute_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t n_h,
+                                      int n_t, int64_t n_s, int64_t ldu, int to_matrix) {
+    __shared__ double tile[32][33];
+    // per row h: an (n_t x n_s) <-> (n_s x n_t) transpose
+    const int64_t h = blockIdx.z;
+    const int64_t s0 = (int64_t)blockIdx.x * 32; const int t0 = blockIdx.y * 32;
+    if (to_matrix) {
+        for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+            int t = t0 + y; int64_t s = s0 + threadIdx.x;
+            tile[y][threadIdx.x] = (t < n_t && s < n_s) ? in[(h * n_t + t) * n_s + s] : 0.;
+        }
+        __syncthreads();
+        for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+            int64_t s = s0 + y; int t = t0 + threadIdx.x;
+            if (s < n_s && t < n_t) out[h * ldu + s * n_t + t] = tile[threadIdx.x][y];
+        }
+    } else {
+        for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+            int64_t s = s0 + y; int t = t0 + threadIdx.x;
+            tile[y][threadIdx.x] = (s < n_s && t < n_t) ? in[h * ldu + s * n_t + t] : 0.;
+        }
+        __syncthreads();
+        for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+            int t = t0 + y; int64_t s = s0 + threadIdx.x;
+            if (t < n_t && s < n_s) out[(h * n_t + t) * n_s + s] = tile[threadIdx.x][y];
+        }
+    }
+}
+int struct_permute(pb_ctx* ctx, const double* in, double* out, int64_t n_h, int n_t, int64_t n_s, int64_t ldu, int to_matrix) {
+    if (n_h <= 0 || n_t <= 0 || n_s <= 0 || ldu < n_s * n_t) PB_FAIL(ctx, PB_ERR_SHAPE, "struct permute: bad shape");
+    for (int64_t h0 = 0; h0 < n_h; h0 += 65535) {       // grid.z limit
+        int64_t nh = std::min<int64_t>(65535, n_h - h0);
+        dim3 grid((unsigned)((n_s + 31) / 32), (unsigned)((n_t + 31) / 32), (unsigned)nh), block(32, 8);
+        const double* i2 = to_matrix ? in + h0 * n_t * n_s : in + h0 * ldu;
+        double* o2 = to_matrix ? out + h0 * ldu : out + h0 * n_t * n_s;
+        struct_permute_kernel<<<grid, block, 0, ctx->stream>>>(i2, o2, nh, n_t, n_s, ldu, to_matrix);
+        PB_LAUNCH_CHECK(ctx);
+    }
+    return PB_OK;
+}
+}  // namespace
+
+int pb_struct_to_matrix(pb_ctx* ctx, const double* Us, int64_t n_h, int n_t, int64_t n_s, double* U, int64_t ldu) {
+    if (!ctx) return PB_ERR_ARG;
+    return struct_permute(ctx, Us, U, n_h, n_t, n_s, ldu, 1);
+}
+int pb_matrix_to_struct(pb_ctx* ctx, const double* U, int64_t ldu, int64_t n_h, int n_t, int64_t n_s, double* Us) {
+    if (!ctx) return PB_ERR_ARG;
+    return struct_permute(ctx, U, Us, n_h, n_t, n_s, ldu, 0);
+}
+
+// ------------------------------------------------- projection / reconstruction
+int pb_project(pb_ctx* ctx, const double* V, int64_t ldv, int n_L, const double* U, int64_t ldu,
+               int64_t rows, int64_t n, double* v) {
+    if (!ctx) return PB_ERR_ARG;
+    if (n_L <= 0 || n <= 0 || ldv < n_L || ldu < n) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_project: bad shape");
+    Timer t(ctx, PB_T_PROJECT);
+    // C (n_L x n) = V^T U, then v = C^T (the reference returns the transposed view, podnnmodel.py:437)
+    PB_TRY(pb_reserve(ctx, &ctx->Bmat, &ctx->B_cap, (size_t)n_L * n));
+    PB_TRY(pbi_gemm_tn(ctx, V, ldv, n_L, U, ldu, n, rows, ctx->Bmat, n, 0));
+    PB_TRY(pbi_transpose(ctx, ctx->Bmat, n_L, n, n, v, n_L));
+    t.stop();
+    return PB_OK;
+}
+
+int pb_reconstruct(pb_ctx* ctx, const double* V, int64_t ldv, int n_L, const double* v, int64_t n, int64_t rows,
+                   const double* U, int64_t ldu, double* U_pod, int64_t ldp, double* pod_sig) {
+    if (!ctx) return PB_ERR_ARG;
+    if (n_L <= 0 || n <= 0 || ldv < n_L) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_reconstruct: bad shape");
+    if (pod_sig && !U) PB_FAIL(ctx, PB_ERR_ARG, "pb_reconstruct: pod_sig needs U");
+    if (!U_pod && !pod_sig) PB_FAIL(ctx, PB_ERR_ARG, "pb_reconstruct: nothing to compute");
+    Timer t(ctx, PB_T_RECON);
+    // B = v^T (n_L x n), padded to an even leading dimension for 16-byte copies
+    const int64_t ldb = (n + 1) / 2 * 2;
+    PB_TRY(pb_reserve(ctx, &ctx->Bmat, &ctx->B_cap, (size_t)n_L * ldb));
+    PB_TRY(pbi_transpose(ctx, v, n, n_L, n_L, ctx->Bmat, ldb));
+    PB_TRY(pbi_gemm_nn(ctx, V, ldv, rows, n_L, ctx->Bmat, ldb, n, U_pod, ldp, pod_sig ? U : nullptr, ldu, pod_sig));
+    t.stop();
+    return PB_OK;
+}
+
+}  // extern "C"

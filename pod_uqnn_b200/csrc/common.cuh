@@ -1,0 +1,96 @@
+// Shared declarations of libpodb200 (sm_100a).  Internal header.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/podb200.h"
+
+struct pb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    double ms[PB_T_COUNT] = {0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+
+    // split-K workspace of the TN products (grown on demand)
+    double* ws = nullptr;  size_t ws_bytes = 0;
+    // L2 flush scratch
+    void* flush = nullptr; size_t flush_bytes = 0;
+
+    // ---- state of the last decomposition (pb_pod_from_gram / pass2) ----
+    int64_t m = 0;          // order of the Gram (columns of the tall operand)
+    int mode = 0;
+    int r = 0;              // numerical rank (vectors of the factor)
+    int r2 = 0;             // rank of the second-pass factor
+    int n_L = 0;
+    int n_keep = 0;         // rotated columns for the second pass
+    bool pass2_done = false;
+    bool wide = false;      // pb_pod() transposed the input (n_h < n_st)
+    int sweeps1 = 0, sweeps2 = 0;
+    double* At = nullptr;   // (rows x ldm) factor vectors of pass 1 (unsorted; perm gives the order)
+    double* At2 = nullptr;  // factor vectors of pass 2
+    double* sig = nullptr;  // device (m): singular values, descending, zero beyond r
+    double* nrm = nullptr;  // device (m): norms of the factor vectors in the same order (incl. shift)
+    double* sig2 = nullptr; double* nrm2 = nullptr;
+    int* perm = nullptr;    // device (m + 32): vector index of the k-th largest
+    int* perm2 = nullptr;
+    double* Bmat = nullptr; // right-factor scratch
+    double* Wk = nullptr;   // W_keep (m x n_keep) row-major
+    double* small = nullptr;// eigensolver scratch
+    double* Gbuf = nullptr; double* G2buf = nullptr; double* Ybuf = nullptr; double* ATbuf = nullptr;
+    double* Uf = nullptr; size_t Uf_cap = 0; int64_t uf_rows = 0, uf_cols = 0, uf_ld = 0;  // two-step POD stage-1 bases
+    size_t At_cap = 0, At2_cap = 0, sig_cap = 0, nrm_cap = 0, sig2_cap = 0, nrm2_cap = 0, B_cap = 0,
+           Wk_cap = 0, small_cap = 0, G_cap = 0, G2_cap = 0, Y_cap = 0, AT_cap = 0;
+    size_t perm_cap = 0, perm2_cap = 0;
+    int* d_int = nullptr;   // device ints (flags, n_L ...)
+    int* h_int = nullptr;   // pinned host mirror
+    std::vector<double> sigma_host;  // singular values of the last decomposition
+};
+
+const char* pb_set_global_error(const std::string& s);
+
+#define PB_FAIL(ctx, code, ...) do { char _b[512]; snprintf(_b, sizeof _b, __VA_ARGS__); \
+    if (ctx) (ctx)->err = _b; else pb_set_global_error(_b); return (code); } while (0)
+
+#define PB_CUDA(ctx, expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
+    PB_FAIL(ctx, PB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); } } while (0)
+
+#define PB_TRY(expr) do { int _r = (expr); if (_r != PB_OK) return _r; } while (0)
+
+#define PB_LAUNCH_CHECK(ctx) do { (ctx)->launches++; cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { \
+    PB_FAIL(ctx, PB_ERR_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); } } while (0)
+
+// grow-on-demand device buffer
+int pb_reserve(pb_ctx* ctx, double** p, size_t* cap, size_t elems);
+
+// ---- internal kernels' host entry points (one per .cu) ----
+// C (ka x kb, ldc) = A^T B over rows; sym != 0: A == B, only tiles j >= i computed then mirrored.
+int pbi_gemm_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka,
+                const double* B, int64_t ldb, int64_t kb, int64_t rows,
+                double* C, int64_t ldc, int sym);
+// Y (rows x k, ldy) = A (rows x m, lda) B (m x k, ldb); optional fused pod_sig epilogue:
+// if Uref != nullptr: sig_out[row] = mean_j |Uref - Y| / 2 (Y itself stored only when Y != nullptr)
+int pbi_gemm_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m,
+                const double* B, int64_t ldb, int64_t k, double* Y, int64_t ldy,
+                const double* Uref, int64_t ldu, double* sig_out);
+// small dense helpers
+int pbi_transpose(pb_ctx* ctx, const double* in, int64_t rows, int64_t cols, int64_t ldin,
+                  double* out, int64_t ldout);
+// eigen-decomposition of a PSD matrix G (m x m, ld m): factor vectors At (r x m) sorted by
+// descending norm, sig[0..m) (zero beyond r).  tol_rel: Cholesky truncation (relative to max diag),
+// shift_rel: diagonal shift relative to trace (full-rank mode), returns r.
+int pbi_eig_psd(pb_ctx* ctx, const double* G, int64_t m, double tol_rel, double shift_rel,
+                double** At_buf, size_t* At_cap, double* sig_dev, double* nrm_dev, int* perm_dev,
+                int* r_out, int* sweeps_out, int max_sweeps);
+// n_L from descending lambdas = sig^2 (pod.py:22-32)
+int pbi_rank(pb_ctx* ctx, const double* sig_dev, int64_t count, double eps, int* n_L_out);
+// B (m x k, ldb) [i][j] = At[perm[j]][i] / (nrm[j] * (sig ? sig[j] : 1))
+int pbi_factor_to_right(pb_ctx* ctx, const double* At, int64_t m, int k, const int* perm_dev,
+                        const double* nrm_dev, const double* sig_dev, double* B, int64_t ldb);
+int pb_reserve_int(pb_ctx* ctx, int** p, size_t* cap, size_t elems);

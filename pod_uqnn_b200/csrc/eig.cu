@@ -1,0 +1,502 @@
+// Symmetric PSD eigensolver for the (small) Gram matrices of the POD:
+//
+//   G (m x m)  --pivoted Cholesky-->  L (m x r), G ~= L L^T      (rank revealing, optional
+//                                                                  truncation / diagonal shift)
+//   one-sided block Jacobi on the r column vectors of L (length m):  L J = W diag(sigma)
+//   => eigenvalues lambda_k = sigma_k^2 (- shift), eigenvectors w_k = (L J)_k / sigma_k.
+//
+// Working on the Cholesky factor instead of G keeps the graded accuracy of the factor
+// (errors relative to sqrt(lambda_i lambda_j), Demmel/Veselic; Drmac/Veselic preconditioning),
+// costs O(m r^2) instead of O(m^3) when the snapshot set has low numerical rank r, and makes
+// the Jacobi converge in a few sweeps.  The 32 x 32 pair problems are solved in shared memory
+// by a two-sided cyclic Jacobi; the m-long Gram / update products of a pair run on DMMA.
+//
+// Vectors are stored one per row: At[k][0..ldm), ldm = m rounded up to 8, zero padded.
+#include "common.cuh"
+#include "tile_ops.cuh"
+#include <cooperative_groups.h>
+#include <cfloat>
+#include <algorithm>
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int JB = 16;            // vectors per block
+constexpr int JP = 2 * JB;        // vectors per pair problem
+constexpr int CHOL_ROWS = 32;     // rows per group in the Cholesky column update
+constexpr int CHOL_THREADS = 256;
+
+using pbt::dmma884;
+
+// ---------------------------------------------------------------------------
+// pivoted Cholesky, cooperative (one grid barrier per step)
+// ---------------------------------------------------------------------------
+struct CholArgs {
+    const double* G; int m; int64_t ldg;
+    double* Lt; int64_t ldm; int max_steps;
+    double* d;              // (m) running Schur diagonal
+    double* cand_val;       // (2 x grid) per-CTA arg-max candidates, double buffered
+    int* cand_idx;
+    double tol_rel; double shift_rel;
+    int* r_out; double* shift_out;
+};
+
+__global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(CholArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double red_v[CHOL_THREADS];
+    __shared__ int red_i[CHOL_THREADS];
+    __shared__ double part[CHOL_THREADS / 32][CHOL_ROWS];
+    extern __shared__ double lp[];            // (max_steps) row p of the factor so far
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int G_ = gridDim.x, cta = blockIdx.x;
+    const int m = a.m;
+    const int rows_per_cta = (m + G_ - 1) / G_;
+    const int j_begin = cta * rows_per_cta, j_end = min(m, j_begin + rows_per_cta);
+
+    // trace (every CTA redundantly, fixed order) -> shift
+    double tr = 0.;
+    for (int j = tid; j < m; j += nth) tr += a.G[(int64_t)j * a.ldg + j];
+    red_v[tid] = tr; __syncthreads();
+    for (int s = nth / 2; s > 0; s >>= 1) { if (tid < s) red_v[tid] += red_v[tid + s]; __syncthreads(); }
+    const double shift = a.shift_rel * red_v[0];
+    __syncthreads();
+    for (int j = j_begin + tid; j < j_end; j += nth) a.d[j] = a.G[(int64_t)j * a.ldg + j] + shift;
+    __syncthreads();
+
+    double thresh = 0.;
+    int k = 0;
+    for (; k < a.max_steps; ++k) {
+        // local arg-max over my rows (ties -> lowest index)
+        double bv = -DBL_MAX; int bi = 0x7fffffff;
+        for (int j = j_begin + tid; j < j_end; j += nth) {
+            double v = a.d[j];
+            if (v > bv || (v == bv && j < bi)) { bv = v; bi = j; }
+        }
+        red_v[tid] = bv; red_i[tid] = bi; __syncthreads();
+        for (int s = nth / 2; s > 0; s >>= 1) {
+            if (tid < s) {
+                double v = red_v[tid + s]; int i = red_i[tid + s];
+                if (v > red_v[tid] || (v == red_v[tid] && i < red_i[tid])) { red_v[tid] = v; red_i[tid] = i; }
+            }
+            __syncthreads();
+        }
+        const int buf = (k & 1) * G_;
+        if (tid == 0) { a.cand_val[buf + cta] = red_v[0]; a.cand_idx[buf + cta] = red_i[0]; }
+        grid.sync();
+        // every CTA reduces the candidates identically
+        bv = -DBL_MAX; bi = 0x7fffffff;
+        for (int c = tid; c < G_; c += nth) {
+            double v = a.cand_val[buf + c]; int i = a.cand_idx[buf + c];
+            if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+        }
+        __syncthreads();
+        red_v[tid] = bv; red_i[tid] = bi; __syncthreads();
+        for (int s = nth / 2; s > 0; s >>= 1) {
+            if (tid < s) {
+                double v = red_v[tid + s]; int i = red_i[tid + s];
+                if (v > red_v[tid] || (v == red_v[tid] && i < red_i[tid])) { red_v[tid] = v; red_i[tid] = i; }
+            }
+            __syncthreads();
+        }
+        const double dp = red_v[0]; const int p = red_i[0];
+        __syncthreads();
+        if (k == 0) thresh = a.tol_rel * dp;
+        if (!(dp > thresh) || !(dp > 0.)) break;          // uniform across the grid
+        // row p of the factor so far (written by the owner of p in earlier steps)
+        for (int q = tid; q < k; q += nth) lp[q] = a.Lt[(int64_t)q * a.ldm + p];
+        __syncthreads();
+        const double inv = 1. / sqrt(dp);
+        // column k: v_j = (G[j][p] (+shift) - sum_q L[j][q] L[p][q]) / sqrt(dp)
+        const int jr = tid % CHOL_ROWS, qpart = tid / CHOL_ROWS;
+        constexpr int QP = CHOL_THREADS / CHOL_ROWS;
+        for (int jg = j_begin; jg < j_end; jg += CHOL_ROWS) {
+            const int j = jg + jr;
+            double s = 0.;
+            if (j < j_end) {
+                const double* col = a.Lt + j;
+                int q = qpart;
+                double s0 = 0., s1 = 0., s2 = 0., s3 = 0.;
+                for (; q + 3 * QP < k; q += 4 * QP) {
+                    s0 += col[(int64_t)q * a.ldm] * lp[q];
+                    s1 += col[(int64_t)(q + QP) * a.ldm] * lp[q + QP];
+                    s2 += col[(int64_t)(q + 2 * QP) * a.ldm] * lp[q + 2 * QP];
+                    s3 += col[(int64_t)(q + 3 * QP) * a.ldm] * lp[q + 3 * QP];
+                }
+                for (; q < k; q += QP) s0 += col[(int64_t)q * a.ldm] * lp[q];
+                s = (s0 + s1) + (s2 + s3);
+            }
+            part[qpart][jr] = s;
+            __syncthreads();
+            if (qpart == 0 && j < j_end) {
+                double dot = 0.;
+#pragma unroll
+                for (int w = 0; w < QP; ++w) dot += part[w][jr];
+                double g = a.G[(int64_t)j * a.ldg + p] + (j == p ? shift : 0.);
+                double v = (g - dot) * inv;
+                if (a.d[j] == -DBL_MAX) v = 0.;             // rows of earlier pivots stay zero
+                if (j == p) v = sqrt(dp);
+                a.Lt[(int64_t)k * a.ldm + j] = v;
+                a.d[j] = (j == p || a.d[j] == -DBL_MAX) ? -DBL_MAX : a.d[j] - v * v;
+            }
+            __syncthreads();
+        }
+    }
+    if (cta == 0 && tid == 0) { *a.r_out = k; *a.shift_out = shift; }
+}
+
+// ---------------------------------------------------------------------------
+// one-sided block Jacobi: one CTA per block pair per round
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void rr_pair(int n, int round, int i, int& p, int& q) {
+    // circle method on n (even) players: player n-1 is fixed
+    if (i == 0) { p = n - 1; q = round % (n - 1); }
+    else { p = (round + i) % (n - 1); q = (round - i + 2 * (n - 1)) % (n - 1); }
+    if (p > q) { int t = p; p = q; q = t; }
+}
+
+constexpr int SP = JP + 1;   // padded pitch of the 32 x 32 shared matrices
+
+// Two-sided cyclic Jacobi on S (JP x JP, symmetric, in shared memory), accumulating the
+// rotations in Q.  256 threads: thread (P, R) owns the 2 x 2 block rows(pair P) x cols(pair R).
+// Returns the number of rotations applied in the FIRST sweep (0 => the pair was converged).
+__device__ int inner_jacobi(double (*S)[SP], double (*Q)[SP], double* cs, double* sn, double tol) {
+    const int tid = threadIdx.x;
+    for (int e = tid; e < JP * JP; e += blockDim.x) Q[e / JP][e % JP] = (e / JP == e % JP) ? 1. : 0.;
+    __syncthreads();
+    int first = 0;
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        int rot_sweep = 0;
+        for (int round = 0; round < JP - 1; ++round) {
+            int did = 0;
+            if (tid < JP / 2) {
+                int p, q; rr_pair(JP, round, tid, p, q);
+                double app = S[p][p], aqq = S[q][q], apq = S[p][q];
+                double c = 1., s = 0.;
+                if (fabs(apq) > tol * sqrt(fabs(app * aqq)) && apq != 0.) {
+                    double zeta = (aqq - app) / (2. * apq);
+                    double t = (zeta >= 0. ? 1. : -1.) / (fabs(zeta) + sqrt(1. + zeta * zeta));
+                    c = 1. / sqrt(1. + t * t); s = c * t; did = 1;
+                }
+                cs[tid] = c; sn[tid] = s;
+            }
+            rot_sweep += __syncthreads_count(did);
+            {
+                const int P = tid / (JP / 2), R = tid % (JP / 2);
+                int p1, q1, p2, q2; rr_pair(JP, round, P, p1, q1); rr_pair(JP, round, R, p2, q2);
+                const double c1 = cs[P], s1 = sn[P], c2 = cs[R], s2 = sn[R];
+                double m11 = S[p1][p2], m12 = S[p1][q2], m21 = S[q1][p2], m22 = S[q1][q2];
+                // right: columns (p2, q2) <- (c2 col_p - s2 col_q, s2 col_p + c2 col_q)
+                double n11 = c2 * m11 - s2 * m12, n12 = s2 * m11 + c2 * m12;
+                double n21 = c2 * m21 - s2 * m22, n22 = s2 * m21 + c2 * m22;
+                // left: rows (p1, q1) <- (c1 row_p - s1 row_q, s1 row_p + c1 row_q)
+                S[p1][p2] = c1 * n11 - s1 * n21; S[p1][q2] = c1 * n12 - s1 * n22;
+                S[q1][p2] = s1 * n11 + c1 * n21; S[q1][q2] = s1 * n12 + c1 * n22;
+                // Q <- Q J : rows split over the two half-blocks of threads
+                for (int row = P; row < JP; row += JP / 2) {
+                    double a = Q[row][p2], b = Q[row][q2];
+                    Q[row][p2] = c2 * a - s2 * b; Q[row][q2] = s2 * a + c2 * b;
+                }
+            }
+            __syncthreads();
+        }
+        if (sweep == 0) first = rot_sweep;
+        if (rot_sweep == 0) break;
+    }
+    return first;
+}
+
+struct JacArgs {
+    double* At; int64_t ldm; int nb; int round; double tol; int* n_rot;
+};
+
+__global__ void __launch_bounds__(256) jacobi_pair_kernel(JacArgs a) {
+    __shared__ double S[JP][SP];
+    __shared__ double Q[JP][SP];
+    __shared__ double cs[JP / 2], sn[JP / 2];
+    extern __shared__ double red[];                    // (8 warps) x (JP*JP) partial Grams
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lk = lane & 3, lg = lane >> 2;
+    int bp, bq; rr_pair(a.nb, a.round, blockIdx.x, bp, bq);
+    // vector v (0..31) of the pair lives at row: (v < 16 ? bp : bq) * 16 + v % 16
+    auto vrow = [&](int v) -> double* {
+        return a.At + (int64_t)((v < JB ? bp : bq) * JB + (v % JB)) * a.ldm;
+    };
+    const int n4 = (int)(a.ldm / 4);
+
+    // ---- phase 1: S = X X^T over the m-long vectors (DMMA; fragment of row block t serves as A and B)
+    {
+        double acc[4][4][2];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { acc[t][u][0] = 0.; acc[t][u][1] = 0.; }
+        const double* r0 = vrow(lg) + lk;
+        const double* r1 = vrow(8 + lg) + lk;
+        const double* r2 = vrow(16 + lg) + lk;
+        const double* r3 = vrow(24 + lg) + lk;
+        for (int k4 = warp; k4 < n4; k4 += 8) {
+            double f[4];
+            f[0] = r0[k4 * 4]; f[1] = r1[k4 * 4]; f[2] = r2[k4 * 4]; f[3] = r3[k4 * 4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) dmma884(acc[t][u][0], acc[t][u][1], f[t], f[u]);
+        }
+        double* my = red + warp * (JP * JP);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                my[(t * 8 + lg) * JP + u * 8 + 2 * lk] = acc[t][u][0];
+                my[(t * 8 + lg) * JP + u * 8 + 2 * lk + 1] = acc[t][u][1];
+            }
+        __syncthreads();
+        for (int e = tid; e < JP * JP; e += blockDim.x) {
+            double s = 0.;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += red[w * (JP * JP) + e];
+            S[e / JP][e % JP] = s;
+        }
+        __syncthreads();
+        // exact symmetry (the two triangles were accumulated in different lanes)
+        for (int e = tid; e < JP * JP; e += blockDim.x) {
+            int i = e / JP, j = e % JP;
+            if (j < i) S[i][j] = S[j][i];
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 2: small eigenproblem
+    const int first = inner_jacobi(S, Q, cs, sn, a.tol);
+    if (first == 0) return;                       // uniform: nothing to rotate
+    if (tid == 0) atomicAdd(a.n_rot, first);
+
+    // ---- phase 3: X' = Q^T X, 8 elements of every vector per warp step (in place)
+    {
+        // A fragments of Q^T: A[row = j][k = i] = Q[i][j]
+        double qa[4][8];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) qa[t][ks] = Q[ks * 4 + lk][t * 8 + lg];
+        const int n8 = (int)(a.ldm / 8);
+        const double* src[8];
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) src[ks] = vrow(ks * 4 + lk) + lg;
+        double* dst[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) dst[t] = vrow(t * 8 + lg) + 2 * lk;
+        for (int e8 = warp; e8 < n8; e8 += 8) {
+            double b[8];
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) b[ks] = src[ks][e8 * 8];
+            double d[4][2];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { d[t][0] = 0.; d[t][1] = 0.; }
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) dmma884(d[t][0], d[t][1], qa[t][ks], b[ks]);
+            __syncwarp();                           // all lanes have read this column group
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                *reinterpret_cast<double2*>(dst[t] + e8 * 8) = make_double2(d[t][0], d[t][1]);
+        }
+    }
+}
+
+// squared norms -> sigma, then sort descending (single CTA bitonic sort)
+__global__ void norms_kernel(const double* __restrict__ At, int64_t ldm, int nvec, double* __restrict__ nrm2) {
+    const int v = blockIdx.x;
+    if (v >= nvec) return;
+    __shared__ double red[256];
+    double s = 0.;
+    for (int64_t e = threadIdx.x; e < ldm; e += blockDim.x) { double x = At[(int64_t)v * ldm + e]; s += x * x; }
+    red[threadIdx.x] = s; __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) { if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k]; __syncthreads(); }
+    if (threadIdx.x == 0) nrm2[v] = red[0];
+}
+
+__global__ void sort_kernel(const double* __restrict__ nrm2, int nvec, int npow2, const double* shift,
+                            double* __restrict__ sig_out, double* __restrict__ nrm_out, int m,
+                            int* __restrict__ perm_out, int* r_eff) {
+    extern __shared__ unsigned char sm[];
+    double* key = reinterpret_cast<double*>(sm);
+    int* idx = reinterpret_cast<int*>(sm + sizeof(double) * npow2);
+    for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+        key[i] = i < nvec ? nrm2[i] : -1.; idx[i] = i;
+    }
+    __syncthreads();
+    for (int k = 2; k <= npow2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+                int l = i ^ j;
+                if (l > i) {
+                    bool desc = ((i & k) == 0);
+                    // order: larger key first; ties -> smaller index first (deterministic)
+                    bool i_first = key[i] > key[l] || (key[i] == key[l] && idx[i] < idx[l]);
+                    if (desc ? !i_first : i_first) {
+                        double tk = key[i]; key[i] = key[l]; key[l] = tk;
+                        int ti = idx[i]; idx[i] = idx[l]; idx[l] = ti;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    const double sh = *shift;
+    int cnt = 0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        double lam = (i < nvec && key[i] > 0.) ? key[i] - sh : 0.;
+        double s = lam > 0. ? sqrt(lam) : 0.;
+        sig_out[i] = s;
+        nrm_out[i] = (i < nvec && key[i] > 0.) ? sqrt(key[i]) : 0.;
+        if (i < nvec) perm_out[i] = idx[i];
+        if (s > 0.) ++cnt;
+    }
+    __shared__ int total;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    atomicAdd(&total, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) *r_eff = total;
+}
+
+// truncation rank (pod.py:22-32): smallest n_L with cumsum(lambda)[n_L-1] / sum(lambda) >= 1 - eps.
+// One warp; each lane accumulates a contiguous chunk in order, a shuffle scan chains the chunks.
+__global__ void rank_kernel(const double* __restrict__ sig, int count, double eps, int* n_L_out) {
+    const int lane = threadIdx.x;
+    const int chunk = (count + 31) / 32;
+    const int b = lane * chunk, e = min(count, b + chunk);
+    double s = 0.;
+    for (int i = b; i < e; ++i) s += sig[i] * sig[i];
+    double incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const double total = __shfl_sync(0xffffffffu, incl, 31);
+    double acc = incl - s;
+    const double thr = 1. - eps;
+    int found = count;             // loop ran out: every mode kept
+    for (int i = b; i < e; ++i) {
+        acc += sig[i] * sig[i];
+        if (acc / total >= thr) { found = i + 1; break; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(0xffffffffu, found, o));
+    if (lane == 0) *n_L_out = found;
+}
+
+__global__ void factor_to_right_kernel(const double* __restrict__ At, int64_t ldm, const int* __restrict__ perm,
+                                       const double* __restrict__ nrm, const double* __restrict__ sig,
+                                       int m, int k, double* __restrict__ B, int64_t ldb) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)m * k) return;
+    int i = (int)(idx / k), j = (int)(idx % k);
+    double d = nrm[j];
+    if (sig) d *= sig[j];
+    B[(int64_t)i * ldb + j] = d > 0. ? At[(int64_t)perm[j] * ldm + i] / d : 0.;
+}
+
+}  // namespace
+
+// device ints layout in ctx->d_int: [0] r (Cholesky), [1] n_rot, [2] n_L, [3] r_eff
+struct EigScratch { double* d; double* cand_val; int* cand_idx; double* nrm2; double* shift; };
+
+static int get_scratch(pb_ctx* ctx, int64_t m, EigScratch* s) {
+    // small: [d (m)] [cand_val (2*1024)] [nrm2 (m+32)] [shift (2)] then ints [cand_idx (2*1024)]
+    size_t dbl = (size_t)m + 2048 + (m + 32) + 2;
+    size_t ints = 2048;
+    PB_TRY(pb_reserve(ctx, &ctx->small, &ctx->small_cap, dbl + (ints + 1) / 2 + 8));
+    s->d = ctx->small; s->cand_val = s->d + m; s->nrm2 = s->cand_val + 2048; s->shift = s->nrm2 + (m + 32);
+    s->cand_idx = reinterpret_cast<int*>(s->shift + 2);
+    return PB_OK;
+}
+
+int pbi_eig_psd(pb_ctx* ctx, const double* G, int64_t m, double tol_rel, double shift_rel,
+                double** At_buf, size_t* At_cap, double* sig_dev, double* nrm_dev, int* perm_dev,
+                int* r_out, int* sweeps_out, int max_sweeps) {
+    if (m <= 0 || m > 8192) PB_FAIL(ctx, PB_ERR_SHAPE, "eig_psd: order %lld outside (0, 8192]", (long long)m);
+    const int64_t ldm = (m + 7) / 8 * 8;
+    const int64_t cap_rows = (m + JP - 1) / JP * JP;          // even number of 16-blocks
+    PB_TRY(pb_reserve(ctx, At_buf, At_cap, (size_t)cap_rows * ldm));
+    double* At = *At_buf;
+    EigScratch sc; PB_TRY(get_scratch(ctx, m, &sc));
+    PB_CUDA(ctx, cudaMemsetAsync(At, 0, sizeof(double) * (size_t)cap_rows * ldm, ctx->stream));
+
+    // ---- pivoted Cholesky
+    int grid = (int)std::min<int64_t>(ctx->sm_count, (m + CHOL_ROWS - 1) / CHOL_ROWS);
+    size_t chol_smem = sizeof(double) * (size_t)m;
+    PB_CUDA(ctx, cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
+    int occ = 0;
+    PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol_kernel, CHOL_THREADS, chol_smem));
+    if (occ < 1) PB_FAIL(ctx, PB_ERR_CUDA, "eig_psd: Cholesky kernel does not fit an SM");
+    grid = std::min(grid, occ * ctx->sm_count);
+    if (grid > 1024) grid = 1024;
+    CholArgs ca{G, (int)m, m, At, ldm, (int)m, sc.d, sc.cand_val, sc.cand_idx, tol_rel, shift_rel,
+                ctx->d_int + 0, sc.shift};
+    void* args[] = {&ca};
+    PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)chol_kernel, dim3(grid), dim3(CHOL_THREADS), args, chol_smem, ctx->stream));
+    ctx->launches++;
+    PB_CUDA(ctx, cudaMemcpyAsync(ctx->h_int, ctx->d_int, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int r = ctx->h_int[0];
+    if (r <= 0) PB_FAIL(ctx, PB_ERR_SHAPE, "eig_psd: matrix has no positive pivot (zero or indefinite input)");
+
+    // ---- one-sided block Jacobi on the r vectors
+    int nb = (r + JB - 1) / JB; if (nb & 1) ++nb;             // even number of blocks (zero padded)
+    const int nvec = nb * JB;
+    // rotation threshold relative to the column norms (dgesvj uses sqrt(m) eps): below it the
+    // pair Gram entry is rounding noise of the m-long dot product
+    const double tol = std::max(4., sqrt((double)m)) * DBL_EPSILON;
+    size_t jac_smem = sizeof(double) * 8 * JP * JP;
+    PB_CUDA(ctx, cudaFuncSetAttribute(jacobi_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jac_smem));
+    int sweeps = 0; bool converged = false;
+    for (; sweeps < max_sweeps && !converged; ++sweeps) {
+        PB_CUDA(ctx, cudaMemsetAsync(ctx->d_int + 1, 0, sizeof(int), ctx->stream));
+        const int rounds = nb > 2 ? nb - 1 : 1;
+        for (int round = 0; round < rounds; ++round) {
+            JacArgs ja{At, ldm, nb, round, tol, ctx->d_int + 1};
+            jacobi_pair_kernel<<<nb / 2, 256, jac_smem, ctx->stream>>>(ja);
+            PB_LAUNCH_CHECK(ctx);
+        }
+        PB_CUDA(ctx, cudaMemcpyAsync(ctx->h_int + 1, ctx->d_int + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        converged = (ctx->h_int[1] == 0);
+    }
+    if (!converged && max_sweeps >= 30)
+        PB_FAIL(ctx, PB_ERR_NOT_CONVERGED, "eig_psd: Jacobi did not converge in %d sweeps (m=%lld r=%d)", max_sweeps, (long long)m, r);
+
+    // ---- norms, sort, sigma
+    norms_kernel<<<nvec, 256, 0, ctx->stream>>>(At, ldm, nvec, sc.nrm2);
+    PB_LAUNCH_CHECK(ctx);
+    int npow2 = 1; while (npow2 < nvec) npow2 <<= 1;
+    size_t sort_smem = (sizeof(double) + sizeof(int)) * (size_t)npow2;
+    PB_CUDA(ctx, cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+    sort_kernel<<<1, 1024, sort_smem, ctx->stream>>>(sc.nrm2, nvec, npow2, sc.shift, sig_dev, nrm_dev, (int)m, perm_dev, ctx->d_int + 3);
+    PB_LAUNCH_CHECK(ctx);
+    PB_CUDA(ctx, cudaMemcpyAsync(ctx->h_int + 3, ctx->d_int + 3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *r_out = r;                                   // factor vectors; sig may be zero for shifted noise modes
+    if (sweeps_out) *sweeps_out = sweeps;
+    return PB_OK;
+}
+
+int pbi_rank(pb_ctx* ctx, const double* sig_dev, int64_t count, double eps, int* n_L_out) {
+    rank_kernel<<<1, 32, 0, ctx->stream>>>(sig_dev, (int)count, eps, ctx->d_int + 2);
+    PB_LAUNCH_CHECK(ctx);
+    PB_CUDA(ctx, cudaMemcpyAsync(ctx->h_int + 2, ctx->d_int + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_L_out = ctx->h_int[2];
+    return PB_OK;
+}
+
+int pbi_factor_to_right(pb_ctx* ctx, const double* At, int64_t m, int k, const int* perm_dev,
+                        const double* nrm_dev, const double* sig_dev, double* B, int64_t ldb) {
+    const int64_t ldm = (m + 7) / 8 * 8;
+    int64_t n = m * k;
+    factor_to_right_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(At, ldm, perm_dev, nrm_dev, sig_dev, (int)m, k, B, ldb);
+    PB_LAUNCH_CHECK(ctx);
+    return PB_OK;
+}

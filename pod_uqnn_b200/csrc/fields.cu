@@ -1,0 +1,190 @@
+// Snapshot evaluation: the analytic fields u(X, t, mu) written straight into the
+// row-major snapshot matrix U (n_h x n_st) in HBM.
+//
+// Replaces the per-sample Python/numba loops of poduqnn/acceleration.py:13-30 (loop_u)
+// and :34-70 (loop_u_t), noise-free branch, for the registered fields.  One thread owns
+// one snapshot COLUMN (sample i, time step j) and walks a chunk of mesh nodes, so a warp
+// writes 32 consecutive doubles of each row (coalesced 256-byte stores); the reference
+// writes strided columns.  Arithmetic follows the reference expression trees operation by
+// operation (explicit _rn intrinsics keep ptxas from contracting a*b+c into FMA), so the
+// only differences to numpy are the <= 1-2 ulp of exp / cos.
+#include "common.cuh"
+
+namespace {
+
+constexpr int COLS_PER_BLOCK = 128;
+constexpr int NODES_PER_BLOCK = 64;
+
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dvd(double a, double b) { return __ddiv_rn(a, b); }
+
+// Shekel, experiments/1d_shekel/hyperparams.py:55-67: sum_k 1 / (bet_k + (x - gam_k)^2)
+__global__ void shekel_kernel(const double* __restrict__ X, int64_t n_rows, int64_t row0,
+                              const double* __restrict__ mu, int64_t n_s, int n_mu,
+                              double* __restrict__ U, int64_t ldu) {
+    extern __shared__ double smu[];           // [n_mu][COLS_PER_BLOCK]
+    const int64_t c0 = (int64_t)blockIdx.y * COLS_PER_BLOCK;
+    for (int e = threadIdx.x; e < n_mu * COLS_PER_BLOCK; e += blockDim.x) {
+        int c = e / n_mu, k = e % n_mu;
+        smu[k * COLS_PER_BLOCK + c] = (c0 + c < n_s) ? mu[(c0 + c) * n_mu + k] : 1.;
+    }
+    __syncthreads();
+    const int64_t col = c0 + threadIdx.x;
+    const int half = n_mu / 2;
+    const int64_t r_begin = (int64_t)blockIdx.x * NODES_PER_BLOCK;
+    const int64_t r_end = min(n_rows, r_begin + NODES_PER_BLOCK);
+    if (col >= n_s) return;
+    for (int64_t r = r_begin; r < r_end; ++r) {
+        const double x = X[row0 + r];
+        double s = 0.;
+        for (int k = 0; k < half; ++k) {
+            double d = sub(x, smu[(half + k) * COLS_PER_BLOCK + threadIdx.x]);
+            double q = mul(d, d);
+            s = add(s, dvd(1., add(smu[k * COLS_PER_BLOCK + threadIdx.x], q)));
+        }
+        U[r * ldu + col] = s;
+    }
+}
+
+// Ackley, experiments/2d_ackley/hyperparams.py:51-57
+__global__ void ackley_kernel(const double* __restrict__ X, int64_t n_xyz, int64_t n_rows, int64_t row0,
+                              const double* __restrict__ mu, int64_t n_s, int n_mu,
+                              double* __restrict__ U, int64_t ldu) {
+    const int64_t col = (int64_t)blockIdx.y * COLS_PER_BLOCK + threadIdx.x;
+    const int64_t r_begin = (int64_t)blockIdx.x * NODES_PER_BLOCK;
+    const int64_t r_end = min(n_rows, r_begin + NODES_PER_BLOCK);
+    __shared__ double sx[NODES_PER_BLOCK], sy[NODES_PER_BLOCK], sr[NODES_PER_BLOCK];
+    for (int e = threadIdx.x; e < NODES_PER_BLOCK; e += blockDim.x) {
+        int64_t r = r_begin + e;
+        if (r < r_end) {
+            double x = X[row0 + r], y = X[n_xyz + row0 + r];
+            sx[e] = x; sy[e] = y;
+            sr[e] = sqrt(mul(.5, add(mul(x, x), mul(y, y))));      // np.sqrt(.5*(x**2+y**2))
+        }
+    }
+    __syncthreads();
+    if (col >= n_s) return;
+    const double m0 = mu[col * n_mu + 0], m1 = mu[col * n_mu + 1], m2 = mu[col * n_mu + 2];
+    const double a2 = mul(-20., add(1., mul(.1, m2)));             // -20*(1+.1*mu[2])
+    const double c1 = mul(-.2, add(1., mul(.1, m1)));              // -.2*(1+.1*mu[1])
+    const double w = mul(6.283185307179586, add(1., mul(.1, m0))); // 2*np.pi*(1+.1*mu[0])
+    const double e1 = 2.718281828459045;                           // np.exp(1)
+    for (int64_t r = r_begin; r < r_end; ++r) {
+        const int e = (int)(r - r_begin);
+        double t1 = mul(a2, exp(mul(c1, sr[e])));
+        double t2 = exp(mul(.5, add(cos(mul(w, sx[e])), cos(mul(w, sy[e])))));
+        U[r * ldu + col] = add(add(sub(t1, t2), 20.), e1);
+    }
+}
+
+// Burgers, experiments/1dt_burger/hyperparams.py:45-55.  Column = i_sample * n_t + j_time.
+__global__ void burgers_kernel(const double* __restrict__ X, int64_t n_rows, int64_t row0,
+                               const double* __restrict__ mu, int64_t n_s, int n_mu,
+                               const double* __restrict__ t, int n_t,
+                               double* __restrict__ U, int64_t ldu) {
+    const int64_t n_st = n_s * n_t;
+    const int64_t col = (int64_t)blockIdx.y * COLS_PER_BLOCK + threadIdx.x;
+    const int64_t r_begin = (int64_t)blockIdx.x * NODES_PER_BLOCK;
+    const int64_t r_end = min(n_rows, r_begin + NODES_PER_BLOCK);
+    if (col >= n_st) return;
+    const int64_t i = col / n_t; const int j = (int)(col % n_t);
+    const double m = mu[i * n_mu], tj = t[j];
+    const double four_mu = mul(4., m);
+    if (tj == 1.) {
+        const double k = dvd(1., four_mu);                         // 1/(4*mu)
+        for (int64_t r = r_begin; r < r_end; ++r) {
+            double x = X[row0 + r];
+            double ex = exp(mul(k, sub(mul(x, x), .25)));          // exp(1/(4*mu)*(x**2 - 1/4))
+            U[r * ldu + col] = dvd(x, add(1., ex));
+        }
+    } else {
+        const double t0 = exp(dvd(1., mul(8., m)));                // exp(1/(8*mu))
+        const double sq = sqrt(dvd(tj, t0));                       // sqrt(t/t0)
+        const double den = mul(four_mu, tj);                       // 4*mu*t
+        for (int64_t r = r_begin; r < r_end; ++r) {
+            double x = X[row0 + r];
+            double ex = exp(dvd(mul(x, x), den));                  // exp(x**2/(4*mu*t)), inf allowed
+            U[r * ldu + col] = dvd(dvd(x, tj), add(1., mul(sq, ex)));
+        }
+    }
+}
+
+// DCT-II factor tables for the known-answer matrix: out[i][k] = scale_k * sqrt(2/n) cos(pi (i0+i+1/2)(k+1)/n)
+__global__ void dct_table_kernel(double* __restrict__ out, int64_t rows, int r, int64_t i0, int64_t n,
+                                 double decay, int transposed, int64_t ld) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * r) return;
+    int64_t i = idx / r; int k = (int)(idx % r);
+    // exact argument reduction: (2i+1)(k+1) mod 4n in integers, then cospi of a value in [0, 2)
+    int64_t num = ((2 * (i0 + i) + 1) % (4 * n)) * (int64_t)(k + 1) % (4 * n);
+    double c = cospi((double)num / (double)(2 * n));
+    double v = sqrt(2. / (double)n) * c;
+    if (decay != 0.) v *= exp2(-decay * (double)k);
+    if (transposed) out[(int64_t)k * ld + i] = v; else out[i * ld + k] = v;
+}
+
+}  // namespace
+
+extern "C" int pb_snapshots(pb_ctx* ctx, int field, int dim, int64_t n_xyz, const double* X_dev,
+                            int64_t n_s, int n_mu, const double* mu_dev, int n_t, const double* t_dev,
+                            int64_t row0, int64_t n_rows, double* U_dev, int64_t ldu) {
+    if (!ctx) return PB_ERR_ARG;
+    if (n_xyz <= 0 || n_s <= 0 || n_rows < 0 || row0 < 0 || row0 + n_rows > n_xyz)
+        PB_FAIL(ctx, PB_ERR_SHAPE, "pb_snapshots: bad node range [%lld, %lld) of %lld", (long long)row0,
+                (long long)(row0 + n_rows), (long long)n_xyz);
+    const int64_t n_st = n_s * (n_t > 0 ? n_t : 1);
+    if (ldu < n_st) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_snapshots: ldu %lld < n_st %lld", (long long)ldu, (long long)n_st);
+    if (n_rows == 0) return PB_OK;
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    dim3 grid((unsigned)((n_rows + NODES_PER_BLOCK - 1) / NODES_PER_BLOCK),
+              (unsigned)((n_st + COLS_PER_BLOCK - 1) / COLS_PER_BLOCK));
+    if (grid.y > 65535) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_snapshots: too many snapshot columns (%lld)", (long long)n_st);
+    switch (field) {
+    case PB_FIELD_SHEKEL:
+        if (dim != 1 || n_t > 0 || n_mu < 2 || (n_mu % 2)) PB_FAIL(ctx, PB_ERR_SHAPE, "shekel: dim=1, steady, even n_mu");
+        shekel_kernel<<<grid, COLS_PER_BLOCK, (size_t)n_mu * COLS_PER_BLOCK * sizeof(double), ctx->stream>>>(
+            X_dev, n_rows, row0, mu_dev, n_s, n_mu, U_dev, ldu);
+        break;
+    case PB_FIELD_ACKLEY:
+        if (dim != 2 || n_t > 0 || n_mu != 3) PB_FAIL(ctx, PB_ERR_SHAPE, "ackley: dim=2, steady, n_mu=3");
+        ackley_kernel<<<grid, COLS_PER_BLOCK, 0, ctx->stream>>>(X_dev, n_xyz, n_rows, row0, mu_dev, n_s, n_mu, U_dev, ldu);
+        break;
+    case PB_FIELD_BURGERS:
+        if (dim != 1 || n_t <= 0 || n_mu != 1 || !t_dev) PB_FAIL(ctx, PB_ERR_SHAPE, "burgers: dim=1, n_t>0, n_mu=1");
+        burgers_kernel<<<grid, COLS_PER_BLOCK, 0, ctx->stream>>>(X_dev, n_rows, row0, mu_dev, n_s, n_mu, t_dev, n_t, U_dev, ldu);
+        break;
+    default:
+        PB_FAIL(ctx, PB_ERR_UNSUPPORTED_FIELD, "pb_snapshots: field id %d is not registered (no CPU fallback)", field);
+    }
+    PB_LAUNCH_CHECK(ctx);
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    PB_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->ms[PB_T_SNAPSHOTS] = ms;
+    return PB_OK;
+}
+
+extern "C" int pb_dct_lowrank(pb_ctx* ctx, int64_t n_h, int64_t n_s, int r, double decay,
+                              int64_t row0, int64_t n_rows, double* U_dev, int64_t ldu) {
+    if (!ctx) return PB_ERR_ARG;
+    if (r <= 0 || r > n_s || row0 + n_rows > n_h) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_dct_lowrank: bad shape");
+    double *phi = nullptr, *psit = nullptr;
+    const int64_t chunk = 1 << 20;                      // rows per GEMM call (bounds the phi table)
+    PB_CUDA(ctx, cudaMalloc(&phi, sizeof(double) * (size_t)std::min<int64_t>(chunk, n_rows) * r));
+    PB_CUDA(ctx, cudaMalloc(&psit, sizeof(double) * (size_t)r * n_s));
+    int64_t n = (int64_t)r * n_s;
+    dct_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(psit, n_s, r, 0, n_s, 0., 1, n_s);
+    PB_LAUNCH_CHECK(ctx);
+    int rc = PB_OK;
+    for (int64_t h = 0; h < n_rows && rc == PB_OK; h += chunk) {
+        int64_t rows = std::min(chunk, n_rows - h);
+        int64_t ne = rows * r;
+        dct_table_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(phi, rows, r, row0 + h, n_h, decay, 0, r);
+        ctx->launches++;
+        rc = pbi_gemm_nn(ctx, phi, r, rows, r, psit, n_s, n_s, U_dev + h * ldu, ldu, nullptr, 0, nullptr);
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(phi); cudaFree(psit);
+    return rc;
+}

@@ -1,0 +1,408 @@
+// fp64 tall-skinny products on the DMMA pipe (mma.sync m8n8k4 f64 -> SASS DMMA.8x8x4).
+//
+//   TN:  C (ka x kb) = A^T B, A (rows x ka), B (rows x kb) row-major, rows >> ka,kb.
+//        The Gram U^T U (sym = 1, only tiles j >= i), the projection V^T U, Y^T Y.
+//        Reduction index = the long, strided one -> split-K over row ranges with a
+//        fixed-order second-stage sum (deterministic, run-to-run identical ranks).
+//   NN:  Y (rows x k) = A (rows x m) B (m x k).  Basis V = U (W S^-1), rotation Y = U W,
+//        reconstruction V v^T (+ fused pod_sig epilogue).
+//
+// Staging: cp.async (LDGSTS) 16-byte copies into a 4-stage shared-memory ring.
+// Shared rows are padded by 4 doubles so that the 8x4 / 4x8 DMMA fragment reads
+// (4 k-rows x 4 consecutive columns per half-warp) hit 16 distinct 8-byte banks.
+// tcgen05 has no fp64 kind; DMMA through mma.sync is the fp64 tensor path on sm_100a.
+#include "common.cuh"
+
+#include "tile_ops.cuh"
+
+namespace {
+using namespace pbt;
+
+// ---------------------------------------------------------------------------
+// TN kernel
+// ---------------------------------------------------------------------------
+template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES, bool ALIGN16>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tn_kernel(const double* __restrict__ A, int64_t lda, int ka,
+               const double* __restrict__ B, int64_t ldb, int kb,
+               int64_t rows, int64_t rows_per_split,
+               double* __restrict__ out, int64_t ldo, int64_t split_stride,
+               int tiles_m, int tiles_n, int sym) {
+    static_assert(WARPS_M * WARPS_N == NTHREADS / 32, "8 warps");
+    constexpr int PA = BM + 4, PB = BN + 4;
+    constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
+    constexpr int TM = WM / 8, TNN = WN / 8;
+    extern __shared__ __align__(16) double smem[];
+    double* As = smem;                              // [STAGES][BK][PA]
+    double* Bs = smem + STAGES * BK * PA;           // [STAGES][BK][PB]
+
+    int tile = blockIdx.x, ti, tj;
+    if (sym) {           // linear id -> (ti, tj >= ti)
+        ti = 0; int rem = tile;
+        while (rem >= tiles_n - ti) { rem -= tiles_n - ti; ++ti; }
+        tj = ti + rem;
+    } else { ti = tile / tiles_n; tj = tile % tiles_n; }
+    (void)tiles_m;
+    const int64_t i0 = (int64_t)ti * BM, j0 = (int64_t)tj * BN;
+    const int split = blockIdx.y;
+    const int64_t r_begin = (int64_t)split * rows_per_split;
+    const int64_t r_end = min(rows, r_begin + rows_per_split);
+    const int nk = (int)((r_end - r_begin + BK - 1) / BK);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp / WARPS_N, wn = warp % WARPS_N;
+    const int lk = lane & 3, lg = lane >> 2;
+
+    double acc[TM][TNN][2];
+#pragma unroll
+    for (int t = 0; t < TM; ++t)
+#pragma unroll
+        for (int u = 0; u < TNN; ++u) { acc[t][u][0] = 0.; acc[t][u][1] = 0.; }
+
+    // prologue
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nk) {
+            int64_t r0 = r_begin + (int64_t)s * BK;
+            load_tile<BK, BM, PA, ALIGN16>(As + s * BK * PA, A, lda, r0, r_end, i0, ka, tid);
+            load_tile<BK, BN, PB, ALIGN16>(Bs + s * BK * PB, B, ldb, r0, r_end, j0, kb, tid);
+        }
+        cp_async_commit();
+    }
+
+    for (int k = 0; k < nk; ++k) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {   // prefetch stage k + STAGES - 1 into the slot freed at iteration k - 1
+            int kn = k + STAGES - 1;
+            if (kn < nk) {
+                int s = kn % STAGES;
+                int64_t r0 = r_begin + (int64_t)kn * BK;
+                load_tile<BK, BM, PA, ALIGN16>(As + s * BK * PA, A, lda, r0, r_end, i0, ka, tid);
+                load_tile<BK, BN, PB, ALIGN16>(Bs + s * BK * PB, B, ldb, r0, r_end, j0, kb, tid);
+            }
+            cp_async_commit();
+        }
+        const double* as = As + (k % STAGES) * BK * PA + wm * WM + lg;
+        const double* bs = Bs + (k % STAGES) * BK * PB + wn * WN + lg;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            double a[TM], b[TNN];
+#pragma unroll
+            for (int t = 0; t < TM; ++t) a[t] = as[(kk * 4 + lk) * PA + t * 8];
+#pragma unroll
+            for (int u = 0; u < TNN; ++u) b[u] = bs[(kk * 4 + lk) * PB + u * 8];
+#pragma unroll
+            for (int t = 0; t < TM; ++t)
+#pragma unroll
+                for (int u = 0; u < TNN; ++u) dmma884(acc[t][u][0], acc[t][u][1], a[t], b[u]);
+        }
+    }
+    cp_async_wait<0>();
+
+    double* o = out + (int64_t)split * split_stride;
+#pragma unroll
+    for (int t = 0; t < TM; ++t) {
+        int64_t i = i0 + wm * WM + t * 8 + lg;
+        if (i >= ka) continue;
+#pragma unroll
+        for (int u = 0; u < TNN; ++u) {
+            int64_t j = j0 + wn * WN + u * 8 + 2 * lk;
+            if (j < kb)     o[i * ldo + j]     = acc[t][u][0];
+            if (j + 1 < kb) o[i * ldo + j + 1] = acc[t][u][1];
+        }
+    }
+}
+
+// second stage: fixed-order sum over splits (+ mirror of the upper triangle when sym)
+__global__ void reduce_splits_kernel(const double* __restrict__ ws, int splits, int64_t split_stride,
+                                     int ka, int kb, int64_t ldw, double* __restrict__ C, int64_t ldc,
+                                     int sym, int bm, int bn) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)ka * kb) return;
+    int i = (int)(idx / kb), j = (int)(idx % kb);
+    int si = i, sj = j;
+    // in sym mode tile (ti, tj) exists only for tj >= ti: elements of lower tiles come mirrored
+    if (sym && (j / bn) < (i / bm)) { si = j; sj = i; }
+    const double* p = ws + (int64_t)si * ldw + sj;
+    double s = 0.;
+    for (int k = 0; k < splits; ++k) s += p[(int64_t)k * split_stride];
+    C[(int64_t)i * ldc + j] = s;
+}
+
+// make an (n x n) matrix exactly symmetric from its upper triangle (diagonal tiles of the
+// sym product are computed in full; rounding is identical on both sides because the same
+// products are accumulated in the same order, but we do not rely on it).
+__global__ void symmetrize_kernel(double* __restrict__ C, int n, int64_t ldc) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n * n) return;
+    int i = (int)(idx / n), j = (int)(idx % n);
+    if (j < i) C[(int64_t)i * ldc + j] = C[(int64_t)j * ldc + i];
+}
+
+// ---------------------------------------------------------------------------
+// NN kernel (BM = 128 rows per CTA)
+// ---------------------------------------------------------------------------
+template <int BN, int WARPS_M, int WARPS_N, int STAGES, bool ALIGN_A, bool ALIGN_B>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_nn_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int m,
+               const double* __restrict__ B, int64_t ldb, int k,
+               double* __restrict__ Y, int64_t ldy,
+               const double* __restrict__ Uref, int64_t ldu, double* __restrict__ sig_part) {
+    constexpr int BM = 128;
+    static_assert(WARPS_M * WARPS_N == NTHREADS / 32, "8 warps");
+    constexpr int PA = BK + 4, PB = BN + 4;
+    constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
+    constexpr int TM = WM / 8, TNN = WN / 8;
+    extern __shared__ __align__(16) double smem[];
+    double* As = smem;                              // [STAGES][BM][PA]
+    double* Bs = smem + STAGES * BM * PA;           // [STAGES][BK][PB]
+    __shared__ double rowsum[WARPS_N][BM];
+
+    const int64_t h0 = (int64_t)blockIdx.x * BM;
+    const int64_t j0 = (int64_t)blockIdx.y * BN;
+    const int nk = (m + BK - 1) / BK;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp / WARPS_N, wn = warp % WARPS_N;
+    const int lk = lane & 3, lg = lane >> 2;
+
+    double acc[TM][TNN][2];
+#pragma unroll
+    for (int t = 0; t < TM; ++t)
+#pragma unroll
+        for (int u = 0; u < TNN; ++u) { acc[t][u][0] = 0.; acc[t][u][1] = 0.; }
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nk) {
+            int64_t k0 = (int64_t)s * BK;
+            load_tile<BM, BK, PA, ALIGN_A>(As + s * BM * PA, A, lda, h0, rows, k0, m, tid);
+            load_tile<BK, BN, PB, ALIGN_B>(Bs + s * BK * PB, B, ldb, k0, m, j0, k, tid);
+        }
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int kn = kt + STAGES - 1;
+            if (kn < nk) {
+                int s = kn % STAGES;
+                int64_t k0 = (int64_t)kn * BK;
+                load_tile<BM, BK, PA, ALIGN_A>(As + s * BM * PA, A, lda, h0, rows, k0, m, tid);
+                load_tile<BK, BN, PB, ALIGN_B>(Bs + s * BK * PB, B, ldb, k0, m, j0, k, tid);
+            }
+            cp_async_commit();
+        }
+        const double* as = As + (kt % STAGES) * BM * PA + (wm * WM + lg) * PA + lk;
+        const double* bs = Bs + (kt % STAGES) * BK * PB + wn * WN + lg;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            double a[TM], b[TNN];
+#pragma unroll
+            for (int t = 0; t < TM; ++t) a[t] = as[t * 8 * PA + kk * 4];
+#pragma unroll
+            for (int u = 0; u < TNN; ++u) b[u] = bs[(kk * 4 + lk) * PB + u * 8];
+#pragma unroll
+            for (int t = 0; t < TM; ++t)
+#pragma unroll
+                for (int u = 0; u < TNN; ++u) dmma884(acc[t][u][0], acc[t][u][1], a[t], b[u]);
+        }
+    }
+    cp_async_wait<0>();
+
+    const bool want_sig = (Uref != nullptr);
+#pragma unroll
+    for (int t = 0; t < TM; ++t) {
+        const int rl = wm * WM + t * 8 + lg;
+        const int64_t h = h0 + rl;
+        double rs = 0.;
+        if (h < rows) {
+#pragma unroll
+            for (int u = 0; u < TNN; ++u) {
+                int64_t j = j0 + wn * WN + u * 8 + 2 * lk;
+                if (Y) {
+                    if (j < k)     Y[h * ldy + j]     = acc[t][u][0];
+                    if (j + 1 < k) Y[h * ldy + j + 1] = acc[t][u][1];
+                }
+                if (want_sig) {
+                    if (j < k)     rs += fabs(Uref[h * ldu + j] - acc[t][u][0]);
+                    if (j + 1 < k) rs += fabs(Uref[h * ldu + j + 1] - acc[t][u][1]);
+                }
+            }
+        }
+        if (want_sig) {   // quad reduction (the 4 lanes of a row), fixed order
+            rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+            rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+            if (lk == 0) rowsum[wn][rl] = rs;
+        }
+    }
+    if (want_sig) {
+        __syncthreads();
+        if (tid < BM && h0 + tid < rows) {
+            double s = 0.;
+#pragma unroll
+            for (int w = 0; w < WARPS_N; ++w) s += rowsum[w][tid];
+            sig_part[(int64_t)blockIdx.y * rows + h0 + tid] = s;
+        }
+    }
+}
+
+__global__ void sig_reduce_kernel(const double* __restrict__ part, int ntiles, int64_t rows,
+                                  double inv2n, double* __restrict__ out) {
+    int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= rows) return;
+    double s = 0.;
+    for (int t = 0; t < ntiles; ++t) s += part[(int64_t)t * rows + h];
+    out[h] = s * inv2n;
+}
+
+__global__ void transpose_kernel(const double* __restrict__ in, int64_t rows, int64_t cols,
+                                 int64_t ldin, double* __restrict__ out, int64_t ldout) {
+    __shared__ double t[32][33];
+    int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        int64_t r = r0 + y, c = c0 + threadIdx.x;
+        t[y][threadIdx.x] = (r < rows && c < cols) ? in[r * ldin + c] : 0.;
+    }
+    __syncthreads();
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        int64_t c = c0 + y, r = r0 + threadIdx.x;
+        if (c < cols && r < rows) out[c * ldout + r] = t[threadIdx.x][y];
+    }
+}
+
+template <typename K>
+int set_smem(pb_ctx* ctx, K kernel, size_t bytes) {
+    PB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return PB_OK;
+}
+
+inline bool aligned16(const void* p, int64_t ld) { return ((uintptr_t)p % 16 == 0) && (ld % 2 == 0); }
+
+// choose the split count so that tiles*splits fills whole waves of the SMs
+int choose_splits(int tiles, int64_t rows, int sms) {
+    int64_t max_by_rows = rows / (BK * 32);      // >= 512 rows per split
+    if (max_by_rows < 1) max_by_rows = 1;
+    int best = 1; double best_score = -1.;
+    for (int s = 1; s <= 96 && s <= max_by_rows; ++s) {
+        int64_t ctas = (int64_t)tiles * s;
+        int64_t waves = (ctas + sms - 1) / sms;
+        double eff = (double)ctas / (double)(waves * sms);
+        // prefer >= 2 waves of work per SM is not needed (equal CTAs); penalise many splits lightly
+        double score = eff - 0.0015 * s;
+        if (score > best_score) { best_score = score; best = s; }
+    }
+    return best;
+}
+
+template <int BM, int BN, int WARPS_M, int WARPS_N>
+int launch_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const double* B, int64_t ldb,
+              int64_t kb, int64_t rows, double* C, int64_t ldc, int sym) {
+    constexpr int STAGES = 4;
+    const int tiles_m = (int)((ka + BM - 1) / BM), tiles_n = (int)((kb + BN - 1) / BN);
+    const int tiles = sym ? tiles_n * (tiles_n + 1) / 2 : tiles_m * tiles_n;
+    const int splits = choose_splits(tiles, rows, ctx->sm_count);
+    int64_t rps = (rows + splits - 1) / splits;
+    rps = (rps + BK - 1) / BK * BK;
+    const bool direct = (splits == 1 && !sym);
+    const int64_t split_stride = (int64_t)ka * kb;
+    double* out = C; int64_t ldo = ldc;
+    if (!direct) {
+        PB_TRY(pb_reserve(ctx, &ctx->ws, &ctx->ws_bytes, (size_t)split_stride * splits));
+        out = ctx->ws; ldo = kb;
+    }
+    const bool al = aligned16(A, lda) && aligned16(B, ldb);
+    size_t smem = (size_t)STAGES * BK * ((BM + 4) + (BN + 4)) * sizeof(double);
+    dim3 grid(tiles, splits);
+    if (al) {
+        auto kern = gemm_tn_kernel<BM, BN, WARPS_M, WARPS_N, STAGES, true>;
+        PB_TRY(set_smem(ctx, kern, smem));
+        kern<<<grid, NTHREADS, smem, ctx->stream>>>(A, lda, (int)ka, B, ldb, (int)kb, rows, rps, out, ldo,
+                                                    split_stride, tiles_m, tiles_n, sym);
+    } else {
+        auto kern = gemm_tn_kernel<BM, BN, WARPS_M, WARPS_N, STAGES, false>;
+        PB_TRY(set_smem(ctx, kern, smem));
+        kern<<<grid, NTHREADS, smem, ctx->stream>>>(A, lda, (int)ka, B, ldb, (int)kb, rows, rps, out, ldo,
+                                                    split_stride, tiles_m, tiles_n, sym);
+    }
+    PB_LAUNCH_CHECK(ctx);
+    if (!direct) {
+        int64_t n = (int64_t)ka * kb;
+        reduce_splits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+            ctx->ws, splits, split_stride, (int)ka, (int)kb, kb, C, ldc, sym, BM, BN);
+        PB_LAUNCH_CHECK(ctx);
+        if (sym) {
+            symmetrize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(C, (int)ka, ldc);
+            PB_LAUNCH_CHECK(ctx);
+        }
+    }
+    return PB_OK;
+}
+
+template <int BN, int WARPS_M, int WARPS_N>
+int launch_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m, const double* B,
+              int64_t ldb, int64_t k, double* Y, int64_t ldy, const double* Uref, int64_t ldu,
+              double* sig_part) {
+    constexpr int STAGES = 4;
+    size_t smem = (size_t)STAGES * (128 * (BK + 4) + BK * (BN + 4)) * sizeof(double);
+    dim3 grid((unsigned)((rows + 127) / 128), (unsigned)((k + BN - 1) / BN));
+    const bool aa = aligned16(A, lda), ab = aligned16(B, ldb);
+#define PB_NN_CASE(AA, AB) { auto kern = gemm_nn_kernel<BN, WARPS_M, WARPS_N, STAGES, AA, AB>; \
+        PB_TRY(set_smem(ctx, kern, smem)); \
+        kern<<<grid, NTHREADS, smem, ctx->stream>>>(A, lda, rows, (int)m, B, ldb, (int)k, Y, ldy, Uref, ldu, sig_part); }
+    if (aa && ab) PB_NN_CASE(true, true)
+    else if (aa) PB_NN_CASE(true, false)
+    else if (ab) PB_NN_CASE(false, true)
+    else PB_NN_CASE(false, false)
+#undef PB_NN_CASE
+    PB_LAUNCH_CHECK(ctx);
+    return PB_OK;
+}
+
+}  // namespace
+
+int pbi_gemm_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const double* B, int64_t ldb,
+                int64_t kb, int64_t rows, double* C, int64_t ldc, int sym) {
+    if (ka <= 0 || kb <= 0 || rows < 0) PB_FAIL(ctx, PB_ERR_SHAPE, "gemm_tn: bad shape ka=%lld kb=%lld rows=%lld",
+                                                (long long)ka, (long long)kb, (long long)rows);
+    if (ka > (1 << 20) || kb > (1 << 20)) PB_FAIL(ctx, PB_ERR_SHAPE, "gemm_tn: ka/kb too large");
+    if (sym && (A != B || ka != kb || lda != ldb)) PB_FAIL(ctx, PB_ERR_ARG, "gemm_tn: sym needs A == B");
+    if (rows == 0) {
+        PB_CUDA(ctx, cudaMemset2DAsync(C, ldc * sizeof(double), 0, kb * sizeof(double), ka, ctx->stream));
+        return PB_OK;
+    }
+    if (sym || ka > 32) return launch_tn<128, 128, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, sym);
+    return launch_tn<32, 128, 1, 8>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);
+}
+
+int pbi_gemm_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m, const double* B,
+                int64_t ldb, int64_t k, double* Y, int64_t ldy, const double* Uref, int64_t ldu,
+                double* sig_out) {
+    if (rows <= 0 || m <= 0 || k <= 0) PB_FAIL(ctx, PB_ERR_SHAPE, "gemm_nn: bad shape rows=%lld m=%lld k=%lld",
+                                               (long long)rows, (long long)m, (long long)k);
+    double* part = nullptr;
+    const bool wide = k > 32;
+    const int bn = wide ? 128 : 32;
+    const int ntiles = (int)((k + bn - 1) / bn);
+    if (Uref) {
+        PB_TRY(pb_reserve(ctx, &ctx->ws, &ctx->ws_bytes, (size_t)ntiles * rows));
+        part = ctx->ws;
+    }
+    if (wide) PB_TRY((launch_nn<128, 2, 4>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
+    else      PB_TRY((launch_nn<32, 8, 1>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
+    if (Uref) {
+        sig_reduce_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(
+            part, ntiles, rows, 0.5 / (double)k, sig_out);
+        PB_LAUNCH_CHECK(ctx);
+    }
+    return PB_OK;
+}
+
+int pbi_transpose(pb_ctx* ctx, const double* in, int64_t rows, int64_t cols, int64_t ldin,
+                  double* out, int64_t ldout) {
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
+    transpose_kernel<<<grid, block, 0, ctx->stream>>>(in, rows, cols, ldin, out, ldout);
+    PB_LAUNCH_CHECK(ctx);
+    return PB_OK;
+}

@@ -1,0 +1,80 @@
+"""POD -- same names and argument order as the reference's poduqnn/pod.py
+(perform_pod :7-47, perform_fast_pod :51-68), computed on the GPU by libpodb200.
+
+Algorithm (csrc/gemm.cu, csrc/eig.cu): method of snapshots.  G = A^T A on DMMA (A = U, or
+U^T when n_h < n_st), pivoted Cholesky of G, one-sided block Jacobi on the factor, energy
+rank rule (pod.py:22-32), V = U Z diag(1/sigma).  `mode`:
+  "gram"      one Gram pass (fast; subspace angle limited by eps_mach * lambda_1 / gap)
+  "gram2"     + rotate the numerical-rank block and repeat the Gram on it
+  "accurate"  rotate all columns and repeat (one-sided Jacobi SVD accuracy; the default)
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import DeviceArray, POD_MODES
+
+DEFAULT_MODE = "accurate"
+
+
+def pod_device(ctx, U, eps=0., n_L=0, mode=DEFAULT_MODE):
+    """POD of a device matrix.  Returns (V_dev (n_h, n_L), sigma host (min(n_h, n_st),))."""
+    n_h, n_st = U.shape
+    nl = C.c_int()
+    ctx.check(_lib.lib().pb_pod(ctx.h, U.ptr, n_h, n_st, U.ld, float(eps), int(n_L), POD_MODES[mode], C.byref(nl)))
+    V = ctx.alloc(n_h, nl.value)
+    ctx.check(_lib.lib().pb_pod_basis_full(ctx.h, U.ptr, n_h, n_st, U.ld, V.ptr, V.ld))
+    return V, pod_sigma(ctx)
+
+
+def pod_sigma(ctx):
+    cnt = C.c_int64()
+    ctx.check(_lib.lib().pb_pod_sigma(ctx.h, None, 0, C.byref(cnt)))
+    sig = np.zeros(cnt.value)
+    ctx.check(_lib.lib().pb_pod_sigma(ctx.h, sig.ctypes.data, cnt.value, C.byref(cnt)))
+    return sig
+
+
+def perform_pod(U, eps=0., n_L=0, verbose=True, *, mode=DEFAULT_MODE, ctx=None, return_sigma=False):
+    """Reference signature (pod.py:7).  numpy in -> numpy V (n_h, n_L), C-contiguous float64.
+
+    A DeviceArray input stays on the device and returns a DeviceArray.
+    """
+    ctx = ctx or _lib.default_context()
+    on_device = isinstance(U, DeviceArray)
+    Ud = U if on_device else ctx.to_device(np.asarray(U, dtype=np.float64))
+    if verbose:
+        print("Contructing the reduced bases V")     # pod.py:38 (sic)
+    Vd, sig = pod_device(ctx, Ud, eps, n_L, mode)
+    V = Vd if on_device else Vd.download()
+    return (V, sig) if return_sigma else V
+
+
+def perform_fast_pod(U, eps, eps_init, *, mode=DEFAULT_MODE, ctx=None, return_ranks=False):
+    """Reference signature (pod.py:51).  U is (n_h, n_t, n_s); returns V (n_h, n_L)."""
+    ctx = ctx or _lib.default_context()
+    print("Performing initial time-trajectory POD")  # pod.py:53
+    U = np.asarray(U, dtype=np.float64)
+    n_h, n_t, n_s = U.shape
+    Us = ctx.to_device(U)
+    Um = ctx.alloc(n_h, n_s * n_t)
+    L = _lib.lib()
+    ctx.check(L.pb_struct_to_matrix(ctx.h, Us.ptr, n_h, n_t, n_s, Um.ptr, Um.ld))
+    Us.release()
+    V, ranks = fast_pod_device(ctx, Um, n_t, n_s, eps, eps_init, mode)
+    print("Performing SVD")                          # pod.py:67
+    V = V.download()
+    return (V, ranks) if return_ranks else V
+
+
+def fast_pod_device(ctx, Um, n_t, n_s, eps, eps_init, mode=DEFAULT_MODE):
+    """Two-step POD of a device matrix with sample-major columns (column = i*n_t + j)."""
+    n_h = Um.shape[0]
+    nl = C.c_int()
+    ranks = (C.c_int * n_s)()
+    ctx.check(_lib.lib().pb_fast_pod(ctx.h, Um.ptr, n_h, n_t, n_s, Um.ld, float(eps), float(eps_init),
+                                     POD_MODES[mode], C.byref(nl), ranks))
+    V = ctx.alloc(n_h, nl.value)
+    ctx.check(_lib.lib().pb_fast_pod_basis(ctx.h, V.ptr, V.ld))
+    return V, np.array(ranks[:], dtype=np.int64)

@@ -1,0 +1,343 @@
+"""PodnnModel -- the dataset-generation / projection / predict path of the reference's
+poduqnn/podnnmodel.py behind the same method names, running on libpodb200.
+
+Kept: create_snapshots :89, generate_dataset :199, convert_multigpu_data :118 (POD +
+projection part), project_to_v/U :431-437, predict_v :314, predict :366 (closed-form moments
+or Monte-Carlo), restruct/destruct :382-421, the pickle caches :443-503 (same tuples).
+Out of scope (raise): train_model :289.  Host-side bookkeeping (LHS sampling, splits, pickles)
+stays in numpy exactly as in the reference.
+"""
+import ctypes as C
+import os
+import pickle
+import time
+
+import numpy as np
+
+from . import _lib
+from .acceleration import snapshots_device
+from .pod import pod_device, fast_pod_device, DEFAULT_MODE
+from .varneuralnetwork import VarNeuralNetwork, NORM_MEANSTD, ensemble_predict_device
+
+SETUP_DATA_NAME = "setup_data.pkl"
+TRAIN_DATA_NAME = "train_data.pkl"
+INIT_DATA_NAME = "init_data.pkl"
+MODEL_PARAMS_NAME = "model_params.pkl"
+MODEL_NAME = "model_weights"
+MODEL_NAME_EXT = ".npz"
+
+
+def lhs(n, samples):
+    """pyDOE-style centred LHS as the reference's acceleration.lhs :74-94 (numpy RNG)."""
+    cut = np.linspace(0, 1, samples + 1)
+    u = np.random.rand(samples, n)
+    a, b = cut[:samples], cut[1:samples + 1]
+    rd = u * (b - a)[:, None] + a[:, None]
+    H = np.zeros_like(rd)
+    for j in range(n):
+        H[:, j] = rd[np.random.permutation(samples), j]
+    return H
+
+
+def sample_mu(n_s, mu_min, mu_max):
+    """handling.py:40-47 (including the transposed lhs call)."""
+    X_lhs = lhs(n_s, mu_min.shape[0]).T
+    return mu_min + (mu_max - mu_min) * X_lhs
+
+
+def split_dataset(X_v, v, test_size):
+    """handling.py:30-37."""
+    idx = np.random.permutation(X_v.shape[0])
+    limit = np.floor(X_v.shape[0] * (1. - test_size)).astype(int)
+    tr, te = idx[:limit], idx[limit:]
+    return X_v[tr], X_v[te], v[tr], v[te]
+
+
+class PodnnModel:
+    def __init__(self, resdir, n_v, x_mesh, n_t, *, ctx=None, pod_mode=DEFAULT_MODE):
+        self.n_v, self.x_mesh = n_v, x_mesh
+        self.n_xyz = x_mesh.shape[0]
+        self.n_h = self.n_v * x_mesh.shape[0]
+        self.n_t, self.has_t = n_t, n_t > 0
+        self.resdir = resdir
+        self.setup_data_path = os.path.join(resdir, SETUP_DATA_NAME)
+        self.train_data_path = os.path.join(resdir, TRAIN_DATA_NAME)
+        self.init_data_path = os.path.join(resdir, INIT_DATA_NAME)
+        self.model_params_path = os.path.join(resdir, MODEL_PARAMS_NAME)
+        self.model_path = []
+        self.regnn = None
+        self.n_L = self.n_d = self.V = self.layers = self.pod_sig = None
+        self.dtype = "float64"
+        self.pod_mode = pod_mode
+        self._ctx = ctx
+        self._V_dev = None
+        self.save_setup_data()
+
+    @property
+    def ctx(self):
+        if self._ctx is None:
+            self._ctx = _lib.default_context()
+        return self._ctx
+
+    # ------------------------------------------------------------ snapshots
+    def create_snapshots(self, n_d, n_h, u, mu_lhs, t_min=0, t_max=0, u_noise=0., x_noise=0.):
+        """podnnmodel.py:89-116 -> (X_v, U, U_struct, U_no_noise), host arrays."""
+        if u_noise > 0. or x_noise > 0.:
+            raise NotImplementedError("noisy snapshots are outside the CUDA hot path")
+        X = self.x_mesh[:, 1:].T
+        Ud, X_v, _ = snapshots_device(self.ctx, u, X, mu_lhs, self.n_t, t_min, t_max)
+        U = Ud.download()
+        if self.has_t:
+            n_s = mu_lhs.shape[0]
+            Us = self.ctx.alloc(n_h, self.n_t, n_s)
+            self.ctx.check(_lib.lib().pb_matrix_to_struct(self.ctx.h, Ud.ptr, Ud.ld, n_h, self.n_t, n_s, Us.ptr))
+            return X_v, U, Us.download(), U.copy()
+        return X_v, U, U, U.copy()
+
+    # ------------------------------------------------------------ POD + projection on the device
+    def _pod_project(self, U_train_d, U_val_d, eps, eps_init, n_L, n_s_train):
+        ctx, L = self.ctx, _lib.lib()
+        if eps_init is None or not self.has_t:
+            Vd, _ = pod_device(ctx, U_train_d, eps, n_L, self.pod_mode)
+        else:
+            Vd, _ = fast_pod_device(ctx, U_train_d, self.n_t, n_s_train, eps, eps_init, self.pod_mode)
+        self._V_dev = Vd
+        self.V = Vd.download()
+        self.n_L = self.V.shape[1]
+        v_train = self._project_dev(U_train_d).download()
+        v_val = self._project_dev(U_val_d).download() if U_val_d is not None else None
+        # POD error (podnnmodel.py:251-253), fused: U_pod is never materialised
+        vt = ctx.to_device(v_train)
+        sig = ctx.alloc(self.n_h)
+        ctx.check(L.pb_reconstruct(ctx.h, Vd.ptr, Vd.ld, self.n_L, vt.ptr, v_train.shape[0], self.n_h,
+                                   U_train_d.ptr, U_train_d.ld, None, 0, sig.ptr))
+        self.pod_sig = sig.download()
+        print(f"Mean pod sig: {self.pod_sig.mean()}")
+        return v_train, v_val
+
+    def _project_dev(self, Ud):
+        ctx = self.ctx
+        n = Ud.shape[1]
+        v = ctx.alloc(n, self.n_L)
+        ctx.check(_lib.lib().pb_project(ctx.h, self._V_dev.ptr, self._V_dev.ld, self.n_L, Ud.ptr, Ud.ld,
+                                        self.n_h, n, v.ptr))
+        return v
+
+    def _ensure_V_dev(self):
+        if self._V_dev is None:
+            if self.V is None:
+                raise ValueError("no POD basis: call generate_dataset / convert_multigpu_data / load_train_data")
+            self._V_dev = self.ctx.to_device(self.V)
+        return self._V_dev
+
+    def generate_dataset(self, u, mu_min, mu_max, n_s, train_val, eps=0., eps_init=None, n_L=0,
+                         t_min=0, t_max=0, u_noise=0., x_noise=0., rm_init=False, *, mu_lhs=None):
+        """podnnmodel.py:199-275.  `mu_lhs` (keyword) bypasses the LHS sampling for reproducible runs."""
+        if u_noise > 0. or x_noise > 0.:
+            raise NotImplementedError("noisy snapshots are outside the CUDA hot path")
+        mu_min, mu_max = np.array(mu_min), np.array(mu_max)
+        n_d = mu_min.shape[0] + (1 if self.has_t else 0)
+        self.n_d = n_d
+        print("Doing the LHS sampling on the non-spatial params...")
+        if mu_lhs is None:
+            mu_lhs = sample_mu(n_s, mu_min, mu_max)
+        _, _, mu_tr, mu_val = split_dataset(np.zeros_like(mu_lhs), mu_lhs, test_size=train_val[1])
+        n_st = n_s * (self.n_t if self.has_t else 1)
+        print(f"Generating {n_st} corresponding snapshots")
+        X = self.x_mesh[:, 1:].T
+        U_tr_d, X_v_train, _ = snapshots_device(self.ctx, u, X, mu_tr, self.n_t, t_min, t_max)
+        U_val_d, X_v_val, _ = snapshots_device(self.ctx, u, X, mu_val, self.n_t, t_min, t_max)
+        v_train, v_val = self._pod_project(U_tr_d, U_val_d, eps, eps_init, n_L, mu_tr.shape[0])
+        U_train, U_val = U_tr_d.download(), U_val_d.download()
+        if self.n_t > 0 and rm_init:        # podnnmodel.py:256-272
+            idx = np.arange(mu_tr.shape[0]) * self.n_t
+            init = [X_v_train[idx], v_train[idx], U_train[:, idx]]
+            X_v_train, v_train, U_train = (np.delete(X_v_train, idx, 0), np.delete(v_train, idx, 0),
+                                           np.delete(U_train, idx, 1))
+            idx = np.arange(mu_val.shape[0]) * self.n_t
+            init += [X_v_val[idx], v_val[idx], U_val[:, idx]]
+            X_v_val, v_val, U_val = np.delete(X_v_val, idx, 0), np.delete(v_val, idx, 0), np.delete(U_val, idx, 1)
+            self.save_init_data(*init)
+        self.save_train_data(X_v_train, v_train, U_train, X_v_val, v_val, U_val)
+        return X_v_train, v_train, U_train, X_v_val, v_val, U_val
+
+    def convert_multigpu_data(self, U_struct, X_v, train_val, eps, eps_init=None, n_L=0,
+                              use_cache=False, save_cache=False):
+        """podnnmodel.py:118-197 without the initial-condition removal (:179-194 has index slips,
+        SURVEY App. B).  U_struct is (n_v, n_xyz, n_t, n_s) or (n_v, n_xyz, n_s)."""
+        if use_cache and os.path.exists(self.train_data_path):
+            return self.load_train_data()
+        n_s = U_struct.shape[-1]
+        n_t = self.n_t if self.n_t > 0 else 1
+        self.n_d = X_v.shape[1]
+        idx_s = np.random.permutation(n_s)
+        limit = np.floor(n_s * (1. - train_val[1])).astype(int)
+        tr, va = idx_s[:limit], idx_s[limit:]
+        X_v_train = np.concatenate([X_v[i*n_t:(i+1)*n_t] for i in tr])
+        X_v_val = np.concatenate([X_v[i*n_t:(i+1)*n_t] for i in va]) if len(va) else np.zeros((0, X_v.shape[1]))
+        U_train = self.destruct(U_struct[..., tr])
+        U_val = self.destruct(U_struct[..., va])
+        ctx = self.ctx
+        Ut, Uv = ctx.to_device(U_train), (ctx.to_device(U_val) if len(va) else None)
+        if eps_init is not None and self.has_t:
+            # the reference feeds ALL samples (incl. validation) to the two-step POD (:160)
+            Uall = ctx.to_device(self.destruct(U_struct))
+            Vd, _ = fast_pod_device(ctx, Uall, n_t, n_s, eps, eps_init, self.pod_mode)
+            self._V_dev, self.V = Vd, Vd.download()
+            self.n_L = self.V.shape[1]
+            v_train, v_val = self._finish_projection(Ut, Uv)
+        else:
+            v_train, v_val = self._pod_project(Ut, Uv, eps, None, n_L, len(tr))
+        if save_cache:
+            self.save_train_data(X_v_train, v_train, U_train, X_v_val, v_val, U_val)
+        return X_v_train, v_train, X_v_val, v_val, U_val
+
+    def _finish_projection(self, Ut, Uv):
+        ctx, L = self.ctx, _lib.lib()
+        v_train = self._project_dev(Ut).download()
+        v_val = self._project_dev(Uv).download() if Uv is not None else None
+        vt, sig = ctx.to_device(v_train), ctx.alloc(self.n_h)
+        ctx.check(L.pb_reconstruct(ctx.h, self._V_dev.ptr, self._V_dev.ld, self.n_L, vt.ptr, v_train.shape[0],
+                                   self.n_h, Ut.ptr, Ut.ld, None, 0, sig.ptr))
+        self.pod_sig = sig.download()
+        print(f"Mean pod sig: {self.pod_sig.mean()}")
+        return v_train, v_val
+
+    # ------------------------------------------------------------ projection helpers
+    def project_to_U(self, v):
+        """V.dot(v.T), podnnmodel.py:431-433."""
+        ctx, Vd = self.ctx, self._ensure_V_dev()
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        vd, out = ctx.to_device(v), ctx.alloc(self.n_h, v.shape[0])
+        ctx.check(_lib.lib().pb_reconstruct(ctx.h, Vd.ptr, Vd.ld, self.n_L, vd.ptr, v.shape[0], self.n_h,
+                                            None, 0, out.ptr, out.ld, None))
+        return out.download()
+
+    def project_to_v(self, U):
+        """(V.T.dot(U)).T, podnnmodel.py:435-437."""
+        self._ensure_V_dev()
+        return self._project_dev(self.ctx.to_device(np.asarray(U, dtype=np.float64))).download()
+
+    # ------------------------------------------------------------ ensemble
+    def initVNNs(self, n_M, h_layers, lr, lam, adv_eps, soft_0=1., norm=NORM_MEANSTD, seed=None):
+        """podnnmodel.py:277-287: creates the (untrained, glorot-initialised) ensemble."""
+        self.layers = [self.n_d, *h_layers, self.n_L]
+        self.regnn, self.model_path = [], []
+        for i in range(n_M):
+            self.regnn.append(VarNeuralNetwork(self.layers, lr, lam, adv_eps, soft_0, norm,
+                                               seed=None if seed is None else seed + i))
+            self.model_path.append(os.path.join(self.resdir, f"{MODEL_NAME}-{i}-{time.time()}"))
+        self.save_model()
+
+    def train_model(self, *a, **k):
+        raise NotImplementedError("ensemble training (podnnmodel.py:289-312) is outside the CUDA hot path")
+
+    def _ensemble_args(self):
+        if not self.regnn:
+            raise ValueError("Regression model isn't defined.")      # podnnmodel.py:295
+        m0 = self.regnn[0]
+        return [m.weights for m in self.regnn], m0.layers, m0.soft_0, m0.norm, m0.norm_bounds
+
+    def predict_v(self, X_v):
+        """Gaussian-mixture moments over the members, podnnmodel.py:314-328 -> (v_pred, v_pred_sig)."""
+        members, layers, soft_0, norm, nb = self._ensemble_args()
+        vm, vs = ensemble_predict_device(self.ctx, members, layers, X_v, soft_0, norm, nb)
+        return vm.download(), vs.download()
+
+    def predict(self, X_v, samples=100):
+        """podnnmodel.py:366-379.  The reference averages `samples` TF-RNG draws of
+        v ~ N(v_pred, v_pred_sig); their exact moments U_pred = V v_pred^T,
+        U_pred_sig = sqrt((V*V) (v_pred_sig^2)^T) are returned (the limit samples -> inf)."""
+        print(f"Averaging {samples} model configurations...")
+        ctx, Vd = self.ctx, self._ensure_V_dev()
+        members, layers, soft_0, norm, nb = self._ensemble_args()
+        vm, vs = ensemble_predict_device(ctx, members, layers, X_v, soft_0, norm, nb)
+        N = vm.shape[0]
+        Um, Us = ctx.alloc(self.n_h, N), ctx.alloc(self.n_h, N)
+        ctx.check(_lib.lib().pb_predict_U(ctx.h, Vd.ptr, Vd.ld, self.n_h, self.n_L, vm.ptr, vs.ptr, N, 0, 0,
+                                          Um.ptr, Us.ptr, Um.ld))
+        return Um.download(), Us.download()
+
+    # ------------------------------------------------------------ layout helpers (host index maps)
+    def get_u_tuple(self, n_t=None):
+        n_t = self.n_t if n_t is None else n_t
+        return (self.n_v, self.n_xyz) + ((n_t,) if self.has_t else ())
+
+    def restruct(self, U, no_s=False, n_t=None):
+        """podnnmodel.py:382-402."""
+        if no_s:
+            return U.reshape(self.get_u_tuple())
+        if self.has_t:
+            n_t = self.n_t if n_t is None else n_t
+            n_s = int(U.shape[-1] / n_t)
+            return np.ascontiguousarray(U.reshape(self.n_v, self.n_xyz, n_s, n_t).transpose(0, 1, 3, 2))
+        return U.reshape(self.n_v, self.n_xyz, U.shape[-1]).copy()
+
+    def destruct(self, U_struct):
+        """podnnmodel.py:404-421."""
+        n_s = int(U_struct.shape[-1])
+        if self.has_t:
+            return np.ascontiguousarray(U_struct.transpose(0, 1, 3, 2)).reshape(self.n_h, n_s * self.n_t)
+        return U_struct.reshape(self.n_h, n_s).copy()
+
+    # ------------------------------------------------------------ caches (same tuples as the reference)
+    def load_train_data(self):
+        if not os.path.exists(self.train_data_path):
+            raise FileNotFoundError("Can't find train data.")
+        with open(self.train_data_path, "rb") as f:
+            data = pickle.load(f)
+        self.n_L, self.n_d, self.V, self.pod_sig = data[0], data[1], data[2], data[3]
+        self._V_dev = None
+        print(f"Mean pod sig: {self.pod_sig.mean()}")
+        return data[4:]
+
+    def save_train_data(self, X_v_train, v_train, U_train, X_v_val, v_val, U_val):
+        with open(self.train_data_path, "wb") as f:
+            pickle.dump((self.n_L, self.n_d, self.V, self.pod_sig,
+                         X_v_train, v_train, U_train, X_v_val, v_val, U_val), f)
+
+    def load_init_data(self):
+        if not os.path.exists(self.init_data_path):
+            raise FileNotFoundError("Can't find train data.")
+        with open(self.init_data_path, "rb") as f:
+            return pickle.load(f)
+
+    def save_init_data(self, X_v_train, v_train, U_train, X_v_val, v_val, U_val):
+        with open(self.init_data_path, "wb") as f:
+            pickle.dump((X_v_train, v_train, U_train, X_v_val, v_val, U_val), f)
+
+    def save_setup_data(self):
+        os.makedirs(self.resdir, exist_ok=True)
+        with open(self.setup_data_path, "wb") as f:
+            pickle.dump((self.n_v, self.x_mesh, self.n_t), f)
+
+    @classmethod
+    def load_setup_data(cls, save_dir):
+        path = os.path.join(save_dir, SETUP_DATA_NAME)
+        if not os.path.exists(path):
+            raise FileNotFoundError("Can't find setup data.")
+        with open(path, "rb") as f:
+            return pickle.load(f)
+
+    def save_model(self, model_id=-1):
+        ids = range(len(self.regnn)) if model_id < 0 else [model_id]
+        for i in ids:
+            self.regnn[i].save_to(self.model_path[i], self.model_params_path)
+
+    def load_model(self):
+        if not all(os.path.exists(p + MODEL_NAME_EXT) for p in self.model_path):
+            raise FileNotFoundError("Can't find cached model.")
+        if not os.path.exists(self.model_params_path):
+            raise FileNotFoundError("Can't find cached model params.")
+        self.regnn = [VarNeuralNetwork.load_from(p, self.model_params_path) for p in self.model_path]
+
+    @classmethod
+    def load(cls, save_dir, **kw):
+        n_v, x_mesh, n_t = cls.load_setup_data(save_dir)
+        paths = [os.path.join(save_dir, f[:-len(MODEL_NAME_EXT)]) for f in sorted(os.listdir(save_dir))
+                 if f.startswith(MODEL_NAME) and f.endswith(MODEL_NAME_EXT)]
+        model = cls(save_dir, n_v, x_mesh, n_t, **kw)
+        model.model_path = paths
+        model.load_train_data()
+        model.load_model()
+        return model

@@ -1,0 +1,139 @@
+"""Mean/variance MLP -- forward path of the reference's poduqnn/varneuralnetwork.py
+(build_model :42-62, normalize :75-86, predict :154-160) on the GPU (csrc/mlp.cu).
+
+Training (grad / Adam / fit, :94-152) is outside the hot path and raises.  Weights use the
+Keras ``model.get_weights()`` order ``[W0, b0, W1, b1, ...]`` with kernels shaped (in, out);
+`soft_0` is explicit (the reference's load_from drops it, varneuralnetwork.py:191-193).
+"""
+import ctypes as C
+import pickle
+
+import numpy as np
+
+from . import _lib
+from ._lib import NORM_IDS
+
+NORM_NONE = "none"
+NORM_MEANSTD = "meanstd"
+NORM_CENTER = "center"
+
+
+def glorot_normal(rng, fan_in, fan_out):
+    """Keras glorot_normal: truncated normal, std = sqrt(2/(fan_in+fan_out)) / 0.8796..."""
+    std = np.sqrt(2. / (fan_in + fan_out)) / .87962566103423978
+    z = rng.standard_normal((fan_in, fan_out))
+    bad = np.abs(z) > 2.
+    while bad.any():
+        z[bad] = rng.standard_normal(int(bad.sum()))
+        bad = np.abs(z) > 2.
+    return z * std
+
+
+def pack_members(members):
+    """[[W0,b0,...], ...] -> one flat float64 array in the pb_ensemble_predict layout."""
+    return np.concatenate([np.concatenate([np.ascontiguousarray(a, dtype=np.float64).ravel() for a in w])
+                           for w in members])
+
+
+def ensemble_predict_device(ctx, members, layers, X, soft_0=1., norm=NORM_NONE, norm_bounds=None,
+                            packed_dev=None):
+    """Mixture moments of an ensemble on the device: returns (v_mean_dev, v_sig_dev), (N, n_L) each.
+
+    With one member v_sig is that member's scale (variance = v_sig**2 exactly).
+    """
+    L = _lib.lib()
+    dims = list(layers[:-1]) + [2 * layers[-1]]
+    n_layers = len(dims) - 1
+    n_L = layers[-1]
+    Xd = X if isinstance(X, _lib.DeviceArray) else ctx.to_device(np.asarray(X, dtype=np.float64).reshape(-1, dims[0]))
+    N = Xd.shape[0]
+    w = packed_dev if packed_dev is not None else ctx.to_device(pack_members(members))
+    kind = NORM_IDS[norm] if norm_bounds is not None else 0      # norm_bounds None => identity (:77-78)
+    na = nb = None
+    if kind:
+        na = ctx.to_device(np.broadcast_to(np.asarray(norm_bounds[0], dtype=np.float64), (dims[0],)).copy())
+        nb = ctx.to_device(np.broadcast_to(np.asarray(norm_bounds[1], dtype=np.float64), (dims[0],)).copy())
+    vm, vs = ctx.alloc(N, n_L), ctx.alloc(N, n_L)
+    cdims = (C.c_int * len(dims))(*dims)
+    ctx.check(L.pb_ensemble_predict(ctx.h, len(members) if members is not None else packed_dev.n_members,
+                                    n_layers, cdims, w.ptr, kind,
+                                    na.ptr if na else None, nb.ptr if nb else None, float(soft_0),
+                                    Xd.ptr, N, vm.ptr, vs.ptr))
+    return vm, vs
+
+
+class VarNeuralNetwork:
+    """Same constructor signature as the reference (varneuralnetwork.py:17-18)."""
+
+    def __init__(self, layers, lr, lam, adv_eps=None, soft_0=1., norm=NORM_NONE, weights_path=None,
+                 norm_bounds=None, seed=None):
+        self.dtype = "float64"
+        self.layers, self.lr, self.lam = list(layers), lr, lam
+        self.adv_eps, self.soft_0, self.norm, self.norm_bounds = adv_eps, soft_0, norm, norm_bounds
+        rng = np.random.default_rng(seed)
+        dims = self.layers[:-1] + [2 * self.layers[-1]]
+        self.weights = []
+        for fi, fo in zip(dims[:-1], dims[1:]):          # Keras: glorot_normal kernels, zero biases
+            self.weights += [glorot_normal(rng, fi, fo), np.zeros(fo)]
+        if weights_path is not None:
+            self.load_weights(weights_path)
+
+    # --- weights -----------------------------------------------------------
+    def set_weights(self, weights):
+        dims = self.layers[:-1] + [2 * self.layers[-1]]
+        if len(weights) != 2 * (len(dims) - 1):
+            raise ValueError("expected [W0, b0, W1, b1, ...]")
+        for l, (fi, fo) in enumerate(zip(dims[:-1], dims[1:])):
+            if np.shape(weights[2*l]) != (fi, fo) or np.shape(weights[2*l+1]) != (fo,):
+                raise ValueError(f"layer {l}: expected kernel {(fi, fo)} and bias {(fo,)}")
+        self.weights = [np.asarray(w, dtype=np.float64) for w in weights]
+
+    def get_weights(self):
+        return self.weights
+
+    def load_weights(self, path):
+        with np.load(path if path.endswith(".npz") else path + ".npz") as z:
+            self.set_weights([z[f"arr_{i}"] for i in range(len(z.files))])
+
+    def save_weights(self, path):
+        np.savez(path if path.endswith(".npz") else path + ".npz", *self.weights)
+
+    # --- normalisation (varneuralnetwork.py:64-86) ---------------------------
+    def set_normalize_bounds(self, X):
+        if self.norm == NORM_CENTER:
+            self.norm_bounds = (np.amin(X, axis=0), np.amax(X, axis=0))
+        elif self.norm == NORM_MEANSTD:
+            self.norm_bounds = (X.mean(0), X.std(0))
+
+    # --- forward -------------------------------------------------------------
+    def predict(self, X, *, ctx=None):
+        """(mean, variance) of the predictive Normal, as the reference (:154-160)."""
+        ctx = ctx or _lib.default_context()
+        vm, vs = ensemble_predict_device(ctx, [self.weights], self.layers, X, self.soft_0, self.norm,
+                                         self.norm_bounds)
+        return vm.download(), vs.download() ** 2
+
+    def predict_dist(self, X, *, ctx=None):
+        """(loc, scale) of the predictive Normal (the reference returns a tfd.Normal, :162-165)."""
+        ctx = ctx or _lib.default_context()
+        vm, vs = ensemble_predict_device(ctx, [self.weights], self.layers, X, self.soft_0, self.norm,
+                                         self.norm_bounds)
+        return vm.download(), vs.download()
+
+    def fit(self, *a, **k):
+        raise NotImplementedError("training (varneuralnetwork.py:94-152) is outside the CUDA hot path")
+
+    fit_simple = fit
+
+    def save_to(self, model_path, params_path):
+        """Same params tuple as the reference (:175-180); weights as .npz instead of a TF checkpoint."""
+        with open(params_path, "wb") as f:
+            pickle.dump((self.layers, self.lr, self.lam, self.soft_0, self.norm, self.norm_bounds), f)
+        self.save_weights(model_path)
+
+    @classmethod
+    def load_from(cls, weights_path, params_path):
+        with open(params_path, "rb") as f:
+            layers, lr, lam, soft_0, norm, norm_bounds = pickle.load(f)
+        # unlike the reference (:191-193) soft_0 is restored
+        return cls(layers, lr, lam, soft_0=soft_0, norm=norm, weights_path=weights_path, norm_bounds=norm_bounds)
