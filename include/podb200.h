@@ -63,7 +63,8 @@ extern "C" {
 #define PB_T_PREDICT    6
 #define PB_T_POD_TOTAL  7
 #define PB_T_PASS2      8
-#define PB_T_COUNT      9
+#define PB_T_TN_KERNEL  9   /* the split-K DMMA kernel of the last pb_gram / TN product alone */
+#define PB_T_COUNT      10
 
 typedef struct pb_ctx pb_ctx;
 
@@ -76,6 +77,9 @@ int  pb_sync(pb_ctx* ctx);
 int  pb_device_info(pb_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* mem_bytes);
 int  pb_last_ms(pb_ctx* ctx, int which, double* ms);  /* device time of the last op of that kind */
 int64_t pb_kernel_launches(pb_ctx* ctx);              /* kernels launched by this context so far */
+/* region timer on the context stream (CUDA events): start, then stop returns the device ms */
+int  pb_timer_start(pb_ctx* ctx);
+int  pb_timer_stop(pb_ctx* ctx, double* ms);
 
 /* ---- device memory (plain cudaMalloc / copies on the context stream) ---- */
 int  pb_malloc(pb_ctx* ctx, size_t bytes, void** dev);

@@ -81,10 +81,19 @@ def loop_u(u, n_h, X_v, U, U_no_noise, X, mu_lhs):
     return X_v, U, U, U_no_noise
 
 
+def linspace_numba_parallel(start, stop, num):
+    """np.linspace as numba evaluates it inside the reference's @jit(parallel=True) loop_u_t
+    (acceleration.py:38): start + (i * (stop - start)) / (num - 1), which differs from numpy's
+    start + i * step in the last bit for some i (pinned against the reference in gen_golden.py)."""
+    if num == 1:
+        return np.array([float(start)])
+    return start + (np.arange(num) * (float(stop) - float(start))) / (num - 1)
+
+
 def loop_u_t(u, n_t, n_v, n_xyz, n_h, X_v, U, U_no_noise, U_struct, X, mu_lhs,
              t_min, t_max):
     """acceleration.py:34-70 with u_noise = x_noise = 0."""
-    t = np.linspace(t_min, t_max, n_t)
+    t = linspace_numba_parallel(t_min, t_max, n_t)
     tT = t.reshape((n_t, 1))
     for i in range(mu_lhs.shape[0]):
         s = n_t * i

@@ -20,7 +20,7 @@ PB_ERR_CUDA, PB_ERR_SHAPE, PB_ERR_UNSUPPORTED_FIELD, PB_ERR_NOT_CONVERGED, PB_ER
 FIELD_IDS = {"shekel": 1, "ackley": 2, "burgers": 3}
 POD_MODES = {"gram": 0, "gram2": 1, "accurate": 2}
 NORM_IDS = {"none": 0, "meanstd": 1, "center": 2}
-T_GRAM, T_EIG, T_BASIS, T_PROJECT, T_RECON, T_SNAPSHOTS, T_PREDICT, T_POD_TOTAL, T_PASS2 = range(9)
+T_GRAM, T_EIG, T_BASIS, T_PROJECT, T_RECON, T_SNAPSHOTS, T_PREDICT, T_POD_TOTAL, T_PASS2, T_TN_KERNEL = range(10)
 
 _i64, _int, _dbl, _vp = C.c_int64, C.c_int, C.c_double, C.c_void_p
 _pi, _pd, _pvp = C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_void_p)
@@ -35,6 +35,8 @@ SIGNATURES = {
     "pb_device_info": (_int, [_vp, _pi, _pi, _pi, C.POINTER(C.c_size_t)]),
     "pb_last_ms": (_int, [_vp, _int, _pd]),
     "pb_kernel_launches": (_i64, [_vp]),
+    "pb_timer_start": (_int, [_vp]),
+    "pb_timer_stop": (_int, [_vp, _pd]),
     "pb_malloc": (_int, [_vp, C.c_size_t, _pvp]),
     "pb_free": (_int, [_vp, _vp]),
     "pb_memset": (_int, [_vp, _vp, _int, C.c_size_t]),
@@ -184,6 +186,14 @@ class Context:
     def ms(self, which):
         v = C.c_double()
         self.check(lib().pb_last_ms(self.h, which, C.byref(v)))
+        return v.value
+
+    def timer_start(self):
+        self.check(lib().pb_timer_start(self.h))
+
+    def timer_stop(self):
+        v = C.c_double()
+        self.check(lib().pb_timer_stop(self.h, C.byref(v)))
         return v.value
 
     def launches(self):

@@ -14,6 +14,14 @@ from . import _lib
 from .fields import resolve
 
 
+def time_grid(t_min, t_max, n_t):
+    """The reference's time steps: np.linspace as numba's parallel JIT evaluates it
+    (start + (i * (stop - start)) / (n - 1); last-bit different from numpy for some i)."""
+    if n_t == 1:
+        return np.array([float(t_min)])
+    return t_min + (np.arange(n_t) * (float(t_max) - float(t_min))) / (n_t - 1)
+
+
 def snapshots_device(ctx, u, X, mu_lhs, n_t=0, t_min=0., t_max=0., row0=0, n_rows=None, out=None):
     """Fill (and return) the device snapshot matrix for nodes [row0, row0+n_rows).
 
@@ -30,7 +38,7 @@ def snapshots_device(ctx, u, X, mu_lhs, n_t=0, t_min=0., t_max=0., row0=0, n_row
         raise ValueError(f"field '{f.name}' is {'time-dependent' if f.has_t else 'steady'}; got n_t={n_t}")
     n_rows = n_xyz - row0 if n_rows is None else n_rows
     n_st = n_s * (n_t if has_t else 1)
-    t = np.linspace(t_min, t_max, n_t) if has_t else None      # acceleration.py:38
+    t = time_grid(t_min, t_max, n_t) if has_t else None        # acceleration.py:38
     Xd, mud = ctx.to_device(X), ctx.to_device(mu)
     td = ctx.to_device(t) if has_t else None
     U = out if out is not None else ctx.alloc(n_rows, n_st)

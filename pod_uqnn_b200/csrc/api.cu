@@ -69,6 +69,8 @@ int pb_create(int device, pb_ctx** out) {
     ctx->stream = ctx->own_stream;
     PB_CUDA(ctx, cudaEventCreate(&ctx->ev0)); PB_CUDA(ctx, cudaEventCreate(&ctx->ev1));
     PB_CUDA(ctx, cudaEventCreate(&ctx->ev2)); PB_CUDA(ctx, cudaEventCreate(&ctx->ev3));
+    PB_CUDA(ctx, cudaEventCreate(&ctx->evk0)); PB_CUDA(ctx, cudaEventCreate(&ctx->evk1));
+    PB_CUDA(ctx, cudaEventCreate(&ctx->evr0)); PB_CUDA(ctx, cudaEventCreate(&ctx->evr1));
     PB_CUDA(ctx, cudaMalloc(&ctx->d_int, 64 * sizeof(int)));
     PB_CUDA(ctx, cudaMemset(ctx->d_int, 0, 64 * sizeof(int)));
     PB_CUDA(ctx, cudaMallocHost(&ctx->h_int, 64 * sizeof(int)));
@@ -85,6 +87,7 @@ int pb_destroy(pb_ctx* ctx) {
     for (void* b : bufs) if (b) cudaFree(b);
     if (ctx->h_int) cudaFreeHost(ctx->h_int);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);
+    cudaEventDestroy(ctx->evk0); cudaEventDestroy(ctx->evk1); cudaEventDestroy(ctx->evr0); cudaEventDestroy(ctx->evr1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return PB_OK;
@@ -103,7 +106,20 @@ int pb_device_info(pb_ctx* ctx, int* sm, int* maj, int* min_, size_t* mem) {
     return PB_OK;
 }
 int pb_last_ms(pb_ctx* ctx, int which, double* ms) {
-    if (!ctx || which < 0 || which >= PB_T_COUNT || !ms) return PB_ERR_ARG; *ms = ctx->ms[which]; return PB_OK;
+    if (!ctx || which < 0 || which >= PB_T_COUNT || !ms) return PB_ERR_ARG;
+    if (which == PB_T_TN_KERNEL && ctx->tn_timing_pending) {
+        PB_CUDA(ctx, cudaEventSynchronize(ctx->evk1));
+        float t = 0; cudaEventElapsedTime(&t, ctx->evk0, ctx->evk1); ctx->ms[PB_T_TN_KERNEL] = t;
+        ctx->tn_timing_pending = false;
+    }
+    *ms = ctx->ms[which]; return PB_OK;
+}
+int pb_timer_start(pb_ctx* ctx) { if (!ctx) return PB_ERR_ARG; PB_CUDA(ctx, cudaEventRecord(ctx->evr0, ctx->stream)); return PB_OK; }
+int pb_timer_stop(pb_ctx* ctx, double* ms) {
+    if (!ctx || !ms) return PB_ERR_ARG;
+    PB_CUDA(ctx, cudaEventRecord(ctx->evr1, ctx->stream));
+    PB_CUDA(ctx, cudaEventSynchronize(ctx->evr1));
+    float t = 0; PB_CUDA(ctx, cudaEventElapsedTime(&t, ctx->evr0, ctx->evr1)); *ms = t; return PB_OK;
 }
 int64_t pb_kernel_launches(pb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
@@ -138,7 +154,7 @@ int pb_gram(pb_ctx* ctx, const double* A, int64_t rows, int64_t cols, int64_t ld
     if (!ctx) return PB_ERR_ARG;
     if (lda < cols) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_gram: lda %lld < n_cols %lld", (long long)lda, (long long)cols);
     Timer t(ctx, PB_T_GRAM);
-    PB_TRY(pbi_gemm_tn(ctx, A, lda, cols, A, lda, cols, rows, G, cols, 1));
+    PB_TRY(pbi_gemm_tn(ctx, A, lda, cols, A, lda, cols, rows, G, cols, 3));   // sym | time the main kernel
     t.stop();
     return PB_OK;
 }

@@ -17,6 +17,9 @@ struct pb_ctx {
     int64_t launches = 0;
     double ms[PB_T_COUNT] = {0};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t evk0 = nullptr, evk1 = nullptr;     // around the TN main kernel
+    cudaEvent_t evr0 = nullptr, evr1 = nullptr;     // user region timer
+    bool tn_timing_pending = false;
 
     // split-K workspace of the TN products (grown on demand)
     double* ws = nullptr;  size_t ws_bytes = 0;

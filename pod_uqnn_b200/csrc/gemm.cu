@@ -296,6 +296,8 @@ int choose_splits(int tiles, int64_t rows, int sms) {
     return best;
 }
 
+bool g_time_tn = false;   // set per call by pbi_gemm_tn (contexts are single-threaded)
+
 template <int BM, int BN, int WARPS_M, int WARPS_N>
 int launch_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const double* B, int64_t ldb,
               int64_t kb, int64_t rows, double* C, int64_t ldc, int sym) {
@@ -315,6 +317,7 @@ int launch_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const doubl
     const bool al = aligned16(A, lda) && aligned16(B, ldb);
     size_t smem = (size_t)STAGES * BK * ((BM + 4) + (BN + 4)) * sizeof(double);
     dim3 grid(tiles, splits);
+    if (g_time_tn) cudaEventRecord(ctx->evk0, ctx->stream);
     if (al) {
         auto kern = gemm_tn_kernel<BM, BN, WARPS_M, WARPS_N, STAGES, true>;
         PB_TRY(set_smem(ctx, kern, smem));
@@ -327,6 +330,7 @@ int launch_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const doubl
                                                     split_stride, tiles_m, tiles_n, sym);
     }
     PB_LAUNCH_CHECK(ctx);
+    if (g_time_tn) { cudaEventRecord(ctx->evk1, ctx->stream); ctx->tn_timing_pending = true; }
     if (!direct) {
         int64_t n = (int64_t)ka * kb;
         reduce_splits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
@@ -363,7 +367,9 @@ int launch_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m
 }  // namespace
 
 int pbi_gemm_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const double* B, int64_t ldb,
-                int64_t kb, int64_t rows, double* C, int64_t ldc, int sym) {
+                int64_t kb, int64_t rows, double* C, int64_t ldc, int flags) {
+    const int sym = flags & 1;
+    g_time_tn = (flags & 2) != 0;
     if (ka <= 0 || kb <= 0 || rows < 0) PB_FAIL(ctx, PB_ERR_SHAPE, "gemm_tn: bad shape ka=%lld kb=%lld rows=%lld",
                                                 (long long)ka, (long long)kb, (long long)rows);
     if (ka > (1 << 20) || kb > (1 << 20)) PB_FAIL(ctx, PB_ERR_SHAPE, "gemm_tn: ka/kb too large");

@@ -1,0 +1,113 @@
+"""Row-sharded POD / projection across the GPUs of one box (one process per GPU).
+
+U is sharded by dof: rank p owns the contiguous row slab row_range(n_h, p, P) of the
+row-major snapshot matrix.  Exchange steps (the only ones on the path):
+  * sum-all-reduce of the local n_st x n_st Gram partial (and of the second-pass Gram),
+  * sum-all-reduce of the local projection partial V_p^T U_p.
+The small eigensolve is replicated: every rank runs it on the bit-identical reduced Gram
+and gets the same rank and factors.  Snapshot generation, basis, reconstruction and
+pod_sig need no communication.
+
+torch is the carrier of the buffers that cross ranks (torch.distributed over NCCL on the
+GPU box, gloo in the CPU tests); the compute is injected as a `backend` so that the host
+logic here is testable without a GPU (tests/test_sharded_gloo.py uses a numpy test double).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import POD_MODES
+
+
+def row_range(n, rank, world):
+    """Contiguous, balanced slab [lo, hi) of n rows for `rank` of `world`."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _all_reduce(t, group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def pod_sharded(backend, A_local, eps=0., n_L=0, mode="gram", group=None):
+    """POD of the row-sharded tall matrix.  Returns (V_local, sigma, n_L)."""
+    G = backend.gram(A_local)
+    backend.reduce(G, group)
+    n_L_out, keep = backend.pod_from_gram(G, eps, n_L, mode)
+    Y = None
+    if keep > 0:
+        Y, G2 = backend.pass2_gram(A_local, keep)
+        backend.reduce(G2, group)
+        n_L_out = backend.pass2_finish(G2, eps, n_L)
+    V = backend.basis(A_local, Y, n_L_out)
+    return V, backend.sigma(), n_L_out
+
+
+def project_sharded(backend, V_local, U_local, group=None):
+    """v (n x n_L) = sum over ranks of (V_p^T U_p)^T."""
+    v = backend.project(V_local, U_local)
+    backend.reduce(v, group)
+    return v
+
+
+class CudaBackend:
+    """libpodb200 on this rank's GPU; reduced buffers are torch CUDA tensors."""
+
+    def __init__(self, ctx):
+        import torch
+        self.ctx, self.torch = ctx, torch
+        self.dev = torch.device("cuda", ctx.device)
+        self.L = _lib.lib()
+
+    def _empty(self, *shape):
+        return self.torch.empty(*shape, dtype=self.torch.float64, device=self.dev)
+
+    def reduce(self, t, group=None):
+        # the library runs on its own stream: order it before NCCL, and NCCL before the next kernel
+        self.ctx.sync()
+        _all_reduce(t, group)
+        self.torch.cuda.current_stream(self.dev).synchronize()
+
+    def gram(self, A):
+        m = A.shape[1]
+        G = self._empty(m, m)
+        self.ctx.check(self.L.pb_gram(self.ctx.h, A.ptr, A.shape[0], m, A.ld, G.data_ptr()))
+        return G
+
+    def pod_from_gram(self, G, eps, n_L, mode):
+        nl, keep = C.c_int(), C.c_int()
+        self.ctx.check(self.L.pb_pod_from_gram(self.ctx.h, G.data_ptr(), G.shape[0], float(eps), int(n_L),
+                                               POD_MODES[mode], C.byref(nl), C.byref(keep)))
+        return nl.value, keep.value
+
+    def pass2_gram(self, A, keep):
+        Y = self.ctx.alloc(A.shape[0], keep)
+        G2 = self._empty(keep, keep)
+        self.ctx.check(self.L.pb_pod_pass2_gram(self.ctx.h, A.ptr, A.shape[0], A.ld, Y.ptr, G2.data_ptr()))
+        return Y, G2
+
+    def pass2_finish(self, G2, eps, n_L):
+        nl = C.c_int()
+        self.ctx.check(self.L.pb_pod_pass2_finish(self.ctx.h, G2.data_ptr(), float(eps), int(n_L), C.byref(nl)))
+        return nl.value
+
+    def basis(self, A, Y, n_L):
+        V = self.ctx.alloc(A.shape[0], n_L)
+        self.ctx.check(self.L.pb_pod_basis(self.ctx.h, A.ptr, A.shape[0], A.ld, Y.ptr if Y is not None else None,
+                                           V.ptr, V.ld))
+        return V
+
+    def sigma(self):
+        from .pod import pod_sigma
+        return pod_sigma(self.ctx)
+
+    def project(self, V, U):
+        n, n_L = U.shape[1], V.shape[1]
+        v = self._empty(n, n_L)
+        self.ctx.check(self.L.pb_project(self.ctx.h, V.ptr, V.ld, n_L, U.ptr, U.ld, U.shape[0], n, v.data_ptr()))
+        return v

@@ -1,0 +1,55 @@
+"""Numpy test double of the compute backend used by pod_uqnn_b200.sharded (CPU tests only).
+
+It lets the gloo world_size-2 test exercise the HOST logic of the sharded path (row
+partition, the two all-reduces, replicated eigensolve, local basis) without a GPU.  It is
+not a fallback: the product never imports it."""
+import numpy as np
+import torch
+
+from oracle import pod_oracle as po
+
+
+class NumpyBackend:
+    def __init__(self):
+        self._sig = None
+        self._W = None
+
+    def reduce(self, t, group=None):
+        from pod_uqnn_b200.sharded import _all_reduce
+        _all_reduce(t, group)
+
+    def gram(self, A):
+        return torch.from_numpy(A.T @ A)
+
+    def pod_from_gram(self, G, eps, n_L, mode):
+        lam, W = np.linalg.eigh(G.numpy())
+        lam, W = np.maximum(lam[::-1], 0.), W[:, ::-1]
+        self._sig, self._W = np.sqrt(lam), W
+        if n_L == 0:
+            n_L = po.truncation_rank(lam, eps, len(lam))
+        self._n_L = n_L
+        return n_L, (0 if mode == "gram" else int((lam > 1e-15 * lam[0]).sum()))
+
+    def pass2_gram(self, A, keep):
+        Y = A @ self._W[:, :keep]
+        return Y, torch.from_numpy(Y.T @ Y)
+
+    def pass2_finish(self, G2, eps, n_L):
+        lam, W2 = np.linalg.eigh(G2.numpy())
+        lam, W2 = np.maximum(lam[::-1], 0.), W2[:, ::-1]
+        self._sig2, self._W2 = np.sqrt(lam), W2
+        if n_L == 0:
+            n_L = po.truncation_rank(lam, eps, len(lam))
+        self._sig = np.concatenate([self._sig2, np.zeros(len(self._sig) - len(lam))])
+        return n_L
+
+    def basis(self, A, Y, n_L):
+        if Y is not None:
+            return Y @ self._W2[:, :n_L] / self._sig2[:n_L]
+        return A @ self._W[:, :n_L] / self._sig[:n_L]
+
+    def sigma(self):
+        return self._sig
+
+    def project(self, V, U):
+        return torch.from_numpy(np.ascontiguousarray((V.T @ U).T))

@@ -1,0 +1,299 @@
+"""GPU parity tests: the CUDA path (through the C-ABI / the reference-named shims) against the
+oracle and the golden vectors of the unmodified reference.  Tolerances are BASELINE.json's:
+sigma to 1e-10 * sigma_max, subspace angle <= 1e-8, identical rank, ensemble 1e-6 relative."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, golden_workload
+from oracle import pod_oracle as po, compare as cmp, ensemble as ens
+from pod_uqnn_b200 import _lib, workloads as wl
+from pod_uqnn_b200.acceleration import snapshots_device, loop_u, loop_u_t
+from pod_uqnn_b200.pod import perform_pod, perform_fast_pod, pod_device
+from pod_uqnn_b200.varneuralnetwork import VarNeuralNetwork, ensemble_predict_device
+
+pytestmark = pytest.mark.gpu
+FIELD = {"shekel": po.u_shekel, "ackley": po.u_ackley, "burgers": po.u_burgers}
+TOL_FIELD = 1e-13          # relative to max|U|: exp / cos are <= 2 ulp on both sides
+
+
+def regen(g, field):
+    x_mesh, mu, n_t, t_min, t_max = golden_workload(g)
+    return po.create_snapshots(x_mesh, 1, n_t, FIELD[field], mu, t_min, t_max)
+
+
+# ------------------------------------------------------------------ snapshots
+@pytest.mark.parametrize("field", ["shekel", "ackley", "burgers"])
+def test_snapshot_kernels_match_reference(ctx, field):
+    g = load_golden(f"snap_{field}")
+    x_mesh, mu, n_t, t_min, t_max = golden_workload(g)
+    Ud, X_v, _ = snapshots_device(ctx, field, x_mesh[:, 1:].T, mu, n_t, t_min, t_max)
+    assert np.array_equal(X_v, g["X_v"])
+    assert cmp.rel_err(Ud.download(), g["U"]) <= TOL_FIELD
+
+
+def test_loop_u_reference_signature(ctx):
+    g = load_golden("snap_ackley")
+    x_mesh, mu, *_ = golden_workload(g)
+    n_h, n_s = x_mesh.shape[0], mu.shape[0]
+    X_v, U, U_nn = np.zeros((n_s, 3)), np.zeros((n_h, n_s)), np.zeros((n_h, n_s))
+    out = loop_u("ackley", n_h, X_v, U, U_nn, x_mesh[:, 1:].T, mu, ctx=ctx)
+    assert out[0] is X_v and out[1] is U and out[2] is U and out[3] is U_nn    # fills the caller's arrays
+    assert cmp.rel_err(U, g["U"]) <= TOL_FIELD and np.array_equal(U_nn, U)
+    with pytest.raises(NotImplementedError):
+        loop_u("ackley", n_h, X_v, U, U_nn, x_mesh[:, 1:].T, mu, u_noise=0.1, ctx=ctx)
+    with pytest.raises(NotImplementedError):
+        loop_u(lambda X, t, m: X, n_h, X_v, U, U_nn, x_mesh[:, 1:].T, mu, ctx=ctx)
+
+
+def test_loop_u_t_reference_signature(ctx):
+    g = load_golden("snap_burgers")
+    x_mesh, mu, n_t, t_min, t_max = golden_workload(g)
+    n_h, n_s = x_mesh.shape[0], mu.shape[0]
+    X_v, U = np.zeros((n_s * n_t, 2)), np.zeros((n_h, n_s * n_t))
+    U_nn, Us = np.zeros_like(U), np.zeros((n_h, n_t, n_s))
+    loop_u_t("burgers", n_t, 1, n_h, n_h, X_v, U, U_nn, Us, x_mesh[:, 1:].T, mu, t_min, t_max, ctx=ctx)
+    assert np.array_equal(X_v, g["X_v"])
+    assert cmp.rel_err(U, g["U"]) <= TOL_FIELD
+    assert cmp.rel_err(Us, g["U_struct"]) <= TOL_FIELD
+    assert U[0].max() == 0. and np.isfinite(U).all()       # x = 0 row; exp overflow -> inf -> 0 handled
+
+
+def test_snapshot_row_sharding(ctx):
+    w = wl.ackley(20, 16, 40)
+    X = w["x_mesh"][:, 1:].T
+    full, _, _ = snapshots_device(ctx, "ackley", X, w["mu"])
+    part, _, _ = snapshots_device(ctx, "ackley", X, w["mu"], row0=100, n_rows=57)
+    assert np.array_equal(part.download(), full.download()[100:157])
+
+
+# ------------------------------------------------------------------ products
+@pytest.mark.parametrize("rows,ka,kb,sym", [(1000, 200, 200, True), (5000, 1000, 1000, True), (777, 71, 71, True),
+                                            (3001, 14, 300, False), (4096, 71, 333, False), (40, 129, 129, True),
+                                            (9000, 33, 1001, False), (1, 5, 5, True), (100000, 256, 256, True)])
+def test_gemm_tn(ctx, rows, ka, kb, sym):
+    rng = np.random.default_rng(rows + ka)
+    A = rng.standard_normal((rows, ka))
+    B = A if sym else rng.standard_normal((rows, kb))
+    L, Ad = _lib.lib(), ctx.to_device(A)
+    Cd = ctx.alloc(ka, kb)
+    if sym:
+        ctx.check(L.pb_gram(ctx.h, Ad.ptr, rows, ka, Ad.ld, Cd.ptr))
+    else:
+        Bd = ctx.to_device(B)
+        ctx.check(L.pb_gemm_tn(ctx.h, Ad.ptr, Ad.ld, ka, Bd.ptr, Bd.ld, kb, rows, Cd.ptr))
+    Cg, Cr = Cd.download(), A.T @ B
+    assert cmp.rel_err(Cg, Cr) < 1e-13
+    if sym:
+        assert np.array_equal(Cg, Cg.T)                    # exactly symmetric
+        Cd2 = ctx.alloc(ka, kb)
+        ctx.check(L.pb_gram(ctx.h, Ad.ptr, rows, ka, Ad.ld, Cd2.ptr))
+        assert np.array_equal(Cd2.download(), Cg)          # deterministic (fixed-order split-K)
+
+
+@pytest.mark.parametrize("rows,m,k", [(1000, 200, 14), (5000, 1000, 71), (777, 333, 333), (130, 14, 1000),
+                                      (300, 71, 2), (999, 15, 33), (1, 3, 1)])
+def test_gemm_nn(ctx, rows, m, k):
+    rng = np.random.default_rng(rows + m + k)
+    A, B = rng.standard_normal((rows, m)), rng.standard_normal((m, k))
+    Ad, Bd, Yd = ctx.to_device(A), ctx.to_device(B), ctx.alloc(rows, k)
+    ctx.check(_lib.lib().pb_gemm_nn(ctx.h, Ad.ptr, Ad.ld, rows, m, Bd.ptr, Bd.ld, k, Yd.ptr, Yd.ld))
+    assert cmp.rel_err(Yd.download(), A @ B) < 1e-13
+
+
+# ------------------------------------------------------------------ POD
+POD_CASES = [("shekel_c1", "shekel"), ("shekel_tall", "shekel"), ("ackley_64", "ackley"), ("burgers_1step", "burgers")]
+
+
+@pytest.mark.parametrize("name,field", POD_CASES)
+@pytest.mark.parametrize("mode", ["gram", "gram2", "accurate"])
+def test_perform_pod_matches_reference(ctx, name, field, mode):
+    g = load_golden(f"pod_{name}")
+    _, U, _, _ = regen(g, field)
+    V, sig = perform_pod(U, float(g["eps"]), 0, False, mode=mode, ctx=ctx, return_sigma=True)
+    n_L = g["V"].shape[1]
+    assert V.shape == g["V"].shape, "truncation rank differs from the reference"
+    assert V.flags["C_CONTIGUOUS"] and V.dtype == np.float64
+    assert cmp.sigma_error(sig[:n_L], g["sigma"][:n_L]) <= cmp.TOL_SIGMA_REL
+    angle = cmp.largest_principal_angle(V, g["V"])
+    if mode == "accurate":
+        assert angle <= cmp.TOL_ANGLE
+        assert cmp.sigma_error(sig, g["sigma"]) <= cmp.TOL_SIGMA_REL       # every singular value
+        v = po.project_to_v(V, U)
+        Va, s = cmp.align_signs(V, g["V"])
+        assert cmp.rel_err(v * s, g["v"]) <= 1e-8                          # coefficients up to sign
+    elif mode == "gram2" and field == "ackley":
+        assert angle <= cmp.TOL_ANGLE
+    else:
+        # one Gram pass: bounded by eps_mach * lambda_1 / gap, reported not required
+        assert angle <= 1e-4
+
+
+def test_perform_pod_fixed_rank_and_full_rank(ctx):
+    rng = np.random.default_rng(11)
+    U = rng.standard_normal((300, 24)) @ np.diag(2. ** -np.arange(24)) @ rng.standard_normal((24, 40))
+    V = perform_pod(U, 0., 7, False, ctx=ctx)                   # n_L given: used verbatim (pod.py:25)
+    assert V.shape == (300, 7)
+    assert cmp.largest_principal_angle(V, po.perform_pod(U, 0., 7)) <= cmp.TOL_ANGLE
+    Uf = rng.standard_normal((64, 12))
+    Vf = perform_pod(Uf, 0., 0, False, ctx=ctx)                 # eps = 0 (the default): every mode
+    assert Vf.shape == (64, 12)
+    assert np.abs(Vf.T @ Vf - np.eye(12)).max() < 1e-10
+    with pytest.raises(ValueError):
+        perform_pod(U, 0., 39, False, mode="gram", ctx=ctx)     # more modes than the numerical rank
+    with pytest.raises(KeyError):
+        perform_pod(U, 1e-4, 0, False, mode="tsqr", ctx=ctx)
+
+
+def test_pod_ragged_shapes(ctx):
+    rng = np.random.default_rng(12)
+    for (n_h, n_st) in ((257, 33), (33, 257), (100, 1), (1, 9), (129, 129)):
+        U = rng.standard_normal((n_h, 3)) @ rng.standard_normal((3, n_st)) if min(n_h, n_st) > 3 \
+            else rng.standard_normal((n_h, n_st))
+        V, sig = perform_pod(U, 1e-6, 0, False, ctx=ctx, return_sigma=True)
+        Vr = po.perform_pod(U, 1e-6)
+        assert V.shape == Vr.shape, (n_h, n_st)
+        assert cmp.largest_principal_angle(V, Vr) <= cmp.TOL_ANGLE
+        D = np.linalg.svd(U, compute_uv=False)
+        assert cmp.sigma_error(sig[:V.shape[1]], D[:V.shape[1]]) <= cmp.TOL_SIGMA_REL
+
+
+@pytest.mark.parametrize("eps", ["0.0001", "1e-08"])
+def test_perform_fast_pod_matches_reference(ctx, eps):
+    g = load_golden(f"fastpod_burgers_{eps}")
+    _, _, U_struct, _ = regen(g, "burgers")
+    V, ranks = perform_fast_pod(U_struct, float(g["eps"]), float(g["eps"]), ctx=ctx, return_ranks=True)
+    assert np.array_equal(ranks, g["ranks"]), "per-sample ranks differ from the reference"
+    assert V.shape == g["V"].shape
+    assert cmp.largest_principal_angle(V, g["V"]) <= cmp.TOL_ANGLE
+
+
+def test_logical_shards_equal_unsharded(ctx):
+    """P row slabs processed one after the other on one device, partial Grams summed in rank
+    order (what the NCCL all-reduce does), replicated eigensolve, per-slab basis."""
+    g = load_golden("pod_ackley_64")
+    _, U, _, _ = regen(g, "ackley")
+    L = _lib.lib()
+    n_h, m = U.shape
+    bounds = [0, 1500, 1501, 3000, n_h]
+    slabs = [ctx.to_device(U[a:b]) for a, b in zip(bounds, bounds[1:])]
+    G = np.zeros((m, m))
+    for s in slabs:
+        Gd = ctx.alloc(m, m)
+        ctx.check(L.pb_gram(ctx.h, s.ptr, s.shape[0], m, s.ld, Gd.ptr))
+        G += Gd.download()
+    nl, keep = C.c_int(), C.c_int()
+    Gd = ctx.to_device(G)
+    ctx.check(L.pb_pod_from_gram(ctx.h, Gd.ptr, m, 1e-10, 0, 1, C.byref(nl), C.byref(keep)))
+    Ys, G2 = [], np.zeros((keep.value, keep.value))
+    for s in slabs:
+        Y, G2d = ctx.alloc(s.shape[0], keep.value), ctx.alloc(keep.value, keep.value)
+        ctx.check(L.pb_pod_pass2_gram(ctx.h, s.ptr, s.shape[0], s.ld, Y.ptr, G2d.ptr))
+        Ys.append(Y); G2 += G2d.download()
+    G2d = ctx.to_device(G2)
+    ctx.check(L.pb_pod_pass2_finish(ctx.h, G2d.ptr, 1e-10, 0, C.byref(nl)))
+    V = np.zeros((n_h, nl.value))
+    for (a, b), s, Y in zip(zip(bounds, bounds[1:]), slabs, Ys):
+        Vd = ctx.alloc(b - a, nl.value)
+        ctx.check(L.pb_pod_basis(ctx.h, s.ptr, b - a, s.ld, Y.ptr, Vd.ptr, Vd.ld))
+        V[a:b] = Vd.download()
+    assert V.shape == g["V"].shape
+    assert cmp.largest_principal_angle(V, g["V"]) <= cmp.TOL_ANGLE
+    V1 = perform_pod(U, 1e-10, 0, False, mode="gram2", ctx=ctx)
+    assert cmp.largest_principal_angle(V, V1) <= 1e-10
+
+
+# ------------------------------------------------------------------ projection / reconstruction
+def test_projection_reconstruction_pod_sig(ctx):
+    g = load_golden("pod_ackley_64")
+    _, U, _, _ = regen(g, "ackley")
+    L = _lib.lib()
+    V = g["V"]; n_h, n = U.shape; nl = V.shape[1]
+    Ud, Vd = ctx.to_device(U), ctx.to_device(V)
+    v = ctx.alloc(n, nl)
+    ctx.check(L.pb_project(ctx.h, Vd.ptr, Vd.ld, nl, Ud.ptr, Ud.ld, n_h, n, v.ptr))
+    assert cmp.rel_err(v.download(), g["v"]) <= 1e-12
+    Up, sig = ctx.alloc(n_h, n), ctx.alloc(n_h)
+    ctx.check(L.pb_reconstruct(ctx.h, Vd.ptr, Vd.ld, nl, v.ptr, n, n_h, Ud.ptr, Ud.ld, Up.ptr, Up.ld, sig.ptr))
+    assert cmp.rel_err(Up.download(), po.project_to_U(V, g["v"])) <= 1e-12
+    assert cmp.rel_err(sig.download(), g["pod_sig"]) <= 1e-9
+    sig2 = ctx.alloc(n_h)                                     # pod_sig alone: U_pod never materialised
+    ctx.check(L.pb_reconstruct(ctx.h, Vd.ptr, Vd.ld, nl, v.ptr, n, n_h, Ud.ptr, Ud.ld, None, 0, sig2.ptr))
+    assert np.array_equal(sig2.download(), sig.download())
+
+
+def test_struct_matrix_roundtrip(ctx):
+    rng = np.random.default_rng(4)
+    Us = rng.standard_normal((37, 9, 5))
+    L = _lib.lib()
+    Usd, Um = ctx.to_device(Us), ctx.alloc(37, 45)
+    ctx.check(L.pb_struct_to_matrix(ctx.h, Usd.ptr, 37, 9, 5, Um.ptr, Um.ld))
+    ref = np.concatenate([Us[:, :, k] for k in range(5)], axis=1)        # pod.py:58 slices
+    assert np.array_equal(Um.download(), ref)
+    back = ctx.alloc(37, 9, 5)
+    ctx.check(L.pb_matrix_to_struct(ctx.h, Um.ptr, Um.ld, 37, 9, 5, back.ptr))
+    assert np.array_equal(back.download(), Us)
+
+
+# ------------------------------------------------------------------ ensemble
+@pytest.mark.parametrize("layers,M,N,norm", [([1, 128, 128, 128, 64], 8, 1000, "meanstd"), ([3, 40, 40, 14], 5, 300, "center"),
+                                             ([11, 128, 128, 128, 71], 3, 257, "none"), ([2, 16, 5], 1, 100, "meanstd"),
+                                             ([1, 40, 40, 130], 2, 129, "meanstd")])
+def test_ensemble_predict_v(ctx, layers, M, N, norm):
+    members = [ens.init_weights(layers, 4000 + i, bias_scale=0.1) for i in range(M)]
+    X = np.random.default_rng(5).uniform(800, 1200, (N, layers[0]))
+    nb = ens.set_normalize_bounds(X, norm)
+    vm_r, vs_r = ens.predict_v(X, members, layers[-1], 0.01, norm, nb)
+    vm, vs = ensemble_predict_device(ctx, members, layers, X, 0.01, norm, nb)
+    assert cmp.rel_err(vm.download(), vm_r) <= cmp.TOL_ENSEMBLE_REL
+    assert cmp.rel_err(vs.download(), vs_r) <= cmp.TOL_ENSEMBLE_REL
+
+
+def test_var_neural_network_predict(ctx):
+    layers = [2, 32, 32, 6]
+    w = ens.init_weights(layers, 77, bias_scale=0.2)
+    X = np.random.default_rng(6).standard_normal((50, 2))
+    net = VarNeuralNetwork(layers, 0.01, 0.001, soft_0=0.3, norm="meanstd")
+    net.set_weights(w)
+    net.set_normalize_bounds(X)
+    mean, var = net.predict(X, ctx=ctx)
+    mean_r, var_r = ens.member_predict(X, w, 6, 0.3, "meanstd", (X.mean(0), X.std(0)))
+    assert cmp.rel_err(mean, mean_r) <= cmp.TOL_ENSEMBLE_REL
+    assert np.max(np.abs(var - var_r) / var_r) <= cmp.TOL_ENSEMBLE_REL     # own variance, no cancellation
+    with pytest.raises(ValueError):                                         # hidden width > 128 is not built
+        ensemble_predict_device(ctx, [ens.init_weights([1, 256, 2], 1)], [1, 256, 2], X[:, :1])
+
+
+def test_predict_U_closed_form(ctx):
+    rng = np.random.default_rng(8)
+    V = np.linalg.qr(rng.standard_normal((500, 9)))[0]
+    vm, vs = rng.standard_normal((33, 9)), rng.uniform(0.01, 0.1, (33, 9))
+    L = _lib.lib()
+    Vd, vmd, vsd = ctx.to_device(V), ctx.to_device(vm), ctx.to_device(vs)
+    Um, Us = ctx.alloc(500, 33), ctx.alloc(500, 33)
+    ctx.check(L.pb_predict_U(ctx.h, Vd.ptr, Vd.ld, 500, 9, vmd.ptr, vsd.ptr, 33, 0, 0, Um.ptr, Us.ptr, Um.ld))
+    Um_r, Us_r = ens.predict_U_moments(V, vm, vs)
+    assert cmp.rel_err(Um.download(), Um_r) <= 1e-12 and cmp.rel_err(Us.download(), Us_r) <= 1e-12
+    # and the reference's Monte-Carlo estimator converges to it (statistical parity)
+    U_mc, Us_mc = ens.predict_mc(V, vm, vs, 4000, np.random.default_rng(9))
+    assert np.abs(U_mc - Um_r).max() < 5 * Us_r.max() / np.sqrt(4000) * 1.5
+    assert cmp.rel_err(Us_mc, Us_r) < 0.15
+
+
+# ------------------------------------------------------------------ errors
+def test_error_behaviour(ctx):
+    L = _lib.lib()
+    w = wl.ackley(4, 4, 4)
+    X = w["x_mesh"][:, 1:].T
+    with pytest.raises(NotImplementedError):
+        Xd, mud, Ud = ctx.to_device(X), ctx.to_device(w["mu"]), ctx.alloc(16, 4)
+        ctx.check(L.pb_snapshots(ctx.h, 99, 2, 16, Xd.ptr, 4, 3, mud.ptr, 0, None, 0, 16, Ud.ptr, 4))
+    with pytest.raises(ValueError):
+        snapshots_device(ctx, "ackley", X, w["mu"], n_t=5, t_min=0., t_max=1.)     # steady field with n_t
+    with pytest.raises(ValueError):
+        snapshots_device(ctx, "shekel", X, w["mu"])                                # wrong dim / n_mu
+    with pytest.raises(ValueError):
+        pod_device(ctx, ctx.to_device(np.ones((4, 4))), eps=1.5)
+    with pytest.raises(ValueError):
+        pod_device(ctx, ctx.to_device(np.zeros((8, 4))), eps=1e-4)                  # zero matrix: no pivot

@@ -1,0 +1,107 @@
+"""GPU: BASELINE.json's full sizes.  C2 (Ackley 160 000 x 1000) against the golden vectors of the
+reference run (spectrum, rank, projection, sampled basis rows) and against the oracle SVD on the
+host; size-independent properties (orthonormality, projection round trip, closed-form DCT
+spectrum) at sizes the oracle cannot hold."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import pod_oracle as po, compare as cmp
+from pod_uqnn_b200 import _lib, workloads as wl
+from pod_uqnn_b200.acceleration import snapshots_device
+from pod_uqnn_b200.pod import pod_device
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c2(ctx):
+    w = wl.ackley(400, 400, 1000)
+    Ud, _, _ = snapshots_device(ctx, "ackley", w["x_mesh"][:, 1:].T, w["mu"])
+    return w, Ud
+
+
+def test_c2_snapshots_match_reference_rows(ctx, c2):
+    g = load_golden("pod_ackley_c2_full")
+    _, Ud = c2
+    U = Ud.download()
+    assert cmp.rel_err(U[g["rows"]][:, ::7], g["U_rows"]) <= 1e-13
+
+
+@pytest.mark.parametrize("mode", ["gram", "gram2"])
+def test_c2_pod_matches_reference(ctx, c2, mode):
+    g = load_golden("pod_ackley_c2_full")
+    _, Ud = c2
+    L = _lib.lib()
+    Vd, sig = pod_device(ctx, Ud, 1e-10, 0, mode)
+    n_L = int(g["n_L"])
+    assert Vd.shape == (160000, n_L), "truncation rank differs from the reference (14)"
+    # one Gram pass resolves sigma_i only to ~ sqrt(n_h) eps sigma_1^2 / sigma_i (sigma_14 / sigma_1 = 1.8e-5):
+    # the tolerance of BASELINE.json is claimed for the two-pass mode, the one-pass error is bounded here
+    assert cmp.sigma_error(sig[:n_L], g["sigma"][:n_L]) <= (cmp.TOL_SIGMA_REL if mode == "gram2" else 5e-9)
+    V = Vd.download()
+    assert np.abs(V.T @ V - np.eye(n_L)).max() <= 1e-7
+    v = ctx.alloc(1000, n_L)
+    ctx.check(L.pb_project(ctx.h, Vd.ptr, Vd.ld, n_L, Ud.ptr, Ud.ld, 160000, 1000, v.ptr))
+    Vrows, s = cmp.align_signs(V[g["rows"]], g["V_rows"])
+    tol = 1e-8 if mode == "gram2" else 1e-5
+    assert np.abs(Vrows - g["V_rows"]).max() <= tol * np.abs(g["V_rows"]).max() * 10
+    assert cmp.rel_err(v.download() * s, g["v"]) <= tol
+
+
+def test_c2_subspace_angle_against_oracle_svd(ctx, c2):
+    """The headline parity claim: gram2 mode vs LAPACK on the same matrix, angle <= 1e-8."""
+    _, Ud = c2
+    U = Ud.download()
+    Vr = po.perform_pod(U, 1e-10)
+    Vd, _ = pod_device(ctx, Ud, 1e-10, 0, "gram2")
+    assert Vd.shape == Vr.shape
+    assert cmp.largest_principal_angle(Vd.download(), Vr) <= cmp.TOL_ANGLE
+
+
+def test_c2_round_trip_and_pod_sig(ctx, c2):
+    _, Ud = c2
+    L = _lib.lib()
+    Vd, _ = pod_device(ctx, Ud, 1e-10, 0, "gram2")
+    n_L = Vd.shape[1]
+    v = ctx.alloc(1000, n_L)
+    ctx.check(L.pb_project(ctx.h, Vd.ptr, Vd.ld, n_L, Ud.ptr, Ud.ld, 160000, 1000, v.ptr))
+    Up, sig = ctx.alloc(160000, 1000), ctx.alloc(160000)
+    ctx.check(L.pb_reconstruct(ctx.h, Vd.ptr, Vd.ld, n_L, v.ptr, 1000, 160000, Ud.ptr, Ud.ld, Up.ptr, Up.ld, sig.ptr))
+    v2 = ctx.alloc(1000, n_L)
+    ctx.check(L.pb_project(ctx.h, Vd.ptr, Vd.ld, n_L, Up.ptr, Up.ld, 160000, 1000, v2.ptr))
+    assert cmp.rel_err(v2.download(), v.download()) <= 1e-9       # project(reconstruct(v)) == v
+    s = sig.download()
+    assert (s >= 0).all() and 1e-6 < s.mean() < 1e-4              # "Mean pod sig" of the reference run: 1.87e-5
+
+
+@pytest.mark.parametrize("n_h,n_s", [(1 << 20, 1024), (200000, 4096)])
+def test_dct_known_answer_at_scale(ctx, n_h, n_s):
+    """U = sum s_k phi_k psi_k^T built in HBM: singular values are exactly s_k = 2^(-k/4), the rank
+    follows in closed form; the host cannot hold these matrices next to an SVD."""
+    L = _lib.lib()
+    Ud = ctx.alloc(n_h, n_s)
+    ctx.check(L.pb_dct_lowrank(ctx.h, n_h, n_s, 256, 0.25, 0, n_h, Ud.ptr, Ud.ld))
+    s = 2. ** (-0.25 * np.arange(256))
+    for mode in ("gram", "gram2"):
+        Vd, sig = pod_device(ctx, Ud, 1e-10, 0, mode)
+        n_L = wl.dct_rank(s, 1e-10)
+        assert Vd.shape[1] == n_L
+        assert cmp.sigma_error(sig[:n_L], s[:n_L]) <= (cmp.TOL_SIGMA_REL if mode == "gram2" else 5e-9)
+    # basis == phi_k up to sign: check a row sample against the closed form
+    rows = np.arange(0, n_h, n_h // 997)
+    V = Vd.download()[rows]
+    k = np.arange(1, n_L + 1)[None, :]
+    phi = np.sqrt(2. / n_h) * np.cos(np.pi * (rows[:, None] + .5) * k / n_h)
+    Va, _ = cmp.align_signs(V, phi)
+    assert np.abs(Va - phi).max() <= 1e-8 * np.sqrt(2. / n_h) * 10
+
+
+def test_dct_generator_matches_host(ctx):
+    L = _lib.lib()
+    U, s, _ = wl.dct_lowrank_host(3000, 200, r=64)
+    Ud = ctx.alloc(1000, 200)
+    ctx.check(L.pb_dct_lowrank(ctx.h, 3000, 200, 64, 0.25, 1500, 1000, Ud.ptr, Ud.ld))
+    assert cmp.rel_err(Ud.download(), U[1500:2500]) <= 1e-12

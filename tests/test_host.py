@@ -1,0 +1,110 @@
+"""CPU: the C-ABI library loads and exports everything include/podb200.h declares, the
+product fails loudly without a GPU, and the host-side logic of the shims."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from pod_uqnn_b200 import _lib, fields, workloads as wl
+from oracle import pod_oracle as po, ensemble as ens
+
+
+def test_library_exports_every_header_symbol():
+    lib = _lib.lib()
+    hs = _lib.header_symbols()
+    assert len(hs) >= 40
+    for name in hs:
+        assert hasattr(lib, name), f"{name} declared in include/podb200.h but not exported"
+    assert set(hs) == set(_lib.SIGNATURES), set(hs) ^ set(_lib.SIGNATURES)
+
+
+def test_no_cpu_fallback_without_gpu():
+    h = ctypes.c_void_p()
+    rc = _lib.lib().pb_create(0, ctypes.byref(h))
+    if rc == 0:                                   # running on a GPU box
+        _lib.lib().pb_destroy(h)
+        pytest.skip("a CUDA device is present")
+    assert rc == _lib.PB_ERR_CUDA
+    assert b"no CPU fallback" in _lib.lib().pb_last_error(None)
+    with pytest.raises(_lib.PodB200Error):
+        _lib.Context(0)
+    from pod_uqnn_b200.pod import perform_pod
+    with pytest.raises(_lib.PodB200Error):
+        perform_pod(np.ones((8, 4)), 1e-4, verbose=False)
+
+
+def test_null_context_is_rejected():
+    L = _lib.lib()
+    assert L.pb_gram(None, None, 1, 1, 1, None) == _lib.PB_ERR_ARG
+    assert L.pb_pod(None, None, 1, 1, 1, 0., 0, 0, None) == _lib.PB_ERR_ARG
+    assert L.pb_snapshots(None, 1, 1, 1, None, 1, 2, None, 0, None, 0, 1, None, 1) == _lib.PB_ERR_ARG
+    assert L.pb_ensemble_predict(None, 1, 1, None, None, 0, None, None, 1., None, 1, None, None) == _lib.PB_ERR_ARG
+
+
+def test_field_registry():
+    assert fields.resolve("ackley") is fields.u_ackley
+    assert fields.resolve(fields.u_burgers).has_t
+
+    def u(X, t, mu):
+        return X
+    with pytest.raises(NotImplementedError):
+        fields.resolve(u)
+    u.pb_field = "shekel"
+    assert fields.resolve(u) is fields.u_shekel
+    with pytest.raises(NotImplementedError):
+        fields.u_shekel(None, 0, None)            # no host implementation
+
+
+def test_workloads_match_reference_mesh():
+    m = wl.create_linear_mesh(-5., 5., 7, -5., 5., 4)
+    assert np.array_equal(m, po.create_linear_mesh(-5., 5., 7, -5., 5., 4))
+    assert np.array_equal(wl.create_linear_mesh(0, 10, 9), po.create_linear_mesh(0, 10, 9))
+    w = wl.ackley(8, 6, 5)
+    assert w["x_mesh"].shape == (48, 3) and w["mu"].shape == (5, 3) and (np.abs(w["mu"]) <= 1).all()
+    U, s, phi = wl.dct_lowrank_host(64, 16, r=8)
+    assert np.allclose(np.linalg.svd(U, compute_uv=False)[:8], s, rtol=0, atol=1e-13)
+    assert wl.dct_rank(s, 1e-2) == po.truncation_rank(s ** 2, 1e-2, 8)
+
+
+def test_time_grid_matches_numba_linspace():
+    from pod_uqnn_b200.acceleration import time_grid
+    assert np.array_equal(time_grid(1., 5., 100), po.linspace_numba_parallel(1., 5., 100))
+    assert time_grid(1., 5., 100)[0] == 1. and time_grid(1., 5., 100)[-1] == 5.
+
+
+def test_pack_members_layout():
+    from pod_uqnn_b200.varneuralnetwork import pack_members, VarNeuralNetwork
+    layers = [2, 4, 3]
+    ms = [ens.init_weights(layers, s, .1) for s in (1, 2)]
+    flat = pack_members(ms)
+    per = 2 * 4 + 4 + 4 * 6 + 6
+    assert flat.shape == (2 * per,)
+    assert np.array_equal(flat[:8], ms[0][0].ravel()) and np.array_equal(flat[per + 8: per + 12], ms[1][1])
+    net = VarNeuralNetwork(layers, 0.01, 0.001, seed=3)
+    assert [w.shape for w in net.weights] == [(2, 4), (4,), (4, 6), (6,)]
+    with pytest.raises(ValueError):
+        net.set_weights(ms[0][:2])
+    with pytest.raises(NotImplementedError):
+        net.fit(None, None, 1, None)
+
+
+def test_podnnmodel_host_layout_helpers(tmp_path):
+    from pod_uqnn_b200.podnnmodel import PodnnModel
+    x_mesh = wl.create_linear_mesh(0, 1, 5)
+    m = PodnnModel(str(tmp_path), 2, x_mesh, 4)
+    rng = np.random.default_rng(0)
+    Us = rng.standard_normal((2, 5, 4, 3))
+    assert np.array_equal(m.destruct(Us), po.destruct(Us, 4))
+    assert np.array_equal(m.restruct(m.destruct(Us)), Us)
+    m0 = PodnnModel(str(tmp_path), 2, x_mesh, 0)
+    Us0 = rng.standard_normal((2, 5, 7))
+    assert np.array_equal(m0.destruct(Us0), po.destruct(Us0, 0))
+    assert np.array_equal(m0.restruct(m0.destruct(Us0)), Us0)
+    assert os.path.exists(os.path.join(str(tmp_path), "setup_data.pkl"))
+    n_v, xm, n_t = PodnnModel.load_setup_data(str(tmp_path))
+    assert n_v == 2 and n_t == 0 and np.array_equal(xm, x_mesh)
+    with pytest.raises(NotImplementedError):
+        m.train_model()
+    with pytest.raises(ValueError):
+        m.predict_v(np.zeros((3, 2)))
