@@ -16,6 +16,7 @@
 #include "tile_ops.cuh"
 #include <cooperative_groups.h>
 #include <cfloat>
+#include <cstdlib>
 #include <algorithm>
 namespace cg = cooperative_groups;
 
@@ -159,12 +160,12 @@ constexpr int SP = JP + 1;   // padded pitch of the 32 x 32 shared matrices
 // Two-sided cyclic Jacobi on S (JP x JP, symmetric, in shared memory), accumulating the
 // rotations in Q.  256 threads: thread (P, R) owns the 2 x 2 block rows(pair P) x cols(pair R).
 // Returns the number of rotations applied in the FIRST sweep (0 => the pair was converged).
-__device__ int inner_jacobi(double (*S)[SP], double (*Q)[SP], double* cs, double* sn, double tol) {
+__device__ int inner_jacobi(double (*S)[SP], double (*Q)[SP], double* cs, double* sn, double tol, int max_inner) {
     const int tid = threadIdx.x;
     for (int e = tid; e < JP * JP; e += blockDim.x) Q[e / JP][e % JP] = (e / JP == e % JP) ? 1. : 0.;
     __syncthreads();
     int first = 0;
-    for (int sweep = 0; sweep < 12; ++sweep) {
+    for (int sweep = 0; sweep < max_inner; ++sweep) {
         int rot_sweep = 0;
         for (int round = 0; round < JP - 1; ++round) {
             int did = 0;
@@ -206,14 +207,32 @@ __device__ int inner_jacobi(double (*S)[SP], double (*Q)[SP], double* cs, double
 }
 
 struct JacArgs {
-    double* At; int64_t ldm; int nb; int round; double tol; int* n_rot;
+    double* At; int64_t ldm; int nb; int round; double tol; int* n_rot; int max_inner;
 };
+
+constexpr int JCH = 256;        // vector elements staged per shared-memory chunk
+constexpr int JPX = JCH + 4;    // chunk pitch (== 4 mod 16: conflict-free DMMA fragment reads)
+
+// stage elements [c0, c0 + JCH) of the 32 pair vectors into Xs[32][JPX] (zero beyond ldm)
+__device__ __forceinline__ void stage_chunk(double* Xs, const double* At, int64_t ldm, int bp, int bq,
+                                            int64_t c0, int tid) {
+#pragma unroll
+    for (int q = 0; q < (JP * JCH / 2) / 256; ++q) {
+        const int idx = tid + q * 256;
+        const int v = idx / (JCH / 2), c = (idx % (JCH / 2)) * 2;
+        const double* row = At + (int64_t)((v < JB ? bp : bq) * JB + (v % JB)) * ldm;
+        const int64_t e = c0 + c;
+        const int bytes = e < ldm ? 16 : 0;
+        pbt::cp_async16(Xs + v * JPX + c, bytes ? row + e : At, bytes);
+    }
+}
 
 __global__ void __launch_bounds__(256) jacobi_pair_kernel(JacArgs a) {
     __shared__ double S[JP][SP];
     __shared__ double Q[JP][SP];
     __shared__ double cs[JP / 2], sn[JP / 2];
-    extern __shared__ double red[];                    // (8 warps) x (JP*JP) partial Grams
+    extern __shared__ __align__(16) double dyn[];      // two chunk buffers; later the 8 partial Grams
+    double* Xs[2] = {dyn, dyn + JP * JPX};
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lk = lane & 3, lg = lane >> 2;
     int bp, bq; rr_pair(a.nb, a.round, blockIdx.x, bp, bq);
@@ -221,27 +240,37 @@ __global__ void __launch_bounds__(256) jacobi_pair_kernel(JacArgs a) {
     auto vrow = [&](int v) -> double* {
         return a.At + (int64_t)((v < JB ? bp : bq) * JB + (v % JB)) * a.ldm;
     };
-    const int n4 = (int)(a.ldm / 4);
+    const int nch = (int)((a.ldm + JCH - 1) / JCH);
 
-    // ---- phase 1: S = X X^T over the m-long vectors (DMMA; fragment of row block t serves as A and B)
+    // ---- phase 1: S = X X^T over the m-long vectors (DMMA; the fragment of row block t is A and B)
     {
         double acc[4][4][2];
 #pragma unroll
         for (int t = 0; t < 4; ++t)
 #pragma unroll
             for (int u = 0; u < 4; ++u) { acc[t][u][0] = 0.; acc[t][u][1] = 0.; }
-        const double* r0 = vrow(lg) + lk;
-        const double* r1 = vrow(8 + lg) + lk;
-        const double* r2 = vrow(16 + lg) + lk;
-        const double* r3 = vrow(24 + lg) + lk;
-        for (int k4 = warp; k4 < n4; k4 += 8) {
-            double f[4];
-            f[0] = r0[k4 * 4]; f[1] = r1[k4 * 4]; f[2] = r2[k4 * 4]; f[3] = r3[k4 * 4];
+        stage_chunk(Xs[0], a.At, a.ldm, bp, bq, 0, tid);
+        pbt::cp_async_commit();
+        for (int c = 0; c < nch; ++c) {
+            if (c + 1 < nch) stage_chunk(Xs[(c + 1) & 1], a.At, a.ldm, bp, bq, (int64_t)(c + 1) * JCH, tid);
+            pbt::cp_async_commit();
+            pbt::cp_async_wait<1>();
+            __syncthreads();
+            const double* x = Xs[c & 1] + lg * JPX + lk;
+#pragma unroll 2
+            for (int k4 = warp; k4 < JCH / 4; k4 += 8) {
+                double f[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
+                for (int t = 0; t < 4; ++t) f[t] = x[t * 8 * JPX + k4 * 4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) dmma884(acc[t][u][0], acc[t][u][1], f[t], f[u]);
+                for (int t = 0; t < 4; ++t)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) dmma884(acc[t][u][0], acc[t][u][1], f[t], f[u]);
+            }
+            __syncthreads();
         }
+        pbt::cp_async_wait<0>();
+        double* red = dyn;                                  // 8 x (JP*JP) doubles, fits the first buffer
         double* my = red + warp * (JP * JP);
 #pragma unroll
         for (int t = 0; t < 4; ++t)
@@ -267,11 +296,11 @@ __global__ void __launch_bounds__(256) jacobi_pair_kernel(JacArgs a) {
     }
 
     // ---- phase 2: small eigenproblem
-    const int first = inner_jacobi(S, Q, cs, sn, a.tol);
+    const int first = inner_jacobi(S, Q, cs, sn, a.tol, a.max_inner);
     if (first == 0) return;                       // uniform: nothing to rotate
     if (tid == 0) atomicAdd(a.n_rot, first);
 
-    // ---- phase 3: X' = Q^T X, 8 elements of every vector per warp step (in place)
+    // ---- phase 3: X' = Q^T X, chunk by chunk through shared memory, written back in place
     {
         // A fragments of Q^T: A[row = j][k = i] = Q[i][j]
         double qa[4][8];
@@ -279,29 +308,38 @@ __global__ void __launch_bounds__(256) jacobi_pair_kernel(JacArgs a) {
         for (int t = 0; t < 4; ++t)
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) qa[t][ks] = Q[ks * 4 + lk][t * 8 + lg];
-        const int n8 = (int)(a.ldm / 8);
-        const double* src[8];
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) src[ks] = vrow(ks * 4 + lk) + lg;
         double* dst[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) dst[t] = vrow(t * 8 + lg) + 2 * lk;
-        for (int e8 = warp; e8 < n8; e8 += 8) {
-            double b[8];
+        __syncthreads();
+        stage_chunk(Xs[0], a.At, a.ldm, bp, bq, 0, tid);
+        pbt::cp_async_commit();
+        for (int c = 0; c < nch; ++c) {
+            if (c + 1 < nch) stage_chunk(Xs[(c + 1) & 1], a.At, a.ldm, bp, bq, (int64_t)(c + 1) * JCH, tid);
+            pbt::cp_async_commit();
+            pbt::cp_async_wait<1>();
+            __syncthreads();
+            const double* x = Xs[c & 1] + lk * JPX + lg;
+            for (int e8 = warp; e8 < JCH / 8; e8 += 8) {
+                const int64_t e = (int64_t)c * JCH + e8 * 8;
+                if (e >= a.ldm) break;
+                double b[8];
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) b[ks] = src[ks][e8 * 8];
-            double d[4][2];
+                for (int ks = 0; ks < 8; ++ks) b[ks] = x[ks * 4 * JPX + e8 * 8];
+                double d[4][2];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) { d[t][0] = 0.; d[t][1] = 0.; }
+                for (int t = 0; t < 4; ++t) { d[t][0] = 0.; d[t][1] = 0.; }
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
+                for (int ks = 0; ks < 8; ++ks)
 #pragma unroll
-                for (int t = 0; t < 4; ++t) dmma884(d[t][0], d[t][1], qa[t][ks], b[ks]);
-            __syncwarp();                           // all lanes have read this column group
+                    for (int t = 0; t < 4; ++t) dmma884(d[t][0], d[t][1], qa[t][ks], b[ks]);
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
-                *reinterpret_cast<double2*>(dst[t] + e8 * 8) = make_double2(d[t][0], d[t][1]);
+                for (int t = 0; t < 4; ++t)
+                    *reinterpret_cast<double2*>(dst[t] + e) = make_double2(d[t][0], d[t][1]);
+            }
+            __syncthreads();
         }
+        pbt::cp_async_wait<0>();
     }
 }
 
@@ -401,6 +439,7 @@ __global__ void factor_to_right_kernel(const double* __restrict__ At, int64_t ld
 
 }  // namespace
 
+static int g_inner_sweeps = []{ const char* e = getenv("PB_JACOBI_INNER"); return e ? atoi(e) : 3; }();
 // device ints layout in ctx->d_int: [0] r (Cholesky), [1] n_rot, [2] n_L, [3] r_eff
 struct EigScratch { double* d; double* cand_val; int* cand_idx; double* nrm2; double* shift; };
 
@@ -450,14 +489,14 @@ int pbi_eig_psd(pb_ctx* ctx, const double* G, int64_t m, double tol_rel, double 
     // rotation threshold relative to the column norms (dgesvj uses sqrt(m) eps): below it the
     // pair Gram entry is rounding noise of the m-long dot product
     const double tol = std::max(4., sqrt((double)m)) * DBL_EPSILON;
-    size_t jac_smem = sizeof(double) * 8 * JP * JP;
+    size_t jac_smem = sizeof(double) * 2 * JP * JPX;
     PB_CUDA(ctx, cudaFuncSetAttribute(jacobi_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jac_smem));
     int sweeps = 0; bool converged = false;
     for (; sweeps < max_sweeps && !converged; ++sweeps) {
         PB_CUDA(ctx, cudaMemsetAsync(ctx->d_int + 1, 0, sizeof(int), ctx->stream));
         const int rounds = nb > 2 ? nb - 1 : 1;
         for (int round = 0; round < rounds; ++round) {
-            JacArgs ja{At, ldm, nb, round, tol, ctx->d_int + 1};
+            JacArgs ja{At, ldm, nb, round, tol, ctx->d_int + 1, g_inner_sweeps};
             jacobi_pair_kernel<<<nb / 2, 256, jac_smem, ctx->stream>>>(ja);
             PB_LAUNCH_CHECK(ctx);
         }

@@ -378,6 +378,11 @@ int pbi_gemm_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const dou
         PB_CUDA(ctx, cudaMemset2DAsync(C, ldc * sizeof(double), 0, kb * sizeof(double), ka, ctx->stream));
         return PB_OK;
     }
+    if (ka <= 32 && kb <= 32) {      // skinny x skinny (second-pass Gram of the rotated block): HBM bound
+        PB_TRY((launch_tn<32, 32, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0)));
+        if (sym) { symmetrize_kernel<<<(unsigned)((ka * kb + 255) / 256), 256, 0, ctx->stream>>>(C, (int)ka, ldc); PB_LAUNCH_CHECK(ctx); }
+        return PB_OK;
+    }
     if (sym || ka > 32) return launch_tn<128, 128, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, sym);
     return launch_tn<32, 128, 1, 8>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);
 }
