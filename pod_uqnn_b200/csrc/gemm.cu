@@ -296,6 +296,10 @@ int choose_splits(int tiles, int64_t rows, int sms) {
     return best;
 }
 
+}  // namespace
+int pbi_gram_tma(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int64_t rows, int splits,
+                 int64_t rows_per_split, double* ws, int64_t split_stride, bool time_it);
+namespace {
 bool g_time_tn = false;   // set per call by pbi_gemm_tn (contexts are single-threaded)
 
 template <int BM, int BN, int WARPS_M, int WARPS_N>
@@ -317,6 +321,11 @@ int launch_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const doubl
     const bool al = aligned16(A, lda) && aligned16(B, ldb);
     size_t smem = (size_t)STAGES * BK * ((BM + 4) + (BN + 4)) * sizeof(double);
     dim3 grid(tiles, splits);
+    if (sym && BM == 128 && BN == 128) {     // TMA + mbarrier pipeline when the layout allows it
+        int rc = pbi_gram_tma(ctx, A, lda, ka, rows, splits, rps, ctx->ws, split_stride, g_time_tn);
+        if (rc < 0) return rc;
+        if (rc == PB_OK) goto reduce;
+    }
     if (g_time_tn) cudaEventRecord(ctx->evk0, ctx->stream);
     if (al) {
         auto kern = gemm_tn_kernel<BM, BN, WARPS_M, WARPS_N, STAGES, true>;
@@ -331,6 +340,7 @@ int launch_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const doubl
     }
     PB_LAUNCH_CHECK(ctx);
     if (g_time_tn) { cudaEventRecord(ctx->evk1, ctx->stream); ctx->tn_timing_pending = true; }
+reduce:
     if (!direct) {
         int64_t n = (int64_t)ka * kb;
         reduce_splits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
@@ -384,6 +394,7 @@ int pbi_gemm_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const dou
         return PB_OK;
     }
     if (sym || ka > 32) return launch_tn<128, 128, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, sym);
+    if (ka <= 16) return launch_tn<16, 128, 1, 8>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);   // n_L <= 16: HBM bound
     return launch_tn<32, 128, 1, 8>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);
 }
 
@@ -394,13 +405,14 @@ int pbi_gemm_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t
                                                (long long)rows, (long long)m, (long long)k);
     double* part = nullptr;
     const bool wide = k > 32;
-    const int bn = wide ? 128 : 32;
+    const int bn = wide ? 128 : (k <= 16 ? 16 : 32);
     const int ntiles = (int)((k + bn - 1) / bn);
     if (Uref) {
         PB_TRY(pb_reserve(ctx, &ctx->ws, &ctx->ws_bytes, (size_t)ntiles * rows));
         part = ctx->ws;
     }
     if (wide) PB_TRY((launch_nn<128, 2, 4>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
+    else if (k <= 16) PB_TRY((launch_nn<16, 8, 1>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
     else      PB_TRY((launch_nn<32, 8, 1>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
     if (Uref) {
         sig_reduce_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(

@@ -1,0 +1,200 @@
+// Gram G = A^T A (SYRK-shaped, upper tiles) with a TMA + mbarrier warp-specialised pipeline.
+//
+// Same tiling and DMMA fragment mapping as gemm_tn_kernel<128,128> (gemm.cu), but the operand
+// panels are brought in by the Tensor Memory Accelerator (cp.async.bulk.tensor, SASS UTMALDG)
+// issued by one producer thread, and the 8 consumer warps never meet at a CTA-wide barrier:
+// a stage is handed over with "full" / "empty" mbarriers, so warps drift and the DMMA pipe stays
+// fed across stage boundaries (the cp.async version loses ~6 % of its issue samples at
+// __syncthreads and spends issue slots on 8 LDGSTS + address math per thread per stage).
+//
+// Shared-memory layout of a panel (128 columns x 16 rows of A): the tensor map views the row-major
+// matrix as (8 columns, rows, column groups) and the box (8, 16, 16) lands as [group][row][8 cols]
+// with the 64-byte swizzle, i.e. the 16-byte chunk index is XORed with (row >> 1) & 3.  A DMMA
+// k-step takes rows {r, r+1, r+4, r+5} of an 8-row block (any 4 rows may form a k-step: the sum
+// over k is order independent), which makes the 16 lanes of a half-warp hit 16 distinct 8-byte
+// banks -- no padding, no conflicts.
+#include "common.cuh"
+#include "tile_ops.cuh"
+#include <cuda.h>
+#include <cstdlib>
+
+namespace {
+using pbt::dmma884;
+
+constexpr int TBK = 16;                 // rows per stage
+constexpr int TSTAGES = 6;
+constexpr int PANEL_DOUBLES = 128 * TBK;            // 2048 doubles = 16 KB
+constexpr int STAGE_BYTES = 2 * PANEL_DOUBLES * 8;  // A panel + B panel
+constexpr int TMA_THREADS = 288;        // 8 consumer warps + 1 producer warp
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+                 :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ka, int64_t rows, int64_t rows_per_split,
+                double* __restrict__ out, int64_t ldo, int64_t split_stride, int tiles_n) {
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    // the swizzle is a function of the absolute shared address: align the panels to 1 KB
+    unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    double* panels = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)TSTAGES * STAGE_BYTES);
+    uint64_t* empty = full + TSTAGES;
+
+    int ti = 0, rem = blockIdx.x;            // linear id -> (ti, tj >= ti)
+    while (rem >= tiles_n - ti) { rem -= tiles_n - ti; ++ti; }
+    const int tj = ti + rem;
+    const bool diag = (ti == tj);
+    const int split = blockIdx.y;
+    const int64_t r_begin = (int64_t)split * rows_per_split;
+    const int64_t r_end = min(rows, r_begin + rows_per_split);
+    const int nk = r_end > r_begin ? (int)((r_end - r_begin + TBK - 1) / TBK) : 0;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < TSTAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 8) {
+        // ---------------- producer: one thread issues the TMA loads
+        if (lane == 0) {
+            for (int k = 0; k < nk; ++k) {
+                const int s = k % TSTAGES;
+                const uint32_t ph = (k / TSTAGES) & 1;
+                mbar_wait(empty + s, ph ^ 1);
+                mbar_expect_tx(full + s, diag ? STAGE_BYTES / 2 : STAGE_BYTES);
+                double* dst = panels + (size_t)s * 2 * PANEL_DOUBLES;
+                const int r0 = (int)(r_begin + (int64_t)k * TBK);
+                tma_load_3d(dst, &tmap, full + s, 0, r0, ti * 16);
+                if (!diag) tma_load_3d(dst + PANEL_DOUBLES, &tmap, full + s, 0, r0, tj * 16);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers: 8 warps as 2 x 4, warp tile 64 x 32
+    const int wm = warp >> 2, wn = warp & 3;
+    const int lk = lane & 3, lg = lane >> 2;
+    double acc[8][4][2];
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { acc[t][u][0] = 0.; acc[t][u][1] = 0.; }
+    // offset (in doubles, inside a [16 rows][8 cols] group block) of this lane's element for k-step kk
+    int koff[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        const int k = (kk >> 1) * 8 + (kk & 1) * 2 + (lk & 1) + (lk >> 1) * 4;
+        koff[kk] = k * 8 + ((((lg >> 1) ^ ((k >> 1) & 3))) << 1) + (lg & 1);
+    }
+    for (int k = 0; k < nk; ++k) {
+        const int s = k % TSTAGES;
+        const uint32_t ph = (k / TSTAGES) & 1;
+        mbar_wait(full + s, ph);
+        const double* As = panels + (size_t)s * 2 * PANEL_DOUBLES;
+        const double* Bs = diag ? As : As + PANEL_DOUBLES;
+        const double* ap = As + (wm * 8) * (TBK * 8);
+        const double* bp = Bs + (wn * 4) * (TBK * 8);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            double a[8], b[4];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) a[t] = ap[t * (TBK * 8) + koff[kk]];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) b[u] = bp[u * (TBK * 8) + koff[kk]];
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) dmma884(acc[t][u][0], acc[t][u][1], a[t], b[u]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+    }
+
+    const int64_t i0 = (int64_t)ti * 128, j0 = (int64_t)tj * 128;
+    double* o = out + (int64_t)split * split_stride;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int64_t i = i0 + wm * 64 + t * 8 + lg;
+        if (i >= ka) continue;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t j = j0 + wn * 32 + u * 8 + 2 * lk;
+            if (j < ka)     o[i * ldo + j]     = acc[t][u][0];
+            if (j + 1 < ka) o[i * ldo + j + 1] = acc[t][u][1];
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+}  // namespace
+
+// returns PB_OK when the TMA kernel was launched, 1 when the caller should use the cp.async kernel
+int pbi_gram_tma(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int64_t rows, int splits,
+                 int64_t rows_per_split, double* ws, int64_t split_stride, bool time_it) {
+    static const bool enabled = []{ const char* e = getenv("PB_GRAM_TMA"); return !e || atoi(e) != 0; }();
+    if (!enabled) return 1;
+    if ((lda % 2) || (ka % 8) || (reinterpret_cast<uintptr_t>(A) % 16) || rows >= (1ll << 31) || rows_per_split % TBK) return 1;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return 1;
+    CUtensorMap map;
+    const cuuint64_t gdim[3] = {8, (cuuint64_t)rows, (cuuint64_t)(ka / 8)};
+    const cuuint64_t gstr[2] = {(cuuint64_t)lda * 8, 64};        // bytes: rows, column groups
+    const cuuint32_t box[3] = {8, (cuuint32_t)TBK, 16};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(A), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return 1;
+    const int tiles_n = (int)((ka + 127) / 128);
+    const int tiles = tiles_n * (tiles_n + 1) / 2;
+    const size_t smem = (size_t)TSTAGES * STAGE_BYTES + 2 * TSTAGES * sizeof(uint64_t) + 1024;
+    PB_CUDA(ctx, cudaFuncSetAttribute(gram_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (time_it) cudaEventRecord(ctx->evk0, ctx->stream);
+    gram_tma_kernel<<<dim3(tiles, splits), TMA_THREADS, smem, ctx->stream>>>(map, (int)ka, rows, rows_per_split, ws, ka,
+                                                                            split_stride, tiles_n);
+    PB_LAUNCH_CHECK(ctx);
+    if (time_it) { cudaEventRecord(ctx->evk1, ctx->stream); ctx->tn_timing_pending = true; }
+    return PB_OK;
+}
