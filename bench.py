@@ -145,6 +145,10 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # rank 0 prints exactly ONE JSON line on stdout: keep library chatter (NCCL banner ...) off it
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     dist = None
     if world > 1:
         import torch
@@ -281,7 +285,8 @@ def run_gpu(args):
             "stage_ms": {k: statistics.mean(v) for k, v in parts.items()},
             "snapshot_kernel": {"ms": snap_ms, "gbs": U.nbytes / (snap_ms * 1e-3) / 1e9,
                                 "note": "Ackley field -> U slab in HBM (outside the timed step)"}}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
 

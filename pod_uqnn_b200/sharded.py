@@ -63,9 +63,17 @@ class CudaBackend:
         self.ctx, self.torch = ctx, torch
         self.dev = torch.device("cuda", ctx.device)
         self.L = _lib.lib()
+        self._cache = {}
 
     def _empty(self, *shape):
         return self.torch.empty(*shape, dtype=self.torch.float64, device=self.dev)
+
+    def _buf(self, name, *shape):
+        """Library-owned HBM buffer reused across steps (cudaMalloc / cudaFree synchronise the device)."""
+        b = self._cache.get(name)
+        if b is None or b.shape != tuple(shape):
+            b = self._cache[name] = self.ctx.alloc(*shape)
+        return b
 
     def reduce(self, t, group=None):
         # the library runs on its own stream: order it before NCCL, and NCCL before the next kernel
@@ -86,7 +94,7 @@ class CudaBackend:
         return nl.value, keep.value
 
     def pass2_gram(self, A, keep):
-        Y = self.ctx.alloc(A.shape[0], keep)
+        Y = self._buf("Y", A.shape[0], keep)
         G2 = self._empty(keep, keep)
         self.ctx.check(self.L.pb_pod_pass2_gram(self.ctx.h, A.ptr, A.shape[0], A.ld, Y.ptr, G2.data_ptr()))
         return Y, G2
@@ -97,7 +105,7 @@ class CudaBackend:
         return nl.value
 
     def basis(self, A, Y, n_L):
-        V = self.ctx.alloc(A.shape[0], n_L)
+        V = self._buf("V", A.shape[0], n_L)
         self.ctx.check(self.L.pb_pod_basis(self.ctx.h, A.ptr, A.shape[0], A.ld, Y.ptr if Y is not None else None,
                                            V.ptr, V.ld))
         return V
