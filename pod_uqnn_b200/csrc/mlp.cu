@@ -6,13 +6,18 @@
 // (mean over members of mu and of sigma^2 + mu^2) -- serial over members and layers in the
 // reference, with (N, n_L, M) intermediates.
 //
-// One persistent CTA owns a tile of 128 points.  Activations stay in shared memory
-// ([128][132] doubles, in place across layers); the layer weights stream through a 4-stage
-// cp.async ring in 16-row chunks (they are L2 resident: ~0.4 MB per member); the layer
-// product runs on DMMA with the accumulators in registers; bias + ReLU are applied in the
-// epilogue that writes the next layer's activations.  The head epilogue adds mu, mu^2 and
-// sigma^2 of the member into three running sums; after the last member the tile is
-// finalised to (mean, sqrt(var)).  No (N, n_L, M) intermediate ever reaches HBM.
+// One persistent CTA owns a tile of 128 points and walks all members and layers for it:
+//   * activations stay in shared memory ([128][132] doubles, rewritten in place per layer);
+//   * the weights are repacked once per call into the order the kernel consumes them
+//     (16-row K chunks padded to a 132-double pitch, each layer followed by its bias row), so a
+//     PRODUCER warp streams them with plain 1-D bulk async copies (cp.async.bulk, SASS UBLKCP)
+//     into a 4-slot ring guarded by full / empty mbarriers and runs ahead across layer and member
+//     boundaries -- the consumers never wait for a pipeline refill at a layer start;
+//   * 8 CONSUMER warps run the layer product on DMMA (warp tile 64 x 32, accumulators in
+//     registers), apply bias + ReLU in the epilogue and meet only at two named barriers per layer;
+//   * the head epilogue stores mu and sigma^2 of the member to a per-CTA scratch (L2 resident);
+//     after the last member the tile is reduced to (mean, sqrt(var)).  No (N, n_L, M)
+//     intermediate reaches HBM as such, and nothing is read-modify-written across members.
 #include "common.cuh"
 #include "tile_ops.cuh"
 
@@ -21,45 +26,144 @@ using namespace pbt;
 
 constexpr int MP = 128;            // points per tile
 constexpr int PACT = 132;          // activation pitch (== 4 mod 16: conflict-free A fragments)
-constexpr int PW = 132;            // weight-stage pitch
-constexpr int STAGES = 4;
+constexpr int PW = 132;            // packed weight pitch
+constexpr int RING = 5;
+constexpr int CHUNK_DOUBLES = BK * PW;             // 2112 doubles = 16 896 B per K chunk
+constexpr int BIAS_DOUBLES = PW;                   // 132 doubles = 1 056 B
 constexpr int MAX_LAYERS = 8;
 constexpr int MAX_WIDTH = 128;     // hidden widths (inputs of every layer) must fit the tile
+constexpr int MLP_THREADS = 384;   // 8 consumer warps + one producer warpgroup (registers are re-balanced)
 
 struct MlpArgs {
     int n_members, n_layers, n_L, norm_kind;
     int dims[MAX_LAYERS + 1];
-    int64_t w_off[MAX_LAYERS], b_off[MAX_LAYERS], member_stride;
-    const double* weights; const double* norm_a; const double* norm_b;
+    int64_t member_stride;          // doubles per member in the packed stream
+    const double* packed; const double* norm_a; const double* norm_b;
     double soft0;
     const double* X; int64_t N;
-    double* s1; double* s2; double* s3;     // running sums: mu, mu^2, sigma^2  (N x n_L each)
+    double* v_mean; double* v_sig;
+    double* scratch;                // per CTA: [member][MP][2*n_L] raw head outputs t = h W + b
     int64_t n_tiles;
 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 
 __device__ __forceinline__ double softplus(double x) {
     // np.logaddexp(0, x) == tf.math.softplus within 1 ulp
     return x > 0. ? x + log1p(exp(-x)) : log1p(exp(x));
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) ensemble_kernel(MlpArgs a) {
-    extern __shared__ __align__(16) double smem[];
-    double* act = smem;                          // [MP][PACT]
-    double* Ws = smem + MP * PACT;               // [STAGES][BK][PW]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;     // 2 x 4 warps, warp tile 64 x 32
-    const int lk = lane & 3, lg = lane >> 2;
-    const int n_d = a.dims[0], n_L = a.n_L;
+// Keras layout (per member: W0 (in x out) row-major, b0, W1, b1, ...) -> packed stream
+// (per member, per layer, per 128-wide output chunk: ceil(in/16) blocks [16][132], then bias [132])
+__global__ void pack_weights_kernel(const double* __restrict__ w, double* __restrict__ packed, int n_members,
+                                    int n_layers, MlpArgs a, int64_t src_member_stride) {
+    const int64_t total = (int64_t)n_members * a.member_stride;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int mem = (int)(idx / a.member_stride);
+        int64_t r = idx % a.member_stride;
+        int64_t src_off = 0;
+        double v = 0.;
+        for (int l = 0; l < n_layers; ++l) {
+            const int in = a.dims[l], out = a.dims[l + 1];
+            const int nk = (in + BK - 1) / BK, nc = (out + 127) / 128;
+            const int64_t per_chunk = (int64_t)nk * CHUNK_DOUBLES + BIAS_DOUBLES;
+            const int64_t layer_sz = per_chunk * nc;
+            if (r < layer_sz) {
+                const int c = (int)(r / per_chunk); const int64_t q = r % per_chunk;
+                const double* W = w + (int64_t)mem * src_member_stride + src_off;
+                if (q < (int64_t)nk * CHUNK_DOUBLES) {
+                    const int kc = (int)(q / CHUNK_DOUBLES); const int e = (int)(q % CHUNK_DOUBLES);
+                    const int row = kc * BK + e / PW, col = c * 128 + e % PW;
+                    if (row < in && (e % PW) < 128 && col < out) v = W[(int64_t)row * out + col];
+                } else {
+                    const int e = (int)(q - (int64_t)nk * CHUNK_DOUBLES); const int col = c * 128 + e;
+                    if (e < 128 && col < out) v = W[(int64_t)in * out + col];
+                }
+                break;
+            }
+            r -= layer_sz;
+            src_off += (int64_t)in * out + out;
+        }
+        packed[idx] = v;
+    }
+}
 
+__global__ void __launch_bounds__(MLP_THREADS, 1) ensemble_kernel(MlpArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    double* act = smem;                                   // [MP][PACT]
+    double* ring = smem + MP * PACT;                      // [RING][CHUNK_DOUBLES]
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + RING * CHUNK_DOUBLES);
+    uint64_t* empty = full + RING;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_L = a.n_L;
+    if (tid == 0) {
+        for (int s = 0; s < RING; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp >= 8) {
+        // ------------------------------------------------ producer: streams the packed weights
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+        if (warp == 8 && lane == 0) {
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x)
+                for (int mem = 0; mem < a.n_members; ++mem) {
+                    const double* src = a.packed + (int64_t)mem * a.member_stride;
+                    for (int l = 0; l < a.n_layers; ++l) {
+                        const int nk = (a.dims[l] + BK - 1) / BK, nc = (a.dims[l + 1] + 127) / 128;
+                        for (int c = 0; c < nc; ++c)
+                            for (int kc = 0; kc <= nk; ++kc, ++it) {       // kc == nk: the bias block
+                                const int s = it % RING; const uint32_t ph = (it / RING) & 1;
+                                const uint32_t bytes = (kc < nk ? CHUNK_DOUBLES : BIAS_DOUBLES) * 8;
+                                mbar_wait(empty + s, ph ^ 1);
+                                mbar_expect_tx(full + s, bytes);
+                                bulk_load(ring + (size_t)s * CHUNK_DOUBLES, src, bytes, full + s);
+                                src += bytes / 8;
+                            }
+                    }
+                }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------- consumers: 2 x 4 warps, warp tile 64 x 32
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
+    const int wm = warp >> 2, wn = warp & 3;
+    const int lk = lane & 3, lg = lane >> 2;
+    const int n_d = a.dims[0];
+    const int out_head = 2 * n_L;
+    double* scr = a.scratch + (size_t)blockIdx.x * a.n_members * MP * out_head;
+    uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const int64_t p0 = tile * MP;
         for (int mem = 0; mem < a.n_members; ++mem) {
-            const double* wbase = a.weights + (int64_t)mem * a.member_stride;
             // ---- input tile, normalised (varneuralnetwork.py:75-86), zero padded to 16 columns
-            __syncthreads();
             const int kin0 = (n_d + BK - 1) / BK * BK;
-            for (int e = tid; e < MP * kin0; e += NTHREADS) {
-                int p = e / kin0, c = e % kin0;
+            for (int e = tid; e < MP * kin0; e += 256) {
+                const int p = e / kin0, c = e % kin0;
                 double v = 0.;
                 if (c < n_d && p0 + p < a.N) {
                     v = a.X[(p0 + p) * n_d + c];
@@ -68,42 +172,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) ensemble_kernel(MlpArgs a) {
                 }
                 act[p * PACT + c] = v;
             }
-            __syncthreads();
+            consumer_sync();
             for (int l = 0; l < a.n_layers; ++l) {
                 const int in = a.dims[l], out = a.dims[l + 1];
                 const bool head = (l == a.n_layers - 1);
-                const double* W = wbase + a.w_off[l];
-                const double* bias = wbase + a.b_off[l];
-                const bool al = ((reinterpret_cast<uintptr_t>(W) % 16) == 0) && (out % 2 == 0);
-                const int nk = (in + BK - 1) / BK;
-                for (int c0 = 0; c0 < out; c0 += 128) {       // > 1 chunk only for a wide head
+                const int nk = (in + BK - 1) / BK, nc = (out + 127) / 128;
+                for (int c = 0; c < nc; ++c) {                 // > 1 chunk only for a wide head
                     double acc[8][4][2];
 #pragma unroll
                     for (int t = 0; t < 8; ++t)
 #pragma unroll
                         for (int u = 0; u < 4; ++u) { acc[t][u][0] = 0.; acc[t][u][1] = 0.; }
-#pragma unroll
-                    for (int s = 0; s < STAGES - 1; ++s) {
-                        if (s < nk) {
-                            if (al) load_tile<BK, 128, PW, true>(Ws + s * BK * PW, W, out, (int64_t)s * BK, in, c0, out, tid);
-                            else    load_tile<BK, 128, PW, false>(Ws + s * BK * PW, W, out, (int64_t)s * BK, in, c0, out, tid);
-                        }
-                        cp_async_commit();
-                    }
-                    for (int kt = 0; kt < nk; ++kt) {
-                        cp_async_wait<STAGES - 2>();
-                        __syncthreads();
-                        {
-                            int kn = kt + STAGES - 1;
-                            if (kn < nk) {
-                                int s = kn % STAGES;
-                                if (al) load_tile<BK, 128, PW, true>(Ws + s * BK * PW, W, out, (int64_t)kn * BK, in, c0, out, tid);
-                                else    load_tile<BK, 128, PW, false>(Ws + s * BK * PW, W, out, (int64_t)kn * BK, in, c0, out, tid);
-                            }
-                            cp_async_commit();
-                        }
+#pragma unroll 1
+                    for (int kt = 0; kt < nk; ++kt, ++it) {
+                        const int s = it % RING; const uint32_t ph = (it / RING) & 1;
+                        mbar_wait(full + s, ph);
                         const double* as = act + (wm * 64 + lg) * PACT + kt * BK + lk;
-                        const double* bs = Ws + (kt % STAGES) * BK * PW + wn * 32 + lg;
+                        const double* bs = ring + (size_t)s * CHUNK_DOUBLES + wn * 32 + lg;
 #pragma unroll
                         for (int kk = 0; kk < BK / 4; ++kk) {
                             double af[8], bf[4];
@@ -116,10 +201,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) ensemble_kernel(MlpArgs a) {
 #pragma unroll
                                 for (int u = 0; u < 4; ++u) dmma884(acc[t][u][0], acc[t][u][1], af[t], bf[u]);
                         }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(empty + s);
                     }
-                    cp_async_wait<0>();
-                    __syncthreads();            // every warp is done reading act and the weight ring
+                    // bias block of this (layer, chunk)
+                    const int sb = it % RING; const uint32_t phb = (it / RING) & 1;
+                    ++it;
+                    mbar_wait(full + sb, phb);
+                    const double* bias = ring + (size_t)sb * CHUNK_DOUBLES;
                     if (!head) {
+                        consumer_sync();            // every warp has finished reading act for this layer
                         // next activations: relu(acc + b), columns [out, ceil16(out)) zeroed
                         const int outp = (out + BK - 1) / BK * BK;
 #pragma unroll
@@ -127,56 +218,74 @@ __global__ void __launch_bounds__(NTHREADS, 1) ensemble_kernel(MlpArgs a) {
                             const int p = wm * 64 + t * 8 + lg;
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-#pragma unroll
-                                for (int q = 0; q < 2; ++q) {
-                                    const int n = wn * 32 + u * 8 + 2 * lk + q;
-                                    if (n < out) act[p * PACT + n] = fmax(acc[t][u][q] + bias[n], 0.);
-                                    else if (n < outp) act[p * PACT + n] = 0.;
-                                }
+                                const int n = wn * 32 + u * 8 + 2 * lk;
+                                double2 v;
+                                v.x = n < out ? fmax(acc[t][u][0] + bias[n], 0.) : 0.;
+                                v.y = n + 1 < out ? fmax(acc[t][u][1] + bias[n + 1], 0.) : 0.;
+                                if (n < outp) *reinterpret_cast<double2*>(act + p * PACT + n) = v;
                             }
                         }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(empty + sb);
+                        consumer_sync();            // activations of the next layer are complete
                     } else {
-                        // head: loc = t[:, :n_L]; scale = softplus(soft_0 * t[:, n_L:]) + 1e-6
+                        // head: raw outputs t = h W + b go to the per-CTA scratch (L2); the Normal's
+                        // parameters are formed in the mixture pass below
+                        double* sm = scr + (size_t)mem * MP * out_head;
 #pragma unroll
                         for (int t = 0; t < 8; ++t) {
-                            const int64_t p = p0 + wm * 64 + t * 8 + lg;
-                            if (p >= a.N) continue;
+                            const int p = wm * 64 + t * 8 + lg;
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-#pragma unroll
-                                for (int q = 0; q < 2; ++q) {
-                                    const int n = c0 + wn * 32 + u * 8 + 2 * lk + q;
-                                    if (n >= out) continue;
-                                    const double v = acc[t][u][q] + bias[n];
-                                    if (n < n_L) {
-                                        const int64_t o = p * n_L + n;
-                                        if (mem == 0) { a.s1[o] = v; a.s2[o] = v * v; }
-                                        else { a.s1[o] += v; a.s2[o] += v * v; }
-                                    } else {
-                                        const int64_t o = p * n_L + (n - n_L);
-                                        const double sc = softplus(a.soft0 * v) + 1e-6;
-                                        if (mem == 0) a.s3[o] = sc * sc; else a.s3[o] += sc * sc;
-                                    }
-                                }
+                                const int nl = wn * 32 + u * 8 + 2 * lk;          // column inside the chunk (even)
+                                const int n = c * 128 + nl;
+                                if (n + 1 < out)
+                                    *reinterpret_cast<double2*>(sm + (size_t)p * out_head + n) =
+                                        make_double2(acc[t][u][0] + bias[nl], acc[t][u][1] + bias[nl + 1]);
+                                else if (n < out) sm[(size_t)p * out_head + n] = acc[t][u][0] + bias[nl];
                             }
                         }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(empty + sb);
                     }
-                    __syncthreads();
                 }
             }
+            consumer_sync();        // act may be overwritten by the next member's input tile
         }
-        // ---- mixture moments (podnnmodel.py:322-326): mean, sqrt(mean(var + mu^2) - mean^2)
-        __syncthreads();
+        // ---- mixture moments (podnnmodel.py:322-326): mean_i mu_i, sqrt(mean_i(var_i + mu_i^2) - mean^2)
+        __threadfence_block();
+        consumer_sync();
         const double invM = 1. / (double)a.n_members;
         const int64_t pts = min((int64_t)MP, a.N - p0);
-        for (int64_t e = tid; e < pts * n_L; e += NTHREADS) {
-            const int64_t o = p0 * n_L + e;
-            const double mean = a.s1[o] * invM;
+#pragma unroll 1
+        for (int e = tid; e < pts * n_L; e += 256) {
+            const int p = e / n_L, j = e % n_L;
+            double s1 = 0., s2 = 0., var1 = 0.;
+#pragma unroll 1
+            for (int m0 = 0; m0 < a.n_members; m0 += 4) {      // loads of 4 members in flight together
+                double mu4[4], rw4[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int mem = min(m0 + k, a.n_members - 1);
+                    const double* tm = scr + ((size_t)mem * MP + p) * out_head;
+                    mu4[k] = tm[j];                                        // loc = t[:, :n_L]   (:57)
+                    rw4[k] = tm[n_L + j];
+                }
+#pragma unroll 1
+                for (int k = 0; k < 4; ++k) {
+                    if (m0 + k >= a.n_members) break;
+                    const double sc = softplus(a.soft0 * rw4[k]) + 1e-6;  // scale              (:58)
+                    var1 = sc * sc;
+                    s1 += mu4[k]; s2 += var1 + mu4[k] * mu4[k];
+                }
+            }
+            const double mean = s1 * invM;
             // one member: its own variance, exactly (VarNeuralNetwork.predict, varneuralnetwork.py:159)
-            const double var = a.n_members == 1 ? a.s3[o] : (a.s3[o] + a.s2[o]) * invM - mean * mean;
-            a.s1[o] = mean;
-            a.s2[o] = sqrt(var);
+            const double var = a.n_members == 1 ? var1 : s2 * invM - mean * mean;
+            a.v_mean[p0 * n_L + e] = mean;
+            a.v_sig[p0 * n_L + e] = sqrt(var);
         }
+        consumer_sync();            // scratch is reused by the next tile
     }
 }
 
@@ -216,23 +325,29 @@ extern "C" int pb_ensemble_predict(pb_ctx* ctx, int n_members, int n_layers, con
     if (norm_kind != PB_NORM_NONE && (!norm_a_dev || !norm_b_dev)) PB_FAIL(ctx, PB_ERR_ARG, "pb_ensemble_predict: normalisation bounds missing");
     MlpArgs a{};
     a.n_members = n_members; a.n_layers = n_layers; a.n_L = out_last / 2; a.norm_kind = norm_kind;
-    int64_t off = 0;
+    int64_t packed = 0, src = 0;
     for (int l = 0; l <= n_layers; ++l) a.dims[l] = dims[l];
     for (int l = 0; l < n_layers; ++l) {
-        a.w_off[l] = off; off += (int64_t)dims[l] * dims[l + 1];
-        a.b_off[l] = off; off += dims[l + 1];
+        const int nk = (dims[l] + BK - 1) / BK, nc = (dims[l + 1] + 127) / 128;
+        packed += (int64_t)nc * ((int64_t)nk * CHUNK_DOUBLES + BIAS_DOUBLES);
+        src += (int64_t)dims[l] * dims[l + 1] + dims[l + 1];
     }
-    a.member_stride = off;
-    a.weights = weights_dev; a.norm_a = norm_a_dev; a.norm_b = norm_b_dev; a.soft0 = soft_0;
-    a.X = X_dev; a.N = N; a.s1 = v_mean_dev; a.s2 = v_sig_dev;
-    PB_TRY(pb_reserve(ctx, &ctx->ws, &ctx->ws_bytes, (size_t)N * a.n_L));
-    a.s3 = ctx->ws;
+    a.member_stride = packed;
+    a.norm_a = norm_a_dev; a.norm_b = norm_b_dev; a.soft0 = soft_0;
+    a.X = X_dev; a.N = N; a.v_mean = v_mean_dev; a.v_sig = v_sig_dev;
     a.n_tiles = (N + MP - 1) / MP;
+    const int grid = (int)std::min<int64_t>(a.n_tiles, ctx->sm_count);
     cudaEventRecord(ctx->ev0, ctx->stream);
-    size_t smem = sizeof(double) * (size_t)(MP * PACT + STAGES * BK * PW);
+    // workspace: packed weights, then the per-CTA member scratch
+    const size_t scr = (size_t)grid * n_members * MP * 2 * a.n_L;
+    PB_TRY(pb_reserve(ctx, &ctx->ws, &ctx->ws_bytes, (size_t)n_members * packed + scr + 16));
+    double* pk = ctx->ws;
+    a.packed = pk; a.scratch = pk + (((size_t)n_members * packed + 1) & ~(size_t)1);
+    pack_weights_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(weights_dev, pk, n_members, n_layers, a, src);
+    PB_LAUNCH_CHECK(ctx);
+    const size_t smem = sizeof(double) * (size_t)(MP * PACT + RING * CHUNK_DOUBLES) + 2 * RING * sizeof(uint64_t);
     PB_CUDA(ctx, cudaFuncSetAttribute(ensemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = (int)std::min<int64_t>(a.n_tiles, ctx->sm_count);
-    ensemble_kernel<<<grid, NTHREADS, smem, ctx->stream>>>(a);
+    ensemble_kernel<<<grid, MLP_THREADS, smem, ctx->stream>>>(a);
     PB_LAUNCH_CHECK(ctx);
     cudaEventRecord(ctx->ev1, ctx->stream);
     PB_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
