@@ -4,6 +4,8 @@
 #include <cfloat>
 #include <algorithm>
 #include <mutex>
+#include <cstdlib>
+#include <vector>
 
 static std::string g_err;
 static std::mutex g_err_mu;
@@ -83,7 +85,8 @@ int pb_destroy(pb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     void* bufs[] = {ctx->ws, ctx->flush, ctx->At, ctx->At2, ctx->sig, ctx->nrm, ctx->sig2, ctx->nrm2, ctx->perm,
-                    ctx->perm2, ctx->Bmat, ctx->Wk, ctx->small, ctx->Gbuf, ctx->G2buf, ctx->Ybuf, ctx->ATbuf, ctx->Uf, ctx->d_int};
+                    ctx->perm2, ctx->Bmat, ctx->Wk, ctx->small, ctx->Gbuf, ctx->G2buf, ctx->Ybuf, ctx->ATbuf, ctx->Uf, ctx->d_int, ctx->fp_ibuf,
+                    ctx->fp_buf[0], ctx->fp_buf[1], ctx->fp_buf[2], ctx->fp_buf[3], ctx->fp_buf[4], ctx->fp_buf[5], ctx->fp_buf[6], ctx->fp_buf[7]};
     for (void* b : bufs) if (b) cudaFree(b);
     if (ctx->h_int) cudaFreeHost(ctx->h_int);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);
@@ -329,10 +332,87 @@ int pb_pod_basis_full(pb_ctx* ctx, const double* U, int64_t n_h, int64_t n_st, i
 }
 
 // ------------------------------------------------- two-step POD (pod.py:51-68)
+namespace {
+// copy the first r_z columns of T_z (rows x m) into U_f at column offset off_z
+__global__ void pack_bases_kernel(const double* __restrict__ T, int64_t rows, int m, const int* __restrict__ ranks,
+                                  const int* __restrict__ offs, double* __restrict__ Uf, int64_t ldf) {
+    const int z = blockIdx.y;
+    const int r = ranks[z]; const int64_t off = offs[z];
+    const double* Tz = T + (int64_t)z * rows * m;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < rows * r; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t h = idx / r; const int c = (int)(idx % r);
+        Uf[h * ldf + off + c] = Tz[h * m + c];
+    }
+}
+
+// Stage 1 of the two-step POD as ONE batch: every kernel below is launched once for all samples.
+int fast_pod_stage1_batched(pb_ctx* ctx, const double* U, int64_t n_h, int n_t, int64_t n_s, int64_t ldu,
+                            double eps_init, int mode, int* ranks, int64_t ldf, int64_t* total) {
+    const int64_t m = n_t; const int B = (int)n_s;
+    const int64_t ldm = (m + 7) / 8 * 8, cap_rows = (m + 31) / 32 * 32;
+    enum { G = 0, AT, SIG, NRM, SCR, BM, T1, T2 };
+    PB_TRY(pb_reserve(ctx, &ctx->fp_buf[G], &ctx->fp_cap[G], (size_t)B * m * m));
+    PB_TRY(pb_reserve(ctx, &ctx->fp_buf[AT], &ctx->fp_cap[AT], (size_t)B * cap_rows * ldm));
+    PB_TRY(pb_reserve(ctx, &ctx->fp_buf[SIG], &ctx->fp_cap[SIG], (size_t)B * m));
+    PB_TRY(pb_reserve(ctx, &ctx->fp_buf[NRM], &ctx->fp_cap[NRM], (size_t)B * m));
+    PB_TRY(pb_reserve(ctx, &ctx->fp_buf[SCR], &ctx->fp_cap[SCR], (size_t)B * (cap_rows + 2) + 16));
+    PB_TRY(pb_reserve(ctx, &ctx->fp_buf[BM], &ctx->fp_cap[BM], (size_t)B * m * m));
+    PB_TRY(pb_reserve(ctx, &ctx->fp_buf[T1], &ctx->fp_cap[T1], (size_t)B * n_h * m));
+    PB_TRY(pb_reserve_int(ctx, &ctx->fp_ibuf, &ctx->fp_icap, (size_t)B * (cap_rows + 4)));
+    double *Gall = ctx->fp_buf[G], *At = ctx->fp_buf[AT], *sig = ctx->fp_buf[SIG], *nrm = ctx->fp_buf[NRM],
+           *scr = ctx->fp_buf[SCR], *Bm = ctx->fp_buf[BM], *Tm = ctx->fp_buf[T1];
+    int *perm = ctx->fp_ibuf, *r_dev = perm + (size_t)B * cap_rows, *nl_dev = r_dev + B, *off_dev = nl_dev + B;
+    const bool full = (mode == PB_POD_ACCURATE) || eps_init == 0.;
+    PB_TRY(pbi_gram_batched(ctx, U, ldu, m, n_t, n_h, Gall, m * m, B));
+    PB_TRY(pbi_eig_psd_batched(ctx, Gall, m, B, full ? 0. : 4. * DBL_EPSILON, full ? 2. * (double)m * DBL_EPSILON : 0.,
+                               At, sig, nrm, perm, r_dev, scr, nullptr, 40));
+    const double* basis_src = Tm;
+    if (mode == PB_POD_GRAM) {
+        PB_TRY(pbi_rank_batched(ctx, sig, m, B, eps_init, nl_dev));
+        PB_TRY(pbi_factor_to_right_batched(ctx, At, m, (int)m, B, perm, nrm, sig, Bm, m * m));
+        PB_TRY(pbi_gemm_nn_batched(ctx, U, ldu, n_t, n_h, m, Bm, m, m * m, m, Tm, m, n_h * m, B));
+    } else {
+        // second pass per sample: Y = U_k W_k, G2 = Y^T Y, Jacobi again, T_k = Y W2 / sigma
+        PB_TRY(pb_reserve(ctx, &ctx->fp_buf[T2], &ctx->fp_cap[T2], (size_t)B * n_h * m));
+        double* T2m = ctx->fp_buf[T2];
+        PB_TRY(pbi_factor_to_right_batched(ctx, At, m, (int)m, B, perm, nrm, nullptr, Bm, m * m));
+        PB_TRY(pbi_gemm_nn_batched(ctx, U, ldu, n_t, n_h, m, Bm, m, m * m, m, Tm, m, n_h * m, B));       // Y
+        PB_TRY(pbi_gram_batched(ctx, Tm, m, m, n_h * m, n_h, Gall, m * m, B));                            // G2
+        PB_TRY(pbi_eig_psd_batched(ctx, Gall, m, B, 0., 0., At, sig, nrm, perm, r_dev, scr, nullptr, 40));
+        PB_TRY(pbi_rank_batched(ctx, sig, m, B, eps_init, nl_dev));
+        PB_TRY(pbi_factor_to_right_batched(ctx, At, m, (int)m, B, perm, nrm, sig, Bm, m * m));
+        PB_TRY(pbi_gemm_nn_batched(ctx, Tm, m, n_h * m, n_h, m, Bm, m, m * m, m, T2m, m, n_h * m, B));
+        basis_src = T2m;
+    }
+    // ranks to the host (one sync), clamp to the numerical rank, prefix offsets back to the device
+    std::vector<int> nl(B), rr(B), off(B);
+    PB_CUDA(ctx, cudaMemcpyAsync(nl.data(), nl_dev, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaMemcpyAsync(rr.data(), r_dev, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int64_t acc = 0;
+    for (int z = 0; z < B; ++z) {
+        if (rr[z] <= 0) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_fast_pod: sample %d has no positive pivot (zero trajectory)", z);
+        nl[z] = std::min(nl[z], rr[z]);
+        off[z] = (int)acc; acc += nl[z];
+        if (ranks) ranks[z] = nl[z];
+    }
+    if (acc > ldf) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_fast_pod: packed basis overflow");
+    PB_CUDA(ctx, cudaMemcpyAsync(nl_dev, nl.data(), sizeof(int) * B, cudaMemcpyHostToDevice, ctx->stream));
+    PB_CUDA(ctx, cudaMemcpyAsync(off_dev, off.data(), sizeof(int) * B, cudaMemcpyHostToDevice, ctx->stream));
+    pack_bases_kernel<<<dim3(64, B), 256, 0, ctx->stream>>>(basis_src, n_h, (int)m, nl_dev, off_dev, ctx->Uf, ldf);
+    PB_LAUNCH_CHECK(ctx);
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // host vectors go out of scope
+    *total = acc;
+    return PB_OK;
+}
+}  // namespace
+
 int pb_fast_pod(pb_ctx* ctx, const double* U, int64_t n_h, int n_t, int64_t n_s, int64_t ldu,
                 double eps, double eps_init, int mode, int* n_L, int* ranks_host) {
     if (!ctx || !n_L) return PB_ERR_ARG;
     if (n_t <= 0 || n_s <= 0 || ldu < n_s * n_t) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_fast_pod: bad shape");
+    if (mode < PB_POD_GRAM || mode > PB_POD_ACCURATE) PB_FAIL(ctx, PB_ERR_ARG, "pb_fast_pod: unknown mode %d", mode);
+    if (!(eps >= 0.) || eps >= 1. || !(eps_init >= 0.) || eps_init >= 1.) PB_FAIL(ctx, PB_ERR_ARG, "pb_fast_pod: eps in [0, 1)");
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, ctx->stream);
     // stage 1: per-sample bases T_k, packed side by side into U_f (n_h x sum r_k); r_k <= min(n_h, n_t)
@@ -340,13 +420,18 @@ int pb_fast_pod(pb_ctx* ctx, const double* U, int64_t n_h, int n_t, int64_t n_s,
     const int64_t ldf = cap_per * n_s;
     int rc = pb_reserve(ctx, &ctx->Uf, &ctx->Uf_cap, (size_t)n_h * ldf);
     int64_t off = 0;
-    for (int64_t k = 0; k < n_s && rc == PB_OK; ++k) {
-        int rk = 0;
-        const double* Uk = U + k * n_t;
-        rc = pb_pod(ctx, Uk, n_h, n_t, ldu, eps_init, 0, mode, &rk);
-        if (rc == PB_OK) rc = pb_pod_basis_full(ctx, Uk, n_h, n_t, ldu, ctx->Uf + off, ldf);
-        if (ranks_host) ranks_host[k] = rk;
-        off += rk;
+    static const bool batched_ok = []{ const char* e = getenv("PB_FASTPOD_BATCHED"); return !e || atoi(e) != 0; }();
+    if (rc == PB_OK && batched_ok && n_h >= n_t && n_t <= 1024 && n_s < 65536) {
+        rc = fast_pod_stage1_batched(ctx, U, n_h, n_t, n_s, ldu, eps_init, mode, ranks_host, ldf, &off);
+    } else {
+        for (int64_t k = 0; k < n_s && rc == PB_OK; ++k) {     // general shapes: one POD per sample
+            int rk = 0;
+            const double* Uk = U + k * n_t;
+            rc = pb_pod(ctx, Uk, n_h, n_t, ldu, eps_init, 0, mode, &rk);
+            if (rc == PB_OK) rc = pb_pod_basis_full(ctx, Uk, n_h, n_t, ldu, ctx->Uf + off, ldf);
+            if (ranks_host) ranks_host[k] = rk;
+            off += rk;
+        }
     }
     // stage 2: global POD of the unweighted concatenation (usually wide: n_h < sum r_k)
     if (rc == PB_OK) rc = pb_pod(ctx, ctx->Uf, n_h, off, ldf, eps, 0, mode, n_L);

@@ -48,6 +48,8 @@ struct pb_ctx {
     double* small = nullptr;// eigensolver scratch
     double* Gbuf = nullptr; double* G2buf = nullptr; double* Ybuf = nullptr; double* ATbuf = nullptr;
     double* Uf = nullptr; size_t Uf_cap = 0; int64_t uf_rows = 0, uf_cols = 0, uf_ld = 0;  // two-step POD stage-1 bases
+    double* fp_buf[8] = {nullptr}; size_t fp_cap[8] = {0};   // batched two-step POD work buffers
+    int* fp_ibuf = nullptr; size_t fp_icap = 0;
     size_t At_cap = 0, At2_cap = 0, sig_cap = 0, nrm_cap = 0, sig2_cap = 0, nrm2_cap = 0, B_cap = 0,
            Wk_cap = 0, small_cap = 0, G_cap = 0, G2_cap = 0, Y_cap = 0, AT_cap = 0;
     size_t perm_cap = 0, perm2_cap = 0;
@@ -97,3 +99,14 @@ int pbi_rank(pb_ctx* ctx, const double* sig_dev, int64_t count, double eps, int*
 int pbi_factor_to_right(pb_ctx* ctx, const double* At, int64_t m, int k, const int* perm_dev,
                         const double* nrm_dev, const double* sig_dev, double* B, int64_t ldb);
 int pb_reserve_int(pb_ctx* ctx, int** p, size_t* cap, size_t elems);
+// batched variants (two-step POD)
+int pbi_gram_batched(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int64_t sA, int64_t rows,
+                     double* C, int64_t sC, int count);
+int pbi_gemm_nn_batched(pb_ctx* ctx, const double* A, int64_t lda, int64_t sA, int64_t rows, int64_t m,
+                        const double* B, int64_t ldb, int64_t sB, int64_t k, double* Y, int64_t ldy, int64_t sY, int count);
+int pbi_eig_psd_batched(pb_ctx* ctx, const double* G_all, int64_t m, int batch, double tol_rel, double shift_rel,
+                        double* At_all, double* sig_all, double* nrm_all, int* perm_all, int* r_dev,
+                        double* scratch_dbl, int* sweeps_out, int max_sweeps);
+int pbi_rank_batched(pb_ctx* ctx, const double* sig_all, int64_t m, int batch, double eps, int* nL_dev);
+int pbi_factor_to_right_batched(pb_ctx* ctx, const double* At_all, int64_t m, int k, int batch, const int* perm_all,
+                                const double* nrm_all, const double* sig_all, double* B_all, int64_t bsB);

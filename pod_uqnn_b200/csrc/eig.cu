@@ -207,7 +207,7 @@ __device__ int inner_jacobi(double (*S)[SP], double (*Q)[SP], double* cs, double
 }
 
 struct JacArgs {
-    double* At; int64_t ldm; int nb; int round; double tol; int* n_rot; int max_inner;
+    double* At; int64_t ldm; int nb; int round; double tol; int* n_rot; int max_inner; int64_t batch_stride;
 };
 
 constexpr int JCH = 256;        // vector elements staged per shared-memory chunk
@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(256) jacobi_pair_kernel(JacArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lk = lane & 3, lg = lane >> 2;
     int bp, bq; rr_pair(a.nb, a.round, blockIdx.x, bp, bq);
+    a.At += (int64_t)blockIdx.y * a.batch_stride;            // batch of independent factors
     // vector v (0..31) of the pair lives at row: (v < 16 ? bp : bq) * 16 + v % 16
     auto vrow = [&](int v) -> double* {
         return a.At + (int64_t)((v < JB ? bp : bq) * JB + (v % JB)) * a.ldm;
@@ -344,9 +345,11 @@ __global__ void __launch_bounds__(256) jacobi_pair_kernel(JacArgs a) {
 }
 
 // squared norms -> sigma, then sort descending (single CTA bitonic sort)
-__global__ void norms_kernel(const double* __restrict__ At, int64_t ldm, int nvec, double* __restrict__ nrm2) {
+__global__ void norms_kernel(const double* __restrict__ At, int64_t ldm, int nvec, double* __restrict__ nrm2,
+                             int64_t bsAt, int64_t bsN) {
     const int v = blockIdx.x;
     if (v >= nvec) return;
+    At += (int64_t)blockIdx.y * bsAt; nrm2 += (int64_t)blockIdx.y * bsN;
     __shared__ double red[256];
     double s = 0.;
     for (int64_t e = threadIdx.x; e < ldm; e += blockDim.x) { double x = At[(int64_t)v * ldm + e]; s += x * x; }
@@ -357,7 +360,10 @@ __global__ void norms_kernel(const double* __restrict__ At, int64_t ldm, int nve
 
 __global__ void sort_kernel(const double* __restrict__ nrm2, int nvec, int npow2, const double* shift,
                             double* __restrict__ sig_out, double* __restrict__ nrm_out, int m,
-                            int* __restrict__ perm_out, int* r_eff) {
+                            int* __restrict__ perm_out, int* r_eff, int64_t bsN, int64_t bsS, int64_t bsP) {
+    nrm2 += (int64_t)blockIdx.x * bsN; shift += blockIdx.x * (bsN ? 1 : 0);
+    sig_out += (int64_t)blockIdx.x * bsS; nrm_out += (int64_t)blockIdx.x * bsS;
+    perm_out += (int64_t)blockIdx.x * bsP; r_eff += blockIdx.x * (bsN ? 1 : 0);
     extern __shared__ unsigned char sm[];
     double* key = reinterpret_cast<double*>(sm);
     int* idx = reinterpret_cast<int*>(sm + sizeof(double) * npow2);
@@ -401,7 +407,8 @@ __global__ void sort_kernel(const double* __restrict__ nrm2, int nvec, int npow2
 
 // truncation rank (pod.py:22-32): smallest n_L with cumsum(lambda)[n_L-1] / sum(lambda) >= 1 - eps.
 // One warp; each lane accumulates a contiguous chunk in order, a shuffle scan chains the chunks.
-__global__ void rank_kernel(const double* __restrict__ sig, int count, double eps, int* n_L_out) {
+__global__ void rank_kernel(const double* __restrict__ sig, int count, double eps, int* n_L_out, int64_t bsS) {
+    sig += (int64_t)blockIdx.x * bsS; n_L_out += blockIdx.x;
     const int lane = threadIdx.x;
     const int chunk = (count + 31) / 32;
     const int b = lane * chunk, e = min(count, b + chunk);
@@ -428,7 +435,11 @@ __global__ void rank_kernel(const double* __restrict__ sig, int count, double ep
 
 __global__ void factor_to_right_kernel(const double* __restrict__ At, int64_t ldm, const int* __restrict__ perm,
                                        const double* __restrict__ nrm, const double* __restrict__ sig,
-                                       int m, int k, double* __restrict__ B, int64_t ldb) {
+                                       int m, int k, double* __restrict__ B, int64_t ldb,
+                                       int64_t bsAt, int64_t bsS, int64_t bsP, int64_t bsB) {
+    At += (int64_t)blockIdx.y * bsAt; perm += (int64_t)blockIdx.y * bsP; nrm += (int64_t)blockIdx.y * bsS;
+    if (sig) sig += (int64_t)blockIdx.y * bsS;
+    B += (int64_t)blockIdx.y * bsB;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)m * k) return;
     int i = (int)(idx / k), j = (int)(idx % k);
@@ -496,7 +507,7 @@ int pbi_eig_psd(pb_ctx* ctx, const double* G, int64_t m, double tol_rel, double 
         PB_CUDA(ctx, cudaMemsetAsync(ctx->d_int + 1, 0, sizeof(int), ctx->stream));
         const int rounds = nb > 2 ? nb - 1 : 1;
         for (int round = 0; round < rounds; ++round) {
-            JacArgs ja{At, ldm, nb, round, tol, ctx->d_int + 1, g_inner_sweeps};
+            JacArgs ja{At, ldm, nb, round, tol, ctx->d_int + 1, g_inner_sweeps, 0};
             jacobi_pair_kernel<<<nb / 2, 256, jac_smem, ctx->stream>>>(ja);
             PB_LAUNCH_CHECK(ctx);
         }
@@ -508,12 +519,12 @@ int pbi_eig_psd(pb_ctx* ctx, const double* G, int64_t m, double tol_rel, double 
         PB_FAIL(ctx, PB_ERR_NOT_CONVERGED, "eig_psd: Jacobi did not converge in %d sweeps (m=%lld r=%d)", max_sweeps, (long long)m, r);
 
     // ---- norms, sort, sigma
-    norms_kernel<<<nvec, 256, 0, ctx->stream>>>(At, ldm, nvec, sc.nrm2);
+    norms_kernel<<<nvec, 256, 0, ctx->stream>>>(At, ldm, nvec, sc.nrm2, 0, 0);
     PB_LAUNCH_CHECK(ctx);
     int npow2 = 1; while (npow2 < nvec) npow2 <<= 1;
     size_t sort_smem = (sizeof(double) + sizeof(int)) * (size_t)npow2;
     PB_CUDA(ctx, cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
-    sort_kernel<<<1, 1024, sort_smem, ctx->stream>>>(sc.nrm2, nvec, npow2, sc.shift, sig_dev, nrm_dev, (int)m, perm_dev, ctx->d_int + 3);
+    sort_kernel<<<1, 1024, sort_smem, ctx->stream>>>(sc.nrm2, nvec, npow2, sc.shift, sig_dev, nrm_dev, (int)m, perm_dev, ctx->d_int + 3, 0, 0, 0);
     PB_LAUNCH_CHECK(ctx);
     PB_CUDA(ctx, cudaMemcpyAsync(ctx->h_int + 3, ctx->d_int + 3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -523,7 +534,7 @@ int pbi_eig_psd(pb_ctx* ctx, const double* G, int64_t m, double tol_rel, double 
 }
 
 int pbi_rank(pb_ctx* ctx, const double* sig_dev, int64_t count, double eps, int* n_L_out) {
-    rank_kernel<<<1, 32, 0, ctx->stream>>>(sig_dev, (int)count, eps, ctx->d_int + 2);
+    rank_kernel<<<1, 32, 0, ctx->stream>>>(sig_dev, (int)count, eps, ctx->d_int + 2, 0);
     PB_LAUNCH_CHECK(ctx);
     PB_CUDA(ctx, cudaMemcpyAsync(ctx->h_int + 2, ctx->d_int + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -535,7 +546,134 @@ int pbi_factor_to_right(pb_ctx* ctx, const double* At, int64_t m, int k, const i
                         const double* nrm_dev, const double* sig_dev, double* B, int64_t ldb) {
     const int64_t ldm = (m + 7) / 8 * 8;
     int64_t n = m * k;
-    factor_to_right_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(At, ldm, perm_dev, nrm_dev, sig_dev, (int)m, k, B, ldb);
+    factor_to_right_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(At, ldm, perm_dev, nrm_dev, sig_dev, (int)m, k, B, ldb, 0, 0, 0, 0);
+    PB_LAUNCH_CHECK(ctx);
+    return PB_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// batched variant (two-step POD, pod.py:51-68): `batch` independent small PSD matrices
+// ---------------------------------------------------------------------------
+namespace {
+// pivoted Cholesky of one matrix per CTA (m <= 1024); same arithmetic as chol_kernel
+__global__ void __launch_bounds__(256) chol_small_kernel(const double* __restrict__ Gall, int m, double* __restrict__ Atall,
+                                                         int64_t ldm, int64_t bsAt, double tol_rel, double shift_rel,
+                                                         int* __restrict__ r_out, double* __restrict__ shift_out) {
+    extern __shared__ double chol_sm[];          // d[m], lp[m]
+    double* d = chol_sm; double* lp = chol_sm + m;
+    __shared__ double red_v[256];
+    __shared__ int red_i[256];
+    const double* G = Gall + (int64_t)blockIdx.x * m * m;
+    double* At = Atall + (int64_t)blockIdx.x * bsAt;
+    const int tid = threadIdx.x;
+    double tr = 0.;
+    for (int j = tid; j < m; j += 256) tr += G[(int64_t)j * m + j];
+    red_v[tid] = tr; __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) { if (tid < s) red_v[tid] += red_v[tid + s]; __syncthreads(); }
+    const double shift = shift_rel * red_v[0];
+    __syncthreads();
+    for (int j = tid; j < m; j += 256) d[j] = G[(int64_t)j * m + j] + shift;
+    __syncthreads();
+    double thresh = 0.;
+    int k = 0;
+    for (; k < m; ++k) {
+        double bv = -DBL_MAX; int bi = 0x7fffffff;
+        for (int j = tid; j < m; j += 256) { double v = d[j]; if (v > bv || (v == bv && j < bi)) { bv = v; bi = j; } }
+        red_v[tid] = bv; red_i[tid] = bi; __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if (tid < s) {
+                double v = red_v[tid + s]; int i = red_i[tid + s];
+                if (v > red_v[tid] || (v == red_v[tid] && i < red_i[tid])) { red_v[tid] = v; red_i[tid] = i; }
+            }
+            __syncthreads();
+        }
+        const double dp = red_v[0]; const int p = red_i[0];
+        __syncthreads();
+        if (k == 0) thresh = tol_rel * dp;
+        if (!(dp > thresh) || !(dp > 0.)) break;
+        for (int q = tid; q < k; q += 256) lp[q] = At[(int64_t)q * ldm + p];
+        __syncthreads();
+        const double inv = 1. / sqrt(dp);
+        for (int j = tid; j < m; j += 256) {
+            double s0 = 0., s1 = 0.;
+            int q = 0;
+            for (; q + 1 < k; q += 2) { s0 += At[(int64_t)q * ldm + j] * lp[q]; s1 += At[(int64_t)(q + 1) * ldm + j] * lp[q + 1]; }
+            if (q < k) s0 += At[(int64_t)q * ldm + j] * lp[q];
+            double v = (G[(int64_t)j * m + p] + (j == p ? shift : 0.) - (s0 + s1)) * inv;
+            if (d[j] == -DBL_MAX) v = 0.;
+            if (j == p) v = sqrt(dp);
+            At[(int64_t)k * ldm + j] = v;
+            d[j] = (j == p || d[j] == -DBL_MAX) ? -DBL_MAX : d[j] - v * v;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { r_out[blockIdx.x] = k; shift_out[blockIdx.x] = shift; }
+}
+}  // namespace
+
+// Eigen-decomposition of `batch` PSD matrices G_z (m x m, contiguous).  Outputs per matrix z:
+// factor vectors At_all + z*bsAt (cap_rows x ldm), sig_all / nrm_all + z*m, perm_all + z*cap_rows,
+// r_dev[z] (device).  scratch_dbl needs batch * (cap_rows + 1) doubles.
+int pbi_eig_psd_batched(pb_ctx* ctx, const double* G_all, int64_t m, int batch, double tol_rel, double shift_rel,
+                        double* At_all, double* sig_all, double* nrm_all, int* perm_all, int* r_dev,
+                        double* scratch_dbl, int* sweeps_out, int max_sweeps) {
+    if (m <= 0 || m > 1024) PB_FAIL(ctx, PB_ERR_SHAPE, "eig_psd_batched: order %lld outside (0, 1024]", (long long)m);
+    const int64_t ldm = (m + 7) / 8 * 8;
+    const int64_t cap_rows = (m + JP - 1) / JP * JP;
+    const int64_t bsAt = cap_rows * ldm;
+    PB_CUDA(ctx, cudaMemsetAsync(At_all, 0, sizeof(double) * (size_t)bsAt * batch, ctx->stream));
+    double* nrm2 = scratch_dbl; double* shift = scratch_dbl + (size_t)batch * cap_rows;
+    chol_small_kernel<<<batch, 256, sizeof(double) * 2 * (size_t)m, ctx->stream>>>(G_all, (int)m, At_all, ldm, bsAt, tol_rel,
+                                                                                shift_rel, r_dev, shift);
+    PB_LAUNCH_CHECK(ctx);
+    const int nb = (int)(cap_rows / JB);
+    const int nvec = (int)cap_rows;
+    const double tol = std::max(4., sqrt((double)m)) * DBL_EPSILON;
+    size_t jac_smem = sizeof(double) * 2 * JP * JPX;
+    PB_CUDA(ctx, cudaFuncSetAttribute(jacobi_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jac_smem));
+    int sweeps = 0; bool converged = false;
+    for (; sweeps < max_sweeps && !converged; ++sweeps) {
+        PB_CUDA(ctx, cudaMemsetAsync(ctx->d_int + 1, 0, sizeof(int), ctx->stream));
+        const int rounds = nb > 2 ? nb - 1 : 1;
+        for (int round = 0; round < rounds; ++round) {
+            JacArgs ja{At_all, ldm, nb, round, tol, ctx->d_int + 1, g_inner_sweeps, bsAt};
+            jacobi_pair_kernel<<<dim3(nb / 2, batch), 256, jac_smem, ctx->stream>>>(ja);
+            PB_LAUNCH_CHECK(ctx);
+        }
+        PB_CUDA(ctx, cudaMemcpyAsync(ctx->h_int + 1, ctx->d_int + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        converged = (ctx->h_int[1] == 0);
+    }
+    if (!converged && max_sweeps >= 30)
+        PB_FAIL(ctx, PB_ERR_NOT_CONVERGED, "eig_psd_batched: Jacobi did not converge in %d sweeps", max_sweeps);
+    norms_kernel<<<dim3(nvec, batch), 256, 0, ctx->stream>>>(At_all, ldm, nvec, nrm2, bsAt, cap_rows);
+    PB_LAUNCH_CHECK(ctx);
+    int npow2 = 1; while (npow2 < nvec) npow2 <<= 1;
+    size_t sort_smem = (sizeof(double) + sizeof(int)) * (size_t)npow2;
+    PB_CUDA(ctx, cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+    // r_eff is not needed for the batch: reuse the tail of the scratch as a dump (ints)
+    int* r_eff = reinterpret_cast<int*>(shift + batch);
+    sort_kernel<<<batch, 1024, sort_smem, ctx->stream>>>(nrm2, nvec, npow2, shift, sig_all, nrm_all, (int)m, perm_all, r_eff,
+                                                        cap_rows, m, cap_rows);
+    PB_LAUNCH_CHECK(ctx);
+    if (sweeps_out) *sweeps_out = sweeps;
+    return PB_OK;
+}
+
+int pbi_rank_batched(pb_ctx* ctx, const double* sig_all, int64_t m, int batch, double eps, int* nL_dev) {
+    rank_kernel<<<batch, 32, 0, ctx->stream>>>(sig_all, (int)m, eps, nL_dev, m);
+    PB_LAUNCH_CHECK(ctx);
+    return PB_OK;
+}
+
+// B_z (m x k, ldb = k) = factor columns / (nrm * (sig ? sig : 1)) for every matrix of the batch
+int pbi_factor_to_right_batched(pb_ctx* ctx, const double* At_all, int64_t m, int k, int batch, const int* perm_all,
+                                const double* nrm_all, const double* sig_all, double* B_all, int64_t bsB) {
+    const int64_t ldm = (m + 7) / 8 * 8, cap_rows = (m + JP - 1) / JP * JP;
+    int64_t n = m * k;
+    factor_to_right_kernel<<<dim3((unsigned)((n + 255) / 256), batch), 256, 0, ctx->stream>>>(
+        At_all, ldm, perm_all, nrm_all, sig_all, (int)m, k, B_all, k, cap_rows * ldm, m, cap_rows, bsB);
     PB_LAUNCH_CHECK(ctx);
     return PB_OK;
 }

@@ -27,8 +27,9 @@ gemm_tn_kernel(const double* __restrict__ A, int64_t lda, int ka,
                const double* __restrict__ B, int64_t ldb, int kb,
                int64_t rows, int64_t rows_per_split,
                double* __restrict__ out, int64_t ldo, int64_t split_stride,
-               int tiles_m, int tiles_n, int sym) {
+               int tiles_m, int tiles_n, int sym, int64_t bsA, int64_t bsB, int64_t bsOut) {
     static_assert(WARPS_M * WARPS_N == NTHREADS / 32, "8 warps");
+    A += (int64_t)blockIdx.z * bsA; B += (int64_t)blockIdx.z * bsB; out += (int64_t)blockIdx.z * bsOut;   // batch
     constexpr int PA = BM + 4, PB = BN + 4;
     constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
     constexpr int TM = WM / 8, TNN = WN / 8;
@@ -117,7 +118,8 @@ gemm_tn_kernel(const double* __restrict__ A, int64_t lda, int ka,
 // second stage: fixed-order sum over splits (+ mirror of the upper triangle when sym)
 __global__ void reduce_splits_kernel(const double* __restrict__ ws, int splits, int64_t split_stride,
                                      int ka, int kb, int64_t ldw, double* __restrict__ C, int64_t ldc,
-                                     int sym, int bm, int bn) {
+                                     int sym, int bm, int bn, int64_t bsW, int64_t bsC) {
+    ws += (int64_t)blockIdx.y * bsW; C += (int64_t)blockIdx.y * bsC;      // batch
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)ka * kb) return;
     int i = (int)(idx / kb), j = (int)(idx % kb);
@@ -133,7 +135,8 @@ __global__ void reduce_splits_kernel(const double* __restrict__ ws, int splits, 
 // make an (n x n) matrix exactly symmetric from its upper triangle (diagonal tiles of the
 // sym product are computed in full; rounding is identical on both sides because the same
 // products are accumulated in the same order, but we do not rely on it).
-__global__ void symmetrize_kernel(double* __restrict__ C, int n, int64_t ldc) {
+__global__ void symmetrize_kernel(double* __restrict__ C, int n, int64_t ldc, int64_t bsC) {
+    C += (int64_t)blockIdx.y * bsC;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)n * n) return;
     int i = (int)(idx / n), j = (int)(idx % n);
@@ -148,8 +151,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_nn_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int m,
                const double* __restrict__ B, int64_t ldb, int k,
                double* __restrict__ Y, int64_t ldy,
-               const double* __restrict__ Uref, int64_t ldu, double* __restrict__ sig_part) {
+               const double* __restrict__ Uref, int64_t ldu, double* __restrict__ sig_part,
+               int64_t bsA, int64_t bsB, int64_t bsY) {
     constexpr int BM = 128;
+    A += (int64_t)blockIdx.z * bsA; B += (int64_t)blockIdx.z * bsB;
+    if (Y) Y += (int64_t)blockIdx.z * bsY;                                   // batch
     static_assert(WARPS_M * WARPS_N == NTHREADS / 32, "8 warps");
     constexpr int PA = BK + 4, PB = BN + 4;
     constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
@@ -302,26 +308,29 @@ int pbi_gram_tma(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int64_t 
 namespace {
 bool g_time_tn = false;   // set per call by pbi_gemm_tn (contexts are single-threaded)
 
+struct Batch { int count = 1; int64_t sA = 0, sB = 0, sC = 0; };
+
 template <int BM, int BN, int WARPS_M, int WARPS_N>
 int launch_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const double* B, int64_t ldb,
-              int64_t kb, int64_t rows, double* C, int64_t ldc, int sym) {
+              int64_t kb, int64_t rows, double* C, int64_t ldc, int sym, Batch bt = Batch()) {
     constexpr int STAGES = 4;
     const int tiles_m = (int)((ka + BM - 1) / BM), tiles_n = (int)((kb + BN - 1) / BN);
     const int tiles = sym ? tiles_n * (tiles_n + 1) / 2 : tiles_m * tiles_n;
-    const int splits = choose_splits(tiles, rows, ctx->sm_count);
+    const int splits = choose_splits(tiles * bt.count, rows, ctx->sm_count);
     int64_t rps = (rows + splits - 1) / splits;
     rps = (rps + BK - 1) / BK * BK;
     const bool direct = (splits == 1 && !sym);
     const int64_t split_stride = (int64_t)ka * kb;
     double* out = C; int64_t ldo = ldc;
     if (!direct) {
-        PB_TRY(pb_reserve(ctx, &ctx->ws, &ctx->ws_bytes, (size_t)split_stride * splits));
+        PB_TRY(pb_reserve(ctx, &ctx->ws, &ctx->ws_bytes, (size_t)split_stride * splits * bt.count));
         out = ctx->ws; ldo = kb;
     }
-    const bool al = aligned16(A, lda) && aligned16(B, ldb);
+    const int64_t bsOut = direct ? bt.sC : split_stride * splits;
+    const bool al = aligned16(A, lda) && aligned16(B, ldb) && (bt.sA % 2 == 0) && (bt.sB % 2 == 0);
     size_t smem = (size_t)STAGES * BK * ((BM + 4) + (BN + 4)) * sizeof(double);
-    dim3 grid(tiles, splits);
-    if (sym && BM == 128 && BN == 128) {     // TMA + mbarrier pipeline when the layout allows it
+    dim3 grid(tiles, splits, bt.count);
+    if (sym && BM == 128 && BN == 128 && bt.count == 1) {     // TMA + mbarrier pipeline when the layout allows it
         int rc = pbi_gram_tma(ctx, A, lda, ka, rows, splits, rps, ctx->ws, split_stride, g_time_tn);
         if (rc < 0) return rc;
         if (rc == PB_OK) goto reduce;
@@ -331,23 +340,23 @@ int launch_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const doubl
         auto kern = gemm_tn_kernel<BM, BN, WARPS_M, WARPS_N, STAGES, true>;
         PB_TRY(set_smem(ctx, kern, smem));
         kern<<<grid, NTHREADS, smem, ctx->stream>>>(A, lda, (int)ka, B, ldb, (int)kb, rows, rps, out, ldo,
-                                                    split_stride, tiles_m, tiles_n, sym);
+                                                    split_stride, tiles_m, tiles_n, sym, bt.sA, bt.sB, bsOut);
     } else {
         auto kern = gemm_tn_kernel<BM, BN, WARPS_M, WARPS_N, STAGES, false>;
         PB_TRY(set_smem(ctx, kern, smem));
         kern<<<grid, NTHREADS, smem, ctx->stream>>>(A, lda, (int)ka, B, ldb, (int)kb, rows, rps, out, ldo,
-                                                    split_stride, tiles_m, tiles_n, sym);
+                                                    split_stride, tiles_m, tiles_n, sym, bt.sA, bt.sB, bsOut);
     }
     PB_LAUNCH_CHECK(ctx);
     if (g_time_tn) { cudaEventRecord(ctx->evk1, ctx->stream); ctx->tn_timing_pending = true; }
 reduce:
     if (!direct) {
         int64_t n = (int64_t)ka * kb;
-        reduce_splits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
-            ctx->ws, splits, split_stride, (int)ka, (int)kb, kb, C, ldc, sym, BM, BN);
+        reduce_splits_kernel<<<dim3((unsigned)((n + 255) / 256), bt.count), 256, 0, ctx->stream>>>(
+            ctx->ws, splits, split_stride, (int)ka, (int)kb, kb, C, ldc, sym, BM, BN, split_stride * splits, bt.sC);
         PB_LAUNCH_CHECK(ctx);
         if (sym) {
-            symmetrize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(C, (int)ka, ldc);
+            symmetrize_kernel<<<dim3((unsigned)((n + 255) / 256), bt.count), 256, 0, ctx->stream>>>(C, (int)ka, ldc, bt.sC);
             PB_LAUNCH_CHECK(ctx);
         }
     }
@@ -357,14 +366,15 @@ reduce:
 template <int BN, int WARPS_M, int WARPS_N>
 int launch_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m, const double* B,
               int64_t ldb, int64_t k, double* Y, int64_t ldy, const double* Uref, int64_t ldu,
-              double* sig_part) {
+              double* sig_part, Batch bt = Batch()) {
     constexpr int STAGES = 4;
     size_t smem = (size_t)STAGES * (128 * (BK + 4) + BK * (BN + 4)) * sizeof(double);
-    dim3 grid((unsigned)((rows + 127) / 128), (unsigned)((k + BN - 1) / BN));
-    const bool aa = aligned16(A, lda), ab = aligned16(B, ldb);
+    dim3 grid((unsigned)((rows + 127) / 128), (unsigned)((k + BN - 1) / BN), bt.count);
+    const bool aa = aligned16(A, lda) && (bt.sA % 2 == 0), ab = aligned16(B, ldb) && (bt.sB % 2 == 0);
 #define PB_NN_CASE(AA, AB) { auto kern = gemm_nn_kernel<BN, WARPS_M, WARPS_N, STAGES, AA, AB>; \
         PB_TRY(set_smem(ctx, kern, smem)); \
-        kern<<<grid, NTHREADS, smem, ctx->stream>>>(A, lda, rows, (int)m, B, ldb, (int)k, Y, ldy, Uref, ldu, sig_part); }
+        kern<<<grid, NTHREADS, smem, ctx->stream>>>(A, lda, rows, (int)m, B, ldb, (int)k, Y, ldy, Uref, ldu, sig_part, \
+                                                    bt.sA, bt.sB, bt.sC); }
     if (aa && ab) PB_NN_CASE(true, true)
     else if (aa) PB_NN_CASE(true, false)
     else if (ab) PB_NN_CASE(false, true)
@@ -390,7 +400,7 @@ int pbi_gemm_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const dou
     }
     if (ka <= 32 && kb <= 32) {      // skinny x skinny (second-pass Gram of the rotated block): HBM bound
         PB_TRY((launch_tn<32, 32, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0)));
-        if (sym) { symmetrize_kernel<<<(unsigned)((ka * kb + 255) / 256), 256, 0, ctx->stream>>>(C, (int)ka, ldc); PB_LAUNCH_CHECK(ctx); }
+        if (sym) { symmetrize_kernel<<<(unsigned)((ka * kb + 255) / 256), 256, 0, ctx->stream>>>(C, (int)ka, ldc, 0); PB_LAUNCH_CHECK(ctx); }
         return PB_OK;
     }
     if (sym || ka > 32) return launch_tn<128, 128, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, sym);
@@ -428,4 +438,18 @@ int pbi_transpose(pb_ctx* ctx, const double* in, int64_t rows, int64_t cols, int
     transpose_kernel<<<grid, block, 0, ctx->stream>>>(in, rows, cols, ldin, out, ldout);
     PB_LAUNCH_CHECK(ctx);
     return PB_OK;
+}
+
+// batch of `count` independent products: A_z = A + z*sA (same lda), C_z = C + z*sC  (two-step POD)
+int pbi_gram_batched(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int64_t sA, int64_t rows,
+                     double* C, int64_t sC, int count) {
+    Batch bt; bt.count = count; bt.sA = sA; bt.sB = sA; bt.sC = sC;
+    g_time_tn = false;
+    return launch_tn<128, 128, 2, 4>(ctx, A, lda, ka, A, lda, ka, rows, C, ka, 1, bt);
+}
+int pbi_gemm_nn_batched(pb_ctx* ctx, const double* A, int64_t lda, int64_t sA, int64_t rows, int64_t m,
+                        const double* B, int64_t ldb, int64_t sB, int64_t k, double* Y, int64_t ldy, int64_t sY, int count) {
+    Batch bt; bt.count = count; bt.sA = sA; bt.sB = sB; bt.sC = sY;
+    if (k > 32) return launch_nn<128, 2, 4>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, nullptr, 0, nullptr, bt);
+    return launch_nn<32, 8, 1>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, nullptr, 0, nullptr, bt);
 }
