@@ -173,10 +173,17 @@ __device__ int inner_jacobi(double (*S)[SP], double (*Q)[SP], double* cs, double
                 int p, q; rr_pair(JP, round, tid, p, q);
                 double app = S[p][p], aqq = S[q][q], apq = S[p][q];
                 double c = 1., s = 0.;
-                if (fabs(apq) > tol * sqrt(fabs(app * aqq)) && apq != 0.) {
-                    double zeta = (aqq - app) / (2. * apq);
-                    double t = (zeta >= 0. ? 1. : -1.) / (fabs(zeta) + sqrt(1. + zeta * zeta));
-                    c = 1. / sqrt(1. + t * t); s = c * t; did = 1;
+                if (apq * apq > tol * tol * fabs(app * aqq) && apq != 0.) {
+                    // small-angle Jacobi rotation from cos(2 theta) = |d| / h, h = hypot(d, 2 apq); two
+                    // reciprocal square roots instead of two divisions and two square roots (the round's
+                    // critical path: 240 threads wait for these 16)
+                    const double d = aqq - app;
+                    const double rh = rsqrt(d * d + 4. * apq * apq);
+                    const double c2 = 0.5 + 0.5 * fabs(d) * rh;          // cos^2 theta in [1/2, 1]
+                    const double rc = rsqrt(c2);
+                    c = c2 * rc;
+                    s = (d >= 0. ? apq : -apq) * rh * rc;                 // sin theta, sign of zeta = d / (2 apq)
+                    did = 1;
                 }
                 cs[tid] = c; sn[tid] = s;
             }
@@ -450,6 +457,7 @@ __global__ void factor_to_right_kernel(const double* __restrict__ At, int64_t ld
 
 }  // namespace
 
+double g_jacobi_tol_override = 0.;   // > 0: rotation threshold of the next eig (first pass of the accurate mode)
 static int g_inner_sweeps = []{ const char* e = getenv("PB_JACOBI_INNER"); return e ? atoi(e) : 3; }();
 // device ints layout in ctx->d_int: [0] r (Cholesky), [1] n_rot, [2] n_L, [3] r_eff
 struct EigScratch { double* d; double* cand_val; int* cand_idx; double* nrm2; double* shift; };
@@ -499,7 +507,8 @@ int pbi_eig_psd(pb_ctx* ctx, const double* G, int64_t m, double tol_rel, double 
     const int nvec = nb * JB;
     // rotation threshold relative to the column norms (dgesvj uses sqrt(m) eps): below it the
     // pair Gram entry is rounding noise of the m-long dot product
-    const double tol = std::max(4., sqrt((double)m)) * DBL_EPSILON;
+    const double tol = g_jacobi_tol_override > 0. ? g_jacobi_tol_override : std::max(4., sqrt((double)m)) * DBL_EPSILON;
+    g_jacobi_tol_override = 0.;
     size_t jac_smem = sizeof(double) * 2 * JP * JPX;
     PB_CUDA(ctx, cudaFuncSetAttribute(jacobi_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jac_smem));
     int sweeps = 0; bool converged = false;
