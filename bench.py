@@ -234,10 +234,20 @@ def run_gpu(args):
     ctx.check(L.pb_download(ctx.h, hU, U.ptr, U.nbytes))
 
     def step_e2e():
-        ctx.check(L.pb_upload_async(ctx.h, U.ptr, hU, U.nbytes))
-        nl = step_resident()
-        ctx.check(L.pb_download_async(ctx.h, hV, state["V"].ptr if world == 1 else state["V"].ptr, n_h_loc * nl * 8))
-        vptr = state["v"].ptr if world == 1 else state["v"].data_ptr()
+        if world == 1:
+            # the reference-facing host call: chunked upload overlapped with the Gram (pb_pod_host)
+            nl_c = C.c_int()
+            ctx.check(L.pb_pod_host(ctx.h, hU, n_h_loc, N_S, N_S, U.ptr, EPS, 0, _lib.POD_MODES[MODE], C.byref(nl_c)))
+            nl = nl_c.value
+            V, v = state["V"], state["v"]
+            ctx.check(L.pb_pod_basis_full(ctx.h, U.ptr, n_h_loc, N_S, U.ld, V.ptr, V.ld))
+            ctx.check(L.pb_project(ctx.h, V.ptr, V.ld, nl, U.ptr, U.ld, n_h_loc, N_S, v.ptr))
+            vptr = v.ptr
+        else:
+            ctx.check(L.pb_upload_async(ctx.h, U.ptr, hU, U.nbytes))
+            nl = step_resident()
+            vptr = state["v"].data_ptr()
+        ctx.check(L.pb_download_async(ctx.h, hV, state["V"].ptr, n_h_loc * nl * 8))
         ctx.check(L.pb_download_async(ctx.h, hv, vptr, N_S * nl * 8))
         ctx.sync()
 

@@ -160,6 +160,10 @@ int  pb_pod(pb_ctx* ctx, const double* U_dev, int64_t n_h, int64_t n_st, int64_t
             double eps, int n_L_in, int mode, int* n_L);
 int  pb_pod_basis_full(pb_ctx* ctx, const double* U_dev, int64_t n_h, int64_t n_st, int64_t ldu,
                        double* V_dev, int64_t ldv);
+/* Same from a HOST matrix (pinned memory for full PCIe speed): the upload into U_dev (n_h x n_st,
+ * ld = n_st, caller-allocated) is cut into row chunks on a copy stream and overlapped with the Gram. */
+int  pb_pod_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, int64_t ldu_host, double* U_dev,
+                 double eps, int n_L_in, int mode, int* n_L);
 
 /* replaces poduqnn/pod.py:51-68 (perform_fast_pod): per-sample POD with eps_init on the
  * n_h x n_t column blocks of U (sample-major columns, as loop_u_t writes them), unweighted

@@ -91,6 +91,8 @@ int pb_destroy(pb_ctx* ctx) {
     if (ctx->h_int) cudaFreeHost(ctx->h_int);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);
     cudaEventDestroy(ctx->evk0); cudaEventDestroy(ctx->evk1); cudaEventDestroy(ctx->evr0); cudaEventDestroy(ctx->evr1);
+    if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); for (auto& e : ctx->chunk_ev) if (e) cudaEventDestroy(e); }
+    if (ctx->Gpart) cudaFree(ctx->Gpart);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return PB_OK;
@@ -294,6 +296,23 @@ int pb_pod_right(pb_ctx* ctx, double* Z, int64_t ldz) {
     return PB_OK;
 }
 
+// eigensolve + (optional) second pass on a tall operand whose Gram is already in ctx->Gbuf
+static int pod_after_gram(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, double eps, int n_L_in,
+                          int mode, int* n_L) {
+    int keep = 0;
+    PB_TRY(pb_pod_from_gram(ctx, ctx->Gbuf, m, eps, n_L_in, mode, n_L, &keep));
+    ctx->ms[PB_T_PASS2] = 0.;
+    if (keep > 0) {
+        Timer t2(ctx, PB_T_PASS2);
+        PB_TRY(pb_reserve(ctx, &ctx->Ybuf, &ctx->Y_cap, (size_t)rows * keep));
+        PB_TRY(pb_reserve(ctx, &ctx->G2buf, &ctx->G2_cap, (size_t)keep * keep));
+        PB_TRY(pb_pod_pass2_gram(ctx, A, rows, lda, ctx->Ybuf, ctx->G2buf));
+        PB_TRY(pb_pod_pass2_finish(ctx, ctx->G2buf, eps, n_L_in, n_L));
+        t2.stop();
+    }
+    return PB_OK;
+}
+
 int pb_pod(pb_ctx* ctx, const double* U, int64_t n_h, int64_t n_st, int64_t ldu, double eps, int n_L_in, int mode, int* n_L) {
     if (!ctx || !n_L) return PB_ERR_ARG;
     if (n_h <= 0 || n_st <= 0 || ldu < n_st) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod: bad shape (%lld x %lld, ld %lld)",
@@ -309,18 +328,67 @@ int pb_pod(pb_ctx* ctx, const double* U, int64_t n_h, int64_t n_st, int64_t ldu,
     if (m > 8192) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod: min(n_h, n_st) = %lld exceeds 8192", (long long)m);
     PB_TRY(pb_reserve(ctx, &ctx->Gbuf, &ctx->G_cap, (size_t)m * m));
     PB_TRY(pb_gram(ctx, A, rows, m, lda, ctx->Gbuf));
-    int keep = 0;
-    PB_TRY(pb_pod_from_gram(ctx, ctx->Gbuf, m, eps, n_L_in, mode, n_L, &keep));
     ctx->wide = wide;
-    ctx->ms[PB_T_PASS2] = 0.;
-    if (keep > 0) {
-        Timer t2(ctx, PB_T_PASS2);
-        PB_TRY(pb_reserve(ctx, &ctx->Ybuf, &ctx->Y_cap, (size_t)rows * keep));
-        PB_TRY(pb_reserve(ctx, &ctx->G2buf, &ctx->G2_cap, (size_t)keep * keep));
-        PB_TRY(pb_pod_pass2_gram(ctx, A, rows, lda, ctx->Ybuf, ctx->G2buf));
-        PB_TRY(pb_pod_pass2_finish(ctx, ctx->G2buf, eps, n_L_in, n_L));
-        t2.stop();
+    PB_TRY(pod_after_gram(ctx, A, rows, m, lda, eps, n_L_in, mode, n_L));
+    cudaEventRecord(ctx->ev3, ctx->stream); cudaEventSynchronize(ctx->ev3);
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3); ctx->ms[PB_T_POD_TOTAL] = ms;
+    return PB_OK;
+}
+
+namespace {
+__global__ void sum_partials_kernel(const double* __restrict__ part, int count, int64_t n, double* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.;
+    for (int c = 0; c < count; ++c) s += part[(int64_t)c * n + i];     // fixed order: deterministic
+    out[i] = s;
+}
+}  // namespace
+
+// POD of a HOST matrix: the upload is cut into row chunks on a copy stream and the Gram of chunk c
+// runs on the compute stream as soon as chunk c has landed, so the 5 ms Gram hides under the PCIe
+// transfer; the chunk Grams are summed in chunk order.  U_dev (n_h x n_st, ld = n_st) receives U.
+int pb_pod_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, int64_t ldu_host, double* U_dev,
+                double eps, int n_L_in, int mode, int* n_L) {
+    if (!ctx || !n_L || !U_host || !U_dev) return PB_ERR_ARG;
+    if (n_h <= 0 || n_st <= 0 || ldu_host < n_st) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod_host: bad shape");
+    const int64_t chunk_rows_min = 8192;
+    int nchunks = (int)std::min<int64_t>(16, n_h / chunk_rows_min);
+    if (n_h < n_st || nchunks < 2 || n_st > 8192) {        // small or wide: plain upload, then the device path
+        PB_CUDA(ctx, cudaMemcpy2DAsync(U_dev, n_st * sizeof(double), U_host, ldu_host * sizeof(double),
+                                       n_st * sizeof(double), n_h, cudaMemcpyHostToDevice, ctx->stream));
+        return pb_pod(ctx, U_dev, n_h, n_st, n_st, eps, n_L_in, mode, n_L);
     }
+    cudaEventRecord(ctx->ev2, ctx->stream);
+    const int64_t m = n_st;
+    if (!ctx->copy_stream) {
+        PB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int c = 0; c < 16; ++c) PB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->chunk_ev[c], cudaEventDisableTiming));
+    }
+    PB_TRY(pb_reserve(ctx, &ctx->Gbuf, &ctx->G_cap, (size_t)m * m));
+    PB_TRY(pb_reserve(ctx, &ctx->Gpart, &ctx->Gpart_cap, (size_t)m * m * nchunks));
+    int64_t rows_c = (n_h + nchunks - 1) / nchunks; rows_c = (rows_c + 15) / 16 * 16;
+    // the copy stream must not start overwriting U_dev before earlier work on the compute stream is done
+    PB_CUDA(ctx, cudaEventRecord(ctx->chunk_ev[0], ctx->stream));
+    PB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[0], 0));
+    int used = 0;
+    Timer tg(ctx, PB_T_GRAM);
+    for (int c = 0; c < nchunks; ++c) {
+        const int64_t r0 = (int64_t)c * rows_c, nr = std::min(rows_c, n_h - r0);
+        if (nr <= 0) break;
+        PB_CUDA(ctx, cudaMemcpy2DAsync(U_dev + r0 * n_st, n_st * sizeof(double), U_host + r0 * ldu_host,
+                                       ldu_host * sizeof(double), n_st * sizeof(double), nr, cudaMemcpyHostToDevice,
+                                       ctx->copy_stream));
+        PB_CUDA(ctx, cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
+        PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
+        PB_TRY(pbi_gemm_tn(ctx, U_dev + r0 * n_st, n_st, m, U_dev + r0 * n_st, n_st, m, nr, ctx->Gpart + (size_t)c * m * m, m, 1));
+        ++used;
+    }
+    sum_partials_kernel<<<(unsigned)((m * m + 255) / 256), 256, 0, ctx->stream>>>(ctx->Gpart, used, m * m, ctx->Gbuf);
+    PB_LAUNCH_CHECK(ctx);
+    tg.stop();
+    ctx->wide = false;
+    PB_TRY(pod_after_gram(ctx, U_dev, n_h, m, n_st, eps, n_L_in, mode, n_L));
     cudaEventRecord(ctx->ev3, ctx->stream); cudaEventSynchronize(ctx->ev3);
     float ms = 0; cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3); ctx->ms[PB_T_POD_TOTAL] = ms;
     return PB_OK;

@@ -20,6 +20,9 @@ struct pb_ctx {
     cudaEvent_t evk0 = nullptr, evk1 = nullptr;     // around the TN main kernel
     cudaEvent_t evr0 = nullptr, evr1 = nullptr;     // user region timer
     bool tn_timing_pending = false;
+    cudaStream_t copy_stream = nullptr;             // pb_pod_host: chunked upload overlapped with the Gram
+    cudaEvent_t chunk_ev[16] = {nullptr};
+    double* Gpart = nullptr; size_t Gpart_cap = 0;
 
     // split-K workspace of the TN products (grown on demand)
     double* ws = nullptr;  size_t ws_bytes = 0;

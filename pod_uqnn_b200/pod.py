@@ -43,12 +43,27 @@ def perform_pod(U, eps=0., n_L=0, verbose=True, *, mode=DEFAULT_MODE, ctx=None, 
     """
     ctx = ctx or _lib.default_context()
     on_device = isinstance(U, DeviceArray)
-    Ud = U if on_device else ctx.to_device(np.asarray(U, dtype=np.float64))
     if verbose:
         print("Contructing the reduced bases V")     # pod.py:38 (sic)
-    Vd, sig = pod_device(ctx, Ud, eps, n_L, mode)
-    V = Vd if on_device else Vd.download()
+    if on_device:
+        Vd, sig = pod_device(ctx, U, eps, n_L, mode)
+        return (Vd, sig) if return_sigma else Vd
+    Vd, sig = pod_host(ctx, U, eps, n_L, mode)
+    V = Vd.download()
     return (V, sig) if return_sigma else V
+
+
+def pod_host(ctx, U, eps=0., n_L=0, mode=DEFAULT_MODE):
+    """POD of a host matrix: chunked upload overlapped with the Gram (pb_pod_host)."""
+    U = np.ascontiguousarray(U, dtype=np.float64)
+    n_h, n_st = U.shape
+    Ud = ctx.alloc(n_h, n_st)
+    nl = C.c_int()
+    ctx.check(_lib.lib().pb_pod_host(ctx.h, U.ctypes.data, n_h, n_st, n_st, Ud.ptr, float(eps), int(n_L),
+                                     POD_MODES[mode], C.byref(nl)))
+    V = ctx.alloc(n_h, nl.value)
+    ctx.check(_lib.lib().pb_pod_basis_full(ctx.h, Ud.ptr, n_h, n_st, Ud.ld, V.ptr, V.ld))
+    return V, pod_sigma(ctx)
 
 
 def perform_fast_pod(U, eps, eps_init, *, mode=DEFAULT_MODE, ctx=None, return_ranks=False):

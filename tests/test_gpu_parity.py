@@ -297,3 +297,23 @@ def test_error_behaviour(ctx):
         pod_device(ctx, ctx.to_device(np.ones((4, 4))), eps=1.5)
     with pytest.raises(ValueError):
         pod_device(ctx, ctx.to_device(np.zeros((8, 4))), eps=1e-4)                  # zero matrix: no pivot
+
+
+def test_pod_host_pipelined_upload(ctx):
+    """pb_pod_host (chunked upload overlapped with the Gram) == upload + pb_pod, incl. a strided host matrix."""
+    rng = np.random.default_rng(21)
+    n_h, n_st = 40000, 96
+    U = (rng.standard_normal((n_h, 12)) * 2. ** -np.arange(12)) @ rng.standard_normal((12, n_st))
+    V1, s1 = perform_pod(U, 1e-8, 0, False, mode="gram2", ctx=ctx, return_sigma=True)          # host path
+    V2d, s2 = pod_device(ctx, ctx.to_device(U), 1e-8, 0, "gram2")
+    assert V1.shape == V2d.shape
+    assert cmp.largest_principal_angle(V1, V2d.download()) <= 1e-10
+    assert cmp.sigma_error(s1, s2) <= 1e-12
+    Vr = po.perform_pod(U, 1e-8)
+    assert V1.shape == Vr.shape and cmp.largest_principal_angle(V1, Vr) <= cmp.TOL_ANGLE
+    # leading dimension of the host matrix larger than n_st
+    big = np.zeros((n_h, n_st + 5)); big[:, :n_st] = U
+    L = _lib.lib()
+    Ud, nl = ctx.alloc(n_h, n_st), C.c_int()
+    ctx.check(L.pb_pod_host(ctx.h, big.ctypes.data, n_h, n_st, n_st + 5, Ud.ptr, 1e-8, 0, 1, C.byref(nl)))
+    assert nl.value == Vr.shape[1] and np.array_equal(Ud.download(), U)
