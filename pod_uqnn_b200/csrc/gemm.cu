@@ -22,7 +22,7 @@ using namespace pbt;
 // TN kernel
 // ---------------------------------------------------------------------------
 template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES, bool ALIGN16>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, (BM <= 32) ? 2 : 1)     // skinny (HBM-bound) tiles: two CTAs per SM
 gemm_tn_kernel(const double* __restrict__ A, int64_t lda, int ka,
                const double* __restrict__ B, int64_t ldb, int kb,
                int64_t rows, int64_t rows_per_split,
@@ -147,7 +147,7 @@ __global__ void symmetrize_kernel(double* __restrict__ C, int n, int64_t ldc, in
 // NN kernel (BM = 128 rows per CTA)
 // ---------------------------------------------------------------------------
 template <int BN, int WARPS_M, int WARPS_N, int STAGES, bool ALIGN_A, bool ALIGN_B>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, (BN <= 32) ? 2 : 1)     // skinny (HBM-bound) tiles: two CTAs per SM
 gemm_nn_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int m,
                const double* __restrict__ B, int64_t ldb, int k,
                double* __restrict__ Y, int64_t ldy,
@@ -316,7 +316,7 @@ int launch_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const doubl
     constexpr int STAGES = 4;
     const int tiles_m = (int)((ka + BM - 1) / BM), tiles_n = (int)((kb + BN - 1) / BN);
     const int tiles = sym ? tiles_n * (tiles_n + 1) / 2 : tiles_m * tiles_n;
-    const int splits = choose_splits(tiles * bt.count, rows, ctx->sm_count);
+    const int splits = choose_splits(tiles * bt.count, rows, ctx->sm_count * ((BM <= 32) ? 2 : 1));
     int64_t rps = (rows + splits - 1) / splits;
     rps = (rps + BK - 1) / BK * BK;
     const bool direct = (splits == 1 && !sym);
