@@ -305,6 +305,8 @@ int choose_splits(int tiles, int64_t rows, int sms) {
 }  // namespace
 int pbi_gram_tma(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int64_t rows, int splits,
                  int64_t rows_per_split, double* ws, int64_t split_stride, bool time_it);
+int pbi_gram_streamk(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int64_t rows, double* C, int64_t ldc,
+                     bool time_it);
 namespace {
 bool g_time_tn = false;   // set per call by pbi_gemm_tn (contexts are single-threaded)
 
@@ -330,6 +332,15 @@ int launch_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const doubl
     const bool al = aligned16(A, lda) && aligned16(B, ldb) && (bt.sA % 2 == 0) && (bt.sB % 2 == 0);
     size_t smem = (size_t)STAGES * BK * ((BM + 4) + (BN + 4)) * sizeof(double);
     dim3 grid(tiles, splits, bt.count);
+    if (sym && BM == 128 && BN == 128 && bt.count == 1) {     // stream-K TMA kernel: writes C itself
+        int rc = pbi_gram_streamk(ctx, A, lda, ka, rows, C, ldc, g_time_tn);
+        if (rc < 0) return rc;
+        if (rc == PB_OK) {
+            symmetrize_kernel<<<(unsigned)(((int64_t)ka * kb + 255) / 256), 256, 0, ctx->stream>>>(C, (int)ka, ldc, 0);
+            PB_LAUNCH_CHECK(ctx);
+            return PB_OK;
+        }
+    }
     if (sym && BM == 128 && BN == 128 && bt.count == 1) {     // TMA + mbarrier pipeline when the layout allows it
         int rc = pbi_gram_tma(ctx, A, lda, ka, rows, splits, rps, ctx->ws, split_stride, g_time_tn);
         if (rc < 0) return rc;

@@ -17,6 +17,8 @@
 #include "tile_ops.cuh"
 #include <cuda.h>
 #include <cstdlib>
+#include <vector>
+#include <algorithm>
 
 namespace {
 using pbt::dmma884;
@@ -148,6 +150,142 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ka, int64_t rows, 
     }
 }
 
+// ---------------------------------------------------------------------------
+// stream-K variant: one persistent CTA per SM owns a contiguous range of the linearised
+// (tile, k-iteration) space, weighted 4 per off-diagonal and 3 per diagonal iteration.
+//   * no wave quantisation and no split heuristics: every SM gets the same weight;
+//   * diagonal tiles skip their strictly-lower 64 x 64 quadrant: warps 0-3 keep their 64 x 32 tiles of
+//     the upper half, warps 4-7 take 64 x 16 tiles of the lower-right quadrant, so each SM sub-partition
+//     issues 3/4 of the DMMAs of an off-diagonal tile (the consumer warps are decoupled, no barrier);
+//   * the partition is static (host tables), so the partial tiles are summed in a fixed order.
+struct SegEntry { int ti, tj, k0, k1, slot; };
+
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+gram_streamk_kernel(const __grid_constant__ CUtensorMap tmap, const SegEntry* __restrict__ segs,
+                    const int* __restrict__ seg_begin, double* __restrict__ ws) {
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    double* panels = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)TSTAGES * STAGE_BYTES);
+    uint64_t* empty = full + TSTAGES;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < TSTAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncthreads();
+    const int sb = seg_begin[blockIdx.x], se = seg_begin[blockIdx.x + 1];
+
+    if (warp == 8) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int sg = sb; sg < se; ++sg) {
+                const SegEntry e = segs[sg];
+                const bool diag = (e.ti == e.tj);
+                for (int k = e.k0; k < e.k1; ++k, ++it) {
+                    const int s = it % TSTAGES; const uint32_t ph = (it / TSTAGES) & 1;
+                    mbar_wait(empty + s, ph ^ 1);
+                    mbar_expect_tx(full + s, diag ? STAGE_BYTES / 2 : STAGE_BYTES);
+                    double* dst = panels + (size_t)s * 2 * PANEL_DOUBLES;
+                    tma_load_3d(dst, &tmap, full + s, 0, k * TBK, e.ti * 16);
+                    if (!diag) tma_load_3d(dst + PANEL_DOUBLES, &tmap, full + s, 0, k * TBK, e.tj * 16);
+                }
+            }
+        }
+        return;
+    }
+
+    const int wm = warp >> 2, wn = warp & 3;
+    const int lk = lane & 3, lg = lane >> 2;
+    int koff[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        const int k = (kk >> 1) * 8 + (kk & 1) * 2 + (lk & 1) + (lk >> 1) * 4;
+        koff[kk] = k * 8 + ((((lg >> 1) ^ ((k >> 1) & 3))) << 1) + (lg & 1);
+    }
+    uint32_t it = 0;
+    for (int sg = sb; sg < se; ++sg) {
+        const SegEntry e = segs[sg];
+        const bool diag = (e.ti == e.tj);
+        const bool half = diag && wm == 1;                 // lower-right quadrant only, 16 columns per warp
+        const int col0 = half ? 64 + wn * 16 : wn * 32;   // first column of this warp inside the tile
+        double acc[8][4][2];
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { acc[t][u][0] = 0.; acc[t][u][1] = 0.; }
+        for (int k = e.k0; k < e.k1; ++k, ++it) {
+            const int s = it % TSTAGES; const uint32_t ph = (it / TSTAGES) & 1;
+            mbar_wait(full + s, ph);
+            const double* As = panels + (size_t)s * 2 * PANEL_DOUBLES;
+            const double* Bs = diag ? As : As + PANEL_DOUBLES;
+            const double* ap = As + (wm * 8) * (TBK * 8);
+            const double* bp = Bs + (col0 / 8) * (TBK * 8);
+            if (!half) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    double a[8], b[4];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) a[t] = ap[t * (TBK * 8) + koff[kk]];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) b[u] = bp[u * (TBK * 8) + koff[kk]];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t)
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) dmma884(acc[t][u][0], acc[t][u][1], a[t], b[u]);
+                }
+            } else {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    double a[8], b[2];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) a[t] = ap[t * (TBK * 8) + koff[kk]];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) b[u] = bp[u * (TBK * 8) + koff[kk]];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t)
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) dmma884(acc[t][u][0], acc[t][u][1], a[t], b[u]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + s);
+        }
+        // partial tile -> workspace slot (dense 128 x 128)
+        double* o = ws + (size_t)e.slot * (128 * 128);
+        const int nu = half ? 2 : 4;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int i = wm * 64 + t * 8 + lg;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (u < nu) {
+                    const int j = col0 + u * 8 + 2 * lk;
+                    *reinterpret_cast<double2*>(o + i * 128 + j) = make_double2(acc[t][u][0], acc[t][u][1]);
+                }
+            }
+        }
+    }
+}
+
+// C[i][j] = sum over the slots of tile (ti, tj) in table order; lower tiles mirrored from the upper ones
+__global__ void streamk_reduce_kernel(const double* __restrict__ ws, const int* __restrict__ tile_src_off,
+                                      const int* __restrict__ tile_src, int ka, int tiles_n,
+                                      double* __restrict__ C, int64_t ldc) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)ka * ka) return;
+    const int i = (int)(idx / ka), j = (int)(idx % ka);
+    int si = i, sj = j;
+    if (j / 128 < i / 128) { si = j; sj = i; }
+    const int ti = si / 128, tj = sj / 128;
+    const int t = ti * tiles_n - ti * (ti - 1) / 2 + (tj - ti);
+    const int li = si % 128, lj = sj % 128;
+    double s = 0.;
+    for (int q = tile_src_off[t]; q < tile_src_off[t + 1]; ++q) s += ws[(size_t)tile_src[q] * (128 * 128) + li * 128 + lj];
+    C[(int64_t)i * ldc + j] = s;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -196,5 +334,90 @@ int pbi_gram_tma(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int64_t 
                                                                             split_stride, tiles_n);
     PB_LAUNCH_CHECK(ctx);
     if (time_it) { cudaEventRecord(ctx->evk1, ctx->stream); ctx->tn_timing_pending = true; }
+    return PB_OK;
+}
+
+
+// stream-K launcher: returns PB_OK when it produced C (upper part; the caller symmetrises), 1 to fall back
+int pbi_gram_streamk(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int64_t rows, double* C, int64_t ldc,
+                     bool time_it) {
+    static const bool enabled = []{ const char* e = getenv("PB_GRAM_STREAMK"); return !e || atoi(e) != 0; }();
+    if (!enabled) return 1;
+    if ((lda % 2) || (ka % 8) || (reinterpret_cast<uintptr_t>(A) % 16) || rows >= (1ll << 31) - 64) return 1;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return 1;
+    const int tiles_n = (int)((ka + 127) / 128);
+    const int T = tiles_n * (tiles_n + 1) / 2;
+    const int P = ctx->sm_count;
+    const int64_t nk = (rows + TBK - 1) / TBK;
+    if (nk * T < 4 * (int64_t)P) return 1;                 // too little work to spread: use the tiled kernel
+    CUtensorMap map;
+    const cuuint64_t gdim[3] = {8, (cuuint64_t)rows, (cuuint64_t)(ka / 8)};
+    const cuuint64_t gstr[2] = {(cuuint64_t)lda * 8, 64};
+    const cuuint32_t box[3] = {8, (cuuint32_t)TBK, 16};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(A), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return 1;
+
+    // ---- static partition (cached per shape)
+    struct Plan { int64_t ka = -1, rows = -1; int P = 0; int nslots = 0; std::vector<SegEntry> segs; std::vector<int> seg_begin,
+                  tile_off, tile_src; int* d_tab = nullptr; size_t d_cap = 0; };
+    static thread_local Plan plan;
+    if (plan.ka != ka || plan.rows != rows || plan.P != P) {
+        plan.ka = ka; plan.rows = rows; plan.P = P; plan.segs.clear(); plan.seg_begin.assign(P + 1, 0);
+        std::vector<int> tti(T), ttj(T); std::vector<int64_t> cum(T + 1, 0);
+        int t = 0;
+        for (int i = 0; i < tiles_n; ++i) for (int j = i; j < tiles_n; ++j, ++t) {
+            tti[t] = i; ttj[t] = j; cum[t + 1] = cum[t] + nk * (i == j ? 3 : 4);
+        }
+        const int64_t W = cum[T];
+        auto locate = [&](int64_t b, int& tile, int64_t& k) {
+            if (b >= W) { tile = T; k = 0; return; }
+            int lo = (int)(std::upper_bound(cum.begin(), cum.end(), b) - cum.begin()) - 1;
+            tile = lo; k = (b - cum[lo]) / (tti[lo] == ttj[lo] ? 3 : 4);
+        };
+        std::vector<std::vector<int>> src(T);
+        int slot = 0;
+        for (int s = 0; s < P; ++s) {
+            int t0, t1; int64_t k0, k1;
+            locate(W / P * s + (W % P) * s / P, t0, k0);
+            locate(s + 1 == P ? W : W / P * (s + 1) + (W % P) * (s + 1) / P, t1, k1);
+            plan.seg_begin[s] = (int)plan.segs.size();
+            for (int tt = t0; tt <= t1 && tt < T; ++tt) {
+                const int64_t ks = (tt == t0) ? k0 : 0, ke = (tt == t1) ? k1 : nk;
+                if (ke > ks) { plan.segs.push_back({tti[tt], ttj[tt], (int)ks, (int)ke, slot}); src[tt].push_back(slot); ++slot; }
+            }
+        }
+        plan.seg_begin[P] = (int)plan.segs.size();
+        plan.nslots = slot;
+        plan.tile_off.assign(T + 1, 0); plan.tile_src.clear();
+        for (int tt = 0; tt < T; ++tt) { plan.tile_off[tt] = (int)plan.tile_src.size(); for (int v : src[tt]) plan.tile_src.push_back(v); }
+        plan.tile_off[T] = (int)plan.tile_src.size();
+        // device tables: [segs (5 ints each)] [seg_begin (P+1)] [tile_off (T+1)] [tile_src]
+        const size_t n_int = plan.segs.size() * 5 + (P + 1) + (T + 1) + plan.tile_src.size();
+        if (plan.d_cap < n_int) { if (plan.d_tab) cudaFree(plan.d_tab); PB_CUDA(ctx, cudaMalloc(&plan.d_tab, n_int * sizeof(int))); plan.d_cap = n_int; }
+        std::vector<int> host(n_int); size_t o = 0;
+        memcpy(host.data(), plan.segs.data(), plan.segs.size() * 5 * sizeof(int)); o += plan.segs.size() * 5;
+        memcpy(host.data() + o, plan.seg_begin.data(), (P + 1) * sizeof(int)); o += P + 1;
+        memcpy(host.data() + o, plan.tile_off.data(), (T + 1) * sizeof(int)); o += T + 1;
+        memcpy(host.data() + o, plan.tile_src.data(), plan.tile_src.size() * sizeof(int));
+        PB_CUDA(ctx, cudaMemcpyAsync(plan.d_tab, host.data(), n_int * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    const SegEntry* d_segs = reinterpret_cast<const SegEntry*>(plan.d_tab);
+    const int* d_seg_begin = plan.d_tab + plan.segs.size() * 5;
+    const int* d_tile_off = d_seg_begin + (P + 1);
+    const int* d_tile_src = d_tile_off + (T + 1);
+    PB_TRY(pb_reserve(ctx, &ctx->ws, &ctx->ws_bytes, (size_t)plan.nslots * 128 * 128));
+    const size_t smem = (size_t)TSTAGES * STAGE_BYTES + 2 * TSTAGES * sizeof(uint64_t) + 1024;
+    PB_CUDA(ctx, cudaFuncSetAttribute(gram_streamk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (time_it) cudaEventRecord(ctx->evk0, ctx->stream);
+    gram_streamk_kernel<<<P, TMA_THREADS, smem, ctx->stream>>>(map, d_segs, d_seg_begin, ctx->ws);
+    PB_LAUNCH_CHECK(ctx);
+    if (time_it) { cudaEventRecord(ctx->evk1, ctx->stream); ctx->tn_timing_pending = true; }
+    const int64_t n = ka * ka;
+    streamk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->ws, d_tile_off, d_tile_src, (int)ka, tiles_n, C, ldc);
+    PB_LAUNCH_CHECK(ctx);
     return PB_OK;
 }

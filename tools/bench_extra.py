@@ -65,7 +65,7 @@ if want("c5"):
     r = {}
     for n_h, n_s in ((250_000, 4096), (1_250_000, 4096)):
         Ud = ctx.alloc(n_h, n_s)
-        t = time.time(); ctx.check(L.pb_dct_lowrank(ctx.h, 10_000_000, n_s, 256, 0.25, 0, n_h, Ud.ptr, Ud.ld)); ctx.sync()
+        t = time.time(); ctx.check(L.pb_dct_lowrank(ctx.h, n_h, n_s, 256, 0.25, 0, n_h, Ud.ptr, Ud.ld)); ctx.sync()
         gen_s = time.time() - t
         rr = {"gen_s": gen_s}
         for mode in ("gram", "gram2"):
