@@ -414,6 +414,8 @@ int pbi_gemm_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const dou
         if (sym) { symmetrize_kernel<<<(unsigned)((ka * kb + 255) / 256), 256, 0, ctx->stream>>>(C, (int)ka, ldc, 0); PB_LAUNCH_CHECK(ctx); }
         return PB_OK;
     }
+    if (!sym && ka > 32 && ka <= 64) return launch_tn<64, 128, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);
+    if (!sym && ka > 64 && ka <= 96) return launch_tn<96, 128, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);
     if (sym || ka > 32) return launch_tn<128, 128, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, sym);
     if (ka <= 16) return launch_tn<16, 128, 1, 8>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);   // n_L <= 16: HBM bound
     return launch_tn<32, 128, 1, 8>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);
@@ -426,13 +428,15 @@ int pbi_gemm_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t
                                                (long long)rows, (long long)m, (long long)k);
     double* part = nullptr;
     const bool wide = k > 32;
-    const int bn = wide ? 128 : (k <= 16 ? 16 : 32);
+    const int bn = k > 96 ? 128 : k > 64 ? 96 : k > 32 ? 64 : (k <= 16 ? 16 : 32);
     const int ntiles = (int)((k + bn - 1) / bn);
     if (Uref) {
         PB_TRY(pb_reserve(ctx, &ctx->ws, &ctx->ws_bytes, (size_t)ntiles * rows));
         part = ctx->ws;
     }
-    if (wide) PB_TRY((launch_nn<128, 2, 4>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
+    if (k > 96) PB_TRY((launch_nn<128, 2, 4>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
+    else if (k > 64) PB_TRY((launch_nn<96, 2, 4>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
+    else if (wide) PB_TRY((launch_nn<64, 4, 2>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
     else if (k <= 16) PB_TRY((launch_nn<16, 8, 1>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
     else      PB_TRY((launch_nn<32, 8, 1>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
     if (Uref) {
