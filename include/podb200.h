@@ -203,8 +203,12 @@ int  pb_ensemble_predict(pb_ctx* ctx, int n_members, int n_layers, const int* di
                          const double* weights_dev, int norm_kind,
                          const double* norm_a_dev, const double* norm_b_dev, double soft_0,
                          const double* X_dev, int64_t N, double* v_mean_dev, double* v_sig_dev);
-/* closed-form U-level moments of PodnnModel.predict (podnnmodel.py:366-379):
- * U_mean = V v_mean^T, U_sig = sqrt((V*V) (v_sig^2)^T); plus optional Monte-Carlo variant. */
+/* U-level prediction, PodnnModel.predict (podnnmodel.py:366-379).
+ * samples == 0: the exact moments of the reference's Monte-Carlo loop, U_mean = V v_mean^T,
+ *               U_sig = sqrt((V*V) (v_sig^2)^T).
+ * samples >= 2: the loop itself: `samples` draws v ~ N(v_mean, v_sig) from a Philox4x32-10 stream keyed
+ *               by (seed, draw, point, mode), U_i = V v_i^T accumulated into running sum / sum of squares in
+ *               the GEMM epilogue (U_i is never stored), then mean and the unbiased sample sigma (:376-378). */
 int  pb_predict_U(pb_ctx* ctx, const double* V_dev, int64_t ldv, int64_t n_rows, int n_L,
                   const double* v_mean_dev, const double* v_sig_dev, int64_t N,
                   int samples, uint64_t seed, double* U_mean_dev, double* U_sig_dev, int64_t ldo);

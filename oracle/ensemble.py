@@ -127,3 +127,20 @@ def predict_mc(V, v_pred, v_pred_sig, samples, rng):
     U_pred = U_sum / samples
     U_pred_sig = np.sqrt((samples * U_sum_sq - U_sum**2) / (samples * (samples - 1)))
     return U_pred, U_pred_sig
+
+
+def predict_mc_moments(V, X_v, members, n_L, soft_0, norm, norm_bounds, pod_sig=None):
+    """PodnnModel.predict_mc (podnnmodel.py:344-364) with each member's Monte-Carlo loop
+    (predict_dist :330-342) replaced by its exact moments."""
+    n_M = len(members)
+    U_s = np.zeros((V.shape[0], X_v.shape[0], n_M))
+    S_s = np.zeros_like(U_s)
+    for i, w in enumerate(members):
+        mu, var = member_predict(X_v, w, n_L, soft_0, norm, norm_bounds)
+        U_s[:, :, i], S_s[:, :, i] = predict_U_moments(V, mu, np.sqrt(var))
+    U_pred = U_s.mean(-1)
+    U_pred_var = (S_s ** 2 + U_s ** 2).mean(-1) - U_pred ** 2
+    U_pred_sig = np.sqrt(U_pred_var)
+    if pod_sig is not None:
+        U_pred_sig += pod_sig[:, np.newaxis]
+    return U_pred, U_pred_sig

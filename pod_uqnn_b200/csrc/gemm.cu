@@ -217,7 +217,11 @@ gemm_nn_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int m,
     }
     cp_async_wait<0>();
 
-    const bool want_sig = (Uref != nullptr);
+    // epilogues: Uref with ldu > 0 -> pod_sig partial row sums; ldu < 0 -> Monte-Carlo moment accumulation
+    // (Uref = running sum, sig_part = running sum of squares, both rows x k with leading dimension -ldu)
+    const bool want_mom = (Uref != nullptr) && ldu < 0;
+    const bool want_sig = (Uref != nullptr) && !want_mom;
+    double* msum = const_cast<double*>(Uref); const int64_t ldm_ = -ldu;
 #pragma unroll
     for (int t = 0; t < TM; ++t) {
         const int rl = wm * WM + t * 8 + lg;
@@ -230,6 +234,10 @@ gemm_nn_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int m,
                 if (Y) {
                     if (j < k)     Y[h * ldy + j]     = acc[t][u][0];
                     if (j + 1 < k) Y[h * ldy + j + 1] = acc[t][u][1];
+                }
+                if (want_mom) {
+                    if (j < k)     { msum[h * ldm_ + j] += acc[t][u][0];     sig_part[h * ldm_ + j] += acc[t][u][0] * acc[t][u][0]; }
+                    if (j + 1 < k) { msum[h * ldm_ + j + 1] += acc[t][u][1]; sig_part[h * ldm_ + j + 1] += acc[t][u][1] * acc[t][u][1]; }
                 }
                 if (want_sig) {
                     if (j < k)     rs += fabs(Uref[h * ldu + j] - acc[t][u][0]);
@@ -430,7 +438,9 @@ int pbi_gemm_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t
     const bool wide = k > 32;
     const int bn = k > 96 ? 128 : k > 64 ? 96 : k > 32 ? 64 : (k <= 16 ? 16 : 32);
     const int ntiles = (int)((k + bn - 1) / bn);
-    if (Uref) {
+    const bool moments = Uref && ldu < 0;
+    if (moments) part = sig_out;                     // running sum of squares, accumulated in place
+    else if (Uref) {
         PB_TRY(pb_reserve(ctx, &ctx->ws, &ctx->ws_bytes, (size_t)ntiles * rows));
         part = ctx->ws;
     }
@@ -439,7 +449,7 @@ int pbi_gemm_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t
     else if (wide) PB_TRY((launch_nn<64, 4, 2>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
     else if (k <= 16) PB_TRY((launch_nn<16, 8, 1>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
     else      PB_TRY((launch_nn<32, 8, 1>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
-    if (Uref) {
+    if (Uref && !moments) {
         sig_reduce_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(
             part, ntiles, rows, 0.5 / (double)k, sig_out);
         PB_LAUNCH_CHECK(ctx);

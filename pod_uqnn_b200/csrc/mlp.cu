@@ -289,6 +289,51 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) ensemble_kernel(MlpArgs a) {
     }
 }
 
+// ---- Monte-Carlo version of PodnnModel.predict (podnnmodel.py:366-379) -----------------------------
+// Philox4x32-10 (counter based: draw, point, mode -> 128 random bits), Box-Muller to N(0, 1).
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        c[1] = (uint32_t)p1; c[3] = (uint32_t)p0; c[0] = n0; c[2] = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+// vT[j][p] = v_mean[p][j] + v_sig[p][j] * z(draw, p, j)      (n_L x ldb, the B operand of V v^T)
+__global__ void sample_v_kernel(const double* __restrict__ v_mean, const double* __restrict__ v_sig, int64_t N, int n_L,
+                                uint64_t seed, uint32_t draw, double* __restrict__ vT, int64_t ldb) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // pair index: two normals per Philox call
+    const int64_t total = N * n_L;
+    if (2 * idx >= total) return;
+    uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), draw, 0x5eedu};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    // two uniforms in (0, 1) with 53 / 32 bits, Box-Muller
+    const double u1 = ((double)(((uint64_t)c[0] << 21) ^ (c[1] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+    const double u2 = ((double)c[2] + 0.5) * (1.0 / 4294967296.0);
+    const double rad = sqrt(-2. * log(u1));
+    double sn, cs; sincospi(2. * u2, &sn, &cs);
+    const double z[2] = {rad * cs, rad * sn};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int64_t e = 2 * idx + q;
+        if (e < total) {
+            const int64_t p = e / n_L; const int j = (int)(e % n_L);
+            vT[(int64_t)j * ldb + p] = v_mean[e] + v_sig[e] * z[q];
+        }
+    }
+}
+// U_pred = sum / S ; U_sig = sqrt((S sumsq - sum^2) / (S (S - 1)))     (podnnmodel.py:376-378)
+__global__ void mc_finalize_kernel(double* __restrict__ sum, double* __restrict__ sq, int64_t rows, int64_t cols, int64_t ld,
+                                   double S) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int64_t o = (i / cols) * ld + i % cols;
+    const double a = sum[o], b = sq[o];
+    sum[o] = a / S;
+    sq[o] = sqrt(fmax(S * b - a * a, 0.) / (S * (S - 1.)));
+}
+
 // closed-form U-level moments: U_mean = V v_mean^T ; U_sig = sqrt((V*V) (v_sig^2)^T)
 __global__ void square_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -359,9 +404,28 @@ extern "C" int pb_predict_U(pb_ctx* ctx, const double* V_dev, int64_t ldv, int64
                             const double* v_mean_dev, const double* v_sig_dev, int64_t N,
                             int samples, uint64_t seed, double* U_mean_dev, double* U_sig_dev, int64_t ldo) {
     if (!ctx) return PB_ERR_ARG;
-    (void)seed;
-    if (samples != 0) PB_FAIL(ctx, PB_ERR_ARG, "pb_predict_U: only the closed-form moments (samples = 0) are built in this round");
     if (n_L <= 0 || N <= 0 || n_rows <= 0 || ldo < N) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_predict_U: bad shape");
+    if (samples < 0 || samples == 1) PB_FAIL(ctx, PB_ERR_ARG, "pb_predict_U: samples must be 0 (closed form) or >= 2");
+    if (samples > 0) {
+        // the reference's loop: S draws of v ~ N(v_mean, v_sig), U_i = V v_i^T, running sum and sum of squares
+        if (!U_mean_dev || !U_sig_dev) PB_FAIL(ctx, PB_ERR_ARG, "pb_predict_U: the Monte-Carlo path needs both outputs");
+        const int64_t ldb = (N + 1) / 2 * 2;
+        PB_TRY(pb_reserve(ctx, &ctx->Bmat, &ctx->B_cap, (size_t)n_L * ldb));
+        PB_CUDA(ctx, cudaMemset2DAsync(U_mean_dev, ldo * sizeof(double), 0, N * sizeof(double), n_rows, ctx->stream));
+        PB_CUDA(ctx, cudaMemset2DAsync(U_sig_dev, ldo * sizeof(double), 0, N * sizeof(double), n_rows, ctx->stream));
+        const int64_t pairs = (N * n_L + 1) / 2;
+        for (int d = 0; d < samples; ++d) {
+            sample_v_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, ctx->stream>>>(v_mean_dev, v_sig_dev, N, n_L, seed,
+                                                                                  (uint32_t)d, ctx->Bmat, ldb);
+            PB_LAUNCH_CHECK(ctx);
+            // fused epilogue: U_i is never stored, the tile adds itself to the running moments
+            PB_TRY(pbi_gemm_nn(ctx, V_dev, ldv, n_rows, n_L, ctx->Bmat, ldb, N, nullptr, 0, U_mean_dev, -ldo, U_sig_dev));
+        }
+        const int64_t n = n_rows * N;
+        mc_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(U_mean_dev, U_sig_dev, n_rows, N, ldo, (double)samples);
+        PB_LAUNCH_CHECK(ctx);
+        return PB_OK;
+    }
     // U_mean = V (n_rows x n_L) * v_mean^T (n_L x N)
     const int64_t ldb = (N + 1) / 2 * 2;
     PB_TRY(pb_reserve(ctx, &ctx->Bmat, &ctx->B_cap, (size_t)n_L * ldb));

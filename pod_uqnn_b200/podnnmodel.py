@@ -244,19 +244,45 @@ class PodnnModel:
         vm, vs = ensemble_predict_device(self.ctx, members, layers, X_v, soft_0, norm, nb)
         return vm.download(), vs.download()
 
-    def predict(self, X_v, samples=100):
+    def predict(self, X_v, samples=100, *, monte_carlo=False, seed=0):
         """podnnmodel.py:366-379.  The reference averages `samples` TF-RNG draws of
-        v ~ N(v_pred, v_pred_sig); their exact moments U_pred = V v_pred^T,
-        U_pred_sig = sqrt((V*V) (v_pred_sig^2)^T) are returned (the limit samples -> inf)."""
+        v ~ N(v_pred, v_pred_sig).  By default their exact moments U_pred = V v_pred^T,
+        U_pred_sig = sqrt((V*V) (v_pred_sig^2)^T) are returned (the limit samples -> inf);
+        `monte_carlo=True` runs the reference's estimator itself on the GPU (Philox draws keyed by
+        `seed`, running sum / sum of squares fused into the V v^T tiles, unbiased sample sigma)."""
         print(f"Averaging {samples} model configurations...")
         ctx, Vd = self.ctx, self._ensure_V_dev()
         members, layers, soft_0, norm, nb = self._ensemble_args()
         vm, vs = ensemble_predict_device(ctx, members, layers, X_v, soft_0, norm, nb)
         N = vm.shape[0]
         Um, Us = ctx.alloc(self.n_h, N), ctx.alloc(self.n_h, N)
-        ctx.check(_lib.lib().pb_predict_U(ctx.h, Vd.ptr, Vd.ld, self.n_h, self.n_L, vm.ptr, vs.ptr, N, 0, 0,
-                                          Um.ptr, Us.ptr, Um.ld))
+        ctx.check(_lib.lib().pb_predict_U(ctx.h, Vd.ptr, Vd.ld, self.n_h, self.n_L, vm.ptr, vs.ptr, N,
+                                          int(samples) if monte_carlo else 0, int(seed), Um.ptr, Us.ptr, Um.ld))
         return Um.download(), Us.download()
+
+    def predict_mc(self, X_v, samples=100, *, monte_carlo=False, seed=0):
+        """podnnmodel.py:344-364: per-member U-level prediction (predict_dist :330-342), Gaussian mixture
+        over the members at the U level, plus pod_sig.  Per member the exact moments of its Monte-Carlo
+        loop are used unless `monte_carlo=True` (Philox draws on the GPU)."""
+        ctx, Vd = self.ctx, self._ensure_V_dev()
+        members, layers, soft_0, norm, nb = self._ensemble_args()
+        Xd = ctx.to_device(np.asarray(X_v, dtype=np.float64).reshape(-1, layers[0]))
+        N = Xd.shape[0]
+        U_sum, U_m2 = np.zeros((self.n_h, N)), np.zeros((self.n_h, N))
+        Um, Us = ctx.alloc(self.n_h, N), ctx.alloc(self.n_h, N)
+        print(f"Ensembling {len(members)} predictions...")
+        for i, w in enumerate(members):
+            vm, vs = ensemble_predict_device(ctx, [w], layers, Xd, soft_0, norm, nb)
+            ctx.check(_lib.lib().pb_predict_U(ctx.h, Vd.ptr, Vd.ld, self.n_h, self.n_L, vm.ptr, vs.ptr, N,
+                                              int(samples) if monte_carlo else 0, int(seed) + i, Um.ptr, Us.ptr, Um.ld))
+            U_i, sig_i = Um.download(), Us.download()
+            U_sum += U_i
+            U_m2 += sig_i ** 2 + U_i ** 2
+        U_pred = U_sum / len(members)
+        U_pred_sig = np.sqrt(U_m2 / len(members) - U_pred ** 2)
+        if self.pod_sig is not None:
+            U_pred_sig += self.pod_sig[:, np.newaxis]
+        return U_pred, U_pred_sig
 
     # ------------------------------------------------------------ layout helpers (host index maps)
     def get_u_tuple(self, n_t=None):

@@ -71,6 +71,12 @@ def test_predict_path(ctx, tmp_path):
     U_pred, U_sig = model.predict(X)
     Ur, Usr = ens.predict_U_moments(model.V, vr, sr)
     assert cmp.rel_err(U_pred, Ur) <= cmp.TOL_ENSEMBLE_REL and cmp.rel_err(U_sig, Usr) <= cmp.TOL_ENSEMBLE_REL
+    # predict_mc: per-member U-level moments, mixture at the U level, + pod_sig (podnnmodel.py:344-364)
+    Um, Usm = model.predict_mc(X)
+    Umr, Usmr = ens.predict_mc_moments(model.V, X, members, model.n_L, 0.01, "meanstd", nb, model.pod_sig)
+    assert cmp.rel_err(Um, Umr) <= cmp.TOL_ENSEMBLE_REL and cmp.rel_err(Usm, Usmr) <= cmp.TOL_ENSEMBLE_REL
+    U_mc, Us_mc = model.predict(X, samples=400, monte_carlo=True, seed=3)
+    assert np.all(np.abs(U_mc - Ur) <= 6. * Usr / np.sqrt(400) + 1e-12) and np.max(np.abs(Us_mc / Usr - 1.)) < 0.3
     # save / load round trip of the ensemble (npz weights + the reference's params tuple)
     model.save_model()
     m2 = PodnnModel.load(str(tmp_path), ctx=ctx)

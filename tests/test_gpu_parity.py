@@ -317,3 +317,33 @@ def test_pod_host_pipelined_upload(ctx):
     Ud, nl = ctx.alloc(n_h, n_st), C.c_int()
     ctx.check(L.pb_pod_host(ctx.h, big.ctypes.data, n_h, n_st, n_st + 5, Ud.ptr, 1e-8, 0, 1, C.byref(nl)))
     assert nl.value == Vr.shape[1] and np.array_equal(Ud.download(), U)
+
+
+def test_predict_U_monte_carlo(ctx):
+    """The reference's MC estimator on the GPU: reproducible per seed, converges to the closed form."""
+    rng = np.random.default_rng(18)
+    V = np.linalg.qr(rng.standard_normal((700, 11)))[0]
+    vm, vs = rng.standard_normal((45, 11)), rng.uniform(0.05, 0.2, (45, 11))
+    L = _lib.lib()
+    Vd, vmd, vsd = ctx.to_device(V), ctx.to_device(vm), ctx.to_device(vs)
+
+    def run(samples, seed):
+        Um, Us = ctx.alloc(700, 45), ctx.alloc(700, 45)
+        ctx.check(L.pb_predict_U(ctx.h, Vd.ptr, Vd.ld, 700, 11, vmd.ptr, vsd.ptr, 45, samples, seed, Um.ptr, Us.ptr, Um.ld))
+        return Um.download(), Us.download()
+
+    Um_r, Us_r = ens.predict_U_moments(V, vm, vs)
+    S = 2000
+    a = run(S, 7)
+    b = run(S, 7)
+    c = run(S, 8)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])          # counter-based: reproducible
+    assert not np.array_equal(a[0], c[0])
+    # sample mean within 6 standard errors everywhere, sample sigma within 12 % (S = 2000 -> ~1.6 % rms)
+    assert np.all(np.abs(a[0] - Um_r) <= 6. * Us_r / np.sqrt(S) + 1e-12)
+    assert np.max(np.abs(a[1] / Us_r - 1.)) < 0.12
+    # the draws are standard normal: pooled z-score of the mean error has unit variance
+    z = (a[0] - Um_r) / (Us_r / np.sqrt(S))
+    assert abs(z.mean()) < 0.1 and abs(z.std() - 1.) < 0.1
+    with pytest.raises(ValueError):
+        run(1, 0)
