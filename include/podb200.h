@@ -108,6 +108,15 @@ int  pb_snapshots(pb_ctx* ctx, int field, int dim, int64_t n_xyz,
                   int n_t, const double* t_dev,
                   int64_t row0, int64_t n_rows, double* U_dev, int64_t ldu);
 
+/* Ackley field with de-duplicated coordinates (tensor grids: n_x + n_y distinct values for n_x n_y nodes):
+ * ux/uy = the distinct x / y values, ix/iy (int32, n_xyz) = index of every node's coordinate in them.
+ * exp(.5 cos(w x)) and exp(.5 cos(w y)) are tabulated per (coordinate, sample); one exp per element is left
+ * and the kernel runs at the HBM write roofline.  Same result as pb_snapshots to ~1e-16 of max|U|. */
+int  pb_snapshots_ackley_indexed(pb_ctx* ctx, int64_t n_xyz, const double* X_dev, int n_ux, const double* ux_dev,
+                                 const int* ix_dev, int n_uy, const double* uy_dev, const int* iy_dev,
+                                 int64_t n_s, const double* mu_dev, int64_t row0, int64_t n_rows,
+                                 double* U_dev, int64_t ldu);
+
 /* Known-answer matrix U = sum_k s_k phi_k psi_k^T (DCT-II vectors, s_k = 2^(-decay k)),
  * rows [row0, row0+n_rows) of an n_h x n_s matrix, filled in HBM. */
 int  pb_dct_lowrank(pb_ctx* ctx, int64_t n_h, int64_t n_s, int r, double decay,

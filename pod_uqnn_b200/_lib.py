@@ -47,6 +47,7 @@ SIGNATURES = {
     "pb_host_alloc": (_int, [C.c_size_t, _pvp]),
     "pb_host_free": (_int, [_vp]),
     "pb_snapshots": (_int, [_vp, _int, _int, _i64, _vp, _i64, _int, _vp, _int, _vp, _i64, _i64, _vp, _i64]),
+    "pb_snapshots_ackley_indexed": (_int, [_vp, _i64, _vp, _int, _vp, _vp, _int, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _i64]),
     "pb_dct_lowrank": (_int, [_vp, _i64, _i64, _int, _dbl, _i64, _i64, _vp, _i64]),
     "pb_gram": (_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
     "pb_gemm_tn": (_int, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _vp]),
@@ -173,6 +174,17 @@ class Context:
     def to_device(self, host):
         host = np.ascontiguousarray(host, dtype=np.float64)
         return DeviceArray(self, host.shape).upload(host)
+
+    def to_device_i32(self, host):
+        """int32 index array in HBM (returned as a DeviceArray of raw bytes; shape is informational)."""
+        host = np.ascontiguousarray(host, dtype=np.int32)
+        d = DeviceArray.__new__(DeviceArray)
+        d.ctx, d.shape, d.nbytes, d.owned = self, host.shape, max(host.nbytes, 8), True
+        p = C.c_void_p()
+        self.check(lib().pb_malloc(self.h, d.nbytes, C.byref(p)))
+        d.ptr = p.value
+        self.check(lib().pb_upload(self.h, d.ptr, host.ctypes.data, host.nbytes))
+        return d
 
     def wrap(self, ptr, shape):
         """Borrow a device pointer (e.g. torch.Tensor.data_ptr()) without taking ownership."""

@@ -42,6 +42,16 @@ def snapshots_device(ctx, u, X, mu_lhs, n_t=0, t_min=0., t_max=0., row0=0, n_row
     Xd, mud = ctx.to_device(X), ctx.to_device(mu)
     td = ctx.to_device(t) if has_t else None
     U = out if out is not None else ctx.alloc(n_rows, n_st)
+    if f.name == "ackley" and dim == 2 and n_mu == 3:
+        # tensor grids repeat coordinates: tabulate the separable term per distinct x / y (fields.cu)
+        ux, ix = np.unique(X[0], return_inverse=True)
+        uy, iy = np.unique(X[1], return_inverse=True)
+        if 4 * (len(ux) + len(uy)) <= n_xyz:
+            uxd, uyd = ctx.to_device(ux), ctx.to_device(uy)
+            ixd, iyd = ctx.to_device_i32(ix), ctx.to_device_i32(iy)
+            ctx.check(_lib.lib().pb_snapshots_ackley_indexed(ctx.h, n_xyz, Xd.ptr, len(ux), uxd.ptr, ixd.ptr, len(uy),
+                                                             uyd.ptr, iyd.ptr, n_s, mud.ptr, row0, n_rows, U.ptr, U.ld))
+            return U, mu.copy(), None
     ctx.check(_lib.lib().pb_snapshots(ctx.h, f.field_id, dim, n_xyz, Xd.ptr, n_s, n_mu, mud.ptr,
                                       n_t if has_t else 0, td.ptr if has_t else None,
                                       row0, n_rows, U.ptr, U.ld))
