@@ -67,7 +67,9 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+// the two consumer groups (warps 0-3: points 0-63, warps 4-7: points 64-127 of the tile) only synchronise
+// internally, so one group's epilogue / mixture pass overlaps the other group's DMMA work
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;\n" :: "r"(1 + g) : "memory"); }
 
 __device__ __forceinline__ double softplus(double x) {
     // np.logaddexp(0, x) == tf.math.softplus within 1 ulp
@@ -162,8 +164,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) ensemble_kernel(MlpArgs a) {
         for (int mem = 0; mem < a.n_members; ++mem) {
             // ---- input tile, normalised (varneuralnetwork.py:75-86), zero padded to 16 columns
             const int kin0 = (n_d + BK - 1) / BK * BK;
-            for (int e = tid; e < MP * kin0; e += 256) {
-                const int p = e / kin0, c = e % kin0;
+            for (int e = (tid & 127); e < (MP / 2) * kin0; e += 128) {
+                const int p = wm * (MP / 2) + e / kin0, c = e % kin0;
                 double v = 0.;
                 if (c < n_d && p0 + p < a.N) {
                     v = a.X[(p0 + p) * n_d + c];
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) ensemble_kernel(MlpArgs a) {
                 }
                 act[p * PACT + c] = v;
             }
-            consumer_sync();
+            group_sync(wm);
             for (int l = 0; l < a.n_layers; ++l) {
                 const int in = a.dims[l], out = a.dims[l + 1];
                 const bool head = (l == a.n_layers - 1);
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) ensemble_kernel(MlpArgs a) {
                     mbar_wait(full + sb, phb);
                     const double* bias = ring + (size_t)sb * CHUNK_DOUBLES;
                     if (!head) {
-                        consumer_sync();            // every warp has finished reading act for this layer
+                        group_sync(wm);            // every warp has finished reading act for this layer
                         // next activations: relu(acc + b), columns [out, ceil16(out)) zeroed
                         const int outp = (out + BK - 1) / BK * BK;
 #pragma unroll
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) ensemble_kernel(MlpArgs a) {
                         }
                         __syncwarp();
                         if (lane == 0) mbar_arrive(empty + sb);
-                        consumer_sync();            // activations of the next layer are complete
+                        group_sync(wm);            // activations of the next layer are complete
                     } else {
                         // head: raw outputs t = h W + b go to the per-CTA scratch (L2); the Normal's
                         // parameters are formed in the mixture pass below
@@ -250,15 +252,16 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) ensemble_kernel(MlpArgs a) {
                     }
                 }
             }
-            consumer_sync();        // act may be overwritten by the next member's input tile
+            group_sync(wm);        // act may be overwritten by the next member's input tile
         }
         // ---- mixture moments (podnnmodel.py:322-326): mean_i mu_i, sqrt(mean_i(var_i + mu_i^2) - mean^2)
         __threadfence_block();
-        consumer_sync();
+        group_sync(wm);
         const double invM = 1. / (double)a.n_members;
-        const int64_t pts = min((int64_t)MP, a.N - p0);
+        const int64_t pts = min((int64_t)(MP / 2), a.N - p0 - wm * (MP / 2));      // points of this group
 #pragma unroll 1
-        for (int e = tid; e < pts * n_L; e += 256) {
+        for (int e0 = (tid & 127); e0 < pts * n_L; e0 += 128) {
+            const int e = wm * (MP / 2) * n_L + e0;
             const int p = e / n_L, j = e % n_L;
             double s1 = 0., s2 = 0., var1 = 0.;
 #pragma unroll 1
@@ -285,7 +288,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) ensemble_kernel(MlpArgs a) {
             a.v_mean[p0 * n_L + e] = mean;
             a.v_sig[p0 * n_L + e] = sqrt(var);
         }
-        consumer_sync();            // scratch is reused by the next tile
+        group_sync(wm);            // scratch is reused by the next tile
     }
 }
 
