@@ -103,7 +103,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -262,6 +262,10 @@ def run_gpu(args):
     e2e_value = algo_flops(n_h, N_S, n_L) / (ms_e2e * 1e-3) / 1e12
     L.pb_host_free(hU); L.pb_host_free(hV); L.pb_host_free(hv)
 
+    # ---- second headline metric: ensemble predict samples/s (C4: M = 8 MLPs [1,128,128,128,2*64], 1e6 points
+    #      split over the ranks, no communication)
+    ens_line = ensemble_bench(ctx, L, world, rank, max_over_ranks, peak_tf, with_cpu=(world == 1 and not args.no_cpu_baseline))
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -293,12 +297,45 @@ def run_gpu(args):
                     "h2d_bytes_per_step": U.nbytes * world, "d2h_bytes_per_step": (n_h + N_S) * n_L * 8},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "stage_ms": {k: statistics.mean(v) for k, v in parts.items()},
+            "ensemble_predict": ens_line,
             "snapshot_kernel": {"ms": snap_ms, "gbs": U.nbytes / (snap_ms * 1e-3) / 1e9,
                                 "note": "Ackley field -> U slab in HBM (outside the timed step)"}}
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
+
+
+def ensemble_bench(ctx, L, world, rank, max_over_ranks, peak_tf, with_cpu):
+    """C4: predict_v of M = 8 members on 1e6 parameter points (batch split over the ranks)."""
+    from oracle import ensemble as ens
+    from pod_uqnn_b200 import _lib
+    from pod_uqnn_b200.varneuralnetwork import ensemble_predict_device
+    layers, M, N_total = [1, 128, 128, 128, 64], 8, 1_000_000
+    lo, hi = N_total * rank // world, N_total * (rank + 1) // world
+    members = [ens.init_weights(layers, 4000 + i) for i in range(M)]
+    X = np.linspace(800, 1200, N_total)[:, None]
+    nb = ens.set_normalize_bounds(X, "meanstd")
+    Xd = ctx.to_device(X[lo:hi])
+    best = 1e30
+    for _ in range(3):
+        vm, vs = ensemble_predict_device(ctx, members, layers, Xd, 0.01, "meanstd", nb)
+        best = min(best, ctx.ms(_lib.T_PREDICT))
+        del vm, vs
+    ms = max_over_ranks(best)
+    dims = layers[:-1] + [2 * layers[-1]]
+    flops = 2 * N_total * M * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+    out = {"workload": "C4 ensemble predict_v: M = 8 x MLP [1,128,128,128,2*64], 1e6 points, fp64, batch split over ranks",
+           "samples_per_s": N_total / (ms * 1e-3), "kernel_ms": ms, "tflops": flops / (ms * 1e-3) / 1e12,
+           "frac_fp64_peak": flops / (ms * 1e-3) / 1e12 / (peak_tf * world)}
+    if with_cpu and rank == 0:
+        n_cpu = 20000
+        t = time.perf_counter()
+        ens.predict_v(X[:n_cpu], members, layers[-1], 0.01, "meanstd", nb)
+        sec = time.perf_counter() - t
+        out["cpu_baseline"] = {"samples_per_s": n_cpu / sec, "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"{n_cpu} points through the numpy restatement (TensorFlow is not in the image)"}
+    return out
 
 
 def load_traffic():
@@ -315,7 +352,7 @@ def load_traffic():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="podb200", choices=["podb200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
