@@ -160,17 +160,36 @@ constexpr int SP = JP + 1;   // padded pitch of the 32 x 32 shared matrices
 // Two-sided cyclic Jacobi on S (JP x JP, symmetric, in shared memory), accumulating the
 // rotations in Q.  256 threads: thread (P, R) owns the 2 x 2 block rows(pair P) x cols(pair R).
 // Returns the number of rotations applied in the FIRST sweep (0 => the pair was converged).
-__device__ int inner_jacobi(double (*S)[SP], double (*Q)[SP], double* cs, double* sn, double tol, int max_inner) {
+// pair `idx` (0..15) of inner round `round`: full mode = round-robin tournament over all 32 vectors
+// (31 rounds); cross mode = vector idx of the first block against vector (idx + round) % 16 of the second
+// (16 rounds cover the 256 cross pairs exactly once)
+__device__ __forceinline__ void inner_pair(int cross, int round, int idx, int& p, int& q) {
+    if (cross) { p = idx; q = JB + ((idx + round) & (JB - 1)); }
+    else rr_pair(JP, round, idx, p, q);
+}
+
+// Two-sided Jacobi on S (JP x JP, symmetric, in shared memory), accumulating the rotations in Q.
+// 256 threads: thread (P, R) owns the 2 x 2 block rows(pair P) x cols(pair R).
+//   cross = 0: cyclic sweeps over all pairs until a sweep does nothing (at most max_inner sweeps);
+//   cross = 1: ONE pass over the 256 pairs between the two 16-vector blocks -- the classical block-cyclic
+//              one-sided Jacobi, where every column pair is rotated once per outer sweep.  The rounds are
+//              barrier-separated and latency bound (16 threads compute the rotations, 240 wait), so 16
+//              rounds instead of up to 3 x 31 is what makes a round of the outer sweep cheap.
+// Returns the number of rotations applied in the first pass (0 => nothing to do for this pair).
+__device__ int inner_jacobi(double (*S)[SP], double (*Q)[SP], double* cs, double* sn, double tol, int max_inner,
+                            int cross) {
     const int tid = threadIdx.x;
     for (int e = tid; e < JP * JP; e += blockDim.x) Q[e / JP][e % JP] = (e / JP == e % JP) ? 1. : 0.;
     __syncthreads();
     int first = 0;
-    for (int sweep = 0; sweep < max_inner; ++sweep) {
+    const int n_rounds = cross ? JB : JP - 1;
+    const int n_sweeps = cross ? 1 : max_inner;
+    for (int sweep = 0; sweep < n_sweeps; ++sweep) {
         int rot_sweep = 0;
-        for (int round = 0; round < JP - 1; ++round) {
+        for (int round = 0; round < n_rounds; ++round) {
             int did = 0;
             if (tid < JP / 2) {
-                int p, q; rr_pair(JP, round, tid, p, q);
+                int p, q; inner_pair(cross, round, tid, p, q);
                 double app = S[p][p], aqq = S[q][q], apq = S[p][q];
                 double c = 1., s = 0.;
                 if (apq * apq > tol * tol * fabs(app * aqq) && apq != 0.) {
@@ -190,7 +209,7 @@ __device__ int inner_jacobi(double (*S)[SP], double (*Q)[SP], double* cs, double
             rot_sweep += __syncthreads_count(did);
             {
                 const int P = tid / (JP / 2), R = tid % (JP / 2);
-                int p1, q1, p2, q2; rr_pair(JP, round, P, p1, q1); rr_pair(JP, round, R, p2, q2);
+                int p1, q1, p2, q2; inner_pair(cross, round, P, p1, q1); inner_pair(cross, round, R, p2, q2);
                 const double c1 = cs[P], s1 = sn[P], c2 = cs[R], s2 = sn[R];
                 double m11 = S[p1][p2], m12 = S[p1][q2], m21 = S[q1][p2], m22 = S[q1][q2];
                 // right: columns (p2, q2) <- (c2 col_p - s2 col_q, s2 col_p + c2 col_q)
@@ -214,7 +233,7 @@ __device__ int inner_jacobi(double (*S)[SP], double (*Q)[SP], double* cs, double
 }
 
 struct JacArgs {
-    double* At; int64_t ldm; int nb; int round; double tol; int* n_rot; int max_inner; int64_t batch_stride;
+    double* At; int64_t ldm; int nb; int round; double tol; int* n_rot; int max_inner; int64_t batch_stride; int cross;
 };
 
 constexpr int JCH = 256;        // vector elements staged per shared-memory chunk
@@ -304,7 +323,9 @@ __global__ void __launch_bounds__(256) jacobi_pair_kernel(JacArgs a) {
     }
 
     // ---- phase 2: small eigenproblem
-    const int first = inner_jacobi(S, Q, cs, sn, a.tol, a.max_inner);
+    // round 0 of a sweep meets every block exactly once: it also rotates the pairs INSIDE the two blocks;
+    // the other rounds only the 256 cross pairs (a.cross)
+    const int first = inner_jacobi(S, Q, cs, sn, a.tol, a.max_inner, a.cross);
     if (first == 0) return;                       // uniform: nothing to rotate
     if (tid == 0) atomicAdd(a.n_rot, first);
 
@@ -458,6 +479,7 @@ __global__ void factor_to_right_kernel(const double* __restrict__ At, int64_t ld
 }  // namespace
 
 double g_jacobi_tol_override = 0.;   // > 0: rotation threshold of the next eig (first pass of the accurate mode)
+static int g_cross_rounds = []{ const char* e = getenv("PB_JACOBI_CROSS"); return e ? atoi(e) : 1; }();
 static int g_inner_sweeps = []{ const char* e = getenv("PB_JACOBI_INNER"); return e ? atoi(e) : 3; }();
 // device ints layout in ctx->d_int: [0] r (Cholesky), [1] n_rot, [2] n_L, [3] r_eff
 struct EigScratch { double* d; double* cand_val; int* cand_idx; double* nrm2; double* shift; };
@@ -516,7 +538,7 @@ int pbi_eig_psd(pb_ctx* ctx, const double* G, int64_t m, double tol_rel, double 
         PB_CUDA(ctx, cudaMemsetAsync(ctx->d_int + 1, 0, sizeof(int), ctx->stream));
         const int rounds = nb > 2 ? nb - 1 : 1;
         for (int round = 0; round < rounds; ++round) {
-            JacArgs ja{At, ldm, nb, round, tol, ctx->d_int + 1, g_inner_sweeps, 0};
+            JacArgs ja{At, ldm, nb, round, tol, ctx->d_int + 1, g_inner_sweeps, 0, (g_cross_rounds && round > 0) ? 1 : 0};
             jacobi_pair_kernel<<<nb / 2, 256, jac_smem, ctx->stream>>>(ja);
             PB_LAUNCH_CHECK(ctx);
         }
@@ -646,7 +668,7 @@ int pbi_eig_psd_batched(pb_ctx* ctx, const double* G_all, int64_t m, int batch, 
         PB_CUDA(ctx, cudaMemsetAsync(ctx->d_int + 1, 0, sizeof(int), ctx->stream));
         const int rounds = nb > 2 ? nb - 1 : 1;
         for (int round = 0; round < rounds; ++round) {
-            JacArgs ja{At_all, ldm, nb, round, tol, ctx->d_int + 1, g_inner_sweeps, bsAt};
+            JacArgs ja{At_all, ldm, nb, round, tol, ctx->d_int + 1, g_inner_sweeps, bsAt, (g_cross_rounds && round > 0) ? 1 : 0};
             jacobi_pair_kernel<<<dim3(nb / 2, batch), 256, jac_smem, ctx->stream>>>(ja);
             PB_LAUNCH_CHECK(ctx);
         }
