@@ -308,14 +308,17 @@ def run_gpu(args):
 
 def ensemble_bench(ctx, L, world, rank, max_over_ranks, peak_tf, with_cpu):
     """C4: predict_v of M = 8 members on 1e6 parameter points (batch split over the ranks)."""
-    from oracle import ensemble as ens
     from pod_uqnn_b200 import _lib
-    from pod_uqnn_b200.varneuralnetwork import ensemble_predict_device
+    from pod_uqnn_b200.varneuralnetwork import ensemble_predict_device, glorot_normal
     layers, M, N_total = [1, 128, 128, 128, 64], 8, 1_000_000
     lo, hi = N_total * rank // world, N_total * (rank + 1) // world
-    members = [ens.init_weights(layers, 4000 + i) for i in range(M)]
+    dims_w = layers[:-1] + [2 * layers[-1]]
+    members = []
+    for i in range(M):                      # synthetic glorot_normal members (Keras initialiser), zero biases
+        rng = np.random.default_rng(4000 + i)
+        members.append([a for fi, fo in zip(dims_w[:-1], dims_w[1:]) for a in (glorot_normal(rng, fi, fo), np.zeros(fo))])
     X = np.linspace(800, 1200, N_total)[:, None]
-    nb = ens.set_normalize_bounds(X, "meanstd")
+    nb = (X.mean(0), X.std(0))              # NORM_MEANSTD bounds, varneuralnetwork.py:70-73
     Xd = ctx.to_device(X[lo:hi])
     best = 1e30
     for _ in range(3):
@@ -329,6 +332,7 @@ def ensemble_bench(ctx, L, world, rank, max_over_ranks, peak_tf, with_cpu):
            "samples_per_s": N_total / (ms * 1e-3), "kernel_ms": ms, "tflops": flops / (ms * 1e-3) / 1e12,
            "frac_fp64_peak": flops / (ms * 1e-3) / 1e12 / (peak_tf * world)}
     if with_cpu and rank == 0:
+        from oracle import ensemble as ens      # CPU baseline leg only
         n_cpu = 20000
         t = time.perf_counter()
         ens.predict_v(X[:n_cpu], members, layers[-1], 0.01, "meanstd", nb)
