@@ -40,6 +40,8 @@ struct CholArgs {
     int* cand_idx;
     double tol_rel; double shift_rel;
     int* r_out; double* shift_out;
+    int k_start;            // > 0: continue a factorisation started by chol_small_kernel (d, shift, thresh in memory)
+    const double* thresh_in;
 };
 
 __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(CholArgs a) {
@@ -59,13 +61,13 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(CholArgs a) {
     for (int j = tid; j < m; j += nth) tr += a.G[(int64_t)j * a.ldg + j];
     red_v[tid] = tr; __syncthreads();
     for (int s = nth / 2; s > 0; s >>= 1) { if (tid < s) red_v[tid] += red_v[tid + s]; __syncthreads(); }
-    const double shift = a.shift_rel * red_v[0];
+    const double shift = a.k_start > 0 ? *a.shift_out : a.shift_rel * red_v[0];
     __syncthreads();
-    for (int j = j_begin + tid; j < j_end; j += nth) a.d[j] = a.G[(int64_t)j * a.ldg + j] + shift;
+    if (a.k_start == 0) for (int j = j_begin + tid; j < j_end; j += nth) a.d[j] = a.G[(int64_t)j * a.ldg + j] + shift;
     __syncthreads();
 
-    double thresh = 0.;
-    int k = 0;
+    double thresh = a.k_start > 0 ? *a.thresh_in : 0.;
+    int k = a.k_start;
     for (; k < a.max_steps; ++k) {
         // local arg-max over my rows (ties -> lowest index)
         double bv = -DBL_MAX; int bi = 0x7fffffff;
@@ -103,6 +105,7 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(CholArgs a) {
         __syncthreads();
         if (k == 0) thresh = a.tol_rel * dp;
         if (!(dp > thresh) || !(dp > 0.)) break;          // uniform across the grid
+        (void)0;
         // row p of the factor so far (written by the owner of p in earlier steps)
         for (int q = tid; q < k; q += nth) lp[q] = a.Lt[(int64_t)q * a.ldm + p];
         __syncthreads();
@@ -505,22 +508,38 @@ int pbi_eig_psd(pb_ctx* ctx, const double* G, int64_t m, double tol_rel, double 
     EigScratch sc; PB_TRY(get_scratch(ctx, m, &sc));
     PB_CUDA(ctx, cudaMemsetAsync(At, 0, sizeof(double) * (size_t)cap_rows * ldm, ctx->stream));
 
-    // ---- pivoted Cholesky
-    int grid = (int)std::min<int64_t>(ctx->sm_count, (m + CHOL_ROWS - 1) / CHOL_ROWS);
-    size_t chol_smem = sizeof(double) * (size_t)m;
-    PB_CUDA(ctx, cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
-    int occ = 0;
-    PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol_kernel, CHOL_THREADS, chol_smem));
-    if (occ < 1) PB_FAIL(ctx, PB_ERR_CUDA, "eig_psd: Cholesky kernel does not fit an SM");
-    grid = std::min(grid, occ * ctx->sm_count);
-    if (grid > 1024) grid = 1024;
-    CholArgs ca{G, (int)m, m, At, ldm, (int)m, sc.d, sc.cand_val, sc.cand_idx, tol_rel, shift_rel,
-                ctx->d_int + 0, sc.shift};
-    void* args[] = {&ca};
-    PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)chol_kernel, dim3(grid), dim3(CHOL_THREADS), args, chol_smem, ctx->stream));
-    ctx->launches++;
-    PB_CUDA(ctx, cudaMemcpyAsync(ctx->h_int, ctx->d_int, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // ---- pivoted Cholesky.  Low numerical rank is the common case (the snapshot sets POD is used on): the first
+    // SMALL_STEPS steps run in ONE CTA without grid barriers (~1.5 us per step instead of ~7); if the pivots have
+    // not dropped below the tolerance by then, the cooperative multi-CTA kernel resumes from that state.
+    constexpr int SMALL_STEPS = 64;
+    int k_start = 0;
+    if (m <= 1024) {
+        // chol_small_kernel is declared further down in this file
+        extern int pbi_chol_small_launch(pb_ctx*, const double*, int64_t, double*, int64_t, double, double, int*, double*, int,
+                                         double*, double*, int*);
+        PB_TRY(pbi_chol_small_launch(ctx, G, m, At, ldm, tol_rel, shift_rel, ctx->d_int + 0, sc.shift, SMALL_STEPS, sc.d,
+                                     sc.shift + 1, ctx->d_int + 5));
+        PB_CUDA(ctx, cudaMemcpyAsync(ctx->h_int, ctx->d_int, 6 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        k_start = ctx->h_int[5] ? -1 : ctx->h_int[0];      // -1: finished
+    }
+    if (k_start >= 0) {
+        int grid = (int)std::min<int64_t>(ctx->sm_count, (m + CHOL_ROWS - 1) / CHOL_ROWS);
+        size_t chol_smem = sizeof(double) * (size_t)m;
+        PB_CUDA(ctx, cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
+        int occ = 0;
+        PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol_kernel, CHOL_THREADS, chol_smem));
+        if (occ < 1) PB_FAIL(ctx, PB_ERR_CUDA, "eig_psd: Cholesky kernel does not fit an SM");
+        grid = std::min(grid, occ * ctx->sm_count);
+        if (grid > 1024) grid = 1024;
+        CholArgs ca{G, (int)m, m, At, ldm, (int)m, sc.d, sc.cand_val, sc.cand_idx, tol_rel, shift_rel,
+                    ctx->d_int + 0, sc.shift, k_start, sc.shift + 1};
+        void* args[] = {&ca};
+        PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)chol_kernel, dim3(grid), dim3(CHOL_THREADS), args, chol_smem, ctx->stream));
+        ctx->launches++;
+        PB_CUDA(ctx, cudaMemcpyAsync(ctx->h_int, ctx->d_int, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     const int r = ctx->h_int[0];
     if (r <= 0) PB_FAIL(ctx, PB_ERR_SHAPE, "eig_psd: matrix has no positive pivot (zero or indefinite input)");
 
@@ -538,7 +557,8 @@ int pbi_eig_psd(pb_ctx* ctx, const double* G, int64_t m, double tol_rel, double 
         PB_CUDA(ctx, cudaMemsetAsync(ctx->d_int + 1, 0, sizeof(int), ctx->stream));
         const int rounds = nb > 2 ? nb - 1 : 1;
         for (int round = 0; round < rounds; ++round) {
-            JacArgs ja{At, ldm, nb, round, tol, ctx->d_int + 1, g_inner_sweeps, 0, (g_cross_rounds && round > 0) ? 1 : 0};
+            // a single pair (r <= 32): its 32 x 32 problem IS the whole problem -- solve it to convergence at once
+            JacArgs ja{At, ldm, nb, round, tol, ctx->d_int + 1, nb == 2 ? 16 : g_inner_sweeps, 0, (g_cross_rounds && round > 0) ? 1 : 0};
             jacobi_pair_kernel<<<nb / 2, 256, jac_smem, ctx->stream>>>(ja);
             PB_LAUNCH_CHECK(ctx);
         }
@@ -588,50 +608,69 @@ int pbi_factor_to_right(pb_ctx* ctx, const double* At, int64_t m, int k, const i
 // ---------------------------------------------------------------------------
 namespace {
 // pivoted Cholesky of one matrix per CTA (m <= 1024); same arithmetic as chol_kernel
-__global__ void __launch_bounds__(256) chol_small_kernel(const double* __restrict__ Gall, int m, double* __restrict__ Atall,
+__global__ void __launch_bounds__(1024) chol_small_kernel(const double* __restrict__ Gall, int m, double* __restrict__ Atall,
                                                          int64_t ldm, int64_t bsAt, double tol_rel, double shift_rel,
-                                                         int* __restrict__ r_out, double* __restrict__ shift_out) {
+                                                         int* __restrict__ r_out, double* __restrict__ shift_out,
+                                                         int max_steps, double* __restrict__ d_out,
+                                                         double* __restrict__ thresh_out, int* __restrict__ done_out) {
     extern __shared__ double chol_sm[];          // d[m], lp[m]
     double* d = chol_sm; double* lp = chol_sm + m;
-    __shared__ double red_v[256];
-    __shared__ int red_i[256];
+    __shared__ double red_v[1024];
+    __shared__ int red_i[1024];
+    const int nth = blockDim.x, nwarps = blockDim.x >> 5;
     const double* G = Gall + (int64_t)blockIdx.x * m * m;
     double* At = Atall + (int64_t)blockIdx.x * bsAt;
     const int tid = threadIdx.x;
     double tr = 0.;
-    for (int j = tid; j < m; j += 256) tr += G[(int64_t)j * m + j];
+    for (int j = tid; j < m; j += nth) tr += G[(int64_t)j * m + j];
     red_v[tid] = tr; __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) { if (tid < s) red_v[tid] += red_v[tid + s]; __syncthreads(); }
+    for (int s = nth / 2; s > 0; s >>= 1) { if (tid < s) red_v[tid] += red_v[tid + s]; __syncthreads(); }
     const double shift = shift_rel * red_v[0];
     __syncthreads();
-    for (int j = tid; j < m; j += 256) d[j] = G[(int64_t)j * m + j] + shift;
+    for (int j = tid; j < m; j += nth) d[j] = G[(int64_t)j * m + j] + shift;
     __syncthreads();
     double thresh = 0.;
-    int k = 0;
-    for (; k < m; ++k) {
+    int k = 0, done = 0;
+    for (; k < max_steps; ++k) {
         double bv = -DBL_MAX; int bi = 0x7fffffff;
-        for (int j = tid; j < m; j += 256) { double v = d[j]; if (v > bv || (v == bv && j < bi)) { bv = v; bi = j; } }
-        red_v[tid] = bv; red_i[tid] = bi; __syncthreads();
-        for (int s = 128; s > 0; s >>= 1) {
-            if (tid < s) {
-                double v = red_v[tid + s]; int i = red_i[tid + s];
-                if (v > red_v[tid] || (v == red_v[tid] && i < red_i[tid])) { red_v[tid] = v; red_i[tid] = i; }
-            }
-            __syncthreads();
+        for (int j = tid; j < m; j += nth) { double v = d[j]; if (v > bv || (v == bv && j < bi)) { bv = v; bi = j; } }
+        // arg-max: warp shuffles, then the 8 warp results through shared memory (2 barriers instead of 9)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
         }
-        const double dp = red_v[0]; const int p = red_i[0];
+        if ((tid & 31) == 0) { red_v[tid >> 5] = bv; red_i[tid >> 5] = bi; }
+        __syncthreads();
+        bv = red_v[0]; bi = red_i[0];
+        for (int w = 1; w < nwarps; ++w) { const double ov = red_v[w]; const int oi = red_i[w]; if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; } }
+        const double dp = bv; const int p = bi;
         __syncthreads();
         if (k == 0) thresh = tol_rel * dp;
-        if (!(dp > thresh) || !(dp > 0.)) break;
-        for (int q = tid; q < k; q += 256) lp[q] = At[(int64_t)q * ldm + p];
+        if (!(dp > thresh) || !(dp > 0.)) { done = 1; break; }
+        for (int q = tid; q < k; q += nth) lp[q] = At[(int64_t)q * ldm + p];
         __syncthreads();
         const double inv = 1. / sqrt(dp);
-        for (int j = tid; j < m; j += 256) {
+        for (int j = tid; j < m; j += nth) {
+            // 8 independent loads in flight per pass (the factor lives in L2: one load at a time costs ~0.35 us)
             double s0 = 0., s1 = 0.;
             int q = 0;
-            for (; q + 1 < k; q += 2) { s0 += At[(int64_t)q * ldm + j] * lp[q]; s1 += At[(int64_t)(q + 1) * ldm + j] * lp[q + 1]; }
-            if (q < k) s0 += At[(int64_t)q * ldm + j] * lp[q];
-            double v = (G[(int64_t)j * m + p] + (j == p ? shift : 0.) - (s0 + s1)) * inv;
+            for (; q + 7 < k; q += 8) {
+                double l[8];
+#pragma unroll
+                for (int x = 0; x < 8; ++x) l[x] = At[(int64_t)(q + x) * ldm + j];
+#pragma unroll
+                for (int x = 0; x < 8; x += 2) { s0 += l[x] * lp[q + x]; s1 += l[x + 1] * lp[q + x + 1]; }
+            }
+            {
+                double l[8];
+#pragma unroll
+                for (int x = 0; x < 8; ++x) l[x] = (q + x < k) ? At[(int64_t)(q + x) * ldm + j] : 0.;
+#pragma unroll
+                for (int x = 0; x < 8; ++x) if (q + x < k) { if (x & 1) s1 += l[x] * lp[q + x]; else s0 += l[x] * lp[q + x]; }
+            }
+            const double gjp = G[(int64_t)j * m + p];
+            double v = (gjp + (j == p ? shift : 0.) - (s0 + s1)) * inv;
             if (d[j] == -DBL_MAX) v = 0.;
             if (j == p) v = sqrt(dp);
             At[(int64_t)k * ldm + j] = v;
@@ -639,7 +678,13 @@ __global__ void __launch_bounds__(256) chol_small_kernel(const double* __restric
         }
         __syncthreads();
     }
-    if (tid == 0) { r_out[blockIdx.x] = k; shift_out[blockIdx.x] = shift; }
+    if (k == m) done = 1;
+    if (d_out) for (int j = tid; j < m; j += nth) d_out[j] = d[j];      // state for the cooperative kernel to resume
+    if (tid == 0) {
+        r_out[blockIdx.x] = k; shift_out[blockIdx.x] = shift;
+        if (thresh_out) *thresh_out = thresh;
+        if (done_out) *done_out = done;
+    }
 }
 }  // namespace
 
@@ -655,8 +700,9 @@ int pbi_eig_psd_batched(pb_ctx* ctx, const double* G_all, int64_t m, int batch, 
     const int64_t bsAt = cap_rows * ldm;
     PB_CUDA(ctx, cudaMemsetAsync(At_all, 0, sizeof(double) * (size_t)bsAt * batch, ctx->stream));
     double* nrm2 = scratch_dbl; double* shift = scratch_dbl + (size_t)batch * cap_rows;
-    chol_small_kernel<<<batch, 256, sizeof(double) * 2 * (size_t)m, ctx->stream>>>(G_all, (int)m, At_all, ldm, bsAt, tol_rel,
-                                                                                shift_rel, r_dev, shift);
+    chol_small_kernel<<<batch, m > 256 ? 1024 : 256, sizeof(double) * 2 * (size_t)m, ctx->stream>>>(G_all, (int)m, At_all, ldm, bsAt, tol_rel,
+                                                                                shift_rel, r_dev, shift, (int)m, nullptr, nullptr,
+                                                                                nullptr);
     PB_LAUNCH_CHECK(ctx);
     const int nb = (int)(cap_rows / JB);
     const int nvec = (int)cap_rows;
@@ -705,6 +751,16 @@ int pbi_factor_to_right_batched(pb_ctx* ctx, const double* At_all, int64_t m, in
     int64_t n = m * k;
     factor_to_right_kernel<<<dim3((unsigned)((n + 255) / 256), batch), 256, 0, ctx->stream>>>(
         At_all, ldm, perm_all, nrm_all, sig_all, (int)m, k, B_all, k, cap_rows * ldm, m, cap_rows, bsB);
+    PB_LAUNCH_CHECK(ctx);
+    return PB_OK;
+}
+
+
+int pbi_chol_small_launch(pb_ctx* ctx, const double* G, int64_t m, double* At, int64_t ldm, double tol_rel, double shift_rel,
+                          int* r_dev, double* shift_dev, int max_steps, double* d_out, double* thresh_out, int* done_out) {
+    chol_small_kernel<<<1, m > 256 ? 1024 : 256, sizeof(double) * 2 * (size_t)m, ctx->stream>>>(G, (int)m, At, ldm, 0, tol_rel, shift_rel, r_dev,
+                                                                            shift_dev, std::min<int>(max_steps, (int)m), d_out,
+                                                                            thresh_out, done_out);
     PB_LAUNCH_CHECK(ctx);
     return PB_OK;
 }
