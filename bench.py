@@ -275,7 +275,7 @@ def run_gpu(args):
     gram_kernel_ms = statistics.mean(gram_ms)
     gram_flops = n_h_loc * N_S * (N_S + 1)
     achieved = gram_flops / (gram_kernel_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "gemm_tn_kernel<128,128> (Gram U^T U, fp64 DMMA)", "achieved": achieved,
+    roofline = {"bound": "tensor", "kernel": "gram_streamk_kernel (Gram U^T U, fp64 DMMA m8n8k4, TMA + mbarrier ring)", "achieved": achieved,
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": load_traffic(),
                 "algorithmic_flops_per_launch": gram_flops, "kernel_ms": gram_kernel_ms,
                 "kernel_share_of_step": gram_kernel_ms / ms_step,

@@ -222,6 +222,22 @@ int  pb_predict_U(pb_ctx* ctx, const double* V_dev, int64_t ldv, int64_t n_rows,
                   const double* v_mean_dev, const double* v_sig_dev, int64_t N,
                   int samples, uint64_t seed, double* U_mean_dev, double* U_sig_dev, int64_t ldo);
 
+/* Ensemble training, SURVEY.md section 8 row f4: `epochs` full-batch steps of VarNeuralNetwork.grad +
+ * tf_optimization_step (varneuralnetwork.py:94-128; optimiser tf.keras.optimizers.Adam(lr) :24, L2 term :88-92)
+ * for all members at once.  dims = [n_d, hidden..., 2 n_L] (n_layers + 1 entries).
+ * params_dev / adam_m_dev / adam_v_dev: n_members x P doubles, per member the Keras get_weights() order
+ *   [W0 (in x out, row-major), b0, W1, b1, ...] flattened; updated in place (Adam moments start at zero,
+ *   step0 = optimiser steps already taken, for the bias correction when a run is resumed).
+ * use_adv != 0: the reference's `adv_eps is not None` branch (adv_eps = 0 included): X_adv = X + adv_eps
+ *   sign(d loss / d X), second NLL + second L2 term.  X_dev (N x n_d) is the NORMALISED input (:136-137),
+ *   v_dev (N x n_L) the targets, both shared by the members.
+ * loss_host (epochs x n_members, may be NULL): loss before the update of each epoch, as tf_optimization_step
+ *   returns it.  use_graph != 0 replays one captured CUDA graph per epoch (the default path); 0 launches eagerly. */
+int  pb_ensemble_train(pb_ctx* ctx, int n_members, int n_layers, const int* dims, double* params_dev,
+                       double* adam_m_dev, double* adam_v_dev, int64_t step0, int epochs, double lr, double lam,
+                       int use_adv, double adv_eps, double soft_0, const double* X_dev, const double* v_dev,
+                       int64_t N, double* loss_host, int use_graph);
+
 /* ---- measurement helpers (used by bench.py; not on the product path) ------ */
 /* kind: 0 = DFMA register loop, 1 = DMMA m8n8k4 loop, 2 = both pipes mixed.  Returns TFLOP/s. */
 int  pb_probe_fp64_peak(pb_ctx* ctx, int kind, double* tflops);

@@ -69,6 +69,8 @@ SIGNATURES = {
     "pb_reconstruct": (_int, [_vp, _vp, _i64, _int, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp]),
     "pb_ensemble_predict": (_int, [_vp, _int, _int, _pi, _vp, _int, _vp, _vp, _dbl, _vp, _i64, _vp, _vp]),
     "pb_predict_U": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp, _i64, _int, C.c_uint64, _vp, _vp, _i64]),
+    "pb_ensemble_train": (_int, [_vp, _int, _int, _pi, _vp, _vp, _vp, _i64, _int, _dbl, _dbl, _int, _dbl, _dbl, _vp, _vp, _i64,
+                          _vp, _int]),
     "pb_probe_fp64_peak": (_int, [_vp, _int, _pd]),
     "pb_probe_hbm_copy": (_int, [_vp, C.c_size_t, _pd]),
     "pb_flush_l2": (_int, [_vp]),

@@ -93,6 +93,7 @@ int pb_destroy(pb_ctx* ctx) {
     cudaEventDestroy(ctx->evk0); cudaEventDestroy(ctx->evk1); cudaEventDestroy(ctx->evr0); cudaEventDestroy(ctx->evr1);
     if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); for (auto& e : ctx->chunk_ev) if (e) cudaEventDestroy(e); }
     if (ctx->Gpart) cudaFree(ctx->Gpart);
+    pbi_train_free(ctx);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return PB_OK;

@@ -59,7 +59,9 @@ struct pb_ctx {
     int* d_int = nullptr;   // device ints (flags, n_L ...)
     int* h_int = nullptr;   // pinned host mirror
     std::vector<double> sigma_host;  // singular values of the last decomposition
+    void* train_state = nullptr;     // pb_ensemble_train: work buffers, side stream, captured epoch graph (train.cu)
 };
+void pbi_train_free(pb_ctx* ctx);
 
 const char* pb_set_global_error(const std::string& s);
 

@@ -17,7 +17,10 @@ import numpy as np
 from . import _lib
 from .acceleration import snapshots_device
 from .pod import pod_device, fast_pod_device, DEFAULT_MODE
-from .varneuralnetwork import VarNeuralNetwork, NORM_MEANSTD, ensemble_predict_device
+from .varneuralnetwork import (VarNeuralNetwork, NORM_MEANSTD, ensemble_predict_device, EnsembleTrainer,
+                               normalize_host)
+from .logger import Logger
+from .metrics import re_s
 
 SETUP_DATA_NAME = "setup_data.pkl"
 TRAIN_DATA_NAME = "train_data.pkl"
@@ -229,8 +232,36 @@ class PodnnModel:
             self.model_path.append(os.path.join(self.resdir, f"{MODEL_NAME}-{i}-{time.time()}"))
         self.save_model()
 
-    def train_model(self, *a, **k):
-        raise NotImplementedError("ensemble training (podnnmodel.py:289-312) is outside the CUDA hot path")
+    def train_model(self, model_id, X_v_train, v_train, X_v_val, v_val, epochs, freq=100, div_max=False):
+        """podnnmodel.py:291-312: trains member `model_id` (csrc/train.cu), logging RE_val / MPIW_val every
+        `freq` epochs."""
+        if self.regnn is None or len(self.regnn) == 0:
+            raise ValueError("Regression model isn't defined.")
+        model = self.regnn[model_id]
+
+        def get_val_err():
+            v_val_pred, var = model.predict(X_v_val, ctx=self.ctx)
+            return {"RE_val": re_s(v_val.T, v_val_pred.T, div_max), "MPIW_val": 4 * var.mean()}
+        logger = Logger(epochs, freq)
+        logger.set_val_err_fn(get_val_err)
+        model.fit(X_v_train, v_train, epochs, logger, ctx=self.ctx)
+        return [logger.get_logs()]
+
+    def train_ensemble(self, X_v_train, v_train, epochs, *, use_graph=True):
+        """All members in the same launches (no reference counterpart: its train.py loops over the members or gives
+        one to each Horovod rank, experiments/*/train.py:30-34).  Returns the losses (epochs, n_M)."""
+        if self.regnn is None or len(self.regnn) == 0:
+            raise ValueError("Regression model isn't defined.")
+        m0 = self.regnn[0]
+        for m in self.regnn:
+            m.set_normalize_bounds(X_v_train)
+        X_n = normalize_host(X_v_train, m0.norm, m0.norm_bounds)
+        tr = EnsembleTrainer(self.ctx, [m.weights for m in self.regnn], m0.layers, X_n, v_train, m0.lr, m0.lam,
+                             m0.adv_eps, m0.soft_0, use_graph=use_graph)
+        losses = tr.run(epochs)
+        for m, w in zip(self.regnn, tr.weights()):
+            m.weights = w
+        return losses
 
     def _ensemble_args(self):
         if not self.regnn:

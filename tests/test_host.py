@@ -85,8 +85,32 @@ def test_pack_members_layout():
     assert [w.shape for w in net.weights] == [(2, 4), (4,), (4, 6), (6,)]
     with pytest.raises(ValueError):
         net.set_weights(ms[0][:2])
-    with pytest.raises(NotImplementedError):
-        net.fit(None, None, 1, None)
+
+
+def test_logger_and_metrics_mirror_reference(capsys):
+    """Logger prints at multiples of `frequency` only (logger.py:45-64); re_s is the mean column-wise relative error
+    (metrics.py:21-30); normalize_host follows varneuralnetwork.py:75-86."""
+    from pod_uqnn_b200.logger import Logger
+    from pod_uqnn_b200.metrics import re_s
+    from pod_uqnn_b200.varneuralnetwork import normalize_host
+    lg = Logger(10, 5)
+    lg.set_val_err_fn(lambda: {"RE_val": 0.5, "MPIW_val": 2.})
+    lg.log_train_start()
+    for e in range(10):
+        lg.log_train_epoch(e, 1.5)
+    lg.log_train_end(10, 1.25)
+    out = capsys.readouterr().out
+    assert out.count("#:") == 3 and "RE_val: 5.0000e-01" in out and "Training finished (epoch 10)" in out
+    header, table = lg.get_logs()
+    assert header == "epoch\tL\tRE_val\tMPIW_val" and table.shape == (3, 4) and list(table[:, 0]) == [0, 5, 10]
+    assert Logger(10, 5, silent=True).get_logs() is None
+    U = np.array([[1., 2.], [2., 0.]]); Up = np.array([[1., 1.], [2., 0.]])
+    assert abs(re_s(U, Up) - 0.5 * (0. + 1. / 2.)) < 1e-15
+    assert abs(re_s(U, Up, div_max=True) - 0.25) < 1e-15
+    X = np.array([[1., 10.], [3., 30.]])
+    assert np.array_equal(normalize_host(X, "meanstd", (X.mean(0), X.std(0))), np.array([[-1., -1.], [1., 1.]]))
+    assert np.array_equal(normalize_host(X, "center", (X.min(0), X.max(0))), np.array([[-1., -10.], [1., 10.]]))
+    assert normalize_host(X, "meanstd", None) is not None and np.array_equal(normalize_host(X, "meanstd", None), X)
 
 
 def test_podnnmodel_host_layout_helpers(tmp_path):
@@ -104,7 +128,7 @@ def test_podnnmodel_host_layout_helpers(tmp_path):
     assert os.path.exists(os.path.join(str(tmp_path), "setup_data.pkl"))
     n_v, xm, n_t = PodnnModel.load_setup_data(str(tmp_path))
     assert n_v == 2 and n_t == 0 and np.array_equal(xm, x_mesh)
-    with pytest.raises(NotImplementedError):
-        m.train_model()
+    with pytest.raises(ValueError):                       # podnnmodel.py:294-295: no ensemble defined yet
+        m.train_model(0, None, None, None, None, 1)
     with pytest.raises(ValueError):
         m.predict_v(np.zeros((3, 2)))
