@@ -24,7 +24,7 @@ using namespace pbt;
 
 constexpr int MAXL = 8;
 constexpr int STAGES = 4;
-constexpr int NLL_BLOCKS = 32;
+constexpr int NLL_BLOCKS_MAX = 256;
 constexpr int MAX_SPLITS = 16;
 
 struct LayerTab {
@@ -267,10 +267,10 @@ train_nll_kernel(double* __restrict__ T, int64_t sT, const double* __restrict__ 
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 train_adam_kernel(LayerTab tab, double* __restrict__ params, double* __restrict__ am, double* __restrict__ av,
-                  double* __restrict__ WT, const double* __restrict__ gpart, int n_pass, int splits, int M,
+                  double* __restrict__ WT, const double* __restrict__ gpart, int n_pass, int n_term, int splits, int M,
                   double lr, double lam, long long* __restrict__ tstep, int* __restrict__ eidx,
-                  const double* __restrict__ nllpart, double* __restrict__ regpart, unsigned* __restrict__ ticket,
-                  double* __restrict__ loss, int update) {
+                  const double* __restrict__ nllpart, int nll_blocks, double* __restrict__ regpart,
+                  unsigned* __restrict__ ticket, double* __restrict__ loss, int update) {
     const int mem = blockIdx.y;
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     __shared__ double s_lrt;
@@ -289,7 +289,9 @@ train_adam_kernel(LayerTab tab, double* __restrict__ params, double* __restrict_
         if (update) {
             double g = 0.;
             for (int q = 0; q < n_pass * splits; ++q) g += gpart[((long long)q * M + mem) * tab.P + p];
-            g += (double)n_pass * lam * w0;
+            // n_term = NLL + L2 terms in the loss (2 with the adversarial branch); when adv_eps == 0 the second
+            // term equals the first exactly (X_adv = X + 0 sign(.) = X), so one pass is run and counted twice
+            g = g * (double)(n_term / n_pass) + (double)n_term * lam * w0;
             double* mp = am + (long long)mem * tab.P + p; double* vp = av + (long long)mem * tab.P + p;
             const double mn = 0.9 * (*mp) + (1. - 0.9) * g;
             const double vn = 0.999 * (*vp) + (1. - 0.999) * g * g;
@@ -330,17 +332,28 @@ train_adam_kernel(LayerTab tab, double* __restrict__ params, double* __restrict_
         s_last = (done == gridDim.x - 1);
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
+    if (s_last) {      // fixed-order block reduction of the partial sums (deterministic for a given launch shape)
         __threadfence();
-        double reg = 0.;
-        for (unsigned b = 0; b < gridDim.x; ++b) reg += ((volatile double*)regpart)[(long long)mem * gridDim.x + b];
-        double nll = 0.;
+        double reg = 0., nll = 0.;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+            reg += ((volatile double*)regpart)[(long long)mem * gridDim.x + b];
         for (int q = 0; q < n_pass; ++q)
-            for (int b = 0; b < NLL_BLOCKS; ++b) nll += nllpart[((long long)q * M + mem) * NLL_BLOCKS + b];
-        loss[(long long)eidx[mem] * M + mem] = nll + (double)n_pass * lam * 0.5 * reg;
-        eidx[mem] += 1;
-        tstep[mem] += 1;
-        ticket[mem] = 0;
+            for (int b = threadIdx.x; b < nll_blocks; b += blockDim.x)
+                nll += nllpart[((long long)q * M + mem) * nll_blocks + b];
+        double tot = nll * (double)(n_term / n_pass) + (double)n_term * lam * 0.5 * reg;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tot;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.;
+            for (int w = 0; w < 8; ++w) t += red[w];
+            loss[(long long)eidx[mem] * M + mem] = t;
+            eidx[mem] += 1;
+            tstep[mem] += 1;
+            ticket[mem] = 0;
+        }
     }
 }
 
@@ -349,6 +362,7 @@ train_adam_kernel(LayerTab tab, double* __restrict__ params, double* __restrict_
 // ---------------------------------------------------------------------------
 struct TrainKey {
     int M, n_layers, dims[MAXL + 1], use_adv;
+    int n_pass;          // forward/backward passes actually run: 2 only when adv_eps != 0
     int64_t N;
     const double *X, *v;
     double *params, *am, *av;
@@ -360,7 +374,7 @@ struct TrainState {
     TrainKey key;
     bool valid = false;
     LayerTab tab;
-    int splits = 1; int64_t rps = 0;
+    int splits = 1; int64_t rps = 0; int nll_blocks = 1;
     int64_t act_off[MAXL + 1], del_off[MAXL + 1], act_total = 0, del_total = 0;
     double* act[2] = {nullptr, nullptr}; double* del[2] = {nullptr, nullptr};
     double *xadv = nullptr, *WT = nullptr, *gpart = nullptr, *nllpart = nullptr, *regpart = nullptr, *loss = nullptr;
@@ -401,7 +415,9 @@ int launch_nn(pb_ctx* ctx, cudaStream_t st, int M, const double* A, int64_t lda,
               const double* aux, int64_t ldaux, int64_t sAux, double eps) {
     const bool aa = al16(A, lda, sA), ab = al16(B, ldb, sB);
     const int64_t big_ctas = ((rows + 127) / 128) * ((k + 63) / 64) * M;
-    const bool big = big_ctas >= ctx->sm_count;
+    static const int force = getenv("PB_TRAIN_TILE") ? atoi(getenv("PB_TRAIN_TILE")) : 0;   // 1 small, 2 big
+    (void)big_ctas;
+    const bool big = (force == 2);     // measured: the 32-row tiles (3 CTAs per SM) win at every N (profiles/r01_notes.md)
 #define PB_NN(BM_, BN_, WM_, WN_) \
     (aa ? (ab ? launch_nn_t<BM_, BN_, WM_, WN_, true, true>(ctx, st, M, A, lda, sA, rows, m, B, ldb, sB, k, Y, ldy, sY, epi, aux, ldaux, sAux, eps) \
               : launch_nn_t<BM_, BN_, WM_, WN_, true, false>(ctx, st, M, A, lda, sA, rows, m, B, ldb, sB, k, Y, ldy, sY, epi, aux, ldaux, sAux, eps)) \
@@ -460,9 +476,9 @@ int configure_all() {
 int launch_adam(pb_ctx* ctx, TrainState& s, int update) {
     const TrainKey& k = s.key;
     dim3 grid((unsigned)((s.tab.P + 255) / 256), (unsigned)k.M);
-    train_adam_kernel<<<grid, 256, 0, ctx->stream>>>(s.tab, k.params, k.am, k.av, s.WT, s.gpart, k.use_adv ? 2 : 1,
-                                                     s.splits, k.M, k.lr, k.lam, s.tstep, s.eidx, s.nllpart,
-                                                     s.regpart, s.ticket, s.loss, update);
+    train_adam_kernel<<<grid, 256, 0, ctx->stream>>>(s.tab, k.params, k.am, k.av, s.WT, s.gpart, k.n_pass,
+                                                     k.use_adv ? 2 : 1, s.splits, k.M, k.lr, k.lam, s.tstep, s.eidx, s.nllpart,
+                                                     s.nll_blocks, s.regpart, s.ticket, s.loss, update);
     PB_LAUNCH_CHECK(ctx);
     return PB_OK;
 }
@@ -475,7 +491,7 @@ int run_epoch(pb_ctx* ctx, TrainState& s) {
     const int64_t N = k.N;
     const int n_L = k.dims[L] / 2;
     cudaStream_t st = ctx->stream;
-    const int n_pass = k.use_adv ? 2 : 1;
+    const int n_pass = k.n_pass;
     for (int p = 0; p < n_pass; ++p) {
         const double* in0 = (p == 0) ? k.X : s.xadv;
         const int64_t s_in0 = (p == 0) ? 0 : N * k.dims[0];
@@ -490,9 +506,9 @@ int run_epoch(pb_ctx* ctx, TrainState& s) {
                              head ? EPI_BIAS : EPI_BIAS_RELU, k.params + s.tab.off_b[l], 0, s.tab.P, 0.));
         }
         {   // NLL + head gradient, in place
-            dim3 grid(NLL_BLOCKS, (unsigned)M);
+            dim3 grid((unsigned)s.nll_blocks, (unsigned)M);
             train_nll_kernel<<<grid, 256, 0, st>>>(s.del[p] + s.del_off[L - 1], N * k.dims[L], k.v, N, n_L, k.soft_0,
-                                                   s.nllpart + (int64_t)p * M * NLL_BLOCKS);
+                                                   s.nllpart + (int64_t)p * M * s.nll_blocks);
             PB_LAUNCH_CHECK(ctx);
         }
         // backward
@@ -513,7 +529,7 @@ int run_epoch(pb_ctx* ctx, TrainState& s) {
                 PB_TRY(launch_nn(ctx, st, M, D, k.dims[l + 1], sD, N, k.dims[l + 1], s.WT + s.tab.off_wt[l], k.dims[l],
                                  s.tab.PT, k.dims[l], s.del[p] + s.del_off[l - 1], k.dims[l], N * k.dims[l], EPI_MASK,
                                  s.act[p] + s.act_off[l], k.dims[l], N * k.dims[l], 0.));
-            } else if (p == 0 && k.use_adv) {
+            } else if (p == 0 && n_pass == 2) {
                 PB_TRY(launch_nn(ctx, st, M, D, k.dims[1], sD, N, k.dims[1], s.WT + s.tab.off_wt[0], k.dims[0],
                                  s.tab.PT, k.dims[0], s.xadv, k.dims[0], N * k.dims[0], EPI_SIGN, k.X, k.dims[0], 0,
                                  k.adv_eps));
@@ -574,6 +590,7 @@ extern "C" int pb_ensemble_train(pb_ctx* ctx, int n_members, int n_layers, const
     key.M = n_members; key.n_layers = n_layers; key.use_adv = use_adv ? 1 : 0; key.N = N;
     for (int l = 0; l <= n_layers; ++l) key.dims[l] = dims[l];
     key.X = X_dev; key.v = v_dev; key.params = params_dev; key.am = adam_m_dev; key.av = adam_v_dev;
+    key.n_pass = (use_adv && adv_eps != 0.) ? 2 : 1;
     key.lr = lr; key.lam = lam; key.adv_eps = use_adv ? adv_eps : 0.; key.soft_0 = soft_0;
     const bool same = s.valid && (s.key == key);
     const int M = n_members, L = n_layers;
@@ -603,7 +620,7 @@ extern "C" int pb_ensemble_train(pb_ctx* ctx, int n_members, int n_layers, const
         int64_t rps = (N + want - 1) / want;
         rps = std::max<int64_t>(64, ((rps + BK - 1) / BK) * BK);
         s.rps = rps; s.splits = (int)((N + rps - 1) / rps);
-        const int n_pass = key.use_adv ? 2 : 1;
+        const int n_pass = key.n_pass;
         for (int p = 0; p < n_pass; ++p) {
             PB_TRY(reserve(ctx, &s.act[p], &s.cap_act[p], (size_t)std::max<int64_t>(s.act_total, 2)));
             PB_TRY(reserve(ctx, &s.del[p], &s.cap_del[p], (size_t)s.del_total));
@@ -611,7 +628,8 @@ extern "C" int pb_ensemble_train(pb_ctx* ctx, int n_members, int n_layers, const
         PB_TRY(reserve(ctx, &s.xadv, &s.cap_xadv, (size_t)M * N * dims[0] + 2));
         PB_TRY(reserve(ctx, &s.WT, &s.cap_WT, (size_t)M * t.PT));
         PB_TRY(reserve(ctx, &s.gpart, &s.cap_gpart, (size_t)n_pass * s.splits * M * t.P));
-        PB_TRY(reserve(ctx, &s.nllpart, &s.cap_nll, (size_t)2 * M * NLL_BLOCKS));
+        s.nll_blocks = (int)std::min<int64_t>(NLL_BLOCKS_MAX, std::max<int64_t>(1, (N * (dims[L] / 2) + 511) / 512));
+        PB_TRY(reserve(ctx, &s.nllpart, &s.cap_nll, (size_t)2 * M * NLL_BLOCKS_MAX));
         PB_TRY(reserve(ctx, &s.regpart, &s.cap_reg, (size_t)M * ((t.P + 255) / 256)));
         if (!s.ticket) {
             PB_CUDA(ctx, cudaMalloc(&s.ticket, 64 * sizeof(unsigned)));
@@ -621,7 +639,7 @@ extern "C" int pb_ensemble_train(pb_ctx* ctx, int n_members, int n_layers, const
             PB_CUDA(ctx, cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
             PB_CUDA(ctx, cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
         }
-        s.launches_per_epoch = n_pass * (L + 1 + L + (L - 1)) + (key.use_adv ? 1 : 0) + 1;
+        s.launches_per_epoch = n_pass * (L + 1 + L + (L - 1)) + (n_pass == 2 ? 1 : 0) + 1;
         s.valid = true;
     }
     // the loss history lives in a context buffer (its address is baked into the captured graph)
