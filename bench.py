@@ -265,6 +265,7 @@ def run_gpu(args):
     # ---- second headline metric: ensemble predict samples/s (C4: M = 8 MLPs [1,128,128,128,2*64], 1e6 points
     #      split over the ranks, no communication)
     ens_line = ensemble_bench(ctx, L, world, rank, max_over_ranks, peak_tf, with_cpu=(world == 1 and not args.no_cpu_baseline))
+    train_lines = train_bench(ctx, world, rank, max_over_ranks, peak_tf, with_cpu=(world == 1 and not args.no_cpu_baseline))
 
     if rank != 0:
         if dist is not None:
@@ -297,7 +298,7 @@ def run_gpu(args):
                     "h2d_bytes_per_step": U.nbytes * world, "d2h_bytes_per_step": (n_h + N_S) * n_L * 8},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "stage_ms": {k: statistics.mean(v) for k, v in parts.items()},
-            "ensemble_predict": ens_line,
+            "ensemble_predict": ens_line, "ensemble_train": train_lines,
             "snapshot_kernel": {"ms": snap_ms, "gbs": U.nbytes / (snap_ms * 1e-3) / 1e9,
                                 "note": "Ackley field -> U slab in HBM (outside the timed step)"}}
     sys.stdout.flush()
@@ -339,6 +340,44 @@ def ensemble_bench(ctx, L, world, rank, max_over_ranks, peak_tf, with_cpu):
         sec = time.perf_counter() - t
         out["cpu_baseline"] = {"samples_per_s": n_cpu / sec, "cores": os.cpu_count(), "kind": "port",
                                "sample": f"{n_cpu} points through the numpy restatement (TensorFlow is not in the image)"}
+    return out
+
+
+def train_bench(ctx, world, rank, max_over_ranks, peak_tf, with_cpu):
+    """full-batch ensemble training epochs (varneuralnetwork.py:94-128) at the reference's own training
+    sizes; every rank trains its own n_M members (the reference gives one member to each Horovod rank)."""
+    from pod_uqnn_b200.varneuralnetwork import EnsembleTrainer, glorot_normal
+    cases = [("2d_ackley: [3,128,128,128,2*14], N = 400, n_M = 5 per rank, adv_eps 0", [3, 128, 128, 128, 14], 400, 5, 0., 1e-3, 1e-3, 0.01, 1000),
+             ("1dt_burger: [2,128,128,128,2*37], N = 4000, n_M = 5 per rank, adv_eps 0.01", [2, 128, 128, 128, 37], 4000, 5, 0.01, 0.01, 1e-8, 0.01, 300)]
+    out = []
+    for ci, (name, layers, N, M, adv, lr, lam, soft_0, epochs) in enumerate(cases):
+        rng = np.random.default_rng(7000 + 10 * ci + rank)
+        dims = layers[:-1] + [2 * layers[-1]]
+        members = [[a for fi, fo in zip(dims[:-1], dims[1:]) for a in (glorot_normal(rng, fi, fo), np.zeros(fo))]
+                   for _ in range(M)]
+        X = rng.uniform(-1.7, 1.7, (N, layers[0]))
+        v = rng.standard_normal((N, layers[-1]))
+        tr = EnsembleTrainer(ctx, members, layers, X, v, lr, lam, adv, soft_0)
+        tr.run(50)
+        ctx.sync()
+        ctx.timer_start()
+        losses = tr.run(epochs)
+        ms = max_over_ranks(ctx.timer_stop())
+        mac = sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+        flops = 2 * 3 * 2 * N * mac * M * world        # 2 loss terms x (forward + delta chain + weight gradient)
+        line = {"workload": name, "us_per_epoch": 1e3 * ms / epochs, "member_epochs_per_s": M * world * epochs / (ms * 1e-3),
+                "tflops_equiv": flops / (ms * 1e-3 / epochs) / 1e12, "epochs": epochs,
+                "loss_first_last": [float(losses[0].mean()), float(losses[-1].mean())],
+                "launches_per_epoch": "CUDA graph replay, see DESIGN.md section 9"}
+        if with_cpu and rank == 0:
+            from oracle import train as otr           # CPU baseline leg only
+            n_ep = 10 if N <= 1000 else 3
+            t = time.perf_counter()
+            otr.train(X, v, [a.copy() for a in members[0]], layers[-1], n_ep, lr, lam, adv, soft_0)
+            sec = time.perf_counter() - t
+            line["cpu_baseline"] = {"member_epochs_per_s": n_ep / sec, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"{n_ep} epochs of one member through the numpy restatement"}
+        out.append(line)
     return out
 
 

@@ -247,19 +247,26 @@ class PodnnModel:
         model.fit(X_v_train, v_train, epochs, logger, ctx=self.ctx)
         return [logger.get_logs()]
 
-    def train_ensemble(self, X_v_train, v_train, epochs, *, use_graph=True):
+    def train_ensemble(self, X_v_train, v_train, epochs, *, use_graph=True, group=None):
         """All members in the same launches (no reference counterpart: its train.py loops over the members or gives
-        one to each Horovod rank, experiments/*/train.py:30-34).  Returns the losses (epochs, n_M)."""
+        one to each Horovod rank, experiments/*/train.py:30-34).  Under an initialised torch.distributed group the
+        members are split over the ranks and the trained ensemble is all-gathered (sharded.train_ensemble_sharded).
+        Returns the losses (epochs, n_M)."""
         if self.regnn is None or len(self.regnn) == 0:
             raise ValueError("Regression model isn't defined.")
+        from .sharded import train_ensemble_sharded
         m0 = self.regnn[0]
         for m in self.regnn:
             m.set_normalize_bounds(X_v_train)
         X_n = normalize_host(X_v_train, m0.norm, m0.norm_bounds)
-        tr = EnsembleTrainer(self.ctx, [m.weights for m in self.regnn], m0.layers, X_n, v_train, m0.lr, m0.lam,
-                             m0.adv_eps, m0.soft_0, use_graph=use_graph)
-        losses = tr.run(epochs)
-        for m, w in zip(self.regnn, tr.weights()):
+
+        def train_fn(members):
+            tr = EnsembleTrainer(self.ctx, members, m0.layers, X_n, v_train, m0.lr, m0.lam, m0.adv_eps, m0.soft_0,
+                                 use_graph=use_graph)
+            losses = tr.run(epochs)
+            return tr.weights(), losses
+        weights, losses = train_ensemble_sharded(train_fn, [m.weights for m in self.regnn], group)
+        for m, w in zip(self.regnn, weights):
             m.weights = w
         return losses
 

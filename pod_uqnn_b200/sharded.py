@@ -119,3 +119,50 @@ class CudaBackend:
         v = self._empty(n, n_L)
         self.ctx.check(self.L.pb_project(self.ctx.h, V.ptr, V.ld, n_L, U.ptr, U.ld, U.shape[0], n, v.data_ptr()))
         return v
+
+
+def train_ensemble_sharded(train_fn, members, group=None):
+    """Ensemble training across ranks: the members are independent (same data, different initialisation), so rank p
+    trains the contiguous slice row_range(n_M, p, P) -- the reference's distributed mode gives one member to each
+    Horovod rank (experiments/*/train.py:19-33).  No exchange during training; afterwards the trained weights and
+    loss histories are all-gathered so that every rank holds the whole ensemble for predict_v.
+
+    `train_fn(member_slice) -> (trained_member_slice, losses (epochs, len(slice)))` is the per-rank trainer
+    (EnsembleTrainer on the GPU box; a numpy double in the gloo test).  Returns (members, losses (epochs, n_M)).
+    """
+    import torch
+    import torch.distributed as dist
+    n_M = len(members)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return train_fn(members)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = row_range(n_M, rank, world)
+    shapes = [np.shape(a) for a in members[0]]
+    per = int(sum(int(np.prod(s)) for s in shapes))
+    mine, losses = train_fn(members[lo:hi]) if hi > lo else ([], np.zeros((0, 0)))
+    epochs = int(np.shape(losses)[0]) if hi > lo else 0
+    ep = torch.tensor([epochs], dtype=torch.int64)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    ep = ep.to(dev)
+    dist.all_reduce(ep, op=dist.ReduceOp.MAX, group=group)
+    epochs = int(ep.item())
+    cap = -(-n_M // world)                                    # slots per rank (ranks with fewer members pad)
+    buf = np.zeros((cap, per + epochs))
+    for i, w in enumerate(mine):
+        buf[i, :per] = np.concatenate([np.asarray(a, dtype=np.float64).ravel() for a in w])
+        buf[i, per:] = np.asarray(losses)[:, i]
+    t = torch.from_numpy(buf).to(dev)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t, group=group)
+    out_members, out_losses = [], np.zeros((epochs, n_M))
+    for p in range(world):
+        a, b = row_range(n_M, p, world)
+        block = parts[p].cpu().numpy()
+        for i in range(b - a):
+            flat, off, w = block[i, :per], 0, []
+            for s in shapes:
+                n = int(np.prod(s))
+                w.append(flat[off:off + n].reshape(s).copy()); off += n
+            out_members.append(w)
+            out_losses[:, a + i] = block[i, per:]
+    return out_members, out_losses

@@ -104,3 +104,41 @@ def test_convert_multigpu_data(ctx, tmp_path):
     assert np.array_equal(U_va, U_va_r) and np.array_equal(X_tr, X_v[idx[:lim]])
     _, s = cmp.align_signs(model.V, Vr)
     assert cmp.rel_err(v_tr * s, po.project_to_v(Vr, U_tr_r)) <= 1e-7
+
+
+def test_workflow_gen_train_predict(ctx, tmp_path, capsys):
+    """The reference's gen.py -> train.py -> pred.py sequence (experiments/1d_shekel) on the GPU: dataset, ensemble
+    training (train_model per member as train.py:30-34, and the batched train_ensemble), prediction.  The trained
+    surrogate must beat the untrained one on the validation set and follow the oracle's training trajectory."""
+    from oracle import train as otr
+    from pod_uqnn_b200.metrics import re_s
+    from pod_uqnn_b200.varneuralnetwork import normalize_host
+    w = wl.shekel(60, 120)
+    model = PodnnModel(str(tmp_path), 1, w["x_mesh"], 0, ctx=ctx)
+    np.random.seed(11)
+    X_tr, v_tr, U_tr, X_val, v_val, U_val = model.generate_dataset(
+        "shekel", wl.SHEKEL_MU_MIN, wl.SHEKEL_MU_MAX, 120, (0.8, 0.2), eps=1e-6, mu_lhs=w["mu"])
+    model.initVNNs(3, [32, 32], 0.01, 1e-6, 0.001, soft_0=0.1, norm="meanstd", seed=77)
+    w_init = [[a.copy() for a in n.weights] for n in model.regnn]
+    for n in model.regnn:
+        n.set_normalize_bounds(X_tr)
+    v0, _ = model.predict_v(X_val)
+    err0 = re_s(v_val.T, v0.T)
+    # member 0 through the reference's per-member entry point, with its log lines.  Full-batch Adam on a ReLU net is
+    # chaotic (a 1e-15 perturbation of the oracle's own initial weights grows to 0.2 after 300 epochs), so the
+    # trajectory is compared over 15 epochs and the long run only through its loss.
+    logs = model.train_model(0, X_tr, v_tr, X_val, v_val, 15, freq=5)
+    out = capsys.readouterr().out
+    assert out.count("RE_val") == 4 and logs[0][1].shape == (4, 4)          # epochs 0, 5, 10 and the closing line
+    Xn = normalize_host(X_tr, "meanstd", (X_tr.mean(0), X_tr.std(0)))
+    w_ref, _, _ = otr.train(Xn, v_tr, w_init[0], model.n_L, 15, 0.01, 1e-6, 0.001, 0.1)
+    for a, b in zip(model.regnn[0].weights, w_ref):
+        assert np.abs(a - b).max() <= 1e-9 * max(1., np.abs(b).max())
+    # the whole ensemble in one batch (member 0 is trained further)
+    losses = model.train_ensemble(X_tr, v_tr, 300)
+    assert losses.shape == (300, 3) and np.all(losses[-1] < losses[0])
+    v1, s1 = model.predict_v(X_val)
+    err1 = re_s(v_val.T, v1.T)
+    assert err1 < 0.5 * err0 and np.all(s1 > 0)
+    U_pred, U_sig = model.predict(X_val)
+    assert U_pred.shape == U_val.shape and np.all(np.isfinite(U_sig))

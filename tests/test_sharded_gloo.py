@@ -72,3 +72,48 @@ def test_row_range_partitions():
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         sizes = [b - a for a, b in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+def _train_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pod_uqnn_b200 import sharded
+    res = sharded.train_ensemble_sharded(_numpy_trainer, _train_members(), None)
+    if rank == 1:                       # any rank holds the full ensemble afterwards
+        members, losses = res
+        np.savez(out, losses=losses, **{f"w{i}_{k}": a for i, w in enumerate(members) for k, a in enumerate(w)})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+_TRAIN_LAYERS = [2, 16, 16, 3]
+
+
+def _train_members():
+    from oracle import ensemble as ens
+    return [ens.init_weights(_TRAIN_LAYERS, seed=40 + i, bias_scale=0.1) for i in range(3)]    # 3 members on 2 ranks
+
+
+def _numpy_trainer(members):
+    """Test double of EnsembleTrainer: the oracle's training loop, member by member."""
+    from oracle import train as otr
+    rng = np.random.default_rng(9)
+    X = rng.uniform(-1, 1, (40, 2)); v = rng.standard_normal((40, 3))
+    outs, losses = [], []
+    for w in members:
+        w1, l1, _ = otr.train(X, v, [a.copy() for a in w], 3, 6, 0.01, 1e-4, 0.01, 0.5)
+        outs.append(w1); losses.append(l1)
+    return outs, np.stack(losses, 1)
+
+
+def test_member_sharded_training_equals_single_process(tmp_path):
+    """Members split 2 + 1 over two ranks, no exchange while training, all-gather of weights and losses at the end."""
+    out = str(tmp_path / "train.npz")
+    mp.spawn(_train_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    ref_members, ref_losses = _numpy_trainer(_train_members())
+    r = np.load(out)
+    np.testing.assert_array_equal(r["losses"], ref_losses)
+    for i, w in enumerate(ref_members):
+        for k, a in enumerate(w):
+            np.testing.assert_array_equal(r[f"w{i}_{k}"], a)
