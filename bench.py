@@ -244,9 +244,12 @@ def run_gpu(args):
             ctx.check(L.pb_project(ctx.h, V.ptr, V.ld, nl, U.ptr, U.ld, n_h_loc, N_S, v.ptr))
             vptr = v.ptr
         else:
-            ctx.check(L.pb_upload_async(ctx.h, U.ptr, hU, U.nbytes))
-            nl = step_resident()
-            vptr = state["v"].data_ptr()
+            # row-sharded host call: each rank's chunked upload overlaps its Gram (pb_gram_host), then the same
+            # all-reduces as the resident step
+            V, _, nl = sharded.pod_sharded(be, U, EPS, 0, MODE, A_host=hU)
+            v = sharded.project_sharded(be, V, U)
+            state["V"], state["v"], state["n_L"] = V, v, nl
+            vptr = v.data_ptr()
         ctx.check(L.pb_download_async(ctx.h, hV, state["V"].ptr, n_h_loc * nl * 8))
         ctx.check(L.pb_download_async(ctx.h, hv, vptr, N_S * nl * 8))
         ctx.sync()

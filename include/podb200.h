@@ -169,6 +169,11 @@ int  pb_pod(pb_ctx* ctx, const double* U_dev, int64_t n_h, int64_t n_st, int64_t
             double eps, int n_L_in, int mode, int* n_L);
 int  pb_pod_basis_full(pb_ctx* ctx, const double* U_dev, int64_t n_h, int64_t n_st, int64_t ldu,
                        double* V_dev, int64_t ldv);
+/* Gram of a HOST matrix, for row-sharded callers (the all-reduce of G follows): chunked upload on a copy
+ * stream overlapped with the per-chunk Gram, as pb_pod_host.  U_dev (n_h x n_st, ld n_st) receives the slab,
+ * G_dev (n_st x n_st) its Gram.  (pod.py:16 applied to one rank's rows.) */
+int  pb_gram_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, int64_t ldu_host,
+                  double* U_dev, double* G_dev);
 /* Same from a HOST matrix (pinned memory for full PCIe speed): the upload into U_dev (n_h x n_st,
  * ld = n_st, caller-allocated) is cut into row chunks on a copy stream and overlapped with the Gram. */
 int  pb_pod_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, int64_t ldu_host, double* U_dev,

@@ -59,6 +59,7 @@ SIGNATURES = {
     "pb_pod_sigma": (_int, [_vp, _vp, _i64, C.POINTER(_i64)]),
     "pb_pod_right": (_int, [_vp, _vp, _i64]),
     "pb_pod": (_int, [_vp, _vp, _i64, _i64, _i64, _dbl, _int, _int, _pi]),
+    "pb_gram_host": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "pb_pod_basis_full": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64]),
     "pb_pod_host": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _dbl, _int, _int, _pi]),
     "pb_fast_pod": (_int, [_vp, _vp, _i64, _int, _i64, _i64, _dbl, _dbl, _int, _pi, _pi]),

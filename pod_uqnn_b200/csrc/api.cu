@@ -346,27 +346,21 @@ __global__ void sum_partials_kernel(const double* __restrict__ part, int count, 
 }
 }  // namespace
 
-// POD of a HOST matrix: the upload is cut into row chunks on a copy stream and the Gram of chunk c
+// Gram of a HOST matrix: the upload is cut into row chunks on a copy stream and the Gram of chunk c
 // runs on the compute stream as soon as chunk c has landed, so the 5 ms Gram hides under the PCIe
 // transfer; the chunk Grams are summed in chunk order.  U_dev (n_h x n_st, ld = n_st) receives U.
-int pb_pod_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, int64_t ldu_host, double* U_dev,
-                double eps, int n_L_in, int mode, int* n_L) {
-    if (!ctx || !n_L || !U_host || !U_dev) return PB_ERR_ARG;
-    if (n_h <= 0 || n_st <= 0 || ldu_host < n_st) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod_host: bad shape");
+// Returns 1 when the matrix is too small / wide to chunk (nothing done).
+namespace {
+int gram_host_chunked(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, int64_t ldu_host, double* U_dev,
+                      double* G_out) {
     const int64_t chunk_rows_min = 8192;
     int nchunks = (int)std::min<int64_t>(16, n_h / chunk_rows_min);
-    if (n_h < n_st || nchunks < 2 || n_st > 8192) {        // small or wide: plain upload, then the device path
-        PB_CUDA(ctx, cudaMemcpy2DAsync(U_dev, n_st * sizeof(double), U_host, ldu_host * sizeof(double),
-                                       n_st * sizeof(double), n_h, cudaMemcpyHostToDevice, ctx->stream));
-        return pb_pod(ctx, U_dev, n_h, n_st, n_st, eps, n_L_in, mode, n_L);
-    }
-    cudaEventRecord(ctx->ev2, ctx->stream);
+    if (n_h < n_st || nchunks < 2 || n_st > 8192) return 1;
     const int64_t m = n_st;
     if (!ctx->copy_stream) {
         PB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         for (int c = 0; c < 16; ++c) PB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->chunk_ev[c], cudaEventDisableTiming));
     }
-    PB_TRY(pb_reserve(ctx, &ctx->Gbuf, &ctx->G_cap, (size_t)m * m));
     PB_TRY(pb_reserve(ctx, &ctx->Gpart, &ctx->Gpart_cap, (size_t)m * m * nchunks));
     int64_t rows_c = (n_h + nchunks - 1) / nchunks; rows_c = (rows_c + 15) / 16 * 16;
     // the copy stream must not start overwriting U_dev before earlier work on the compute stream is done
@@ -385,9 +379,39 @@ int pb_pod_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, in
         PB_TRY(pbi_gemm_tn(ctx, U_dev + r0 * n_st, n_st, m, U_dev + r0 * n_st, n_st, m, nr, ctx->Gpart + (size_t)c * m * m, m, 1));
         ++used;
     }
-    sum_partials_kernel<<<(unsigned)((m * m + 255) / 256), 256, 0, ctx->stream>>>(ctx->Gpart, used, m * m, ctx->Gbuf);
+    sum_partials_kernel<<<(unsigned)((m * m + 255) / 256), 256, 0, ctx->stream>>>(ctx->Gpart, used, m * m, G_out);
     PB_LAUNCH_CHECK(ctx);
     tg.stop();
+    return PB_OK;
+}
+}  // namespace
+
+int pb_gram_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, int64_t ldu_host, double* U_dev,
+                 double* G_dev) {
+    if (!ctx || !U_host || !U_dev || !G_dev) return PB_ERR_ARG;
+    if (n_h <= 0 || n_st <= 0 || ldu_host < n_st) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_gram_host: bad shape");
+    int rc = gram_host_chunked(ctx, U_host, n_h, n_st, ldu_host, U_dev, G_dev);
+    if (rc != 1) return rc;
+    PB_CUDA(ctx, cudaMemcpy2DAsync(U_dev, n_st * sizeof(double), U_host, ldu_host * sizeof(double),
+                                   n_st * sizeof(double), n_h, cudaMemcpyHostToDevice, ctx->stream));
+    return pb_gram(ctx, U_dev, n_h, n_st, n_st, G_dev);
+}
+
+// POD of a HOST matrix (see gram_host_chunked)
+int pb_pod_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, int64_t ldu_host, double* U_dev,
+                double eps, int n_L_in, int mode, int* n_L) {
+    if (!ctx || !n_L || !U_host || !U_dev) return PB_ERR_ARG;
+    if (n_h <= 0 || n_st <= 0 || ldu_host < n_st) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod_host: bad shape");
+    cudaEventRecord(ctx->ev2, ctx->stream);
+    const int64_t m = n_st;
+    if (n_h >= n_st) PB_TRY(pb_reserve(ctx, &ctx->Gbuf, &ctx->G_cap, (size_t)m * m));
+    int rc = gram_host_chunked(ctx, U_host, n_h, n_st, ldu_host, U_dev, ctx->Gbuf);
+    if (rc == 1) {        // small or wide: plain upload, then the device path
+        PB_CUDA(ctx, cudaMemcpy2DAsync(U_dev, n_st * sizeof(double), U_host, ldu_host * sizeof(double),
+                                       n_st * sizeof(double), n_h, cudaMemcpyHostToDevice, ctx->stream));
+        return pb_pod(ctx, U_dev, n_h, n_st, n_st, eps, n_L_in, mode, n_L);
+    }
+    if (rc != PB_OK) return rc;
     ctx->wide = false;
     PB_TRY(pod_after_gram(ctx, U_dev, n_h, m, n_st, eps, n_L_in, mode, n_L));
     cudaEventRecord(ctx->ev3, ctx->stream); cudaEventSynchronize(ctx->ev3);

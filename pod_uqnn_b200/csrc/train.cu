@@ -25,7 +25,7 @@ using namespace pbt;
 constexpr int MAXL = 8;
 constexpr int STAGES = 4;
 constexpr int NLL_BLOCKS_MAX = 256;
-constexpr int MAX_SPLITS = 16;
+constexpr int MAX_SPLITS = 24;
 
 struct LayerTab {
     int n_layers;
@@ -374,7 +374,7 @@ struct TrainState {
     TrainKey key;
     bool valid = false;
     LayerTab tab;
-    int splits = 1; int64_t rps = 0; int nll_blocks = 1;
+    int splits = 1; int64_t rps = 0; int nll_blocks = 1; bool dw_big = false;
     int64_t act_off[MAXL + 1], del_off[MAXL + 1], act_total = 0, del_total = 0;
     double* act[2] = {nullptr, nullptr}; double* del[2] = {nullptr, nullptr};
     double *xadv = nullptr, *WT = nullptr, *gpart = nullptr, *nllpart = nullptr, *regpart = nullptr, *loss = nullptr;
@@ -428,11 +428,11 @@ int launch_nn(pb_ctx* ctx, cudaStream_t st, int M, const double* A, int64_t lda,
 #undef PB_NN
 }
 
-template <bool AA, bool AB>
+template <bool BIG, bool AA, bool AB>
 int launch_dw_t(pb_ctx* ctx, cudaStream_t st, int M, const double* A, int64_t lda, int64_t sA, int ka,
                 const double* B, int64_t ldb, int64_t sB, int kb, int64_t rows, int64_t rps, int splits,
                 double* out, int64_t ldo, int64_t split_stride, int64_t sOut, double* bias_out) {
-    constexpr int BM = 64, BN = 64;
+    constexpr int BM = BIG ? 128 : 64, BN = BM;
     auto kern = train_dw_kernel<BM, BN, 2, 4, AA, AB>;
     constexpr size_t smem = (size_t)STAGES * BK * ((BM + 4) + (BN + 4)) * sizeof(double);
     if (!ctx) return set_smem(ctx, kern, smem);      // configuration pass (before any capture)
@@ -444,14 +444,18 @@ int launch_dw_t(pb_ctx* ctx, cudaStream_t st, int M, const double* A, int64_t ld
     return PB_OK;
 }
 
-int launch_dw(pb_ctx* ctx, cudaStream_t st, int M, const double* A, int64_t lda, int64_t sA, int ka,
+int launch_dw(pb_ctx* ctx, cudaStream_t st, bool big, int M, const double* A, int64_t lda, int64_t sA, int ka,
               const double* B, int64_t ldb, int64_t sB, int kb, int64_t rows, int64_t rps, int splits,
               double* out, int64_t ldo, int64_t split_stride, int64_t sOut, double* bias_out) {
     const bool aa = al16(A, lda, sA), ab = al16(B, ldb, sB);
-    if (aa && ab) return launch_dw_t<true, true>(ctx, st, M, A, lda, sA, ka, B, ldb, sB, kb, rows, rps, splits, out, ldo, split_stride, sOut, bias_out);
-    if (aa)       return launch_dw_t<true, false>(ctx, st, M, A, lda, sA, ka, B, ldb, sB, kb, rows, rps, splits, out, ldo, split_stride, sOut, bias_out);
-    if (ab)       return launch_dw_t<false, true>(ctx, st, M, A, lda, sA, ka, B, ldb, sB, kb, rows, rps, splits, out, ldo, split_stride, sOut, bias_out);
-    return launch_dw_t<false, false>(ctx, st, M, A, lda, sA, ka, B, ldb, sB, kb, rows, rps, splits, out, ldo, split_stride, sOut, bias_out);
+#define PB_DW(BIG_) \
+    (aa ? (ab ? launch_dw_t<BIG_, true, true>(ctx, st, M, A, lda, sA, ka, B, ldb, sB, kb, rows, rps, splits, out, ldo, split_stride, sOut, bias_out) \
+              : launch_dw_t<BIG_, true, false>(ctx, st, M, A, lda, sA, ka, B, ldb, sB, kb, rows, rps, splits, out, ldo, split_stride, sOut, bias_out)) \
+        : (ab ? launch_dw_t<BIG_, false, true>(ctx, st, M, A, lda, sA, ka, B, ldb, sB, kb, rows, rps, splits, out, ldo, split_stride, sOut, bias_out) \
+              : launch_dw_t<BIG_, false, false>(ctx, st, M, A, lda, sA, ka, B, ldb, sB, kb, rows, rps, splits, out, ldo, split_stride, sOut, bias_out)))
+    if (big) return PB_DW(true);
+    return PB_DW(false);
+#undef PB_DW
 }
 
 // opt every instantiation into its dynamic shared memory once, outside any stream capture
@@ -466,10 +470,14 @@ int configure_nn() {
 int configure_all() {
     int rc = configure_nn<128, 64, 4, 2>();
     if (rc == PB_OK) rc = configure_nn<32, 64, 2, 4>();
-    if (rc == PB_OK) rc = launch_dw_t<true, true>(nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
-    if (rc == PB_OK) rc = launch_dw_t<true, false>(nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
-    if (rc == PB_OK) rc = launch_dw_t<false, true>(nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
-    if (rc == PB_OK) rc = launch_dw_t<false, false>(nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+    if (rc == PB_OK) rc = launch_dw_t<false, true, true>(nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+    if (rc == PB_OK) rc = launch_dw_t<true, true, true>(nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+    if (rc == PB_OK) rc = launch_dw_t<false, true, false>(nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+    if (rc == PB_OK) rc = launch_dw_t<true, true, false>(nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+    if (rc == PB_OK) rc = launch_dw_t<false, false, true>(nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+    if (rc == PB_OK) rc = launch_dw_t<true, false, true>(nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+    if (rc == PB_OK) rc = launch_dw_t<false, false, false>(nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+    if (rc == PB_OK) rc = launch_dw_t<true, false, false>(nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
     return rc;
 }
 
@@ -521,7 +529,7 @@ int run_epoch(pb_ctx* ctx, TrainState& s) {
                 const double* A = (l == 0) ? in0 : s.act[p] + s.act_off[l];
                 const int64_t sA = (l == 0) ? s_in0 : N * k.dims[l];
                 double* gp = s.gpart + (int64_t)p * s.splits * M * s.tab.P;
-                PB_TRY(launch_dw(ctx, s.side, M, A, k.dims[l], sA, k.dims[l], D, k.dims[l + 1], sD, k.dims[l + 1], N,
+                PB_TRY(launch_dw(ctx, s.side, s.dw_big, M, A, k.dims[l], sA, k.dims[l], D, k.dims[l + 1], sD, k.dims[l + 1], N,
                                  s.rps, s.splits, gp + s.tab.off_w[l], k.dims[l + 1], (int64_t)M * s.tab.P, s.tab.P,
                                  gp + s.tab.off_b[l]));
             }
@@ -612,14 +620,20 @@ extern "C" int pb_ensemble_train(pb_ctx* ctx, int n_members, int n_layers, const
         s.act_total = 0; s.del_total = 0;
         for (int l = 1; l < L; ++l) { s.act_off[l] = s.act_total; s.act_total += (int64_t)M * N * dims[l]; }
         for (int l = 0; l < L; ++l) { s.del_off[l] = s.del_total; s.del_total += (int64_t)M * N * dims[l + 1]; }
-        // split-K of the weight gradients: fill the SMs, at least 64 rows per split
-        int tiles = 0;
-        for (int l = 0; l < L; ++l) tiles = std::max(tiles, ((dims[l] + 63) / 64) * ((dims[l + 1] + 63) / 64));
-        int want = std::max(1, ctx->sm_count / std::max(1, tiles * M));
-        want = std::min(want, MAX_SPLITS);
-        int64_t rps = (N + want - 1) / want;
-        rps = std::max<int64_t>(64, ((rps + BK - 1) / BK) * BK);
-        s.rps = rps; s.splits = (int)((N + rps - 1) / rps);
+        // split-K of the weight gradients: fill the SMs, at least 64 rows per split.  Large batches take 128 x 128
+        // tiles (half the operand traffic per flop: the 64 x 64 tiles are HBM / L2 bound there).
+        {
+            static const int force = getenv("PB_TRAIN_DW") ? atoi(getenv("PB_TRAIN_DW")) : 0;   // 1 small, 2 big
+            s.dw_big = force ? (force == 2) : ((int64_t)N * M >= 65536);
+            const int bt = s.dw_big ? 128 : 64;
+            int tiles = 0;
+            for (int l = 0; l < L; ++l) tiles = std::max(tiles, ((dims[l] + bt - 1) / bt) * ((dims[l + 1] + bt - 1) / bt));
+            int want = std::max(1, ctx->sm_count / std::max(1, tiles * M));
+            want = std::min(want, MAX_SPLITS);
+            int64_t rps = (N + want - 1) / want;
+            rps = std::max<int64_t>(64, ((rps + BK - 1) / BK) * BK);
+            s.rps = rps; s.splits = (int)((N + rps - 1) / rps);
+        }
         const int n_pass = key.n_pass;
         for (int p = 0; p < n_pass; ++p) {
             PB_TRY(reserve(ctx, &s.act[p], &s.cap_act[p], (size_t)std::max<int64_t>(s.act_total, 2)));

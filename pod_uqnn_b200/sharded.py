@@ -34,9 +34,12 @@ def _all_reduce(t, group=None):
     return t
 
 
-def pod_sharded(backend, A_local, eps=0., n_L=0, mode="gram", group=None):
-    """POD of the row-sharded tall matrix.  Returns (V_local, sigma, n_L)."""
-    G = backend.gram(A_local)
+def pod_sharded(backend, A_local, eps=0., n_L=0, mode="gram", group=None, A_host=None):
+    """POD of the row-sharded tall matrix.  Returns (V_local, sigma, n_L).
+
+    `A_host` (address of this rank's slab in pinned host memory, same shape as `A_local`): the slab is uploaded into
+    `A_local` in row chunks overlapped with the chunk Grams (pb_gram_host) instead of being read from HBM."""
+    G = backend.gram(A_local) if A_host is None else backend.gram_host(A_host, A_local)
     backend.reduce(G, group)
     n_L_out, keep = backend.pod_from_gram(G, eps, n_L, mode)
     Y = None
@@ -64,9 +67,19 @@ class CudaBackend:
         self.dev = torch.device("cuda", ctx.device)
         self.L = _lib.lib()
         self._cache = {}
+        # the library and NCCL share one torch stream: the all-reduces are ordered against the kernels on the
+        # device (NCCL's stream waits on / is waited for by this stream through events), no host synchronisation
+        self.stream = torch.cuda.Stream(self.dev)
+        ctx.check(self.L.pb_set_stream(ctx.h, C.c_void_p(self.stream.cuda_stream)))
+
+    def close(self):
+        """Give the context its own stream back."""
+        self.stream.synchronize()
+        self.ctx.check(self.L.pb_set_stream(self.ctx.h, None))
 
     def _empty(self, *shape):
-        return self.torch.empty(*shape, dtype=self.torch.float64, device=self.dev)
+        with self.torch.cuda.stream(self.stream):
+            return self.torch.empty(*shape, dtype=self.torch.float64, device=self.dev)
 
     def _buf(self, name, *shape):
         """Library-owned HBM buffer reused across steps (cudaMalloc / cudaFree synchronise the device)."""
@@ -76,15 +89,19 @@ class CudaBackend:
         return b
 
     def reduce(self, t, group=None):
-        # the library runs on its own stream: order it before NCCL, and NCCL before the next kernel
-        self.ctx.sync()
-        _all_reduce(t, group)
-        self.torch.cuda.current_stream(self.dev).synchronize()
+        with self.torch.cuda.stream(self.stream):
+            _all_reduce(t, group)
 
     def gram(self, A):
         m = A.shape[1]
         G = self._empty(m, m)
         self.ctx.check(self.L.pb_gram(self.ctx.h, A.ptr, A.shape[0], m, A.ld, G.data_ptr()))
+        return G
+
+    def gram_host(self, host_ptr, A):
+        m = A.shape[1]
+        G = self._empty(m, m)
+        self.ctx.check(self.L.pb_gram_host(self.ctx.h, host_ptr, A.shape[0], m, m, A.ptr, G.data_ptr()))
         return G
 
     def pod_from_gram(self, G, eps, n_L, mode):

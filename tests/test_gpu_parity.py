@@ -204,6 +204,41 @@ def test_logical_shards_equal_unsharded(ctx):
     assert cmp.largest_principal_angle(V, V1) <= 1e-10
 
 
+def test_gram_host_and_cuda_backend(ctx):
+    """pb_gram_host (chunked upload overlapped with the chunk Grams; plain upload when too small to chunk) equals
+    pb_gram of the resident slab, and sharded.CudaBackend (library and NCCL on one torch stream) reproduces the
+    single-GPU POD when there is no process group."""
+    from pod_uqnn_b200 import sharded
+    L = _lib.lib()
+    rng = np.random.default_rng(12)
+    for n_h, m in ((40000, 96), (700, 64)):                 # 4 chunks of 10 000 rows; too small: fallback
+        U = rng.standard_normal((n_h, m))
+        Ud, Gd, G2d, Uh = ctx.to_device(U), ctx.alloc(m, m), ctx.alloc(m, m), ctx.alloc(n_h, m)
+        ctx.check(L.pb_gram(ctx.h, Ud.ptr, n_h, m, m, Gd.ptr))
+        ctx.check(L.pb_gram_host(ctx.h, U.ctypes.data, n_h, m, m, Uh.ptr, G2d.ptr))
+        assert np.array_equal(Uh.download(), U)
+        G, G2 = Gd.download(), G2d.download()
+        assert np.abs(G - G2).max() <= 1e-13 * np.abs(G).max()
+        assert np.abs(G - U.T @ U).max() <= 1e-12 * np.abs(G).max()
+    g = load_golden("pod_ackley_64")
+    _, U, _, _ = regen(g, "ackley")
+    be = sharded.CudaBackend(ctx)
+    try:
+        Ud = ctx.to_device(U)
+        V, sig, n_L = sharded.pod_sharded(be, Ud, 1e-10, 0, "gram2")
+        v = sharded.project_sharded(be, V, Ud)
+        be.stream.synchronize()
+        assert n_L == g["V"].shape[1]
+        assert cmp.largest_principal_angle(V.download(), g["V"]) <= cmp.TOL_ANGLE
+        assert cmp.rel_err(v.cpu().numpy(), po.project_to_v(V.download(), U)) <= 1e-12
+        Uh = ctx.alloc(*U.shape)
+        V2, _, n2 = sharded.pod_sharded(be, Uh, 1e-10, 0, "gram2", A_host=np.ascontiguousarray(U).ctypes.data)
+        be.stream.synchronize()
+        assert n2 == n_L and cmp.largest_principal_angle(V2.download(), V.download()) <= 1e-10
+    finally:
+        be.close()
+
+
 # ------------------------------------------------------------------ projection / reconstruction
 def test_projection_reconstruction_pod_sig(ctx):
     g = load_golden("pod_ackley_64")
