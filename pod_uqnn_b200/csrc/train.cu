@@ -32,9 +32,62 @@ struct LayerTab {
     int in[MAXL], out[MAXL];
     long long off_w[MAXL], off_b[MAXL], off_wt[MAXL];
     long long P, PT;
+    // fused path: packed weight streams (see train_fused_kernel)
+    int fused;
+    long long pk_f[MAXL], pk_b[MAXL], SP;
 };
 
+constexpr int FPITCH = 132;                 // pitch of the staged activations and of the packed weight rows
+constexpr int FCH = BK * FPITCH;            // one packed K chunk: 16 rows x 132 doubles = 16 896 B
+constexpr int FRING = 4;
+
+// where parameter p of a member lives in the derived layouts: the transposed kernels (layer-by-layer path) or the
+// packed forward / backward streams (fused path)
+__device__ __forceinline__ void scatter_param(const LayerTab& tab, double* __restrict__ WT, double* __restrict__ packed,
+                                              int mem, long long p, double val) {
+    for (int l = 0; l < tab.n_layers; ++l) {
+        const long long q = p - tab.off_w[l];
+        if (q >= 0 && q < (long long)tab.in[l] * tab.out[l]) {
+            const int i = (int)(q / tab.out[l]), j = (int)(q % tab.out[l]);
+            if (tab.fused) {
+                double* pk = packed + (long long)mem * tab.SP;
+                pk[tab.pk_f[l] + (long long)(i / BK) * FCH + (i % BK) * FPITCH + j] = val;
+                pk[tab.pk_b[l] + (long long)(j / BK) * FCH + (j % BK) * FPITCH + i] = val;
+            } else {
+                WT[(long long)mem * tab.PT + tab.off_wt[l] + (long long)j * tab.in[l] + i] = val;
+            }
+            return;
+        }
+        const long long qb = p - tab.off_b[l];
+        if (tab.fused && qb >= 0 && qb < tab.out[l]) {
+            const int nk = (tab.in[l] + BK - 1) / BK;
+            packed[(long long)mem * tab.SP + tab.pk_f[l] + (long long)nk * FCH + qb] = val;
+            return;
+        }
+    }
+}
+
 enum { EPI_BIAS_RELU = 0, EPI_BIAS = 1, EPI_MASK = 2, EPI_SIGN = 3 };
+
+// Programmatic dependent launch: every kernel of the epoch lets its successor's CTAs become resident at once and
+// then waits for its own predecessors' writes before touching global memory, so launch latency, block
+// scheduling and the prologue overlap the previous kernel's tail (the epoch is a chain of ~5 us kernels).
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+bool g_pdl = false;   // measured: no gain at N = 400 (68.4 -> 69.2 us), a loss at N = 4000 (641 -> 748 us): early-resident CTAs steal SM slots
 
 // ---------------------------------------------------------------------------
 // Y (rows x k) = A (rows x m) B (m x k) with a fused epilogue; blockIdx.z = member
@@ -46,6 +99,7 @@ train_nn_kernel(const double* __restrict__ A, int64_t lda, int64_t sA, int64_t r
                 double* __restrict__ Y, int64_t ldy, int64_t sY,
                 int epi, const double* __restrict__ aux, int64_t ldaux, int64_t sAux, double eps) {
     static_assert(WARPS_M * WARPS_N == NTHREADS / 32, "8 warps");
+    pdl_prologue();
     constexpr int PA = BK + 4, PB = BN + 4;
     constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
     constexpr int TM = WM / 8, TNN = WN / 8;
@@ -140,6 +194,7 @@ train_dw_kernel(const double* __restrict__ A, int64_t lda, int64_t sA, int ka,
                 double* __restrict__ out, int64_t ldo, int64_t split_stride, int64_t sOut,
                 double* __restrict__ bias_out, int tiles_n) {
     static_assert(WARPS_M * WARPS_N == NTHREADS / 32, "8 warps");
+    pdl_prologue();
     constexpr int PA = BM + 4, PB = BN + 4;
     constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
     constexpr int TM = WM / 8, TNN = WN / 8;
@@ -232,6 +287,7 @@ train_dw_kernel(const double* __restrict__ A, int64_t lda, int64_t sA, int ka,
 __global__ void __launch_bounds__(256)
 train_nll_kernel(double* __restrict__ T, int64_t sT, const double* __restrict__ v, int64_t N, int n_L,
                  double soft_0, double* __restrict__ nllpart) {
+    pdl_prologue();
     T += (int64_t)blockIdx.y * sT;
     const int64_t total = N * n_L;
     double s = 0.;
@@ -267,10 +323,12 @@ train_nll_kernel(double* __restrict__ T, int64_t sT, const double* __restrict__ 
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 train_adam_kernel(LayerTab tab, double* __restrict__ params, double* __restrict__ am, double* __restrict__ av,
-                  double* __restrict__ WT, const double* __restrict__ gpart, int n_pass, int n_term, int splits, int M,
+                  double* __restrict__ WT, double* __restrict__ packed, const double* __restrict__ gpart, int n_pass,
+                  int n_term, int splits, int M,
                   double lr, double lam, long long* __restrict__ tstep, int* __restrict__ eidx,
                   const double* __restrict__ nllpart, int nll_blocks, double* __restrict__ regpart,
                   unsigned* __restrict__ ticket, double* __restrict__ loss, int update) {
+    pdl_prologue();
     const int mem = blockIdx.y;
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     __shared__ double s_lrt;
@@ -298,24 +356,9 @@ train_adam_kernel(LayerTab tab, double* __restrict__ params, double* __restrict_
             *mp = mn; *vp = vn;
             const double wn = w0 - s_lrt * mn / (sqrt(vn) + 1e-7);
             *w = wn;
-            // transposed copy of the kernels
-            for (int l = 0; l < tab.n_layers; ++l) {
-                const long long q = p - tab.off_w[l];
-                if (q >= 0 && q < (long long)tab.in[l] * tab.out[l]) {
-                    const int i = (int)(q / tab.out[l]), j = (int)(q % tab.out[l]);
-                    WT[(long long)mem * tab.PT + tab.off_wt[l] + (long long)j * tab.in[l] + i] = wn;
-                    break;
-                }
-            }
+            scatter_param(tab, WT, packed, mem, p, wn);
         } else {
-            for (int l = 0; l < tab.n_layers; ++l) {
-                const long long q = p - tab.off_w[l];
-                if (q >= 0 && q < (long long)tab.in[l] * tab.out[l]) {
-                    const int i = (int)(q / tab.out[l]), j = (int)(q % tab.out[l]);
-                    WT[(long long)mem * tab.PT + tab.off_wt[l] + (long long)j * tab.in[l] + i] = w0;
-                    break;
-                }
-            }
+            scatter_param(tab, WT, packed, mem, p, w0);
         }
     }
     if (!update) return;
@@ -357,6 +400,405 @@ train_adam_kernel(LayerTab tab, double* __restrict__ params, double* __restrict_
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Fused forward + NLL + delta chain (+ FGSM input and the second pass) for one (member, row tile): the activations
+// stay in shared memory from the input to the input gradient, the ReLU masks stay in registers, and the weights
+// arrive as a continuous packed stream (forward kernels + bias rows, then the transposed kernels in reverse layer
+// order) through a 4-slot cp.async.bulk / mbarrier ring filled by a producer warp that runs ahead across layer,
+// pass and tile boundaries.  Only what the weight-gradient products need goes to global memory: H_l, delta_l and
+// X_adv.  Requires every width <= 128 (one 128-column chunk per layer); wider nets take the layer-by-layer path.
+// ---------------------------------------------------------------------------
+struct FusedArgs {
+    int M, L, n_L, n_pass, n_tiles;
+    long long N;
+    int dims[MAXL + 1];
+    const double* packed; long long SP; long long pk_f[MAXL], pk_b[MAXL];
+    const double* X; const double* v;
+    double* xadv;
+    double* act[2]; double* del[2];
+    long long act_off[MAXL + 1], del_off[MAXL + 1];
+    double* nllpart;
+    double adv_eps, soft_0;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+
+constexpr int FUSED_THREADS = 288;          // 8 consumer warps + 1 producer warp
+
+template <int MT>
+__global__ void __launch_bounds__(FUSED_THREADS, (MT <= 32) ? 2 : 1) train_fused_kernel(FusedArgs a) {
+    constexpr int TM = MT / 8;              // m8 row blocks per warp (every warp covers all MT rows, 16 columns)
+    extern __shared__ __align__(16) double smem[];
+    double* act = smem;                                   // [MT][FPITCH]
+    double* ring = smem + MT * FPITCH;                    // [FRING][FCH]
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + FRING * FCH);
+    uint64_t* empty = full + FRING;
+    double* red = reinterpret_cast<double*>(empty + FRING);   // [8]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < FRING; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncthreads();
+    const int L = a.L, n_L = a.n_L;
+    const long long n_items = (long long)a.M * a.n_tiles;
+
+    if (warp == 8) {
+        // ------------------------------------------------ producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int mem = (int)(item / a.n_tiles);
+                const double* base = a.packed + (long long)mem * a.SP;
+                for (int pass = 0; pass < a.n_pass; ++pass) {
+                    for (int l = 0; l < L; ++l) {                       // forward kernels, each followed by its bias row
+                        const int nk = (a.dims[l] + BK - 1) / BK;
+                        const double* src = base + a.pk_f[l];
+                        for (int kc = 0; kc <= nk; ++kc, ++it) {
+                            const int s = it % FRING; const uint32_t ph = (it / FRING) & 1;
+                            const uint32_t bytes = (kc < nk ? FCH : FPITCH) * 8;
+                            mbar_wait(empty + s, ph ^ 1);
+                            mbar_expect_tx(full + s, bytes);
+                            bulk_load(ring + (size_t)s * FCH, src + (size_t)kc * FCH, bytes, full + s);
+                        }
+                    }
+                    const int l_last = (pass == 0 && a.n_pass == 2) ? 0 : 1;
+                    for (int l = L - 1; l >= l_last; --l) {             // transposed kernels for the delta chain
+                        const int nk = (a.dims[l + 1] + BK - 1) / BK;
+                        const double* src = base + a.pk_b[l];
+                        for (int kc = 0; kc < nk; ++kc, ++it) {
+                            const int s = it % FRING; const uint32_t ph = (it / FRING) & 1;
+                            mbar_wait(empty + s, ph ^ 1);
+                            mbar_expect_tx(full + s, FCH * 8);
+                            bulk_load(ring + (size_t)s * FCH, src + (size_t)kc * FCH, FCH * 8, full + s);
+                        }
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------- consumers: warp w owns columns [16 w, 16 w + 16)
+    const int lk = lane & 3, lg = lane >> 2;
+    const int n_d = a.dims[0];
+    uint32_t it = 0;
+    double acc[TM][2][2];
+
+    // acc = act(:, 0:16 nk) * (nk packed chunks from the ring); warps whose 16 columns lie beyond `ncols` only keep the
+    // ring moving (narrow outputs: the head, the input gradient)
+    auto gemm = [&](int nk, int ncols) {
+        const bool active = warp * 16 < ncols;
+#pragma unroll
+        for (int t = 0; t < TM; ++t)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) { acc[t][u][0] = 0.; acc[t][u][1] = 0.; }
+#pragma unroll 1
+        for (int kt = 0; kt < nk; ++kt, ++it) {
+            const int s = it % FRING; const uint32_t ph = (it / FRING) & 1;
+            mbar_wait(full + s, ph);
+            const double* as = act + lg * FPITCH + kt * BK + lk;
+            const double* bs = ring + (size_t)s * FCH + warp * 16 + lg;
+            if (active)
+#pragma unroll
+            for (int kk = 0; kk < BK / 4; ++kk) {
+                double af[TM], bf[2];
+#pragma unroll
+                for (int t = 0; t < TM; ++t) af[t] = as[t * 8 * FPITCH + kk * 4];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) bf[u] = bs[(kk * 4 + lk) * FPITCH + u * 8];
+#pragma unroll
+                for (int t = 0; t < TM; ++t)
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) dmma884(acc[t][u][0], acc[t][u][1], af[t], bf[u]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + s);
+        }
+    };
+
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int mem = (int)(item / a.n_tiles);
+        const int tile = (int)(item % a.n_tiles);
+        const long long r0 = (long long)tile * MT;
+        const int kin0 = (n_d + BK - 1) / BK * BK;
+        // input tile, zero padded to 16 columns and to MT rows
+        for (int e = tid; e < MT * kin0; e += 256) {
+            const int r = e / kin0, c = e % kin0;
+            act[r * FPITCH + c] = (c < n_d && r0 + r < a.N) ? a.X[(r0 + r) * n_d + c] : 0.;
+        }
+        consumer_sync();
+        for (int pass = 0; pass < a.n_pass; ++pass) {
+            uint32_t mask[MAXL];               // ReLU masks of the hidden layers, one bit per accumulator element
+            // ---------------- forward
+            for (int l = 0; l < L; ++l) {
+                const int in = a.dims[l], out = a.dims[l + 1];
+                const bool head = (l == L - 1);
+                gemm((in + BK - 1) / BK, out);
+                const int sb = it % FRING; const uint32_t phb = (it / FRING) & 1;
+                ++it;
+                mbar_wait(full + sb, phb);
+                const double* bias = ring + (size_t)sb * FCH;
+                consumer_sync();               // every warp has finished reading act for this layer
+                const int outp = (out + BK - 1) / BK * BK;
+                double* gout = head ? nullptr : a.act[pass] + a.act_off[l + 1] + ((long long)mem * a.N + r0) * out;
+                uint32_t mk = 0;
+#pragma unroll
+                for (int t = 0; t < TM; ++t) {
+                    const int r = t * 8 + lg;
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int n = warp * 16 + u * 8 + 2 * lk;
+                        double x0 = acc[t][u][0] + bias[n], x1 = acc[t][u][1] + bias[n + 1];
+                        if (!head) {
+                            x0 = fmax(x0, 0.); x1 = fmax(x1, 0.);
+                            mk |= (x0 > 0. ? 1u : 0u) << (t * 4 + u * 2);
+                            mk |= (x1 > 0. ? 1u : 0u) << (t * 4 + u * 2 + 1);
+                        }
+                        if (n >= out) x0 = 0.;
+                        if (n + 1 >= out) x1 = 0.;
+                        if (n < outp) *reinterpret_cast<double2*>(act + r * FPITCH + n) = make_double2(x0, x1);
+                        if (!head && r0 + r < a.N) {
+                            if (n + 1 < out && !(out & 1)) *reinterpret_cast<double2*>(gout + (long long)r * out + n) = make_double2(x0, x1);
+                            else { if (n < out) gout[(long long)r * out + n] = x0; if (n + 1 < out) gout[(long long)r * out + n + 1] = x1; }
+                        }
+                    }
+                }
+                if (!head) mask[l] = mk;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + sb);
+                consumer_sync();               // the next layer's input is complete
+            }
+            // ---------------- NLL and head gradient, in place on the staged head outputs
+            {
+                const int w2 = 2 * n_L;
+                double* gd = a.del[pass] + a.del_off[L - 1] + ((long long)mem * a.N + r0) * w2;
+                double sacc = 0.;
+                for (int e = tid; e < MT * n_L; e += 256) {
+                    const int r = e / n_L, j = e % n_L;
+                    double* row = act + r * FPITCH;
+                    double d0 = 0., d1 = 0.;
+                    if (r0 + r < a.N) {
+                        const double loc = row[j], z = a.soft_0 * row[n_L + j];
+                        const double ex = exp(-fabs(z));
+                        const double scale = fmax(z, 0.) + log1p(ex) + 1e-6;
+                        const double inv = 1. / scale;
+                        const double rr = (a.v[(r0 + r) * n_L + j] - loc) * inv;
+                        sacc += 0.5 * rr * rr + log(scale) + 0.91893853320467274178;
+                        const double sg = (z >= 0.) ? 1. / (1. + ex) : ex / (1. + ex);
+                        d0 = -rr * inv;
+                        d1 = (1. - rr * rr) * inv * a.soft_0 * sg;
+                        gd[(long long)r * w2 + j] = d0;
+                        gd[(long long)r * w2 + n_L + j] = d1;
+                    }
+                    row[j] = d0; row[n_L + j] = d1;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+                if (lane == 0) red[warp] = sacc;
+                consumer_sync();
+                if (tid == 0) {
+                    double tsum = 0.;
+                    for (int w = 0; w < 8; ++w) tsum += red[w];
+                    a.nllpart[((long long)pass * a.M + mem) * a.n_tiles + tile] = tsum;
+                }
+            }
+            // ---------------- delta chain (and the FGSM input after the first pass)
+            const int l_last = (pass == 0 && a.n_pass == 2) ? 0 : 1;
+            for (int l = L - 1; l >= l_last; --l) {
+                const int in = a.dims[l], out = a.dims[l + 1];     // delta_l (MT x out) -> delta_{l-1} (MT x in)
+                gemm((out + BK - 1) / BK, in);
+                consumer_sync();
+                const int inp = (in + BK - 1) / BK * BK;
+                if (l > 0) {
+                    double* gout = a.del[pass] + a.del_off[l - 1] + ((long long)mem * a.N + r0) * in;
+                    const uint32_t mk = mask[l - 1];
+#pragma unroll
+                    for (int t = 0; t < TM; ++t) {
+                        const int r = t * 8 + lg;
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int n = warp * 16 + u * 8 + 2 * lk;
+                            double x0 = ((mk >> (t * 4 + u * 2)) & 1u) ? acc[t][u][0] : 0.;
+                            double x1 = ((mk >> (t * 4 + u * 2 + 1)) & 1u) ? acc[t][u][1] : 0.;
+                            if (n >= in) x0 = 0.;
+                            if (n + 1 >= in) x1 = 0.;
+                            if (n < inp) *reinterpret_cast<double2*>(act + r * FPITCH + n) = make_double2(x0, x1);
+                            if (r0 + r < a.N) {
+                                if (n + 1 < in && !(in & 1)) *reinterpret_cast<double2*>(gout + (long long)r * in + n) = make_double2(x0, x1);
+                                else { if (n < in) gout[(long long)r * in + n] = x0; if (n + 1 < in) gout[(long long)r * in + n + 1] = x1; }
+                            }
+                        }
+                    }
+                } else {
+                    // X_adv = X + adv_eps sign(d loss / d X): the next pass's input, and the A operand of its dW_0
+                    double* gx = a.xadv + ((long long)mem * a.N + r0) * n_d;
+#pragma unroll
+                    for (int t = 0; t < TM; ++t) {
+                        const int r = t * 8 + lg;
+#pragma unroll
+                        for (int u = 0; u < 2; ++u)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int n = warp * 16 + u * 8 + 2 * lk + e;
+                                if (n >= inp) continue;
+                                double x = 0.;
+                                if (n < n_d && r0 + r < a.N) {
+                                    const double g = acc[t][u][e];
+                                    x = a.X[(r0 + r) * n_d + n] + a.adv_eps * ((g > 0.) ? 1. : ((g < 0.) ? -1. : 0.));
+                                    gx[(long long)r * n_d + n] = x;
+                                }
+                                act[r * FPITCH + n] = x;
+                            }
+                    }
+                }
+                consumer_sync();
+            }
+        }
+        consumer_sync();       // act is overwritten by the next item's input tile
+    }
+}
+
+// ---------------------------------------------------------------------------
+// All weight-gradient products of an epoch in one launch: jobs = (pass, layer), each cut into tiles and split-K
+// row ranges like train_dw_kernel.  blockIdx.x = (job, tile), blockIdx.y = split, blockIdx.z = member.
+// ---------------------------------------------------------------------------
+struct DwJob {
+    const double* A; const double* B;
+    long long lda, sA, ldb, sB, out_off, bias_off;
+    int ka, kb, tiles_n, tile0, alignA, alignB;
+};
+struct DwJobs { int n_jobs; DwJob job[2 * MAXL]; };
+
+template <int BM, int BN, int WARPS_M, int WARPS_N>
+__global__ void __launch_bounds__(NTHREADS)
+train_dw_multi_kernel(DwJobs jobs, int64_t rows, int64_t rows_per_split, double* __restrict__ gpart,
+                      int64_t split_stride, int64_t sOut) {
+    constexpr int PA = BM + 4, PB = BN + 4;
+    constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
+    constexpr int TM = WM / 8, TNN = WN / 8;
+    int jb = 0;
+    while (jb + 1 < jobs.n_jobs && (int)blockIdx.x >= jobs.job[jb + 1].tile0) ++jb;
+    const DwJob& J = jobs.job[jb];
+    const double* A = J.A + (int64_t)blockIdx.z * J.sA;
+    const double* B = J.B + (int64_t)blockIdx.z * J.sB;
+    double* base = gpart + (int64_t)blockIdx.z * sOut + (int64_t)blockIdx.y * split_stride;
+    double* out = base + J.out_off;
+    double* bias_out = base + J.bias_off;
+    const int ka = J.ka, kb = J.kb;
+    const int64_t lda = J.lda, ldb = J.ldb, ldo = kb;
+    extern __shared__ __align__(16) double smem[];
+    double* As = smem;
+    double* Bs = smem + STAGES * BK * PA;
+    const int tl = blockIdx.x - J.tile0;
+    const int ti = tl / J.tiles_n, tj = tl % J.tiles_n;
+    const int64_t i0 = (int64_t)ti * BM, j0 = (int64_t)tj * BN;
+    const int64_t r_begin = (int64_t)blockIdx.y * rows_per_split;
+    const int64_t r_end = min(rows, r_begin + rows_per_split);
+    const int nk = (r_end > r_begin) ? (int)((r_end - r_begin + BK - 1) / BK) : 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp / WARPS_N, wn = warp % WARPS_N;
+    const int lk = lane & 3, lg = lane >> 2;
+    const bool alA = J.alignA != 0, alB = J.alignB != 0;
+    // m8 / n8 blocks of this warp that hold valid rows / columns (narrow layers: the input layer has ka = n_d rows)
+    const int t_cnt = max(0, min(TM, (int)((ka - i0 - wm * WM + 7) / 8)));
+    const int u_cnt = max(0, min(TNN, (int)((kb - j0 - wn * WN + 7) / 8)));
+    const bool full_tile = (t_cnt == TM) && (u_cnt == TNN), any_tile = (t_cnt > 0) && (u_cnt > 0);
+
+    double acc[TM][TNN][2];
+#pragma unroll
+    for (int t = 0; t < TM; ++t)
+#pragma unroll
+        for (int u = 0; u < TNN; ++u) { acc[t][u][0] = 0.; acc[t][u][1] = 0.; }
+    double csum = 0.;
+    const bool do_bias = (ti == 0) && tid < BN;
+
+    auto stage = [&](int s, int64_t r0) {
+        if (alA) load_tile<BK, BM, PA, true>(As + s * BK * PA, A, lda, r0, r_end, i0, ka, tid);
+        else     load_tile<BK, BM, PA, false>(As + s * BK * PA, A, lda, r0, r_end, i0, ka, tid);
+        if (alB) load_tile<BK, BN, PB, true>(Bs + s * BK * PB, B, ldb, r0, r_end, j0, kb, tid);
+        else     load_tile<BK, BN, PB, false>(Bs + s * BK * PB, B, ldb, r0, r_end, j0, kb, tid);
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nk) stage(s, r_begin + (int64_t)s * BK);
+        cp_async_commit();
+    }
+    for (int k = 0; k < nk; ++k) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int kn = k + STAGES - 1;
+            if (kn < nk) stage(kn % STAGES, r_begin + (int64_t)kn * BK);
+            cp_async_commit();
+        }
+        const double* as = As + (k % STAGES) * BK * PA + wm * WM + lg;
+        const double* bs = Bs + (k % STAGES) * BK * PB + wn * WN + lg;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            double av[TM], bv[TNN];
+#pragma unroll
+            for (int t = 0; t < TM; ++t) av[t] = as[(kk * 4 + lk) * PA + t * 8];
+#pragma unroll
+            for (int u = 0; u < TNN; ++u) bv[u] = bs[(kk * 4 + lk) * PB + u * 8];
+            if (full_tile) {
+#pragma unroll
+                for (int t = 0; t < TM; ++t)
+#pragma unroll
+                    for (int u = 0; u < TNN; ++u) dmma884(acc[t][u][0], acc[t][u][1], av[t], bv[u]);
+            } else if (any_tile) {
+#pragma unroll
+                for (int t = 0; t < TM; ++t)
+                    if (t < t_cnt)
+#pragma unroll
+                        for (int u = 0; u < TNN; ++u)
+                            if (u < u_cnt) dmma884(acc[t][u][0], acc[t][u][1], av[t], bv[u]);
+            }
+        }
+        if (do_bias) {
+            const double* bc = Bs + (k % STAGES) * BK * PB + tid;
+#pragma unroll
+            for (int r = 0; r < BK; ++r) csum += bc[r * PB];
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int t = 0; t < TM; ++t) {
+        int64_t i = i0 + wm * WM + t * 8 + lg;
+        if (i >= ka) continue;
+#pragma unroll
+        for (int u = 0; u < TNN; ++u) {
+            int64_t j = j0 + wn * WN + u * 8 + 2 * lk;
+            if (j < kb)     out[i * ldo + j]     = acc[t][u][0];
+            if (j + 1 < kb) out[i * ldo + j + 1] = acc[t][u][1];
+        }
+    }
+    if (do_bias && j0 + tid < kb) bias_out[j0 + tid] = csum;
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -375,6 +817,9 @@ struct TrainState {
     bool valid = false;
     LayerTab tab;
     int splits = 1; int64_t rps = 0; int nll_blocks = 1; bool dw_big = false;
+    bool fused = false; int mt = 64, n_tiles = 0, fused_grid = 0;       // fused forward/backward path
+    double* packed = nullptr; size_t cap_packed = 0;
+    DwJobs jobs; int dw_tiles = 0;
     int64_t act_off[MAXL + 1], del_off[MAXL + 1], act_total = 0, del_total = 0;
     double* act[2] = {nullptr, nullptr}; double* del[2] = {nullptr, nullptr};
     double *xadv = nullptr, *WT = nullptr, *gpart = nullptr, *nllpart = nullptr, *regpart = nullptr, *loss = nullptr;
@@ -405,7 +850,7 @@ int launch_nn_t(pb_ctx* ctx, cudaStream_t st, int M, const double* A, int64_t ld
     constexpr size_t smem = (size_t)STAGES * (BM * (BK + 4) + BK * (BN + 4)) * sizeof(double);
     if (!ctx) return set_smem(ctx, kern, smem);      // configuration pass (before any capture)
     dim3 grid((unsigned)((rows + BM - 1) / BM), (unsigned)((k + BN - 1) / BN), (unsigned)M);
-    kern<<<grid, NTHREADS, smem, st>>>(A, lda, sA, rows, m, B, ldb, sB, k, Y, ldy, sY, epi, aux, ldaux, sAux, eps);
+    PB_CUDA(ctx, launch_k(kern, grid, dim3(NTHREADS), smem, st, g_pdl, A, lda, sA, rows, m, B, ldb, sB, k, Y, ldy, sY, epi, aux, ldaux, sAux, eps));
     PB_LAUNCH_CHECK(ctx);
     return PB_OK;
 }
@@ -438,8 +883,8 @@ int launch_dw_t(pb_ctx* ctx, cudaStream_t st, int M, const double* A, int64_t ld
     if (!ctx) return set_smem(ctx, kern, smem);      // configuration pass (before any capture)
     const int tiles_m = (ka + BM - 1) / BM, tiles_n = (kb + BN - 1) / BN;
     dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)splits, (unsigned)M);
-    kern<<<grid, NTHREADS, smem, st>>>(A, lda, sA, ka, B, ldb, sB, kb, rows, rps, out, ldo, split_stride, sOut,
-                                       bias_out, tiles_n);
+    PB_CUDA(ctx, launch_k(kern, grid, dim3(NTHREADS), smem, st, g_pdl, A, lda, sA, ka, B, ldb, sB, kb, rows, rps, out, ldo,
+                          split_stride, sOut, bias_out, tiles_n));
     PB_LAUNCH_CHECK(ctx);
     return PB_OK;
 }
@@ -467,8 +912,11 @@ int configure_nn() {
     if (rc == PB_OK) rc = launch_nn_t<BM, BN, WM_, WN_, false, false>(nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.);
     return rc;
 }
+int launch_fused(pb_ctx* ctx, struct TrainState& s);
+int configure_fused();
 int configure_all() {
     int rc = configure_nn<128, 64, 4, 2>();
+    if (rc == PB_OK) rc = configure_fused();
     if (rc == PB_OK) rc = configure_nn<32, 64, 2, 4>();
     if (rc == PB_OK) rc = launch_dw_t<false, true, true>(nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
     if (rc == PB_OK) rc = launch_dw_t<true, true, true>(nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
@@ -484,10 +932,71 @@ int configure_all() {
 int launch_adam(pb_ctx* ctx, TrainState& s, int update) {
     const TrainKey& k = s.key;
     dim3 grid((unsigned)((s.tab.P + 255) / 256), (unsigned)k.M);
-    train_adam_kernel<<<grid, 256, 0, ctx->stream>>>(s.tab, k.params, k.am, k.av, s.WT, s.gpart, k.n_pass,
-                                                     k.use_adv ? 2 : 1, s.splits, k.M, k.lr, k.lam, s.tstep, s.eidx, s.nllpart,
-                                                     s.nll_blocks, s.regpart, s.ticket, s.loss, update);
+    PB_CUDA(ctx, launch_k(train_adam_kernel, grid, dim3(256), 0, ctx->stream, g_pdl && update, s.tab, k.params, k.am, k.av,
+                          s.WT, s.packed, (const double*)s.gpart, k.n_pass, k.use_adv ? 2 : 1, s.splits, k.M, k.lr, k.lam, s.tstep,
+                          s.eidx, (const double*)s.nllpart, s.nll_blocks, s.regpart, s.ticket, s.loss, update));
     PB_LAUNCH_CHECK(ctx);
+    return PB_OK;
+}
+
+
+struct TrainState;
+template <int MT>
+int launch_fused_t(pb_ctx* ctx, TrainState* sp) {
+    auto kern = train_fused_kernel<MT>;
+    constexpr size_t smem = ((size_t)MT * FPITCH + (size_t)FRING * FCH) * sizeof(double) + 2 * FRING * sizeof(uint64_t) + 8 * sizeof(double);
+    if (!ctx) return set_smem(ctx, kern, smem);
+    TrainState& s = *sp; const TrainKey& k = s.key;
+    FusedArgs a;
+    a.M = k.M; a.L = k.n_layers; a.n_L = k.dims[k.n_layers] / 2; a.n_pass = k.n_pass; a.n_tiles = s.n_tiles; a.N = k.N;
+    for (int l = 0; l <= k.n_layers; ++l) a.dims[l] = k.dims[l];
+    a.packed = s.packed; a.SP = s.tab.SP;
+    for (int l = 0; l < k.n_layers; ++l) { a.pk_f[l] = s.tab.pk_f[l]; a.pk_b[l] = s.tab.pk_b[l]; }
+    a.X = k.X; a.v = k.v; a.xadv = s.xadv;
+    for (int p = 0; p < 2; ++p) { a.act[p] = s.act[p]; a.del[p] = s.del[p]; }
+    for (int l = 0; l <= k.n_layers; ++l) { a.act_off[l] = s.act_off[l]; a.del_off[l] = s.del_off[l]; }
+    a.nllpart = s.nllpart; a.adv_eps = k.adv_eps; a.soft_0 = k.soft_0;
+    PB_CUDA(ctx, launch_k(kern, dim3((unsigned)s.fused_grid), dim3(FUSED_THREADS), smem, ctx->stream, false, a));
+    PB_LAUNCH_CHECK(ctx);
+    return PB_OK;
+}
+
+int launch_fused(pb_ctx* ctx, TrainState& s) {
+    switch (s.mt) {
+        case 16: return launch_fused_t<16>(ctx, &s);
+        case 32: return launch_fused_t<32>(ctx, &s);
+        default: return launch_fused_t<64>(ctx, &s);
+    }
+}
+
+template <bool BIG>
+int launch_dw_multi_t(pb_ctx* ctx, TrainState* sp) {
+    constexpr int BM = BIG ? 128 : 64;
+    auto kern = train_dw_multi_kernel<BM, BM, 2, 4>;
+    constexpr size_t smem = (size_t)STAGES * BK * 2 * (BM + 4) * sizeof(double);
+    if (!ctx) return set_smem(ctx, kern, smem);
+    TrainState& s = *sp; const TrainKey& k = s.key;
+    dim3 grid((unsigned)s.dw_tiles, (unsigned)s.splits, (unsigned)k.M);
+    PB_CUDA(ctx, launch_k(kern, grid, dim3(NTHREADS), smem, ctx->stream, false, s.jobs, (int64_t)k.N, s.rps, s.gpart,
+                          (int64_t)k.M * s.tab.P, (int64_t)s.tab.P));
+    PB_LAUNCH_CHECK(ctx);
+    return PB_OK;
+}
+
+int configure_fused() {
+    int rc = launch_fused_t<16>(nullptr, nullptr);
+    if (rc == PB_OK) rc = launch_fused_t<32>(nullptr, nullptr);
+    if (rc == PB_OK) rc = launch_fused_t<64>(nullptr, nullptr);
+    if (rc == PB_OK) rc = launch_dw_multi_t<false>(nullptr, nullptr);
+    if (rc == PB_OK) rc = launch_dw_multi_t<true>(nullptr, nullptr);
+    return rc;
+}
+
+// fused epoch: 3 launches (forward + NLL + delta chain of both passes; all weight gradients; Adam)
+int run_epoch_fused(pb_ctx* ctx, TrainState& s) {
+    PB_TRY(launch_fused(ctx, s));
+    PB_TRY(s.dw_big ? launch_dw_multi_t<true>(ctx, &s) : launch_dw_multi_t<false>(ctx, &s));
+    PB_TRY(launch_adam(ctx, s, 1));
     return PB_OK;
 }
 
@@ -515,8 +1024,9 @@ int run_epoch(pb_ctx* ctx, TrainState& s) {
         }
         {   // NLL + head gradient, in place
             dim3 grid((unsigned)s.nll_blocks, (unsigned)M);
-            train_nll_kernel<<<grid, 256, 0, st>>>(s.del[p] + s.del_off[L - 1], N * k.dims[L], k.v, N, n_L, k.soft_0,
-                                                   s.nllpart + (int64_t)p * M * s.nll_blocks);
+            PB_CUDA(ctx, launch_k(train_nll_kernel, grid, dim3(256), 0, st, g_pdl, s.del[p] + s.del_off[L - 1],
+                                  (int64_t)(N * k.dims[L]), k.v, N, n_L, k.soft_0,
+                                  s.nllpart + (int64_t)p * M * s.nll_blocks));
             PB_LAUNCH_CHECK(ctx);
         }
         // backward
@@ -559,6 +1069,7 @@ void pbi_train_free(pb_ctx* ctx) {
     if (!s) return;
     if (s->exec) cudaGraphExecDestroy(s->exec);
     for (int p = 0; p < 2; ++p) { cudaFree(s->act[p]); cudaFree(s->del[p]); }
+    cudaFree(s->packed);
     cudaFree(s->xadv); cudaFree(s->WT); cudaFree(s->gpart); cudaFree(s->nllpart); cudaFree(s->regpart);
     cudaFree(s->loss); cudaFree(s->ticket); cudaFree(s->tstep); cudaFree(s->eidx);
     if (s->side) cudaStreamDestroy(s->side);
@@ -587,6 +1098,7 @@ extern "C" int pb_ensemble_train(pb_ctx* ctx, int n_members, int n_layers, const
     {
         static bool configured = false;
         if (!configured) {
+            if (getenv("PB_TRAIN_PDL")) g_pdl = atoi(getenv("PB_TRAIN_PDL")) != 0;
             if (configure_all() != PB_OK) PB_FAIL(ctx, PB_ERR_CUDA, "pb_ensemble_train: kernel configuration failed: %s", pb_last_error(nullptr));
             configured = true;
         }
@@ -635,6 +1147,36 @@ extern "C" int pb_ensemble_train(pb_ctx* ctx, int n_members, int n_layers, const
             s.rps = rps; s.splits = (int)((N + rps - 1) / rps);
         }
         const int n_pass = key.n_pass;
+        {   // fused path: every width fits one 128-column chunk
+            static const int want_fused = getenv("PB_TRAIN_FUSED") ? atoi(getenv("PB_TRAIN_FUSED")) : 1;
+            bool ok = want_fused != 0;
+            for (int l = 0; l <= L; ++l) ok = ok && dims[l] <= 128;
+            s.fused = ok; t.fused = ok ? 1 : 0;
+            long long offp = 0;
+            for (int l = 0; l < L; ++l) {         // forward stream: K chunks of W_l, then its bias row
+                t.pk_f[l] = offp; offp += (long long)((dims[l] + BK - 1) / BK) * FCH + FPITCH;
+            }
+            for (int l = L - 1; l >= 0; --l) {    // backward stream: K chunks of W_l^T
+                t.pk_b[l] = offp; offp += (long long)((dims[l + 1] + BK - 1) / BK) * FCH;
+            }
+            t.SP = offp;
+            if (s.fused) {
+                // rows per tile: the largest of 64 / 32 / 16 that still gives every SM an item (weights are
+                // re-streamed from L2 per item, so larger tiles halve that traffic)
+                static const int force_mt = getenv("PB_TRAIN_MT") ? atoi(getenv("PB_TRAIN_MT")) : 0;
+                // 32-row tiles (two co-resident CTAs per SM overlap each other's epilogues) once there are enough
+                // items to fill them twice over, else 16-row tiles (measured: profiles/r01_notes.md)
+                int mt = ((int64_t)M * ((N + 31) / 32) >= 4 * (int64_t)ctx->sm_count) ? 32 : 16;
+                if (force_mt == 16 || force_mt == 32 || force_mt == 64) mt = force_mt;
+                s.mt = mt; s.n_tiles = (int)((N + mt - 1) / mt);
+                static const int cps_env = getenv("PB_TRAIN_CPS") ? atoi(getenv("PB_TRAIN_CPS")) : 0;
+                const int cps = cps_env ? cps_env : (mt <= 32 ? 2 : 1);            // co-resident CTAs per SM
+                s.fused_grid = (int)std::min<int64_t>((int64_t)M * s.n_tiles, (int64_t)ctx->sm_count * cps);
+                s.nll_blocks = s.n_tiles;
+                PB_TRY(reserve(ctx, &s.packed, &s.cap_packed, (size_t)M * t.SP));
+                PB_CUDA(ctx, cudaMemsetAsync(s.packed, 0, (size_t)M * t.SP * sizeof(double), ctx->stream));
+            }
+        }
         for (int p = 0; p < n_pass; ++p) {
             PB_TRY(reserve(ctx, &s.act[p], &s.cap_act[p], (size_t)std::max<int64_t>(s.act_total, 2)));
             PB_TRY(reserve(ctx, &s.del[p], &s.cap_del[p], (size_t)s.del_total));
@@ -642,8 +1184,26 @@ extern "C" int pb_ensemble_train(pb_ctx* ctx, int n_members, int n_layers, const
         PB_TRY(reserve(ctx, &s.xadv, &s.cap_xadv, (size_t)M * N * dims[0] + 2));
         PB_TRY(reserve(ctx, &s.WT, &s.cap_WT, (size_t)M * t.PT));
         PB_TRY(reserve(ctx, &s.gpart, &s.cap_gpart, (size_t)n_pass * s.splits * M * t.P));
-        s.nll_blocks = (int)std::min<int64_t>(NLL_BLOCKS_MAX, std::max<int64_t>(1, (N * (dims[L] / 2) + 511) / 512));
-        PB_TRY(reserve(ctx, &s.nllpart, &s.cap_nll, (size_t)2 * M * NLL_BLOCKS_MAX));
+        if (!s.fused) s.nll_blocks = (int)std::min<int64_t>(NLL_BLOCKS_MAX, std::max<int64_t>(1, (N * (dims[L] / 2) + 511) / 512));
+        PB_TRY(reserve(ctx, &s.nllpart, &s.cap_nll, (size_t)2 * M * std::max(NLL_BLOCKS_MAX, s.nll_blocks)));
+        if (s.fused) {   // job table of the batched weight-gradient launch: (pass, layer)
+            const int bt = s.dw_big ? 128 : 64;
+            s.jobs.n_jobs = 0; int tile0 = 0;
+            for (int p = 0; p < n_pass; ++p)
+                for (int l = 0; l < L; ++l) {
+                    DwJob& J = s.jobs.job[s.jobs.n_jobs++];
+                    J.A = (l == 0) ? (p == 0 ? X_dev : s.xadv) : s.act[p] + s.act_off[l];
+                    J.sA = (l == 0) ? (p == 0 ? 0 : N * dims[0]) : N * dims[l];
+                    J.lda = dims[l]; J.ka = dims[l];
+                    J.B = s.del[p] + s.del_off[l]; J.sB = N * dims[l + 1]; J.ldb = dims[l + 1]; J.kb = dims[l + 1];
+                    J.out_off = (long long)p * s.splits * M * t.P + t.off_w[l];
+                    J.bias_off = (long long)p * s.splits * M * t.P + t.off_b[l];
+                    J.tiles_n = (dims[l + 1] + bt - 1) / bt;
+                    J.tile0 = tile0; tile0 += ((dims[l] + bt - 1) / bt) * J.tiles_n;
+                    J.alignA = al16(J.A, J.lda, J.sA) ? 1 : 0; J.alignB = al16(J.B, J.ldb, J.sB) ? 1 : 0;
+                }
+            s.dw_tiles = tile0;
+        }
         PB_TRY(reserve(ctx, &s.regpart, &s.cap_reg, (size_t)M * ((t.P + 255) / 256)));
         if (!s.ticket) {
             PB_CUDA(ctx, cudaMalloc(&s.ticket, 64 * sizeof(unsigned)));
@@ -653,7 +1213,7 @@ extern "C" int pb_ensemble_train(pb_ctx* ctx, int n_members, int n_layers, const
             PB_CUDA(ctx, cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
             PB_CUDA(ctx, cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
         }
-        s.launches_per_epoch = n_pass * (L + 1 + L + (L - 1)) + (n_pass == 2 ? 1 : 0) + 1;
+        s.launches_per_epoch = s.fused ? 3 : n_pass * (L + 1 + L + (L - 1)) + (n_pass == 2 ? 1 : 0) + 1;
         s.valid = true;
     }
     // the loss history lives in a context buffer (its address is baked into the captured graph)
@@ -676,7 +1236,7 @@ extern "C" int pb_ensemble_train(pb_ctx* ctx, int n_members, int n_layers, const
             cudaGraph_t graph = nullptr;
             const int64_t before = ctx->launches;
             PB_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-            int rc = run_epoch(ctx, s);
+            int rc = s.fused ? run_epoch_fused(ctx, s) : run_epoch(ctx, s);
             cudaError_t e = cudaStreamEndCapture(st, &graph);
             ctx->launches = before;
             if (rc != PB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -688,7 +1248,7 @@ extern "C" int pb_ensemble_train(pb_ctx* ctx, int n_members, int n_layers, const
         for (int ep = 0; ep < epochs; ++ep) PB_CUDA(ctx, cudaGraphLaunch(s.exec, st));
         ctx->launches += (int64_t)epochs * s.launches_per_epoch;
     } else {
-        for (int ep = 0; ep < epochs; ++ep) PB_TRY(run_epoch(ctx, s));
+        for (int ep = 0; ep < epochs; ++ep) PB_TRY(s.fused ? run_epoch_fused(ctx, s) : run_epoch(ctx, s));
     }
     if (loss_host) {
         PB_CUDA(ctx, cudaMemcpyAsync(loss_host, s.loss, (size_t)epochs * M * sizeof(double), cudaMemcpyDeviceToHost, st));
