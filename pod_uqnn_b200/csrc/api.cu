@@ -215,6 +215,11 @@ int pb_pod_from_gram(pb_ctx* ctx, const double* G, int64_t m, double eps, int n_
         static const double tol1 = []{ const char* e = getenv("PB_ACC_TOL1"); return e ? atof(e) : 0.; }();
         if (mode == PB_POD_ACCURATE && tol1 > 0.) g_jacobi_tol_override = tol1;
     }
+    {   // a second pass re-orthogonalises: when the first factor is a single 32-vector pair, its in-kernel solve
+        // (iterated to the rotation threshold) is taken as is, without the confirming sweep
+        extern bool g_trust_single_pair;
+        g_trust_single_pair = (mode != PB_POD_GRAM);
+    }
     PB_TRY(pbi_eig_psd(ctx, G, m, tol_rel, shift_rel, &ctx->At, &ctx->At_cap, ctx->sig, ctx->nrm, ctx->perm,
                        &ctx->r, &ctx->sweeps1, 40));
     ctx->n_keep = (mode == PB_POD_GRAM) ? 0 : ctx->r;

@@ -481,6 +481,7 @@ __global__ void factor_to_right_kernel(const double* __restrict__ At, int64_t ld
 
 }  // namespace
 
+bool g_trust_single_pair = false;      // next eig: skip the confirming sweep of a single-pair problem (a second pass follows)
 double g_jacobi_tol_override = 0.;   // > 0: rotation threshold of the next eig (first pass of the accurate mode)
 static int g_cross_rounds = []{ const char* e = getenv("PB_JACOBI_CROSS"); return e ? atoi(e) : 1; }();
 static int g_inner_sweeps = []{ const char* e = getenv("PB_JACOBI_INNER"); return e ? atoi(e) : 3; }();
@@ -553,6 +554,8 @@ int pbi_eig_psd(pb_ctx* ctx, const double* G, int64_t m, double tol_rel, double 
     size_t jac_smem = sizeof(double) * 2 * JP * JPX;
     PB_CUDA(ctx, cudaFuncSetAttribute(jacobi_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jac_smem));
     int sweeps = 0; bool converged = false;
+    const bool trust_single = g_trust_single_pair && nb == 2;
+    g_trust_single_pair = false;
     for (; sweeps < max_sweeps && !converged; ++sweeps) {
         PB_CUDA(ctx, cudaMemsetAsync(ctx->d_int + 1, 0, sizeof(int), ctx->stream));
         const int rounds = nb > 2 ? nb - 1 : 1;
@@ -562,6 +565,7 @@ int pbi_eig_psd(pb_ctx* ctx, const double* G, int64_t m, double tol_rel, double 
             jacobi_pair_kernel<<<nb / 2, 256, jac_smem, ctx->stream>>>(ja);
             PB_LAUNCH_CHECK(ctx);
         }
+        if (trust_single) { converged = true; continue; }
         PB_CUDA(ctx, cudaMemcpyAsync(ctx->h_int + 1, ctx->d_int + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         converged = (ctx->h_int[1] == 0);
@@ -710,6 +714,8 @@ int pbi_eig_psd_batched(pb_ctx* ctx, const double* G_all, int64_t m, int batch, 
     size_t jac_smem = sizeof(double) * 2 * JP * JPX;
     PB_CUDA(ctx, cudaFuncSetAttribute(jacobi_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jac_smem));
     int sweeps = 0; bool converged = false;
+    const bool trust_single = g_trust_single_pair && nb == 2;
+    g_trust_single_pair = false;
     for (; sweeps < max_sweeps && !converged; ++sweeps) {
         PB_CUDA(ctx, cudaMemsetAsync(ctx->d_int + 1, 0, sizeof(int), ctx->stream));
         const int rounds = nb > 2 ? nb - 1 : 1;

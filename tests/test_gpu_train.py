@@ -57,6 +57,13 @@ def test_ragged_and_odd_widths(ctx):
     check_against_oracle(ctx, [2, 1], 9, 2, 3, 0.01, 1e-2, 0.1, 1., seed=5)          # head only
 
 
+def test_wide_layers_take_layer_by_layer_path(ctx):
+    """Widths above 128 do not fit the fused kernel's single 128-column chunk: per-layer kernels + forked dW graph
+    branch (the PB_TRAIN_FUSED=0 path)."""
+    check_against_oracle(ctx, [3, 160, 136, 10], 300, 2, 3, 1e-3, 1e-3, 0.01, 0.5, seed=10)
+    check_against_oracle(ctx, [2, 64, 70], 130, 2, 3, 1e-3, 1e-3, None, 0.5, seed=11)      # head 2 n_L = 140 > 128
+
+
 def test_large_batch_tiles(ctx):
     """Enough rows for the 128-row tiles and 16 split-K partials."""
     check_against_oracle(ctx, [2, 128, 128, 128, 20], 6000, 8, 2, 1e-3, 1e-4, 0.01, 0.01, seed=6)
