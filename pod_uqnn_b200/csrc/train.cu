@@ -565,6 +565,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 32) ? 2 : 1) train_fused
                 consumer_sync();               // every warp has finished reading act for this layer
                 const int outp = (out + BK - 1) / BK * BK;
                 double* gout = head ? nullptr : a.act[pass] + a.act_off[l + 1] + ((long long)mem * a.N + r0) * out;
+                const bool vec_ok = !(out & 1) && ((reinterpret_cast<uintptr_t>(gout) & 15) == 0);
                 uint32_t mk = 0;
 #pragma unroll
                 for (int t = 0; t < TM; ++t) {
@@ -582,7 +583,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 32) ? 2 : 1) train_fused
                         if (n + 1 >= out) x1 = 0.;
                         if (n < outp) *reinterpret_cast<double2*>(act + r * FPITCH + n) = make_double2(x0, x1);
                         if (!head && r0 + r < a.N) {
-                            if (n + 1 < out && !(out & 1)) *reinterpret_cast<double2*>(gout + (long long)r * out + n) = make_double2(x0, x1);
+                            if (n + 1 < out && vec_ok) *reinterpret_cast<double2*>(gout + (long long)r * out + n) = make_double2(x0, x1);
                             else { if (n < out) gout[(long long)r * out + n] = x0; if (n + 1 < out) gout[(long long)r * out + n + 1] = x1; }
                         }
                     }
@@ -636,6 +637,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 32) ? 2 : 1) train_fused
                 if (l > 0) {
                     double* gout = a.del[pass] + a.del_off[l - 1] + ((long long)mem * a.N + r0) * in;
                     const uint32_t mk = mask[l - 1];
+                    const bool vec_ok = !(in & 1) && ((reinterpret_cast<uintptr_t>(gout) & 15) == 0);
 #pragma unroll
                     for (int t = 0; t < TM; ++t) {
                         const int r = t * 8 + lg;
@@ -648,7 +650,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 32) ? 2 : 1) train_fused
                             if (n + 1 >= in) x1 = 0.;
                             if (n < inp) *reinterpret_cast<double2*>(act + r * FPITCH + n) = make_double2(x0, x1);
                             if (r0 + r < a.N) {
-                                if (n + 1 < in && !(in & 1)) *reinterpret_cast<double2*>(gout + (long long)r * in + n) = make_double2(x0, x1);
+                                if (n + 1 < in && vec_ok) *reinterpret_cast<double2*>(gout + (long long)r * in + n) = make_double2(x0, x1);
                                 else { if (n < in) gout[(long long)r * in + n] = x0; if (n + 1 < in) gout[(long long)r * in + n + 1] = x1; }
                             }
                         }
@@ -1130,8 +1132,9 @@ extern "C" int pb_ensemble_train(pb_ctx* ctx, int n_members, int n_layers, const
         t.P = off; t.PT = offt + (offt & 1);
         // buffers
         s.act_total = 0; s.del_total = 0;
-        for (int l = 1; l < L; ++l) { s.act_off[l] = s.act_total; s.act_total += (int64_t)M * N * dims[l]; }
-        for (int l = 0; l < L; ++l) { s.del_off[l] = s.del_total; s.del_total += (int64_t)M * N * dims[l + 1]; }
+        // every segment starts 16-byte aligned (vector stores / 16-byte staging of even-width layers)
+        for (int l = 1; l < L; ++l) { s.act_off[l] = s.act_total; s.act_total += (int64_t)M * N * dims[l]; s.act_total += s.act_total & 1; }
+        for (int l = 0; l < L; ++l) { s.del_off[l] = s.del_total; s.del_total += (int64_t)M * N * dims[l + 1]; s.del_total += s.del_total & 1; }
         // split-K of the weight gradients: fill the SMs, at least 64 rows per split.  Large batches take 128 x 128
         // tiles (half the operand traffic per flop: the 64 x 64 tiles are HBM / L2 bound there).
         {

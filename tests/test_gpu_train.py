@@ -55,6 +55,9 @@ def test_ragged_and_odd_widths(ctx):
     check_against_oracle(ctx, [1, 33, 17, 5], 77, 2, 4, 0.01, 1e-3, 0.02, 1., seed=3)
     check_against_oracle(ctx, [5, 40, 3], 19, 1, 3, 0.01, 0., None, 1., seed=4)
     check_against_oracle(ctx, [2, 1], 9, 2, 3, 0.01, 1e-2, 0.1, 1., seed=5)          # head only
+    # odd layer width followed by even ones, odd N: buffer segments of the later layers must stay 16-byte aligned
+    check_against_oracle(ctx, [2, 33, 64, 4], 77, 1, 3, 0.01, 1e-3, 0.05, 1., seed=12)
+    check_against_oracle(ctx, [3, 15, 128, 9], 401, 3, 3, 0.01, 1e-3, 0.05, 1., seed=13)
 
 
 def test_wide_layers_take_layer_by_layer_path(ctx):
