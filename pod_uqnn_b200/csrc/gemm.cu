@@ -147,7 +147,7 @@ __global__ void symmetrize_kernel(double* __restrict__ C, int n, int64_t ldc, in
 // NN kernel (BM = 128 rows per CTA)
 // ---------------------------------------------------------------------------
 template <int BN, int WARPS_M, int WARPS_N, int STAGES, bool ALIGN_A, bool ALIGN_B>
-__global__ void __launch_bounds__(NTHREADS, (BN <= 32) ? 2 : 1)     // skinny (HBM-bound) tiles: two CTAs per SM
+__global__ void __launch_bounds__(NTHREADS, (BN <= 32 || STAGES <= 2) ? 2 : 1)   // skinny / short-K (HBM-bound) tiles: two CTAs per SM
 gemm_nn_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int m,
                const double* __restrict__ B, int64_t ldb, int k,
                double* __restrict__ Y, int64_t ldy,
@@ -259,6 +259,111 @@ gemm_nn_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int m,
             for (int w = 0; w < WARPS_N; ++w) s += rowsum[w][tid];
             sig_part[(int64_t)blockIdx.y * rows + h0 + tid] = s;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Reconstruction strip kernel: Y (rows x n) = A (rows x K) B (K x n) with K = n_L <= 64 and n wide -- the op is
+// bound by the output / U traffic, not by flops.  One CTA owns a strip of 32 rows and sweeps the column tiles:
+// the A strip is staged once, the B tile and the U tile of the NEXT column tile are in flight (cp.async) while the
+// current tile is multiplied and compared, so HBM streams continuously; a CTA owns whole rows, so
+// pod_sig[h] = mean_j |U - Y| / 2 is finished in the kernel (no partial buffer, no second pass).
+// ---------------------------------------------------------------------------
+template <int KP, bool ALIGN_A, bool ALIGN_B, bool ALIGN_U>
+__global__ void __launch_bounds__(NTHREADS, (KP <= 32) ? 2 : 1)
+recon_strip_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int K,
+                   const double* __restrict__ B, int64_t ldb, int64_t n,
+                   double* __restrict__ Y, int64_t ldy,
+                   const double* __restrict__ U, int64_t ldu, double* __restrict__ sig_out) {
+    constexpr int MS = 32, NT = 64;
+    constexpr int STG = (KP <= 16) ? 3 : 2;    // tiles in flight: 2 CTAs x 2 tiles x 16 KB keep HBM busy (n_L <= 16)
+    constexpr int PA = KP + 4, PB = NT + 4, PU = NT + 4;
+    extern __shared__ __align__(16) double smem[];
+    double* As = smem;                         // [MS][PA]
+    double* Bs = As + MS * PA;                 // [STG][KP][PB]
+    double* Us = Bs + STG * KP * PB;           // [STG][MS][PU]
+    __shared__ double rowsum[4][MS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;   // 2 x 4 warps, warp tile 16 x 16
+    const int lk = lane & 3, lg = lane >> 2;
+    const int64_t h0 = (int64_t)blockIdx.x * MS;
+    const int n_tiles = (int)((n + NT - 1) / NT);
+    const bool want_sig = (U != nullptr);
+    const bool y_vec = Y && (ldy % 2 == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0);
+
+    load_tile<MS, KP, PA, ALIGN_A>(As, A, lda, h0, rows, 0, K, tid);
+    auto prefetch = [&](int t) {
+        const int64_t j0 = (int64_t)t * NT;
+        load_tile<KP, NT, PB, ALIGN_B>(Bs + (t % STG) * KP * PB, B, ldb, 0, K, j0, n, tid);
+        if (want_sig) load_tile<MS, NT, PU, ALIGN_U>(Us + (t % STG) * MS * PU, U, ldu, h0, rows, j0, n, tid);
+    };
+#pragma unroll
+    for (int t = 0; t < STG - 1; ++t) {
+        if (t < n_tiles) prefetch(t);
+        cp_async_commit();
+    }
+    double rs[2] = {0., 0.};
+    for (int t = 0; t < n_tiles; ++t) {
+        cp_async_wait<STG - 2>();
+        __syncthreads();                       // tile t has landed; everyone is done with tile t - 1's buffers
+        if (t + STG - 1 < n_tiles) prefetch(t + STG - 1);
+        cp_async_commit();
+        double acc[2][2][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) { acc[a][u][0] = 0.; acc[a][u][1] = 0.; }
+        const double* as = As + (wm * 16 + lg) * PA + lk;
+        const double* bs = Bs + (t % STG) * KP * PB + wn * 16 + lg;
+#pragma unroll
+        for (int kk = 0; kk < KP / 4; ++kk) {
+            if (kk * 4 < K) {
+                double af[2], bf[2];
+#pragma unroll
+                for (int a = 0; a < 2; ++a) af[a] = as[a * 8 * PA + kk * 4];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) bf[u] = bs[(kk * 4 + lk) * PB + u * 8];
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) dmma884(acc[a][u][0], acc[a][u][1], af[a], bf[u]);
+            }
+        }
+        const int64_t j0 = (int64_t)t * NT;
+        const double* us = Us + (t % STG) * MS * PU;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int rl = wm * 16 + a * 8 + lg;
+            const int64_t h = h0 + rl;
+            if (h >= rows) continue;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int cl = wn * 16 + u * 8 + 2 * lk;
+                const int64_t j = j0 + cl;
+                if (Y) {
+                    if (y_vec && j + 1 < n) *reinterpret_cast<double2*>(Y + h * ldy + j) = make_double2(acc[a][u][0], acc[a][u][1]);
+                    else { if (j < n) Y[h * ldy + j] = acc[a][u][0]; if (j + 1 < n) Y[h * ldy + j + 1] = acc[a][u][1]; }
+                }
+                if (want_sig) {
+                    const double2 uv = *reinterpret_cast<const double2*>(us + rl * PU + cl);
+                    if (j < n)     rs[a] += fabs(uv.x - acc[a][u][0]);
+                    if (j + 1 < n) rs[a] += fabs(uv.y - acc[a][u][1]);
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    if (want_sig) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            double v = rs[a];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (lk == 0) rowsum[wn][wm * 16 + a * 8 + lg] = v;
+        }
+        __syncthreads();
+        if (tid < MS && h0 + tid < rows)
+            sig_out[h0 + tid] = (rowsum[0][tid] + rowsum[1][tid] + rowsum[2][tid] + rowsum[3][tid]) * (0.5 / (double)n);
     }
 }
 
@@ -382,11 +487,10 @@ reduce:
     return PB_OK;
 }
 
-template <int BN, int WARPS_M, int WARPS_N>
+template <int BN, int WARPS_M, int WARPS_N, int STAGES = 4>
 int launch_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m, const double* B,
               int64_t ldb, int64_t k, double* Y, int64_t ldy, const double* Uref, int64_t ldu,
               double* sig_part, Batch bt = Batch()) {
-    constexpr int STAGES = 4;
     size_t smem = (size_t)STAGES * (128 * (BK + 4) + BK * (BN + 4)) * sizeof(double);
     dim3 grid((unsigned)((rows + 127) / 128), (unsigned)((k + BN - 1) / BN), bt.count);
     const bool aa = aligned16(A, lda) && (bt.sA % 2 == 0), ab = aligned16(B, ldb) && (bt.sB % 2 == 0);
@@ -399,6 +503,26 @@ int launch_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m
     else if (ab) PB_NN_CASE(false, true)
     else PB_NN_CASE(false, false)
 #undef PB_NN_CASE
+    PB_LAUNCH_CHECK(ctx);
+    return PB_OK;
+}
+
+
+template <int KP>
+int launch_recon_strip(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m, const double* B,
+                       int64_t ldb, int64_t k, double* Y, int64_t ldy, const double* Uref, int64_t ldu, double* sig_out) {
+    constexpr int STG = (KP <= 16) ? 3 : 2;
+    constexpr size_t smem = (size_t)(32 * (KP + 4) + STG * KP * 68 + STG * 32 * 68) * sizeof(double);
+    const bool aa = aligned16(A, lda), ab = aligned16(B, ldb), au = !Uref || aligned16(Uref, ldu);
+    dim3 grid((unsigned)((rows + 31) / 32));
+#define PB_RS_CASE(AA, AB, AU) { auto kern = recon_strip_kernel<KP, AA, AB, AU>; \
+        PB_TRY(set_smem(ctx, kern, smem)); \
+        kern<<<grid, NTHREADS, smem, ctx->stream>>>(A, lda, rows, (int)m, B, ldb, k, Y, ldy, Uref, ldu, sig_out); }
+    if (aa && ab && au) PB_RS_CASE(true, true, true)
+    else if (ab && au) PB_RS_CASE(false, true, true)
+    else if (ab) PB_RS_CASE(false, true, false)
+    else PB_RS_CASE(false, false, false)
+#undef PB_RS_CASE
     PB_LAUNCH_CHECK(ctx);
     return PB_OK;
 }
@@ -434,9 +558,22 @@ int pbi_gemm_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t
                 double* sig_out) {
     if (rows <= 0 || m <= 0 || k <= 0) PB_FAIL(ctx, PB_ERR_SHAPE, "gemm_nn: bad shape rows=%lld m=%lld k=%lld",
                                                (long long)rows, (long long)m, (long long)k);
+    const bool moments_mode = Uref && ldu < 0;
+    {   // reconstruction / pod_sig with n_L <= 64 and a wide output: the strip kernel (HBM streaming)
+        static const int strip_env = getenv("PB_NN_STRIP") ? atoi(getenv("PB_NN_STRIP")) : 1;
+        if (strip_env && !moments_mode && m <= 64 && k >= 256) {
+            if (m <= 16) return launch_recon_strip<16>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, sig_out);
+            if (m <= 32) return launch_recon_strip<32>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, sig_out);
+            return launch_recon_strip<64>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, sig_out);
+        }
+    }
     double* part = nullptr;
     const bool wide = k > 32;
-    const int bn = k > 96 ? 128 : k > 64 ? 96 : k > 32 ? 64 : (k <= 16 ? 16 : 32);
+    // short K, wide output (reconstruction V v^T and its pod_sig epilogue, n_L <= 32): the kernel is one load / one
+    // product / one epilogue per tile, so several small CTAs per SM are needed to keep HBM busy
+    static const int shortk_env = getenv("PB_NN_SHORTK") ? atoi(getenv("PB_NN_SHORTK")) : 1;
+    const bool shortk = shortk_env && wide && m <= 2 * BK;
+    const int bn = shortk ? 64 : k > 96 ? 128 : k > 64 ? 96 : k > 32 ? 64 : (k <= 16 ? 16 : 32);
     const int ntiles = (int)((k + bn - 1) / bn);
     const bool moments = Uref && ldu < 0;
     if (moments) part = sig_out;                     // running sum of squares, accumulated in place
@@ -444,7 +581,8 @@ int pbi_gemm_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t
         PB_TRY(pb_reserve(ctx, &ctx->ws, &ctx->ws_bytes, (size_t)ntiles * rows));
         part = ctx->ws;
     }
-    if (k > 96) PB_TRY((launch_nn<128, 2, 4>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
+    if (shortk) PB_TRY((launch_nn<64, 4, 2, 2>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
+    else if (k > 96) PB_TRY((launch_nn<128, 2, 4>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
     else if (k > 64) PB_TRY((launch_nn<96, 2, 4>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
     else if (wide) PB_TRY((launch_nn<64, 4, 2>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
     else if (k <= 16) PB_TRY((launch_nn<16, 8, 1>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
