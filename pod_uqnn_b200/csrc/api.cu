@@ -376,9 +376,13 @@ int gram_host_chunked(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_
     for (int c = 0; c < nchunks; ++c) {
         const int64_t r0 = (int64_t)c * rows_c, nr = std::min(rows_c, n_h - r0);
         if (nr <= 0) break;
-        PB_CUDA(ctx, cudaMemcpy2DAsync(U_dev + r0 * n_st, n_st * sizeof(double), U_host + r0 * ldu_host,
-                                       ldu_host * sizeof(double), n_st * sizeof(double), nr, cudaMemcpyHostToDevice,
-                                       ctx->copy_stream));
+        if (ldu_host == n_st)      // contiguous rows: one linear copy (the pitched path is slower for 8 KB rows)
+            PB_CUDA(ctx, cudaMemcpyAsync(U_dev + r0 * n_st, U_host + r0 * n_st, (size_t)nr * n_st * sizeof(double),
+                                         cudaMemcpyHostToDevice, ctx->copy_stream));
+        else
+            PB_CUDA(ctx, cudaMemcpy2DAsync(U_dev + r0 * n_st, n_st * sizeof(double), U_host + r0 * ldu_host,
+                                           ldu_host * sizeof(double), n_st * sizeof(double), nr, cudaMemcpyHostToDevice,
+                                           ctx->copy_stream));
         PB_CUDA(ctx, cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
         PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
         PB_TRY(pbi_gemm_tn(ctx, U_dev + r0 * n_st, n_st, m, U_dev + r0 * n_st, n_st, m, nr, ctx->Gpart + (size_t)c * m * m, m, 1));
