@@ -147,7 +147,7 @@ __global__ void symmetrize_kernel(double* __restrict__ C, int n, int64_t ldc, in
 // NN kernel (BM = 128 rows per CTA)
 // ---------------------------------------------------------------------------
 template <int BN, int WARPS_M, int WARPS_N, int STAGES, bool ALIGN_A, bool ALIGN_B>
-__global__ void __launch_bounds__(NTHREADS, (BN <= 32 || STAGES <= 2) ? 2 : 1)   // skinny / short-K (HBM-bound) tiles: two CTAs per SM
+__global__ void __launch_bounds__(NTHREADS, (BN <= 32) ? 2 : 1)     // skinny (HBM-bound) tiles: two CTAs per SM
 gemm_nn_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int m,
                const double* __restrict__ B, int64_t ldb, int k,
                double* __restrict__ Y, int64_t ldy,
@@ -569,11 +569,7 @@ int pbi_gemm_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t
     }
     double* part = nullptr;
     const bool wide = k > 32;
-    // short K, wide output (reconstruction V v^T and its pod_sig epilogue, n_L <= 32): the kernel is one load / one
-    // product / one epilogue per tile, so several small CTAs per SM are needed to keep HBM busy
-    static const int shortk_env = getenv("PB_NN_SHORTK") ? atoi(getenv("PB_NN_SHORTK")) : 1;
-    const bool shortk = shortk_env && wide && m <= 2 * BK;
-    const int bn = shortk ? 64 : k > 96 ? 128 : k > 64 ? 96 : k > 32 ? 64 : (k <= 16 ? 16 : 32);
+    const int bn = k > 96 ? 128 : k > 64 ? 96 : k > 32 ? 64 : (k <= 16 ? 16 : 32);
     const int ntiles = (int)((k + bn - 1) / bn);
     const bool moments = Uref && ldu < 0;
     if (moments) part = sig_out;                     // running sum of squares, accumulated in place
@@ -581,8 +577,7 @@ int pbi_gemm_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t
         PB_TRY(pb_reserve(ctx, &ctx->ws, &ctx->ws_bytes, (size_t)ntiles * rows));
         part = ctx->ws;
     }
-    if (shortk) PB_TRY((launch_nn<64, 4, 2, 2>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
-    else if (k > 96) PB_TRY((launch_nn<128, 2, 4>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
+    if (k > 96) PB_TRY((launch_nn<128, 2, 4>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
     else if (k > 64) PB_TRY((launch_nn<96, 2, 4>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
     else if (wide) PB_TRY((launch_nn<64, 4, 2>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
     else if (k <= 16) PB_TRY((launch_nn<16, 8, 1>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));

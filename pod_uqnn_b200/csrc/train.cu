@@ -69,25 +69,13 @@ __device__ __forceinline__ void scatter_param(const LayerTab& tab, double* __res
 
 enum { EPI_BIAS_RELU = 0, EPI_BIAS = 1, EPI_MASK = 2, EPI_SIGN = 3 };
 
-// Programmatic dependent launch: every kernel of the epoch lets its successor's CTAs become resident at once and
-// then waits for its own predecessors' writes before touching global memory, so launch latency, block
-// scheduling and the prologue overlap the previous kernel's tail (the epoch is a chain of ~5 us kernels).
-__device__ __forceinline__ void pdl_prologue() {
-    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
-    asm volatile("griddepcontrol.wait;\n" ::: "memory");
-}
-
 template <typename... KArgs, typename... Args>
-cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
-bool g_pdl = false;   // measured: no gain at N = 400 (68.4 -> 69.2 us), a loss at N = 4000 (641 -> 748 us): early-resident CTAs steal SM slots
+// (programmatic dependent launch between the per-layer kernels was measured and rejected: profiles/r01_notes.md)
 
 // ---------------------------------------------------------------------------
 // Y (rows x k) = A (rows x m) B (m x k) with a fused epilogue; blockIdx.z = member
@@ -99,7 +87,6 @@ train_nn_kernel(const double* __restrict__ A, int64_t lda, int64_t sA, int64_t r
                 double* __restrict__ Y, int64_t ldy, int64_t sY,
                 int epi, const double* __restrict__ aux, int64_t ldaux, int64_t sAux, double eps) {
     static_assert(WARPS_M * WARPS_N == NTHREADS / 32, "8 warps");
-    pdl_prologue();
     constexpr int PA = BK + 4, PB = BN + 4;
     constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
     constexpr int TM = WM / 8, TNN = WN / 8;
@@ -194,7 +181,6 @@ train_dw_kernel(const double* __restrict__ A, int64_t lda, int64_t sA, int ka,
                 double* __restrict__ out, int64_t ldo, int64_t split_stride, int64_t sOut,
                 double* __restrict__ bias_out, int tiles_n) {
     static_assert(WARPS_M * WARPS_N == NTHREADS / 32, "8 warps");
-    pdl_prologue();
     constexpr int PA = BM + 4, PB = BN + 4;
     constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
     constexpr int TM = WM / 8, TNN = WN / 8;
@@ -287,7 +273,6 @@ train_dw_kernel(const double* __restrict__ A, int64_t lda, int64_t sA, int ka,
 __global__ void __launch_bounds__(256)
 train_nll_kernel(double* __restrict__ T, int64_t sT, const double* __restrict__ v, int64_t N, int n_L,
                  double soft_0, double* __restrict__ nllpart) {
-    pdl_prologue();
     T += (int64_t)blockIdx.y * sT;
     const int64_t total = N * n_L;
     double s = 0.;
@@ -328,7 +313,6 @@ train_adam_kernel(LayerTab tab, double* __restrict__ params, double* __restrict_
                   double lr, double lam, long long* __restrict__ tstep, int* __restrict__ eidx,
                   const double* __restrict__ nllpart, int nll_blocks, double* __restrict__ regpart,
                   unsigned* __restrict__ ticket, double* __restrict__ loss, int update) {
-    pdl_prologue();
     const int mem = blockIdx.y;
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     __shared__ double s_lrt;
@@ -448,7 +432,7 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;
 constexpr int FUSED_THREADS = 288;          // 8 consumer warps + 1 producer warp
 
 template <int MT>
-__global__ void __launch_bounds__(FUSED_THREADS, (MT <= 32) ? 2 : 1) train_fused_kernel(FusedArgs a) {
+__global__ void __launch_bounds__(FUSED_THREADS, 2) train_fused_kernel(FusedArgs a) {
     constexpr int TM = MT / 8;              // m8 row blocks per warp (every warp covers all MT rows, 16 columns)
     extern __shared__ __align__(16) double smem[];
     double* act = smem;                                   // [MT][FPITCH]
@@ -852,7 +836,7 @@ int launch_nn_t(pb_ctx* ctx, cudaStream_t st, int M, const double* A, int64_t ld
     constexpr size_t smem = (size_t)STAGES * (BM * (BK + 4) + BK * (BN + 4)) * sizeof(double);
     if (!ctx) return set_smem(ctx, kern, smem);      // configuration pass (before any capture)
     dim3 grid((unsigned)((rows + BM - 1) / BM), (unsigned)((k + BN - 1) / BN), (unsigned)M);
-    PB_CUDA(ctx, launch_k(kern, grid, dim3(NTHREADS), smem, st, g_pdl, A, lda, sA, rows, m, B, ldb, sB, k, Y, ldy, sY, epi, aux, ldaux, sAux, eps));
+    PB_CUDA(ctx, launch_k(kern, grid, dim3(NTHREADS), smem, st, A, lda, sA, rows, m, B, ldb, sB, k, Y, ldy, sY, epi, aux, ldaux, sAux, eps));
     PB_LAUNCH_CHECK(ctx);
     return PB_OK;
 }
@@ -861,16 +845,12 @@ int launch_nn(pb_ctx* ctx, cudaStream_t st, int M, const double* A, int64_t lda,
               const double* B, int64_t ldb, int64_t sB, int k, double* Y, int64_t ldy, int64_t sY, int epi,
               const double* aux, int64_t ldaux, int64_t sAux, double eps) {
     const bool aa = al16(A, lda, sA), ab = al16(B, ldb, sB);
-    const int64_t big_ctas = ((rows + 127) / 128) * ((k + 63) / 64) * M;
-    static const int force = getenv("PB_TRAIN_TILE") ? atoi(getenv("PB_TRAIN_TILE")) : 0;   // 1 small, 2 big
-    (void)big_ctas;
-    const bool big = (force == 2);     // measured: the 32-row tiles (3 CTAs per SM) win at every N (profiles/r01_notes.md)
+    // 32-row tiles, 3 CTAs per SM: measured faster than 128-row tiles at every batch size (profiles/r01_notes.md)
 #define PB_NN(BM_, BN_, WM_, WN_) \
     (aa ? (ab ? launch_nn_t<BM_, BN_, WM_, WN_, true, true>(ctx, st, M, A, lda, sA, rows, m, B, ldb, sB, k, Y, ldy, sY, epi, aux, ldaux, sAux, eps) \
               : launch_nn_t<BM_, BN_, WM_, WN_, true, false>(ctx, st, M, A, lda, sA, rows, m, B, ldb, sB, k, Y, ldy, sY, epi, aux, ldaux, sAux, eps)) \
         : (ab ? launch_nn_t<BM_, BN_, WM_, WN_, false, true>(ctx, st, M, A, lda, sA, rows, m, B, ldb, sB, k, Y, ldy, sY, epi, aux, ldaux, sAux, eps) \
               : launch_nn_t<BM_, BN_, WM_, WN_, false, false>(ctx, st, M, A, lda, sA, rows, m, B, ldb, sB, k, Y, ldy, sY, epi, aux, ldaux, sAux, eps)))
-    if (big) return PB_NN(128, 64, 4, 2);
     return PB_NN(32, 64, 2, 4);
 #undef PB_NN
 }
@@ -885,7 +865,7 @@ int launch_dw_t(pb_ctx* ctx, cudaStream_t st, int M, const double* A, int64_t ld
     if (!ctx) return set_smem(ctx, kern, smem);      // configuration pass (before any capture)
     const int tiles_m = (ka + BM - 1) / BM, tiles_n = (kb + BN - 1) / BN;
     dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)splits, (unsigned)M);
-    PB_CUDA(ctx, launch_k(kern, grid, dim3(NTHREADS), smem, st, g_pdl, A, lda, sA, ka, B, ldb, sB, kb, rows, rps, out, ldo,
+    PB_CUDA(ctx, launch_k(kern, grid, dim3(NTHREADS), smem, st, A, lda, sA, ka, B, ldb, sB, kb, rows, rps, out, ldo,
                           split_stride, sOut, bias_out, tiles_n));
     PB_LAUNCH_CHECK(ctx);
     return PB_OK;
@@ -917,9 +897,8 @@ int configure_nn() {
 int launch_fused(pb_ctx* ctx, struct TrainState& s);
 int configure_fused();
 int configure_all() {
-    int rc = configure_nn<128, 64, 4, 2>();
+    int rc = configure_nn<32, 64, 2, 4>();
     if (rc == PB_OK) rc = configure_fused();
-    if (rc == PB_OK) rc = configure_nn<32, 64, 2, 4>();
     if (rc == PB_OK) rc = launch_dw_t<false, true, true>(nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
     if (rc == PB_OK) rc = launch_dw_t<true, true, true>(nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
     if (rc == PB_OK) rc = launch_dw_t<false, true, false>(nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
@@ -934,7 +913,7 @@ int configure_all() {
 int launch_adam(pb_ctx* ctx, TrainState& s, int update) {
     const TrainKey& k = s.key;
     dim3 grid((unsigned)((s.tab.P + 255) / 256), (unsigned)k.M);
-    PB_CUDA(ctx, launch_k(train_adam_kernel, grid, dim3(256), 0, ctx->stream, g_pdl && update, s.tab, k.params, k.am, k.av,
+    PB_CUDA(ctx, launch_k(train_adam_kernel, grid, dim3(256), 0, ctx->stream, s.tab, k.params, k.am, k.av,
                           s.WT, s.packed, (const double*)s.gpart, k.n_pass, k.use_adv ? 2 : 1, s.splits, k.M, k.lr, k.lam, s.tstep,
                           s.eidx, (const double*)s.nllpart, s.nll_blocks, s.regpart, s.ticket, s.loss, update));
     PB_LAUNCH_CHECK(ctx);
@@ -958,17 +937,13 @@ int launch_fused_t(pb_ctx* ctx, TrainState* sp) {
     for (int p = 0; p < 2; ++p) { a.act[p] = s.act[p]; a.del[p] = s.del[p]; }
     for (int l = 0; l <= k.n_layers; ++l) { a.act_off[l] = s.act_off[l]; a.del_off[l] = s.del_off[l]; }
     a.nllpart = s.nllpart; a.adv_eps = k.adv_eps; a.soft_0 = k.soft_0;
-    PB_CUDA(ctx, launch_k(kern, dim3((unsigned)s.fused_grid), dim3(FUSED_THREADS), smem, ctx->stream, false, a));
+    PB_CUDA(ctx, launch_k(kern, dim3((unsigned)s.fused_grid), dim3(FUSED_THREADS), smem, ctx->stream, a));
     PB_LAUNCH_CHECK(ctx);
     return PB_OK;
 }
 
 int launch_fused(pb_ctx* ctx, TrainState& s) {
-    switch (s.mt) {
-        case 16: return launch_fused_t<16>(ctx, &s);
-        case 32: return launch_fused_t<32>(ctx, &s);
-        default: return launch_fused_t<64>(ctx, &s);
-    }
+    return s.mt == 16 ? launch_fused_t<16>(ctx, &s) : launch_fused_t<32>(ctx, &s);
 }
 
 template <bool BIG>
@@ -979,7 +954,7 @@ int launch_dw_multi_t(pb_ctx* ctx, TrainState* sp) {
     if (!ctx) return set_smem(ctx, kern, smem);
     TrainState& s = *sp; const TrainKey& k = s.key;
     dim3 grid((unsigned)s.dw_tiles, (unsigned)s.splits, (unsigned)k.M);
-    PB_CUDA(ctx, launch_k(kern, grid, dim3(NTHREADS), smem, ctx->stream, false, s.jobs, (int64_t)k.N, s.rps, s.gpart,
+    PB_CUDA(ctx, launch_k(kern, grid, dim3(NTHREADS), smem, ctx->stream, s.jobs, (int64_t)k.N, s.rps, s.gpart,
                           (int64_t)k.M * s.tab.P, (int64_t)s.tab.P));
     PB_LAUNCH_CHECK(ctx);
     return PB_OK;
@@ -988,7 +963,6 @@ int launch_dw_multi_t(pb_ctx* ctx, TrainState* sp) {
 int configure_fused() {
     int rc = launch_fused_t<16>(nullptr, nullptr);
     if (rc == PB_OK) rc = launch_fused_t<32>(nullptr, nullptr);
-    if (rc == PB_OK) rc = launch_fused_t<64>(nullptr, nullptr);
     if (rc == PB_OK) rc = launch_dw_multi_t<false>(nullptr, nullptr);
     if (rc == PB_OK) rc = launch_dw_multi_t<true>(nullptr, nullptr);
     return rc;
@@ -1026,7 +1000,7 @@ int run_epoch(pb_ctx* ctx, TrainState& s) {
         }
         {   // NLL + head gradient, in place
             dim3 grid((unsigned)s.nll_blocks, (unsigned)M);
-            PB_CUDA(ctx, launch_k(train_nll_kernel, grid, dim3(256), 0, st, g_pdl, s.del[p] + s.del_off[L - 1],
+            PB_CUDA(ctx, launch_k(train_nll_kernel, grid, dim3(256), 0, st, s.del[p] + s.del_off[L - 1],
                                   (int64_t)(N * k.dims[L]), k.v, N, n_L, k.soft_0,
                                   s.nllpart + (int64_t)p * M * s.nll_blocks));
             PB_LAUNCH_CHECK(ctx);
@@ -1100,7 +1074,6 @@ extern "C" int pb_ensemble_train(pb_ctx* ctx, int n_members, int n_layers, const
     {
         static bool configured = false;
         if (!configured) {
-            if (getenv("PB_TRAIN_PDL")) g_pdl = atoi(getenv("PB_TRAIN_PDL")) != 0;
             if (configure_all() != PB_OK) PB_FAIL(ctx, PB_ERR_CUDA, "pb_ensemble_train: kernel configuration failed: %s", pb_last_error(nullptr));
             configured = true;
         }
@@ -1170,10 +1143,10 @@ extern "C" int pb_ensemble_train(pb_ctx* ctx, int n_members, int n_layers, const
                 // 32-row tiles (two co-resident CTAs per SM overlap each other's epilogues) once there are enough
                 // items to fill them twice over, else 16-row tiles (measured: profiles/r01_notes.md)
                 int mt = ((int64_t)M * ((N + 31) / 32) >= 4 * (int64_t)ctx->sm_count) ? 32 : 16;
-                if (force_mt == 16 || force_mt == 32 || force_mt == 64) mt = force_mt;
+                if (force_mt == 16 || force_mt == 32) mt = force_mt;
                 s.mt = mt; s.n_tiles = (int)((N + mt - 1) / mt);
                 static const int cps_env = getenv("PB_TRAIN_CPS") ? atoi(getenv("PB_TRAIN_CPS")) : 0;
-                const int cps = cps_env ? cps_env : (mt <= 32 ? 2 : 1);            // co-resident CTAs per SM
+                const int cps = cps_env ? cps_env : 2;                             // co-resident CTAs per SM
                 s.fused_grid = (int)std::min<int64_t>((int64_t)M * s.n_tiles, (int64_t)ctx->sm_count * cps);
                 s.nll_blocks = s.n_tiles;
                 PB_TRY(reserve(ctx, &s.packed, &s.cap_packed, (size_t)M * t.SP));

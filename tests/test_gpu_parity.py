@@ -258,6 +258,28 @@ def test_projection_reconstruction_pod_sig(ctx):
     assert np.array_equal(sig2.download(), sig.download())
 
 
+@pytest.mark.parametrize("n_h,n,nl", [(1000, 256, 5), (777, 1000, 14), (333, 1001, 32), (129, 513, 37), (64, 300, 64),
+                                      (50, 260, 70), (31, 255, 14)])
+def test_reconstruction_strip_kernel_shapes(ctx, n_h, n, nl):
+    """V v^T and pod_sig = mean_j |U - V v^T| / 2 (podnnmodel.py:251-253) over ragged shapes: the strip kernel
+    (n_L <= 64, n >= 256; odd n takes the unaligned staging path), the tiled kernel otherwise."""
+    rng = np.random.default_rng(n_h + n + nl)
+    V, v, U = rng.standard_normal((n_h, nl)), rng.standard_normal((n, nl)), rng.standard_normal((n_h, n))
+    L = _lib.lib()
+    Vd, vd, Ud = ctx.to_device(V), ctx.to_device(v), ctx.to_device(U)
+    Up, sig, sig2 = ctx.alloc(n_h, n), ctx.alloc(n_h), ctx.alloc(n_h)
+    ctx.check(L.pb_reconstruct(ctx.h, Vd.ptr, Vd.ld, nl, vd.ptr, n, n_h, Ud.ptr, Ud.ld, Up.ptr, Up.ld, sig.ptr))
+    ref = V @ v.T
+    assert np.abs(Up.download() - ref).max() <= 1e-13 * np.abs(ref).max() * nl
+    ref_sig = po.pod_sig(U, ref)
+    assert cmp.rel_err(sig.download(), ref_sig) <= 1e-12
+    ctx.check(L.pb_reconstruct(ctx.h, Vd.ptr, Vd.ld, nl, vd.ptr, n, n_h, Ud.ptr, Ud.ld, None, 0, sig2.ptr))
+    assert np.array_equal(sig2.download(), sig.download())
+    Up2 = ctx.alloc(n_h, n)                                   # U_pod alone
+    ctx.check(L.pb_reconstruct(ctx.h, Vd.ptr, Vd.ld, nl, vd.ptr, n, n_h, None, 0, Up2.ptr, Up2.ld, None))
+    assert np.array_equal(Up2.download(), Up.download())
+
+
 def test_struct_matrix_roundtrip(ctx):
     rng = np.random.default_rng(4)
     Us = rng.standard_normal((37, 9, 5))
