@@ -47,6 +47,7 @@ extern "C" {
 #define PB_POD_GRAM      0  /* method of snapshots, one Gram pass                     */
 #define PB_POD_GRAM2     1  /* + second Gram pass on the rotated numerical-rank block */
 #define PB_POD_ACCURATE  2  /* full rotate + second Gram (Jacobi-SVD accuracy class)  */
+#define PB_POD_TSQR      3  /* Householder QR of U (never U^T U), pivoted QR + Jacobi SVD of R */
 
 /* input normalisation of the surrogate (varneuralnetwork.py:10-12,75-86) */
 #define PB_NORM_NONE     0
@@ -64,7 +65,8 @@ extern "C" {
 #define PB_T_POD_TOTAL  7
 #define PB_T_PASS2      8
 #define PB_T_TN_KERNEL  9   /* the split-K DMMA kernel of the last pb_gram / TN product alone */
-#define PB_T_COUNT      10
+#define PB_T_QR         10  /* the blocked Householder QR of the last pb_tsqr_r / TSQR-mode pb_pod */
+#define PB_T_COUNT      11
 
 typedef struct pb_ctx pb_ctx;
 
@@ -163,6 +165,18 @@ int  pb_pod_basis(pb_ctx* ctx, const double* A_dev, int64_t n_rows, int64_t lda,
 int  pb_pod_sigma(pb_ctx* ctx, double* sigma_host, int64_t capacity, int64_t* count);
 /* right factor of the last decomposition: Z (n_cols x n_L, ld = n_L), V = A Z diag(1/sigma) */
 int  pb_pod_right(pb_ctx* ctx, double* Z_dev, int64_t ldz);
+
+/* TSQR accuracy mode (north_star: "a TSQR accuracy mode for ill-conditioned snapshot sets"; the reference's SVD,
+ * pod.py:16, works on U itself -- so does this mode, the Gram modes work on U^T U).
+ *   pb_tsqr_r:     R (n_cols x n_cols, ld = n_cols, upper triangular, zeros below) of the local slab A
+ *                  (n_rows x n_cols): blocked Householder QR, Q is not formed.  Row-sharded: every rank calls it on
+ *                  its slab, all-gathers the P factors, stacks them (P n_cols x n_cols) and calls pb_tsqr_r again
+ *                  on the stack (replicated) -- TSQR with one leaf per GPU.
+ *   pb_pod_from_r: rank-revealing pivoted QR of R, one-sided Jacobi SVD of the factor, truncation rank
+ *                  (pod.py:22-32).  Afterwards pb_pod_basis(A, ..., Y = NULL, V) gives V = A Z / sigma (pod.py:42-45)
+ *                  and pb_pod_sigma / pb_pod_right work as after pb_pod_from_gram. */
+int  pb_tsqr_r(pb_ctx* ctx, const double* A_dev, int64_t n_rows, int64_t n_cols, int64_t lda, double* R_dev);
+int  pb_pod_from_r(pb_ctx* ctx, const double* R_dev, int64_t n_cols, double eps, int n_L_in, int* n_L);
 
 /* One-call single-GPU POD of a device matrix (tall or wide).  V via pb_pod_basis_full(). */
 int  pb_pod(pb_ctx* ctx, const double* U_dev, int64_t n_h, int64_t n_st, int64_t ldu,

@@ -85,7 +85,7 @@ int pb_destroy(pb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     void* bufs[] = {ctx->ws, ctx->flush, ctx->At, ctx->At2, ctx->sig, ctx->nrm, ctx->sig2, ctx->nrm2, ctx->perm,
-                    ctx->perm2, ctx->Bmat, ctx->Wk, ctx->small, ctx->Gbuf, ctx->G2buf, ctx->Ybuf, ctx->ATbuf, ctx->Uf, ctx->d_int, ctx->fp_ibuf,
+                    ctx->perm2, ctx->Bmat, ctx->Wk, ctx->small, ctx->qr_W, ctx->qr_Y, ctx->qr_scr, ctx->qr_scr2, ctx->Gbuf, ctx->G2buf, ctx->Ybuf, ctx->ATbuf, ctx->Uf, ctx->d_int, ctx->fp_ibuf,
                     ctx->fp_buf[0], ctx->fp_buf[1], ctx->fp_buf[2], ctx->fp_buf[3], ctx->fp_buf[4], ctx->fp_buf[5], ctx->fp_buf[6], ctx->fp_buf[7]};
     for (void* b : bufs) if (b) cudaFree(b);
     if (ctx->h_int) cudaFreeHost(ctx->h_int);
@@ -198,6 +198,7 @@ static int fetch_sigma(pb_ctx* ctx, const double* sig_dev, int64_t count, int64_
 
 int pb_pod_from_gram(pb_ctx* ctx, const double* G, int64_t m, double eps, int n_L_in, int mode, int* n_L, int* n_keep) {
     if (!ctx || !n_L) return PB_ERR_ARG;
+    if (mode == PB_POD_TSQR) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod_from_gram: the TSQR mode starts from pb_tsqr_r / pb_pod_from_r, not from a Gram matrix");
     if (mode < PB_POD_GRAM || mode > PB_POD_ACCURATE) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod: unknown mode %d", mode);
     if (!(eps >= 0.) || eps >= 1.) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod: eps must be in [0, 1)");
     Timer t(ctx, PB_T_EIG);
@@ -269,7 +270,7 @@ int pb_pod_basis(pb_ctx* ctx, const double* A, int64_t rows, int64_t lda, const 
         PB_TRY(pbi_factor_to_right(ctx, ctx->At2, keep, nl, ctx->perm2, ctx->nrm2, ctx->sig2, ctx->Bmat, nl));
         PB_TRY(pbi_gemm_nn(ctx, Y, keep, rows, keep, ctx->Bmat, nl, nl, V, ldv, nullptr, 0, nullptr));
     } else {
-        if (ctx->mode != PB_POD_GRAM) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod_basis: second pass not finished");
+        if (ctx->mode != PB_POD_GRAM && ctx->mode != PB_POD_TSQR) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod_basis: second pass not finished");
         const int64_t m = ctx->m;
         PB_TRY(pb_reserve(ctx, &ctx->Bmat, &ctx->B_cap, (size_t)m * nl));
         PB_TRY(pbi_factor_to_right(ctx, ctx->At, m, nl, ctx->perm, ctx->nrm, ctx->sig, ctx->Bmat, nl));
@@ -299,6 +300,41 @@ int pb_pod_right(pb_ctx* ctx, double* Z, int64_t ldz) {
     } else {
         PB_TRY(pbi_factor_to_right(ctx, ctx->At, m, nl, ctx->perm, ctx->nrm, nullptr, Z, ldz));
     }
+    return PB_OK;
+}
+
+// ---------------------------------------------------------------- TSQR mode
+int pb_tsqr_r(pb_ctx* ctx, const double* A, int64_t rows, int64_t cols, int64_t lda, double* R) {
+    if (!ctx || !A || !R) return PB_ERR_ARG;
+    if (rows <= 0 || cols <= 0 || lda < cols) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_tsqr_r: bad shape (%lld x %lld, ld %lld)",
+                                                       (long long)rows, (long long)cols, (long long)lda);
+    Timer t(ctx, PB_T_QR);
+    PB_TRY(pbi_qr_r(ctx, A, rows, cols, lda, R, cols, cols));
+    t.stop();
+    return PB_OK;
+}
+
+int pb_pod_from_r(pb_ctx* ctx, const double* R, int64_t m, double eps, int n_L_in, int* n_L) {
+    if (!ctx || !R || !n_L) return PB_ERR_ARG;
+    if (m <= 0 || m > 8192) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod_from_r: order %lld outside (0, 8192]", (long long)m);
+    if (!(eps >= 0.) || eps >= 1.) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod: eps must be in [0, 1)");
+    Timer t(ctx, PB_T_EIG);
+    ctx->m = m; ctx->mode = PB_POD_TSQR; ctx->pass2_done = false; ctx->n_keep = 0;
+    PB_TRY(pb_reserve(ctx, &ctx->sig, &ctx->sig_cap, (size_t)m + 32));
+    PB_TRY(pb_reserve(ctx, &ctx->nrm, &ctx->nrm_cap, (size_t)m + 32));
+    PB_TRY(pb_reserve_int(ctx, &ctx->perm, &ctx->perm_cap, (size_t)m + 64));
+    const int64_t ldm = (m + 7) / 8 * 8, cap_rows = (m + 31) / 32 * 32;
+    PB_TRY(pb_reserve(ctx, &ctx->At, &ctx->At_cap, (size_t)cap_rows * ldm));
+    PB_TRY(pbi_qr_load_factor(ctx, R, m, m, ctx->At, ldm, cap_rows));
+    // eps == 0 asks for every mode (pod.py default): no truncation.  Otherwise stop the pivoted QR at the numerical
+    // rank: what is left is below m eps |R| -- the backward error of the QR itself
+    const bool full = (eps == 0. && n_L_in == 0);
+    PB_TRY(pbi_qrcp_factor(ctx, ctx->At, m, ldm, cap_rows, full ? 0. : (double)m * DBL_EPSILON, &ctx->r));
+    if (ctx->r <= 0) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod_from_r: zero matrix");
+    PB_TRY(pbi_jacobi_factor(ctx, ctx->At, m, ctx->r, nullptr, ctx->sig, ctx->nrm, ctx->perm, &ctx->sweeps1, 60));
+    PB_TRY(fetch_sigma(ctx, ctx->sig, m, m));
+    PB_TRY(finish_rank(ctx, ctx->sig, m, ctx->r, eps, n_L_in, n_L));
+    t.stop();
     return PB_OK;
 }
 
@@ -333,9 +369,15 @@ int pb_pod(pb_ctx* ctx, const double* U, int64_t n_h, int64_t n_st, int64_t ldu,
     }
     if (m > 8192) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod: min(n_h, n_st) = %lld exceeds 8192", (long long)m);
     PB_TRY(pb_reserve(ctx, &ctx->Gbuf, &ctx->G_cap, (size_t)m * m));
-    PB_TRY(pb_gram(ctx, A, rows, m, lda, ctx->Gbuf));
     ctx->wide = wide;
-    PB_TRY(pod_after_gram(ctx, A, rows, m, lda, eps, n_L_in, mode, n_L));
+    if (mode == PB_POD_TSQR) {
+        ctx->ms[PB_T_GRAM] = 0.; ctx->ms[PB_T_PASS2] = 0.;
+        PB_TRY(pb_tsqr_r(ctx, A, rows, m, lda, ctx->Gbuf));
+        PB_TRY(pb_pod_from_r(ctx, ctx->Gbuf, m, eps, n_L_in, n_L));
+    } else {
+        PB_TRY(pb_gram(ctx, A, rows, m, lda, ctx->Gbuf));
+        PB_TRY(pod_after_gram(ctx, A, rows, m, lda, eps, n_L_in, mode, n_L));
+    }
     cudaEventRecord(ctx->ev3, ctx->stream); cudaEventSynchronize(ctx->ev3);
     float ms = 0; cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3); ctx->ms[PB_T_POD_TOTAL] = ms;
     return PB_OK;
@@ -414,7 +456,8 @@ int pb_pod_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, in
     cudaEventRecord(ctx->ev2, ctx->stream);
     const int64_t m = n_st;
     if (n_h >= n_st) PB_TRY(pb_reserve(ctx, &ctx->Gbuf, &ctx->G_cap, (size_t)m * m));
-    int rc = gram_host_chunked(ctx, U_host, n_h, n_st, ldu_host, U_dev, ctx->Gbuf);
+    // the TSQR mode has no Gram to overlap with the upload: plain copy, then the device path
+    int rc = mode == PB_POD_TSQR ? 1 : gram_host_chunked(ctx, U_host, n_h, n_st, ldu_host, U_dev, ctx->Gbuf);
     if (rc == 1) {        // small or wide: plain upload, then the device path
         PB_CUDA(ctx, cudaMemcpy2DAsync(U_dev, n_st * sizeof(double), U_host, ldu_host * sizeof(double),
                                        n_st * sizeof(double), n_h, cudaMemcpyHostToDevice, ctx->stream));
@@ -519,7 +562,7 @@ int pb_fast_pod(pb_ctx* ctx, const double* U, int64_t n_h, int n_t, int64_t n_s,
                 double eps, double eps_init, int mode, int* n_L, int* ranks_host) {
     if (!ctx || !n_L) return PB_ERR_ARG;
     if (n_t <= 0 || n_s <= 0 || ldu < n_s * n_t) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_fast_pod: bad shape");
-    if (mode < PB_POD_GRAM || mode > PB_POD_ACCURATE) PB_FAIL(ctx, PB_ERR_ARG, "pb_fast_pod: unknown mode %d", mode);
+    if (mode < PB_POD_GRAM || mode > PB_POD_TSQR) PB_FAIL(ctx, PB_ERR_ARG, "pb_fast_pod: unknown mode %d", mode);
     if (!(eps >= 0.) || eps >= 1. || !(eps_init >= 0.) || eps_init >= 1.) PB_FAIL(ctx, PB_ERR_ARG, "pb_fast_pod: eps in [0, 1)");
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, ctx->stream);
@@ -530,7 +573,10 @@ int pb_fast_pod(pb_ctx* ctx, const double* U, int64_t n_h, int n_t, int64_t n_s,
     int64_t off = 0;
     static const bool batched_ok = []{ const char* e = getenv("PB_FASTPOD_BATCHED"); return !e || atoi(e) != 0; }();
     if (rc == PB_OK && batched_ok && n_h >= n_t && n_t <= 1024 && n_s < 65536) {
-        rc = fast_pod_stage1_batched(ctx, U, n_h, n_t, n_s, ldu, eps_init, mode, ranks_host, ldf, &off);
+        // TSQR mode: the per-sample stage runs the batched accurate path (n_s small PODs of n_h x n_t), the global
+        // stage below the TSQR path
+        rc = fast_pod_stage1_batched(ctx, U, n_h, n_t, n_s, ldu, eps_init, mode == PB_POD_TSQR ? PB_POD_ACCURATE : mode,
+                                     ranks_host, ldf, &off);
     } else {
         for (int64_t k = 0; k < n_s && rc == PB_OK; ++k) {     // general shapes: one POD per sample
             int rk = 0;

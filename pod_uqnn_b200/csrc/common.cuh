@@ -59,6 +59,8 @@ struct pb_ctx {
     int* d_int = nullptr;   // device ints (flags, n_L ...)
     int* h_int = nullptr;   // pinned host mirror
     std::vector<double> sigma_host;  // singular values of the last decomposition
+    double* qr_W = nullptr; double* qr_Y = nullptr; double* qr_scr = nullptr; double* qr_scr2 = nullptr;   // TSQR mode (qr.cu)
+    size_t qr_W_cap = 0, qr_Y_cap = 0, qr_scr_cap = 0, qr_scr2_cap = 0;
     void* train_state = nullptr;     // pb_ensemble_train: work buffers, side stream, captured epoch graph (train.cu)
 };
 void pbi_train_free(pb_ctx* ctx);
@@ -98,6 +100,16 @@ int pbi_transpose(pb_ctx* ctx, const double* in, int64_t rows, int64_t cols, int
 int pbi_eig_psd(pb_ctx* ctx, const double* G, int64_t m, double tol_rel, double shift_rel,
                 double** At_buf, size_t* At_cap, double* sig_dev, double* nrm_dev, int* perm_dev,
                 int* r_out, int* sweeps_out, int max_sweeps);
+// one-sided block Jacobi + norms + sort on r factor vectors already in At (shift_dev == nullptr: no shift)
+int pbi_jacobi_factor(pb_ctx* ctx, double* At, int64_t m, int r, const double* shift_dev, double* sig_dev, double* nrm_dev,
+                      int* perm_dev, int* sweeps_out, int max_sweeps);
+// TSQR mode (qr.cu): R factor of a tall matrix; rank-revealing pivoted QR of the small factor held in At
+int pbi_qr_r(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, double* R, int64_t ldr, int64_t rows_out);
+int pbi_qr_load_factor(pb_ctx* ctx, const double* R, int64_t ldr, int64_t m, double* At, int64_t ldm, int64_t rows_total);
+int pbi_qrcp_factor(pb_ctx* ctx, double* At, int64_t m, int64_t ldm, int64_t rows_total, double tol_rel, int* r_out);
+// Y (rows x k, ldy) -= A (rows x m, lda) B (m x k, ldb)
+int pbi_gemm_nn_sub(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m, const double* B, int64_t ldb,
+                    int64_t k, double* Y, int64_t ldy);
 // n_L from descending lambdas = sig^2 (pod.py:22-32)
 int pbi_rank(pb_ctx* ctx, const double* sig_dev, int64_t count, double eps, int* n_L_out);
 // B (m x k, ldb) [i][j] = At[perm[j]][i] / (nrm[j] * (sig ? sig[j] : 1))

@@ -498,6 +498,62 @@ static int get_scratch(pb_ctx* ctx, int64_t m, EigScratch* s) {
     return PB_OK;
 }
 
+// One-sided block Jacobi on the r factor vectors held in At (rows of length ldm, zero padded up to a multiple of 32
+// rows), then norms, sort, sigma = sqrt(norm^2 - *shift_dev).  Shared by the Cholesky path (pbi_eig_psd) and the TSQR
+// path (qr.cu: rows of the pivoted R factor).
+int pbi_jacobi_factor(pb_ctx* ctx, double* At, int64_t m, int r, const double* shift_dev, double* sig_dev, double* nrm_dev,
+                      int* perm_dev, int* sweeps_out, int max_sweeps) {
+    const int64_t ldm = (m + 7) / 8 * 8;
+    EigScratch sc; PB_TRY(get_scratch(ctx, m, &sc));
+    double* nrm2_scr = sc.nrm2;
+    if (!shift_dev) {                                         // no diagonal shift (TSQR path)
+        PB_CUDA(ctx, cudaMemsetAsync(sc.shift, 0, sizeof(double), ctx->stream));
+        shift_dev = sc.shift;
+    }
+    // ---- one-sided block Jacobi on the r vectors
+    int nb = (r + JB - 1) / JB; if (nb & 1) ++nb;             // even number of blocks (zero padded)
+    const int nvec = nb * JB;
+    // rotation threshold relative to the column norms (dgesvj uses sqrt(m) eps): below it the
+    // pair Gram entry is rounding noise of the m-long dot product
+    const double tol = g_jacobi_tol_override > 0. ? g_jacobi_tol_override : std::max(4., sqrt((double)m)) * DBL_EPSILON;
+    g_jacobi_tol_override = 0.;
+    size_t jac_smem = sizeof(double) * 2 * JP * JPX;
+    PB_CUDA(ctx, cudaFuncSetAttribute(jacobi_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jac_smem));
+    int sweeps = 0; bool converged = false;
+    const bool trust_single = g_trust_single_pair && nb == 2;
+    g_trust_single_pair = false;
+    for (; sweeps < max_sweeps && !converged; ++sweeps) {
+        PB_CUDA(ctx, cudaMemsetAsync(ctx->d_int + 1, 0, sizeof(int), ctx->stream));
+        const int rounds = nb > 2 ? nb - 1 : 1;
+        for (int round = 0; round < rounds; ++round) {
+            // a single pair (r <= 32): its 32 x 32 problem IS the whole problem -- solve it to convergence at once
+            JacArgs ja{At, ldm, nb, round, tol, ctx->d_int + 1, nb == 2 ? 16 : g_inner_sweeps, 0, (g_cross_rounds && round > 0) ? 1 : 0};
+            jacobi_pair_kernel<<<nb / 2, 256, jac_smem, ctx->stream>>>(ja);
+            PB_LAUNCH_CHECK(ctx);
+        }
+        if (trust_single) { converged = true; continue; }
+        PB_CUDA(ctx, cudaMemcpyAsync(ctx->h_int + 1, ctx->d_int + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        converged = (ctx->h_int[1] == 0);
+    }
+    if (!converged && max_sweeps >= 30)
+        PB_FAIL(ctx, PB_ERR_NOT_CONVERGED, "eig_psd: Jacobi did not converge in %d sweeps (m=%lld r=%d)", max_sweeps, (long long)m, r);
+
+    // ---- norms, sort, sigma
+    norms_kernel<<<nvec, 256, 0, ctx->stream>>>(At, ldm, nvec, nrm2_scr, 0, 0);
+    PB_LAUNCH_CHECK(ctx);
+    int npow2 = 1; while (npow2 < nvec) npow2 <<= 1;
+    size_t sort_smem = (sizeof(double) + sizeof(int)) * (size_t)npow2;
+    PB_CUDA(ctx, cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+    sort_kernel<<<1, 1024, sort_smem, ctx->stream>>>(nrm2_scr, nvec, npow2, shift_dev, sig_dev, nrm_dev, (int)m, perm_dev, ctx->d_int + 3, 0, 0, 0);
+    PB_LAUNCH_CHECK(ctx);
+    PB_CUDA(ctx, cudaMemcpyAsync(ctx->h_int + 3, ctx->d_int + 3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (sweeps_out) *sweeps_out = sweeps;
+    return PB_OK;
+}
+
+
 int pbi_eig_psd(pb_ctx* ctx, const double* G, int64_t m, double tol_rel, double shift_rel,
                 double** At_buf, size_t* At_cap, double* sig_dev, double* nrm_dev, int* perm_dev,
                 int* r_out, int* sweeps_out, int max_sweeps) {
@@ -543,48 +599,8 @@ int pbi_eig_psd(pb_ctx* ctx, const double* G, int64_t m, double tol_rel, double 
     }
     const int r = ctx->h_int[0];
     if (r <= 0) PB_FAIL(ctx, PB_ERR_SHAPE, "eig_psd: matrix has no positive pivot (zero or indefinite input)");
-
-    // ---- one-sided block Jacobi on the r vectors
-    int nb = (r + JB - 1) / JB; if (nb & 1) ++nb;             // even number of blocks (zero padded)
-    const int nvec = nb * JB;
-    // rotation threshold relative to the column norms (dgesvj uses sqrt(m) eps): below it the
-    // pair Gram entry is rounding noise of the m-long dot product
-    const double tol = g_jacobi_tol_override > 0. ? g_jacobi_tol_override : std::max(4., sqrt((double)m)) * DBL_EPSILON;
-    g_jacobi_tol_override = 0.;
-    size_t jac_smem = sizeof(double) * 2 * JP * JPX;
-    PB_CUDA(ctx, cudaFuncSetAttribute(jacobi_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jac_smem));
-    int sweeps = 0; bool converged = false;
-    const bool trust_single = g_trust_single_pair && nb == 2;
-    g_trust_single_pair = false;
-    for (; sweeps < max_sweeps && !converged; ++sweeps) {
-        PB_CUDA(ctx, cudaMemsetAsync(ctx->d_int + 1, 0, sizeof(int), ctx->stream));
-        const int rounds = nb > 2 ? nb - 1 : 1;
-        for (int round = 0; round < rounds; ++round) {
-            // a single pair (r <= 32): its 32 x 32 problem IS the whole problem -- solve it to convergence at once
-            JacArgs ja{At, ldm, nb, round, tol, ctx->d_int + 1, nb == 2 ? 16 : g_inner_sweeps, 0, (g_cross_rounds && round > 0) ? 1 : 0};
-            jacobi_pair_kernel<<<nb / 2, 256, jac_smem, ctx->stream>>>(ja);
-            PB_LAUNCH_CHECK(ctx);
-        }
-        if (trust_single) { converged = true; continue; }
-        PB_CUDA(ctx, cudaMemcpyAsync(ctx->h_int + 1, ctx->d_int + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        converged = (ctx->h_int[1] == 0);
-    }
-    if (!converged && max_sweeps >= 30)
-        PB_FAIL(ctx, PB_ERR_NOT_CONVERGED, "eig_psd: Jacobi did not converge in %d sweeps (m=%lld r=%d)", max_sweeps, (long long)m, r);
-
-    // ---- norms, sort, sigma
-    norms_kernel<<<nvec, 256, 0, ctx->stream>>>(At, ldm, nvec, sc.nrm2, 0, 0);
-    PB_LAUNCH_CHECK(ctx);
-    int npow2 = 1; while (npow2 < nvec) npow2 <<= 1;
-    size_t sort_smem = (sizeof(double) + sizeof(int)) * (size_t)npow2;
-    PB_CUDA(ctx, cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
-    sort_kernel<<<1, 1024, sort_smem, ctx->stream>>>(sc.nrm2, nvec, npow2, sc.shift, sig_dev, nrm_dev, (int)m, perm_dev, ctx->d_int + 3, 0, 0, 0);
-    PB_LAUNCH_CHECK(ctx);
-    PB_CUDA(ctx, cudaMemcpyAsync(ctx->h_int + 3, ctx->d_int + 3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PB_TRY(pbi_jacobi_factor(ctx, At, m, r, sc.shift, sig_dev, nrm_dev, perm_dev, sweeps_out, max_sweeps));
     *r_out = r;                                   // factor vectors; sig may be zero for shifted noise modes
-    if (sweeps_out) *sweeps_out = sweeps;
     return PB_OK;
 }
 

@@ -152,7 +152,7 @@ gemm_nn_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int m,
                const double* __restrict__ B, int64_t ldb, int k,
                double* __restrict__ Y, int64_t ldy,
                const double* __restrict__ Uref, int64_t ldu, double* __restrict__ sig_part,
-               int64_t bsA, int64_t bsB, int64_t bsY) {
+               int64_t bsA, int64_t bsB, int64_t bsY, int subtract) {
     constexpr int BM = 128;
     A += (int64_t)blockIdx.z * bsA; B += (int64_t)blockIdx.z * bsB;
     if (Y) Y += (int64_t)blockIdx.z * bsY;                                   // batch
@@ -232,8 +232,13 @@ gemm_nn_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int m,
             for (int u = 0; u < TNN; ++u) {
                 int64_t j = j0 + wn * WN + u * 8 + 2 * lk;
                 if (Y) {
-                    if (j < k)     Y[h * ldy + j]     = acc[t][u][0];
-                    if (j + 1 < k) Y[h * ldy + j + 1] = acc[t][u][1];
+                    if (subtract) {          // Y -= A B (trailing update of the blocked Householder QR, qr.cu)
+                        if (j < k)     Y[h * ldy + j]     -= acc[t][u][0];
+                        if (j + 1 < k) Y[h * ldy + j + 1] -= acc[t][u][1];
+                    } else {
+                        if (j < k)     Y[h * ldy + j]     = acc[t][u][0];
+                        if (j + 1 < k) Y[h * ldy + j + 1] = acc[t][u][1];
+                    }
                 }
                 if (want_mom) {
                     if (j < k)     { msum[h * ldm_ + j] += acc[t][u][0];     sig_part[h * ldm_ + j] += acc[t][u][0] * acc[t][u][0]; }
@@ -490,14 +495,14 @@ reduce:
 template <int BN, int WARPS_M, int WARPS_N, int STAGES = 4>
 int launch_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m, const double* B,
               int64_t ldb, int64_t k, double* Y, int64_t ldy, const double* Uref, int64_t ldu,
-              double* sig_part, Batch bt = Batch()) {
+              double* sig_part, Batch bt = Batch(), int subtract = 0) {
     size_t smem = (size_t)STAGES * (128 * (BK + 4) + BK * (BN + 4)) * sizeof(double);
     dim3 grid((unsigned)((rows + 127) / 128), (unsigned)((k + BN - 1) / BN), bt.count);
     const bool aa = aligned16(A, lda) && (bt.sA % 2 == 0), ab = aligned16(B, ldb) && (bt.sB % 2 == 0);
 #define PB_NN_CASE(AA, AB) { auto kern = gemm_nn_kernel<BN, WARPS_M, WARPS_N, STAGES, AA, AB>; \
         PB_TRY(set_smem(ctx, kern, smem)); \
         kern<<<grid, NTHREADS, smem, ctx->stream>>>(A, lda, rows, (int)m, B, ldb, (int)k, Y, ldy, Uref, ldu, sig_part, \
-                                                    bt.sA, bt.sB, bt.sC); }
+                                                    bt.sA, bt.sB, bt.sC, subtract); }
     if (aa && ab) PB_NN_CASE(true, true)
     else if (aa) PB_NN_CASE(true, false)
     else if (ab) PB_NN_CASE(false, true)
@@ -588,6 +593,16 @@ int pbi_gemm_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t
         PB_LAUNCH_CHECK(ctx);
     }
     return PB_OK;
+}
+
+int pbi_gemm_nn_sub(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m, const double* B, int64_t ldb,
+                    int64_t k, double* Y, int64_t ldy) {
+    if (rows <= 0 || m <= 0 || k <= 0) PB_FAIL(ctx, PB_ERR_SHAPE, "gemm_nn_sub: bad shape");
+    if (k > 96) return launch_nn<128, 2, 4>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, nullptr, 0, nullptr, Batch(), 1);
+    if (k > 64) return launch_nn<96, 2, 4>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, nullptr, 0, nullptr, Batch(), 1);
+    if (k > 32) return launch_nn<64, 4, 2>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, nullptr, 0, nullptr, Batch(), 1);
+    if (k > 16) return launch_nn<32, 8, 1>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, nullptr, 0, nullptr, Batch(), 1);
+    return launch_nn<16, 8, 1>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, nullptr, 0, nullptr, Batch(), 1);
 }
 
 int pbi_transpose(pb_ctx* ctx, const double* in, int64_t rows, int64_t cols, int64_t ldin,

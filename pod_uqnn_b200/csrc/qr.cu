@@ -1,0 +1,633 @@
+// TSQR accuracy mode of the POD (BASELINE.json north_star: "a TSQR accuracy mode for ill-conditioned snapshot
+// sets"; SURVEY.md section 8e: local QR per row shard, all-gather of the R factors, QR of the stack).
+//
+//   A (rows x m, tall)  --blocked Householder QR, R only-->  R1 (m x m)          [qr_panel_kernel + DMMA GEMMs]
+//   R1                  --Householder QR with column pivoting, rank revealing-->  r factor vectors  [qrcp_kernel]
+//   one-sided block Jacobi on the r vectors (eig.cu)  -->  sigma, right singular vectors Z;  V = A Z / sigma
+//
+// Working on A itself (never on A^T A) keeps the singular values and the right singular vectors at the accuracy of
+// LAPACK's dgesdd, which is what the reference calls (poduqnn/pod.py:16); V = A z / sigma is the reference's own
+// formula for the basis (pod.py:42-45), so Q is never formed or stored.
+//
+// Big QR: right-looking, outer panels of QNB = 64 columns on a working copy W of A.
+//   panel (cooperative kernel, CTAs own row ranges): inner panels of 16 columns, column by column with ONE grid
+//     barrier per column -- every CTA sends the partial dot products of the current column with the columns to its
+//     right (rows below the diagonal row) and the owner of the diagonal row sends that row; with those 2 x 16 numbers
+//     every CTA forms the same reflector (LAPACK dlarfg formulas) and updates its rows, accumulating the partial dot
+//     products of the NEXT column in the same pass.  The inner block reflector is applied to the rest of the outer
+//     panel on DMMA (Z = Y^T C reduced over the grid, X from tau and striu(Y^T Y) by forward substitution --
+//     T^-1 = diag(1/tau) + striu(Y^T Y), so T is never formed -- then C -= Y X).
+//   trailing update: Z = Y^T C and C -= Y X with the tall-skinny DMMA kernels of gemm.cu.
+// Small QRCP: CTAs own groups of 8 columns; a step picks the remaining column of largest norm (exactly recomputed in
+//   the previous update pass), reflects it and updates the remaining columns -- columns are never moved, so the rows
+//   of the result are the factor vectors in the ORIGINAL column order; one grid barrier per step; stops at the
+//   numerical rank.
+#include "common.cuh"
+#include "tile_ops.cuh"
+#include <cooperative_groups.h>
+#include <cfloat>
+#include <algorithm>
+namespace cg = cooperative_groups;
+
+namespace {
+using pbt::dmma884;
+
+constexpr int QNB = 64;     // outer panel width (columns)
+constexpr int QIB = 16;     // inner panel width
+constexpr int QT = 256;     // threads per CTA
+constexpr int ZE = QIB * QNB;   // entries of the inner Z block: 16 x (16 + up to 48)
+
+// explicit entry of the unit-lower-trapezoidal reflector block whose first column is c0: column a has its diagonal
+// in row c0 + a
+__device__ __forceinline__ double yval(const double* __restrict__ W, int64_t ldw, int64_t r, int c0, int a) {
+    const int64_t d = (int64_t)c0 + a;
+    return r > d ? W[r * ldw + d] : (r == d ? 1. : 0.);
+}
+
+// sum of v[0..16) over the CTA, result in out[0..16) (shared); fixed order
+__device__ __forceinline__ void block_sum16(double (&v)[QIB], double (*red)[QIB], double* out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < QIB; ++k) {
+        double s = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) red[warp][k] = s;
+    }
+    __syncthreads();
+    if (tid < QIB) {
+        double s = 0.;
+#pragma unroll
+        for (int w = 0; w < QT / 32; ++w) s += red[w][tid];
+        out[tid] = s;
+    }
+    __syncthreads();
+}
+
+struct QrPanelArgs {
+    double* W; int64_t ldw; int64_t rows;    // working copy (rows >= padded column count, zero padded)
+    int J; int nbo;                          // outer panel: columns [J, J + nbo), nbo a multiple of 16, <= 64
+    double* tau;                             // tau + J
+    double* part;                            // [2][G][16] partial dot products, double buffered
+    double* diag;                            // [2][16] the published diagonal row
+    double* zpart;                           // [G][ZE] per-CTA partial Z of the inner apply
+    double* zfin;                            // [ZE]
+};
+
+__global__ void __launch_bounds__(QT) qr_panel_kernel(QrPanelArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) double zred[];          // [8 warps][ZE]
+    __shared__ double red[QT / 32][QIB];
+    __shared__ double red2[QIB][QIB];
+    __shared__ double gsh[QIB], dsh[QIB], tau_sh[QIB], outsh[QIB];
+    __shared__ double Zs[ZE];
+    __shared__ double Xs[QIB][QNB - QIB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lk = lane & 3, lg = lane >> 2;
+    const int G = gridDim.x, b = blockIdx.x;
+    double* __restrict__ W = a.W; const int64_t ldw = a.ldw;
+    // row range of this CTA over the active rows [J, rows)
+    int64_t rpc = (a.rows - a.J + G - 1) / G; rpc = (rpc + 7) / 8 * 8;
+    const int64_t lo = (int64_t)a.J + (int64_t)b * rpc;
+    const int64_t hi = lo < a.rows ? (lo + rpc < a.rows ? lo + rpc : a.rows) : lo;
+    int par = 0;
+
+    for (int i0 = 0; i0 < a.nbo; i0 += QIB) {
+        const int c0 = a.J + i0;
+        // ---- prime: partial dots of column c0 with the 16 columns, rows below the diagonal row c0
+        {
+            double g[QIB];
+#pragma unroll
+            for (int k = 0; k < QIB; ++k) g[k] = 0.;
+            const int64_t rb = lo > c0 ? lo : (int64_t)c0;
+            for (int64_t r = rb + tid; r < hi; r += QT) {
+                double x[QIB];
+                const double2* src = reinterpret_cast<const double2*>(W + r * ldw + c0);
+#pragma unroll
+                for (int k = 0; k < QIB / 2; ++k) { double2 v = src[k]; x[2 * k] = v.x; x[2 * k + 1] = v.y; }
+                if (r == c0) {
+#pragma unroll
+                    for (int k = 0; k < QIB; ++k) a.diag[par * QIB + k] = x[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < QIB; ++k) g[k] += x[0] * x[k];
+                }
+            }
+            block_sum16(g, red, outsh);
+            if (tid < QIB) a.part[((size_t)par * G + b) * QIB + tid] = outsh[tid];
+        }
+        grid.sync();
+
+        for (int c = 0; c < QIB; ++c) {
+            const int64_t d = (int64_t)c0 + c;
+            // ---- every CTA reduces the partials in the same order
+            {
+                const int k = tid & 15, grp = tid >> 4;
+                double s = 0.;
+                for (int bb = grp; bb < G; bb += QT / 16) s += a.part[((size_t)par * G + bb) * QIB + k];
+                red2[grp][k] = s;
+                __syncthreads();
+                if (tid < QIB) {
+                    double t = 0.;
+#pragma unroll
+                    for (int q = 0; q < QT / 16; ++q) t += red2[q][tid];
+                    gsh[tid] = t; dsh[tid] = a.diag[par * QIB + tid];
+                }
+                __syncthreads();
+            }
+            // ---- reflector (LAPACK dlarfg): beta = -sign(alpha) hypot(alpha, xnorm), tau = (beta - alpha) / beta
+            const double alpha = dsh[c], xn2 = gsh[c];
+            double beta = alpha, tau = 0., scale = 0.;
+            if (xn2 > 0.) {
+                beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+                tau = (beta - alpha) / beta;
+                scale = 1. / (alpha - beta);
+            }
+            double w[QIB];
+#pragma unroll
+            for (int k = 0; k < QIB; ++k) w[k] = dsh[k] + gsh[k] * scale;     // v^T (column k), k > c
+            if (tid == 0) { tau_sh[c] = tau; if (b == 0) a.tau[i0 + c] = tau; }
+            // ---- update my rows; accumulate the partials of column c + 1
+            double g[QIB];
+#pragma unroll
+            for (int k = 0; k < QIB; ++k) g[k] = 0.;
+            const int64_t rb = lo > d ? lo : d;
+            for (int64_t r = rb + tid; r < hi; r += QT) {
+                double x[QIB];
+                double2* p = reinterpret_cast<double2*>(W + r * ldw + c0);
+#pragma unroll
+                for (int k = 0; k < QIB / 2; ++k) { double2 v = p[k]; x[2 * k] = v.x; x[2 * k + 1] = v.y; }
+                if (r == d) {
+#pragma unroll
+                    for (int k = 0; k < QIB; ++k) { if (k == c) x[k] = beta; else if (k > c) x[k] -= tau * w[k]; }
+                } else {
+                    double xc = 0.;
+#pragma unroll
+                    for (int k = 0; k < QIB; ++k) if (k == c) xc = x[k];
+                    const double v = xc * scale, tv = tau * v;
+                    double xn = 0.;
+#pragma unroll
+                    for (int k = 0; k < QIB; ++k) {
+                        if (k == c) x[k] = v; else if (k > c) x[k] -= tv * w[k];
+                        if (k == c + 1) xn = x[k];
+                    }
+                    if (c + 1 < QIB) {
+                        if (r == d + 1) {
+#pragma unroll
+                            for (int k = 0; k < QIB; ++k) if (k > c) a.diag[(par ^ 1) * QIB + k] = x[k];
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < QIB; ++k) if (k > c) g[k] += xn * x[k];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < QIB / 2; ++k) p[k] = make_double2(x[2 * k], x[2 * k + 1]);
+            }
+            if (c + 1 < QIB) {
+                block_sum16(g, red, outsh);
+                if (tid < QIB) a.part[((size_t)(par ^ 1) * G + b) * QIB + tid] = outsh[tid];
+                par ^= 1;
+                grid.sync();
+            }
+        }
+        par ^= 1;
+        __syncthreads();
+
+        // ---- apply the inner block reflector to the rest of the outer panel
+        const int ncols = a.nbo - i0 - QIB;
+        if (ncols > 0) {                                           // uniform
+            const int c1 = c0 + QIB;
+            const int nblk = (QIB + ncols) / 8;
+            const int64_t lo2 = lo > c0 ? lo : (int64_t)c0;
+            double zacc[2][QNB / 8][2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+#pragma unroll
+                for (int u = 0; u < QNB / 8; ++u) { zacc[t][u][0] = 0.; zacc[t][u][1] = 0.; }
+            for (int64_t r0 = lo2 + 4 * warp; r0 < hi; r0 += 4 * (QT / 32)) {
+                const int64_t r = r0 + lk;
+                const bool ok = r < hi;
+                const double a0 = ok ? yval(W, ldw, r, c0, lg) : 0.;
+                const double a1 = ok ? yval(W, ldw, r, c0, 8 + lg) : 0.;
+#pragma unroll
+                for (int u = 0; u < QNB / 8; ++u) {
+                    if (u < nblk) {
+                        double bv;
+                        if (u == 0) bv = a0; else if (u == 1) bv = a1;
+                        else bv = ok ? W[r * ldw + c1 + (u - 2) * 8 + lg] : 0.;
+                        dmma884(zacc[0][u][0], zacc[0][u][1], a0, bv);
+                        dmma884(zacc[1][u][0], zacc[1][u][1], a1, bv);
+                    }
+                }
+            }
+            double* my = zred + (size_t)warp * ZE;
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+#pragma unroll
+                for (int u = 0; u < QNB / 8; ++u) {
+                    my[(t * 8 + lg) * QNB + u * 8 + 2 * lk] = zacc[t][u][0];
+                    my[(t * 8 + lg) * QNB + u * 8 + 2 * lk + 1] = zacc[t][u][1];
+                }
+            __syncthreads();
+            for (int e = tid; e < ZE; e += QT) {
+                double s = 0.;
+#pragma unroll
+                for (int wq = 0; wq < QT / 32; ++wq) s += zred[(size_t)wq * ZE + e];
+                a.zpart[(size_t)b * ZE + e] = s;
+            }
+            grid.sync();
+            {   // second stage: CTA b finishes entries [b * epc, (b + 1) * epc)
+                const int epc = (ZE + G - 1) / G;
+                for (int el = warp; el < epc; el += QT / 32) {
+                    const int e = b * epc + el;
+                    if (e < ZE) {
+                        double s = 0.;
+                        for (int bb = lane; bb < G; bb += 32) s += a.zpart[(size_t)bb * ZE + e];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                        if (lane == 0) a.zfin[e] = s;
+                    }
+                }
+            }
+            grid.sync();
+            for (int e = tid; e < ZE; e += QT) Zs[e] = a.zfin[e];
+            __syncthreads();
+            // X = T^T Z: X_i = tau_i (Z_i - sum_{k<i} S_ki X_k), S = striu(Y^T Y) = Zs[:, 0:16]
+            if (tid < ncols) {
+                for (int i = 0; i < QIB; ++i) {
+                    double s = Zs[i * QNB + QIB + tid];
+                    for (int k = 0; k < i; ++k) s -= Zs[k * QNB + i] * Xs[k][tid];
+                    Xs[i][tid] = tau_sh[i] * s;
+                }
+            }
+            __syncthreads();
+            // C -= Y X on my rows
+            for (int64_t r0 = lo2 + 8 * warp; r0 < hi; r0 += 8 * (QT / 32)) {
+                const int64_t rr = r0 + lg;
+                const bool ok = rr < hi;
+                double af[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) af[q] = ok ? yval(W, ldw, rr, c0, 4 * q + lk) : 0.;
+#pragma unroll
+                for (int u = 0; u < (QNB - QIB) / 8; ++u) {
+                    if (u * 8 < ncols) {
+                        double2* cp = reinterpret_cast<double2*>(W + rr * ldw + c1 + u * 8 + 2 * lk);
+                        double2 acc = ok ? *cp : make_double2(0., 0.);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) dmma884(acc.x, acc.y, af[q], -Xs[4 * q + lk][u * 8 + lg]);
+                        if (ok) *cp = acc;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// explicit reflector block of an outer panel: Y (rows x 64, ld 64), zero above the panel and beyond nbo columns
+__global__ void qr_write_y_kernel(const double* __restrict__ W, int64_t ldw, int64_t rows, int J, int nbo,
+                                  double* __restrict__ Y) {
+    const int64_t total = rows * (QNB / 2);
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx / (QNB / 2); const int a0 = (int)(idx % (QNB / 2)) * 2;
+        double2 v = make_double2(0., 0.);
+        if (r >= J) {
+            if (a0 < nbo) v.x = yval(W, ldw, r, J, a0);
+            if (a0 + 1 < nbo) v.y = yval(W, ldw, r, J, a0 + 1);
+        }
+        *reinterpret_cast<double2*>(Y + r * QNB + a0) = v;
+    }
+}
+
+// X = T^T Z in place: X_i = tau_i (Z_i - sum_{k<i} S_ki X_k); one thread per trailing column
+__global__ void qr_xsolve_kernel(double* __restrict__ Z, int64_t ldz, int64_t ncols, const double* __restrict__ S, int nbo,
+                                 const double* __restrict__ tau) {
+    __shared__ double Ss[QNB * QNB];
+    __shared__ double ts[QNB];
+    for (int e = threadIdx.x; e < nbo * nbo; e += blockDim.x) Ss[e] = S[e];
+    if (threadIdx.x < nbo) ts[threadIdx.x] = tau[threadIdx.x];
+    __syncthreads();
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncols) return;
+    for (int i = 0; i < nbo; ++i) {
+        double s0 = Z[(int64_t)i * ldz + j], s1 = 0.;
+        int k = 0;
+        for (; k + 1 < i; k += 2) {
+            s0 -= Ss[k * nbo + i] * Z[(int64_t)k * ldz + j];
+            s1 -= Ss[(k + 1) * nbo + i] * Z[(int64_t)(k + 1) * ldz + j];
+        }
+        if (k < i) s0 -= Ss[k * nbo + i] * Z[(int64_t)k * ldz + j];
+        Z[(int64_t)i * ldz + j] = ts[i] * (s0 + s1);
+    }
+}
+
+// W (rowsW x ldw) = A (rows x m) zero padded
+__global__ void qr_copy_pad_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int64_t m,
+                                   double* __restrict__ W, int64_t ldw, int64_t rowsW) {
+    const int64_t total = rowsW * ldw;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx / ldw, c = idx % ldw;
+        W[idx] = (r < rows && c < m) ? A[r * lda + c] : 0.;
+    }
+}
+
+// R (m x m, ld ldr) = upper triangle of W, zero below; rows [m, rows_out) of the destination are zeroed as well
+__global__ void qr_extract_r_kernel(const double* __restrict__ W, int64_t ldw, int64_t m, double* __restrict__ R,
+                                    int64_t ldr, int64_t rows_out) {
+    const int64_t total = rows_out * ldr;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = idx / ldr, j = idx % ldr;
+        R[idx] = (i < m && j < m && j >= i) ? W[i * ldw + j] : 0.;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Householder QR with column pivoting of the small factor, columns never moved
+// ---------------------------------------------------------------------------
+struct QrcpArgs {
+    double* At; int64_t ldm; int m; int max_steps; double tol2;
+    double* cand_val; int* cand_idx;      // [2][G]
+    int* done_step;                       // [ldm] step at which a column was eliminated (-1: not yet)
+    double* diagval;                      // [m] beta of each step
+    int* r_out;
+};
+
+__device__ __forceinline__ void block_sum8(double (&v)[8], double (*red)[8], double* out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        double s = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) red[warp][k] = s;
+    }
+    __syncthreads();
+    if (tid < 8) {
+        double s = 0.;
+#pragma unroll
+        for (int w = 0; w < QT / 32; ++w) s += red[w][tid];
+        out[tid] = s;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void block_argmax(double& v, int& i, double* rv, int* ri) {
+    const int tid = threadIdx.x;
+    rv[tid] = v; ri[tid] = i; __syncthreads();
+    for (int s = QT / 2; s > 0; s >>= 1) {
+        if (tid < s) {
+            const double ov = rv[tid + s]; const int oi = ri[tid + s];
+            if (ov > rv[tid] || (ov == rv[tid] && oi < ri[tid])) { rv[tid] = ov; ri[tid] = oi; }
+        }
+        __syncthreads();
+    }
+    v = rv[0]; i = ri[0];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(QT) qrcp_kernel(QrcpArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) double qsm[];
+    const int m = a.m; const int64_t ldm = a.ldm;
+    const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
+    const int ngroups = (int)(ldm / 8);
+    const int mg = b < ngroups ? (ngroups - b + G - 1) / G : 0;      // my column groups: b, b + G, ...
+    double* xs = qsm;                                   // [m] the pivot column below the diagonal row
+    double* cn2 = qsm + (m + 7) / 8 * 8;                // [mg * 8] squared norms of my columns below the current row
+    __shared__ int active[64 * 8];                      // my columns still to be eliminated (mg <= 64)
+    __shared__ double red[QT / 32][8];
+    __shared__ double out8[8], wsh[8];
+    __shared__ double rv[QT]; __shared__ int ri[QT];
+    double* __restrict__ At = a.At;
+
+    // ---- prologue: norms of my columns over all rows
+    for (int j = 0; j < mg; ++j) {
+        const int k0 = (b + j * G) * 8;
+        double acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = 0.;
+        for (int r = tid; r < m; r += QT) {
+            const double2* p = reinterpret_cast<const double2*>(At + (int64_t)r * ldm + k0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { double2 v = p[q]; acc[2 * q] += v.x * v.x; acc[2 * q + 1] += v.y * v.y; }
+        }
+        block_sum8(acc, red, out8);
+        if (tid < 8) {
+            const bool real = k0 + tid < m;
+            cn2[j * 8 + tid] = real ? out8[tid] : -1.;
+            active[j * 8 + tid] = real ? 1 : 0;
+            a.done_step[k0 + tid] = -1;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+
+    double first = 0.;
+    int par = 0, c = 0;
+    for (; c < a.max_steps; ++c) {
+        // ---- pivot: largest remaining column norm (ties -> lowest column index)
+        double bv = -1.; int bi = 0x7fffffff;
+        for (int e = tid; e < mg * 8; e += QT) {
+            if (active[e]) {
+                const double v = cn2[e]; const int k = (b + (e / 8) * G) * 8 + (e % 8);
+                if (v > bv || (v == bv && k < bi)) { bv = v; bi = k; }
+            }
+        }
+        block_argmax(bv, bi, rv, ri);
+        if (tid == 0) { a.cand_val[par * G + b] = bv; a.cand_idx[par * G + b] = bi; }
+        grid.sync();
+        bv = -1.; bi = 0x7fffffff;
+        for (int e = tid; e < G; e += QT) {
+            const double v = a.cand_val[par * G + e]; const int k = a.cand_idx[par * G + e];
+            if (v > bv || (v == bv && k < bi)) { bv = v; bi = k; }
+        }
+        block_argmax(bv, bi, rv, ri);
+        par ^= 1;
+        const int p = bi; const double pv = bv;
+        if (c == 0) first = pv;
+        if (!(pv > a.tol2 * first) || !(pv > 0.)) break;            // uniform over the grid
+
+        // ---- reflector from column p, rows c..m-1
+        const int len = m - c;
+        for (int r = tid; r < len; r += QT) xs[r] = At[(int64_t)(c + r) * ldm + p];
+        __syncthreads();
+        double part = 0.;
+        for (int r = 1 + tid; r < len; r += QT) part += xs[r] * xs[r];
+        rv[tid] = part; __syncthreads();
+        for (int s = QT / 2; s > 0; s >>= 1) { if (tid < s) rv[tid] += rv[tid + s]; __syncthreads(); }
+        const double xn2 = rv[0], alpha = xs[0];
+        __syncthreads();
+        double beta = alpha, tau = 0., scale = 0.;
+        if (xn2 > 0.) {
+            beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+            tau = (beta - alpha) / beta;
+            scale = 1. / (alpha - beta);
+        }
+        const bool mine = (p / 8) % G == b;
+        if (mine && tid == 0) {
+            a.diagval[c] = beta; a.done_step[p] = c;
+            const int e = ((p / 8 - b) / G) * 8 + (p % 8);
+            active[e] = 0; cn2[e] = -1.;
+        }
+        __syncthreads();
+
+        // ---- update my remaining columns, recompute their norms below row c
+        for (int j = 0; j < mg; ++j) {
+            const int k0 = (b + j * G) * 8;
+            int any = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) any |= active[j * 8 + q];
+            if (!any) continue;                                        // uniform (shared memory)
+            double acc[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = 0.;
+            for (int r = c + 1 + tid; r < m; r += QT) {
+                const double xr = xs[r - c];
+                const double2* pp = reinterpret_cast<const double2*>(At + (int64_t)r * ldm + k0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { double2 v = pp[q]; acc[2 * q] += xr * v.x; acc[2 * q + 1] += xr * v.y; }
+            }
+            block_sum8(acc, red, out8);
+            if (tid < 8) {
+                const double rc = At[(int64_t)c * ldm + k0 + tid];
+                const double wv = rc + out8[tid] * scale;
+                wsh[tid] = wv;
+                if (active[j * 8 + tid]) At[(int64_t)c * ldm + k0 + tid] = rc - tau * wv;
+            }
+            __syncthreads();
+            double w[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) w[q] = wsh[q];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = 0.;
+            for (int r = c + 1 + tid; r < m; r += QT) {
+                const double tv = tau * (xs[r - c] * scale);
+                double* pr = At + (int64_t)r * ldm + k0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (active[j * 8 + q]) {
+                        const double v = pr[q] - tv * w[q];
+                        pr[q] = v; acc[q] += v * v;
+                    }
+                }
+            }
+            block_sum8(acc, red, out8);
+            if (tid < 8 && active[j * 8 + tid]) cn2[j * 8 + tid] = out8[tid];
+            __syncthreads();
+        }
+    }
+    if (b == 0 && tid == 0) *a.r_out = c;
+}
+
+// put the betas on the diagonal positions, zero what lies below them and every row >= r
+__global__ void qrcp_cleanup_kernel(double* __restrict__ At, int64_t ldm, int64_t rows_total, int m,
+                                    const int* __restrict__ done_step, const double* __restrict__ diagval,
+                                    const int* __restrict__ r_ptr) {
+    const int r_fin = *r_ptr;
+    const int64_t total = rows_total * ldm;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx / ldm; const int k = (int)(idx % ldm);
+        if (r >= r_fin || k >= m) { At[idx] = 0.; continue; }
+        const int s = done_step[k];
+        if (s >= 0 && s < r_fin) {
+            if (r == s) At[idx] = diagval[s];
+            else if (r > s) At[idx] = 0.;
+        }
+    }
+}
+
+int coop_grid(pb_ctx* ctx, const void* kernel, size_t smem, int want, int* grid_out) {
+    int occ = 0;
+    PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, QT, smem));
+    if (occ < 1) PB_FAIL(ctx, PB_ERR_CUDA, "tsqr: cooperative kernel does not fit an SM (%zu bytes of shared memory)", smem);
+    *grid_out = std::max(1, std::min(want, ctx->sm_count));
+    return PB_OK;
+}
+
+}  // namespace
+
+int pbi_gemm_nn_sub(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m, const double* B, int64_t ldb,
+                    int64_t k, double* Y, int64_t ldy);
+
+// R (m x m upper triangular, ld ldr, rows_out >= m rows written: zero below the triangle) of A (rows x m, lda).
+int pbi_qr_r(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, double* R, int64_t ldr, int64_t rows_out) {
+    if (rows <= 0 || m <= 0 || lda < m || ldr < m || rows_out < m) PB_FAIL(ctx, PB_ERR_SHAPE, "tsqr: bad shape");
+    if (m > 8192) PB_FAIL(ctx, PB_ERR_SHAPE, "tsqr: %lld columns exceed 8192", (long long)m);
+    const int64_t mp = (m + QIB - 1) / QIB * QIB;            // padded column count (zero columns reflect to nothing)
+    const int64_t ldw = mp;
+    const int64_t rowsW = std::max(rows, mp);
+    PB_TRY(pb_reserve(ctx, &ctx->qr_W, &ctx->qr_W_cap, (size_t)rowsW * ldw));
+    PB_TRY(pb_reserve(ctx, &ctx->qr_Y, &ctx->qr_Y_cap, (size_t)rowsW * QNB));
+    const int Gmax = ctx->sm_count;
+    // scratch: tau [mp] | part [2*G*16] | diag [32] | zpart [G*ZE] | zfin [ZE] | Z [64*mp] | S [64*64]
+    const size_t n_scr = (size_t)mp + 2 * (size_t)Gmax * QIB + 2 * QIB + (size_t)Gmax * ZE + ZE + (size_t)QNB * mp + QNB * QNB;
+    PB_TRY(pb_reserve(ctx, &ctx->qr_scr, &ctx->qr_scr_cap, n_scr));
+    double* tau = ctx->qr_scr; double* part = tau + mp; double* diag = part + 2 * (size_t)Gmax * QIB;
+    double* zpart = diag + 2 * QIB; double* zfin = zpart + (size_t)Gmax * ZE; double* Zb = zfin + ZE;
+    double* Sb = Zb + (size_t)QNB * mp;
+    double* W = ctx->qr_W; double* Y = ctx->qr_Y;
+    const int cp_grid = ctx->sm_count * 8;
+    qr_copy_pad_kernel<<<cp_grid, 256, 0, ctx->stream>>>(A, lda, rows, m, W, ldw, rowsW);
+    PB_LAUNCH_CHECK(ctx);
+    const size_t smem = sizeof(double) * (size_t)(QT / 32) * ZE;
+    PB_CUDA(ctx, cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int64_t J = 0; J < mp; J += QNB) {
+        const int nbo = (int)std::min<int64_t>(QNB, mp - J);
+        int grid = 1;
+        PB_TRY(coop_grid(ctx, (const void*)qr_panel_kernel, smem, (int)((rowsW - J + 127) / 128), &grid));
+        QrPanelArgs pa{W, ldw, rowsW, (int)J, nbo, tau + J, part, diag, zpart, zfin};
+        void* args[] = {&pa};
+        PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)qr_panel_kernel, dim3(grid), dim3(QT), args, smem, ctx->stream));
+        ctx->launches++;
+        const int64_t ntrail = mp - J - nbo;
+        if (ntrail <= 0) break;
+        qr_write_y_kernel<<<cp_grid, 256, 0, ctx->stream>>>(W, ldw, rowsW, (int)J, nbo, Y);
+        PB_LAUNCH_CHECK(ctx);
+        PB_TRY(pbi_gemm_tn(ctx, Y, QNB, nbo, Y, QNB, nbo, rowsW, Sb, nbo, 0));                   // S = Y^T Y
+        PB_TRY(pbi_gemm_tn(ctx, Y, QNB, nbo, W + J + nbo, ldw, ntrail, rowsW, Zb, ntrail, 0));   // Z = Y^T C
+        qr_xsolve_kernel<<<(unsigned)((ntrail + 127) / 128), 128, 0, ctx->stream>>>(Zb, ntrail, ntrail, Sb, nbo, tau + J);
+        PB_LAUNCH_CHECK(ctx);
+        PB_TRY(pbi_gemm_nn_sub(ctx, Y, QNB, rowsW, nbo, Zb, ntrail, ntrail, W + J + nbo, ldw));  // C -= Y X
+    }
+    qr_extract_r_kernel<<<cp_grid, 256, 0, ctx->stream>>>(W, ldw, m, R, ldr, rows_out);
+    PB_LAUNCH_CHECK(ctx);
+    return PB_OK;
+}
+
+// At (rows_total x ldm, zero padded) = upper triangle of R (m x m, ld ldr)
+int pbi_qr_load_factor(pb_ctx* ctx, const double* R, int64_t ldr, int64_t m, double* At, int64_t ldm, int64_t rows_total) {
+    qr_extract_r_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(R, ldr, m, At, ldm, rows_total);
+    PB_LAUNCH_CHECK(ctx);
+    return PB_OK;
+}
+
+// Rank-revealing QR with column pivoting of the factor held in At (m rows x ldm, rows = vectors after the call).
+// tol_rel: stop when the largest remaining column norm <= tol_rel * the first pivot norm (0: all m steps).
+// The number of vectors r is left in ctx->d_int[0] / returned.
+int pbi_qrcp_factor(pb_ctx* ctx, double* At, int64_t m, int64_t ldm, int64_t rows_total, double tol_rel, int* r_out) {
+    const int Gmax = ctx->sm_count;
+    const int ngroups = (int)(ldm / 8);
+    int grid = std::min(Gmax, ngroups);
+    const int mg_max = (ngroups + grid - 1) / grid;
+    if (mg_max > 64) PB_FAIL(ctx, PB_ERR_SHAPE, "tsqr: %lld columns exceed the pivoted QR's limit", (long long)m);
+    const size_t smem = sizeof(double) * ((size_t)(m + 7) / 8 * 8 + (size_t)mg_max * 8);
+    PB_CUDA(ctx, cudaFuncSetAttribute(qrcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PB_TRY(coop_grid(ctx, (const void*)qrcp_kernel, smem, grid, &grid));
+    // scratch: cand_val [2*G] | diagval [m] | then ints: cand_idx [2*G] | done_step [ldm]
+    const size_t n_dbl = 2 * (size_t)Gmax + (size_t)m + 8;
+    const size_t n_int = 2 * (size_t)Gmax + (size_t)ldm + 8;
+    PB_TRY(pb_reserve(ctx, &ctx->qr_scr2, &ctx->qr_scr2_cap, n_dbl + (n_int + 1) / 2));
+    double* cand_val = ctx->qr_scr2; double* diagval = cand_val + 2 * (size_t)Gmax;
+    int* cand_idx = reinterpret_cast<int*>(diagval + m + 8); int* done_step = cand_idx + 2 * (size_t)Gmax;
+    QrcpArgs qa{At, ldm, (int)m, (int)m, tol_rel * tol_rel, cand_val, cand_idx, done_step, diagval, ctx->d_int + 0};
+    void* args[] = {&qa};
+    PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)qrcp_kernel, dim3(grid), dim3(QT), args, smem, ctx->stream));
+    ctx->launches++;
+    qrcp_cleanup_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(At, ldm, rows_total, (int)m, done_step, diagval, ctx->d_int + 0);
+    PB_LAUNCH_CHECK(ctx);
+    PB_CUDA(ctx, cudaMemcpyAsync(ctx->h_int, ctx->d_int, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *r_out = ctx->h_int[0];
+    return PB_OK;
+}

@@ -3,7 +3,8 @@
 U is sharded by dof: rank p owns the contiguous row slab row_range(n_h, p, P) of the
 row-major snapshot matrix.  Exchange steps (the only ones on the path):
   * sum-all-reduce of the local n_st x n_st Gram partial (and of the second-pass Gram),
-  * sum-all-reduce of the local projection partial V_p^T U_p.
+  * sum-all-reduce of the local projection partial V_p^T U_p,
+  * TSQR mode: all-gather of the P local R factors (n_st x n_st each), then the QR of the stack is replicated.
 The small eigensolve is replicated: every rank runs it on the bit-identical reduced Gram
 and gets the same rank and factors.  Snapshot generation, basis, reconstruction and
 pod_sig need no communication.
@@ -34,11 +35,36 @@ def _all_reduce(t, group=None):
     return t
 
 
+def _all_gather_stack(backend, R, group=None):
+    """(P m x m) stack of every rank's m x m factor, in rank order (identical on all ranks)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return R
+    return backend.all_gather_rows(R, group)
+
+
+def pod_sharded_tsqr(backend, A_local, eps=0., n_L=0, group=None):
+    """TSQR mode: one leaf per rank.  R_p = qr(A_p).R locally (blocked Householder, Q not formed), all-gather, the QR
+    of the (P n_st x n_st) stack and the Jacobi SVD of its factor are replicated (same bits on every rank, hence the
+    same rank and factors), V_p = A_p Z / sigma locally (pod.py:42-45).  Returns (V_local, sigma, n_L)."""
+    R = backend.tsqr_r(A_local)
+    stack = _all_gather_stack(backend, R, group)
+    if stack is not R:
+        R = backend.tsqr_r(stack)
+    n_L_out = backend.pod_from_r(R, eps, n_L)
+    V = backend.basis(A_local, None, n_L_out)
+    return V, backend.sigma(), n_L_out
+
+
 def pod_sharded(backend, A_local, eps=0., n_L=0, mode="gram", group=None, A_host=None):
     """POD of the row-sharded tall matrix.  Returns (V_local, sigma, n_L).
 
     `A_host` (address of this rank's slab in pinned host memory, same shape as `A_local`): the slab is uploaded into
     `A_local` in row chunks overlapped with the chunk Grams (pb_gram_host) instead of being read from HBM."""
+    if mode == "tsqr":
+        if A_host is not None:
+            backend.upload(A_host, A_local)
+        return pod_sharded_tsqr(backend, A_local, eps, n_L, group)
     G = backend.gram(A_local) if A_host is None else backend.gram_host(A_host, A_local)
     backend.reduce(G, group)
     n_L_out, keep = backend.pod_from_gram(G, eps, n_L, mode)
@@ -103,6 +129,31 @@ class CudaBackend:
         G = self._empty(m, m)
         self.ctx.check(self.L.pb_gram_host(self.ctx.h, host_ptr, A.shape[0], m, m, A.ptr, G.data_ptr()))
         return G
+
+    def upload(self, host_ptr, A):
+        self.ctx.check(self.L.pb_upload(self.ctx.h, A.ptr, host_ptr, A.nbytes))
+
+    def tsqr_r(self, A):
+        """R factor (torch tensor m x m) of a DeviceArray slab or of a torch (rows x m) stack."""
+        is_t = isinstance(A, self.torch.Tensor)
+        rows, m = A.shape
+        R = self._empty(m, m)
+        ptr, ld = (A.data_ptr(), A.stride(0)) if is_t else (A.ptr, A.ld)
+        self.ctx.check(self.L.pb_tsqr_r(self.ctx.h, ptr, rows, m, ld, R.data_ptr()))
+        return R
+
+    def all_gather_rows(self, R, group=None):
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        with self.torch.cuda.stream(self.stream):
+            stack = self.torch.empty(world * R.shape[0], R.shape[1], dtype=R.dtype, device=R.device)
+            dist.all_gather_into_tensor(stack, R.contiguous(), group=group)
+        return stack
+
+    def pod_from_r(self, R, eps, n_L):
+        nl = C.c_int()
+        self.ctx.check(self.L.pb_pod_from_r(self.ctx.h, R.data_ptr(), R.shape[0], float(eps), int(n_L), C.byref(nl)))
+        return nl.value
 
     def pod_from_gram(self, G, eps, n_L, mode):
         nl, keep = C.c_int(), C.c_int()

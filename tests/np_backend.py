@@ -21,6 +21,23 @@ class NumpyBackend:
     def gram(self, A):
         return torch.from_numpy(A.T @ A)
 
+    def tsqr_r(self, A):
+        A = A.numpy() if isinstance(A, torch.Tensor) else A
+        return torch.from_numpy(np.linalg.qr(A, mode="r"))
+
+    def all_gather_rows(self, R, group=None):
+        import torch.distributed as dist
+        parts = [torch.empty_like(R) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(parts, R.contiguous(), group=group)
+        return torch.cat(parts, 0)
+
+    def pod_from_r(self, R, eps, n_L):
+        _, s, Zt = np.linalg.svd(R.numpy())
+        self._sig, self._W = s, Zt.T
+        if n_L == 0:
+            n_L = po.truncation_rank(s ** 2, eps, len(s))
+        return n_L
+
     def pod_from_gram(self, G, eps, n_L, mode):
         lam, W = np.linalg.eigh(G.numpy())
         lam, W = np.maximum(lam[::-1], 0.), W[:, ::-1]

@@ -43,7 +43,7 @@ def _worker(rank, world, port, mode, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["gram", "gram2"])
+@pytest.mark.parametrize("mode", ["gram", "gram2", "tsqr"])
 def test_sharded_equals_unsharded(tmp_path, mode):
     out = str(tmp_path / "res.npz")
     mp.spawn(_worker, args=(2, _free_port(), mode, out), nprocs=2, join=True)
