@@ -279,7 +279,9 @@ __global__ void __launch_bounds__(NTHREADS, (KP <= 32) ? 2 : 1)
 recon_strip_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int K,
                    const double* __restrict__ B, int64_t ldb, int64_t n,
                    double* __restrict__ Y, int64_t ldy,
-                   const double* __restrict__ U, int64_t ldu, double* __restrict__ sig_out) {
+                   const double* U, int64_t ldu, double* __restrict__ sig_out, int subtract) {
+    // subtract != 0: Y = U - A B with U == Y allowed (the in-place trailing update C -= Y X of the blocked
+    // Householder QR, qr.cu): the U tile of a column tile is read from its staged copy before the tile is written
     constexpr int MS = 32, NT = 64;
     constexpr int STG = (KP <= 16) ? 3 : 2;    // tiles in flight: 2 CTAs x 2 tiles x 16 KB keep HBM busy (n_L <= 16)
     constexpr int PA = KP + 4, PB = NT + 4, PU = NT + 4;
@@ -293,14 +295,15 @@ recon_strip_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int 
     const int lk = lane & 3, lg = lane >> 2;
     const int64_t h0 = (int64_t)blockIdx.x * MS;
     const int n_tiles = (int)((n + NT - 1) / NT);
-    const bool want_sig = (U != nullptr);
+    const bool want_u = (U != nullptr);
+    const bool want_sig = want_u && !subtract;
     const bool y_vec = Y && (ldy % 2 == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0);
 
     load_tile<MS, KP, PA, ALIGN_A>(As, A, lda, h0, rows, 0, K, tid);
     auto prefetch = [&](int t) {
         const int64_t j0 = (int64_t)t * NT;
         load_tile<KP, NT, PB, ALIGN_B>(Bs + (t % STG) * KP * PB, B, ldb, 0, K, j0, n, tid);
-        if (want_sig) load_tile<MS, NT, PU, ALIGN_U>(Us + (t % STG) * MS * PU, U, ldu, h0, rows, j0, n, tid);
+        if (want_u) load_tile<MS, NT, PU, ALIGN_U>(Us + (t % STG) * MS * PU, U, ldu, h0, rows, j0, n, tid);
     };
 #pragma unroll
     for (int t = 0; t < STG - 1; ++t) {
@@ -345,6 +348,10 @@ recon_strip_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int 
             for (int u = 0; u < 2; ++u) {
                 const int cl = wn * 16 + u * 8 + 2 * lk;
                 const int64_t j = j0 + cl;
+                if (subtract) {
+                    const double2 uv = *reinterpret_cast<const double2*>(us + rl * PU + cl);
+                    acc[a][u][0] = uv.x - acc[a][u][0]; acc[a][u][1] = uv.y - acc[a][u][1];
+                }
                 if (Y) {
                     if (y_vec && j + 1 < n) *reinterpret_cast<double2*>(Y + h * ldy + j) = make_double2(acc[a][u][0], acc[a][u][1]);
                     else { if (j < n) Y[h * ldy + j] = acc[a][u][0]; if (j + 1 < n) Y[h * ldy + j + 1] = acc[a][u][1]; }
@@ -515,14 +522,15 @@ int launch_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m
 
 template <int KP>
 int launch_recon_strip(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m, const double* B,
-                       int64_t ldb, int64_t k, double* Y, int64_t ldy, const double* Uref, int64_t ldu, double* sig_out) {
+                       int64_t ldb, int64_t k, double* Y, int64_t ldy, const double* Uref, int64_t ldu, double* sig_out,
+                       int subtract = 0) {
     constexpr int STG = (KP <= 16) ? 3 : 2;
     constexpr size_t smem = (size_t)(32 * (KP + 4) + STG * KP * 68 + STG * 32 * 68) * sizeof(double);
     const bool aa = aligned16(A, lda), ab = aligned16(B, ldb), au = !Uref || aligned16(Uref, ldu);
     dim3 grid((unsigned)((rows + 31) / 32));
 #define PB_RS_CASE(AA, AB, AU) { auto kern = recon_strip_kernel<KP, AA, AB, AU>; \
         PB_TRY(set_smem(ctx, kern, smem)); \
-        kern<<<grid, NTHREADS, smem, ctx->stream>>>(A, lda, rows, (int)m, B, ldb, k, Y, ldy, Uref, ldu, sig_out); }
+        kern<<<grid, NTHREADS, smem, ctx->stream>>>(A, lda, rows, (int)m, B, ldb, k, Y, ldy, Uref, ldu, sig_out, subtract); }
     if (aa && ab && au) PB_RS_CASE(true, true, true)
     else if (ab && au) PB_RS_CASE(false, true, true)
     else if (ab) PB_RS_CASE(false, true, false)
@@ -598,6 +606,13 @@ int pbi_gemm_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t
 int pbi_gemm_nn_sub(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m, const double* B, int64_t ldb,
                     int64_t k, double* Y, int64_t ldy) {
     if (rows <= 0 || m <= 0 || k <= 0) PB_FAIL(ctx, PB_ERR_SHAPE, "gemm_nn_sub: bad shape");
+    // K <= 64 and a wide C: the strip kernel streams C through shared memory once (in place)
+    static const int strip_env = getenv("PB_QR_STRIP") ? atoi(getenv("PB_QR_STRIP")) : 1;
+    if (strip_env && m <= 64 && k >= 64) {
+        if (m <= 16) return launch_recon_strip<16>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Y, ldy, nullptr, 1);
+        if (m <= 32) return launch_recon_strip<32>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Y, ldy, nullptr, 1);
+        return launch_recon_strip<64>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Y, ldy, nullptr, 1);
+    }
     if (k > 96) return launch_nn<128, 2, 4>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, nullptr, 0, nullptr, Batch(), 1);
     if (k > 64) return launch_nn<96, 2, 4>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, nullptr, 0, nullptr, Batch(), 1);
     if (k > 32) return launch_nn<64, 4, 2>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, nullptr, 0, nullptr, Batch(), 1);

@@ -26,6 +26,7 @@
 #include "tile_ops.cuh"
 #include <cooperative_groups.h>
 #include <cfloat>
+#include <cstdlib>
 #include <algorithm>
 namespace cg = cooperative_groups;
 
@@ -72,11 +73,15 @@ struct QrPanelArgs {
     double* diag;                            // [2][16] the published diagonal row
     double* zpart;                           // [G][ZE] per-CTA partial Z of the inner apply
     double* zfin;                            // [ZE]
+    int use_smem;                            // the CTA's rows of an inner panel fit shared memory: the 16 column steps
+                                             // run on the staged copy (pitch QP), written back once
 };
+constexpr int QP = QIB + 2;                  // shared-memory row pitch: 16-byte aligned, conflict-free double2 access
 
 __global__ void __launch_bounds__(QT) qr_panel_kernel(QrPanelArgs a) {
     cg::grid_group grid = cg::this_grid();
-    extern __shared__ __align__(16) double zred[];          // [8 warps][ZE]
+    extern __shared__ __align__(16) double zred[];          // [8 warps][ZE]; before that the staged inner panel
+    double* Ps = zred;
     __shared__ double red[QT / 32][QIB];
     __shared__ double red2[QIB][QIB];
     __shared__ double gsh[QIB], dsh[QIB], tau_sh[QIB], outsh[QIB];
@@ -105,6 +110,11 @@ __global__ void __launch_bounds__(QT) qr_panel_kernel(QrPanelArgs a) {
                 const double2* src = reinterpret_cast<const double2*>(W + r * ldw + c0);
 #pragma unroll
                 for (int k = 0; k < QIB / 2; ++k) { double2 v = src[k]; x[2 * k] = v.x; x[2 * k + 1] = v.y; }
+                if (a.use_smem) {
+                    double2* dst = reinterpret_cast<double2*>(Ps + (size_t)(r - lo) * QP);
+#pragma unroll
+                    for (int k = 0; k < QIB / 2; ++k) dst[k] = make_double2(x[2 * k], x[2 * k + 1]);
+                }
                 if (r == c0) {
 #pragma unroll
                     for (int k = 0; k < QIB; ++k) a.diag[par * QIB + k] = x[k];
@@ -124,14 +134,14 @@ __global__ void __launch_bounds__(QT) qr_panel_kernel(QrPanelArgs a) {
             {
                 const int k = tid & 15, grp = tid >> 4;
                 double s = 0.;
-                for (int bb = grp; bb < G; bb += QT / 16) s += a.part[((size_t)par * G + bb) * QIB + k];
+                for (int bb = grp; bb < G; bb += QT / 16) s += __ldcg(a.part + ((size_t)par * G + bb) * QIB + k);
                 red2[grp][k] = s;
                 __syncthreads();
                 if (tid < QIB) {
                     double t = 0.;
 #pragma unroll
                     for (int q = 0; q < QT / 16; ++q) t += red2[q][tid];
-                    gsh[tid] = t; dsh[tid] = a.diag[par * QIB + tid];
+                    gsh[tid] = t; dsh[tid] = __ldcg(a.diag + par * QIB + tid);
                 }
                 __syncthreads();
             }
@@ -154,7 +164,8 @@ __global__ void __launch_bounds__(QT) qr_panel_kernel(QrPanelArgs a) {
             const int64_t rb = lo > d ? lo : d;
             for (int64_t r = rb + tid; r < hi; r += QT) {
                 double x[QIB];
-                double2* p = reinterpret_cast<double2*>(W + r * ldw + c0);
+                double2* p = a.use_smem ? reinterpret_cast<double2*>(Ps + (size_t)(r - lo) * QP)
+                                        : reinterpret_cast<double2*>(W + r * ldw + c0);
 #pragma unroll
                 for (int k = 0; k < QIB / 2; ++k) { double2 v = p[k]; x[2 * k] = v.x; x[2 * k + 1] = v.y; }
                 if (r == d) {
@@ -188,11 +199,21 @@ __global__ void __launch_bounds__(QT) qr_panel_kernel(QrPanelArgs a) {
                 block_sum16(g, red, outsh);
                 if (tid < QIB) a.part[((size_t)(par ^ 1) * G + b) * QIB + tid] = outsh[tid];
                 par ^= 1;
-                grid.sync();
+                grid.sync();        // (a flag-per-CTA exchange instead of this barrier measured slower: 1.14 vs 0.83 ms per panel)
             }
         }
         par ^= 1;
         __syncthreads();
+        if (a.use_smem) {                                           // staged inner panel back to the working copy
+            const int64_t rb = lo > c0 ? lo : (int64_t)c0;
+            for (int64_t r = rb + tid; r < hi; r += QT) {
+                const double2* src = reinterpret_cast<const double2*>(Ps + (size_t)(r - lo) * QP);
+                double2* dst = reinterpret_cast<double2*>(W + r * ldw + c0);
+#pragma unroll
+                for (int k = 0; k < QIB / 2; ++k) dst[k] = src[k];
+            }
+            __syncthreads();
+        }
 
         // ---- apply the inner block reflector to the rest of the outer panel
         const int ncols = a.nbo - i0 - QIB;
@@ -300,25 +321,48 @@ __global__ void qr_write_y_kernel(const double* __restrict__ W, int64_t ldw, int
     }
 }
 
-// X = T^T Z in place: X_i = tau_i (Z_i - sum_{k<i} S_ki X_k); one thread per trailing column
-__global__ void qr_xsolve_kernel(double* __restrict__ Z, int64_t ldz, int64_t ncols, const double* __restrict__ S, int nbo,
-                                 const double* __restrict__ tau) {
-    __shared__ double Ss[QNB * QNB];
-    __shared__ double ts[QNB];
-    for (int e = threadIdx.x; e < nbo * nbo; e += blockDim.x) Ss[e] = S[e];
-    if (threadIdx.x < nbo) ts[threadIdx.x] = tau[threadIdx.x];
+// T^T (nbo x nbo lower triangular, ld 64) from tau and S = Y^T Y: the recurrence X_i = tau_i (Z_i - sum_{k<i} S_ki X_k)
+// applied to Z = I (T^-1 = diag(1/tau) + striu(S); tau_i = 0 gives a zero row, i.e. H_i = I).  One CTA, thread = column.
+__global__ void __launch_bounds__(4 * QNB) qr_tt_kernel(const double* __restrict__ S, int nbo, const double* __restrict__ tau,
+                                                        double* __restrict__ Tt) {
+    __shared__ double Xs[QNB][QNB + 1];
+    const int tid = threadIdx.x, j = tid >> 2, q = tid & 3;      // 4 threads share the k-sum of a column
+    for (int e = tid; e < QNB * QNB; e += 4 * QNB) Xs[e / QNB][e % QNB] = 0.;
     __syncthreads();
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= ncols) return;
     for (int i = 0; i < nbo; ++i) {
-        double s0 = Z[(int64_t)i * ldz + j], s1 = 0.;
+        double s = 0.;
+        for (int k = j + q; k < i; k += 4) s -= S[k * nbo + i] * Xs[k][j];       // X_kj = 0 for k < j
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (q == 0 && j < nbo && i >= j) Xs[i][j] = tau[i] * ((i == j ? 1. : 0.) + s);
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int e = tid; e < QNB * QNB; e += 4 * QNB) {
+        const int i = e / QNB, c = e % QNB;
+        Tt[e] = (i < nbo && c < nbo) ? Xs[i][c] : 0.;
+    }
+}
+
+// X = T^T Z in place for a tile of 64 trailing columns per CTA
+__global__ void __launch_bounds__(QT) qr_applyt_kernel(double* __restrict__ Z, int64_t ldz, int64_t ncols,
+                                                       const double* __restrict__ Tt, int nbo) {
+    __shared__ double Zs[QNB][QNB + 1];
+    const int tid = threadIdx.x;
+    const int64_t j0 = (int64_t)blockIdx.x * QNB;
+    for (int e = tid; e < QNB * QNB; e += QT) {
+        const int k = e / QNB, jj = e % QNB;
+        Zs[k][jj] = (k < nbo && j0 + jj < ncols) ? Z[(int64_t)k * ldz + j0 + jj] : 0.;
+    }
+    __syncthreads();
+    const int jj = tid % QNB, part = tid / QNB;
+    if (j0 + jj >= ncols) return;
+    for (int i = part; i < nbo; i += QT / QNB) {
+        double s0 = 0., s1 = 0.;
         int k = 0;
-        for (; k + 1 < i; k += 2) {
-            s0 -= Ss[k * nbo + i] * Z[(int64_t)k * ldz + j];
-            s1 -= Ss[(k + 1) * nbo + i] * Z[(int64_t)(k + 1) * ldz + j];
-        }
-        if (k < i) s0 -= Ss[k * nbo + i] * Z[(int64_t)k * ldz + j];
-        Z[(int64_t)i * ldz + j] = ts[i] * (s0 + s1);
+        for (; k + 1 <= i; k += 2) { s0 += Tt[i * QNB + k] * Zs[k][jj]; s1 += Tt[i * QNB + k + 1] * Zs[k + 1][jj]; }
+        if (k <= i) s0 += Tt[i * QNB + k] * Zs[k][jj];
+        Z[(int64_t)i * ldz + j0 + jj] = s0 + s1;
     }
 }
 
@@ -560,23 +604,28 @@ int pbi_qr_r(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda,
     PB_TRY(pb_reserve(ctx, &ctx->qr_W, &ctx->qr_W_cap, (size_t)rowsW * ldw));
     PB_TRY(pb_reserve(ctx, &ctx->qr_Y, &ctx->qr_Y_cap, (size_t)rowsW * QNB));
     const int Gmax = ctx->sm_count;
-    // scratch: tau [mp] | part [2*G*16] | diag [32] | zpart [G*ZE] | zfin [ZE] | Z [64*mp] | S [64*64]
-    const size_t n_scr = (size_t)mp + 2 * (size_t)Gmax * QIB + 2 * QIB + (size_t)Gmax * ZE + ZE + (size_t)QNB * mp + QNB * QNB;
+    // scratch: tau [mp] | part [2*G*16] | diag [32] | zpart [G*ZE] | zfin [ZE] | Z [64*mp] | S [64*64] | T^T [64*64] 
+    const size_t n_scr = (size_t)mp + 2 * (size_t)Gmax * QIB + 2 * QIB + (size_t)Gmax * ZE + ZE + (size_t)QNB * mp + 2 * QNB * QNB;
     PB_TRY(pb_reserve(ctx, &ctx->qr_scr, &ctx->qr_scr_cap, n_scr));
     double* tau = ctx->qr_scr; double* part = tau + mp; double* diag = part + 2 * (size_t)Gmax * QIB;
     double* zpart = diag + 2 * QIB; double* zfin = zpart + (size_t)Gmax * ZE; double* Zb = zfin + ZE;
-    double* Sb = Zb + (size_t)QNB * mp;
+    double* Sb = Zb + (size_t)QNB * mp; double* Tt = Sb + QNB * QNB;
     double* W = ctx->qr_W; double* Y = ctx->qr_Y;
     const int cp_grid = ctx->sm_count * 8;
     qr_copy_pad_kernel<<<cp_grid, 256, 0, ctx->stream>>>(A, lda, rows, m, W, ldw, rowsW);
     PB_LAUNCH_CHECK(ctx);
-    const size_t smem = sizeof(double) * (size_t)(QT / 32) * ZE;
-    PB_CUDA(ctx, cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem_z = sizeof(double) * (size_t)(QT / 32) * ZE;
+    constexpr int64_t RS_MAX = 1400;             // rows of an inner panel staged per CTA (1400 x 18 doubles = 197 KB)
+    static const int stage_env = getenv("PB_QR_STAGE") ? atoi(getenv("PB_QR_STAGE")) : 1;
     for (int64_t J = 0; J < mp; J += QNB) {
         const int nbo = (int)std::min<int64_t>(QNB, mp - J);
-        int grid = 1;
-        PB_TRY(coop_grid(ctx, (const void*)qr_panel_kernel, smem, (int)((rowsW - J + 127) / 128), &grid));
-        QrPanelArgs pa{W, ldw, rowsW, (int)J, nbo, tau + J, part, diag, zpart, zfin};
+        int grid = std::max(1, std::min<int>((int)((rowsW - J + 127) / 128), ctx->sm_count));
+        int64_t rpc = (rowsW - J + grid - 1) / grid; rpc = (rpc + 7) / 8 * 8;       // as the kernel computes it
+        const int use_smem = (stage_env && rpc <= RS_MAX) ? 1 : 0;
+        const size_t smem = use_smem ? std::max(smem_z, sizeof(double) * (size_t)rpc * QP) : smem_z;
+        PB_CUDA(ctx, cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PB_TRY(coop_grid(ctx, (const void*)qr_panel_kernel, smem, grid, &grid));
+        QrPanelArgs pa{W, ldw, rowsW, (int)J, nbo, tau + J, part, diag, zpart, zfin, use_smem};
         void* args[] = {&pa};
         PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)qr_panel_kernel, dim3(grid), dim3(QT), args, smem, ctx->stream));
         ctx->launches++;
@@ -586,7 +635,9 @@ int pbi_qr_r(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda,
         PB_LAUNCH_CHECK(ctx);
         PB_TRY(pbi_gemm_tn(ctx, Y, QNB, nbo, Y, QNB, nbo, rowsW, Sb, nbo, 0));                   // S = Y^T Y
         PB_TRY(pbi_gemm_tn(ctx, Y, QNB, nbo, W + J + nbo, ldw, ntrail, rowsW, Zb, ntrail, 0));   // Z = Y^T C
-        qr_xsolve_kernel<<<(unsigned)((ntrail + 127) / 128), 128, 0, ctx->stream>>>(Zb, ntrail, ntrail, Sb, nbo, tau + J);
+        qr_tt_kernel<<<1, 4 * QNB, 0, ctx->stream>>>(Sb, nbo, tau + J, Tt);
+        PB_LAUNCH_CHECK(ctx);
+        qr_applyt_kernel<<<(unsigned)((ntrail + QNB - 1) / QNB), QT, 0, ctx->stream>>>(Zb, ntrail, ntrail, Tt, nbo);   // X = T^T Z
         PB_LAUNCH_CHECK(ctx);
         PB_TRY(pbi_gemm_nn_sub(ctx, Y, QNB, rowsW, nbo, Zb, ntrail, ntrail, W + J + nbo, ldw));  // C -= Y X
     }

@@ -107,7 +107,7 @@ POD_CASES = [("shekel_c1", "shekel"), ("shekel_tall", "shekel"), ("ackley_64", "
 
 
 @pytest.mark.parametrize("name,field", POD_CASES)
-@pytest.mark.parametrize("mode", ["gram", "gram2", "accurate"])
+@pytest.mark.parametrize("mode", ["gram", "gram2", "accurate", "tsqr"])
 def test_perform_pod_matches_reference(ctx, name, field, mode):
     g = load_golden(f"pod_{name}")
     _, U, _, _ = regen(g, field)
@@ -117,7 +117,7 @@ def test_perform_pod_matches_reference(ctx, name, field, mode):
     assert V.flags["C_CONTIGUOUS"] and V.dtype == np.float64
     assert cmp.sigma_error(sig[:n_L], g["sigma"][:n_L]) <= cmp.TOL_SIGMA_REL
     angle = cmp.largest_principal_angle(V, g["V"])
-    if mode == "accurate":
+    if mode in ("accurate", "tsqr"):
         assert angle <= cmp.TOL_ANGLE
         assert cmp.sigma_error(sig, g["sigma"]) <= cmp.TOL_SIGMA_REL       # every singular value
         v = po.project_to_v(V, U)
@@ -143,20 +143,121 @@ def test_perform_pod_fixed_rank_and_full_rank(ctx):
     with pytest.raises(ValueError):
         perform_pod(U, 0., 39, False, mode="gram", ctx=ctx)     # more modes than the numerical rank
     with pytest.raises(KeyError):
-        perform_pod(U, 1e-4, 0, False, mode="tsqr", ctx=ctx)
+        perform_pod(U, 1e-4, 0, False, mode="householder", ctx=ctx)
+    Vt = perform_pod(U, 0., 7, False, mode="tsqr", ctx=ctx)
+    assert Vt.shape == (300, 7) and cmp.largest_principal_angle(Vt, po.perform_pod(U, 0., 7)) <= cmp.TOL_ANGLE
+    Vft = perform_pod(Uf, 0., 0, False, mode="tsqr", ctx=ctx)   # eps = 0: no truncation of the pivoted QR
+    assert Vft.shape == (64, 12) and np.abs(Vft.T @ Vft - np.eye(12)).max() < 1e-10
 
 
-def test_pod_ragged_shapes(ctx):
+@pytest.mark.parametrize("mode", ["accurate", "tsqr"])
+def test_pod_ragged_shapes(ctx, mode):
     rng = np.random.default_rng(12)
     for (n_h, n_st) in ((257, 33), (33, 257), (100, 1), (1, 9), (129, 129)):
         U = rng.standard_normal((n_h, 3)) @ rng.standard_normal((3, n_st)) if min(n_h, n_st) > 3 \
             else rng.standard_normal((n_h, n_st))
-        V, sig = perform_pod(U, 1e-6, 0, False, ctx=ctx, return_sigma=True)
+        V, sig = perform_pod(U, 1e-6, 0, False, mode=mode, ctx=ctx, return_sigma=True)
         Vr = po.perform_pod(U, 1e-6)
         assert V.shape == Vr.shape, (n_h, n_st)
         assert cmp.largest_principal_angle(V, Vr) <= cmp.TOL_ANGLE
         D = np.linalg.svd(U, compute_uv=False)
         assert cmp.sigma_error(sig[:V.shape[1]], D[:V.shape[1]]) <= cmp.TOL_SIGMA_REL
+
+
+# ------------------------------------------------------------------ TSQR mode building blocks
+@pytest.mark.parametrize("rows,m", [(700, 130), (64, 64), (100, 1), (33, 70), (5000, 333), (1500, 1000), (4097, 65)])
+def test_tsqr_r_factor(ctx, rows, m):
+    """pb_tsqr_r: R is upper triangular, R^T R = A^T A to rounding, and equals LAPACK's R up to row signs."""
+    rng = np.random.default_rng(rows + m)
+    A = rng.standard_normal((rows, m))
+    Ad, Rd = ctx.to_device(A), ctx.alloc(m, m)
+    ctx.check(_lib.lib().pb_tsqr_r(ctx.h, Ad.ptr, rows, m, Ad.ld, Rd.ptr))
+    R = Rd.download()
+    assert np.array_equal(Ad.download(), A), "pb_tsqr_r must not modify its input"
+    assert np.abs(np.tril(R, -1)).max() == 0.
+    G = A.T @ A
+    assert np.abs(R.T @ R - G).max() <= 1e-13 * np.abs(G).max()
+    Rl = np.linalg.qr(A, mode="r")
+    k = Rl.shape[0]
+    s = np.sign(np.diag(R)[:k]) * np.sign(np.diag(Rl)); s[s == 0] = 1.
+    assert np.abs(R[:k] * s[:, None] - Rl).max() <= 1e-12 * np.abs(Rl).max()
+    if k < m:
+        assert np.abs(R[k:]).max() == 0.
+
+
+def test_tsqr_r_ill_conditioned_and_strided(ctx):
+    """Graded columns (kappa 1e15), a zero column, a leading dimension larger than the column count."""
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((900, 96)) * (10. ** -np.linspace(0, 15, 96))
+    A[:, 17] = 0.
+    big = np.zeros((900, 128)); big[:, :96] = A
+    Bd, Rd = ctx.to_device(big), ctx.alloc(96, 96)
+    ctx.check(_lib.lib().pb_tsqr_r(ctx.h, Bd.ptr, 900, 96, 128, Rd.ptr))
+    R = Rd.download()
+    # column-wise backward error: |A - Q R| <= c eps |A_j|  <=>  the Gram entries agree relative to the column norms
+    cn = np.linalg.norm(A, axis=0); cn[cn == 0] = 1.
+    E = (R.T @ R - A.T @ A) / np.outer(cn, cn)
+    assert np.abs(E).max() <= 1e-13
+    assert np.abs(R[:, 17]).max() == 0.
+
+
+def test_tsqr_logical_shards_equal_unsharded(ctx):
+    """TSQR with one leaf per (logical) rank: R of the stacked slab factors gives the POD of the whole matrix."""
+    g = load_golden("pod_ackley_64")
+    _, U, _, _ = regen(g, "ackley")
+    L = _lib.lib()
+    n_h, m = U.shape
+    bounds = [0, 1500, 1501, 3000, n_h]          # includes a one-row slab (rows < columns)
+    slabs = [ctx.to_device(U[a:b]) for a, b in zip(bounds, bounds[1:])]
+    stack = np.zeros((len(slabs) * m, m))
+    for i, s in enumerate(slabs):
+        Rd = ctx.alloc(m, m)
+        ctx.check(L.pb_tsqr_r(ctx.h, s.ptr, s.shape[0], m, s.ld, Rd.ptr))
+        stack[i * m:(i + 1) * m] = Rd.download()
+    Sd, Rd = ctx.to_device(stack), ctx.alloc(m, m)
+    ctx.check(L.pb_tsqr_r(ctx.h, Sd.ptr, stack.shape[0], m, m, Rd.ptr))
+    nl = C.c_int()
+    ctx.check(L.pb_pod_from_r(ctx.h, Rd.ptr, m, 1e-10, 0, C.byref(nl)))
+    V = np.zeros((n_h, nl.value))
+    for (a, b), s in zip(zip(bounds, bounds[1:]), slabs):
+        Vd = ctx.alloc(b - a, nl.value)
+        ctx.check(L.pb_pod_basis(ctx.h, s.ptr, b - a, s.ld, None, Vd.ptr, Vd.ld))
+        V[a:b] = Vd.download()
+    assert V.shape == g["V"].shape
+    assert cmp.largest_principal_angle(V, g["V"]) <= cmp.TOL_ANGLE
+    from pod_uqnn_b200.pod import pod_sigma
+    assert cmp.sigma_error(pod_sigma(ctx), g["sigma"]) <= cmp.TOL_SIGMA_REL
+    with pytest.raises(ValueError):              # a Gram matrix is not an input of this mode
+        ctx.check(L.pb_pod_from_gram(ctx.h, Rd.ptr, m, 1e-10, 0, 3, C.byref(nl), C.byref(nl)))
+
+
+def test_tsqr_cuda_backend(ctx):
+    from pod_uqnn_b200 import sharded
+    g = load_golden("pod_ackley_64")
+    _, U, _, _ = regen(g, "ackley")
+    be = sharded.CudaBackend(ctx)
+    try:
+        Ud = ctx.to_device(U)
+        V, sig, n_L = sharded.pod_sharded(be, Ud, 1e-10, 0, "tsqr")
+        be.stream.synchronize()
+        assert n_L == g["V"].shape[1]
+        assert cmp.largest_principal_angle(V.download(), g["V"]) <= cmp.TOL_ANGLE
+        import torch
+        st = torch.from_numpy(np.vstack([U[:2000], U[2000:]])).to(be.dev)       # a torch stack as pb_tsqr_r input
+        R = be.tsqr_r(st)
+        be.stream.synchronize()
+        assert np.abs(R.cpu().numpy().T @ R.cpu().numpy() - U.T @ U).max() <= 1e-13 * np.abs(U.T @ U).max()
+    finally:
+        be.close()
+
+
+@pytest.mark.parametrize("eps", ["0.0001", "1e-08"])
+def test_perform_fast_pod_tsqr(ctx, eps):
+    g = load_golden(f"fastpod_burgers_{eps}")
+    _, _, U_struct, _ = regen(g, "burgers")
+    V, ranks = perform_fast_pod(U_struct, float(g["eps"]), float(g["eps"]), mode="tsqr", ctx=ctx, return_ranks=True)
+    assert np.array_equal(ranks, g["ranks"]) and V.shape == g["V"].shape
+    assert cmp.largest_principal_angle(V, g["V"]) <= cmp.TOL_ANGLE
 
 
 @pytest.mark.parametrize("eps", ["0.0001", "1e-08"])

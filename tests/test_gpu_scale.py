@@ -52,13 +52,32 @@ def test_c2_pod_matches_reference(ctx, c2, mode):
 
 
 def test_c2_subspace_angle_against_oracle_svd(ctx, c2):
-    """The headline parity claim: gram2 mode vs LAPACK on the same matrix, angle <= 1e-8."""
+    """The headline parity claim: gram2 and TSQR modes vs LAPACK on the same matrix, angle <= 1e-8."""
     _, Ud = c2
     U = Ud.download()
     Vr = po.perform_pod(U, 1e-10)
-    Vd, _ = pod_device(ctx, Ud, 1e-10, 0, "gram2")
-    assert Vd.shape == Vr.shape
-    assert cmp.largest_principal_angle(Vd.download(), Vr) <= cmp.TOL_ANGLE
+    for mode in ("gram2", "tsqr"):
+        Vd, _ = pod_device(ctx, Ud, 1e-10, 0, mode)
+        assert Vd.shape == Vr.shape
+        assert cmp.largest_principal_angle(Vd.download(), Vr) <= cmp.TOL_ANGLE
+
+
+def test_c2_tsqr_matches_reference(ctx, c2):
+    """TSQR mode at full C2 size against the reference run's golden spectrum / rows / coefficients."""
+    g = load_golden("pod_ackley_c2_full")
+    _, Ud = c2
+    Vd, sig = pod_device(ctx, Ud, 1e-10, 0, "tsqr")
+    n_L = int(g["n_L"])
+    assert Vd.shape == (160000, n_L)
+    k = min(len(sig), len(g["sigma"]))
+    assert cmp.sigma_error(sig[:k], g["sigma"][:k]) <= cmp.TOL_SIGMA_REL          # every singular value the fixture holds
+    V = Vd.download()
+    assert np.abs(V.T @ V - np.eye(n_L)).max() <= 1e-9
+    Vrows, s = cmp.align_signs(V[g["rows"]], g["V_rows"])
+    assert np.abs(Vrows - g["V_rows"]).max() <= 1e-9 * np.abs(g["V_rows"]).max()
+    v = ctx.alloc(1000, n_L)
+    ctx.check(_lib.lib().pb_project(ctx.h, Vd.ptr, Vd.ld, n_L, Ud.ptr, Ud.ld, 160000, 1000, v.ptr))
+    assert cmp.rel_err(v.download() * s, g["v"]) <= 1e-9
 
 
 def test_c2_round_trip_and_pod_sig(ctx, c2):
@@ -101,14 +120,15 @@ def test_dct_known_answer_at_scale(ctx, n_h, n_s):
     assert np.abs(Va - phi).max() <= 1e-6 * np.sqrt(2. / n_h)
 
 
-def test_dct_known_answer_accurate_mode(ctx):
-    """Same known-answer matrix, accurate mode: every singular value and the modes to the 1e-8 class."""
+@pytest.mark.parametrize("mode", ["accurate", "tsqr"])
+def test_dct_known_answer_accurate_mode(ctx, mode):
+    """Same known-answer matrix, accurate / TSQR modes: every singular value and the modes to the 1e-8 class."""
     L = _lib.lib()
     n_h, n_s = 300000, 512
     Ud = ctx.alloc(n_h, n_s)
     ctx.check(L.pb_dct_lowrank(ctx.h, n_h, n_s, 256, 0.25, 0, n_h, Ud.ptr, Ud.ld))
     s = 2. ** (-0.25 * np.arange(256))
-    Vd, sig = pod_device(ctx, Ud, 1e-10, 0, "accurate")
+    Vd, sig = pod_device(ctx, Ud, 1e-10, 0, mode)
     n_L = wl.dct_rank(s, 1e-10)
     assert Vd.shape[1] == n_L
     assert cmp.sigma_error(sig[:150], s[:150]) <= 1e-13

@@ -29,16 +29,17 @@ if want("c1"):
     w = wl.shekel(400, 1000)
     Ud, _, _ = snapshots_device(ctx, "shekel", w["x_mesh"][:, 1:].T, w["mu"])
     r = {"snap_ms": ctx.ms(_lib.T_SNAPSHOTS)}
-    for mode in ("gram", "gram2", "accurate"):
+    for mode in ("gram", "gram2", "accurate", "tsqr"):
         ms, (V, sig) = timed(lambda: pod_device(ctx, Ud, 1e-10, 0, mode))
-        r[mode] = {"ms": ms, "n_L": V.shape[1], "eig_ms": ctx.ms(_lib.T_EIG), "pass2_ms": ctx.ms(_lib.T_PASS2)}
+        r[mode] = {"ms": ms, "n_L": V.shape[1], "eig_ms": ctx.ms(_lib.T_EIG), "pass2_ms": ctx.ms(_lib.T_PASS2),
+                   "qr_ms": ctx.ms(_lib.T_QR) if mode == "tsqr" else 0.}
     OUT["c1_shekel_400x1000"] = r; print("c1", r, flush=True)
 
 if want("c3"):
     w = wl.burgers(256, 100, 300)
     Ud, _, _ = snapshots_device(ctx, "burgers", w["x_mesh"][:, 1:].T, w["mu"], 100, 1., 5.)
     r = {"snap_ms": ctx.ms(_lib.T_SNAPSHOTS)}
-    for mode, eps in (("gram", 1e-4), ("accurate", 1e-4), ("accurate", 1e-10)):
+    for mode, eps in (("gram", 1e-4), ("accurate", 1e-4), ("accurate", 1e-10), ("tsqr", 1e-4)):
         ms, (V, ranks) = timed(lambda: fast_pod_device(ctx, Ud, 100, 300, eps, eps, mode), reps=1)
         r[f"two_step_{mode}_{eps:g}"] = {"ms": ms, "n_L": V.shape[1], "ranks_sum": int(ranks.sum()), "ranks_max": int(ranks.max())}
     ms, (V, sig) = timed(lambda: pod_device(ctx, Ud, 1e-4, 0, "accurate"))
@@ -61,6 +62,19 @@ if want("c4"):
                           "frac_fp64_peak": flops / (kms * 1e-3) / 1e12 / pk.value}
     OUT["c4_ensemble_M8_N1e6"] = r; print("c4", r, flush=True)
 
+if want("c2"):
+    w = wl.ackley(400, 400, 1000)
+    Ud, _, _ = snapshots_device(ctx, "ackley", w["x_mesh"][:, 1:].T, w["mu"])
+    r = {}
+    for mode in ("gram2", "accurate", "tsqr"):
+        ms, (V, sig) = timed(lambda: pod_device(ctx, Ud, 1e-10, 0, mode))
+        r[mode] = {"ms": ms, "n_L": V.shape[1], "gram_ms": ctx.ms(_lib.T_GRAM) if mode != "tsqr" else 0., "eig_ms": ctx.ms(_lib.T_EIG),
+                   "pass2_ms": ctx.ms(_lib.T_PASS2), "qr_ms": ctx.ms(_lib.T_QR) if mode == "tsqr" else 0.}
+        if mode == "tsqr":      # Householder flop count 2 n_h n_s^2 - (2/3) n_s^3
+            r[mode]["qr_tflops"] = (2 * 160000 * 1000 ** 2 - 2 / 3 * 1000 ** 3) / (ctx.ms(_lib.T_QR) * 1e-3) / 1e12
+    OUT["c2_ackley_160000x1000"] = r; print("c2", r, flush=True)
+    Ud.release()
+
 if want("c5"):
     r = {}
     for n_h, n_s in ((250_000, 4096), (1_250_000, 4096)):
@@ -68,8 +82,15 @@ if want("c5"):
         t = time.time(); ctx.check(L.pb_dct_lowrank(ctx.h, n_h, n_s, 256, 0.25, 0, n_h, Ud.ptr, Ud.ld)); ctx.sync()
         gen_s = time.time() - t
         rr = {"gen_s": gen_s}
-        for mode in ("gram", "gram2"):
-            ms, (V, sig) = timed(lambda: pod_device(ctx, Ud, 1e-10, 0, mode), reps=2)
+        for mode in ("gram", "gram2", "tsqr"):
+            ms, (V, sig) = timed(lambda: pod_device(ctx, Ud, 1e-10, 0, mode), reps=2 if mode != "tsqr" else 1)
+            if mode == "tsqr":
+                qr = ctx.ms(_lib.T_QR)
+                rr[mode] = {"ms": ms, "n_L": V.shape[1], "qr_ms": qr, "eig_ms": ctx.ms(_lib.T_EIG), "basis_ms": ctx.ms(_lib.T_BASIS),
+                            "qr_tflops": (2 * n_h * n_s ** 2 - 2 / 3 * n_s ** 3) / (qr * 1e-3) / 1e12,
+                            "sig_err_vs_closed_form": float(np.max(np.abs(sig[:V.shape[1]] / sig[0] - 2. ** (-0.25 * np.arange(V.shape[1])))))}
+                del V
+                continue
             gk = ctx.ms(_lib.T_TN_KERNEL)
             rr[mode] = {"ms": ms, "n_L": V.shape[1], "gram_kernel_ms": gk, "gram_tflops": n_h * n_s * (n_s + 1) / (gk * 1e-3) / 1e12,
                         "gram_frac": n_h * n_s * (n_s + 1) / (gk * 1e-3) / 1e12 / pk.value, "eig_ms": ctx.ms(_lib.T_EIG),
