@@ -267,6 +267,31 @@ def run_gpu(args):
 
     # ---- second headline metric: ensemble predict samples/s (C4: M = 8 MLPs [1,128,128,128,2*64], 1e6 points
     #      split over the ranks, no communication)
+    # ---- the TSQR accuracy mode on the same resident slab(s): Householder QR per rank, all-gather of the R factors,
+    #      replicated QR of the stack + pivoted QR + Jacobi SVD, basis, projection
+    def step_tsqr():
+        if world == 1:
+            nl = C.c_int()
+            ctx.check(L.pb_pod(ctx.h, U.ptr, n_h_loc, N_S, U.ld, EPS, 0, _lib.POD_MODES["tsqr"], C.byref(nl)))
+            V = ctx.alloc(n_h_loc, nl.value); v = ctx.alloc(N_S, nl.value)
+            ctx.check(L.pb_pod_basis_full(ctx.h, U.ptr, n_h_loc, N_S, U.ld, V.ptr, V.ld))
+            ctx.check(L.pb_project(ctx.h, V.ptr, V.ld, nl.value, U.ptr, U.ld, n_h_loc, N_S, v.ptr))
+            return nl.value
+        V, _, nl = sharded.pod_sharded(be, U, EPS, 0, "tsqr")
+        sharded.project_sharded(be, V, U)
+        return nl
+    step_tsqr(); barrier()
+    t_best = 1e30
+    for _ in range(3):
+        barrier(); ctx.timer_start(); nl_t = step_tsqr(); t_best = min(t_best, ctx.timer_stop())
+    barrier()
+    t_tsqr = max_over_ranks(t_best)
+    qr_flops = world * (2 * n_h_loc * N_S ** 2 - 2 / 3 * N_S ** 3)
+    tsqr_line = {"workload": "same slabs, mode tsqr (blocked Householder QR of U, pivoted QR + Jacobi SVD of R), basis, projection",
+                 "ms_per_step": t_tsqr, "n_L": nl_t, "local_qr_ms": ctx.ms(_lib.T_QR),
+                 "householder_tflops": qr_flops / (t_tsqr * 1e-3) / 1e12,
+                 "note": "flop count 2 n_h n_s^2 - (2/3) n_s^3 per slab (SURVEY 8d); at N > 1 T_QR is the replicated QR of the stacked R factors"}
+
     ens_line = ensemble_bench(ctx, L, world, rank, max_over_ranks, peak_tf, with_cpu=(world == 1 and not args.no_cpu_baseline))
     train_lines = train_bench(ctx, world, rank, max_over_ranks, peak_tf, with_cpu=(world == 1 and not args.no_cpu_baseline))
 
@@ -300,7 +325,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "steps": e2e_steps,
                     "h2d_bytes_per_step": U.nbytes * world, "d2h_bytes_per_step": (n_h + N_S) * n_L * 8},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "stage_ms": {k: statistics.mean(v) for k, v in parts.items()},
+            "stage_ms": {k: statistics.mean(v) for k, v in parts.items()}, "tsqr_mode": tsqr_line,
             "ensemble_predict": ens_line, "ensemble_train": train_lines,
             "snapshot_kernel": {"ms": snap_ms, "gbs": U.nbytes / (snap_ms * 1e-3) / 1e9,
                                 "note": "Ackley field -> U slab in HBM (outside the timed step)"}}

@@ -274,24 +274,29 @@ gemm_nn_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int m,
 // current tile is multiplied and compared, so HBM streams continuously; a CTA owns whole rows, so
 // pod_sig[h] = mean_j |U - Y| / 2 is finished in the kernel (no partial buffer, no second pass).
 // ---------------------------------------------------------------------------
-template <int KP, bool ALIGN_A, bool ALIGN_B, bool ALIGN_U>
-__global__ void __launch_bounds__(NTHREADS, (KP <= 32) ? 2 : 1)
+template <int KP, int MS, bool ALIGN_A, bool ALIGN_B, bool ALIGN_U>
+__global__ void __launch_bounds__(NTHREADS, (KP <= 32 && MS == 32) ? 2 : 1)
 recon_strip_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int K,
                    const double* __restrict__ B, int64_t ldb, int64_t n,
                    double* __restrict__ Y, int64_t ldy,
                    const double* U, int64_t ldu, double* __restrict__ sig_out, int subtract) {
     // subtract != 0: Y = U - A B with U == Y allowed (the in-place trailing update C -= Y X of the blocked
-    // Householder QR, qr.cu): the U tile of a column tile is read from its staged copy before the tile is written
-    constexpr int MS = 32, NT = 64;
+    // Householder QR, qr.cu): the U tile of a column tile is read from its staged copy before the tile is written.
+    // MS = rows per strip: 32 for the HBM-bound reconstruction; 64 for the QR update (K = 64 is compute bound and a
+    // 32-row strip re-reads the B tiles from L2 twice as often as it can afford)
+    constexpr int NT = 64;
+    constexpr int RA = MS / 16;                // 8-row fragments per warp (2 x 4 warps, warp tile MS/2 x 16)
     constexpr int STG = (KP <= 16) ? 3 : 2;    // tiles in flight: 2 CTAs x 2 tiles x 16 KB keep HBM busy (n_L <= 16)
-    constexpr int PA = KP + 4, PB = NT + 4, PU = NT + 4;
+    constexpr int PA = KP + 4, PB = NT + 4;
+    constexpr int PU = NT + 8;                 // the U tile is read back as double2 per (row, column pair): a row pitch of
+                                               // 64 bytes mod 128 keeps the 8 lanes of a quarter-warp on distinct banks
     extern __shared__ __align__(16) double smem[];
     double* As = smem;                         // [MS][PA]
     double* Bs = As + MS * PA;                 // [STG][KP][PB]
     double* Us = Bs + STG * KP * PB;           // [STG][MS][PU]
     __shared__ double rowsum[4][MS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;   // 2 x 4 warps, warp tile 16 x 16
+    const int wm = warp >> 2, wn = warp & 3;
     const int lk = lane & 3, lg = lane >> 2;
     const int64_t h0 = (int64_t)blockIdx.x * MS;
     const int n_tiles = (int)((n + NT - 1) / NT);
@@ -310,29 +315,31 @@ recon_strip_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int 
         if (t < n_tiles) prefetch(t);
         cp_async_commit();
     }
-    double rs[2] = {0., 0.};
+    double rs[RA];
+#pragma unroll
+    for (int a = 0; a < RA; ++a) rs[a] = 0.;
     for (int t = 0; t < n_tiles; ++t) {
         cp_async_wait<STG - 2>();
         __syncthreads();                       // tile t has landed; everyone is done with tile t - 1's buffers
         if (t + STG - 1 < n_tiles) prefetch(t + STG - 1);
         cp_async_commit();
-        double acc[2][2][2];
+        double acc[RA][2][2];
 #pragma unroll
-        for (int a = 0; a < 2; ++a)
+        for (int a = 0; a < RA; ++a)
 #pragma unroll
             for (int u = 0; u < 2; ++u) { acc[a][u][0] = 0.; acc[a][u][1] = 0.; }
-        const double* as = As + (wm * 16 + lg) * PA + lk;
+        const double* as = As + (wm * (MS / 2) + lg) * PA + lk;
         const double* bs = Bs + (t % STG) * KP * PB + wn * 16 + lg;
 #pragma unroll
         for (int kk = 0; kk < KP / 4; ++kk) {
             if (kk * 4 < K) {
-                double af[2], bf[2];
+                double af[RA], bf[2];
 #pragma unroll
-                for (int a = 0; a < 2; ++a) af[a] = as[a * 8 * PA + kk * 4];
+                for (int a = 0; a < RA; ++a) af[a] = as[a * 8 * PA + kk * 4];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) bf[u] = bs[(kk * 4 + lk) * PB + u * 8];
 #pragma unroll
-                for (int a = 0; a < 2; ++a)
+                for (int a = 0; a < RA; ++a)
 #pragma unroll
                     for (int u = 0; u < 2; ++u) dmma884(acc[a][u][0], acc[a][u][1], af[a], bf[u]);
             }
@@ -340,8 +347,8 @@ recon_strip_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int 
         const int64_t j0 = (int64_t)t * NT;
         const double* us = Us + (t % STG) * MS * PU;
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
-            const int rl = wm * 16 + a * 8 + lg;
+        for (int a = 0; a < RA; ++a) {
+            const int rl = wm * (MS / 2) + a * 8 + lg;
             const int64_t h = h0 + rl;
             if (h >= rows) continue;
 #pragma unroll
@@ -367,11 +374,11 @@ recon_strip_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int 
     cp_async_wait<0>();
     if (want_sig) {
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < RA; ++a) {
             double v = rs[a];
             v += __shfl_xor_sync(0xffffffffu, v, 1);
             v += __shfl_xor_sync(0xffffffffu, v, 2);
-            if (lk == 0) rowsum[wn][wm * 16 + a * 8 + lg] = v;
+            if (lk == 0) rowsum[wn][wm * (MS / 2) + a * 8 + lg] = v;
         }
         __syncthreads();
         if (tid < MS && h0 + tid < rows)
@@ -520,15 +527,15 @@ int launch_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m
 }
 
 
-template <int KP>
+template <int KP, int MS = 32>
 int launch_recon_strip(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m, const double* B,
                        int64_t ldb, int64_t k, double* Y, int64_t ldy, const double* Uref, int64_t ldu, double* sig_out,
                        int subtract = 0) {
     constexpr int STG = (KP <= 16) ? 3 : 2;
-    constexpr size_t smem = (size_t)(32 * (KP + 4) + STG * KP * 68 + STG * 32 * 68) * sizeof(double);
+    constexpr size_t smem = (size_t)(MS * (KP + 4) + STG * KP * 68 + STG * MS * 72) * sizeof(double);
     const bool aa = aligned16(A, lda), ab = aligned16(B, ldb), au = !Uref || aligned16(Uref, ldu);
-    dim3 grid((unsigned)((rows + 31) / 32));
-#define PB_RS_CASE(AA, AB, AU) { auto kern = recon_strip_kernel<KP, AA, AB, AU>; \
+    dim3 grid((unsigned)((rows + MS - 1) / MS));
+#define PB_RS_CASE(AA, AB, AU) { auto kern = recon_strip_kernel<KP, MS, AA, AB, AU>; \
         PB_TRY(set_smem(ctx, kern, smem)); \
         kern<<<grid, NTHREADS, smem, ctx->stream>>>(A, lda, rows, (int)m, B, ldb, k, Y, ldy, Uref, ldu, sig_out, subtract); }
     if (aa && ab && au) PB_RS_CASE(true, true, true)
@@ -559,6 +566,7 @@ int pbi_gemm_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const dou
         if (sym) { symmetrize_kernel<<<(unsigned)((ka * kb + 255) / 256), 256, 0, ctx->stream>>>(C, (int)ka, ldc, 0); PB_LAUNCH_CHECK(ctx); }
         return PB_OK;
     }
+    if (!sym && ka > 32 && ka <= 64 && kb <= 64) return launch_tn<64, 64, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);   // Y^T Y of a QR panel
     if (!sym && ka > 32 && ka <= 64) return launch_tn<64, 128, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);
     if (!sym && ka > 64 && ka <= 96) return launch_tn<96, 128, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);
     if (sym || ka > 32) return launch_tn<128, 128, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, sym);
@@ -611,6 +619,8 @@ int pbi_gemm_nn_sub(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int
     if (strip_env && m <= 64 && k >= 64) {
         if (m <= 16) return launch_recon_strip<16>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Y, ldy, nullptr, 1);
         if (m <= 32) return launch_recon_strip<32>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Y, ldy, nullptr, 1);
+        static const int ms64 = getenv("PB_QR_STRIP_ROWS") ? atoi(getenv("PB_QR_STRIP_ROWS")) : 64;
+        if (ms64 == 64) return launch_recon_strip<64, 64>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Y, ldy, nullptr, 1);
         return launch_recon_strip<64>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Y, ldy, nullptr, 1);
     }
     if (k > 96) return launch_nn<128, 2, 4>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, nullptr, 0, nullptr, Batch(), 1);

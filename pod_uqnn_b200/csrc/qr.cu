@@ -80,8 +80,7 @@ constexpr int QP = QIB + 2;                  // shared-memory row pitch: 16-byte
 
 __global__ void __launch_bounds__(QT) qr_panel_kernel(QrPanelArgs a) {
     cg::grid_group grid = cg::this_grid();
-    extern __shared__ __align__(16) double zred[];          // [8 warps][ZE]; before that the staged inner panel
-    double* Ps = zred;
+    extern __shared__ __align__(16) double Ps[];            // the staged inner panel (use_smem), pitch QP
     __shared__ double red[QT / 32][QIB];
     __shared__ double red2[QIB][QIB];
     __shared__ double gsh[QIB], dsh[QIB], tau_sh[QIB], outsh[QIB];
@@ -221,42 +220,57 @@ __global__ void __launch_bounds__(QT) qr_panel_kernel(QrPanelArgs a) {
             const int c1 = c0 + QIB;
             const int nblk = (QIB + ncols) / 8;
             const int64_t lo2 = lo > c0 ? lo : (int64_t)c0;
+            // entry (r, col) of the explicit reflector block: from the staged copy when there is one
+            auto yv = [&](int64_t r, int col) -> double {
+                const int64_t d = (int64_t)c0 + col;
+                if (r > d) return a.use_smem ? Ps[(size_t)(r - lo) * QP + col] : W[r * ldw + d];
+                return r == d ? 1. : 0.;
+            };
+            // Z = Y^T [Y | C] over my rows: two 4-row steps per warp iteration, all loads issued before the DMMAs
             double zacc[2][QNB / 8][2];
 #pragma unroll
             for (int t = 0; t < 2; ++t)
 #pragma unroll
                 for (int u = 0; u < QNB / 8; ++u) { zacc[t][u][0] = 0.; zacc[t][u][1] = 0.; }
-            for (int64_t r0 = lo2 + 4 * warp; r0 < hi; r0 += 4 * (QT / 32)) {
-                const int64_t r = r0 + lk;
-                const bool ok = r < hi;
-                const double a0 = ok ? yval(W, ldw, r, c0, lg) : 0.;
-                const double a1 = ok ? yval(W, ldw, r, c0, 8 + lg) : 0.;
+            for (int64_t r0 = lo2 + 4 * warp; r0 < hi; r0 += 8 * (QT / 32)) {
+                double a0[2], a1[2], bv[2][QNB / 8 - 2];
 #pragma unroll
-                for (int u = 0; u < QNB / 8; ++u) {
-                    if (u < nblk) {
-                        double bv;
-                        if (u == 0) bv = a0; else if (u == 1) bv = a1;
-                        else bv = ok ? W[r * ldw + c1 + (u - 2) * 8 + lg] : 0.;
-                        dmma884(zacc[0][u][0], zacc[0][u][1], a0, bv);
-                        dmma884(zacc[1][u][0], zacc[1][u][1], a1, bv);
+                for (int h = 0; h < 2; ++h) {
+                    const int64_t r = r0 + h * 4 * (QT / 32) + lk;
+                    const bool ok = r < hi;
+                    a0[h] = ok ? yv(r, lg) : 0.;
+                    a1[h] = ok ? yv(r, 8 + lg) : 0.;
+#pragma unroll
+                    for (int u = 2; u < QNB / 8; ++u)
+                        bv[h][u - 2] = (ok && u < nblk) ? W[r * ldw + c1 + (u - 2) * 8 + lg] : 0.;
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int u = 0; u < QNB / 8; ++u) {
+                        if (u < nblk) {
+                            const double b_ = u == 0 ? a0[h] : (u == 1 ? a1[h] : bv[h][u >= 2 ? u - 2 : 0]);
+                            dmma884(zacc[0][u][0], zacc[0][u][1], a0[h], b_);
+                            dmma884(zacc[1][u][0], zacc[1][u][1], a1[h], b_);
+                        }
                     }
-                }
             }
-            double* my = zred + (size_t)warp * ZE;
-#pragma unroll
-            for (int t = 0; t < 2; ++t)
-#pragma unroll
-                for (int u = 0; u < QNB / 8; ++u) {
-                    my[(t * 8 + lg) * QNB + u * 8 + 2 * lk] = zacc[t][u][0];
-                    my[(t * 8 + lg) * QNB + u * 8 + 2 * lk + 1] = zacc[t][u][1];
-                }
+            // CTA sum in warp order (fixed), straight into Zs
+            for (int e = tid; e < ZE; e += QT) Zs[e] = 0.;
             __syncthreads();
-            for (int e = tid; e < ZE; e += QT) {
-                double s = 0.;
+            for (int wq = 0; wq < QT / 32; ++wq) {
+                if (warp == wq) {
 #pragma unroll
-                for (int wq = 0; wq < QT / 32; ++wq) s += zred[(size_t)wq * ZE + e];
-                a.zpart[(size_t)b * ZE + e] = s;
+                    for (int t = 0; t < 2; ++t)
+#pragma unroll
+                        for (int u = 0; u < QNB / 8; ++u) {
+                            Zs[(t * 8 + lg) * QNB + u * 8 + 2 * lk] += zacc[t][u][0];
+                            Zs[(t * 8 + lg) * QNB + u * 8 + 2 * lk + 1] += zacc[t][u][1];
+                        }
+                }
+                __syncthreads();
             }
+            for (int e = tid; e < ZE; e += QT) a.zpart[(size_t)b * ZE + e] = Zs[e];
             grid.sync();
             {   // second stage: CTA b finishes entries [b * epc, (b + 1) * epc)
                 const int epc = (ZE + G - 1) / G;
@@ -264,7 +278,7 @@ __global__ void __launch_bounds__(QT) qr_panel_kernel(QrPanelArgs a) {
                     const int e = b * epc + el;
                     if (e < ZE) {
                         double s = 0.;
-                        for (int bb = lane; bb < G; bb += 32) s += a.zpart[(size_t)bb * ZE + e];
+                        for (int bb = lane; bb < G; bb += 32) s += __ldcg(a.zpart + (size_t)bb * ZE + e);
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                         if (lane == 0) a.zfin[e] = s;
@@ -272,7 +286,7 @@ __global__ void __launch_bounds__(QT) qr_panel_kernel(QrPanelArgs a) {
                 }
             }
             grid.sync();
-            for (int e = tid; e < ZE; e += QT) Zs[e] = a.zfin[e];
+            for (int e = tid; e < ZE; e += QT) Zs[e] = __ldcg(a.zfin + e);
             __syncthreads();
             // X = T^T Z: X_i = tau_i (Z_i - sum_{k<i} S_ki X_k), S = striu(Y^T Y) = Zs[:, 0:16]
             if (tid < ncols) {
@@ -283,21 +297,32 @@ __global__ void __launch_bounds__(QT) qr_panel_kernel(QrPanelArgs a) {
                 }
             }
             __syncthreads();
-            // C -= Y X on my rows
-            for (int64_t r0 = lo2 + 8 * warp; r0 < hi; r0 += 8 * (QT / 32)) {
-                const int64_t rr = r0 + lg;
-                const bool ok = rr < hi;
-                double af[4];
+            // C -= Y X on my rows: two 8-row groups per warp iteration
+            for (int64_t r0 = lo2 + 8 * warp; r0 < hi; r0 += 16 * (QT / 32)) {
+                double af[2][4];
+                double2 cc[2][(QNB - QIB) / 8];
+                bool ok[2];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) af[q] = ok ? yval(W, ldw, rr, c0, 4 * q + lk) : 0.;
+                for (int h = 0; h < 2; ++h) {
+                    const int64_t rr = r0 + h * 8 * (QT / 32) + lg;
+                    ok[h] = rr < hi;
 #pragma unroll
-                for (int u = 0; u < (QNB - QIB) / 8; ++u) {
-                    if (u * 8 < ncols) {
-                        double2* cp = reinterpret_cast<double2*>(W + rr * ldw + c1 + u * 8 + 2 * lk);
-                        double2 acc = ok ? *cp : make_double2(0., 0.);
+                    for (int q = 0; q < 4; ++q) af[h][q] = ok[h] ? yv(rr, 4 * q + lk) : 0.;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) dmma884(acc.x, acc.y, af[q], -Xs[4 * q + lk][u * 8 + lg]);
-                        if (ok) *cp = acc;
+                    for (int u = 0; u < (QNB - QIB) / 8; ++u)
+                        cc[h][u] = (ok[h] && u * 8 < ncols) ? *reinterpret_cast<const double2*>(W + rr * ldw + c1 + u * 8 + 2 * lk)
+                                                            : make_double2(0., 0.);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int64_t rr = r0 + h * 8 * (QT / 32) + lg;
+#pragma unroll
+                    for (int u = 0; u < (QNB - QIB) / 8; ++u) {
+                        if (u * 8 < ncols) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) dmma884(cc[h][u].x, cc[h][u].y, af[h][q], -Xs[4 * q + lk][u * 8 + lg]);
+                            if (ok[h]) *reinterpret_cast<double2*>(W + rr * ldw + c1 + u * 8 + 2 * lk) = cc[h][u];
+                        }
                     }
                 }
             }
@@ -614,7 +639,6 @@ int pbi_qr_r(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda,
     const int cp_grid = ctx->sm_count * 8;
     qr_copy_pad_kernel<<<cp_grid, 256, 0, ctx->stream>>>(A, lda, rows, m, W, ldw, rowsW);
     PB_LAUNCH_CHECK(ctx);
-    const size_t smem_z = sizeof(double) * (size_t)(QT / 32) * ZE;
     constexpr int64_t RS_MAX = 1400;             // rows of an inner panel staged per CTA (1400 x 18 doubles = 197 KB)
     static const int stage_env = getenv("PB_QR_STAGE") ? atoi(getenv("PB_QR_STAGE")) : 1;
     for (int64_t J = 0; J < mp; J += QNB) {
@@ -622,7 +646,7 @@ int pbi_qr_r(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda,
         int grid = std::max(1, std::min<int>((int)((rowsW - J + 127) / 128), ctx->sm_count));
         int64_t rpc = (rowsW - J + grid - 1) / grid; rpc = (rpc + 7) / 8 * 8;       // as the kernel computes it
         const int use_smem = (stage_env && rpc <= RS_MAX) ? 1 : 0;
-        const size_t smem = use_smem ? std::max(smem_z, sizeof(double) * (size_t)rpc * QP) : smem_z;
+        const size_t smem = use_smem ? sizeof(double) * (size_t)rpc * QP : 0;
         PB_CUDA(ctx, cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PB_TRY(coop_grid(ctx, (const void*)qr_panel_kernel, smem, grid, &grid));
         QrPanelArgs pa{W, ldw, rowsW, (int)J, nbo, tau + J, part, diag, zpart, zfin, use_smem};

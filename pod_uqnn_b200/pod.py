@@ -1,12 +1,15 @@
 """POD -- same names and argument order as the reference's poduqnn/pod.py
 (perform_pod :7-47, perform_fast_pod :51-68), computed on the GPU by libpodb200.
 
-Algorithm (csrc/gemm.cu, csrc/eig.cu): method of snapshots.  G = A^T A on DMMA (A = U, or
-U^T when n_h < n_st), pivoted Cholesky of G, one-sided block Jacobi on the factor, energy
+Algorithm (csrc/gemm.cu, csrc/eig.cu, csrc/qr.cu).  Gram modes -- method of snapshots: G = A^T A on DMMA
+(A = U, or U^T when n_h < n_st), pivoted Cholesky of G, one-sided block Jacobi on the factor, energy
 rank rule (pod.py:22-32), V = U Z diag(1/sigma).  `mode`:
   "gram"      one Gram pass (fast; subspace angle limited by eps_mach * lambda_1 / gap)
   "gram2"     + rotate the numerical-rank block and repeat the Gram on it
-  "accurate"  rotate all columns and repeat (one-sided Jacobi SVD accuracy; the default)
+  "accurate"  rotate all columns and repeat (one-sided Jacobi SVD accuracy)
+  "tsqr"      blocked Householder QR of A itself (never A^T A), rank-revealing pivoted QR of R, Jacobi SVD of
+              the factor: the accuracy class of the reference's LAPACK SVD (pod.py:16) at half the cost of
+              "accurate" -- the default
 """
 import ctypes as C
 
@@ -15,7 +18,7 @@ import numpy as np
 from . import _lib
 from ._lib import DeviceArray, POD_MODES
 
-DEFAULT_MODE = "accurate"
+DEFAULT_MODE = "tsqr"
 
 
 def pod_device(ctx, U, eps=0., n_L=0, mode=DEFAULT_MODE):
