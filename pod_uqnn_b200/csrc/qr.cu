@@ -619,10 +619,35 @@ int coop_grid(pb_ctx* ctx, const void* kernel, size_t smem, int want, int* grid_
 int pbi_gemm_nn_sub(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m, const double* B, int64_t ldb,
                     int64_t k, double* Y, int64_t ldy);
 
+namespace {
+constexpr int64_t RS_MAX = 1400;                 // rows of an inner panel staged per CTA (1400 x 18 doubles = 197 KB)
+int qr_leaf(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, double* R, int64_t ldr, int64_t rows_out);
+}
+
 // R (m x m upper triangular, ld ldr, rows_out >= m rows written: zero below the triangle) of A (rows x m, lda).
+// Slabs taller than what the staged panel kernel holds (sm_count x 1400 rows) are cut into equal row blocks -- TSQR
+// leaves inside the GPU: R_i = qr(A_i), then the QR of the stacked factors.  The stack adds n_leaves m / rows of the
+// flops (2 % at 1.25 M x 4096), every leaf runs the shared-memory panel path, and the working copy is one leaf, not
+// the whole slab (6.8 GB instead of 41 GB at C5).
 int pbi_qr_r(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, double* R, int64_t ldr, int64_t rows_out) {
     if (rows <= 0 || m <= 0 || lda < m || ldr < m || rows_out < m) PB_FAIL(ctx, PB_ERR_SHAPE, "tsqr: bad shape");
     if (m > 8192) PB_FAIL(ctx, PB_ERR_SHAPE, "tsqr: %lld columns exceed 8192", (long long)m);
+    static const int leaves_env = getenv("PB_QR_LEAVES") ? atoi(getenv("PB_QR_LEAVES")) : 1;
+    const int64_t leaf_max = (int64_t)ctx->sm_count * RS_MAX;
+    const int64_t n_leaves = (rows + leaf_max - 1) / leaf_max;
+    if (!leaves_env || n_leaves < 2 || rows < 4 * m || n_leaves * m > leaf_max)
+        return qr_leaf(ctx, A, rows, m, lda, R, ldr, rows_out);
+    PB_TRY(pb_reserve(ctx, &ctx->qr_stack, &ctx->qr_stack_cap, (size_t)n_leaves * m * m));
+    const int64_t per = (rows + n_leaves - 1) / n_leaves;
+    for (int64_t i = 0; i < n_leaves; ++i) {
+        const int64_t r0 = i * per, nr = std::min(per, rows - r0);
+        PB_TRY(qr_leaf(ctx, A + r0 * lda, nr, m, lda, ctx->qr_stack + (size_t)i * m * m, m, m));
+    }
+    return qr_leaf(ctx, ctx->qr_stack, n_leaves * m, m, m, R, ldr, rows_out);
+}
+
+namespace {
+int qr_leaf(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, double* R, int64_t ldr, int64_t rows_out) {
     const int64_t mp = (m + QIB - 1) / QIB * QIB;            // padded column count (zero columns reflect to nothing)
     const int64_t ldw = mp;
     const int64_t rowsW = std::max(rows, mp);
@@ -639,7 +664,6 @@ int pbi_qr_r(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda,
     const int cp_grid = ctx->sm_count * 8;
     qr_copy_pad_kernel<<<cp_grid, 256, 0, ctx->stream>>>(A, lda, rows, m, W, ldw, rowsW);
     PB_LAUNCH_CHECK(ctx);
-    constexpr int64_t RS_MAX = 1400;             // rows of an inner panel staged per CTA (1400 x 18 doubles = 197 KB)
     static const int stage_env = getenv("PB_QR_STAGE") ? atoi(getenv("PB_QR_STAGE")) : 1;
     for (int64_t J = 0; J < mp; J += QNB) {
         const int nbo = (int)std::min<int64_t>(QNB, mp - J);
@@ -669,6 +693,7 @@ int pbi_qr_r(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda,
     PB_LAUNCH_CHECK(ctx);
     return PB_OK;
 }
+}  // namespace
 
 // At (rows_total x ldm, zero padded) = upper triangle of R (m x m, ld ldr)
 int pbi_qr_load_factor(pb_ctx* ctx, const double* R, int64_t ldr, int64_t m, double* At, int64_t ldm, int64_t rows_total) {

@@ -44,6 +44,8 @@ if world > 1:
     tt = torch.tensor([sec], dtype=torch.float64, device=f"cuda:{local}"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); sec = float(tt.item())
 s = 2. ** (-0.25 * np.arange(r))
 flops = n_h * n_s * (n_s + 1) + 4 * n_h * n_s * n_L
+if mode == "tsqr":      # Householder count of the local QRs + basis + projection
+    flops = 2 * n_h * n_s ** 2 - world * (2 / 3) * n_s ** 3 + 4 * n_h * n_s * n_L
 if rank == 0:
     out = {"n_gpus": world, "n_h": n_h, "n_s": n_s, "mode": mode, "n_L": n_L, "n_L_closed_form": wl.dct_rank(s, eps), "wall_s": sec,
            "pod_tflops": flops / sec / 1e12, "fp64_peak_per_gpu": pk.value, "frac_of_aggregate_peak": flops / sec / 1e12 / (pk.value * world),
