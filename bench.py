@@ -273,7 +273,9 @@ def run_gpu(args):
         if world == 1:
             nl = C.c_int()
             ctx.check(L.pb_pod(ctx.h, U.ptr, n_h_loc, N_S, U.ld, EPS, 0, _lib.POD_MODES["tsqr"], C.byref(nl)))
-            V = ctx.alloc(n_h_loc, nl.value); v = ctx.alloc(N_S, nl.value)
+            if state.get("t_nL") != nl.value:
+                state["tV"], state["tv"], state["t_nL"] = ctx.alloc(n_h_loc, nl.value), ctx.alloc(N_S, nl.value), nl.value
+            V, v = state["tV"], state["tv"]
             ctx.check(L.pb_pod_basis_full(ctx.h, U.ptr, n_h_loc, N_S, U.ld, V.ptr, V.ld))
             ctx.check(L.pb_project(ctx.h, V.ptr, V.ld, nl.value, U.ptr, U.ld, n_h_loc, N_S, v.ptr))
             return nl.value

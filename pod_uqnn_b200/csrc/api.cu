@@ -85,7 +85,7 @@ int pb_destroy(pb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     void* bufs[] = {ctx->ws, ctx->flush, ctx->At, ctx->At2, ctx->sig, ctx->nrm, ctx->sig2, ctx->nrm2, ctx->perm,
-                    ctx->perm2, ctx->Bmat, ctx->Wk, ctx->small, ctx->qr_W, ctx->qr_Y, ctx->qr_scr, ctx->qr_scr2, ctx->qr_stack, ctx->Gbuf, ctx->G2buf, ctx->Ybuf, ctx->ATbuf, ctx->Uf, ctx->d_int, ctx->fp_ibuf,
+                    ctx->perm2, ctx->Bmat, ctx->Wk, ctx->small, ctx->qr_W, ctx->qr_scr, ctx->qr_scr2, ctx->qr_stack, ctx->Gbuf, ctx->G2buf, ctx->Ybuf, ctx->ATbuf, ctx->Uf, ctx->d_int, ctx->fp_ibuf,
                     ctx->fp_buf[0], ctx->fp_buf[1], ctx->fp_buf[2], ctx->fp_buf[3], ctx->fp_buf[4], ctx->fp_buf[5], ctx->fp_buf[6], ctx->fp_buf[7]};
     for (void* b : bufs) if (b) cudaFree(b);
     if (ctx->h_int) cudaFreeHost(ctx->h_int);

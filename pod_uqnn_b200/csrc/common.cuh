@@ -59,9 +59,9 @@ struct pb_ctx {
     int* d_int = nullptr;   // device ints (flags, n_L ...)
     int* h_int = nullptr;   // pinned host mirror
     std::vector<double> sigma_host;  // singular values of the last decomposition
-    double* qr_W = nullptr; double* qr_Y = nullptr; double* qr_scr = nullptr; double* qr_scr2 = nullptr;   // TSQR mode (qr.cu)
+    double* qr_W = nullptr; double* qr_scr = nullptr; double* qr_scr2 = nullptr;   // TSQR mode (qr.cu)
     double* qr_stack = nullptr; size_t qr_stack_cap = 0;
-    size_t qr_W_cap = 0, qr_Y_cap = 0, qr_scr_cap = 0, qr_scr2_cap = 0;
+    size_t qr_W_cap = 0, qr_scr_cap = 0, qr_scr2_cap = 0;
     void* train_state = nullptr;     // pb_ensemble_train: work buffers, side stream, captured epoch graph (train.cu)
 };
 void pbi_train_free(pb_ctx* ctx);

@@ -331,32 +331,34 @@ __global__ void __launch_bounds__(QT) qr_panel_kernel(QrPanelArgs a) {
     }
 }
 
-// explicit reflector block of an outer panel: Y (rows x 64, ld 64), zero above the panel and beyond nbo columns
-__global__ void qr_write_y_kernel(const double* __restrict__ W, int64_t ldw, int64_t rows, int J, int nbo,
-                                  double* __restrict__ Y) {
-    const int64_t total = rows * (QNB / 2);
+// After a panel is factored its columns of W hold R (on and above the diagonal, rows 0 .. J + a) and the reflector
+// vectors (below).  Move the R entries to the output and put the explicit unit-lower-trapezoidal form in their place
+// (zeros above, ones on the diagonal): the panel columns of W then ARE the block Y, so that [Y^T Y | Y^T C] is one TN
+// product over W[:, J:] and the update reads Y in place -- no copy of Y, no separate Y^T Y launch.
+__global__ void qr_save_r_make_y_kernel(double* __restrict__ W, int64_t ldw, int J, int nbo, int64_t m,
+                                        double* __restrict__ R, int64_t ldr) {
+    const int64_t total = (int64_t)(J + nbo) * nbo;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = idx / (QNB / 2); const int a0 = (int)(idx % (QNB / 2)) * 2;
-        double2 v = make_double2(0., 0.);
-        if (r >= J) {
-            if (a0 < nbo) v.x = yval(W, ldw, r, J, a0);
-            if (a0 + 1 < nbo) v.y = yval(W, ldw, r, J, a0 + 1);
-        }
-        *reinterpret_cast<double2*>(Y + r * QNB + a0) = v;
+        const int64_t r = idx / nbo; const int a = (int)(idx % nbo);
+        const int64_t d = (int64_t)J + a;
+        if (r > d) continue;
+        double* p = W + r * ldw + d;
+        if (r < m && d < m) R[r * ldr + d] = *p;
+        *p = (r == d) ? 1. : 0.;
     }
 }
 
 // T^T (nbo x nbo lower triangular, ld 64) from tau and S = Y^T Y: the recurrence X_i = tau_i (Z_i - sum_{k<i} S_ki X_k)
 // applied to Z = I (T^-1 = diag(1/tau) + striu(S); tau_i = 0 gives a zero row, i.e. H_i = I).  One CTA, thread = column.
-__global__ void __launch_bounds__(4 * QNB) qr_tt_kernel(const double* __restrict__ S, int nbo, const double* __restrict__ tau,
-                                                        double* __restrict__ Tt) {
+__global__ void __launch_bounds__(4 * QNB) qr_tt_kernel(const double* __restrict__ S, int64_t lds, int nbo,
+                                                        const double* __restrict__ tau, double* __restrict__ Tt) {
     __shared__ double Xs[QNB][QNB + 1];
     const int tid = threadIdx.x, j = tid >> 2, q = tid & 3;      // 4 threads share the k-sum of a column
     for (int e = tid; e < QNB * QNB; e += 4 * QNB) Xs[e / QNB][e % QNB] = 0.;
     __syncthreads();
     for (int i = 0; i < nbo; ++i) {
         double s = 0.;
-        for (int k = j + q; k < i; k += 4) s -= S[k * nbo + i] * Xs[k][j];       // X_kj = 0 for k < j
+        for (int k = j + q; k < i; k += 4) s -= S[k * lds + i] * Xs[k][j];       // X_kj = 0 for k < j
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         if (q == 0 && j < nbo && i >= j) Xs[i][j] = tau[i] * ((i == j ? 1. : 0.) + s);
@@ -625,17 +627,20 @@ int qr_leaf(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, 
 }
 
 // R (m x m upper triangular, ld ldr, rows_out >= m rows written: zero below the triangle) of A (rows x m, lda).
-// Slabs taller than what the staged panel kernel holds (sm_count x 1400 rows) are cut into equal row blocks -- TSQR
-// leaves inside the GPU: R_i = qr(A_i), then the QR of the stacked factors.  The stack adds n_leaves m / rows of the
-// flops (2 % at 1.25 M x 4096), every leaf runs the shared-memory panel path, and the working copy is one leaf, not
-// the whole slab (6.8 GB instead of 41 GB at C5).
+// Slabs whose working copy would exceed 16 GiB are cut into equal row blocks of at most sm_count x 1400 rows -- TSQR
+// leaves inside the GPU: R_i = qr(A_i), then the QR of the stacked factors.  The working copy is then one leaf, not the
+// whole slab (6.8 GB instead of 41 GB at C5), every leaf runs the shared-memory panel path, and the stack adds
+// n_leaves m / rows of the flops (2 % at 1.25 M x 4096).  Measured time-neutral at 1.25 M x 4096 (2.20 vs 2.24 s) and
+// 4 % slower at 250 000 x 4096 (two leaves), hence the memory criterion.
 int pbi_qr_r(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, double* R, int64_t ldr, int64_t rows_out) {
     if (rows <= 0 || m <= 0 || lda < m || ldr < m || rows_out < m) PB_FAIL(ctx, PB_ERR_SHAPE, "tsqr: bad shape");
     if (m > 8192) PB_FAIL(ctx, PB_ERR_SHAPE, "tsqr: %lld columns exceed 8192", (long long)m);
-    static const int leaves_env = getenv("PB_QR_LEAVES") ? atoi(getenv("PB_QR_LEAVES")) : 1;
+    const char* le = getenv("PB_QR_LEAVES");            // 0: never, 1 (default): by the memory criterion, 2: whenever possible
+    const int leaves_env = le ? atoi(le) : 1;
     const int64_t leaf_max = (int64_t)ctx->sm_count * RS_MAX;
     const int64_t n_leaves = (rows + leaf_max - 1) / leaf_max;
-    if (!leaves_env || n_leaves < 2 || rows < 4 * m || n_leaves * m > leaf_max)
+    const bool big = (double)rows * (double)((m + QIB - 1) / QIB * QIB) * 8. > 16. * 1073741824.;
+    if (!(leaves_env == 2 || (leaves_env == 1 && big)) || n_leaves < 2 || rows < 4 * m || n_leaves * m > leaf_max)
         return qr_leaf(ctx, A, rows, m, lda, R, ldr, rows_out);
     PB_TRY(pb_reserve(ctx, &ctx->qr_stack, &ctx->qr_stack_cap, (size_t)n_leaves * m * m));
     const int64_t per = (rows + n_leaves - 1) / n_leaves;
@@ -652,15 +657,15 @@ int qr_leaf(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, 
     const int64_t ldw = mp;
     const int64_t rowsW = std::max(rows, mp);
     PB_TRY(pb_reserve(ctx, &ctx->qr_W, &ctx->qr_W_cap, (size_t)rowsW * ldw));
-    PB_TRY(pb_reserve(ctx, &ctx->qr_Y, &ctx->qr_Y_cap, (size_t)rowsW * QNB));
     const int Gmax = ctx->sm_count;
-    // scratch: tau [mp] | part [2*G*16] | diag [32] | zpart [G*ZE] | zfin [ZE] | Z [64*mp] | S [64*64] | T^T [64*64] 
-    const size_t n_scr = (size_t)mp + 2 * (size_t)Gmax * QIB + 2 * QIB + (size_t)Gmax * ZE + ZE + (size_t)QNB * mp + 2 * QNB * QNB;
+    // scratch: tau [mp] | part [2*G*16] | diag [32] | zpart [G*ZE] | zfin [ZE] | [S | Z] [64*mp] | T^T [64*64]
+    const size_t n_scr = (size_t)mp + 2 * (size_t)Gmax * QIB + 2 * QIB + (size_t)Gmax * ZE + ZE + (size_t)QNB * mp + QNB * QNB;
     PB_TRY(pb_reserve(ctx, &ctx->qr_scr, &ctx->qr_scr_cap, n_scr));
     double* tau = ctx->qr_scr; double* part = tau + mp; double* diag = part + 2 * (size_t)Gmax * QIB;
     double* zpart = diag + 2 * QIB; double* zfin = zpart + (size_t)Gmax * ZE; double* Zb = zfin + ZE;
-    double* Sb = Zb + (size_t)QNB * mp; double* Tt = Sb + QNB * QNB;
-    double* W = ctx->qr_W; double* Y = ctx->qr_Y;
+    double* Tt = Zb + (size_t)QNB * mp;
+    double* W = ctx->qr_W;
+    PB_CUDA(ctx, cudaMemset2DAsync(R, ldr * sizeof(double), 0, m * sizeof(double), rows_out, ctx->stream));
     const int cp_grid = ctx->sm_count * 8;
     qr_copy_pad_kernel<<<cp_grid, 256, 0, ctx->stream>>>(A, lda, rows, m, W, ldw, rowsW);
     PB_LAUNCH_CHECK(ctx);
@@ -677,20 +682,20 @@ int qr_leaf(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, 
         void* args[] = {&pa};
         PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)qr_panel_kernel, dim3(grid), dim3(QT), args, smem, ctx->stream));
         ctx->launches++;
+        qr_save_r_make_y_kernel<<<(unsigned)std::min<int64_t>(cp_grid, ((J + nbo) * nbo + 255) / 256), 256, 0, ctx->stream>>>(
+            W, ldw, (int)J, nbo, m, R, ldr);
+        PB_LAUNCH_CHECK(ctx);
         const int64_t ntrail = mp - J - nbo;
         if (ntrail <= 0) break;
-        qr_write_y_kernel<<<cp_grid, 256, 0, ctx->stream>>>(W, ldw, rowsW, (int)J, nbo, Y);
+        const double* Y = W + J;                                      // the panel columns are the explicit block Y now
+        const int64_t ldz = nbo + ntrail;
+        PB_TRY(pbi_gemm_tn(ctx, Y, ldw, nbo, Y, ldw, ldz, rowsW, Zb, ldz, 0));                    // [Y^T Y | Y^T C]
+        qr_tt_kernel<<<1, 4 * QNB, 0, ctx->stream>>>(Zb, ldz, nbo, tau + J, Tt);
         PB_LAUNCH_CHECK(ctx);
-        PB_TRY(pbi_gemm_tn(ctx, Y, QNB, nbo, Y, QNB, nbo, rowsW, Sb, nbo, 0));                   // S = Y^T Y
-        PB_TRY(pbi_gemm_tn(ctx, Y, QNB, nbo, W + J + nbo, ldw, ntrail, rowsW, Zb, ntrail, 0));   // Z = Y^T C
-        qr_tt_kernel<<<1, 4 * QNB, 0, ctx->stream>>>(Sb, nbo, tau + J, Tt);
+        qr_applyt_kernel<<<(unsigned)((ntrail + QNB - 1) / QNB), QT, 0, ctx->stream>>>(Zb + nbo, ldz, ntrail, Tt, nbo);   // X = T^T Z
         PB_LAUNCH_CHECK(ctx);
-        qr_applyt_kernel<<<(unsigned)((ntrail + QNB - 1) / QNB), QT, 0, ctx->stream>>>(Zb, ntrail, ntrail, Tt, nbo);   // X = T^T Z
-        PB_LAUNCH_CHECK(ctx);
-        PB_TRY(pbi_gemm_nn_sub(ctx, Y, QNB, rowsW, nbo, Zb, ntrail, ntrail, W + J + nbo, ldw));  // C -= Y X
+        PB_TRY(pbi_gemm_nn_sub(ctx, Y, ldw, rowsW, nbo, Zb + nbo, ldz, ntrail, W + J + nbo, ldw)); // C -= Y X
     }
-    qr_extract_r_kernel<<<cp_grid, 256, 0, ctx->stream>>>(W, ldw, m, R, ldr, rows_out);
-    PB_LAUNCH_CHECK(ctx);
     return PB_OK;
 }
 }  // namespace

@@ -167,9 +167,11 @@ def test_pod_ragged_shapes(ctx, mode):
 # ------------------------------------------------------------------ TSQR mode building blocks
 @pytest.mark.parametrize("rows,m", [(700, 130), (64, 64), (100, 1), (33, 70), (5000, 333), (1500, 1000), (4097, 65),
                                     (450000, 24)])
-def test_tsqr_r_factor(ctx, rows, m):
+def test_tsqr_r_factor(ctx, rows, m, monkeypatch):
     """pb_tsqr_r: R is upper triangular, R^T R = A^T A to rounding, and equals LAPACK's R up to row signs.
-    (450 000 rows: taller than one leaf of the staged panel kernel -> three row blocks + the QR of their stack.)"""
+    (450 000 rows with the leaf split forced: three row blocks + the QR of their stacked factors.)"""
+    if rows > 400000:
+        monkeypatch.setenv("PB_QR_LEAVES", "2")       # force the leaf split (by default only above 16 GiB of working copy)
     rng = np.random.default_rng(rows + m)
     A = rng.standard_normal((rows, m))
     Ad, Rd = ctx.to_device(A), ctx.alloc(m, m)

@@ -96,6 +96,19 @@ def test_c2_round_trip_and_pod_sig(ctx, c2):
     assert (s >= 0).all() and 1e-6 < s.mean() < 1e-4              # "Mean pod sig" of the reference run: 1.87e-5
 
 
+def test_dct_known_answer_tsqr_leaves(ctx, monkeypatch):
+    """TSQR with the in-GPU leaf split forced (six row blocks of 1 << 20 rows + the QR of the stacked factors)
+    reproduces the closed-form spectrum and rank."""
+    monkeypatch.setenv("PB_QR_LEAVES", "2")
+    n_h, n_s = 1 << 20, 512
+    Ud = ctx.alloc(n_h, n_s)
+    ctx.check(_lib.lib().pb_dct_lowrank(ctx.h, n_h, n_s, 256, 0.25, 0, n_h, Ud.ptr, Ud.ld))
+    s = 2. ** (-0.25 * np.arange(256))
+    Vd, sig = pod_device(ctx, Ud, 1e-10, 0, "tsqr")
+    assert Vd.shape[1] == wl.dct_rank(s, 1e-10)
+    assert cmp.sigma_error(sig[:150], s[:150]) <= 1e-13
+
+
 @pytest.mark.parametrize("n_h,n_s", [(1 << 20, 1024), (200000, 4096)])
 def test_dct_known_answer_at_scale(ctx, n_h, n_s):
     """U = sum s_k phi_k psi_k^T built in HBM: singular values are exactly s_k = 2^(-k/4), the rank
@@ -104,7 +117,7 @@ def test_dct_known_answer_at_scale(ctx, n_h, n_s):
     Ud = ctx.alloc(n_h, n_s)
     ctx.check(L.pb_dct_lowrank(ctx.h, n_h, n_s, 256, 0.25, 0, n_h, Ud.ptr, Ud.ld))
     s = 2. ** (-0.25 * np.arange(256))
-    for mode in ("tsqr", "gram", "gram2"):      # tsqr: 1 << 20 rows = six leaves + the QR of the stacked factors
+    for mode in ("tsqr", "gram", "gram2"):
         Vd, sig = pod_device(ctx, Ud, 1e-10, 0, mode)
         n_L = wl.dct_rank(s, 1e-10)
         assert Vd.shape[1] == n_L
