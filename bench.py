@@ -164,6 +164,8 @@ def run_gpu(args):
     n_h_loc = N_X * N_Y
     X = w["x_mesh"][:, 1:].T
     U, _, _ = snapshots_device(ctx, "ackley", X, w["mu"], row0=rank * n_h_loc, n_rows=n_h_loc)
+    U.release()                              # first call: table / workspace allocation; time the second
+    U, _, _ = snapshots_device(ctx, "ackley", X, w["mu"], row0=rank * n_h_loc, n_rows=n_h_loc)
     snap_ms = ctx.ms(_lib.T_SNAPSHOTS)
     n_h = n_h_loc * world
 
@@ -330,7 +332,7 @@ def run_gpu(args):
             "stage_ms": {k: statistics.mean(v) for k, v in parts.items()}, "tsqr_mode": tsqr_line,
             "ensemble_predict": ens_line, "ensemble_train": train_lines,
             "snapshot_kernel": {"ms": snap_ms, "gbs": U.nbytes / (snap_ms * 1e-3) / 1e9,
-                                "note": "Ackley field -> U slab in HBM (outside the timed step)"}}
+                                "note": "Ackley field -> U slab in HBM (outside the timed step): table kernels + ackley_indexed_kernel, second call"}}
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:

@@ -118,10 +118,12 @@ __global__ void ackley_indexed_kernel(const double* __restrict__ X, int64_t n_xy
     const double a2 = mul(-20., add(1., mul(.1, m2)));
     const double c1 = mul(-.2, add(1., mul(.1, m1)));
     const double e1 = 2.718281828459045;
+    int last_y = -1; double ey = 0.;          // consecutive nodes of a tensor grid share y: one Ey load per grid row
     for (int64_t r = r_begin; r < r_end; ++r) {
         const int e = (int)(r - r_begin);
         const double t1 = mul(a2, exp(mul(c1, sr[e])));
-        const double t2 = mul(Ex[(int64_t)sx[e] * n_s + col], Ey[(int64_t)sy[e] * n_s + col]);
+        if (sy[e] != last_y) { last_y = sy[e]; ey = Ey[(int64_t)last_y * n_s + col]; }
+        const double t2 = mul(Ex[(int64_t)sx[e] * n_s + col], ey);
         U[r * ldu + col] = add(add(sub(t1, t2), 20.), e1);
     }
 }

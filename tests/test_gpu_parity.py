@@ -459,6 +459,8 @@ def test_error_behaviour(ctx):
         pod_device(ctx, ctx.to_device(np.ones((4, 4))), eps=1.5)
     with pytest.raises(ValueError):
         pod_device(ctx, ctx.to_device(np.zeros((8, 4))), eps=1e-4)                  # zero matrix: no pivot
+    with pytest.raises(ValueError):
+        pod_device(ctx, ctx.to_device(np.zeros((8, 4))), eps=1e-4, mode="gram2")
 
 
 def test_pod_host_pipelined_upload(ctx):
