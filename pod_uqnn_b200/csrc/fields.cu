@@ -101,16 +101,15 @@ __global__ void ackley_indexed_kernel(const double* __restrict__ X, int64_t n_xy
                                       double* __restrict__ U, int64_t ldu) {
     const int64_t col = (int64_t)blockIdx.y * COLS_PER_BLOCK + threadIdx.x;
     const int64_t r_begin = (int64_t)blockIdx.x * NODES_PER_BLOCK;
-    const int64_t r_end = min(n_rows, r_begin + NODES_PER_BLOCK);
+    const int n_here = (int)(min(n_rows, r_begin + NODES_PER_BLOCK) - r_begin);
     __shared__ double sr[NODES_PER_BLOCK];
-    __shared__ int sx[NODES_PER_BLOCK], sy[NODES_PER_BLOCK];
-    for (int e = threadIdx.x; e < NODES_PER_BLOCK; e += blockDim.x) {
-        int64_t r = r_begin + e;
-        if (r < r_end) {
-            double x = X[row0 + r], y = X[n_xyz + row0 + r];
-            sr[e] = sqrt(mul(.5, add(mul(x, x), mul(y, y))));
-            sx[e] = ix[row0 + r]; sy[e] = iy[row0 + r];
-        }
+    __shared__ int64_t sxo[NODES_PER_BLOCK];          // row offset of the node's x entry in the table (ix * n_s)
+    __shared__ int sy[NODES_PER_BLOCK];
+    for (int e = threadIdx.x; e < n_here; e += blockDim.x) {
+        const int64_t r = r_begin + e;
+        double x = X[row0 + r], y = X[n_xyz + row0 + r];
+        sr[e] = sqrt(mul(.5, add(mul(x, x), mul(y, y))));
+        sxo[e] = (int64_t)ix[row0 + r] * n_s; sy[e] = iy[row0 + r];
     }
     __syncthreads();
     if (col >= n_s) return;
@@ -118,13 +117,18 @@ __global__ void ackley_indexed_kernel(const double* __restrict__ X, int64_t n_xy
     const double a2 = mul(-20., add(1., mul(.1, m2)));
     const double c1 = mul(-.2, add(1., mul(.1, m1)));
     const double e1 = 2.718281828459045;
+    // the loop is bound by instruction issue (exp is ~35 instructions): keep the index arithmetic to one pointer
+    // bump and one table offset per element
+    const double* __restrict__ exc = Ex + col;
+    const double* __restrict__ eyc = Ey + col;
+    double* __restrict__ up = U + r_begin * ldu + col;
     int last_y = -1; double ey = 0.;          // consecutive nodes of a tensor grid share y: one Ey load per grid row
-    for (int64_t r = r_begin; r < r_end; ++r) {
-        const int e = (int)(r - r_begin);
+#pragma unroll 4
+    for (int e = 0; e < n_here; ++e, up += ldu) {
         const double t1 = mul(a2, exp(mul(c1, sr[e])));
-        if (sy[e] != last_y) { last_y = sy[e]; ey = Ey[(int64_t)last_y * n_s + col]; }
-        const double t2 = mul(Ex[(int64_t)sx[e] * n_s + col], ey);
-        U[r * ldu + col] = add(add(sub(t1, t2), 20.), e1);
+        if (sy[e] != last_y) { last_y = sy[e]; ey = eyc[(int64_t)last_y * n_s]; }
+        const double t2 = mul(exc[sxo[e]], ey);
+        *up = add(add(sub(t1, t2), 20.), e1);
     }
 }
 

@@ -293,10 +293,29 @@ class PodnnModel:
         members, layers, soft_0, norm, nb = self._ensemble_args()
         vm, vs = ensemble_predict_device(ctx, members, layers, X_v, soft_0, norm, nb)
         N = vm.shape[0]
-        Um, Us = ctx.alloc(self.n_h, N), ctx.alloc(self.n_h, N)
-        ctx.check(_lib.lib().pb_predict_U(ctx.h, Vd.ptr, Vd.ld, self.n_h, self.n_L, vm.ptr, vs.ptr, N,
-                                          int(samples) if monte_carlo else 0, int(seed), Um.ptr, Us.ptr, Um.ld))
-        return Um.download(), Us.download()
+        U_pred, U_pred_sig = np.empty((self.n_h, N)), np.empty((self.n_h, N))
+        # the (n_h x N) outputs are streamed to the host in column tiles so that the device buffers stay bounded
+        # (C4 shape: n_h = 75 000 -- 100 000 points would need 2 x 60 GB of HBM in one piece)
+        for j0, j1, Um, Us, t in self._u_tiles(N):
+            ctx.check(_lib.lib().pb_predict_U(ctx.h, Vd.ptr, Vd.ld, self.n_h, self.n_L, vm.ptr + 8 * j0 * self.n_L,
+                                              vs.ptr + 8 * j0 * self.n_L, j1 - j0, int(samples) if monte_carlo else 0,
+                                              int(seed) + 7919 * t, Um.ptr, Us.ptr, Um.ld))
+            U_pred[:, j0:j1], U_pred_sig[:, j0:j1] = Um.download(), Us.download()
+        return U_pred, U_pred_sig
+
+    U_TILE_BYTES = 4 << 30          # per device output buffer of predict / predict_mc
+
+    def _u_tiles(self, N):
+        """Column tiles [j0, j1) of an (n_h x N) U-level output with a pair of device buffers for each tile."""
+        cols = int(max(1, min(N, self.U_TILE_BYTES // (8 * self.n_h))))
+        bufs = {}
+        for t, j0 in enumerate(range(0, N, cols)):
+            j1 = min(N, j0 + cols)
+            if (j1 - j0) not in bufs:
+                bufs.clear()
+                bufs[j1 - j0] = (self.ctx.alloc(self.n_h, j1 - j0), self.ctx.alloc(self.n_h, j1 - j0))
+            Um, Us = bufs[j1 - j0]
+            yield j0, j1, Um, Us, t
 
     def predict_mc(self, X_v, samples=100, *, monte_carlo=False, seed=0):
         """podnnmodel.py:344-364: per-member U-level prediction (predict_dist :330-342), Gaussian mixture
@@ -307,15 +326,16 @@ class PodnnModel:
         Xd = ctx.to_device(np.asarray(X_v, dtype=np.float64).reshape(-1, layers[0]))
         N = Xd.shape[0]
         U_sum, U_m2 = np.zeros((self.n_h, N)), np.zeros((self.n_h, N))
-        Um, Us = ctx.alloc(self.n_h, N), ctx.alloc(self.n_h, N)
         print(f"Ensembling {len(members)} predictions...")
         for i, w in enumerate(members):
             vm, vs = ensemble_predict_device(ctx, [w], layers, Xd, soft_0, norm, nb)
-            ctx.check(_lib.lib().pb_predict_U(ctx.h, Vd.ptr, Vd.ld, self.n_h, self.n_L, vm.ptr, vs.ptr, N,
-                                              int(samples) if monte_carlo else 0, int(seed) + i, Um.ptr, Us.ptr, Um.ld))
-            U_i, sig_i = Um.download(), Us.download()
-            U_sum += U_i
-            U_m2 += sig_i ** 2 + U_i ** 2
+            for j0, j1, Um, Us, t in self._u_tiles(N):
+                ctx.check(_lib.lib().pb_predict_U(ctx.h, Vd.ptr, Vd.ld, self.n_h, self.n_L, vm.ptr + 8 * j0 * self.n_L,
+                                                  vs.ptr + 8 * j0 * self.n_L, j1 - j0, int(samples) if monte_carlo else 0,
+                                                  int(seed) + i + 7919 * t, Um.ptr, Us.ptr, Um.ld))
+                U_i, sig_i = Um.download(), Us.download()
+                U_sum[:, j0:j1] += U_i
+                U_m2[:, j0:j1] += sig_i ** 2 + U_i ** 2
         U_pred = U_sum / len(members)
         U_pred_sig = np.sqrt(U_m2 / len(members) - U_pred ** 2)
         if self.pod_sig is not None:

@@ -77,6 +77,15 @@ def test_predict_path(ctx, tmp_path):
     assert cmp.rel_err(Um, Umr) <= cmp.TOL_ENSEMBLE_REL and cmp.rel_err(Usm, Usmr) <= cmp.TOL_ENSEMBLE_REL
     U_mc, Us_mc = model.predict(X, samples=400, monte_carlo=True, seed=3)
     assert np.all(np.abs(U_mc - Ur) <= 6. * Usr / np.sqrt(400) + 1e-12) and np.max(np.abs(Us_mc / Usr - 1.)) < 0.3
+    # U-level outputs streamed in column tiles (32 + 32 + 11 points here) equal the one-piece result
+    model.U_TILE_BYTES = 8 * model.n_h * 32
+    U_t, Us_t = model.predict(X)
+    assert np.array_equal(U_t, U_pred) and np.array_equal(Us_t, U_sig)
+    Um_t, Usm_t = model.predict_mc(X)
+    assert np.array_equal(Um_t, Um) and np.array_equal(Usm_t, Usm)
+    U_mc_t, Us_mc_t = model.predict(X, samples=400, monte_carlo=True, seed=3)
+    assert np.all(np.abs(U_mc_t - Ur) <= 6. * Usr / np.sqrt(400) + 1e-12)
+    del model.U_TILE_BYTES
     # save / load round trip of the ensemble (npz weights + the reference's params tuple)
     model.save_model()
     m2 = PodnnModel.load(str(tmp_path), ctx=ctx)
