@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(QT) qrcp_kernel(QrcpArgs a) {
         grid.sync();
         bv = -1.; bi = 0x7fffffff;
         for (int e = tid; e < G; e += QT) {
-            const double v = a.cand_val[par * G + e]; const int k = a.cand_idx[par * G + e];
+            const double v = __ldcg(a.cand_val + par * G + e); const int k = __ldcg(a.cand_idx + par * G + e);
             if (v > bv || (v == bv && k < bi)) { bv = v; bi = k; }
         }
         block_argmax(bv, bi, rv, ri);
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(QT) qrcp_kernel(QrcpArgs a) {
 
         // ---- reflector from column p, rows c..m-1
         const int len = m - c;
-        for (int r = tid; r < len; r += QT) xs[r] = At[(int64_t)(c + r) * ldm + p];
+        for (int r = tid; r < len; r += QT) xs[r] = __ldcg(At + (int64_t)(c + r) * ldm + p);    // written by the column's owner CTA: read through L2
         __syncthreads();
         double part = 0.;
         for (int r = 1 + tid; r < len; r += QT) part += xs[r] * xs[r];
