@@ -108,7 +108,7 @@ int pbi_jacobi_factor(pb_ctx* ctx, double* At, int64_t m, int r, const double* s
 int pbi_qr_r(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, double* R, int64_t ldr, int64_t rows_out);
 int pbi_qr_load_factor(pb_ctx* ctx, const double* R, int64_t ldr, int64_t m, double* At, int64_t ldm, int64_t rows_total);
 int pbi_qrcp_factor(pb_ctx* ctx, double* At, int64_t m, int64_t ldm, int64_t rows_total, double tol_rel, int* r_out);
-// Y (rows x k, ldy) -= A (rows x m, lda) B (m x k, ldb)
+// Y (rows x k, ldy) += A (rows x m, lda) B (m x k, ldb), in place
 int pbi_gemm_nn_sub(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m, const double* B, int64_t ldb,
                     int64_t k, double* Y, int64_t ldy);
 // n_L from descending lambdas = sig^2 (pod.py:22-32)

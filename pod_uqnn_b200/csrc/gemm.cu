@@ -232,9 +232,9 @@ gemm_nn_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int m,
             for (int u = 0; u < TNN; ++u) {
                 int64_t j = j0 + wn * WN + u * 8 + 2 * lk;
                 if (Y) {
-                    if (subtract) {          // Y -= A B (trailing update of the blocked Householder QR, qr.cu)
-                        if (j < k)     Y[h * ldy + j]     -= acc[t][u][0];
-                        if (j + 1 < k) Y[h * ldy + j + 1] -= acc[t][u][1];
+                    if (subtract) {          // Y += A B (trailing update of the blocked Householder QR, qr.cu: B = -X)
+                        if (j < k)     Y[h * ldy + j]     += acc[t][u][0];
+                        if (j + 1 < k) Y[h * ldy + j + 1] += acc[t][u][1];
                     } else {
                         if (j < k)     Y[h * ldy + j]     = acc[t][u][0];
                         if (j + 1 < k) Y[h * ldy + j + 1] = acc[t][u][1];
@@ -280,8 +280,9 @@ recon_strip_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int 
                    const double* __restrict__ B, int64_t ldb, int64_t n,
                    double* __restrict__ Y, int64_t ldy,
                    const double* U, int64_t ldu, double* __restrict__ sig_out, int subtract) {
-    // subtract != 0: Y = U - A B with U == Y allowed (the in-place trailing update C -= Y X of the blocked
-    // Householder QR, qr.cu): the U tile of a column tile is read from its staged copy before the tile is written.
+    // subtract != 0: Y = U + A B with U == Y allowed (the in-place trailing update C -= Y X of the blocked
+    // Householder QR, qr.cu, which passes B = -X): the accumulators start from the staged copy of the U tile, so the
+    // epilogue is stores only.
     // MS = rows per strip: 32 for the HBM-bound reconstruction; 64 for the QR update (K = 64 is compute bound and a
     // 32-row strip re-reads the B tiles from L2 twice as often as it can afford)
     constexpr int NT = 64;
@@ -324,10 +325,21 @@ recon_strip_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int 
         if (t + STG - 1 < n_tiles) prefetch(t + STG - 1);
         cp_async_commit();
         double acc[RA][2][2];
+        const double* us = Us + (t % STG) * MS * PU;
+        if (subtract) {      // in-place update: the accumulators start from the staged C tile, the caller passes B = -X
 #pragma unroll
-        for (int a = 0; a < RA; ++a)
+            for (int a = 0; a < RA; ++a)
 #pragma unroll
-            for (int u = 0; u < 2; ++u) { acc[a][u][0] = 0.; acc[a][u][1] = 0.; }
+                for (int u = 0; u < 2; ++u) {
+                    const double2 uv = *reinterpret_cast<const double2*>(us + (wm * (MS / 2) + a * 8 + lg) * PU + wn * 16 + u * 8 + 2 * lk);
+                    acc[a][u][0] = uv.x; acc[a][u][1] = uv.y;
+                }
+        } else {
+#pragma unroll
+            for (int a = 0; a < RA; ++a)
+#pragma unroll
+                for (int u = 0; u < 2; ++u) { acc[a][u][0] = 0.; acc[a][u][1] = 0.; }
+        }
         const double* as = As + (wm * (MS / 2) + lg) * PA + lk;
         const double* bs = Bs + (t % STG) * KP * PB + wn * 16 + lg;
 #pragma unroll
@@ -345,7 +357,6 @@ recon_strip_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int 
             }
         }
         const int64_t j0 = (int64_t)t * NT;
-        const double* us = Us + (t % STG) * MS * PU;
 #pragma unroll
         for (int a = 0; a < RA; ++a) {
             const int rl = wm * (MS / 2) + a * 8 + lg;
@@ -355,10 +366,6 @@ recon_strip_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int 
             for (int u = 0; u < 2; ++u) {
                 const int cl = wn * 16 + u * 8 + 2 * lk;
                 const int64_t j = j0 + cl;
-                if (subtract) {
-                    const double2 uv = *reinterpret_cast<const double2*>(us + rl * PU + cl);
-                    acc[a][u][0] = uv.x - acc[a][u][0]; acc[a][u][1] = uv.y - acc[a][u][1];
-                }
                 if (Y) {
                     if (y_vec && j + 1 < n) *reinterpret_cast<double2*>(Y + h * ldy + j) = make_double2(acc[a][u][0], acc[a][u][1]);
                     else { if (j < n) Y[h * ldy + j] = acc[a][u][0]; if (j + 1 < n) Y[h * ldy + j + 1] = acc[a][u][1]; }
@@ -611,6 +618,7 @@ int pbi_gemm_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t
     return PB_OK;
 }
 
+// Y += A * B in place (the QR trailing update passes B = -X)
 int pbi_gemm_nn_sub(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m, const double* B, int64_t ldb,
                     int64_t k, double* Y, int64_t ldy) {
     if (rows <= 0 || m <= 0 || k <= 0) PB_FAIL(ctx, PB_ERR_SHAPE, "gemm_nn_sub: bad shape");

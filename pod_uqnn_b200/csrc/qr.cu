@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(4 * QNB) qr_tt_kernel(const double* __restrict
     }
 }
 
-// X = T^T Z in place for a tile of 64 trailing columns per CTA
+// -X = -T^T Z in place for a tile of 64 trailing columns per CTA
 __global__ void __launch_bounds__(QT) qr_applyt_kernel(double* __restrict__ Z, int64_t ldz, int64_t ncols,
                                                        const double* __restrict__ Tt, int nbo) {
     __shared__ double Zs[QNB][QNB + 1];
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(QT) qr_applyt_kernel(double* __restrict__ Z, i
         int k = 0;
         for (; k + 1 <= i; k += 2) { s0 += Tt[i * QNB + k] * Zs[k][jj]; s1 += Tt[i * QNB + k + 1] * Zs[k + 1][jj]; }
         if (k <= i) s0 += Tt[i * QNB + k] * Zs[k][jj];
-        Z[(int64_t)i * ldz + j0 + jj] = s0 + s1;
+        Z[(int64_t)i * ldz + j0 + jj] = -(s0 + s1);            // -X: the update kernel accumulates C += Y (-X)
     }
 }
 
@@ -555,6 +555,7 @@ __global__ void __launch_bounds__(QT) qrcp_kernel(QrcpArgs a) {
             double acc[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) acc[q] = 0.;
+#pragma unroll 4
             for (int r = c + 1 + tid; r < m; r += QT) {
                 const double xr = xs[r - c];
                 const double2* pp = reinterpret_cast<const double2*>(At + (int64_t)r * ldm + k0);
@@ -574,6 +575,7 @@ __global__ void __launch_bounds__(QT) qrcp_kernel(QrcpArgs a) {
             for (int q = 0; q < 8; ++q) w[q] = wsh[q];
 #pragma unroll
             for (int q = 0; q < 8; ++q) acc[q] = 0.;
+#pragma unroll 4
             for (int r = c + 1 + tid; r < m; r += QT) {
                 const double tv = tau * (xs[r - c] * scale);
                 double* pr = At + (int64_t)r * ldm + k0;
@@ -696,7 +698,7 @@ int qr_leaf(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, 
         PB_LAUNCH_CHECK(ctx);
         qr_applyt_kernel<<<(unsigned)((ntrail + QNB - 1) / QNB), QT, 0, ctx->stream>>>(Zb + nbo, ldz, ntrail, Tt, nbo);   // X = T^T Z
         PB_LAUNCH_CHECK(ctx);
-        PB_TRY(pbi_gemm_nn_sub(ctx, Y, ldw, rowsW, nbo, Zb + nbo, ldz, ntrail, W + J + nbo, ldw)); // C -= Y X
+        PB_TRY(pbi_gemm_nn_sub(ctx, Y, ldw, rowsW, nbo, Zb + nbo, ldz, ntrail, W + J + nbo, ldw)); // C += Y (-X)
     }
     return PB_OK;
 }
