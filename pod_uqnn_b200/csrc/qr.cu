@@ -555,7 +555,6 @@ __global__ void __launch_bounds__(QT) qrcp_kernel(QrcpArgs a) {
             double acc[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) acc[q] = 0.;
-#pragma unroll 4
             for (int r = c + 1 + tid; r < m; r += QT) {
                 const double xr = xs[r - c];
                 const double2* pp = reinterpret_cast<const double2*>(At + (int64_t)r * ldm + k0);
@@ -575,7 +574,6 @@ __global__ void __launch_bounds__(QT) qrcp_kernel(QrcpArgs a) {
             for (int q = 0; q < 8; ++q) w[q] = wsh[q];
 #pragma unroll
             for (int q = 0; q < 8; ++q) acc[q] = 0.;
-#pragma unroll 4
             for (int r = c + 1 + tid; r < m; r += QT) {
                 const double tv = tau * (xs[r - c] * scale);
                 double* pr = At + (int64_t)r * ldm + k0;
