@@ -45,16 +45,52 @@ __device__ __forceinline__ double yval(const double* __restrict__ W, int64_t ldw
     return r > d ? W[r * ldw + d] : (r == d ? 1. : 0.);
 }
 
-// sum of v[0..16) over the CTA, result in out[0..16) (shared); fixed order
+// sum of v[0..16) over the CTA, result in out[0..16) (shared); fixed order.  Warp stage: a butterfly that halves the
+// number of values a lane carries at every step (8 + 4 + 2 + 1 + 1 = 16 exchanges instead of 16 x 5): after it lane l
+// holds the warp sum of value (l >> 1) & 15 ... see the index algebra below.
 __device__ __forceinline__ void block_sum16(double (&v)[QIB], double (*red)[QIB], double* out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // stage with xor 16: lanes with bit 4 clear keep values 0..7, the others 8..15
+    double a8[8];
+    {
+        const bool up = lane & 16;
 #pragma unroll
-    for (int k = 0; k < QIB; ++k) {
-        double s = v[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) red[warp][k] = s;
+        for (int k = 0; k < 8; ++k) {
+            const double send = up ? v[k] : v[k + 8];
+            const double keep = up ? v[k + 8] : v[k];
+            a8[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
     }
+    double a4[4];
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double send = up ? a8[k] : a8[k + 4];
+            const double keep = up ? a8[k + 4] : a8[k];
+            a4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    double a2[2];
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const double send = up ? a4[k] : a4[k + 2];
+            const double keep = up ? a4[k + 2] : a4[k];
+            a2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    double a1;
+    {
+        const bool up = lane & 2;
+        const double send = up ? a2[0] : a2[1];
+        const double keep = up ? a2[1] : a2[0];
+        a1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+    // lane l now holds the warp sum of value index 8 b4 + 4 b3 + 2 b2 + b1 (b_i = bit i of l)
+    if ((lane & 1) == 0) red[warp][((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = a1;
     __syncthreads();
     if (tid < QIB) {
         double s = 0.;
@@ -78,7 +114,51 @@ struct QrPanelArgs {
 };
 constexpr int QP = QIB + 2;                  // shared-memory row pitch: 16-byte aligned, conflict-free double2 access
 
-__global__ void __launch_bounds__(QT) qr_panel_kernel(QrPanelArgs a) {
+// Row pass of column step C of an inner panel (C is a compile-time constant: no predicate / select chains in the loop,
+// only the 16-byte chunks that hold columns >= C are touched).  Applies the reflector to my rows, stores v in column C,
+// accumulates the partial dot products of column C + 1 with the columns to its right (rows below the next diagonal row)
+// and lets the owner of the next diagonal row publish it.
+template <int C>
+__device__ __forceinline__ void qr_row_pass(double* __restrict__ W, int64_t ldw, double* Ps, int use_smem, int c0, int64_t lo,
+                                            int64_t hi, int64_t d, double beta, double tau, double scale,
+                                            const double* __restrict__ gsh, const double* __restrict__ dsh,
+                                            double* __restrict__ diag_next, double (&g)[QIB], int tid) {
+    constexpr int K0 = C / 2;                       // first 16-byte chunk that holds a column >= C
+    double w[QIB];
+#pragma unroll
+    for (int k = 0; k < QIB; ++k) w[k] = k > C ? dsh[k] + gsh[k] * scale : 0.;     // v^T (column k)
+    const int64_t rb = lo > d ? lo : d;
+    for (int64_t r = rb + tid; r < hi; r += QT) {
+        double x[QIB];
+        double2* p = use_smem ? reinterpret_cast<double2*>(Ps + (size_t)(r - lo) * QP) : reinterpret_cast<double2*>(W + r * ldw + c0);
+#pragma unroll
+        for (int k = K0; k < QIB / 2; ++k) { double2 v = p[k]; x[2 * k] = v.x; x[2 * k + 1] = v.y; }
+        if (r == d) {
+            x[C] = beta;
+#pragma unroll
+            for (int k = C + 1; k < QIB; ++k) x[k] -= tau * w[k];
+        } else {
+            const double v = x[C] * scale, tv = tau * v;
+            x[C] = v;
+#pragma unroll
+            for (int k = C + 1; k < QIB; ++k) x[k] -= tv * w[k];
+            if (C + 1 < QIB) {
+                if (r == d + 1) {
+#pragma unroll
+                    for (int k = C + 1; k < QIB; ++k) diag_next[k] = x[k];
+                } else {
+                    const double xn = x[C + 1 < QIB ? C + 1 : C];
+#pragma unroll
+                    for (int k = C + 1; k < QIB; ++k) g[k] += xn * x[k];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = K0; k < QIB / 2; ++k) p[k] = make_double2(x[2 * k], x[2 * k + 1]);
+    }
+}
+
+__global__ void __launch_bounds__(QT, 1) qr_panel_kernel(QrPanelArgs a) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) double Ps[];            // the staged inner panel (use_smem), pitch QP
     __shared__ double red[QT / 32][QIB];
@@ -95,6 +175,13 @@ __global__ void __launch_bounds__(QT) qr_panel_kernel(QrPanelArgs a) {
     const int64_t lo = (int64_t)a.J + (int64_t)b * rpc;
     const int64_t hi = lo < a.rows ? (lo + rpc < a.rows ? lo + rpc : a.rows) : lo;
     int par = 0;
+#ifdef PB_QR_TIMING
+    long long tq[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t0q, t1q;
+#define TQ(i) do { t1q = clock64(); tq[i] += t1q - t0q; t0q = t1q; } while (0)
+    t0q = clock64();
+#else
+#define TQ(i) do { } while (0)
+#endif
 
     for (int i0 = 0; i0 < a.nbo; i0 += QIB) {
         const int c0 = a.J + i0;
@@ -125,7 +212,9 @@ __global__ void __launch_bounds__(QT) qr_panel_kernel(QrPanelArgs a) {
             block_sum16(g, red, outsh);
             if (tid < QIB) a.part[((size_t)par * G + b) * QIB + tid] = outsh[tid];
         }
+        TQ(0);
         grid.sync();
+        TQ(1);
 
         for (int c = 0; c < QIB; ++c) {
             const int64_t d = (int64_t)c0 + c;
@@ -144,6 +233,7 @@ __global__ void __launch_bounds__(QT) qr_panel_kernel(QrPanelArgs a) {
                 }
                 __syncthreads();
             }
+            TQ(2);
             // ---- reflector (LAPACK dlarfg): beta = -sign(alpha) hypot(alpha, xnorm), tau = (beta - alpha) / beta
             const double alpha = dsh[c], xn2 = gsh[c];
             double beta = alpha, tau = 0., scale = 0.;
@@ -152,53 +242,27 @@ __global__ void __launch_bounds__(QT) qr_panel_kernel(QrPanelArgs a) {
                 tau = (beta - alpha) / beta;
                 scale = 1. / (alpha - beta);
             }
-            double w[QIB];
-#pragma unroll
-            for (int k = 0; k < QIB; ++k) w[k] = dsh[k] + gsh[k] * scale;     // v^T (column k), k > c
             if (tid == 0) { tau_sh[c] = tau; if (b == 0) a.tau[i0 + c] = tau; }
             // ---- update my rows; accumulate the partials of column c + 1
             double g[QIB];
 #pragma unroll
             for (int k = 0; k < QIB; ++k) g[k] = 0.;
-            const int64_t rb = lo > d ? lo : d;
-            for (int64_t r = rb + tid; r < hi; r += QT) {
-                double x[QIB];
-                double2* p = a.use_smem ? reinterpret_cast<double2*>(Ps + (size_t)(r - lo) * QP)
-                                        : reinterpret_cast<double2*>(W + r * ldw + c0);
-#pragma unroll
-                for (int k = 0; k < QIB / 2; ++k) { double2 v = p[k]; x[2 * k] = v.x; x[2 * k + 1] = v.y; }
-                if (r == d) {
-#pragma unroll
-                    for (int k = 0; k < QIB; ++k) { if (k == c) x[k] = beta; else if (k > c) x[k] -= tau * w[k]; }
-                } else {
-                    double xc = 0.;
-#pragma unroll
-                    for (int k = 0; k < QIB; ++k) if (k == c) xc = x[k];
-                    const double v = xc * scale, tv = tau * v;
-                    double xn = 0.;
-#pragma unroll
-                    for (int k = 0; k < QIB; ++k) {
-                        if (k == c) x[k] = v; else if (k > c) x[k] -= tv * w[k];
-                        if (k == c + 1) xn = x[k];
-                    }
-                    if (c + 1 < QIB) {
-                        if (r == d + 1) {
-#pragma unroll
-                            for (int k = 0; k < QIB; ++k) if (k > c) a.diag[(par ^ 1) * QIB + k] = x[k];
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < QIB; ++k) if (k > c) g[k] += xn * x[k];
-                        }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < QIB / 2; ++k) p[k] = make_double2(x[2 * k], x[2 * k + 1]);
+            double* dn = a.diag + (par ^ 1) * QIB;
+#define PB_QR_CASE(CC) case CC: qr_row_pass<CC>(W, ldw, Ps, a.use_smem, c0, lo, hi, d, beta, tau, scale, gsh, dsh, dn, g, tid); break;
+            switch (c) {
+                PB_QR_CASE(0) PB_QR_CASE(1) PB_QR_CASE(2) PB_QR_CASE(3) PB_QR_CASE(4) PB_QR_CASE(5) PB_QR_CASE(6) PB_QR_CASE(7)
+                PB_QR_CASE(8) PB_QR_CASE(9) PB_QR_CASE(10) PB_QR_CASE(11) PB_QR_CASE(12) PB_QR_CASE(13) PB_QR_CASE(14)
+                default: qr_row_pass<15>(W, ldw, Ps, a.use_smem, c0, lo, hi, d, beta, tau, scale, gsh, dsh, dn, g, tid); break;
             }
+#undef PB_QR_CASE
+            TQ(3);
             if (c + 1 < QIB) {
                 block_sum16(g, red, outsh);
                 if (tid < QIB) a.part[((size_t)(par ^ 1) * G + b) * QIB + tid] = outsh[tid];
                 par ^= 1;
+                TQ(4);
                 grid.sync();        // (a flag-per-CTA exchange instead of this barrier measured slower: 1.14 vs 0.83 ms per panel)
+                TQ(1);
             }
         }
         par ^= 1;
@@ -214,6 +278,7 @@ __global__ void __launch_bounds__(QT) qr_panel_kernel(QrPanelArgs a) {
             __syncthreads();
         }
 
+        TQ(9);
         // ---- apply the inner block reflector to the rest of the outer panel
         const int ncols = a.nbo - i0 - QIB;
         if (ncols > 0) {                                           // uniform
@@ -255,6 +320,7 @@ __global__ void __launch_bounds__(QT) qr_panel_kernel(QrPanelArgs a) {
                         }
                     }
             }
+            TQ(6);
             // CTA sum in warp order (fixed), straight into Zs
             for (int e = tid; e < ZE; e += QT) Zs[e] = 0.;
             __syncthreads();
@@ -288,6 +354,7 @@ __global__ void __launch_bounds__(QT) qr_panel_kernel(QrPanelArgs a) {
             grid.sync();
             for (int e = tid; e < ZE; e += QT) Zs[e] = __ldcg(a.zfin + e);
             __syncthreads();
+            TQ(7);
             // X = T^T Z: X_i = tau_i (Z_i - sum_{k<i} S_ki X_k), S = striu(Y^T Y) = Zs[:, 0:16]
             if (tid < ncols) {
                 for (int i = 0; i < QIB; ++i) {
@@ -297,6 +364,7 @@ __global__ void __launch_bounds__(QT) qr_panel_kernel(QrPanelArgs a) {
                 }
             }
             __syncthreads();
+            TQ(8);
             // C -= Y X on my rows: two 8-row groups per warp iteration
             for (int64_t r0 = lo2 + 8 * warp; r0 < hi; r0 += 16 * (QT / 32)) {
                 double af[2][4];
@@ -328,7 +396,13 @@ __global__ void __launch_bounds__(QT) qr_panel_kernel(QrPanelArgs a) {
             }
             __syncthreads();
         }
+        TQ(5);
     }
+#ifdef PB_QR_TIMING
+    if (tid == 0 && (b == 0 || b == G / 2) && a.J == 256)
+        printf("cta %d J %d: prime %lld  gridsync %lld  gather %lld  rowpass %lld  blocksum+publish %lld  writeback %lld | apply: zpass %lld  reduce+2syncs %lld  solve %lld  update %lld (cycles)\n", b, a.J,
+               tq[0], tq[1], tq[2], tq[3], tq[4], tq[9], tq[6], tq[7], tq[8], tq[5]);
+#endif
 }
 
 // After a panel is factored its columns of W hold R (on and above the diagonal, rows 0 .. J + a) and the reflector
