@@ -423,19 +423,28 @@ __global__ void qr_save_r_make_y_kernel(double* __restrict__ W, int64_t ldw, int
 }
 
 // T^T (nbo x nbo lower triangular, ld 64) from tau and S = Y^T Y: the recurrence X_i = tau_i (Z_i - sum_{k<i} S_ki X_k)
-// applied to Z = I (T^-1 = diag(1/tau) + striu(S); tau_i = 0 gives a zero row, i.e. H_i = I).  One CTA, thread = column.
+// applied to Z = I (T^-1 = diag(1/tau) + striu(S); tau_i = 0 gives a zero row, i.e. H_i = I).  One CTA; 4 threads share the
+// k-sum of a column; S is staged in shared memory (its loads were the critical path of the 64 serial steps).
 __global__ void __launch_bounds__(4 * QNB) qr_tt_kernel(const double* __restrict__ S, int64_t lds, int nbo,
                                                         const double* __restrict__ tau, double* __restrict__ Tt) {
-    __shared__ double Xs[QNB][QNB + 1];
-    const int tid = threadIdx.x, j = tid >> 2, q = tid & 3;      // 4 threads share the k-sum of a column
-    for (int e = tid; e < QNB * QNB; e += 4 * QNB) Xs[e / QNB][e % QNB] = 0.;
+    extern __shared__ __align__(16) double tts[];
+    double (*Xs)[QNB + 1] = reinterpret_cast<double (*)[QNB + 1]>(tts);
+    double (*Ss)[QNB + 1] = reinterpret_cast<double (*)[QNB + 1]>(tts + QNB * (QNB + 1));
+    __shared__ double ts[QNB];
+    const int tid = threadIdx.x, j = tid >> 2, q = tid & 3;
+    for (int e = tid; e < QNB * QNB; e += 4 * QNB) {
+        const int i = e / QNB, c = e % QNB;
+        Xs[i][c] = 0.;
+        Ss[c][i] = (i < nbo && c < nbo) ? S[(int64_t)i * lds + c] : 0.;        // transposed: Ss[i][k] = S_ki
+    }
+    if (tid < QNB) ts[tid] = tid < nbo ? tau[tid] : 0.;
     __syncthreads();
     for (int i = 0; i < nbo; ++i) {
         double s = 0.;
-        for (int k = j + q; k < i; k += 4) s -= S[k * lds + i] * Xs[k][j];       // X_kj = 0 for k < j
+        for (int k = j + q; k < i; k += 4) s -= Ss[i][k] * Xs[k][j];             // X_kj = 0 for k < j
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (q == 0 && j < nbo && i >= j) Xs[i][j] = tau[i] * ((i == j ? 1. : 0.) + s);
+        if (q == 0 && j < nbo && i >= j) Xs[i][j] = ts[i] * ((i == j ? 1. : 0.) + s);
         __syncwarp();
     }
     __syncthreads();
@@ -445,24 +454,28 @@ __global__ void __launch_bounds__(4 * QNB) qr_tt_kernel(const double* __restrict
     }
 }
 
-// -X = -T^T Z in place for a tile of 64 trailing columns per CTA
+// -X = -T^T Z in place for a tile of QAT trailing columns per CTA (narrow tiles: the product is tiny, the point is to
+// spread it over enough CTAs)
+constexpr int QAT = 16;
 __global__ void __launch_bounds__(QT) qr_applyt_kernel(double* __restrict__ Z, int64_t ldz, int64_t ncols,
                                                        const double* __restrict__ Tt, int nbo) {
-    __shared__ double Zs[QNB][QNB + 1];
+    __shared__ double Zs[QNB][QAT + 1];
+    __shared__ double Ts[QNB][QNB + 1];
     const int tid = threadIdx.x;
-    const int64_t j0 = (int64_t)blockIdx.x * QNB;
-    for (int e = tid; e < QNB * QNB; e += QT) {
-        const int k = e / QNB, jj = e % QNB;
+    const int64_t j0 = (int64_t)blockIdx.x * QAT;
+    for (int e = tid; e < QNB * QAT; e += QT) {
+        const int k = e / QAT, jj = e % QAT;
         Zs[k][jj] = (k < nbo && j0 + jj < ncols) ? Z[(int64_t)k * ldz + j0 + jj] : 0.;
     }
+    for (int e = tid; e < QNB * QNB; e += QT) Ts[e / QNB][e % QNB] = Tt[e];
     __syncthreads();
-    const int jj = tid % QNB, part = tid / QNB;
+    const int jj = tid % QAT, part = tid / QAT;               // 16 row groups
     if (j0 + jj >= ncols) return;
-    for (int i = part; i < nbo; i += QT / QNB) {
+    for (int i = part; i < nbo; i += QT / QAT) {
         double s0 = 0., s1 = 0.;
         int k = 0;
-        for (; k + 1 <= i; k += 2) { s0 += Tt[i * QNB + k] * Zs[k][jj]; s1 += Tt[i * QNB + k + 1] * Zs[k + 1][jj]; }
-        if (k <= i) s0 += Tt[i * QNB + k] * Zs[k][jj];
+        for (; k + 1 <= i; k += 2) { s0 += Ts[i][k] * Zs[k][jj]; s1 += Ts[i][k + 1] * Zs[k + 1][jj]; }
+        if (k <= i) s0 += Ts[i][k] * Zs[k][jj];
         Z[(int64_t)i * ldz + j0 + jj] = -(s0 + s1);            // -X: the update kernel accumulates C += Y (-X)
     }
 }
@@ -746,6 +759,8 @@ int qr_leaf(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, 
     qr_copy_pad_kernel<<<cp_grid, 256, 0, ctx->stream>>>(A, lda, rows, m, W, ldw, rowsW);
     PB_LAUNCH_CHECK(ctx);
     static const int stage_env = getenv("PB_QR_STAGE") ? atoi(getenv("PB_QR_STAGE")) : 1;
+    const size_t tt_smem = sizeof(double) * 2 * QNB * (QNB + 1);
+    PB_CUDA(ctx, cudaFuncSetAttribute(qr_tt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tt_smem));
     for (int64_t J = 0; J < mp; J += QNB) {
         const int nbo = (int)std::min<int64_t>(QNB, mp - J);
         int grid = std::max(1, std::min<int>((int)((rowsW - J + 127) / 128), ctx->sm_count));
@@ -766,9 +781,9 @@ int qr_leaf(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, 
         const double* Y = W + J;                                      // the panel columns are the explicit block Y now
         const int64_t ldz = nbo + ntrail;
         PB_TRY(pbi_gemm_tn(ctx, Y, ldw, nbo, Y, ldw, ldz, rowsW, Zb, ldz, 0));                    // [Y^T Y | Y^T C]
-        qr_tt_kernel<<<1, 4 * QNB, 0, ctx->stream>>>(Zb, ldz, nbo, tau + J, Tt);
+        qr_tt_kernel<<<1, 4 * QNB, tt_smem, ctx->stream>>>(Zb, ldz, nbo, tau + J, Tt);
         PB_LAUNCH_CHECK(ctx);
-        qr_applyt_kernel<<<(unsigned)((ntrail + QNB - 1) / QNB), QT, 0, ctx->stream>>>(Zb + nbo, ldz, ntrail, Tt, nbo);   // X = T^T Z
+        qr_applyt_kernel<<<(unsigned)((ntrail + QAT - 1) / QAT), QT, 0, ctx->stream>>>(Zb + nbo, ldz, ntrail, Tt, nbo);   // -X = -T^T Z
         PB_LAUNCH_CHECK(ctx);
         PB_TRY(pbi_gemm_nn_sub(ctx, Y, ldw, rowsW, nbo, Zb + nbo, ldz, ntrail, W + J + nbo, ldw)); // C += Y (-X)
     }
