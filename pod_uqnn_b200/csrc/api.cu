@@ -31,14 +31,17 @@ int pb_reserve_int(pb_ctx* ctx, int** p, size_t* cap, size_t elems) {
 }
 
 namespace {
+// Stage timer: two events on the context stream, NO host synchronisation -- pb_last_ms() waits for the stop event when the
+// number is asked for.  (A synchronising timer cost one pipeline bubble per stage: 6 of the 16 host syncs of a C2 step.)
 struct Timer {
-    pb_ctx* c; int which; cudaEvent_t a, b;
-    Timer(pb_ctx* ctx, int w, bool inner = false) : c(ctx), which(w), a(inner ? ctx->ev2 : ctx->ev0), b(inner ? ctx->ev3 : ctx->ev1) {
-        cudaEventRecord(a, c->stream);
+    pb_ctx* c; int which;
+    Timer(pb_ctx* ctx, int w, bool = false) : c(ctx), which(w) {
+        c->t_pending[which] = false;
+        cudaEventRecord(c->tev[which][0], c->stream);
     }
     void stop() {
-        cudaEventRecord(b, c->stream); cudaEventSynchronize(b);
-        float ms = 0; cudaEventElapsedTime(&ms, a, b); c->ms[which] = ms;
+        cudaEventRecord(c->tev[which][1], c->stream);
+        c->t_pending[which] = true;
     }
 };
 }  // namespace
@@ -73,6 +76,7 @@ int pb_create(int device, pb_ctx** out) {
     PB_CUDA(ctx, cudaEventCreate(&ctx->ev2)); PB_CUDA(ctx, cudaEventCreate(&ctx->ev3));
     PB_CUDA(ctx, cudaEventCreate(&ctx->evk0)); PB_CUDA(ctx, cudaEventCreate(&ctx->evk1));
     PB_CUDA(ctx, cudaEventCreate(&ctx->evr0)); PB_CUDA(ctx, cudaEventCreate(&ctx->evr1));
+    for (int w = 0; w < PB_T_COUNT; ++w) { PB_CUDA(ctx, cudaEventCreate(&ctx->tev[w][0])); PB_CUDA(ctx, cudaEventCreate(&ctx->tev[w][1])); }
     PB_CUDA(ctx, cudaMalloc(&ctx->d_int, 64 * sizeof(int)));
     PB_CUDA(ctx, cudaMemset(ctx->d_int, 0, 64 * sizeof(int)));
     PB_CUDA(ctx, cudaMallocHost(&ctx->h_int, 64 * sizeof(int)));
@@ -89,8 +93,10 @@ int pb_destroy(pb_ctx* ctx) {
                     ctx->fp_buf[0], ctx->fp_buf[1], ctx->fp_buf[2], ctx->fp_buf[3], ctx->fp_buf[4], ctx->fp_buf[5], ctx->fp_buf[6], ctx->fp_buf[7]};
     for (void* b : bufs) if (b) cudaFree(b);
     if (ctx->h_int) cudaFreeHost(ctx->h_int);
+    if (ctx->h_sig) cudaFreeHost(ctx->h_sig);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);
     cudaEventDestroy(ctx->evk0); cudaEventDestroy(ctx->evk1); cudaEventDestroy(ctx->evr0); cudaEventDestroy(ctx->evr1);
+    for (int w = 0; w < PB_T_COUNT; ++w) { cudaEventDestroy(ctx->tev[w][0]); cudaEventDestroy(ctx->tev[w][1]); }
     if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); for (auto& e : ctx->chunk_ev) if (e) cudaEventDestroy(e); }
     if (ctx->Gpart) cudaFree(ctx->Gpart);
     pbi_train_free(ctx);
@@ -117,6 +123,11 @@ int pb_last_ms(pb_ctx* ctx, int which, double* ms) {
         PB_CUDA(ctx, cudaEventSynchronize(ctx->evk1));
         float t = 0; cudaEventElapsedTime(&t, ctx->evk0, ctx->evk1); ctx->ms[PB_T_TN_KERNEL] = t;
         ctx->tn_timing_pending = false;
+    }
+    if (ctx->t_pending[which]) {
+        PB_CUDA(ctx, cudaEventSynchronize(ctx->tev[which][1]));
+        float t = 0; PB_CUDA(ctx, cudaEventElapsedTime(&t, ctx->tev[which][0], ctx->tev[which][1]));
+        ctx->ms[which] = t; ctx->t_pending[which] = false;
     }
     *ms = ctx->ms[which]; return PB_OK;
 }
@@ -190,9 +201,17 @@ static int finish_rank(pb_ctx* ctx, const double* sig_dev, int64_t count, int av
 }
 
 static int fetch_sigma(pb_ctx* ctx, const double* sig_dev, int64_t count, int64_t total) {
-    ctx->sigma_host.assign((size_t)total, 0.);
-    PB_CUDA(ctx, cudaMemcpyAsync(ctx->sigma_host.data(), sig_dev, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
-    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // asynchronous copy into pinned memory: a copy into the pageable vector would block the host until the stream drains.
+    // Copies are ordered on the stream, so a pending earlier one needs no wait -- unless the buffer is about to be replaced
+    if (ctx->h_sig_cap < (size_t)total) {
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_sig) cudaFreeHost(ctx->h_sig);
+        ctx->h_sig = nullptr; ctx->h_sig_cap = 0;
+        PB_CUDA(ctx, cudaMallocHost(&ctx->h_sig, sizeof(double) * (size_t)(total + 64)));
+        ctx->h_sig_cap = (size_t)total + 64;
+    }
+    PB_CUDA(ctx, cudaMemcpyAsync(ctx->h_sig, sig_dev, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sig_count = count; ctx->sig_total = total; ctx->sigma_pending = true;
     return PB_OK;
 }
 
@@ -282,6 +301,12 @@ int pb_pod_basis(pb_ctx* ctx, const double* A, int64_t rows, int64_t lda, const 
 
 int pb_pod_sigma(pb_ctx* ctx, double* sigma_host, int64_t capacity, int64_t* count) {
     if (!ctx) return PB_ERR_ARG;
+    if (ctx->sigma_pending) {
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->sigma_host.assign((size_t)ctx->sig_total, 0.);
+        memcpy(ctx->sigma_host.data(), ctx->h_sig, sizeof(double) * (size_t)ctx->sig_count);
+        ctx->sigma_pending = false;
+    }
     int64_t n = std::min<int64_t>(capacity, (int64_t)ctx->sigma_host.size());
     if (sigma_host && n > 0) memcpy(sigma_host, ctx->sigma_host.data(), sizeof(double) * (size_t)n);
     if (count) *count = (int64_t)ctx->sigma_host.size();
@@ -343,7 +368,7 @@ static int pod_after_gram(pb_ctx* ctx, const double* A, int64_t rows, int64_t m,
                           int mode, int* n_L) {
     int keep = 0;
     PB_TRY(pb_pod_from_gram(ctx, ctx->Gbuf, m, eps, n_L_in, mode, n_L, &keep));
-    ctx->ms[PB_T_PASS2] = 0.;
+    ctx->ms[PB_T_PASS2] = 0.; ctx->t_pending[PB_T_PASS2] = false;
     if (keep > 0) {
         Timer t2(ctx, PB_T_PASS2);
         PB_TRY(pb_reserve(ctx, &ctx->Ybuf, &ctx->Y_cap, (size_t)rows * keep));
@@ -359,7 +384,7 @@ int pb_pod(pb_ctx* ctx, const double* U, int64_t n_h, int64_t n_st, int64_t ldu,
     if (!ctx || !n_L) return PB_ERR_ARG;
     if (n_h <= 0 || n_st <= 0 || ldu < n_st) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod: bad shape (%lld x %lld, ld %lld)",
                                                        (long long)n_h, (long long)n_st, (long long)ldu);
-    cudaEventRecord(ctx->ev2, ctx->stream);
+    Timer t_total(ctx, PB_T_POD_TOTAL);
     const bool wide = n_h < n_st;
     const double* A = U; int64_t rows = n_h, m = n_st, lda = ldu;
     if (wide) {   // POD of U^T: its right singular vectors are the modes themselves
@@ -371,15 +396,14 @@ int pb_pod(pb_ctx* ctx, const double* U, int64_t n_h, int64_t n_st, int64_t ldu,
     PB_TRY(pb_reserve(ctx, &ctx->Gbuf, &ctx->G_cap, (size_t)m * m));
     ctx->wide = wide;
     if (mode == PB_POD_TSQR) {
-        ctx->ms[PB_T_GRAM] = 0.; ctx->ms[PB_T_PASS2] = 0.;
+        ctx->ms[PB_T_GRAM] = 0.; ctx->ms[PB_T_PASS2] = 0.; ctx->t_pending[PB_T_GRAM] = ctx->t_pending[PB_T_PASS2] = false;
         PB_TRY(pb_tsqr_r(ctx, A, rows, m, lda, ctx->Gbuf));
         PB_TRY(pb_pod_from_r(ctx, ctx->Gbuf, m, eps, n_L_in, n_L));
     } else {
         PB_TRY(pb_gram(ctx, A, rows, m, lda, ctx->Gbuf));
         PB_TRY(pod_after_gram(ctx, A, rows, m, lda, eps, n_L_in, mode, n_L));
     }
-    cudaEventRecord(ctx->ev3, ctx->stream); cudaEventSynchronize(ctx->ev3);
-    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3); ctx->ms[PB_T_POD_TOTAL] = ms;
+    t_total.stop();
     return PB_OK;
 }
 
@@ -453,7 +477,7 @@ int pb_pod_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, in
                 double eps, int n_L_in, int mode, int* n_L) {
     if (!ctx || !n_L || !U_host || !U_dev) return PB_ERR_ARG;
     if (n_h <= 0 || n_st <= 0 || ldu_host < n_st) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod_host: bad shape");
-    cudaEventRecord(ctx->ev2, ctx->stream);
+    Timer t_total(ctx, PB_T_POD_TOTAL);
     const int64_t m = n_st;
     if (n_h >= n_st) PB_TRY(pb_reserve(ctx, &ctx->Gbuf, &ctx->G_cap, (size_t)m * m));
     // the TSQR mode has no Gram to overlap with the upload: plain copy, then the device path
@@ -466,8 +490,7 @@ int pb_pod_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, in
     if (rc != PB_OK) return rc;
     ctx->wide = false;
     PB_TRY(pod_after_gram(ctx, U_dev, n_h, m, n_st, eps, n_L_in, mode, n_L));
-    cudaEventRecord(ctx->ev3, ctx->stream); cudaEventSynchronize(ctx->ev3);
-    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3); ctx->ms[PB_T_POD_TOTAL] = ms;
+    t_total.stop();
     return PB_OK;
 }
 
@@ -591,7 +614,7 @@ int pb_fast_pod(pb_ctx* ctx, const double* U, int64_t n_h, int n_t, int64_t n_s,
     if (rc == PB_OK) rc = pb_pod(ctx, ctx->Uf, n_h, off, ldf, eps, 0, mode, n_L);
     ctx->uf_rows = n_h; ctx->uf_cols = off; ctx->uf_ld = ldf;
     cudaEventRecord(e1, ctx->stream); cudaEventSynchronize(e1);
-    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ctx->ms[PB_T_POD_TOTAL] = ms;
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ctx->ms[PB_T_POD_TOTAL] = ms; ctx->t_pending[PB_T_POD_TOTAL] = false;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return rc;
 }

@@ -19,6 +19,10 @@ struct pb_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     cudaEvent_t evk0 = nullptr, evk1 = nullptr;     // around the TN main kernel
     cudaEvent_t evr0 = nullptr, evr1 = nullptr;     // user region timer
+    cudaEvent_t tev[PB_T_COUNT][2] = {{nullptr}};   // stage timers: recorded on the stream, read lazily by pb_last_ms
+    bool t_pending[PB_T_COUNT] = {false};           // (no host synchronisation inside the ops)
+    bool sigma_pending = false;                     // h_sig (pinned) is being filled by an async copy; pb_pod_sigma finishes it
+    double* h_sig = nullptr; size_t h_sig_cap = 0; int64_t sig_count = 0, sig_total = 0;
     bool tn_timing_pending = false;
     cudaStream_t copy_stream = nullptr;             // pb_pod_host: chunked upload overlapped with the Gram
     cudaEvent_t chunk_ev[16] = {nullptr};

@@ -180,7 +180,7 @@ __device__ __forceinline__ void inner_pair(int cross, int round, int idx, int& p
 //              rounds instead of up to 3 x 31 is what makes a round of the outer sweep cheap.
 // Returns the number of rotations applied in the first pass (0 => nothing to do for this pair).
 __device__ int inner_jacobi(double (*S)[SP], double (*Q)[SP], double* cs, double* sn, double tol, int max_inner,
-                            int cross) {
+                            int cross, int* clean_exit) {
     const int tid = threadIdx.x;
     for (int e = tid; e < JP * JP; e += blockDim.x) Q[e / JP][e % JP] = (e / JP == e % JP) ? 1. : 0.;
     __syncthreads();
@@ -230,6 +230,7 @@ __device__ int inner_jacobi(double (*S)[SP], double (*Q)[SP], double* cs, double
             __syncthreads();
         }
         if (sweep == 0) first = rot_sweep;
+        *clean_exit = (rot_sweep == 0);       // the sweeps ended on one without rotations: converged to the threshold
         if (rot_sweep == 0) break;
     }
     return first;
@@ -237,6 +238,7 @@ __device__ int inner_jacobi(double (*S)[SP], double (*Q)[SP], double* cs, double
 
 struct JacArgs {
     double* At; int64_t ldm; int nb; int round; double tol; int* n_rot; int max_inner; int64_t batch_stride; int cross;
+    int* clean;      // single-pair problems: set to 1 when the in-kernel solve ended on a sweep without rotations (nullable)
 };
 
 constexpr int JCH = 256;        // vector elements staged per shared-memory chunk
@@ -328,7 +330,9 @@ __global__ void __launch_bounds__(256) jacobi_pair_kernel(JacArgs a) {
     // ---- phase 2: small eigenproblem
     // round 0 of a sweep meets every block exactly once: it also rotates the pairs INSIDE the two blocks;
     // the other rounds only the 256 cross pairs (a.cross)
-    const int first = inner_jacobi(S, Q, cs, sn, a.tol, a.max_inner, a.cross);
+    int clean = 0;
+    const int first = inner_jacobi(S, Q, cs, sn, a.tol, a.max_inner, a.cross, &clean);
+    if (a.clean && tid == 0) *a.clean = clean;
     if (first == 0) return;                       // uniform: nothing to rotate
     if (tid == 0) atomicAdd(a.n_rot, first);
 
@@ -527,14 +531,17 @@ int pbi_jacobi_factor(pb_ctx* ctx, double* At, int64_t m, int r, const double* s
         const int rounds = nb > 2 ? nb - 1 : 1;
         for (int round = 0; round < rounds; ++round) {
             // a single pair (r <= 32): its 32 x 32 problem IS the whole problem -- solve it to convergence at once
-            JacArgs ja{At, ldm, nb, round, tol, ctx->d_int + 1, nb == 2 ? 16 : g_inner_sweeps, 0, (g_cross_rounds && round > 0) ? 1 : 0};
+            JacArgs ja{At, ldm, nb, round, tol, ctx->d_int + 1, nb == 2 ? 16 : g_inner_sweeps, 0, (g_cross_rounds && round > 0) ? 1 : 0,
+                       nb == 2 ? ctx->d_int + 4 : nullptr};
             jacobi_pair_kernel<<<nb / 2, 256, jac_smem, ctx->stream>>>(ja);
             PB_LAUNCH_CHECK(ctx);
         }
         if (trust_single) { converged = true; continue; }
-        PB_CUDA(ctx, cudaMemcpyAsync(ctx->h_int + 1, ctx->d_int + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        // d_int[1] = rotations of the first inner sweep, d_int[4] = the single-pair solve ended on a clean sweep
+        PB_CUDA(ctx, cudaMemcpyAsync(ctx->h_int + 1, ctx->d_int + 1, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        converged = (ctx->h_int[1] == 0);
+        // a single pair iterated to a clean sweep inside the kernel IS converged: no confirming launch (82 us + a sync at C2)
+        converged = (ctx->h_int[1] == 0) || (nb == 2 && ctx->h_int[4] == 1);
     }
     if (!converged && max_sweeps >= 30)
         PB_FAIL(ctx, PB_ERR_NOT_CONVERGED, "eig_psd: Jacobi did not converge in %d sweeps (m=%lld r=%d)", max_sweeps, (long long)m, r);
@@ -547,8 +554,6 @@ int pbi_jacobi_factor(pb_ctx* ctx, double* At, int64_t m, int r, const double* s
     PB_CUDA(ctx, cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
     sort_kernel<<<1, 1024, sort_smem, ctx->stream>>>(nrm2_scr, nvec, npow2, shift_dev, sig_dev, nrm_dev, (int)m, perm_dev, ctx->d_int + 3, 0, 0, 0);
     PB_LAUNCH_CHECK(ctx);
-    PB_CUDA(ctx, cudaMemcpyAsync(ctx->h_int + 3, ctx->d_int + 3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (sweeps_out) *sweeps_out = sweeps;
     return PB_OK;
 }
@@ -736,7 +741,7 @@ int pbi_eig_psd_batched(pb_ctx* ctx, const double* G_all, int64_t m, int batch, 
         PB_CUDA(ctx, cudaMemsetAsync(ctx->d_int + 1, 0, sizeof(int), ctx->stream));
         const int rounds = nb > 2 ? nb - 1 : 1;
         for (int round = 0; round < rounds; ++round) {
-            JacArgs ja{At_all, ldm, nb, round, tol, ctx->d_int + 1, g_inner_sweeps, bsAt, (g_cross_rounds && round > 0) ? 1 : 0};
+            JacArgs ja{At_all, ldm, nb, round, tol, ctx->d_int + 1, g_inner_sweeps, bsAt, (g_cross_rounds && round > 0) ? 1 : 0, nullptr};
             jacobi_pair_kernel<<<dim3(nb / 2, batch), 256, jac_smem, ctx->stream>>>(ja);
             PB_LAUNCH_CHECK(ctx);
         }
