@@ -132,3 +132,34 @@ def test_podnnmodel_host_layout_helpers(tmp_path):
         m.train_model(0, None, None, None, None, 1)
     with pytest.raises(ValueError):
         m.predict_v(np.zeros((3, 2)))
+
+
+def test_null_context_is_rejected_tsqr():
+    L = _lib.lib()
+    assert L.pb_tsqr_r(None, None, 1, 1, 1, None) == _lib.PB_ERR_ARG
+    assert L.pb_pod_from_r(None, None, 1, 0., 0, None) == _lib.PB_ERR_ARG
+    assert _lib.POD_MODES["tsqr"] == 3 and _lib.T_QR == 10
+
+
+def test_u_level_output_tiles():
+    """PodnnModel._u_tiles: column tiles cover [0, N) exactly once, each with device buffers of the tile's shape."""
+    from pod_uqnn_b200.podnnmodel import PodnnModel
+
+    class FakeArr:
+        def __init__(self, *shape):
+            self.shape = shape
+
+    class FakeCtx:
+        def alloc(self, *shape):
+            return FakeArr(*shape)
+
+    m = PodnnModel.__new__(PodnnModel)
+    m._ctx, m.n_h = FakeCtx(), 100
+    for N, cap in ((75, 8 * 100 * 32), (64, 8 * 100 * 32), (5, 8 * 100 * 1000), (7, 1)):
+        m.U_TILE_BYTES = cap
+        tiles = list(m._u_tiles(N))
+        assert tiles[0][0] == 0 and tiles[-1][1] == N
+        assert all(a[1] == b[0] for a, b in zip(tiles, tiles[1:]))
+        for j0, j1, Um, Us, t in tiles:
+            assert Um.shape == Us.shape == (100, j1 - j0) and 0 < j1 - j0 <= max(1, cap // 800)
+        assert [t[4] for t in tiles] == list(range(len(tiles)))
