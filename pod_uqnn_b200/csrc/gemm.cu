@@ -342,9 +342,9 @@ recon_strip_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int 
         }
         const double* as = As + (wm * (MS / 2) + lg) * PA + lk;
         const double* bs = Bs + (t % STG) * KP * PB + wn * 16 + lg;
+        if (K == KP) {       // full-depth product (the QR update): straight-line code, the fragment loads can run ahead
 #pragma unroll
-        for (int kk = 0; kk < KP / 4; ++kk) {
-            if (kk * 4 < K) {
+            for (int kk = 0; kk < KP / 4; ++kk) {
                 double af[RA], bf[2];
 #pragma unroll
                 for (int a = 0; a < RA; ++a) af[a] = as[a * 8 * PA + kk * 4];
@@ -354,6 +354,21 @@ recon_strip_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int 
                 for (int a = 0; a < RA; ++a)
 #pragma unroll
                     for (int u = 0; u < 2; ++u) dmma884(acc[a][u][0], acc[a][u][1], af[a], bf[u]);
+            }
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < KP / 4; ++kk) {
+                if (kk * 4 < K) {
+                    double af[RA], bf[2];
+#pragma unroll
+                    for (int a = 0; a < RA; ++a) af[a] = as[a * 8 * PA + kk * 4];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) bf[u] = bs[(kk * 4 + lk) * PB + u * 8];
+#pragma unroll
+                    for (int a = 0; a < RA; ++a)
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) dmma884(acc[a][u][0], acc[a][u][1], af[a], bf[u]);
+                }
             }
         }
         const int64_t j0 = (int64_t)t * NT;
