@@ -115,3 +115,55 @@ def test_restatement_against_live_reference():
     V = ref.pod.perform_pod(U, 1e-8, 0, False)
     V2 = po.perform_pod(U2, 1e-8)
     assert V.shape == V2.shape and cmp.largest_principal_angle(V2, V) < 1e-9
+
+
+def test_ensemble_restatement_against_torch_ops():
+    """TensorFlow / TFP are not in the image, so the ensemble oracle cannot be pinned against the reference itself.
+    Second opinion: the same forward built from PyTorch's own modules -- torch.nn.Linear (Keras Dense with an
+    (in, out) kernel = Linear with the transposed weight), ReLU, torch.nn.functional.softplus (= tf.math.softplus) and
+    torch.distributions.Normal / its mean and variance (= tfp.distributions.Normal, varneuralnetwork.py:56-59,
+    154-160) -- must agree with oracle/ensemble.py, including the mixture moments of predict_v
+    (podnnmodel.py:314-328) and a sampled Monte-Carlo estimate of predict (:366-379)."""
+    import torch
+    torch.manual_seed(0)
+    layers, n_L, soft_0 = [3, 24, 24, 5], 5, 0.01
+    members = [ens.init_weights(layers, 70 + i, bias_scale=.2) for i in range(3)]
+    rng = np.random.default_rng(4)
+    X = rng.uniform(-2, 2, (41, 3))
+    nb = ens.set_normalize_bounds(X, ens.NORM_MEANSTD)
+
+    def torch_member(w):
+        mods = []
+        for l in range(len(w) // 2):
+            lin = torch.nn.Linear(w[2 * l].shape[0], w[2 * l].shape[1]).double()
+            with torch.no_grad():
+                lin.weight.copy_(torch.from_numpy(w[2 * l].T)); lin.bias.copy_(torch.from_numpy(w[2 * l + 1]))
+            mods.append(lin)
+            if l < len(w) // 2 - 1:
+                mods.append(torch.nn.ReLU())
+        net = torch.nn.Sequential(*mods)
+        Xn = (torch.from_numpy(X) - torch.from_numpy(nb[0])) / torch.from_numpy(nb[1])
+        t = net(Xn)
+        dist = torch.distributions.Normal(t[..., :n_L], torch.nn.functional.softplus(soft_0 * t[..., n_L:]) + 1e-6)
+        return dist
+
+    mus, vars_ = [], []
+    for w in members:
+        d = torch_member(w)
+        mu_o, var_o = ens.member_predict(X, w, n_L, soft_0, ens.NORM_MEANSTD, nb)
+        assert np.allclose(d.mean.detach().numpy(), mu_o, rtol=1e-13, atol=1e-14)
+        assert np.allclose(d.variance.detach().numpy(), var_o, rtol=1e-12, atol=0)
+        mus.append(d.mean.detach()); vars_.append(d.variance.detach())
+    mus, vars_ = torch.stack(mus, -1), torch.stack(vars_, -1)
+    v_pred = mus.mean(-1)
+    v_sig = torch.sqrt((vars_ + mus ** 2).mean(-1) - v_pred ** 2)
+    vm, vs = ens.predict_v(X, members, n_L, soft_0, ens.NORM_MEANSTD, nb)
+    assert np.allclose(v_pred.numpy(), vm, rtol=1e-13, atol=1e-14) and np.allclose(v_sig.numpy(), vs, rtol=1e-10)
+    # predict(): torch draws of Normal(v_pred, v_sig) pushed through V against the closed-form moments
+    V = torch.from_numpy(np.linalg.qr(rng.standard_normal((30, n_L)))[0])
+    S = 4000
+    draws = torch.distributions.Normal(v_pred, v_sig).sample((S,))                   # (S, N, n_L)
+    U = torch.einsum("hl,snl->shn", V, draws)
+    Um, Us = ens.predict_U_moments(V.numpy(), vm, vs)
+    assert np.all(np.abs(U.mean(0).numpy() - Um) <= 6. * Us / np.sqrt(S) + 1e-12)
+    assert np.max(np.abs(U.std(0, unbiased=True).numpy() / Us - 1.)) < 0.12
