@@ -694,7 +694,7 @@ __global__ void __launch_bounds__(1024) chol_small_kernel(const double* __restri
 #pragma unroll
                 for (int x = 0; x < 8; ++x) if (q + x < k) { if (x & 1) s1 += l[x] * lp[q + x]; else s0 += l[x] * lp[q + x]; }
             }
-            const double gjp = G[(int64_t)j * m + p];
+            const double gjp = G[(int64_t)p * m + j];      // G is symmetric: row p (coalesced) instead of column p
             double v = (gjp + (j == p ? shift : 0.) - (s0 + s1)) * inv;
             if (d[j] == -DBL_MAX) v = 0.;
             if (j == p) v = sqrt(dp);
