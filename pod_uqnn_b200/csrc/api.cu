@@ -193,8 +193,13 @@ static int finish_rank(pb_ctx* ctx, const double* sig_dev, int64_t count, int av
         if (n_L_in > avail) PB_FAIL(ctx, PB_ERR_SHAPE, "requested n_L=%d exceeds the numerical rank %d", n_L_in, avail);
         nl = n_L_in;
     } else {
-        PB_TRY(pbi_rank(ctx, sig_dev, count, eps, &nl));
+        PB_TRY(pbi_rank(ctx, sig_dev, count, eps, &nl));     // synchronises the stream: a pending sigma copy has landed too
         if (nl > avail) nl = avail;
+        if (ctx->sigma_pending) {
+            ctx->sigma_host.assign((size_t)ctx->sig_total, 0.);
+            memcpy(ctx->sigma_host.data(), ctx->h_sig, sizeof(double) * (size_t)ctx->sig_count);
+            ctx->sigma_pending = false;
+        }
     }
     ctx->n_L = nl; *n_L = nl;
     return PB_OK;

@@ -94,18 +94,30 @@ class CudaBackend:
         self.L = _lib.lib()
         self._cache = {}
         # the library and NCCL share one torch stream: the all-reduces are ordered against the kernels on the
-        # device (NCCL's stream waits on / is waited for by this stream through events), no host synchronisation
+        # device (NCCL's stream waits on / is waited for by this stream through events), no host synchronisation.
+        # It is made torch's CURRENT stream for the life of the backend (restored by close()): a `with
+        # torch.cuda.stream(...)` around every allocation / collective costs host time exactly where the GPU is
+        # waiting for the host (after the data-dependent syncs of the eigensolve)
         self.stream = torch.cuda.Stream(self.dev)
+        self._prev_stream = torch.cuda.current_stream(self.dev)
+        torch.cuda.set_stream(self.stream)
         ctx.check(self.L.pb_set_stream(ctx.h, C.c_void_p(self.stream.cuda_stream)))
 
     def close(self):
-        """Give the context its own stream back."""
+        """Give the context its own stream back and restore torch's current stream."""
         self.stream.synchronize()
+        self.torch.cuda.set_stream(self._prev_stream)
         self.ctx.check(self.L.pb_set_stream(self.ctx.h, None))
 
     def _empty(self, *shape):
-        with self.torch.cuda.stream(self.stream):
-            return self.torch.empty(*shape, dtype=self.torch.float64, device=self.dev)
+        return self.torch.empty(*shape, dtype=self.torch.float64, device=self.dev)
+
+    def _scratch(self, name, *shape):
+        """torch tensor reused across steps for internal temporaries (the Gram partials that are all-reduced)."""
+        t = self._cache.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = self._cache[name] = self._empty(*shape)
+        return t
 
     def _buf(self, name, *shape):
         """Library-owned HBM buffer reused across steps (cudaMalloc / cudaFree synchronise the device)."""
@@ -115,18 +127,17 @@ class CudaBackend:
         return b
 
     def reduce(self, t, group=None):
-        with self.torch.cuda.stream(self.stream):
-            _all_reduce(t, group)
+        _all_reduce(t, group)
 
     def gram(self, A):
         m = A.shape[1]
-        G = self._empty(m, m)
+        G = self._scratch("G", m, m)
         self.ctx.check(self.L.pb_gram(self.ctx.h, A.ptr, A.shape[0], m, A.ld, G.data_ptr()))
         return G
 
     def gram_host(self, host_ptr, A):
         m = A.shape[1]
-        G = self._empty(m, m)
+        G = self._scratch("G", m, m)
         self.ctx.check(self.L.pb_gram_host(self.ctx.h, host_ptr, A.shape[0], m, m, A.ptr, G.data_ptr()))
         return G
 
@@ -145,9 +156,8 @@ class CudaBackend:
     def all_gather_rows(self, R, group=None):
         import torch.distributed as dist
         world = dist.get_world_size(group)
-        with self.torch.cuda.stream(self.stream):
-            stack = self.torch.empty(world * R.shape[0], R.shape[1], dtype=R.dtype, device=R.device)
-            dist.all_gather_into_tensor(stack, R.contiguous(), group=group)
+        stack = self._scratch("Rstack", world * R.shape[0], R.shape[1])
+        dist.all_gather_into_tensor(stack, R.contiguous(), group=group)
         return stack
 
     def pod_from_r(self, R, eps, n_L):
@@ -163,7 +173,7 @@ class CudaBackend:
 
     def pass2_gram(self, A, keep):
         Y = self._buf("Y", A.shape[0], keep)
-        G2 = self._empty(keep, keep)
+        G2 = self._scratch("G2", keep, keep)
         self.ctx.check(self.L.pb_pod_pass2_gram(self.ctx.h, A.ptr, A.shape[0], A.ld, Y.ptr, G2.data_ptr()))
         return Y, G2
 
