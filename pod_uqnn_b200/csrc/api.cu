@@ -438,7 +438,9 @@ int gram_host_chunked(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_
         for (int c = 0; c < 16; ++c) PB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->chunk_ev[c], cudaEventDisableTiming));
     }
     PB_TRY(pb_reserve(ctx, &ctx->Gpart, &ctx->Gpart_cap, (size_t)m * m * nchunks));
-    int64_t rows_c = (n_h + nchunks - 1) / nchunks; rows_c = (rows_c + 15) / 16 * 16;
+    // the Gram of the LAST chunk cannot overlap anything (nothing is left to upload): keep that chunk small, a quarter of
+    // the others (its Gram then takes ~0.1 instead of 0.34 ms at C2)
+    int64_t rows_c = (4 * n_h + 4 * nchunks - 4) / (4 * nchunks - 3); rows_c = (rows_c + 15) / 16 * 16;
     // the copy stream must not start overwriting U_dev before earlier work on the compute stream is done
     PB_CUDA(ctx, cudaEventRecord(ctx->chunk_ev[0], ctx->stream));
     PB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[0], 0));
