@@ -589,6 +589,12 @@ int pbi_gemm_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const dou
         return PB_OK;
     }
     if (!sym && ka > 32 && ka <= 64 && kb <= 64) return launch_tn<64, 64, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);   // Y^T Y of a QR panel
+    {   // wide right operand (the QR trailing product [Y^T Y | Y^T C]): 64 x 256 tiles, warp tile 32 x 64 (12 fragment
+        // loads per 32 DMMAs instead of 8 per 16)
+        static const int wide_env = getenv("PB_TN_WIDE") ? atoi(getenv("PB_TN_WIDE")) : 1;
+        if (wide_env && !sym && ka > 32 && ka <= 64 && kb >= 512)
+            return launch_tn<64, 256, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);
+    }
     if (!sym && ka > 32 && ka <= 64) return launch_tn<64, 128, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);
     if (!sym && ka > 64 && ka <= 96) return launch_tn<96, 128, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);
     if (sym || ka > 32) return launch_tn<128, 128, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, sym);
