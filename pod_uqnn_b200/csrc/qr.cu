@@ -544,7 +544,7 @@ __device__ __forceinline__ void block_argmax(double& v, int& i, double* rv, int*
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(QT) qrcp_kernel(QrcpArgs a) {
+__global__ void __launch_bounds__(QT, 1) qrcp_kernel(QrcpArgs a) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) double qsm[];
     const int m = a.m; const int64_t ldm = a.ldm;
@@ -555,7 +555,10 @@ __global__ void __launch_bounds__(QT) qrcp_kernel(QrcpArgs a) {
     double* cn2 = qsm + (m + 7) / 8 * 8;                // [mg * 8] squared norms of my columns below the current row
     __shared__ int active[64 * 8];                      // my columns still to be eliminated (mg <= 64)
     __shared__ double red[QT / 32][8];
-    __shared__ double out8[8], wsh[8];
+    __shared__ double out8[8];
+    __shared__ double red16[QT / 32][QIB];
+    __shared__ double out16[QIB], wsh16[QIB];
+    __shared__ int act16[QIB];
     __shared__ double rv[QT]; __shared__ int ri[QT];
     double* __restrict__ At = a.At;
 
@@ -632,48 +635,57 @@ __global__ void __launch_bounds__(QT) qrcp_kernel(QrcpArgs a) {
         }
         __syncthreads();
 
-        // ---- update my remaining columns, recompute their norms below row c
-        for (int j = 0; j < mg; ++j) {
-            const int k0 = (b + j * G) * 8;
+        // ---- update my remaining columns, recompute their norms below row c.  Two column groups (16 columns) per pass:
+        // half the passes over the rows and half the block reductions of a group-at-a-time loop (m = 4096: 4 groups per CTA)
+        for (int j0 = 0; j0 < mg; j0 += 2) {
+            const bool two = j0 + 1 < mg;
+            const int ka = (b + j0 * G) * 8, kb = two ? (b + (j0 + 1) * G) * 8 : ka;
             int any = 0;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) any |= active[j * 8 + q];
+            for (int q = 0; q < 8; ++q) any |= active[j0 * 8 + q] | (two ? active[(j0 + 1) * 8 + q] : 0);
             if (!any) continue;                                        // uniform (shared memory)
-            double acc[8];
+            double acc[QIB];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) acc[q] = 0.;
+            for (int q = 0; q < QIB; ++q) acc[q] = 0.;
             for (int r = c + 1 + tid; r < m; r += QT) {
                 const double xr = xs[r - c];
-                const double2* pp = reinterpret_cast<const double2*>(At + (int64_t)r * ldm + k0);
+                const double2* pa = reinterpret_cast<const double2*>(At + (int64_t)r * ldm + ka);
+                const double2* pb = reinterpret_cast<const double2*>(At + (int64_t)r * ldm + kb);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { double2 v = pp[q]; acc[2 * q] += xr * v.x; acc[2 * q + 1] += xr * v.y; }
-            }
-            block_sum8(acc, red, out8);
-            if (tid < 8) {
-                const double rc = At[(int64_t)c * ldm + k0 + tid];
-                const double wv = rc + out8[tid] * scale;
-                wsh[tid] = wv;
-                if (active[j * 8 + tid]) At[(int64_t)c * ldm + k0 + tid] = rc - tau * wv;
-            }
-            __syncthreads();
-            double w[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) w[q] = wsh[q];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) acc[q] = 0.;
-            for (int r = c + 1 + tid; r < m; r += QT) {
-                const double tv = tau * (xs[r - c] * scale);
-                double* pr = At + (int64_t)r * ldm + k0;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    if (active[j * 8 + q]) {
-                        const double v = pr[q] - tv * w[q];
-                        pr[q] = v; acc[q] += v * v;
-                    }
+                for (int q = 0; q < 4; ++q) {
+                    const double2 va = pa[q], vb = pb[q];
+                    acc[2 * q] += xr * va.x; acc[2 * q + 1] += xr * va.y;
+                    acc[8 + 2 * q] += xr * vb.x; acc[8 + 2 * q + 1] += xr * vb.y;
                 }
             }
-            block_sum8(acc, red, out8);
-            if (tid < 8 && active[j * 8 + tid]) cn2[j * 8 + tid] = out8[tid];
+            block_sum16(acc, red16, out16);
+            if (tid < QIB) {
+                const int e = (tid < 8 ? j0 : j0 + 1) * 8 + (tid & 7);
+                const int col = (tid < 8 ? ka : kb) + (tid & 7);
+                const bool act = (tid < 8 || two) && active[e];
+                const double rc = At[(int64_t)c * ldm + col];
+                const double wv = rc + out16[tid] * scale;
+                wsh16[tid] = wv; act16[tid] = act ? 1 : 0;
+                if (act) At[(int64_t)c * ldm + col] = rc - tau * wv;
+            }
+            __syncthreads();
+            double w[QIB]; int am = 0;
+#pragma unroll
+            for (int q = 0; q < QIB; ++q) { w[q] = wsh16[q]; am |= act16[q] << q; }
+#pragma unroll
+            for (int q = 0; q < QIB; ++q) acc[q] = 0.;
+            for (int r = c + 1 + tid; r < m; r += QT) {
+                const double tv = tau * (xs[r - c] * scale);
+                double* pa = At + (int64_t)r * ldm + ka;
+                double* pb = At + (int64_t)r * ldm + kb;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (am & (1 << q)) { const double v = pa[q] - tv * w[q]; pa[q] = v; acc[q] += v * v; }
+                    if (am & (1 << (8 + q))) { const double v = pb[q] - tv * w[8 + q]; pb[q] = v; acc[8 + q] += v * v; }
+                }
+            }
+            block_sum16(acc, red16, out16);
+            if (tid < QIB && act16[tid]) cn2[(tid < 8 ? j0 : j0 + 1) * 8 + (tid & 7)] = out16[tid];
             __syncthreads();
         }
     }
