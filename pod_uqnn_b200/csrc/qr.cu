@@ -674,14 +674,31 @@ __global__ void __launch_bounds__(QT, 1) qrcp_kernel(QrcpArgs a) {
             for (int q = 0; q < QIB; ++q) { w[q] = wsh16[q]; am |= act16[q] << q; }
 #pragma unroll
             for (int q = 0; q < QIB; ++q) acc[q] = 0.;
-            for (int r = c + 1 + tid; r < m; r += QT) {
-                const double tv = tau * (xs[r - c] * scale);
-                double* pa = At + (int64_t)r * ldm + ka;
-                double* pb = At + (int64_t)r * ldm + kb;
+            if (am == 0xffff) {                                        // all 16 columns active: 16-byte accesses
+                for (int r = c + 1 + tid; r < m; r += QT) {
+                    const double tv = tau * (xs[r - c] * scale);
+                    double2* pa = reinterpret_cast<double2*>(At + (int64_t)r * ldm + ka);
+                    double2* pb = reinterpret_cast<double2*>(At + (int64_t)r * ldm + kb);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    if (am & (1 << q)) { const double v = pa[q] - tv * w[q]; pa[q] = v; acc[q] += v * v; }
-                    if (am & (1 << (8 + q))) { const double v = pb[q] - tv * w[8 + q]; pb[q] = v; acc[8 + q] += v * v; }
+                    for (int q = 0; q < 4; ++q) {
+                        double2 va = pa[q], vb = pb[q];
+                        va.x -= tv * w[2 * q]; va.y -= tv * w[2 * q + 1];
+                        vb.x -= tv * w[8 + 2 * q]; vb.y -= tv * w[8 + 2 * q + 1];
+                        pa[q] = va; pb[q] = vb;
+                        acc[2 * q] += va.x * va.x; acc[2 * q + 1] += va.y * va.y;
+                        acc[8 + 2 * q] += vb.x * vb.x; acc[8 + 2 * q + 1] += vb.y * vb.y;
+                    }
+                }
+            } else {
+                for (int r = c + 1 + tid; r < m; r += QT) {
+                    const double tv = tau * (xs[r - c] * scale);
+                    double* pa = At + (int64_t)r * ldm + ka;
+                    double* pb = At + (int64_t)r * ldm + kb;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (am & (1 << q)) { const double v = pa[q] - tv * w[q]; pa[q] = v; acc[q] += v * v; }
+                        if (am & (1 << (8 + q))) { const double v = pb[q] - tv * w[8 + q]; pb[q] = v; acc[8 + q] += v * v; }
+                    }
                 }
             }
             block_sum16(acc, red16, out16);
