@@ -15,6 +15,7 @@ const char* pb_set_global_error(const std::string& s) {
 
 int pb_reserve(pb_ctx* ctx, double** p, size_t* cap, size_t elems) {
     if (*cap >= elems && *p) return PB_OK;
+    PB_ENTER(ctx);
     if (*p) { PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(*p); *p = nullptr; *cap = 0; }
     cudaError_t e = cudaMalloc(p, elems * sizeof(double));
     if (e != cudaSuccess) { cudaGetLastError(); PB_FAIL(ctx, PB_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", elems * sizeof(double), cudaGetErrorString(e)); }
@@ -23,6 +24,7 @@ int pb_reserve(pb_ctx* ctx, double** p, size_t* cap, size_t elems) {
 }
 int pb_reserve_int(pb_ctx* ctx, int** p, size_t* cap, size_t elems) {
     if (*cap >= elems && *p) return PB_OK;
+    PB_ENTER(ctx);
     if (*p) { PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(*p); *p = nullptr; *cap = 0; }
     cudaError_t e = cudaMalloc(p, elems * sizeof(int));
     if (e != cudaSuccess) { cudaGetLastError(); PB_FAIL(ctx, PB_ERR_NOMEM, "cudaMalloc(%zu bytes) failed", elems * sizeof(int)); }
@@ -100,6 +102,7 @@ int pb_destroy(pb_ctx* ctx) {
     if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); for (auto& e : ctx->chunk_ev) if (e) cudaEventDestroy(e); }
     if (ctx->Gpart) cudaFree(ctx->Gpart);
     pbi_train_free(ctx);
+    pbi_gram_plan_free(ctx);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return PB_OK;
@@ -109,16 +112,16 @@ const char* pb_last_error(const pb_ctx* ctx) {
     if (ctx) return ctx->err.c_str();
     std::lock_guard<std::mutex> l(g_err_mu); return g_err.c_str();
 }
-int pb_set_stream(pb_ctx* ctx, void* s) { if (!ctx) return PB_ERR_ARG; ctx->stream = s ? (cudaStream_t)s : ctx->own_stream; return PB_OK; }
-int pb_sync(pb_ctx* ctx) { if (!ctx) return PB_ERR_ARG; PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return PB_OK; }
+int pb_set_stream(pb_ctx* ctx, void* s) { PB_ENTER(ctx); ctx->stream = s ? (cudaStream_t)s : ctx->own_stream; return PB_OK; }
+int pb_sync(pb_ctx* ctx) { PB_ENTER(ctx); PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return PB_OK; }
 int pb_device_info(pb_ctx* ctx, int* sm, int* maj, int* min_, size_t* mem) {
-    if (!ctx) return PB_ERR_ARG;
+    PB_ENTER(ctx);
     cudaDeviceProp p; PB_CUDA(ctx, cudaGetDeviceProperties(&p, ctx->device));
     if (sm) *sm = p.multiProcessorCount; if (maj) *maj = p.major; if (min_) *min_ = p.minor; if (mem) *mem = p.totalGlobalMem;
     return PB_OK;
 }
 int pb_last_ms(pb_ctx* ctx, int which, double* ms) {
-    if (!ctx || which < 0 || which >= PB_T_COUNT || !ms) return PB_ERR_ARG;
+    PB_ENTER(ctx); if (which < 0 || which >= PB_T_COUNT || !ms) return PB_ERR_ARG;
     if (which == PB_T_TN_KERNEL && ctx->tn_timing_pending) {
         PB_CUDA(ctx, cudaEventSynchronize(ctx->evk1));
         float t = 0; cudaEventElapsedTime(&t, ctx->evk0, ctx->evk1); ctx->ms[PB_T_TN_KERNEL] = t;
@@ -131,9 +134,9 @@ int pb_last_ms(pb_ctx* ctx, int which, double* ms) {
     }
     *ms = ctx->ms[which]; return PB_OK;
 }
-int pb_timer_start(pb_ctx* ctx) { if (!ctx) return PB_ERR_ARG; PB_CUDA(ctx, cudaEventRecord(ctx->evr0, ctx->stream)); return PB_OK; }
+int pb_timer_start(pb_ctx* ctx) { PB_ENTER(ctx); PB_CUDA(ctx, cudaEventRecord(ctx->evr0, ctx->stream)); return PB_OK; }
 int pb_timer_stop(pb_ctx* ctx, double* ms) {
-    if (!ctx || !ms) return PB_ERR_ARG;
+    PB_ENTER(ctx); if (!ms) return PB_ERR_ARG;
     PB_CUDA(ctx, cudaEventRecord(ctx->evr1, ctx->stream));
     PB_CUDA(ctx, cudaEventSynchronize(ctx->evr1));
     float t = 0; PB_CUDA(ctx, cudaEventElapsedTime(&t, ctx->evr0, ctx->evr1)); *ms = t; return PB_OK;
@@ -142,19 +145,18 @@ int64_t pb_kernel_launches(pb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // ---------------------------------------------------------------- memory
 int pb_malloc(pb_ctx* ctx, size_t bytes, void** dev) {
-    if (!ctx || !dev) return PB_ERR_ARG;
-    cudaSetDevice(ctx->device);
+    PB_ENTER(ctx); if (!dev) return PB_ERR_ARG;
     cudaError_t e = cudaMalloc(dev, bytes ? bytes : 8);
     if (e != cudaSuccess) { cudaGetLastError(); PB_FAIL(ctx, PB_ERR_NOMEM, "pb_malloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
     return PB_OK;
 }
-int pb_free(pb_ctx* ctx, void* dev) { if (!ctx) return PB_ERR_ARG; if (dev) { cudaStreamSynchronize(ctx->stream); PB_CUDA(ctx, cudaFree(dev)); } return PB_OK; }
-int pb_memset(pb_ctx* ctx, void* dev, int v, size_t bytes) { if (!ctx) return PB_ERR_ARG; PB_CUDA(ctx, cudaMemsetAsync(dev, v, bytes, ctx->stream)); return PB_OK; }
+int pb_free(pb_ctx* ctx, void* dev) { PB_ENTER(ctx); if (dev) { cudaStreamSynchronize(ctx->stream); PB_CUDA(ctx, cudaFree(dev)); } return PB_OK; }
+int pb_memset(pb_ctx* ctx, void* dev, int v, size_t bytes) { PB_ENTER(ctx); PB_CUDA(ctx, cudaMemsetAsync(dev, v, bytes, ctx->stream)); return PB_OK; }
 int pb_upload_async(pb_ctx* ctx, void* dev, const void* host, size_t bytes) {
-    if (!ctx) return PB_ERR_ARG; PB_CUDA(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream)); return PB_OK;
+    PB_ENTER(ctx); PB_CUDA(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream)); return PB_OK;
 }
 int pb_download_async(pb_ctx* ctx, void* host, const void* dev, size_t bytes) {
-    if (!ctx) return PB_ERR_ARG; PB_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream)); return PB_OK;
+    PB_ENTER(ctx); PB_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream)); return PB_OK;
 }
 int pb_upload(pb_ctx* ctx, void* dev, const void* host, size_t bytes) { PB_TRY(pb_upload_async(ctx, dev, host, bytes)); return pb_sync(ctx); }
 int pb_download(pb_ctx* ctx, void* host, const void* dev, size_t bytes) { PB_TRY(pb_download_async(ctx, host, dev, bytes)); return pb_sync(ctx); }
@@ -168,7 +170,7 @@ int pb_host_free(void* host) { if (host) cudaFreeHost(host); return PB_OK; }
 
 // ---------------------------------------------------------------- products
 int pb_gram(pb_ctx* ctx, const double* A, int64_t rows, int64_t cols, int64_t lda, double* G) {
-    if (!ctx) return PB_ERR_ARG;
+    PB_ENTER(ctx);
     if (lda < cols) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_gram: lda %lld < n_cols %lld", (long long)lda, (long long)cols);
     Timer t(ctx, PB_T_GRAM);
     PB_TRY(pbi_gemm_tn(ctx, A, lda, cols, A, lda, cols, rows, G, cols, 3));   // sym | time the main kernel
@@ -177,12 +179,12 @@ int pb_gram(pb_ctx* ctx, const double* A, int64_t rows, int64_t cols, int64_t ld
 }
 int pb_gemm_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const double* B, int64_t ldb, int64_t kb,
                int64_t rows, double* C) {
-    if (!ctx) return PB_ERR_ARG;
+    PB_ENTER(ctx);
     return pbi_gemm_tn(ctx, A, lda, ka, B, ldb, kb, rows, C, kb, 0);
 }
 int pb_gemm_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m, const double* B, int64_t ldb,
                int64_t k, double* Y, int64_t ldy) {
-    if (!ctx) return PB_ERR_ARG;
+    PB_ENTER(ctx);
     return pbi_gemm_nn(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, nullptr, 0, nullptr);
 }
 
@@ -221,7 +223,7 @@ static int fetch_sigma(pb_ctx* ctx, const double* sig_dev, int64_t count, int64_
 }
 
 int pb_pod_from_gram(pb_ctx* ctx, const double* G, int64_t m, double eps, int n_L_in, int mode, int* n_L, int* n_keep) {
-    if (!ctx || !n_L) return PB_ERR_ARG;
+    PB_ENTER(ctx); if (!n_L) return PB_ERR_ARG;
     if (mode == PB_POD_TSQR) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod_from_gram: the TSQR mode starts from pb_tsqr_r / pb_pod_from_r, not from a Gram matrix");
     if (mode < PB_POD_GRAM || mode > PB_POD_ACCURATE) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod: unknown mode %d", mode);
     if (!(eps >= 0.) || eps >= 1.) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod: eps must be in [0, 1)");
@@ -236,14 +238,12 @@ int pb_pod_from_gram(pb_ctx* ctx, const double* G, int64_t m, double eps, int n_
     const double shift_rel = full ? 2. * (double)m * DBL_EPSILON : 0.;
     {   // measured on B200 (profiles/r01_notes.md): loosening the first-pass rotation threshold of the accurate
         // mode to 1e-9 / 1e-6 costs 4 / 6 digits of subspace angle and saves < 15 % -- off unless asked for
-        extern double g_jacobi_tol_override;
         static const double tol1 = []{ const char* e = getenv("PB_ACC_TOL1"); return e ? atof(e) : 0.; }();
-        if (mode == PB_POD_ACCURATE && tol1 > 0.) g_jacobi_tol_override = tol1;
+        if (mode == PB_POD_ACCURATE && tol1 > 0.) ctx->eig_jacobi_tol = tol1;
     }
     {   // a second pass re-orthogonalises: when the first factor is a single 32-vector pair, its in-kernel solve
         // (iterated to the rotation threshold) is taken as is, without the confirming sweep
-        extern bool g_trust_single_pair;
-        g_trust_single_pair = (mode != PB_POD_GRAM);
+        ctx->eig_trust_single_pair = (mode != PB_POD_GRAM);
     }
     PB_TRY(pbi_eig_psd(ctx, G, m, tol_rel, shift_rel, &ctx->At, &ctx->At_cap, ctx->sig, ctx->nrm, ctx->perm,
                        &ctx->r, &ctx->sweeps1, 40));
@@ -256,7 +256,7 @@ int pb_pod_from_gram(pb_ctx* ctx, const double* G, int64_t m, double eps, int n_
 }
 
 int pb_pod_pass2_gram(pb_ctx* ctx, const double* A, int64_t rows, int64_t lda, double* Y, double* G2) {
-    if (!ctx) return PB_ERR_ARG;
+    PB_ENTER(ctx);
     const int keep = ctx->n_keep; const int64_t m = ctx->m;
     if (keep <= 0) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod_pass2_gram: the last decomposition has no second pass (mode GRAM)");
     PB_TRY(pb_reserve(ctx, &ctx->Wk, &ctx->Wk_cap, (size_t)m * keep));
@@ -267,7 +267,7 @@ int pb_pod_pass2_gram(pb_ctx* ctx, const double* A, int64_t rows, int64_t lda, d
 }
 
 int pb_pod_pass2_finish(pb_ctx* ctx, const double* G2, double eps, int n_L_in, int* n_L) {
-    if (!ctx || !n_L) return PB_ERR_ARG;
+    PB_ENTER(ctx); if (!n_L) return PB_ERR_ARG;
     const int keep = ctx->n_keep;
     if (keep <= 0) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod_pass2_finish: no second pass pending");
     PB_TRY(pb_reserve(ctx, &ctx->sig2, &ctx->sig2_cap, (size_t)keep + 32));
@@ -283,7 +283,7 @@ int pb_pod_pass2_finish(pb_ctx* ctx, const double* G2, double eps, int n_L_in, i
 }
 
 int pb_pod_basis(pb_ctx* ctx, const double* A, int64_t rows, int64_t lda, const double* Y, double* V, int64_t ldv) {
-    if (!ctx) return PB_ERR_ARG;
+    PB_ENTER(ctx);
     const int nl = ctx->n_L;
     if (nl <= 0) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod_basis: no decomposition available");
     Timer t(ctx, PB_T_BASIS);
@@ -305,7 +305,7 @@ int pb_pod_basis(pb_ctx* ctx, const double* A, int64_t rows, int64_t lda, const 
 }
 
 int pb_pod_sigma(pb_ctx* ctx, double* sigma_host, int64_t capacity, int64_t* count) {
-    if (!ctx) return PB_ERR_ARG;
+    PB_ENTER(ctx);
     if (ctx->sigma_pending) {
         PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->sigma_host.assign((size_t)ctx->sig_total, 0.);
@@ -319,7 +319,7 @@ int pb_pod_sigma(pb_ctx* ctx, double* sigma_host, int64_t capacity, int64_t* cou
 }
 
 int pb_pod_right(pb_ctx* ctx, double* Z, int64_t ldz) {
-    if (!ctx) return PB_ERR_ARG;
+    PB_ENTER(ctx);
     const int nl = ctx->n_L; const int64_t m = ctx->m;
     if (nl <= 0) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod_right: no decomposition available");
     if (ctx->pass2_done) {
@@ -335,7 +335,7 @@ int pb_pod_right(pb_ctx* ctx, double* Z, int64_t ldz) {
 
 // ---------------------------------------------------------------- TSQR mode
 int pb_tsqr_r(pb_ctx* ctx, const double* A, int64_t rows, int64_t cols, int64_t lda, double* R) {
-    if (!ctx || !A || !R) return PB_ERR_ARG;
+    PB_ENTER(ctx); if (!A || !R) return PB_ERR_ARG;
     if (rows <= 0 || cols <= 0 || lda < cols) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_tsqr_r: bad shape (%lld x %lld, ld %lld)",
                                                        (long long)rows, (long long)cols, (long long)lda);
     Timer t(ctx, PB_T_QR);
@@ -345,7 +345,7 @@ int pb_tsqr_r(pb_ctx* ctx, const double* A, int64_t rows, int64_t cols, int64_t 
 }
 
 int pb_pod_from_r(pb_ctx* ctx, const double* R, int64_t m, double eps, int n_L_in, int* n_L) {
-    if (!ctx || !R || !n_L) return PB_ERR_ARG;
+    PB_ENTER(ctx); if (!R || !n_L) return PB_ERR_ARG;
     if (m <= 0 || m > 8192) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod_from_r: order %lld outside (0, 8192]", (long long)m);
     if (!(eps >= 0.) || eps >= 1.) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod: eps must be in [0, 1)");
     Timer t(ctx, PB_T_EIG);
@@ -386,7 +386,7 @@ static int pod_after_gram(pb_ctx* ctx, const double* A, int64_t rows, int64_t m,
 }
 
 int pb_pod(pb_ctx* ctx, const double* U, int64_t n_h, int64_t n_st, int64_t ldu, double eps, int n_L_in, int mode, int* n_L) {
-    if (!ctx || !n_L) return PB_ERR_ARG;
+    PB_ENTER(ctx); if (!n_L) return PB_ERR_ARG;
     if (n_h <= 0 || n_st <= 0 || ldu < n_st) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod: bad shape (%lld x %lld, ld %lld)",
                                                        (long long)n_h, (long long)n_st, (long long)ldu);
     Timer t_total(ctx, PB_T_POD_TOTAL);
@@ -470,7 +470,7 @@ int gram_host_chunked(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_
 
 int pb_gram_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, int64_t ldu_host, double* U_dev,
                  double* G_dev) {
-    if (!ctx || !U_host || !U_dev || !G_dev) return PB_ERR_ARG;
+    PB_ENTER(ctx); if (!U_host || !U_dev || !G_dev) return PB_ERR_ARG;
     if (n_h <= 0 || n_st <= 0 || ldu_host < n_st) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_gram_host: bad shape");
     int rc = gram_host_chunked(ctx, U_host, n_h, n_st, ldu_host, U_dev, G_dev);
     if (rc != 1) return rc;
@@ -482,7 +482,7 @@ int pb_gram_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, i
 // POD of a HOST matrix (see gram_host_chunked)
 int pb_pod_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, int64_t ldu_host, double* U_dev,
                 double eps, int n_L_in, int mode, int* n_L) {
-    if (!ctx || !n_L || !U_host || !U_dev) return PB_ERR_ARG;
+    PB_ENTER(ctx); if (!n_L || !U_host || !U_dev) return PB_ERR_ARG;
     if (n_h <= 0 || n_st <= 0 || ldu_host < n_st) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod_host: bad shape");
     Timer t_total(ctx, PB_T_POD_TOTAL);
     const int64_t m = n_st;
@@ -502,7 +502,7 @@ int pb_pod_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, in
 }
 
 int pb_pod_basis_full(pb_ctx* ctx, const double* U, int64_t n_h, int64_t n_st, int64_t ldu, double* V, int64_t ldv) {
-    if (!ctx) return PB_ERR_ARG;
+    PB_ENTER(ctx);
     if (ldv < ctx->n_L) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod_basis_full: ldv %lld < n_L %d", (long long)ldv, ctx->n_L);
     if (!ctx->wide) return pb_pod_basis(ctx, U, n_h, ldu, ctx->pass2_done ? ctx->Ybuf : nullptr, V, ldv);
     (void)n_st;
@@ -590,7 +590,7 @@ int fast_pod_stage1_batched(pb_ctx* ctx, const double* U, int64_t n_h, int n_t, 
 
 int pb_fast_pod(pb_ctx* ctx, const double* U, int64_t n_h, int n_t, int64_t n_s, int64_t ldu,
                 double eps, double eps_init, int mode, int* n_L, int* ranks_host) {
-    if (!ctx || !n_L) return PB_ERR_ARG;
+    PB_ENTER(ctx); if (!n_L) return PB_ERR_ARG;
     if (n_t <= 0 || n_s <= 0 || ldu < n_s * n_t) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_fast_pod: bad shape");
     if (mode < PB_POD_GRAM || mode > PB_POD_TSQR) PB_FAIL(ctx, PB_ERR_ARG, "pb_fast_pod: unknown mode %d", mode);
     if (!(eps >= 0.) || eps >= 1. || !(eps_init >= 0.) || eps_init >= 1.) PB_FAIL(ctx, PB_ERR_ARG, "pb_fast_pod: eps in [0, 1)");
@@ -627,7 +627,7 @@ int pb_fast_pod(pb_ctx* ctx, const double* U, int64_t n_h, int n_t, int64_t n_s,
 }
 
 int pb_fast_pod_basis(pb_ctx* ctx, double* V, int64_t ldv) {
-    if (!ctx) return PB_ERR_ARG;
+    PB_ENTER(ctx);
     if (!ctx->Uf || ctx->uf_cols <= 0) PB_FAIL(ctx, PB_ERR_ARG, "pb_fast_pod_basis: call pb_fast_pod first");
     return pb_pod_basis_full(ctx, ctx->Uf, ctx->uf_rows, ctx->uf_cols, ctx->uf_ld, V, ldv);
 }
@@ -677,18 +677,18 @@ int struct_permute(pb_ctx* ctx, const double* in, double* out, int64_t n_h, int 
 }  // namespace
 
 int pb_struct_to_matrix(pb_ctx* ctx, const double* Us, int64_t n_h, int n_t, int64_t n_s, double* U, int64_t ldu) {
-    if (!ctx) return PB_ERR_ARG;
+    PB_ENTER(ctx);
     return struct_permute(ctx, Us, U, n_h, n_t, n_s, ldu, 1);
 }
 int pb_matrix_to_struct(pb_ctx* ctx, const double* U, int64_t ldu, int64_t n_h, int n_t, int64_t n_s, double* Us) {
-    if (!ctx) return PB_ERR_ARG;
+    PB_ENTER(ctx);
     return struct_permute(ctx, U, Us, n_h, n_t, n_s, ldu, 0);
 }
 
 // ------------------------------------------------- projection / reconstruction
 int pb_project(pb_ctx* ctx, const double* V, int64_t ldv, int n_L, const double* U, int64_t ldu,
                int64_t rows, int64_t n, double* v) {
-    if (!ctx) return PB_ERR_ARG;
+    PB_ENTER(ctx);
     if (n_L <= 0 || n <= 0 || ldv < n_L || ldu < n) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_project: bad shape");
     Timer t(ctx, PB_T_PROJECT);
     // C (n_L x n) = V^T U, then v = C^T (the reference returns the transposed view, podnnmodel.py:437)
@@ -701,7 +701,7 @@ int pb_project(pb_ctx* ctx, const double* V, int64_t ldv, int n_L, const double*
 
 int pb_reconstruct(pb_ctx* ctx, const double* V, int64_t ldv, int n_L, const double* v, int64_t n, int64_t rows,
                    const double* U, int64_t ldu, double* U_pod, int64_t ldp, double* pod_sig) {
-    if (!ctx) return PB_ERR_ARG;
+    PB_ENTER(ctx);
     if (n_L <= 0 || n <= 0 || ldv < n_L) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_reconstruct: bad shape");
     if (pod_sig && !U) PB_FAIL(ctx, PB_ERR_ARG, "pb_reconstruct: pod_sig needs U");
     if (!U_pod && !pod_sig) PB_FAIL(ctx, PB_ERR_ARG, "pb_reconstruct: nothing to compute");

@@ -66,9 +66,14 @@ struct pb_ctx {
     double* qr_W = nullptr; double* qr_scr = nullptr; double* qr_scr2 = nullptr;   // TSQR mode (qr.cu)
     double* qr_stack = nullptr; size_t qr_stack_cap = 0;
     size_t qr_W_cap = 0, qr_scr_cap = 0, qr_scr2_cap = 0;
+    // per-call knobs of the next eigensolve (set by the POD orchestration, consumed and cleared by eig.cu)
+    bool eig_trust_single_pair = false;   // skip the confirming sweep of a single-pair problem (a second pass follows)
+    double eig_jacobi_tol = 0.;           // > 0: rotation threshold of the next eig (first pass of the accurate mode)
+    void* gram_plan = nullptr;            // stream-K schedule of the last Gram shape (gram_tma.cu), owned by the context
     void* train_state = nullptr;     // pb_ensemble_train: work buffers, side stream, captured epoch graph (train.cu)
 };
 void pbi_train_free(pb_ctx* ctx);
+void pbi_gram_plan_free(pb_ctx* ctx);
 
 const char* pb_set_global_error(const std::string& s);
 
@@ -77,6 +82,11 @@ const char* pb_set_global_error(const std::string& s);
 
 #define PB_CUDA(ctx, expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
     PB_FAIL(ctx, PB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); } } while (0)
+
+// every extern "C" entry point that takes a context: null check + make the context's GPU the calling thread's current
+// device (the caller may be a new Python thread, or torch may have switched devices since the last call)
+#define PB_ENTER(ctx) do { if (!(ctx)) return PB_ERR_ARG; int _dev = -1; \
+    if (cudaGetDevice(&_dev) != cudaSuccess || _dev != (ctx)->device) PB_CUDA(ctx, cudaSetDevice((ctx)->device)); } while (0)
 
 #define PB_TRY(expr) do { int _r = (expr); if (_r != PB_OK) return _r; } while (0)
 

@@ -485,8 +485,6 @@ __global__ void factor_to_right_kernel(const double* __restrict__ At, int64_t ld
 
 }  // namespace
 
-bool g_trust_single_pair = false;      // next eig: skip the confirming sweep of a single-pair problem (a second pass follows)
-double g_jacobi_tol_override = 0.;   // > 0: rotation threshold of the next eig (first pass of the accurate mode)
 static int g_cross_rounds = []{ const char* e = getenv("PB_JACOBI_CROSS"); return e ? atoi(e) : 1; }();
 static int g_inner_sweeps = []{ const char* e = getenv("PB_JACOBI_INNER"); return e ? atoi(e) : 3; }();
 // device ints layout in ctx->d_int: [0] r (Cholesky), [1] n_rot, [2] n_L, [3] r_eff
@@ -519,13 +517,13 @@ int pbi_jacobi_factor(pb_ctx* ctx, double* At, int64_t m, int r, const double* s
     const int nvec = nb * JB;
     // rotation threshold relative to the column norms (dgesvj uses sqrt(m) eps): below it the
     // pair Gram entry is rounding noise of the m-long dot product
-    const double tol = g_jacobi_tol_override > 0. ? g_jacobi_tol_override : std::max(4., sqrt((double)m)) * DBL_EPSILON;
-    g_jacobi_tol_override = 0.;
+    const double tol = ctx->eig_jacobi_tol > 0. ? ctx->eig_jacobi_tol : std::max(4., sqrt((double)m)) * DBL_EPSILON;
+    ctx->eig_jacobi_tol = 0.;
     size_t jac_smem = sizeof(double) * 2 * JP * JPX;
     PB_CUDA(ctx, cudaFuncSetAttribute(jacobi_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jac_smem));
     int sweeps = 0; bool converged = false;
-    const bool trust_single = g_trust_single_pair && nb == 2;
-    g_trust_single_pair = false;
+    const bool trust_single = ctx->eig_trust_single_pair && nb == 2;
+    ctx->eig_trust_single_pair = false;
     for (; sweeps < max_sweeps && !converged; ++sweeps) {
         PB_CUDA(ctx, cudaMemsetAsync(ctx->d_int + 1, 0, sizeof(int), ctx->stream));
         const int rounds = nb > 2 ? nb - 1 : 1;
@@ -735,8 +733,8 @@ int pbi_eig_psd_batched(pb_ctx* ctx, const double* G_all, int64_t m, int batch, 
     size_t jac_smem = sizeof(double) * 2 * JP * JPX;
     PB_CUDA(ctx, cudaFuncSetAttribute(jacobi_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jac_smem));
     int sweeps = 0; bool converged = false;
-    const bool trust_single = g_trust_single_pair && nb == 2;
-    g_trust_single_pair = false;
+    const bool trust_single = ctx->eig_trust_single_pair && nb == 2;
+    ctx->eig_trust_single_pair = false;
     for (; sweeps < max_sweeps && !converged; ++sweeps) {
         PB_CUDA(ctx, cudaMemsetAsync(ctx->d_int + 1, 0, sizeof(int), ctx->stream));
         const int rounds = nb > 2 ? nb - 1 : 1;

@@ -183,7 +183,7 @@ __global__ void dct_table_kernel(double* __restrict__ out, int64_t rows, int r, 
 extern "C" int pb_snapshots(pb_ctx* ctx, int field, int dim, int64_t n_xyz, const double* X_dev,
                             int64_t n_s, int n_mu, const double* mu_dev, int n_t, const double* t_dev,
                             int64_t row0, int64_t n_rows, double* U_dev, int64_t ldu) {
-    if (!ctx) return PB_ERR_ARG;
+    PB_ENTER(ctx);
     if (n_xyz <= 0 || n_s <= 0 || n_rows < 0 || row0 < 0 || row0 + n_rows > n_xyz)
         PB_FAIL(ctx, PB_ERR_SHAPE, "pb_snapshots: bad node range [%lld, %lld) of %lld", (long long)row0,
                 (long long)(row0 + n_rows), (long long)n_xyz);
@@ -222,7 +222,7 @@ extern "C" int pb_snapshots_ackley_indexed(pb_ctx* ctx, int64_t n_xyz, const dou
                                            const int* ix_dev, int n_uy, const double* uy_dev, const int* iy_dev,
                                            int64_t n_s, const double* mu_dev, int64_t row0, int64_t n_rows,
                                            double* U_dev, int64_t ldu) {
-    if (!ctx) return PB_ERR_ARG;
+    PB_ENTER(ctx);
     if (n_xyz <= 0 || n_s <= 0 || n_rows < 0 || row0 < 0 || row0 + n_rows > n_xyz || n_ux <= 0 || n_uy <= 0 || ldu < n_s)
         PB_FAIL(ctx, PB_ERR_SHAPE, "pb_snapshots_ackley_indexed: bad shape");
     if (n_rows == 0) return PB_OK;
@@ -246,7 +246,7 @@ extern "C" int pb_snapshots_ackley_indexed(pb_ctx* ctx, int64_t n_xyz, const dou
 
 extern "C" int pb_dct_lowrank(pb_ctx* ctx, int64_t n_h, int64_t n_s, int r, double decay,
                               int64_t row0, int64_t n_rows, double* U_dev, int64_t ldu) {
-    if (!ctx) return PB_ERR_ARG;
+    PB_ENTER(ctx);
     if (r <= 0 || r > n_s || row0 + n_rows > n_h) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_dct_lowrank: bad shape");
     double *phi = nullptr, *psit = nullptr;
     const int64_t chunk = 1 << 20;                      // rows per GEMM call (bounds the phi table)

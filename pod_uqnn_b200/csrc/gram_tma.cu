@@ -159,6 +159,8 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ka, int64_t rows, 
 //     issues 3/4 of the DMMAs of an off-diagonal tile (the consumer warps are decoupled, no barrier);
 //   * the partition is static (host tables), so the partial tiles are summed in a fixed order.
 struct SegEntry { int ti, tj, k0, k1, slot; };
+struct GramPlan { int64_t ka = -1, rows = -1; int P = 0; int nslots = 0; std::vector<SegEntry> segs; std::vector<int> seg_begin,
+                  tile_off, tile_src; int* d_tab = nullptr; size_t d_cap = 0; };
 
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 gram_streamk_kernel(const __grid_constant__ CUtensorMap tmap, const SegEntry* __restrict__ segs,
@@ -308,6 +310,13 @@ EncodeTiledFn get_encode() {
 
 }  // namespace
 
+void pbi_gram_plan_free(pb_ctx* ctx) {
+    if (!ctx->gram_plan) return;
+    GramPlan* p = static_cast<GramPlan*>(ctx->gram_plan);
+    if (p->d_tab) cudaFree(p->d_tab);
+    delete p; ctx->gram_plan = nullptr;
+}
+
 // returns PB_OK when the TMA kernel was launched, 1 when the caller should use the cp.async kernel
 int pbi_gram_tma(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int64_t rows, int splits,
                  int64_t rows_per_split, double* ws, int64_t split_stride, bool time_it) {
@@ -361,9 +370,9 @@ int pbi_gram_streamk(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int6
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return 1;
 
     // ---- static partition (cached per shape)
-    struct Plan { int64_t ka = -1, rows = -1; int P = 0; int nslots = 0; std::vector<SegEntry> segs; std::vector<int> seg_begin,
-                  tile_off, tile_src; int* d_tab = nullptr; size_t d_cap = 0; };
-    static thread_local Plan plan;
+    // the schedule and its device table belong to the context (one GPU each): another context in the same thread builds its own
+    if (!ctx->gram_plan) ctx->gram_plan = new GramPlan();
+    GramPlan& plan = *static_cast<GramPlan*>(ctx->gram_plan);
     if (plan.ka != ka || plan.rows != rows || plan.P != P) {
         plan.ka = ka; plan.rows = rows; plan.P = P; plan.segs.clear(); plan.seg_begin.assign(P + 1, 0);
         // Static schedule.  Two parts:

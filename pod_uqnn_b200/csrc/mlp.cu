@@ -410,7 +410,7 @@ extern "C" int pb_ensemble_predict(pb_ctx* ctx, int n_members, int n_layers, con
                                    const double* weights_dev, int norm_kind, const double* norm_a_dev,
                                    const double* norm_b_dev, double soft_0, const double* X_dev, int64_t N,
                                    double* v_mean_dev, double* v_sig_dev) {
-    if (!ctx || !dims) return PB_ERR_ARG;
+    PB_ENTER(ctx); if (!dims) return PB_ERR_ARG;
     if (n_members <= 0 || n_layers < 1 || n_layers > MAX_LAYERS || N <= 0)
         PB_FAIL(ctx, PB_ERR_SHAPE, "pb_ensemble_predict: need 1..%d layers, >= 1 member, N > 0", MAX_LAYERS);
     const int out_last = dims[n_layers];
@@ -455,7 +455,7 @@ extern "C" int pb_ensemble_predict(pb_ctx* ctx, int n_members, int n_layers, con
 extern "C" int pb_predict_U(pb_ctx* ctx, const double* V_dev, int64_t ldv, int64_t n_rows, int n_L,
                             const double* v_mean_dev, const double* v_sig_dev, int64_t N,
                             int samples, uint64_t seed, double* U_mean_dev, double* U_sig_dev, int64_t ldo) {
-    if (!ctx) return PB_ERR_ARG;
+    PB_ENTER(ctx);
     if (n_L <= 0 || N <= 0 || n_rows <= 0 || ldo < N) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_predict_U: bad shape");
     if (samples < 0 || samples == 1) PB_FAIL(ctx, PB_ERR_ARG, "pb_predict_U: samples must be 0 (closed form) or >= 2");
     if (samples > 0) {

@@ -53,7 +53,7 @@ __global__ void fill_kernel(double4* __restrict__ out, size_t n, double v) {
 }  // namespace
 
 extern "C" int pb_probe_fp64_peak(pb_ctx* ctx, int kind, double* tflops) {
-    if (!ctx || !tflops || kind < 0 || kind > 2) return PB_ERR_ARG;
+    PB_ENTER(ctx); if (!tflops || kind < 0 || kind > 2) return PB_ERR_ARG;
     double* out = nullptr;
     PB_CUDA(ctx, cudaMalloc(&out, 64));
     const int blocks = ctx->sm_count * 4;
@@ -80,7 +80,7 @@ extern "C" int pb_probe_fp64_peak(pb_ctx* ctx, int kind, double* tflops) {
 }
 
 extern "C" int pb_probe_hbm_copy(pb_ctx* ctx, size_t bytes, double* gbs) {
-    if (!ctx || !gbs) return PB_ERR_ARG;
+    PB_ENTER(ctx); if (!gbs) return PB_ERR_ARG;
     bytes = bytes / 32 * 32;
     void *a = nullptr, *b = nullptr;
     PB_CUDA(ctx, cudaMalloc(&a, bytes)); PB_CUDA(ctx, cudaMalloc(&b, bytes));
@@ -104,7 +104,7 @@ extern "C" int pb_probe_hbm_copy(pb_ctx* ctx, size_t bytes, double* gbs) {
 }
 
 extern "C" int pb_flush_l2(pb_ctx* ctx) {
-    if (!ctx) return PB_ERR_ARG;
+    PB_ENTER(ctx);
     const size_t bytes = (size_t)256 << 20;     // 2 x the 126 MB L2
     if (!ctx->flush) { PB_CUDA(ctx, cudaMalloc(&ctx->flush, bytes)); ctx->flush_bytes = bytes; }
     fill_kernel<<<ctx->sm_count * 8, 512, 0, ctx->stream>>>((double4*)ctx->flush, bytes / 32, 0.0);

@@ -17,6 +17,7 @@
 // per epoch: at the reference's sizes (N = 400..4000 rows, 128-wide layers) the step is bound by
 // kernel latency, not by flops.
 #include "common.cuh"
+#include <mutex>
 #include "tile_ops.cuh"
 
 namespace {
@@ -1071,11 +1072,14 @@ extern "C" int pb_ensemble_train(pb_ctx* ctx, int n_members, int n_layers, const
     if (epochs == 0) return PB_OK;
     if (n_members > 64) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_ensemble_train: at most 64 members per call (got %d)", n_members);
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
-    {
-        static bool configured = false;
-        if (!configured) {
+    {   // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: configure once per GPU, under a lock
+        static std::mutex cfg_mu;
+        static bool configured[64] = {false};
+        std::lock_guard<std::mutex> lk(cfg_mu);
+        const int d = ctx->device;
+        if (d < 0 || d >= 64 || !configured[d]) {
             if (configure_all() != PB_OK) PB_FAIL(ctx, PB_ERR_CUDA, "pb_ensemble_train: kernel configuration failed: %s", pb_last_error(nullptr));
-            configured = true;
+            if (d >= 0 && d < 64) configured[d] = true;
         }
     }
 

@@ -107,16 +107,7 @@ class PodnnModel:
         self._V_dev = Vd
         self.V = Vd.download()
         self.n_L = self.V.shape[1]
-        v_train = self._project_dev(U_train_d).download()
-        v_val = self._project_dev(U_val_d).download() if U_val_d is not None else None
-        # POD error (podnnmodel.py:251-253), fused: U_pod is never materialised
-        vt = ctx.to_device(v_train)
-        sig = ctx.alloc(self.n_h)
-        ctx.check(L.pb_reconstruct(ctx.h, Vd.ptr, Vd.ld, self.n_L, vt.ptr, v_train.shape[0], self.n_h,
-                                   U_train_d.ptr, U_train_d.ld, None, 0, sig.ptr))
-        self.pod_sig = sig.download()
-        print(f"Mean pod sig: {self.pod_sig.mean()}")
-        return v_train, v_val
+        return self._finish_projection(U_train_d, U_val_d)
 
     def _project_dev(self, Ud):
         ctx = self.ctx
@@ -191,15 +182,17 @@ class PodnnModel:
             v_train, v_val = self._finish_projection(Ut, Uv)
         else:
             v_train, v_val = self._pod_project(Ut, Uv, eps, None, n_L, len(tr))
-        if save_cache:
-            self.save_train_data(X_v_train, v_train, U_train, X_v_val, v_val, U_val)
+        # the reference saves unconditionally (:196; `save_cache` is accepted and ignored there too): gen.py ->
+        # train.py relies on PodnnModel.load() finding train_data.pkl
+        self.save_train_data(X_v_train, v_train, U_train, X_v_val, v_val, U_val)
         return X_v_train, v_train, X_v_val, v_val, U_val
 
     def _finish_projection(self, Ut, Uv):
         ctx, L = self.ctx, _lib.lib()
-        v_train = self._project_dev(Ut).download()
-        v_val = self._project_dev(Uv).download() if Uv is not None else None
-        vt, sig = ctx.to_device(v_train), ctx.alloc(self.n_h)
+        vt = self._project_dev(Ut)                 # stays in HBM for the POD error below (podnnmodel.py:251-253,
+        v_train = vt.download()                    # fused: U_pod is never materialised)
+        v_val = self._project_dev(Uv).download() if Uv is not None else np.zeros((0, self.n_L))
+        sig = ctx.alloc(self.n_h)
         ctx.check(L.pb_reconstruct(ctx.h, self._V_dev.ptr, self._V_dev.ld, self.n_L, vt.ptr, v_train.shape[0],
                                    self.n_h, Ut.ptr, Ut.ld, None, 0, sig.ptr))
         self.pod_sig = sig.download()

@@ -113,6 +113,16 @@ def test_convert_multigpu_data(ctx, tmp_path):
     assert np.array_equal(U_va, U_va_r) and np.array_equal(X_tr, X_v[idx[:lim]])
     _, s = cmp.align_signs(model.V, Vr)
     assert cmp.rel_err(v_tr * s, po.project_to_v(Vr, U_tr_r)) <= 1e-7
+    # the reference's gen.py -> train.py hand-over: convert_multigpu_data always writes train_data.pkl (:196), and a
+    # fresh model finds it (load_train_data is what PodnnModel.load() calls first)
+    fresh = PodnnModel(str(tmp_path), n_v, x_mesh, 0, ctx=ctx)
+    X_tr2, v_tr2, U_tr2, X_va2, v_va2, U_va2 = fresh.load_train_data()
+    assert fresh.n_L == model.n_L and np.array_equal(fresh.V, model.V) and np.array_equal(v_tr2, v_tr)
+    assert np.array_equal(U_va2, U_va) and np.array_equal(v_va2, v_va)
+    # no validation split: empty arrays, not None
+    np.random.seed(9)
+    out = model.convert_multigpu_data(U_struct, X_v, (1.0, 0.0), 1e-10)
+    assert out[3].shape == (0, model.n_L) and out[2].shape == (0, 1) and out[4].shape[1] == 0
 
 
 def test_workflow_gen_train_predict(ctx, tmp_path, capsys):
