@@ -13,19 +13,39 @@ with NCCL all-reduces, the small eigensolve is replicated.
 
 value  : algorithmic TFLOP/s, (n_h n_s (n_s+1) + 4 n_h n_s n_L) / wall, U resident in HBM.
 e2e    : the same metric through the reference-facing call with HOST buffers: the step uploads the
-         U slab from pinned host memory and downloads V and v.
+         U slab from pinned host memory and downloads V and v.  e2e_api: the Python entry points
+         pod.perform_pod(ndarray) + PodnnModel.project_to_v(ndarray) on ordinary (pageable) numpy
+         arrays, timed with time.perf_counter around the calls.
 roofline: the split-K DMMA Gram kernel against the fp64 tensor peak measured live in this process
          (MEASURED_PEAKS.json carries no fp64 figure).
-cpu_baseline / --impl reference: the reference's algorithm (numpy.linalg.svd -> LAPACK dgesdd, the
-         routine numba calls in pod.py:16, + the V and projection products) from oracle/, on the
-         host cores, on a bounded row sample of the same workload.
+c5     : BASELINE.json configs[4] (the north-star target): the DCT known-answer slab, 1.25 M rows
+         per GPU x 4096 snapshots, modes gram2 AND tsqr, POD + projection, with the closed-form
+         rank / singular values / modes ASSERTED (the run fails otherwise).
+parity : at N > 1 the sharded C2 result is compared on rank 0 with a single-GPU run over the same
+         rows (rank, singular values, rank 0's rows of V); the run fails on a mismatch.
+cpu_baseline / --impl reference: the reference's OWN perform_pod (oracle/_ref, byte copies of
+         poduqnn/pod.py made by oracle/build_ref.py; numba -> LAPACK dgesdd) + the projection of
+         podnnmodel.py:437, on all host cores, on the same matrix.  Falls back to the numpy port in
+         oracle/pod_oracle.py (kind "port") only when oracle/_ref was never built.
 """
+import os
+import sys
+
+# ---- host threads of the CPU legs: decided BEFORE numpy / numba load their thread pools.  torchrun exports
+#      OMP_NUM_THREADS=1 to every rank; the reference arm must use all host cores (rank 0 alone works).
+try:
+    HOST_CORES = len(os.sched_getaffinity(0))
+except AttributeError:
+    HOST_CORES = os.cpu_count() or 1
+_IMPL_REFERENCE = any(a == "reference" or a == "--impl=reference" for a in sys.argv[1:])
+if _IMPL_REFERENCE or int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMBA_NUM_THREADS"):
+        os.environ[_k] = str(HOST_CORES)
+
 import argparse
 import json
-import os
 import statistics
 import subprocess
-import sys
 import tempfile
 import time
 
@@ -36,7 +56,7 @@ sys.path.insert(0, ROOT)
 
 N_X, N_Y, N_S, EPS, MODE = 400, 400, 1000, 1e-10, "gram2"
 METRIC, UNIT = "pod_fp64_tflops", "TFLOP/s"
-CPU_SAMPLE_ROWS = 160000   # the whole C2 matrix: ~7 s per pass on the 16 host cores of the GPU box
+C5_ROWS_PER_GPU, C5_NS, C5_R, C5_DECAY = 1_250_000, 4096, 256, 0.25
 
 
 def algo_flops(n_h, n_s, n_L):
@@ -52,44 +72,109 @@ def workload_config(n_gpus):
             "l2_policy": "inputs larger than L2 (U slab = 1.28 GB vs 126 MB L2); no flush needed"}
 
 
+def blas_threads():
+    """Threads the BLAS / numba pools really run with (reported next to every CPU number)."""
+    out = {"host_cores": HOST_CORES}
+    try:
+        from threadpoolctl import threadpool_info
+        out["blas"] = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:  # noqa: BLE001
+        out["blas"] = None
+    try:
+        import numba
+        out["numba"] = numba.get_num_threads()
+    except Exception:  # noqa: BLE001
+        out["numba"] = None
+    return out
+
+
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_reference_steps(steps, warmup, rows=CPU_SAMPLE_ROWS):
-    """The oracle port of perform_pod + projection on the first `rows` mesh nodes of C2."""
-    from oracle import pod_oracle as po
+def ackley_matrix_host(n_gpus, rows=None):
+    """The C2 snapshot matrix of the weak-scaled workload (400 x 400 N mesh, the same mu), built on the host by
+    broadcasting the reference's field formula (2d_ackley/hyperparams.py:51-57) over row chunks.  Input generation
+    only: never inside a timed region."""
     from pod_uqnn_b200 import workloads as wl
-    w = wl.ackley(N_X, N_Y, N_S)
-    x_mesh = w["x_mesh"][:rows]
-    _, U, _, _ = po.create_snapshots(x_mesh, 1, 0, po.u_ackley, w["mu"])
-    times, n_L = [], 0
-    for i in range(warmup + steps):
+    w = wl.ackley(N_X, N_Y * n_gpus, N_S)
+    xm = w["x_mesh"] if rows is None else w["x_mesh"][:rows]
+    mu = w["mu"]
+    m0, m1, m2 = mu[:, 0][None, :], mu[:, 1][None, :], mu[:, 2][None, :]
+    U = np.empty((xm.shape[0], N_S))
+    for lo in range(0, xm.shape[0], 20000):
+        x, y = xm[lo:lo + 20000, 1][:, None], xm[lo:lo + 20000, 2][:, None]
+        U[lo:lo + 20000] = (-20 * (1 + .1 * m2) * np.exp(-.2 * (1 + .1 * m1) * np.sqrt(.5 * (x ** 2 + y ** 2)))
+                            - np.exp(.5 * (np.cos(2 * np.pi * (1 + .1 * m0) * x) + np.cos(2 * np.pi * (1 + .1 * m0) * y)))
+                            + 20 + np.exp(1))
+    return U
+
+
+class CpuPod:
+    """perform_pod + projection on the host cores: the reference's own code when oracle/_ref is built."""
+
+    def __init__(self):
+        from oracle import build_ref
+        self.kind = "reference" if build_ref.available() else "port"
+        if self.kind == "reference":
+            self.pod_mod, _ = build_ref.load()
+            # numba compiles perform_pod on first use (~7 s): warm it on a tiny matrix of the same dtype / layout
+            self.pod_mod.perform_pod(np.ascontiguousarray(np.random.default_rng(0).random((64, 8))), EPS, 0, False)
+        else:
+            from oracle import pod_oracle as po
+            self.po = po
+
+    def step(self, U):
         t = time.perf_counter()
-        V = po.perform_pod(U, EPS)
-        v = po.project_to_v(V, U)
+        if self.kind == "reference":
+            V = self.pod_mod.perform_pod(U, EPS, 0, False)        # poduqnn/pod.py:7-47, unmodified
+            v = (V.T.dot(U)).T                                    # podnnmodel.py:437
+        else:
+            V = self.po.perform_pod(U, EPS)
+            v = self.po.project_to_v(V, U)
         dt = time.perf_counter() - t
-        n_L = V.shape[1]
-        if i >= warmup:
-            times.append(dt)
-        del v
-    sec = statistics.mean(times)
-    return algo_flops(rows, N_S, n_L) / sec / 1e12, sec, n_L
+        return dt, V.shape[1], v.shape
+
+    def describe(self):
+        if self.kind == "reference":
+            return ("the reference's own poduqnn/pod.py:perform_pod (byte copy in oracle/_ref, numba -> LAPACK dgesdd) "
+                    "+ (V.T.dot(U)).T of podnnmodel.py:437")
+        return ("numpy port of pod.py:7-47 + podnnmodel.py:437 (oracle/pod_oracle.py; numpy.linalg.svd = the same LAPACK "
+                "dgesdd); oracle/_ref was not built")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
-    tf, sec, n_L = cpu_reference_steps(steps, warmup)
-    sample = (f"the whole C2 matrix, {CPU_SAMPLE_ROWS} mesh rows x {N_S} snapshots (n_L = {n_L}), "
-              f"{steps} timed step(s) after {warmup} warm-up; TFLOP/s uses the same algorithmic flop count")
+    n_gpus = max(1, args.gpus)
+    rows_full = N_X * N_Y * n_gpus
+    rows, note = rows_full, ""
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+        if 6 * rows_full * N_S * 8 > avail:                       # U, its Fortran-order copy, the thin left factor, V ...
+            rows = N_X * N_Y
+            note = (f"; host memory ({avail / 2**30:.0f} GiB free) cannot hold the SVD workspace of the {rows_full}-row matrix: "
+                    f"ran ONE {rows}-row slab, TFLOP/s is per-slab work over per-slab time")
+    except ImportError:
+        pass
+    cpu = CpuPod()
+    U = ackley_matrix_host(n_gpus, rows)
+    threads = blas_threads()
+    dt, n_L, _ = cpu.step(U)                                      # warm-up (page faults, pools)
+    steps = max(1, min(args.steps, 3, int(150. / max(dt, 1e-3))))
+    times = [cpu.step(U)[0] for _ in range(steps)]
+    sec = statistics.mean(times)
+    tf = algo_flops(rows, N_S, n_L) / sec / 1e12
+    cfg = workload_config(n_gpus)
+    cfg["rows_factored"] = rows
+    sample = (f"the whole weak-scaled C2 matrix, {rows} mesh rows x {N_S} snapshots (n_L = {n_L}), {steps} timed step(s) "
+              f"after 1 warm-up{note}; TFLOP/s uses the same algorithmic flop count")
     line = {"impl": "reference", "metric": METRIC, "value": tf, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": tf, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": tf, "unit": UNIT, "cores": threads["blas"] or HOST_CORES, "threads": threads,
+                             "kind": cpu.kind, "sample": sample},
             "e2e": {"value": tf, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
-            "note": "oracle port of pod.py:7-47 + podnnmodel.py:247 (numpy.linalg.svd = LAPACK dgesdd, all host threads); "
-                    "/root/reference is not present on the GPU box"}
+            "gpu_launches": 0, "note": cpu.describe()}
     print(json.dumps(line))
 
 
@@ -171,21 +256,28 @@ def run_gpu(args):
 
     state = {}
 
+    def pod_single(Ud, mode, key):
+        """single-GPU POD + basis + projection of a resident slab through the C-ABI; buffers cached under `key`."""
+        rows, ns = Ud.shape
+        nl = C.c_int()
+        ctx.check(L.pb_pod(ctx.h, Ud.ptr, rows, ns, Ud.ld, EPS, 0, _lib.POD_MODES[mode], C.byref(nl)))
+        n_L = nl.value
+        if state.get(key + "n_L") != n_L or state.get(key + "rows") != rows:
+            state[key + "V"], state[key + "v"] = ctx.alloc(rows, n_L), ctx.alloc(ns, n_L)
+            state[key + "n_L"], state[key + "rows"] = n_L, rows
+        V, v = state[key + "V"], state[key + "v"]
+        ctx.check(L.pb_pod_basis_full(ctx.h, Ud.ptr, rows, ns, Ud.ld, V.ptr, V.ld))
+        ctx.check(L.pb_project(ctx.h, V.ptr, V.ld, n_L, Ud.ptr, Ud.ld, rows, ns, v.ptr))
+        return V, v, n_L
+
     def step_resident():
         if world == 1:
-            nl = C.c_int()
-            ctx.check(L.pb_pod(ctx.h, U.ptr, n_h_loc, N_S, U.ld, EPS, 0, _lib.POD_MODES[MODE], C.byref(nl)))
-            n_L = nl.value
-            if state.get("n_L") != n_L:
-                state["V"], state["v"], state["n_L"] = ctx.alloc(n_h_loc, n_L), ctx.alloc(N_S, n_L), n_L
-            V, v = state["V"], state["v"]
-            ctx.check(L.pb_pod_basis_full(ctx.h, U.ptr, n_h_loc, N_S, U.ld, V.ptr, V.ld))
-            ctx.check(L.pb_project(ctx.h, V.ptr, V.ld, n_L, U.ptr, U.ld, n_h_loc, N_S, v.ptr))
+            V, v, n_L = pod_single(U, MODE, "")
         else:
             V, _, n_L = sharded.pod_sharded(be, U, EPS, 0, MODE)
             v = sharded.project_sharded(be, V, U)
-            state["V"], state["v"], state["n_L"] = V, v, n_L
-        return state["n_L"]
+        state["V"], state["v"], state["n_L"] = V, v, n_L
+        return n_L
 
     def barrier():
         ctx.sync()
@@ -201,6 +293,15 @@ def run_gpu(args):
         t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def sum_over_ranks(a):
+        """small host array summed over the ranks (checks only)"""
+        if dist is None:
+            return a
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy()
 
     # ---- fp64 peak of this GPU, measured live (roofline denominator)
     pk = C.c_double()
@@ -265,22 +366,56 @@ def run_gpu(args):
     ms_e2e = max_over_ranks(ctx.timer_stop() / e2e_steps)
     barrier()
     e2e_value = algo_flops(n_h, N_S, n_L) / (ms_e2e * 1e-3) / 1e12
+
+    # ---- e2e through the Python API a reference user calls: ordinary numpy arrays in, numpy arrays out
+    e2e_api = None
+    if world == 1:
+        from pod_uqnn_b200 import pod as pod_mod
+        U_np = np.ctypeslib.as_array(C.cast(hU, C.POINTER(C.c_double)), shape=(n_h_loc, N_S)).copy()   # pageable copy
+        pod_mod.perform_pod(U_np, EPS, 0, False, mode=MODE, ctx=ctx)        # warm: staging ring, device slab
+        t_pod, t_prj, t_reuse = [], [], []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            V_np = pod_mod.perform_pod(U_np, EPS, 0, False, mode=MODE, ctx=ctx)
+            t1 = time.perf_counter()
+            v_np = pod_mod.project_to_v(V_np, U_np, ctx=ctx)
+            t2 = time.perf_counter()
+            t_pod.append(t1 - t0); t_prj.append(t2 - t1)
+            t0 = time.perf_counter()
+            V_np = pod_mod.perform_pod(U_np, EPS, 0, False, mode=MODE, ctx=ctx)
+            v2_np = pod_mod.project_to_v(V_np, U_np, ctx=ctx, reuse_slab=True)
+            t_reuse.append(time.perf_counter() - t0)
+        assert np.allclose(v_np, v2_np, rtol=0, atol=1e-9 * np.abs(v_np).max())
+        fl = algo_flops(n_h_loc, N_S, V_np.shape[1])
+        sec_api, sec_reuse = min(t_pod) + min(t_prj), min(t_reuse)
+        e2e_api = {"value": fl / sec_api / 1e12, "unit": UNIT, "ms_per_step": sec_api * 1e3, "mode": MODE,
+                   "perform_pod_ms": min(t_pod) * 1e3, "project_to_v_ms": min(t_prj) * 1e3,
+                   "call": "V = pod.perform_pod(U_ndarray, eps, mode=...); v = pod.project_to_v(V, U_ndarray): pageable numpy in, "
+                           "numpy out, time.perf_counter, best of 3 (U crosses PCIe twice, V three times)",
+                   "reuse_slab": {"value": fl / sec_reuse / 1e12, "ms_per_step": sec_reuse * 1e3, "ratio_to_e2e": ms_e2e / (sec_reuse * 1e3),
+                                  "call": "the same with project_to_v(..., reuse_slab=True): U and V stay in HBM between the two calls"},
+                   "ratio_to_e2e": ms_e2e / (sec_api * 1e3), "v_shape": list(v_np.shape)}
+        del U_np
+    # ---- the host -> device ceiling of this box with every rank copying at once (explains the e2e scaling)
+    ctx.sync(); barrier()
+    ctx.timer_start()
+    ctx.check(L.pb_upload_async(ctx.h, U.ptr, hU, U.nbytes))
+    ms_h2d = max_over_ranks(ctx.timer_stop())
+    barrier()
+    h2d = {"aggregate_gbs": n_h * N_S * 8 / (ms_h2d * 1e-3) / 1e9, "ms": ms_h2d,
+           "e2e_floor_ms": ms_h2d, "note": "plain pinned cudaMemcpyAsync of every rank's 1.28 GB slab at the same time, max over ranks"}
     L.pb_host_free(hU); L.pb_host_free(hV); L.pb_host_free(hv)
 
-    # ---- second headline metric: ensemble predict samples/s (C4: M = 8 MLPs [1,128,128,128,2*64], 1e6 points
-    #      split over the ranks, no communication)
+    # ---- N > 1: the sharded result against a single-GPU run over the same rows, on rank 0 (fails the run on a mismatch)
+    parity = None
+    if world > 1:
+        parity = parity_vs_single_gpu(ctx, be, sharded, snapshots_device, X, w["mu"], U, n_h, rank, state, pod_single, barrier)
+
     # ---- the TSQR accuracy mode on the same resident slab(s): Householder QR per rank, all-gather of the R factors,
     #      replicated QR of the stack + pivoted QR + Jacobi SVD, basis, projection
     def step_tsqr():
         if world == 1:
-            nl = C.c_int()
-            ctx.check(L.pb_pod(ctx.h, U.ptr, n_h_loc, N_S, U.ld, EPS, 0, _lib.POD_MODES["tsqr"], C.byref(nl)))
-            if state.get("t_nL") != nl.value:
-                state["tV"], state["tv"], state["t_nL"] = ctx.alloc(n_h_loc, nl.value), ctx.alloc(N_S, nl.value), nl.value
-            V, v = state["tV"], state["tv"]
-            ctx.check(L.pb_pod_basis_full(ctx.h, U.ptr, n_h_loc, N_S, U.ld, V.ptr, V.ld))
-            ctx.check(L.pb_project(ctx.h, V.ptr, V.ld, nl.value, U.ptr, U.ld, n_h_loc, N_S, v.ptr))
-            return nl.value
+            return pod_single(U, "tsqr", "t")[2]
         V, _, nl = sharded.pod_sharded(be, U, EPS, 0, "tsqr")
         sharded.project_sharded(be, V, U)
         return nl
@@ -294,10 +429,21 @@ def run_gpu(args):
     tsqr_line = {"workload": "same slabs, mode tsqr (blocked Householder QR of U, pivoted QR + Jacobi SVD of R), basis, projection",
                  "ms_per_step": t_tsqr, "n_L": nl_t, "local_qr_ms": ctx.ms(_lib.T_QR),
                  "householder_tflops": qr_flops / (t_tsqr * 1e-3) / 1e12,
+                 "frac_fp64_peak": qr_flops / (t_tsqr * 1e-3) / 1e12 / (peak_tf * world),
                  "note": "flop count 2 n_h n_s^2 - (2/3) n_s^3 per slab (SURVEY 8d); at N > 1 T_QR is the replicated QR of the stacked R factors"}
+    for k in [k for k in state if k.startswith("t")]:
+        state.pop(k)
 
     ens_line = ensemble_bench(ctx, L, world, rank, max_over_ranks, peak_tf, with_cpu=(world == 1 and not args.no_cpu_baseline))
     train_lines = train_bench(ctx, world, rank, max_over_ranks, peak_tf, with_cpu=(world == 1 and not args.no_cpu_baseline))
+
+    # ---- C5 (BASELINE.json configs[4], the north-star target): 1.25 M rows per GPU x 4096, both modes, asserted
+    c5 = None
+    if not args.skip_c5:
+        U.release(); state.clear()
+        if be is not None:
+            be._cache.clear()
+        c5 = c5_leg(ctx, L, be, sharded, wl, world, rank, barrier, max_over_ranks, sum_over_ranks, peak_tf, pod_single, state)
 
     if rank != 0:
         if dist is not None:
@@ -315,28 +461,143 @@ def run_gpu(args):
                 "peak_source": "live pb_probe_fp64_peak (DMMA m8n8k4 register loop on all SMs, burst); "
                                "MEASURED_PEAKS.json has no fp64 entry (nominal 37.2 TFLOP/s at 1965 MHz)"}
 
-    # ---- CPU baseline (N = 1 only): the oracle port on a bounded sample
+    # ---- CPU baseline (N = 1 only): the reference's perform_pod + projection on the whole C2 matrix, one pass
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        tf, sec, nl_cpu = cpu_reference_steps(1, 0)
-        cpu = {"value": tf, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": f"the whole C2 matrix ({CPU_SAMPLE_ROWS} of {n_h_loc} mesh rows x {N_S} snapshots), 1 pass of the oracle's "
-                         f"perform_pod + projection ({sec:.2f} s, n_L = {nl_cpu}); same flop formula"}
+        cp = CpuPod()
+        Uh = ackley_matrix_host(1)
+        threads = blas_threads()
+        sec, nl_cpu, _ = cp.step(Uh)
+        del Uh
+        cpu = {"value": algo_flops(n_h_loc, N_S, nl_cpu) / sec / 1e12, "unit": UNIT, "cores": threads["blas"] or HOST_CORES,
+               "threads": threads, "kind": cp.kind,
+               "sample": f"the whole C2 matrix ({n_h_loc} mesh rows x {N_S} snapshots), 1 pass of {cp.describe()} "
+                         f"({sec:.2f} s, n_L = {nl_cpu}); same flop formula"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(world), "n_L": n_L,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "steps": e2e_steps,
-                    "h2d_bytes_per_step": U.nbytes * world, "d2h_bytes_per_step": (n_h + N_S) * n_L * 8},
+                    "h2d_bytes_per_step": n_h * N_S * 8, "d2h_bytes_per_step": (n_h + N_S) * n_L * 8},
+            "e2e_api": e2e_api, "h2d_probe": h2d,
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "stage_ms": {k: statistics.mean(v) for k, v in parts.items()}, "tsqr_mode": tsqr_line,
+            "stage_ms": {k: statistics.mean(v) for k, v in parts.items()}, "parity": parity, "tsqr_mode": tsqr_line, "c5": c5,
             "ensemble_predict": ens_line, "ensemble_train": train_lines,
-            "snapshot_kernel": {"ms": snap_ms, "gbs": U.nbytes / (snap_ms * 1e-3) / 1e9,
+            "snapshot_kernel": {"ms": snap_ms, "gbs": n_h_loc * N_S * 8 / (snap_ms * 1e-3) / 1e9,
                                 "note": "Ackley field -> U slab in HBM (outside the timed step): table kernels + ackley_indexed_kernel, second call"}}
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
+
+
+def parity_vs_single_gpu(ctx, be, sharded, snapshots_device, X, mu, U, n_h, rank, state, pod_single, barrier):
+    """N > 1: the row-sharded NCCL result (both modes) against ONE GPU factoring all n_h rows (rank 0 regenerates the
+    whole matrix in its HBM: 1.28 GB per rank of the job).  Rank, singular values to 1e-10 sigma_max, rank 0's rows of
+    V up to the per-mode sign to 1e-8 (north_star tolerances).  Raises on a mismatch; the other ranks wait."""
+    from pod_uqnn_b200.pod import pod_sigma
+    out = {}
+    n_loc = U.shape[0]
+    for mode in (MODE, "tsqr"):
+        V_sh, sig_sh, nL_sh = sharded.pod_sharded(be, U, EPS, 0, mode)
+        V_sh_host = V_sh.download() if rank == 0 else None
+        barrier()
+        if rank == 0:
+            Ufull, _, _ = snapshots_device(ctx, "ackley", X, mu, row0=0, n_rows=n_h)
+            V1, _, nL1 = pod_single(Ufull, mode, "p")
+            sig1 = pod_sigma(ctx)
+            V1_host = V1.download()[:n_loc]
+            Ufull.release()
+            for k in [k for k in state if k.startswith("p")]:
+                state.pop(k)
+            smax = float(sig1[0])
+            sig_err = float(np.max(np.abs(sig_sh[:nL1] - sig1[:nL1])) / smax)
+            signs = np.sign(np.sum(V_sh_host * V1_host, axis=0))
+            v_err = float(np.max(np.abs(V_sh_host * signs - V1_host))) if nL_sh == nL1 else float("inf")
+            ok = (nL_sh == nL1) and sig_err <= 1e-10 and v_err <= 1e-8
+            out[mode] = {"n_L_sharded": nL_sh, "n_L_single_gpu": nL1, "sigma_err_rel_sigma_max": sig_err,
+                         "V_rows_rank0_max_abs_err": v_err, "status": "ok" if ok else "MISMATCH"}
+        barrier()
+    if rank == 0:
+        bad = {m: o for m, o in out.items() if o["status"] != "ok"}
+        if bad:
+            raise SystemExit(f"bench.py: sharded result differs from the single-GPU run: {json.dumps(bad)}")
+        out["status"] = "ok"
+        out["how"] = ("rank 0 factors all n_h rows on one GPU (pb_pod) and compares with the NCCL row-sharded run: equal n_L, "
+                      "sigma to 1e-10 sigma_max, rank 0's rows of V to 1e-8 up to sign")
+    return out or None
+
+
+def c5_leg(ctx, L, be, sharded, wl, world, rank, barrier, max_over_ranks, sum_over_ranks, peak_tf, pod_single, state):
+    """BASELINE.json configs[4] at 1.25 M rows per GPU: U = sum_k s_k phi_k psi_k^T (DCT-II vectors) filled in
+    HBM, POD (gram2 and tsqr) + projection.  ASSERTS the closed form (north_star tolerances): n_L, sigma_k = s_k to
+    1e-10 sigma_max, largest principal angle between span(V) and the closed-form modes <= 1e-8 (all rows, all ranks).
+    V_rows_err_rel (first rows of V against phi_k, per mode: angle / relative gap) is reported, not asserted."""
+    import ctypes as C
+    from pod_uqnn_b200 import _lib
+    n_loc, n_s, r = C5_ROWS_PER_GPU, C5_NS, C5_R
+    n_h = n_loc * world
+    Uc = ctx.alloc(n_loc, n_s)
+    ctx.check(L.pb_dct_lowrank(ctx.h, n_h, n_s, r, C5_DECAY, rank * n_loc, n_loc, Uc.ptr, Uc.ld))
+    ctx.sync()
+    s = 2. ** (-C5_DECAY * np.arange(r))
+    nL_closed = wl.dct_rank(s, EPS)
+    out = {"workload": f"C5 DCT known-answer slab(s): n_h = {n_h} ({n_loc} rows per GPU) x n_s = {n_s}, fp64, eps = {EPS:g}, "
+                       f"POD + projection, r = {r} exact singular values 2^(-k/4)", "n_L_closed_form": nL_closed}
+    n_chk = 4096
+    for mode in ("gram2", "tsqr"):
+        def step():
+            if world == 1:
+                V, v, nl = pod_single(Uc, mode, "c")
+            else:
+                V, _, nl = sharded.pod_sharded(be, Uc, EPS, 0, mode)
+                v = sharded.project_sharded(be, V, Uc)
+            return V, nl
+        step(); barrier()
+        best = 1e30
+        for _ in range(2):
+            barrier(); ctx.timer_start(); V, nl = step(); best = min(best, ctx.timer_stop())
+        barrier()
+        ms = max_over_ranks(best)
+        from pod_uqnn_b200.pod import pod_sigma
+        sig = pod_sigma(ctx)
+        flops = algo_flops(n_h, n_s, nl) if mode != "tsqr" else \
+            world * (2 * n_loc * n_s ** 2 - (2 / 3) * n_s ** 3) + 4 * n_h * n_s * nl
+        # closed-form checks (every rank checks its own rows of V; rank 0 reports)
+        sig_err = float(np.max(np.abs(sig[:nL_closed] - s[:nL_closed])) / s[0]) if len(sig) >= nL_closed else float("inf")
+        Vh = np.empty((n_chk, nl))
+        ctx.check(L.pb_download(ctx.h, Vh.ctypes.data, V.ptr, n_chk * nl * 8))
+        i = (rank * n_loc + np.arange(n_chk) + .5)[:, None]
+        phi = np.sqrt(2. / n_h) * np.cos(np.pi * i * (np.arange(nl) + 1.)[None, :] / n_h)
+        sg = np.sign(np.sum(Vh * phi, axis=0))
+        v_err = max_over_ranks(float(np.max(np.abs(Vh * sg - phi)) / np.sqrt(2. / n_h)))
+        # largest principal angle between span(V) and the closed-form modes, from the residual V - Phi (Phi^T V) itself
+        Phi, Cd, Gd = ctx.alloc(n_loc, nl), ctx.alloc(nl, nl), ctx.alloc(nl, nl)
+        ctx.check(L.pb_dct_basis(ctx.h, n_h, nl, rank * n_loc, n_loc, Phi.ptr, Phi.ld))
+        ctx.check(L.pb_gemm_tn(ctx.h, Phi.ptr, Phi.ld, nl, V.ptr, V.ld, nl, n_loc, Cd.ptr))
+        Cd.upload(sum_over_ranks(Cd.download()))
+        ctx.check(L.pb_residual_gram(ctx.h, V.ptr, V.ld, nl, Phi.ptr, Phi.ld, nl, n_loc, Cd.ptr, Gd.ptr))
+        angle = float(np.sqrt(max(0., np.linalg.eigvalsh(sum_over_ranks(Gd.download()))[-1])))
+        Phi.release(); Cd.release(); Gd.release()
+        ok = (nl == nL_closed) and sig_err <= 1e-10 and angle <= 1e-8
+        out[mode] = {"wall_s": ms * 1e-3, "n_L": nl, "tflops": flops / (ms * 1e-3) / 1e12,
+                     "frac": flops / (ms * 1e-3) / 1e12 / (peak_tf * world),
+                     "sigma_err_rel_sigma_max": sig_err, "subspace_angle": angle, "V_rows_err_rel": v_err,
+                     "flop_count": "n_h n_s (n_s+1) + 4 n_h n_s n_L" if mode != "tsqr" else
+                                   "Householder N (2 n_loc n_s^2 - 2/3 n_s^3) + 4 n_h n_s n_L",
+                     "stage_ms": {"gram_or_qr": ctx.ms(_lib.T_GRAM if mode != "tsqr" else _lib.T_QR), "eig": ctx.ms(_lib.T_EIG),
+                                  "basis": ctx.ms(_lib.T_BASIS), "project": ctx.ms(_lib.T_PROJECT)},
+                     "status": "ok" if ok else "MISMATCH"}
+        if not ok:
+            raise SystemExit(f"bench.py: C5 {mode} does not match the closed form: {json.dumps(out[mode])}")
+        for k in [k for k in state if k.startswith("c")]:
+            state.pop(k)
+        if be is not None:
+            be._cache.clear()
+    out["parity"] = "ok"
+    out["peak_tflops_per_gpu"] = peak_tf
+    Uc.release()
+    return out
 
 
 def ensemble_bench(ctx, L, world, rank, max_over_ranks, peak_tf, with_cpu):
@@ -370,7 +631,7 @@ def ensemble_bench(ctx, L, world, rank, max_over_ranks, peak_tf, with_cpu):
         t = time.perf_counter()
         ens.predict_v(X[:n_cpu], members, layers[-1], 0.01, "meanstd", nb)
         sec = time.perf_counter() - t
-        out["cpu_baseline"] = {"samples_per_s": n_cpu / sec, "cores": os.cpu_count(), "kind": "port",
+        out["cpu_baseline"] = {"samples_per_s": n_cpu / sec, "cores": HOST_CORES, "kind": "port",
                                "sample": f"{n_cpu} points through the numpy restatement (TensorFlow is not in the image)"}
     return out
 
@@ -407,7 +668,7 @@ def train_bench(ctx, world, rank, max_over_ranks, peak_tf, with_cpu):
             t = time.perf_counter()
             otr.train(X, v, [a.copy() for a in members[0]], layers[-1], n_ep, lr, lam, adv, soft_0)
             sec = time.perf_counter() - t
-            line["cpu_baseline"] = {"member_epochs_per_s": n_ep / sec, "cores": os.cpu_count(), "kind": "port",
+            line["cpu_baseline"] = {"member_epochs_per_s": n_ep / sec, "cores": HOST_CORES, "kind": "port",
                                     "sample": f"{n_ep} epochs of one member through the numpy restatement"}
         out.append(line)
     return out
@@ -431,6 +692,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="podb200", choices=["podb200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-c5", action="store_true", help="skip the C5 (1.25 M x 4096 per GPU) leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "podb200" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -91,6 +91,13 @@ int  pb_upload(pb_ctx* ctx, void* dev, const void* host, size_t bytes);   /* H2D
 int  pb_download(pb_ctx* ctx, void* host, const void* dev, size_t bytes); /* D2H + sync */
 int  pb_upload_async(pb_ctx* ctx, void* dev, const void* host, size_t bytes);
 int  pb_download_async(pb_ctx* ctx, void* host, const void* dev, size_t bytes);
+/* Context-owned device slab for the host-facing calls (pb_pod_host / pb_gram_host receive the uploaded matrix in
+ * it): grown on demand, reused across calls (a cudaMalloc / cudaFree pair of 1.28 GB per perform_pod call costs
+ * milliseconds and synchronises the device).  Valid until a later pb_slab asks for more, or pb_destroy. */
+int  pb_slab(pb_ctx* ctx, size_t bytes, void** dev);
+/* Host matrix (n_h x n_st doubles, row pitch ldu_host) -> U_dev (row pitch n_st), queued on the context stream.  Pinned
+ * sources are copied directly, pageable ones (numpy arrays) through the pinned staging ring filled by host threads. */
+int  pb_upload_matrix(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, int64_t ldu_host, double* U_dev);
 int  pb_host_alloc(size_t bytes, void** host);        /* pinned host memory */
 int  pb_host_free(void* host);
 
@@ -188,8 +195,10 @@ int  pb_pod_basis_full(pb_ctx* ctx, const double* U_dev, int64_t n_h, int64_t n_
  * G_dev (n_st x n_st) its Gram.  (pod.py:16 applied to one rank's rows.) */
 int  pb_gram_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, int64_t ldu_host,
                   double* U_dev, double* G_dev);
-/* Same from a HOST matrix (pinned memory for full PCIe speed): the upload into U_dev (n_h x n_st,
- * ld = n_st, caller-allocated) is cut into row chunks on a copy stream and overlapped with the Gram. */
+/* Same from a HOST matrix: the upload into U_dev (n_h x n_st, ld = n_st, caller-allocated) is cut into row chunks on
+ * a copy stream and overlapped with the Gram.  Pinned memory (pb_host_alloc) is copied directly; pageable memory
+ * (an ordinary numpy array, what poduqnn/pod.py:7 is handed) goes through a ring of pinned staging buffers filled by
+ * host threads (PB_HOST_COPY_THREADS, default half the cores, at most 16). */
 int  pb_pod_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, int64_t ldu_host, double* U_dev,
                  double eps, int n_L_in, int mode, int* n_L);
 
@@ -257,7 +266,14 @@ int  pb_ensemble_train(pb_ctx* ctx, int n_members, int n_layers, const int* dims
                        int use_adv, double adv_eps, double soft_0, const double* X_dev, const double* v_dev,
                        int64_t N, double* loss_host, int use_graph);
 
-/* ---- measurement helpers (used by bench.py; not on the product path) ------ */
+/* ---- measurement helpers (used by bench.py and the tests; not on the product path) ------ */
+/* Closed-form left basis of pb_dct_lowrank's matrix: Phi (n_rows x r, ld) rows [row0, row0 + n_rows) of
+ * Phi[i][k] = sqrt(2/n_h) cos(pi (i + 1/2)(k + 1) / n_h)  (the exact modes of the C5 known-answer case). */
+int  pb_dct_basis(pb_ctx* ctx, int64_t n_h, int r, int64_t row0, int64_t n_rows, double* Phi_dev, int64_t ld);
+/* G_out (n_L x n_L) = R^T R with R = V - Phi C over the local rows (C: k x n_L, normally Phi^T V summed over all rows).
+ * sqrt(lambda_max) of the sum over ranks = sin(largest principal angle between span V and span Phi). */
+int  pb_residual_gram(pb_ctx* ctx, const double* V_dev, int64_t ldv, int n_L, const double* Phi_dev, int64_t ldp, int k,
+                      int64_t n_rows, const double* C_dev, double* G_out_dev);
 /* kind: 0 = DFMA register loop, 1 = DMMA m8n8k4 loop, 2 = both pipes mixed.  Returns TFLOP/s. */
 int  pb_probe_fp64_peak(pb_ctx* ctx, int kind, double* tflops);
 /* device-to-device copy of `bytes` (read+write counted).  Returns GB/s. */

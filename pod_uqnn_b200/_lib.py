@@ -44,6 +44,8 @@ SIGNATURES = {
     "pb_download": (_int, [_vp, _vp, _vp, C.c_size_t]),
     "pb_upload_async": (_int, [_vp, _vp, _vp, C.c_size_t]),
     "pb_download_async": (_int, [_vp, _vp, _vp, C.c_size_t]),
+    "pb_slab": (_int, [_vp, C.c_size_t, _pvp]),
+    "pb_upload_matrix": (_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
     "pb_host_alloc": (_int, [C.c_size_t, _pvp]),
     "pb_host_free": (_int, [_vp]),
     "pb_snapshots": (_int, [_vp, _int, _int, _i64, _vp, _i64, _int, _vp, _int, _vp, _i64, _i64, _vp, _i64]),
@@ -74,6 +76,8 @@ SIGNATURES = {
     "pb_predict_U": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp, _i64, _int, C.c_uint64, _vp, _vp, _i64]),
     "pb_ensemble_train": (_int, [_vp, _int, _int, _pi, _vp, _vp, _vp, _i64, _int, _dbl, _dbl, _int, _dbl, _dbl, _vp, _vp, _i64,
                           _vp, _int]),
+    "pb_dct_basis": (_int, [_vp, _i64, _int, _i64, _i64, _vp, _i64]),
+    "pb_residual_gram": (_int, [_vp, _vp, _i64, _int, _vp, _i64, _int, _i64, _vp, _vp]),
     "pb_probe_fp64_peak": (_int, [_vp, _int, _pd]),
     "pb_probe_hbm_copy": (_int, [_vp, C.c_size_t, _pd]),
     "pb_flush_l2": (_int, [_vp]),
@@ -140,7 +144,13 @@ class DeviceArray:
     def upload(self, host):
         host = np.ascontiguousarray(host, dtype=np.float64)
         assert host.shape == self.shape, (host.shape, self.shape)
-        self.ctx.check(lib().pb_upload(self.ctx.h, self.ptr, host.ctypes.data, self.nbytes))
+        if self.nbytes >= (8 << 20) and host.ndim >= 2:
+            # large pageable arrays: the library's pinned staging ring (host threads) instead of the driver's bounce buffer
+            cols = self.shape[-1]
+            self.ctx.check(lib().pb_upload_matrix(self.ctx.h, host.ctypes.data, self.nbytes // (8 * cols), cols, cols, self.ptr))
+            self.ctx.sync()
+        else:
+            self.ctx.check(lib().pb_upload(self.ctx.h, self.ptr, host.ctypes.data, self.nbytes))
         return self
 
     def release(self):

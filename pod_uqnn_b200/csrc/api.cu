@@ -4,6 +4,7 @@
 #include <cfloat>
 #include <algorithm>
 #include <mutex>
+#include <thread>
 #include <cstdlib>
 #include <vector>
 
@@ -101,6 +102,8 @@ int pb_destroy(pb_ctx* ctx) {
     for (int w = 0; w < PB_T_COUNT; ++w) { cudaEventDestroy(ctx->tev[w][0]); cudaEventDestroy(ctx->tev[w][1]); }
     if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); for (auto& e : ctx->chunk_ev) if (e) cudaEventDestroy(e); }
     if (ctx->Gpart) cudaFree(ctx->Gpart);
+    for (int s = 0; s < PB_STAGE_SLOTS; ++s) { if (ctx->stage[s]) cudaFreeHost(ctx->stage[s]); if (ctx->stage_ev[s]) cudaEventDestroy(ctx->stage_ev[s]); }
+    if (ctx->slab) cudaFree(ctx->slab);
     pbi_train_free(ctx);
     pbi_gram_plan_free(ctx);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -160,6 +163,13 @@ int pb_download_async(pb_ctx* ctx, void* host, const void* dev, size_t bytes) {
 }
 int pb_upload(pb_ctx* ctx, void* dev, const void* host, size_t bytes) { PB_TRY(pb_upload_async(ctx, dev, host, bytes)); return pb_sync(ctx); }
 int pb_download(pb_ctx* ctx, void* host, const void* dev, size_t bytes) { PB_TRY(pb_download_async(ctx, host, dev, bytes)); return pb_sync(ctx); }
+int pb_slab(pb_ctx* ctx, size_t bytes, void** dev) {
+    PB_ENTER(ctx); if (!dev) return PB_ERR_ARG;
+    size_t elems = (bytes + 7) / 8; if (elems == 0) elems = 1;
+    PB_TRY(pb_reserve(ctx, &ctx->slab, &ctx->slab_cap, elems));
+    *dev = ctx->slab;
+    return PB_OK;
+}
 int pb_host_alloc(size_t bytes, void** host) {
     if (!host) return PB_ERR_ARG;
     cudaError_t e = cudaMallocHost(host, bytes ? bytes : 8);
@@ -413,12 +423,87 @@ int pb_pod(pb_ctx* ctx, const double* U, int64_t n_h, int64_t n_st, int64_t ldu,
 }
 
 namespace {
+__global__ void scale_kernel(const double* __restrict__ in, int64_t n, double f, double* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = f * in[i];
+}
 __global__ void sum_partials_kernel(const double* __restrict__ part, int count, int64_t n, double* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double s = 0.;
     for (int c = 0; c < count; ++c) s += part[(int64_t)c * n + i];     // fixed order: deterministic
     out[i] = s;
+}
+}  // namespace
+
+// ---- pageable host buffers: pinned staging ring filled by host threads -------------------------------------------
+// cudaMemcpyAsync from pageable memory goes through the driver's own single-threaded bounce buffer (a fraction of the
+// PCIe rate).  An ordinary numpy array (what pod.perform_pod is handed) is therefore copied by a few host threads into
+// one of PB_STAGE_SLOTS pinned chunk buffers, and the H2D copy of chunk c runs while the threads fill chunk c + 1.
+namespace {
+bool host_is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+int host_copy_threads() {
+    static const int n = []{
+        const char* e = getenv("PB_HOST_COPY_THREADS");
+        int v = e ? atoi(e) : 0;
+        if (v <= 0) { v = (int)std::thread::hardware_concurrency() / 2; if (v > 16) v = 16; }
+        return v < 1 ? 1 : v;
+    }();
+    return n;
+}
+// dst (contiguous, row length `row_bytes`) <- src rows with pitch `src_pitch`, split over the host threads
+void parallel_host_copy(char* dst, const char* src, size_t rows, size_t row_bytes, size_t src_pitch) {
+    const int T = (int)std::min<size_t>((size_t)host_copy_threads(), std::max<size_t>(1, rows * row_bytes / (4u << 20)));
+    auto work = [=](int t) {
+        const size_t r0 = rows * t / T, r1 = rows * (t + 1) / T;
+        if (src_pitch == row_bytes) memcpy(dst + r0 * row_bytes, src + r0 * src_pitch, (r1 - r0) * row_bytes);
+        else for (size_t r = r0; r < r1; ++r) memcpy(dst + r * row_bytes, src + r * src_pitch, row_bytes);
+    };
+    if (T <= 1) { work(0); return; }
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+}
+int stage_reserve(pb_ctx* ctx, size_t bytes) {
+    if (ctx->stage_cap >= bytes && ctx->stage[0]) return PB_OK;
+    for (int s = 0; s < PB_STAGE_SLOTS; ++s) {
+        if (ctx->stage[s]) { cudaFreeHost(ctx->stage[s]); ctx->stage[s] = nullptr; }
+        cudaError_t e = cudaMallocHost(&ctx->stage[s], bytes);
+        if (e != cudaSuccess) { cudaGetLastError(); ctx->stage_cap = 0; PB_FAIL(ctx, PB_ERR_NOMEM, "pinned staging buffer (%zu bytes): %s", bytes, cudaGetErrorString(e)); }
+        if (!ctx->stage_ev[s]) PB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[s], cudaEventDisableTiming));
+    }
+    ctx->stage_cap = bytes;
+    return PB_OK;
+}
+// rows [0, n_rows) of a host matrix (pitch ld_host doubles, n_cols used) -> dev (pitch n_cols) on `stream`.
+// pinned source: one async copy; pageable source: through the staging ring (the host thread returns when the last
+// chunk has been handed to the copy engine).  `slot` carries the ring position across calls.
+int upload_rows(pb_ctx* ctx, double* dev, const double* host, int64_t n_rows, int64_t n_cols, int64_t ld_host, bool pinned,
+                cudaStream_t stream, int* slot) {
+    const size_t row_bytes = (size_t)n_cols * sizeof(double);
+    if (pinned) {
+        if (ld_host == n_cols)      // contiguous rows: one linear copy (the pitched path is slower for 8 KB rows)
+            PB_CUDA(ctx, cudaMemcpyAsync(dev, host, (size_t)n_rows * row_bytes, cudaMemcpyHostToDevice, stream));
+        else
+            PB_CUDA(ctx, cudaMemcpy2DAsync(dev, row_bytes, host, ld_host * sizeof(double), row_bytes, n_rows, cudaMemcpyHostToDevice, stream));
+        return PB_OK;
+    }
+    const size_t piece_rows = std::max<size_t>(1, ctx->stage_cap / row_bytes);
+    for (int64_t r0 = 0; r0 < n_rows; r0 += (int64_t)piece_rows) {
+        const size_t nr = (size_t)std::min<int64_t>((int64_t)piece_rows, n_rows - r0);
+        const int s = (*slot)++ % PB_STAGE_SLOTS;
+        PB_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[s]));          // the copy that last read this slot is done
+        parallel_host_copy(reinterpret_cast<char*>(ctx->stage[s]), reinterpret_cast<const char*>(host + r0 * ld_host), nr, row_bytes,
+                           (size_t)ld_host * sizeof(double));
+        PB_CUDA(ctx, cudaMemcpyAsync(dev + r0 * n_cols, ctx->stage[s], nr * row_bytes, cudaMemcpyHostToDevice, stream));
+        PB_CUDA(ctx, cudaEventRecord(ctx->stage_ev[s], stream));
+    }
+    return PB_OK;
 }
 }  // namespace
 
@@ -446,16 +531,13 @@ int gram_host_chunked(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_
     PB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[0], 0));
     int used = 0;
     Timer tg(ctx, PB_T_GRAM);
+    const bool pinned = host_is_pinned(U_host);
+    if (!pinned) PB_TRY(stage_reserve(ctx, (size_t)64 << 20));
+    int slot = 0;
     for (int c = 0; c < nchunks; ++c) {
         const int64_t r0 = (int64_t)c * rows_c, nr = std::min(rows_c, n_h - r0);
         if (nr <= 0) break;
-        if (ldu_host == n_st)      // contiguous rows: one linear copy (the pitched path is slower for 8 KB rows)
-            PB_CUDA(ctx, cudaMemcpyAsync(U_dev + r0 * n_st, U_host + r0 * n_st, (size_t)nr * n_st * sizeof(double),
-                                         cudaMemcpyHostToDevice, ctx->copy_stream));
-        else
-            PB_CUDA(ctx, cudaMemcpy2DAsync(U_dev + r0 * n_st, n_st * sizeof(double), U_host + r0 * ldu_host,
-                                           ldu_host * sizeof(double), n_st * sizeof(double), nr, cudaMemcpyHostToDevice,
-                                           ctx->copy_stream));
+        PB_TRY(upload_rows(ctx, U_dev + r0 * n_st, U_host + r0 * ldu_host, nr, n_st, ldu_host, pinned, ctx->copy_stream, &slot));
         PB_CUDA(ctx, cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
         PB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
         PB_TRY(pbi_gemm_tn(ctx, U_dev + r0 * n_st, n_st, m, U_dev + r0 * n_st, n_st, m, nr, ctx->Gpart + (size_t)c * m * m, m, 1));
@@ -468,14 +550,37 @@ int gram_host_chunked(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_
 }
 }  // namespace
 
+namespace {
+// whole-matrix upload on the compute stream (small / wide inputs and the TSQR mode)
+int upload_whole(pb_ctx* ctx, double* U_dev, const double* U_host, int64_t n_h, int64_t n_st, int64_t ldu_host) {
+    const bool pinned = host_is_pinned(U_host);
+    if (!pinned && (size_t)n_h * n_st * sizeof(double) >= ((size_t)8 << 20)) {
+        PB_TRY(stage_reserve(ctx, (size_t)64 << 20));
+        int slot = 0;
+        return upload_rows(ctx, U_dev, U_host, n_h, n_st, ldu_host, false, ctx->stream, &slot);
+    }
+    PB_CUDA(ctx, cudaMemcpy2DAsync(U_dev, n_st * sizeof(double), U_host, ldu_host * sizeof(double),
+                                   n_st * sizeof(double), n_h, cudaMemcpyHostToDevice, ctx->stream));
+    return PB_OK;
+}
+}  // namespace
+
+// Host matrix (n_h x n_st, pitch ldu_host) -> U_dev (pitch n_st) on the context stream, asynchronous with respect to
+// the GPU work already queued; pageable sources go through the staging ring (the call returns when the last piece has
+// been handed to the copy engine, so the host array may be reused after pb_sync)
+int pb_upload_matrix(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, int64_t ldu_host, double* U_dev) {
+    PB_ENTER(ctx); if (!U_host || !U_dev) return PB_ERR_ARG;
+    if (n_h <= 0 || n_st <= 0 || ldu_host < n_st) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_upload_matrix: bad shape");
+    return upload_whole(ctx, U_dev, U_host, n_h, n_st, ldu_host);
+}
+
 int pb_gram_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, int64_t ldu_host, double* U_dev,
                  double* G_dev) {
     PB_ENTER(ctx); if (!U_host || !U_dev || !G_dev) return PB_ERR_ARG;
     if (n_h <= 0 || n_st <= 0 || ldu_host < n_st) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_gram_host: bad shape");
     int rc = gram_host_chunked(ctx, U_host, n_h, n_st, ldu_host, U_dev, G_dev);
     if (rc != 1) return rc;
-    PB_CUDA(ctx, cudaMemcpy2DAsync(U_dev, n_st * sizeof(double), U_host, ldu_host * sizeof(double),
-                                   n_st * sizeof(double), n_h, cudaMemcpyHostToDevice, ctx->stream));
+    PB_TRY(upload_whole(ctx, U_dev, U_host, n_h, n_st, ldu_host));
     return pb_gram(ctx, U_dev, n_h, n_st, n_st, G_dev);
 }
 
@@ -489,9 +594,8 @@ int pb_pod_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, in
     if (n_h >= n_st) PB_TRY(pb_reserve(ctx, &ctx->Gbuf, &ctx->G_cap, (size_t)m * m));
     // the TSQR mode has no Gram to overlap with the upload: plain copy, then the device path
     int rc = mode == PB_POD_TSQR ? 1 : gram_host_chunked(ctx, U_host, n_h, n_st, ldu_host, U_dev, ctx->Gbuf);
-    if (rc == 1) {        // small or wide: plain upload, then the device path
-        PB_CUDA(ctx, cudaMemcpy2DAsync(U_dev, n_st * sizeof(double), U_host, ldu_host * sizeof(double),
-                                       n_st * sizeof(double), n_h, cudaMemcpyHostToDevice, ctx->stream));
+    if (rc == 1) {        // small or wide, or the TSQR mode: upload (staged when pageable), then the device path
+        PB_TRY(upload_whole(ctx, U_dev, U_host, n_h, n_st, ldu_host));
         return pb_pod(ctx, U_dev, n_h, n_st, n_st, eps, n_L_in, mode, n_L);
     }
     if (rc != PB_OK) return rc;
@@ -713,6 +817,30 @@ int pb_reconstruct(pb_ctx* ctx, const double* V, int64_t ldv, int n_L, const dou
     PB_TRY(pbi_gemm_nn(ctx, V, ldv, rows, n_L, ctx->Bmat, ldb, n, U_pod, ldp, pod_sig ? U : nullptr, ldu, pod_sig));
     t.stop();
     return PB_OK;
+}
+
+// ---- measurement helper: residual of a computed basis against a reference basis ------------------------------
+// R = V - Phi C over the local rows, G_out = R^T R (n_L x n_L).  With C = Phi^T V summed over all rows (pb_gemm_tn +
+// all-reduce) and Phi orthonormal, sqrt(lambda_max(sum over ranks of G_out)) = sin of the largest principal angle
+// between span(V) and span(Phi) -- computed from the residual itself, so angles of 1e-12 are resolved (1 - cos is not).
+int pb_residual_gram(pb_ctx* ctx, const double* V, int64_t ldv, int n_L, const double* Phi, int64_t ldp, int k,
+                     int64_t rows, const double* C_dev, double* G_out) {
+    PB_ENTER(ctx); if (!V || !Phi || !C_dev || !G_out) return PB_ERR_ARG;
+    if (n_L <= 0 || k <= 0 || rows <= 0 || ldv < n_L || ldp < k) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_residual_gram: bad shape");
+    // own scratch (a measurement helper must not disturb the buffers of the last decomposition)
+    double* R = nullptr; double* Cn = nullptr;
+    PB_CUDA(ctx, cudaMalloc(&R, sizeof(double) * (size_t)rows * n_L));
+    if (cudaMalloc(&Cn, sizeof(double) * (size_t)k * n_L) != cudaSuccess) { cudaGetLastError(); cudaFree(R); PB_FAIL(ctx, PB_ERR_NOMEM, "pb_residual_gram: out of memory"); }
+    int rc = PB_OK;
+    if (cudaMemcpy2DAsync(R, n_L * sizeof(double), V, ldv * sizeof(double), n_L * sizeof(double), rows,
+                          cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) rc = PB_ERR_CUDA;
+    scale_kernel<<<(unsigned)(((int64_t)k * n_L + 255) / 256), 256, 0, ctx->stream>>>(C_dev, (int64_t)k * n_L, -1., Cn);
+    ctx->launches++;
+    if (rc == PB_OK) rc = pbi_gemm_nn_sub(ctx, Phi, ldp, rows, k, Cn, n_L, n_L, R, n_L);      // R = V + Phi (-C)
+    if (rc == PB_OK) rc = pbi_gemm_tn(ctx, R, n_L, n_L, R, n_L, n_L, rows, G_out, n_L, 0);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(R); cudaFree(Cn);
+    return rc;
 }
 
 }  // extern "C"

@@ -8,6 +8,8 @@
 #include <vector>
 #include "../../include/podb200.h"
 
+constexpr int PB_STAGE_SLOTS = 3;
+
 struct pb_ctx {
     int device = 0;
     int sm_count = 148;
@@ -27,6 +29,9 @@ struct pb_ctx {
     cudaStream_t copy_stream = nullptr;             // pb_pod_host: chunked upload overlapped with the Gram
     cudaEvent_t chunk_ev[16] = {nullptr};
     double* Gpart = nullptr; size_t Gpart_cap = 0;
+    void* stage[PB_STAGE_SLOTS] = {nullptr};        // pinned staging ring for pageable host inputs (api.cu)
+    cudaEvent_t stage_ev[PB_STAGE_SLOTS] = {nullptr}; size_t stage_cap = 0;
+    double* slab = nullptr; size_t slab_cap = 0;    // cached device slab of the host-facing calls (pb_slab)
 
     // split-K workspace of the TN products (grown on demand)
     double* ws = nullptr;  size_t ws_bytes = 0;

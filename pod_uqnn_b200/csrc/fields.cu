@@ -244,6 +244,16 @@ extern "C" int pb_snapshots_ackley_indexed(pb_ctx* ctx, int64_t n_xyz, const dou
     return PB_OK;
 }
 
+// Closed-form left basis of the known-answer matrix: Phi[i][k] = sqrt(2/n_h) cos(pi (row0 + i + 1/2)(k + 1) / n_h)
+extern "C" int pb_dct_basis(pb_ctx* ctx, int64_t n_h, int r, int64_t row0, int64_t n_rows, double* Phi_dev, int64_t ld) {
+    PB_ENTER(ctx);
+    if (r <= 0 || ld < r || n_rows <= 0 || row0 < 0 || row0 + n_rows > n_h) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_dct_basis: bad shape");
+    const int64_t ne = n_rows * r;
+    dct_table_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(Phi_dev, n_rows, r, row0, n_h, 0., 0, ld);
+    PB_LAUNCH_CHECK(ctx);
+    return PB_OK;
+}
+
 extern "C" int pb_dct_lowrank(pb_ctx* ctx, int64_t n_h, int64_t n_s, int r, double decay,
                               int64_t row0, int64_t n_rows, double* U_dev, int64_t ldu) {
     PB_ENTER(ctx);

@@ -56,17 +56,60 @@ def perform_pod(U, eps=0., n_L=0, verbose=True, *, mode=DEFAULT_MODE, ctx=None, 
     return (V, sig) if return_sigma else V
 
 
+def _slab(ctx, n_h, n_st):
+    """The context-owned device slab (pb_slab: grown on demand, reused across calls) viewed as an (n_h, n_st) matrix."""
+    p = C.c_void_p()
+    ctx.check(_lib.lib().pb_slab(ctx.h, 8 * n_h * n_st, C.byref(p)))
+    return ctx.wrap(p.value, (n_h, n_st))
+
+
 def pod_host(ctx, U, eps=0., n_L=0, mode=DEFAULT_MODE):
-    """POD of a host matrix: chunked upload overlapped with the Gram (pb_pod_host)."""
+    """POD of a host matrix (an ordinary numpy array): chunked upload overlapped with the Gram (pb_pod_host; pageable
+    memory goes through the library's pinned staging ring).  The uploaded matrix stays in the context's slab until the
+    next host-facing call: `project_to_v(V, U, reuse_slab=True)` can project onto it without a second upload."""
     U = np.ascontiguousarray(U, dtype=np.float64)
     n_h, n_st = U.shape
-    Ud = ctx.alloc(n_h, n_st)
+    Ud = _slab(ctx, n_h, n_st)
+    ctx._slab_shape = None
     nl = C.c_int()
     ctx.check(_lib.lib().pb_pod_host(ctx.h, U.ctypes.data, n_h, n_st, n_st, Ud.ptr, float(eps), int(n_L),
                                      POD_MODES[mode], C.byref(nl)))
     V = ctx.alloc(n_h, nl.value)
     ctx.check(_lib.lib().pb_pod_basis_full(ctx.h, Ud.ptr, n_h, n_st, Ud.ld, V.ptr, V.ld))
+    ctx._slab_shape = (n_h, n_st)
+    ctx._slab_V = V                                   # the basis of the slab's matrix, still in HBM
     return V, pod_sigma(ctx)
+
+
+def project_to_v(V, U, *, ctx=None, reuse_slab=False):
+    """v = (V.T.dot(U)).T (podnnmodel.py:435-437) as a module-level call: numpy in, numpy (n, n_L) out.
+
+    reuse_slab=True: `U` is the array the last perform_pod on this context was given and `V` what it returned; both
+    are still resident in HBM and are not uploaded again (the caller vouches that U has not been modified since)."""
+    ctx = ctx or _lib.default_context()
+    L = _lib.lib()
+    n_h, n = U.shape
+    n_L = V.shape[1]
+    if reuse_slab:
+        if getattr(ctx, "_slab_shape", None) != (n_h, n) or ctx._slab_V.shape != (n_h, n_L):
+            raise ValueError("project_to_v(reuse_slab=True): the context does not hold this matrix (call perform_pod on it first)")
+        Ud, Vd = _slab(ctx, n_h, n), ctx._slab_V
+    else:
+        Ud = U if isinstance(U, DeviceArray) else _slab_upload(ctx, U)
+        Vd = V if isinstance(V, DeviceArray) else ctx.to_device(V)
+    v = ctx.alloc(n, n_L)
+    ctx.check(L.pb_project(ctx.h, Vd.ptr, Vd.ld, n_L, Ud.ptr, Ud.ld, n_h, n, v.ptr))
+    return v.download()
+
+
+def _slab_upload(ctx, U):
+    """Host matrix -> the context's slab (staged upload for pageable memory)."""
+    U = np.ascontiguousarray(U, dtype=np.float64)
+    n_h, n = U.shape
+    Ud = _slab(ctx, n_h, n)
+    ctx._slab_shape = None
+    ctx.check(_lib.lib().pb_upload_matrix(ctx.h, U.ctypes.data, n_h, n, n, Ud.ptr))
+    return Ud
 
 
 def perform_fast_pod(U, eps, eps_init, *, mode=DEFAULT_MODE, ctx=None, return_ranks=False):
