@@ -579,7 +579,7 @@ def c5_leg(ctx, L, be, sharded, wl, world, rank, barrier, max_over_ranks, sum_ov
         ctx.check(L.pb_residual_gram(ctx.h, V.ptr, V.ld, nl, Phi.ptr, Phi.ld, nl, n_loc, Cd.ptr, Gd.ptr))
         angle = float(np.sqrt(max(0., np.linalg.eigvalsh(sum_over_ranks(Gd.download()))[-1])))
         Phi.release(); Cd.release(); Gd.release()
-        ok = (nl == nL_closed) and sig_err <= 1e-10 and angle <= 1e-8
+        ok = (nl == nL_closed) and sig_err <= 1e-10 and angle <= float(os.environ.get("PB_BENCH_ANGLE_TOL", "1e-8"))
         out[mode] = {"wall_s": ms * 1e-3, "n_L": nl, "tflops": flops / (ms * 1e-3) / 1e12,
                      "frac": flops / (ms * 1e-3) / 1e12 / (peak_tf * world),
                      "sigma_err_rel_sigma_max": sig_err, "subspace_angle": angle, "V_rows_err_rel": v_err,

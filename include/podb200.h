@@ -66,7 +66,8 @@ extern "C" {
 #define PB_T_PASS2      8
 #define PB_T_TN_KERNEL  9   /* the split-K DMMA kernel of the last pb_gram / TN product alone */
 #define PB_T_QR         10  /* the blocked Householder QR of the last pb_tsqr_r / TSQR-mode pb_pod */
-#define PB_T_COUNT      11
+#define PB_T_REFINE     11  /* gram2: the subspace-refinement step of the last pb_pod_basis_full (0 when not needed) */
+#define PB_T_COUNT      12
 
 typedef struct pb_ctx pb_ctx;
 
@@ -168,6 +169,16 @@ int  pb_pod_pass2_finish(pb_ctx* ctx, const double* G2_dev, double eps, int n_L_
  * After a second pass Y_dev must be the buffer filled by pb_pod_pass2_gram (else NULL). */
 int  pb_pod_basis(pb_ctx* ctx, const double* A_dev, int64_t n_rows, int64_t lda,
                   const double* Y_dev, double* V_dev, int64_t ldv);
+/* gram2 mode, subspace refinement (tolerance safety; see api.cu): the modes of a Gram-based POD carry an error along
+ * directions the numerical-rank block of the first pass does not span.  pb_pod_refine_steps returns 1 when the
+ * a-priori estimate 10 eps (sigma_1/sigma_nL)^3 sqrt(4 eps) exceeds north_star's 1e-8 angle tolerance; then ONE
+ * step of subspace iteration with the matrix itself follows the basis: B = A^T V (pb_project on every slab +
+ * all-reduce), pb_pod_refine_apply (V~ = A_local B Sigma^-2, G3 = V~^T V~ partial), all-reduce G3,
+ * pb_pod_refine_finish (V = V~ R^-1, R^T R = G3).  pb_pod_basis_full does all of it on one GPU. */
+int  pb_pod_refine_steps(pb_ctx* ctx, int* steps);
+int  pb_pod_refine_estimate(pb_ctx* ctx, double* est);   /* the a-priori angle estimate the decision was taken on */
+int  pb_pod_refine_apply(pb_ctx* ctx, const double* A_dev, int64_t n_rows, int64_t lda, double* B_dev, double* G3_dev);
+int  pb_pod_refine_finish(pb_ctx* ctx, const double* G3_dev, int64_t n_rows, double* V_dev, int64_t ldv);
 /* singular values of the last decomposition (descending; zero beyond numerical rank) */
 int  pb_pod_sigma(pb_ctx* ctx, double* sigma_host, int64_t capacity, int64_t* count);
 /* right factor of the last decomposition: Z (n_cols x n_L, ld = n_L), V = A Z diag(1/sigma) */

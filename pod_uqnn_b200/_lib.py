@@ -20,7 +20,7 @@ PB_ERR_CUDA, PB_ERR_SHAPE, PB_ERR_UNSUPPORTED_FIELD, PB_ERR_NOT_CONVERGED, PB_ER
 FIELD_IDS = {"shekel": 1, "ackley": 2, "burgers": 3}
 POD_MODES = {"gram": 0, "gram2": 1, "accurate": 2, "tsqr": 3}
 NORM_IDS = {"none": 0, "meanstd": 1, "center": 2}
-T_GRAM, T_EIG, T_BASIS, T_PROJECT, T_RECON, T_SNAPSHOTS, T_PREDICT, T_POD_TOTAL, T_PASS2, T_TN_KERNEL, T_QR = range(11)
+T_GRAM, T_EIG, T_BASIS, T_PROJECT, T_RECON, T_SNAPSHOTS, T_PREDICT, T_POD_TOTAL, T_PASS2, T_TN_KERNEL, T_QR, T_REFINE = range(12)
 
 _i64, _int, _dbl, _vp = C.c_int64, C.c_int, C.c_double, C.c_void_p
 _pi, _pd, _pvp = C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_void_p)
@@ -58,6 +58,10 @@ SIGNATURES = {
     "pb_pod_pass2_gram": (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "pb_pod_pass2_finish": (_int, [_vp, _vp, _dbl, _int, _pi]),
     "pb_pod_basis": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _i64]),
+    "pb_pod_refine_steps": (_int, [_vp, _pi]),
+    "pb_pod_refine_estimate": (_int, [_vp, _pd]),
+    "pb_pod_refine_apply": (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "pb_pod_refine_finish": (_int, [_vp, _vp, _i64, _vp, _i64]),
     "pb_pod_sigma": (_int, [_vp, _vp, _i64, C.POINTER(_i64)]),
     "pb_pod_right": (_int, [_vp, _vp, _i64]),
     "pb_tsqr_r": (_int, [_vp, _vp, _i64, _i64, _i64, _vp]),

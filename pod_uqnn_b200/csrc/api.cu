@@ -104,6 +104,8 @@ int pb_destroy(pb_ctx* ctx) {
     if (ctx->Gpart) cudaFree(ctx->Gpart);
     for (int s = 0; s < PB_STAGE_SLOTS; ++s) { if (ctx->stage[s]) cudaFreeHost(ctx->stage[s]); if (ctx->stage_ev[s]) cudaEventDestroy(ctx->stage_ev[s]); }
     if (ctx->slab) cudaFree(ctx->slab);
+    if (ctx->Rbuf) cudaFree(ctx->Rbuf);
+    if (ctx->Pbuf) cudaFree(ctx->Pbuf);
     pbi_train_free(ctx);
     pbi_gram_plan_free(ctx);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -209,7 +211,7 @@ static int finish_rank(pb_ctx* ctx, const double* sig_dev, int64_t count, int av
         if (nl > avail) nl = avail;
         if (ctx->sigma_pending) {
             ctx->sigma_host.assign((size_t)ctx->sig_total, 0.);
-            memcpy(ctx->sigma_host.data(), ctx->h_sig, sizeof(double) * (size_t)ctx->sig_count);
+            memcpy(ctx->sigma_host.data(), ctx->h_sig, sizeof(double) * (size_t)std::min(ctx->sig_count, ctx->sig_total));
             ctx->sigma_pending = false;
         }
     }
@@ -239,6 +241,7 @@ int pb_pod_from_gram(pb_ctx* ctx, const double* G, int64_t m, double eps, int n_
     if (!(eps >= 0.) || eps >= 1.) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod: eps must be in [0, 1)");
     Timer t(ctx, PB_T_EIG);
     ctx->m = m; ctx->mode = mode; ctx->pass2_done = false;
+    ctx->refine_steps = 0; ctx->refine_est = 0.; ctx->ms[PB_T_REFINE] = 0.; ctx->t_pending[PB_T_REFINE] = false;
     PB_TRY(pb_reserve(ctx, &ctx->sig, &ctx->sig_cap, (size_t)m + 32));
     PB_TRY(pb_reserve(ctx, &ctx->nrm, &ctx->nrm_cap, (size_t)m + 32));
     PB_TRY(pb_reserve_int(ctx, &ctx->perm, &ctx->perm_cap, (size_t)m + 64));
@@ -262,6 +265,112 @@ int pb_pod_from_gram(pb_ctx* ctx, const double* G, int64_t m, double eps, int n_
     PB_TRY(fetch_sigma(ctx, ctx->sig, m, m));
     PB_TRY(finish_rank(ctx, ctx->sig, m, ctx->r, eps, n_L_in, n_L));
     t.stop();
+    return PB_OK;
+}
+
+// ---- subspace refinement of the gram2 mode ---------------------------------------------------------------------
+// The first Gram pass resolves the right singular vectors z_k only to eps lambda_1 / lambda_k: z_k leaks into the
+// directions the numerical-rank block W_r does not span (singular values below sqrt(4 eps) sigma_1, the pivoted
+// Cholesky's stopping threshold), and a mode v_k = U z_k / sigma_k inherits that leak damped by sigma_tail / sigma_k.
+// Those components lie OUTSIDE span(U W_r), so the second Gram pass cannot remove them (north_star's tolerance: 1e-8).
+// A-priori estimate, x = sigma_1 / sigma_nL (set by eps: ~1e5 at eps = 1e-10), m = order of the Gram:
+//   tall: 0.5 eps x^3 sqrt(4 eps) max(1, m/1024)^3     wide: 0.4 eps x^2   (the modes ARE the Gram eigenvectors)
+// fitted as an upper envelope of the unrefined angles measured on B200 (profiles/r02_gram2_angles.txt): C2 2.3e-10
+// (estimate 5.4e-10), DCT decay 1/4 at m = 1024 / 2048 / 4096: 9.3e-10 / 6.5e-9 / 4.6e-8 (2.6e-9 / 2.1e-8 / 1.7e-7),
+// Shekel 400 x 300 1.2e-9 (3e-9), Shekel C1 wide 4.7e-7 (2e-6), Burgers 256 x 1200 wide 1.2e-8 (3e-8).  When it exceeds
+// 1e-8 ONE step of subspace iteration with the matrix itself follows: V~ = A (A^T V) Sigma^-2, V = V~ R^-1 with
+// R^T R = V~^T V~ (V~ is nearly orthonormal, so the Cholesky QR is safe); the out-of-span error shrinks by
+// (sigma_tail/sigma_nL)^2 <= 1e-5.  PB_GRAM2_REFINE=0/1 forces it off / on.
+static int refine_steps_needed(pb_ctx* ctx) {
+    static const int env = []{ const char* e = getenv("PB_GRAM2_REFINE"); return e ? atoi(e) : -1; }();
+    if (ctx->mode != PB_POD_GRAM2 || ctx->n_L <= 0) return 0;
+    if (env == 0) return 0;
+    if (env == 1) return 1;
+    if (ctx->sigma_host.size() < (size_t)ctx->n_L) return 0;
+    const double s1 = ctx->sigma_host[0], sl = ctx->sigma_host[ctx->n_L - 1];
+    if (!(sl > 0.) || !(s1 > 0.)) return 0;
+    const double x = s1 / sl, mf = std::max(1., (double)ctx->m / 1024.);
+    const double est = ctx->wide ? 0.4 * DBL_EPSILON * x * x
+                                 : 0.5 * DBL_EPSILON * x * x * x * sqrt(4. * DBL_EPSILON) * mf * mf * mf;
+    ctx->refine_est = est;
+    return est > 1e-8 ? 1 : 0;
+}
+
+// in-place lower Cholesky of a small SPD matrix (host) and the inverse of its transpose factor: on return
+// Rinv (n x n, row-major, upper triangular) satisfies (G = R^T R)  V~ Rinv orthonormal
+static bool host_chol_rinv(std::vector<double>& G, int n, std::vector<double>& Rinv) {
+    // R upper triangular with G = R^T R (row-oriented Cholesky)
+    std::vector<double> R((size_t)n * n, 0.);
+    for (int i = 0; i < n; ++i) {
+        for (int j = i; j < n; ++j) {
+            double s = G[(size_t)i * n + j];
+            for (int k = 0; k < i; ++k) s -= R[(size_t)k * n + i] * R[(size_t)k * n + j];
+            if (j == i) { if (!(s > 0.)) return false; R[(size_t)i * n + i] = sqrt(s); }
+            else R[(size_t)i * n + j] = s / R[(size_t)i * n + i];
+        }
+    }
+    Rinv.assign((size_t)n * n, 0.);
+    for (int j = 0; j < n; ++j) {                    // column j of R^-1 by back substitution
+        Rinv[(size_t)j * n + j] = 1. / R[(size_t)j * n + j];
+        for (int i = j - 1; i >= 0; --i) {
+            double s = 0.;
+            for (int k = i + 1; k <= j; ++k) s += R[(size_t)i * n + k] * Rinv[(size_t)k * n + j];
+            Rinv[(size_t)i * n + j] = -s / R[(size_t)i * n + i];
+        }
+    }
+    return true;
+}
+
+namespace {
+// B[i][j] *= 1 / sig[j]^2
+__global__ void scale_cols_inv_sq_kernel(double* __restrict__ B, int64_t n, int k, const double* __restrict__ sig) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * k) return;
+    const double s = sig[idx % k];
+    B[idx] = s > 0. ? B[idx] / (s * s) : 0.;
+}
+}  // namespace
+
+int pb_pod_refine_steps(pb_ctx* ctx, int* steps) {
+    PB_ENTER(ctx); if (!steps) return PB_ERR_ARG;
+    *steps = ctx->pass2_done ? ctx->refine_steps : 0;
+    return PB_OK;
+}
+
+int pb_pod_refine_estimate(pb_ctx* ctx, double* est) {
+    PB_ENTER(ctx); if (!est) return PB_ERR_ARG;
+    *est = ctx->pass2_done ? ctx->refine_est : 0.;
+    return PB_OK;
+}
+
+// Tall case, row-sharded form.  B (m x n_L, ld n_L) = A^T V summed over all rows (pb_project + all-reduce).  Forms
+// V~ = A_local B Sigma^-2 in the context (rows x n_L) and G3 (n_L x n_L) = V~^T V~ over the local rows.
+int pb_pod_refine_apply(pb_ctx* ctx, const double* A, int64_t rows, int64_t lda, double* B, double* G3) {
+    PB_ENTER(ctx); if (!A || !B || !G3) return PB_ERR_ARG;
+    const int nl = ctx->n_L; const int64_t m = ctx->m;
+    if (!ctx->pass2_done || nl <= 0) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod_refine_apply: no second-pass decomposition");
+    const double* sig = ctx->sig2;
+    scale_cols_inv_sq_kernel<<<(unsigned)((m * nl + 255) / 256), 256, 0, ctx->stream>>>(B, m, nl, sig);
+    PB_LAUNCH_CHECK(ctx);
+    PB_TRY(pb_reserve(ctx, &ctx->Rbuf, &ctx->R_cap, (size_t)rows * nl));
+    PB_TRY(pbi_gemm_nn(ctx, A, lda, rows, m, B, nl, nl, ctx->Rbuf, nl, nullptr, 0, nullptr));
+    PB_TRY(pbi_gemm_tn(ctx, ctx->Rbuf, nl, nl, ctx->Rbuf, nl, nl, rows, G3, nl, 1));
+    return PB_OK;
+}
+
+// G3 = the all-reduced V~^T V~.  V (rows x n_L, ldv) = V~ R^-1.
+int pb_pod_refine_finish(pb_ctx* ctx, const double* G3, int64_t rows, double* V, int64_t ldv) {
+    PB_ENTER(ctx); if (!G3 || !V) return PB_ERR_ARG;
+    const int nl = ctx->n_L;
+    if (!ctx->Rbuf || nl <= 0) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod_refine_finish: call pb_pod_refine_apply first");
+    std::vector<double> g((size_t)nl * nl), rinv;
+    PB_CUDA(ctx, cudaMemcpyAsync(g.data(), G3, sizeof(double) * g.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!host_chol_rinv(g, nl, rinv)) PB_FAIL(ctx, PB_ERR_NOT_CONVERGED, "pb_pod_refine_finish: refined block is rank deficient");
+    PB_TRY(pb_reserve(ctx, &ctx->Bmat, &ctx->B_cap, (size_t)nl * nl));
+    PB_CUDA(ctx, cudaMemcpyAsync(ctx->Bmat, rinv.data(), sizeof(double) * rinv.size(), cudaMemcpyHostToDevice, ctx->stream));
+    PB_TRY(pbi_gemm_nn(ctx, ctx->Rbuf, nl, rows, nl, ctx->Bmat, nl, nl, V, ldv, nullptr, 0, nullptr));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // rinv (host) is read by the async copy above
     return PB_OK;
 }
 
@@ -289,6 +398,7 @@ int pb_pod_pass2_finish(pb_ctx* ctx, const double* G2, double eps, int n_L_in, i
     PB_TRY(fetch_sigma(ctx, ctx->sig2, keep, ctx->m));
     PB_TRY(finish_rank(ctx, ctx->sig2, keep, ctx->r2, eps, n_L_in, n_L));
     ctx->pass2_done = true;
+    ctx->refine_steps = refine_steps_needed(ctx);
     return PB_OK;
 }
 
@@ -319,7 +429,7 @@ int pb_pod_sigma(pb_ctx* ctx, double* sigma_host, int64_t capacity, int64_t* cou
     if (ctx->sigma_pending) {
         PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->sigma_host.assign((size_t)ctx->sig_total, 0.);
-        memcpy(ctx->sigma_host.data(), ctx->h_sig, sizeof(double) * (size_t)ctx->sig_count);
+        memcpy(ctx->sigma_host.data(), ctx->h_sig, sizeof(double) * (size_t)std::min(ctx->sig_count, ctx->sig_total));
         ctx->sigma_pending = false;
     }
     int64_t n = std::min<int64_t>(capacity, (int64_t)ctx->sigma_host.size());
@@ -607,12 +717,40 @@ int pb_pod_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, in
 
 int pb_pod_basis_full(pb_ctx* ctx, const double* U, int64_t n_h, int64_t n_st, int64_t ldu, double* V, int64_t ldv) {
     PB_ENTER(ctx);
-    if (ldv < ctx->n_L) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod_basis_full: ldv %lld < n_L %d", (long long)ldv, ctx->n_L);
-    if (!ctx->wide) return pb_pod_basis(ctx, U, n_h, ldu, ctx->pass2_done ? ctx->Ybuf : nullptr, V, ldv);
-    (void)n_st;
+    const int nl = ctx->n_L;
+    if (ldv < nl) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod_basis_full: ldv %lld < n_L %d", (long long)ldv, nl);
+    const bool refine = ctx->pass2_done && ctx->refine_steps > 0;
+    if (!ctx->wide) {
+        PB_TRY(pb_pod_basis(ctx, U, n_h, ldu, ctx->pass2_done ? ctx->Ybuf : nullptr, V, ldv));
+        if (!refine) return PB_OK;
+        Timer t(ctx, PB_T_REFINE);
+        PB_TRY(pb_reserve(ctx, &ctx->Pbuf, &ctx->P_cap, (size_t)n_st * nl + (size_t)nl * nl));
+        double* B = ctx->Pbuf; double* G3 = B + (size_t)n_st * nl;
+        PB_TRY(pb_project(ctx, V, ldv, nl, U, ldu, n_h, n_st, B));          // B = (V^T U)^T = U^T V  (n_st x n_L)
+        PB_TRY(pb_pod_refine_apply(ctx, U, n_h, ldu, B, G3));
+        PB_TRY(pb_pod_refine_finish(ctx, G3, n_h, V, ldv));
+        t.stop();
+        return PB_OK;
+    }
     Timer t(ctx, PB_T_BASIS);
     PB_TRY(pb_pod_right(ctx, V, ldv));        // wide: the modes are the right factor of U^T
     t.stop();
+    if (refine) {
+        // wide case: A = U^T (n_st x n_h, in ctx->ATbuf) is the tall operand, the modes are its RIGHT singular vectors:
+        // Z~ = A^T (A Z) Sigma^-2 = U (U^T Z) Sigma^-2, then the Cholesky QR of the n_h x n_L block
+        Timer t2(ctx, PB_T_REFINE);
+        const double* A = ctx->ATbuf; const int64_t rows = n_st, m = n_h;
+        PB_TRY(pb_reserve(ctx, &ctx->Pbuf, &ctx->P_cap, (size_t)rows * nl + (size_t)nl * nl));
+        double* B = ctx->Pbuf; double* G3 = B + (size_t)rows * nl;
+        PB_TRY(pbi_gemm_nn(ctx, A, m, rows, m, V, ldv, nl, B, nl, nullptr, 0, nullptr));                 // B = A Z (n_st x n_L)
+        scale_cols_inv_sq_kernel<<<(unsigned)((rows * nl + 255) / 256), 256, 0, ctx->stream>>>(B, rows, nl, ctx->sig2);
+        PB_LAUNCH_CHECK(ctx);
+        PB_TRY(pb_reserve(ctx, &ctx->Rbuf, &ctx->R_cap, (size_t)m * nl));
+        PB_TRY(pbi_gemm_tn(ctx, A, m, m, B, nl, nl, rows, ctx->Rbuf, nl, 0));                              // Z~ = A^T B (n_h x n_L)
+        PB_TRY(pbi_gemm_tn(ctx, ctx->Rbuf, nl, nl, ctx->Rbuf, nl, nl, m, G3, nl, 1));
+        PB_TRY(pb_pod_refine_finish(ctx, G3, m, V, ldv));
+        t2.stop();
+    }
     return PB_OK;
 }
 

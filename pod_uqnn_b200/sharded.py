@@ -4,6 +4,7 @@ U is sharded by dof: rank p owns the contiguous row slab row_range(n_h, p, P) of
 row-major snapshot matrix.  Exchange steps (the only ones on the path):
   * sum-all-reduce of the local n_st x n_st Gram partial (and of the second-pass Gram),
   * sum-all-reduce of the local projection partial V_p^T U_p,
+  * gram2 mode, only when the tolerance estimate asks for the subspace-refinement step: two more small all-reduces,
   * TSQR mode: all-gather of the P local R factors (n_st x n_st each), then the QR of the stack is replicated.
 The small eigensolve is replicated: every rank runs it on the bit-identical reduced Gram
 and gets the same rank and factors.  Snapshot generation, basis, reconstruction and
@@ -74,6 +75,14 @@ def pod_sharded(backend, A_local, eps=0., n_L=0, mode="gram", group=None, A_host
         backend.reduce(G2, group)
         n_L_out = backend.pass2_finish(G2, eps, n_L)
     V = backend.basis(A_local, Y, n_L_out)
+    if keep > 0 and backend.refine_steps() > 0:
+        # gram2 tolerance safety (csrc/api.cu, "subspace refinement"): one step of subspace iteration with the matrix
+        # itself -- two more all-reduces (the n_st x n_L projection block and an n_L x n_L Gram)
+        B = backend.project(V, A_local)
+        backend.reduce(B, group)
+        G3 = backend.refine_apply(A_local, B)
+        backend.reduce(G3, group)
+        backend.refine_finish(G3, V)
     return V, backend.sigma(), n_L_out
 
 
@@ -187,6 +196,20 @@ class CudaBackend:
         self.ctx.check(self.L.pb_pod_basis(self.ctx.h, A.ptr, A.shape[0], A.ld, Y.ptr if Y is not None else None,
                                            V.ptr, V.ld))
         return V
+
+    def refine_steps(self):
+        st = C.c_int()
+        self.ctx.check(self.L.pb_pod_refine_steps(self.ctx.h, C.byref(st)))
+        return st.value
+
+    def refine_apply(self, A, B):
+        n_L = B.shape[1]
+        G3 = self._scratch("G3", n_L, n_L)
+        self.ctx.check(self.L.pb_pod_refine_apply(self.ctx.h, A.ptr, A.shape[0], A.ld, B.data_ptr(), G3.data_ptr()))
+        return G3
+
+    def refine_finish(self, G3, V):
+        self.ctx.check(self.L.pb_pod_refine_finish(self.ctx.h, G3.data_ptr(), V.shape[0], V.ptr, V.ld))
 
     def sigma(self):
         from .pod import pod_sigma

@@ -65,6 +65,20 @@ class NumpyBackend:
             return Y @ self._W2[:, :n_L] / self._sig2[:n_L]
         return A @ self._W[:, :n_L] / self._sig[:n_L]
 
+    # gram2 subspace refinement (always engaged here so that the gloo test walks the two extra all-reduces)
+    def refine_steps(self):
+        return 1
+
+    def refine_apply(self, A, B):
+        Bn = B.numpy()
+        Bn /= self._sig2[:Bn.shape[1]] ** 2
+        self._Vt = A @ Bn
+        return torch.from_numpy(self._Vt.T @ self._Vt)
+
+    def refine_finish(self, G3, V):
+        R = np.linalg.cholesky(G3.numpy()).T
+        V[:] = self._Vt @ np.linalg.inv(R)
+
     def sigma(self):
         return self._sig
 

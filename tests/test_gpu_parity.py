@@ -123,7 +123,9 @@ def test_perform_pod_matches_reference(ctx, name, field, mode):
         v = po.project_to_v(V, U)
         Va, s = cmp.align_signs(V, g["V"])
         assert cmp.rel_err(v * s, g["v"]) <= 1e-8                          # coefficients up to sign
-    elif mode == "gram2" and field == "ackley":
+    elif mode == "gram2":
+        # tolerance-safe since round 2: the library adds one subspace-refinement step when its a-priori estimate of
+        # the Gram-path angle exceeds 1e-8 (csrc/api.cu); unrefined it measured 4.7e-7 on shekel_c1, 1.2e-8 on burgers_1step
         assert angle <= cmp.TOL_ANGLE
     else:
         # one Gram pass: bounded by eps_mach * lambda_1 / gap, reported not required
