@@ -2,6 +2,7 @@
 // See include/podb200.h for the contract and the reference interfaces each entry replaces.
 #include "common.cuh"
 #include <cfloat>
+#include <cmath>
 #include <algorithm>
 #include <mutex>
 #include <thread>
@@ -185,6 +186,7 @@ int pb_gram(pb_ctx* ctx, const double* A, int64_t rows, int64_t cols, int64_t ld
     PB_ENTER(ctx);
     if (lda < cols) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_gram: lda %lld < n_cols %lld", (long long)lda, (long long)cols);
     Timer t(ctx, PB_T_GRAM);
+    ctx->gram_rows = rows;
     PB_TRY(pbi_gemm_tn(ctx, A, lda, cols, A, lda, cols, rows, G, cols, 3));   // sym | time the main kernel
     t.stop();
     return PB_OK;
@@ -273,11 +275,13 @@ int pb_pod_from_gram(pb_ctx* ctx, const double* G, int64_t m, double eps, int n_
 // directions the numerical-rank block W_r does not span (singular values below sqrt(4 eps) sigma_1, the pivoted
 // Cholesky's stopping threshold), and a mode v_k = U z_k / sigma_k inherits that leak damped by sigma_tail / sigma_k.
 // Those components lie OUTSIDE span(U W_r), so the second Gram pass cannot remove them (north_star's tolerance: 1e-8).
-// A-priori estimate, x = sigma_1 / sigma_nL (set by eps: ~1e5 at eps = 1e-10), m = order of the Gram:
-//   tall: 0.5 eps x^3 sqrt(4 eps) max(1, m/1024)^3     wide: 0.4 eps x^2   (the modes ARE the Gram eigenvectors)
-// fitted as an upper envelope of the unrefined angles measured on B200 (profiles/r02_gram2_angles.txt): C2 2.3e-10
-// (estimate 5.4e-10), DCT decay 1/4 at m = 1024 / 2048 / 4096: 9.3e-10 / 6.5e-9 / 4.6e-8 (2.6e-9 / 2.1e-8 / 1.7e-7),
-// Shekel 400 x 300 1.2e-9 (3e-9), Shekel C1 wide 4.7e-7 (2e-6), Burgers 256 x 1200 wide 1.2e-8 (3e-8).  When it exceeds
+// A-priori estimate, x = sigma_1 / sigma_nL (set by eps: ~1e5 at eps = 1e-10), m = order of the Gram, n = rows the
+// Gram was accumulated over on this GPU (its rounding error grows ~ n^1.2: 9.3e-10 -> 2.9e-8 from 65 536 to 1 M rows):
+//   tall: 0.54 eps x^3 sqrt(4 eps) max(1, n/65536)^1.2 max(1, m/1024)^0.8      wide: 0.4 eps x^2  (no damping)
+// fitted as an upper envelope (x 3 at the anchor) of the unrefined angles measured on B200 (profiles/r02_gram2_angles.txt):
+// DCT decay 1/4 at 65 536 x 1024 / 1 M x 1024 / 200 000 x 2048 / 1.25 M x 4096: 9.3e-10 / 2.9e-8 / 6.5e-9 / 4.6e-8
+// (estimates 2.8e-9 / 7.8e-8 / 1.9e-8 / 2.9e-7), C2 2.3e-10 (1.8e-9), Shekel 400 x 300 1.2e-9 (3e-9), Shekel C1 wide
+// 4.7e-7 (2e-6), Burgers 256 x 1200 wide 1.2e-8 (3e-8).  When it exceeds
 // 1e-8 ONE step of subspace iteration with the matrix itself follows: V~ = A (A^T V) Sigma^-2, V = V~ R^-1 with
 // R^T R = V~^T V~ (V~ is nearly orthonormal, so the Cholesky QR is safe); the out-of-span error shrinks by
 // (sigma_tail/sigma_nL)^2 <= 1e-5.  PB_GRAM2_REFINE=0/1 forces it off / on.
@@ -289,9 +293,10 @@ static int refine_steps_needed(pb_ctx* ctx) {
     if (ctx->sigma_host.size() < (size_t)ctx->n_L) return 0;
     const double s1 = ctx->sigma_host[0], sl = ctx->sigma_host[ctx->n_L - 1];
     if (!(sl > 0.) || !(s1 > 0.)) return 0;
-    const double x = s1 / sl, mf = std::max(1., (double)ctx->m / 1024.);
+    const double x = s1 / sl;
+    const double size_f = pow(std::max(1., (double)ctx->gram_rows / 65536.), 1.2) * pow(std::max(1., (double)ctx->m / 1024.), 0.8);
     const double est = ctx->wide ? 0.4 * DBL_EPSILON * x * x
-                                 : 0.5 * DBL_EPSILON * x * x * x * sqrt(4. * DBL_EPSILON) * mf * mf * mf;
+                                 : 0.54 * DBL_EPSILON * x * x * x * sqrt(4. * DBL_EPSILON) * size_f;
     ctx->refine_est = est;
     return est > 1e-8 ? 1 : 0;
 }
@@ -640,6 +645,7 @@ int gram_host_chunked(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_
     PB_CUDA(ctx, cudaEventRecord(ctx->chunk_ev[0], ctx->stream));
     PB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[0], 0));
     int used = 0;
+    ctx->gram_rows = n_h;
     Timer tg(ctx, PB_T_GRAM);
     const bool pinned = host_is_pinned(U_host);
     if (!pinned) PB_TRY(stage_reserve(ctx, (size_t)64 << 20));
