@@ -47,7 +47,9 @@ extern "C" {
 #define PB_POD_GRAM      0  /* method of snapshots, one Gram pass                     */
 #define PB_POD_GRAM2     1  /* + second Gram pass on the rotated numerical-rank block */
 #define PB_POD_ACCURATE  2  /* full rotate + second Gram (Jacobi-SVD accuracy class)  */
-#define PB_POD_TSQR      3  /* Householder QR of U (never U^T U), pivoted QR + Jacobi SVD of R */
+#define PB_POD_TSQR      3  /* Householder QR of U (never U^T U), pivoted QR + Jacobi SVD of the factor; rank-revealing:
+                               block column pivoting, stops when the residual is below the QR's rounding error */
+#define PB_POD_TSQR_FULL 4  /* the same without the early stop: all n_cols/64 panels (pb_pod only; benchmarking) */
 
 /* input normalisation of the surrogate (varneuralnetwork.py:10-12,75-86) */
 #define PB_NORM_NONE     0
@@ -195,6 +197,24 @@ int  pb_pod_right(pb_ctx* ctx, double* Z_dev, int64_t ldz);
  *                  and pb_pod_sigma / pb_pod_right work as after pb_pod_from_gram. */
 int  pb_tsqr_r(pb_ctx* ctx, const double* A_dev, int64_t n_rows, int64_t n_cols, int64_t lda, double* R_dev);
 int  pb_pod_from_r(pb_ctx* ctx, const double* R_dev, int64_t n_cols, double eps, int n_L_in, int* n_L);
+/* Rank-revealing form (what PB_POD_TSQR runs).  Snapshot matrices have low numerical rank, and the SVD (pod.py:16)
+ * needs only a factor F with F^T F = A^T A to working accuracy:
+ *   pb_tsqr_factor:     blocked Householder QR with block column pivoting (before each 64-column panel the columns
+ *                       with the largest residual norms are moved into it) that STOPS as soon as every residual column
+ *                       is below 16 eps sqrt(panels) x the largest column norm of A -- the level of the rounding error
+ *                       the reflections themselves leave in the kept rows.  F_dev is an n_cols x n_cols buffer (ld =
+ *                       n_cols): rows [0, *f_rows) hold the factor (dense, in A's column order), the rest is zeroed.
+ *                       A matrix of full numerical rank runs every panel and gets the triangular R, column-permuted.
+ *                       Row-sharded: every rank factors its slab, the first max_p f_rows_p rows of the P factors are
+ *                       all-gathered and stacked, pb_tsqr_factor again on the stack (replicated).
+ *   pb_pod_from_factor: pivoted QR + Jacobi SVD of a dense factor (f_rows x n_cols, ld ldf), as pb_pod_from_r.
+ *   pb_tsqr_stats:      of the last pb_tsqr_r / pb_tsqr_factor: 64-column panels run (all leaves), rows of the factor,
+ *                       Householder flop count of the panels actually run. */
+int  pb_tsqr_factor(pb_ctx* ctx, const double* A_dev, int64_t n_rows, int64_t n_cols, int64_t lda, double* F_dev,
+                    int64_t* f_rows);
+int  pb_pod_from_factor(pb_ctx* ctx, const double* F_dev, int64_t f_rows, int64_t n_cols, int64_t ldf, double eps,
+                        int n_L_in, int* n_L);
+int  pb_tsqr_stats(pb_ctx* ctx, int64_t* panels, int64_t* f_rows, double* flops);
 
 /* One-call single-GPU POD of a device matrix (tall or wide).  V via pb_pod_basis_full(). */
 int  pb_pod(pb_ctx* ctx, const double* U_dev, int64_t n_h, int64_t n_st, int64_t ldu,

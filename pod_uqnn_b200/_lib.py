@@ -18,7 +18,7 @@ PB_OK = 0
 PB_ERR_CUDA, PB_ERR_SHAPE, PB_ERR_UNSUPPORTED_FIELD, PB_ERR_NOT_CONVERGED, PB_ERR_ARG, PB_ERR_NOMEM = \
     -1, -2, -3, -4, -5, -6
 FIELD_IDS = {"shekel": 1, "ackley": 2, "burgers": 3}
-POD_MODES = {"gram": 0, "gram2": 1, "accurate": 2, "tsqr": 3}
+POD_MODES = {"gram": 0, "gram2": 1, "accurate": 2, "tsqr": 3, "tsqr_full": 4}
 NORM_IDS = {"none": 0, "meanstd": 1, "center": 2}
 T_GRAM, T_EIG, T_BASIS, T_PROJECT, T_RECON, T_SNAPSHOTS, T_PREDICT, T_POD_TOTAL, T_PASS2, T_TN_KERNEL, T_QR, T_REFINE = range(12)
 
@@ -66,6 +66,9 @@ SIGNATURES = {
     "pb_pod_right": (_int, [_vp, _vp, _i64]),
     "pb_tsqr_r": (_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
     "pb_pod_from_r": (_int, [_vp, _vp, _i64, _dbl, _int, _pi]),
+    "pb_tsqr_factor": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "pb_pod_from_factor": (_int, [_vp, _vp, _i64, _i64, _i64, _dbl, _int, _pi]),
+    "pb_tsqr_stats": (_int, [_vp, _vp, _vp, _vp]),
     "pb_pod": (_int, [_vp, _vp, _i64, _i64, _i64, _dbl, _int, _int, _pi]),
     "pb_gram_host": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "pb_pod_basis_full": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64]),

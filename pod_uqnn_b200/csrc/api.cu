@@ -81,9 +81,9 @@ int pb_create(int device, pb_ctx** out) {
     PB_CUDA(ctx, cudaEventCreate(&ctx->evk0)); PB_CUDA(ctx, cudaEventCreate(&ctx->evk1));
     PB_CUDA(ctx, cudaEventCreate(&ctx->evr0)); PB_CUDA(ctx, cudaEventCreate(&ctx->evr1));
     for (int w = 0; w < PB_T_COUNT; ++w) { PB_CUDA(ctx, cudaEventCreate(&ctx->tev[w][0])); PB_CUDA(ctx, cudaEventCreate(&ctx->tev[w][1])); }
-    PB_CUDA(ctx, cudaMalloc(&ctx->d_int, 64 * sizeof(int)));
-    PB_CUDA(ctx, cudaMemset(ctx->d_int, 0, 64 * sizeof(int)));
-    PB_CUDA(ctx, cudaMallocHost(&ctx->h_int, 64 * sizeof(int)));
+    PB_CUDA(ctx, cudaMalloc(&ctx->d_int, 256 * sizeof(int)));
+    PB_CUDA(ctx, cudaMemset(ctx->d_int, 0, 256 * sizeof(int)));
+    PB_CUDA(ctx, cudaMallocHost(&ctx->h_int, 256 * sizeof(int)));
     *out = ctx;
     return PB_OK;
 }
@@ -464,14 +464,39 @@ int pb_tsqr_r(pb_ctx* ctx, const double* A, int64_t rows, int64_t cols, int64_t 
     if (rows <= 0 || cols <= 0 || lda < cols) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_tsqr_r: bad shape (%lld x %lld, ld %lld)",
                                                        (long long)rows, (long long)cols, (long long)lda);
     Timer t(ctx, PB_T_QR);
+    ctx->qr_panels = 0; ctx->qr_flops = 0.;
     PB_TRY(pbi_qr_r(ctx, A, rows, cols, lda, R, cols, cols));
+    ctx->qr_f_rows = cols;
     t.stop();
     return PB_OK;
 }
 
-int pb_pod_from_r(pb_ctx* ctx, const double* R, int64_t m, double eps, int n_L_in, int* n_L) {
-    PB_ENTER(ctx); if (!R || !n_L) return PB_ERR_ARG;
+int pb_tsqr_factor(pb_ctx* ctx, const double* A, int64_t rows, int64_t cols, int64_t lda, double* F, int64_t* f_rows) {
+    PB_ENTER(ctx); if (!A || !F || !f_rows) return PB_ERR_ARG;
+    if (rows <= 0 || cols <= 0 || lda < cols) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_tsqr_factor: bad shape (%lld x %lld, ld %lld)",
+                                                       (long long)rows, (long long)cols, (long long)lda);
+    Timer t(ctx, PB_T_QR);
+    ctx->qr_panels = 0; ctx->qr_flops = 0.;
+    PB_TRY(pbi_qr_factor(ctx, A, rows, cols, lda, F, cols, cols, true, f_rows));
+    ctx->qr_f_rows = *f_rows;
+    t.stop();
+    return PB_OK;
+}
+
+int pb_tsqr_stats(pb_ctx* ctx, int64_t* panels, int64_t* f_rows, double* flops) {
+    PB_ENTER(ctx);
+    if (panels) *panels = ctx->qr_panels;
+    if (f_rows) *f_rows = ctx->qr_f_rows;
+    if (flops) *flops = ctx->qr_flops;
+    return PB_OK;
+}
+
+// F (f_rows x m, ld ldf): upper != 0 -> an upper-triangular R (only the triangle is read)
+static int pod_from_factor(pb_ctx* ctx, const double* F, int64_t f_rows, int64_t m, int64_t ldf, int upper, double eps,
+                           int n_L_in, int* n_L) {
     if (m <= 0 || m > 8192) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod_from_r: order %lld outside (0, 8192]", (long long)m);
+    if (f_rows <= 0 || f_rows > m || ldf < m) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod_from_factor: %lld factor rows for %lld columns (ld %lld)",
+                                                       (long long)f_rows, (long long)m, (long long)ldf);
     if (!(eps >= 0.) || eps >= 1.) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod: eps must be in [0, 1)");
     Timer t(ctx, PB_T_EIG);
     ctx->m = m; ctx->mode = PB_POD_TSQR; ctx->pass2_done = false; ctx->n_keep = 0;
@@ -480,17 +505,28 @@ int pb_pod_from_r(pb_ctx* ctx, const double* R, int64_t m, double eps, int n_L_i
     PB_TRY(pb_reserve_int(ctx, &ctx->perm, &ctx->perm_cap, (size_t)m + 64));
     const int64_t ldm = (m + 7) / 8 * 8, cap_rows = (m + 31) / 32 * 32;
     PB_TRY(pb_reserve(ctx, &ctx->At, &ctx->At_cap, (size_t)cap_rows * ldm));
-    PB_TRY(pbi_qr_load_factor(ctx, R, m, m, ctx->At, ldm, cap_rows));
+    if (upper) PB_TRY(pbi_qr_load_factor(ctx, F, ldf, m, ctx->At, ldm, cap_rows));
+    else PB_TRY(pbi_qr_load_dense(ctx, F, ldf, f_rows, m, ctx->At, ldm, cap_rows));
     // eps == 0 asks for every mode (pod.py default): no truncation.  Otherwise stop the pivoted QR at the numerical
     // rank: what is left is below m eps |R| -- the backward error of the QR itself
     const bool full = (eps == 0. && n_L_in == 0);
-    PB_TRY(pbi_qrcp_factor(ctx, ctx->At, m, ldm, cap_rows, full ? 0. : (double)m * DBL_EPSILON, &ctx->r));
+    PB_TRY(pbi_qrcp_factor(ctx, ctx->At, m, f_rows, ldm, cap_rows, full ? 0. : (double)m * DBL_EPSILON, &ctx->r));
     if (ctx->r <= 0) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod_from_r: zero matrix");
     PB_TRY(pbi_jacobi_factor(ctx, ctx->At, m, ctx->r, nullptr, ctx->sig, ctx->nrm, ctx->perm, &ctx->sweeps1, 60));
     PB_TRY(fetch_sigma(ctx, ctx->sig, m, m));
     PB_TRY(finish_rank(ctx, ctx->sig, m, ctx->r, eps, n_L_in, n_L));
     t.stop();
     return PB_OK;
+}
+
+int pb_pod_from_r(pb_ctx* ctx, const double* R, int64_t m, double eps, int n_L_in, int* n_L) {
+    PB_ENTER(ctx); if (!R || !n_L) return PB_ERR_ARG;
+    return pod_from_factor(ctx, R, m, m, m, 1, eps, n_L_in, n_L);
+}
+
+int pb_pod_from_factor(pb_ctx* ctx, const double* F, int64_t f_rows, int64_t m, int64_t ldf, double eps, int n_L_in, int* n_L) {
+    PB_ENTER(ctx); if (!F || !n_L) return PB_ERR_ARG;
+    return pod_from_factor(ctx, F, f_rows, m, ldf, 0, eps, n_L_in, n_L);
 }
 
 // eigensolve + (optional) second pass on a tall operand whose Gram is already in ctx->Gbuf
@@ -525,10 +561,18 @@ int pb_pod(pb_ctx* ctx, const double* U, int64_t n_h, int64_t n_st, int64_t ldu,
     if (m > 8192) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod: min(n_h, n_st) = %lld exceeds 8192", (long long)m);
     PB_TRY(pb_reserve(ctx, &ctx->Gbuf, &ctx->G_cap, (size_t)m * m));
     ctx->wide = wide;
-    if (mode == PB_POD_TSQR) {
+    if (mode == PB_POD_TSQR || mode == PB_POD_TSQR_FULL) {
         ctx->ms[PB_T_GRAM] = 0.; ctx->ms[PB_T_PASS2] = 0.; ctx->t_pending[PB_T_GRAM] = ctx->t_pending[PB_T_PASS2] = false;
-        PB_TRY(pb_tsqr_r(ctx, A, rows, m, lda, ctx->Gbuf));
-        PB_TRY(pb_pod_from_r(ctx, ctx->Gbuf, m, eps, n_L_in, n_L));
+        // eps == 0 with no n_L asks for every mode: nothing may be dropped, so the plain QR runs
+        if (mode == PB_POD_TSQR_FULL || (eps == 0. && n_L_in == 0)) {
+            PB_TRY(pb_tsqr_r(ctx, A, rows, m, lda, ctx->Gbuf));
+            PB_TRY(pb_pod_from_r(ctx, ctx->Gbuf, m, eps, n_L_in, n_L));
+        } else {
+            int64_t f_rows = 0;
+            PB_TRY(pb_tsqr_factor(ctx, A, rows, m, lda, ctx->Gbuf, &f_rows));
+            if (f_rows <= 0) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod: zero matrix");
+            PB_TRY(pb_pod_from_factor(ctx, ctx->Gbuf, f_rows, m, m, eps, n_L_in, n_L));
+        }
     } else {
         PB_TRY(pb_gram(ctx, A, rows, m, lda, ctx->Gbuf));
         PB_TRY(pod_after_gram(ctx, A, rows, m, lda, eps, n_L_in, mode, n_L));
@@ -709,7 +753,7 @@ int pb_pod_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, in
     const int64_t m = n_st;
     if (n_h >= n_st) PB_TRY(pb_reserve(ctx, &ctx->Gbuf, &ctx->G_cap, (size_t)m * m));
     // the TSQR mode has no Gram to overlap with the upload: plain copy, then the device path
-    int rc = mode == PB_POD_TSQR ? 1 : gram_host_chunked(ctx, U_host, n_h, n_st, ldu_host, U_dev, ctx->Gbuf);
+    int rc = (mode == PB_POD_TSQR || mode == PB_POD_TSQR_FULL) ? 1 : gram_host_chunked(ctx, U_host, n_h, n_st, ldu_host, U_dev, ctx->Gbuf);
     if (rc == 1) {        // small or wide, or the TSQR mode: upload (staged when pageable), then the device path
         PB_TRY(upload_whole(ctx, U_dev, U_host, n_h, n_st, ldu_host));
         return pb_pod(ctx, U_dev, n_h, n_st, n_st, eps, n_L_in, mode, n_L);

@@ -70,6 +70,7 @@ struct pb_ctx {
     std::vector<double> sigma_host;  // singular values of the last decomposition
     double* qr_W = nullptr; double* qr_scr = nullptr; double* qr_scr2 = nullptr;   // TSQR mode (qr.cu)
     double* qr_stack = nullptr; size_t qr_stack_cap = 0;
+    int64_t qr_panels = 0; double qr_flops = 0.; int64_t qr_f_rows = 0;   // last factorisation: panels run, Householder flops, factor rows
     size_t qr_W_cap = 0, qr_scr_cap = 0, qr_scr2_cap = 0;
     // per-call knobs of the next eigensolve (set by the POD orchestration, consumed and cleared by eig.cu)
     bool eig_trust_single_pair = false;   // skip the confirming sweep of a single-pair problem (a second pass follows)
@@ -128,8 +129,12 @@ int pbi_jacobi_factor(pb_ctx* ctx, double* At, int64_t m, int r, const double* s
                       int* perm_dev, int* sweeps_out, int max_sweeps);
 // TSQR mode (qr.cu): R factor of a tall matrix; rank-revealing pivoted QR of the small factor held in At
 int pbi_qr_r(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, double* R, int64_t ldr, int64_t rows_out);
+// rr: rank-revealing (block pivoting + early termination): *f_rows <= m dense rows in the input's column order
+int pbi_qr_factor(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, double* R, int64_t ldr, int64_t rows_out,
+                  bool rr, int64_t* f_rows);
 int pbi_qr_load_factor(pb_ctx* ctx, const double* R, int64_t ldr, int64_t m, double* At, int64_t ldm, int64_t rows_total);
-int pbi_qrcp_factor(pb_ctx* ctx, double* At, int64_t m, int64_t ldm, int64_t rows_total, double tol_rel, int* r_out);
+int pbi_qr_load_dense(pb_ctx* ctx, const double* F, int64_t ldf, int64_t f_rows, int64_t m, double* At, int64_t ldm, int64_t rows_total);
+int pbi_qrcp_factor(pb_ctx* ctx, double* At, int64_t m, int64_t nrows, int64_t ldm, int64_t rows_total, double tol_rel, int* r_out);
 // Y (rows x k, ldy) += A (rows x m, lda) B (m x k, ldb), in place
 int pbi_gemm_nn_sub(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m, const double* B, int64_t ldb,
                     int64_t k, double* Y, int64_t ldy);

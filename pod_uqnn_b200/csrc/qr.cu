@@ -410,14 +410,16 @@ __global__ void __launch_bounds__(QT, 1) qr_panel_kernel(QrPanelArgs a) {
 // (zeros above, ones on the diagonal): the panel columns of W then ARE the block Y, so that [Y^T Y | Y^T C] is one TN
 // product over W[:, J:] and the update reads Y in place -- no copy of Y, no separate Y^T Y launch.
 __global__ void qr_save_r_make_y_kernel(double* __restrict__ W, int64_t ldw, int J, int nbo, int64_t m,
-                                        double* __restrict__ R, int64_t ldr) {
+                                        double* __restrict__ R, int64_t ldr, const int* __restrict__ colperm) {
+    // colperm (rank-revealing mode): position d of the working copy holds column colperm[d] of the input
     const int64_t total = (int64_t)(J + nbo) * nbo;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = idx / nbo; const int a = (int)(idx % nbo);
         const int64_t d = (int64_t)J + a;
         if (r > d) continue;
         double* p = W + r * ldw + d;
-        if (r < m && d < m) R[r * ldr + d] = *p;
+        const int64_t dc = colperm ? colperm[d] : d;
+        if (r < m && dc < m) R[r * ldr + dc] = *p;
         *p = (r == d) ? 1. : 0.;
     }
 }
@@ -501,10 +503,197 @@ __global__ void qr_extract_r_kernel(const double* __restrict__ W, int64_t ldw, i
 }
 
 // ---------------------------------------------------------------------------
+// Rank-revealing mode of the big QR: block column pivoting + early termination.
+//
+// POD snapshot matrices have low numerical rank (C2: 36 of 1000 columns at m eps, C5: ~190 of 4096), and the modes
+// need only a factor F with F^T F = A^T A to working accuracy.  After k panels the working copy holds
+// Q^T A P = [R11 R12; 0 S]: once every column of the residual S is below tol * (largest column norm of A), S is at
+// the level of the QR's own rounding error and is dropped -- F = [R11 R12] P^T has 64 k rows instead of m, and the
+// remaining (m/64 - k) panels (almost all of the 2 n m^2 flops) are never run.  Before each panel the columns with
+// the largest residual norms are swapped into the panel position (block pivoting: it only has to expose the rank
+// early, any column order gives a valid QR), so an unlucky column order cannot delay the stop.  Residual norms are
+// downdated with the new R rows after each panel (LAPACK dgeqp3's scheme); downdated squares cannot resolve anything
+// below eps * the original, so the stop decision is taken only on exactly recomputed norms (one read pass over the
+// trailing matrix, run when the downdated maximum falls below 1e-6 of the start).  A full-rank matrix never triggers
+// the recomputation and costs the same as the plain blocked QR.
+// ---------------------------------------------------------------------------
+constexpr int CN_COLS = 256;        // columns per CTA of the norm kernel (128 threads x double2)
+
+// part[rb][c] = sum over the rows of block rb (within [r0, rows)) of W[r][c0 + c]^2
+__global__ void __launch_bounds__(128) qr_colnorm_part_kernel(const double* __restrict__ W, int64_t ldw, int64_t r0,
+                                                              int64_t rows, int c0, int ncols, double* __restrict__ part,
+                                                              int64_t ldp) {
+    const int c = blockIdx.x * CN_COLS + 2 * threadIdx.x;
+    if (c >= ncols) return;
+    const int nrb = gridDim.y, rb = blockIdx.y;
+    const int64_t per = (rows - r0 + nrb - 1) / nrb;
+    const int64_t lo = r0 + (int64_t)rb * per, hi = lo + per < rows ? lo + per : rows;
+    const double* p = W + (int64_t)c0 + c;
+    double s0 = 0., s1 = 0.;
+    int64_t r = lo;
+    for (; r + 4 <= hi; r += 4) {
+        const double2 v0 = *reinterpret_cast<const double2*>(p + r * ldw);
+        const double2 v1 = *reinterpret_cast<const double2*>(p + (r + 1) * ldw);
+        const double2 v2 = *reinterpret_cast<const double2*>(p + (r + 2) * ldw);
+        const double2 v3 = *reinterpret_cast<const double2*>(p + (r + 3) * ldw);
+        s0 += v0.x * v0.x; s1 += v0.y * v0.y; s0 += v1.x * v1.x; s1 += v1.y * v1.y;
+        s0 += v2.x * v2.x; s1 += v2.y * v2.y; s0 += v3.x * v3.x; s1 += v3.y * v3.y;
+    }
+    for (; r < hi; ++r) { const double2 v = *reinterpret_cast<const double2*>(p + r * ldw); s0 += v.x * v.x; s1 += v.y * v.y; }
+    part[(int64_t)rb * ldp + c] = s0; part[(int64_t)rb * ldp + c + 1] = s1;
+}
+__global__ void qr_colnorm_reduce_kernel(const double* __restrict__ part, int nrb, int64_t ldp, int ncols, double* __restrict__ cn2) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    double s = 0.;
+    for (int rb = 0; rb < nrb; ++rb) s += part[(int64_t)rb * ldp + c];       // fixed order
+    cn2[c] = s;
+}
+
+// cn2[j] -= sum_{k in [J, J + nbo)} W[k][j]^2 for the trailing columns j >= J + nbo (rows J .. J + nbo - 1 are final R rows)
+__global__ void qr_downdate_kernel(const double* __restrict__ W, int64_t ldw, int J, int nbo, int mp, double* __restrict__ cn2) {
+    const int j = J + nbo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= mp) return;
+    double s = 0.;
+    for (int k = 0; k < nbo; ++k) { const double v = W[(int64_t)(J + k) * ldw + j]; s += v * v; }
+    const double d = cn2[j] - s;
+    cn2[j] = d > 0. ? d : 0.;
+}
+
+struct QrPivArgs {
+    double* cn2; int* colperm; int J, nbo, mp;
+    double tol2;            // stop when the largest exact residual norm^2 <= tol2 * first
+    double* first;          // device scalar: largest column norm^2 of the input (written at J == 0)
+    int exact;              // cn2[J..) was recomputed exactly just now
+    int pivot;              // block pivoting on / off
+    int* out;               // [0] stop, [1] exact norms wanted, [2] number of swaps; [4 + 2 s], [5 + 2 s]: positions of swap s
+};
+constexpr int PIVT = 1024;
+
+// One CTA.  Decides stop / recompute / the column swaps of the next panel.
+// Choice of the nbo panel columns: the candidates are the trailing columns whose residual norm is within 4x of the
+// largest one; nbo of them are taken EVENLY SPREAD over their positions.  Taking simply the nbo largest norms fails on
+// smooth snapshot sets (neighbouring columns -- consecutive time steps, neighbouring DCT sample points -- have
+// neighbouring norms and are nearly parallel, so a panel made of them exposes few new directions: measured 27 panels
+// instead of 4 on the 250 000 x 4096 DCT matrix).  Fewer than nbo candidates: the nbo largest norms.  Columns that are
+// already in the panel window and wanted stay; the others trade places with the wanted columns outside, in order.
+__global__ void __launch_bounds__(PIVT) qr_pivot_kernel(QrPivArgs a) {
+    extern __shared__ __align__(16) double pv[];        // [n] residual norms^2 of the trailing columns
+    __shared__ double redv[PIVT / 32];
+    __shared__ int scan[PIVT / 32];
+    __shared__ int wlist[QNB], cand[QNB];
+    __shared__ double t_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = a.mp - a.J, nbo = a.nbo;
+    double mx = 0.;
+    for (int j = tid; j < n; j += PIVT) { const double v = a.cn2[a.J + j]; pv[j] = v; mx = v > mx ? v : mx; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, mx, o); mx = t > mx ? t : mx; }
+    if (lane == 0) redv[warp] = mx;
+    __syncthreads();
+    mx = 0.;
+    for (int w = 0; w < PIVT / 32; ++w) mx = redv[w] > mx ? redv[w] : mx;
+    double first = mx;
+    if (a.J == 0) { if (tid == 0) *a.first = mx; } else first = *a.first;
+    if (tid == 0) { a.out[0] = 0; a.out[1] = 0; a.out[2] = 0; }
+    if (a.exact) { if (!(mx > a.tol2 * first)) { if (tid == 0) a.out[0] = 1; return; } }      // (also a zero matrix)
+    else if (!(mx >= 1e-9 * first)) { if (tid == 0) a.out[1] = 1; return; }              // too small for downdated values
+    if (!a.pivot || n <= nbo) return;
+    if (tid < QNB) { wlist[tid] = -1; cand[tid] = -1; }
+    // ---- candidates: within 4x of the largest norm (16x in the squares) -- widened by further factors of 4 while there
+    // are fewer candidates than panel columns (after a panel the residual is largest BETWEEN the columns just taken, in
+    // narrow clusters; a panel of cluster neighbours would again expose few directions); ordinal of each by position
+    const int per = (n + PIVT - 1) / PIVT, j0 = tid * per, j1 = j0 + per < n ? j0 + per : n;
+    double thr = mx;
+    int cnt = 0, inc = 0, base = 0, nS = 0;
+    for (int widen = 0; widen < 8 && nS < nbo; ++widen) {
+        thr *= 0.0625;
+        cnt = 0;
+        for (int j = j0; j < j1; ++j) cnt += pv[j] >= thr ? 1 : 0;
+        inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        __syncthreads();
+        if (lane == 31) scan[warp] = inc;
+        __syncthreads();
+        base = 0; nS = 0;
+        for (int w = 0; w < PIVT / 32; ++w) { if (w < warp) base += scan[w]; nS += scan[w]; }
+    }
+    if (nS >= nbo) {
+        int q = base + inc - cnt;                       // ordinal of my first candidate
+        for (int j = j0; j < j1; ++j) {
+            if (pv[j] >= thr) {
+                const int w0 = (int)(((long long)q * nbo) / nS), w1 = (int)(((long long)(q + 1) * nbo) / nS);
+                if (w1 != w0) wlist[w0] = j;            // the w0-th wanted column
+                ++q;
+            }
+        }
+    } else {
+        // ---- fewer candidates than panel columns: the nbo largest norms (rank by counting; ties by position)
+        for (int j = tid; j < n; j += PIVT) {
+            const double vj = pv[j];
+            int ra = 0;
+            for (int k = 0; k < n; ++k) { const double vk = pv[k]; ra += (vk > vj || (vk == vj && k < j)) ? 1 : 0; }
+            if (ra < nbo) wlist[ra] = j;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // window positions that are not wanted <-> wanted columns outside the window, both in ascending order
+        bool inwin[QNB];
+        for (int w = 0; w < nbo; ++w) inwin[w] = false;
+        int nc = 0;
+        // wlist is ascending in the spread branch; in the rank branch sort the outside ones by position (<= 64 entries)
+        for (int i = 0; i < nbo; ++i) {
+            const int j = wlist[i];
+            if (j < 0) continue;
+            if (j < nbo) inwin[j] = true;
+            else { int k = nc++; while (k > 0 && cand[k - 1] > j) { cand[k] = cand[k - 1]; --k; } cand[k] = j; }
+        }
+        int ns = 0, ci = 0;
+        for (int w = 0; w < nbo && ci < nc; ++w) {
+            if (inwin[w]) continue;
+            const int c = cand[ci++];
+            a.out[4 + 2 * ns] = a.J + w; a.out[5 + 2 * ns] = a.J + c; ++ns;
+            const double tv = a.cn2[a.J + w]; a.cn2[a.J + w] = a.cn2[a.J + c]; a.cn2[a.J + c] = tv;
+            const int tp = a.colperm[a.J + w]; a.colperm[a.J + w] = a.colperm[a.J + c]; a.colperm[a.J + c] = tp;
+        }
+        a.out[2] = ns;
+    }
+}
+
+// W[r][a_s] <-> W[r][b_s] for every row and every swap of the list (disjoint pairs)
+__global__ void qr_swap_cols_kernel(double* __restrict__ W, int64_t ldw, int64_t rows, const int* __restrict__ sw, int ns) {
+    const int64_t total = rows * ns;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx / ns; const int s = (int)(idx % ns);
+        double* pa = W + r * ldw + sw[2 * s]; double* pb = W + r * ldw + sw[2 * s + 1];
+        const double t = *pa; *pa = *pb; *pb = t;
+    }
+}
+
+__global__ void qr_iota_kernel(int* __restrict__ p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+// rows [0, K) of the columns that were never factored (positions >= K): R12, back in the input's column order
+__global__ void qr_gather_tail_kernel(const double* __restrict__ W, int64_t ldw, int K, int mp, int64_t m,
+                                      const int* __restrict__ colperm, double* __restrict__ R, int64_t ldr) {
+    const int nt = mp - K;
+    const int64_t total = (int64_t)K * nt;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = idx / nt; const int j = K + (int)(idx % nt);
+        const int64_t jc = colperm ? colperm[j] : j;
+        if (i < m && jc < m) R[i * ldr + jc] = W[i * ldw + j];
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Householder QR with column pivoting of the small factor, columns never moved
 // ---------------------------------------------------------------------------
 struct QrcpArgs {
-    double* At; int64_t ldm; int m; int max_steps; double tol2;
+    double* At; int64_t ldm; int m; int nrows; int max_steps; double tol2;   // nrows: rows of the factor that can be non-zero
     double* cand_val; int* cand_idx;      // [2][G]
     int* done_step;                       // [ldm] step at which a column was eliminated (-1: not yet)
     double* diagval;                      // [m] beta of each step
@@ -547,12 +736,12 @@ __device__ __forceinline__ void block_argmax(double& v, int& i, double* rv, int*
 __global__ void __launch_bounds__(QT, 1) qrcp_kernel(QrcpArgs a) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) double qsm[];
-    const int m = a.m; const int64_t ldm = a.ldm;
+    const int m = a.m, nr = a.nrows; const int64_t ldm = a.ldm;
     const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
     const int ngroups = (int)(ldm / 8);
     const int mg = b < ngroups ? (ngroups - b + G - 1) / G : 0;      // my column groups: b, b + G, ...
-    double* xs = qsm;                                   // [m] the pivot column below the diagonal row
-    double* cn2 = qsm + (m + 7) / 8 * 8;                // [mg * 8] squared norms of my columns below the current row
+    double* xs = qsm;                                   // [nr] the pivot column below the diagonal row
+    double* cn2 = qsm + (nr + 7) / 8 * 8;                // [mg * 8] squared norms of my columns below the current row
     __shared__ int active[64 * 8];                      // my columns still to be eliminated (mg <= 64)
     __shared__ double red[QT / 32][8];
     __shared__ double out8[8];
@@ -568,7 +757,7 @@ __global__ void __launch_bounds__(QT, 1) qrcp_kernel(QrcpArgs a) {
         double acc[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) acc[q] = 0.;
-        for (int r = tid; r < m; r += QT) {
+        for (int r = tid; r < nr; r += QT) {
             const double2* p = reinterpret_cast<const double2*>(At + (int64_t)r * ldm + k0);
 #pragma unroll
             for (int q = 0; q < 4; ++q) { double2 v = p[q]; acc[2 * q] += v.x * v.x; acc[2 * q + 1] += v.y * v.y; }
@@ -610,7 +799,7 @@ __global__ void __launch_bounds__(QT, 1) qrcp_kernel(QrcpArgs a) {
         if (!(pv > a.tol2 * first) || !(pv > 0.)) break;            // uniform over the grid
 
         // ---- reflector from column p, rows c..m-1
-        const int len = m - c;
+        const int len = nr - c;
         // column p was written by its owner CTA before the grid barrier above (grid.sync orders those writes before these
         // reads).  Plain loads: forcing them through L2 (ld.cg) made the kernel 3x slower at m = 4096 (214 vs 75 ms)
         for (int r = tid; r < len; r += QT) xs[r] = At[(int64_t)(c + r) * ldm + p];
@@ -647,7 +836,7 @@ __global__ void __launch_bounds__(QT, 1) qrcp_kernel(QrcpArgs a) {
             double acc[QIB];
 #pragma unroll
             for (int q = 0; q < QIB; ++q) acc[q] = 0.;
-            for (int r = c + 1 + tid; r < m; r += QT) {
+            for (int r = c + 1 + tid; r < nr; r += QT) {
                 const double xr = xs[r - c];
                 const double2* pa = reinterpret_cast<const double2*>(At + (int64_t)r * ldm + ka);
                 const double2* pb = reinterpret_cast<const double2*>(At + (int64_t)r * ldm + kb);
@@ -675,7 +864,7 @@ __global__ void __launch_bounds__(QT, 1) qrcp_kernel(QrcpArgs a) {
 #pragma unroll
             for (int q = 0; q < QIB; ++q) acc[q] = 0.;
             if (am == 0xffff) {                                        // all 16 columns active: 16-byte accesses
-                for (int r = c + 1 + tid; r < m; r += QT) {
+                for (int r = c + 1 + tid; r < nr; r += QT) {
                     const double tv = tau * (xs[r - c] * scale);
                     double2* pa = reinterpret_cast<double2*>(At + (int64_t)r * ldm + ka);
                     double2* pb = reinterpret_cast<double2*>(At + (int64_t)r * ldm + kb);
@@ -690,7 +879,7 @@ __global__ void __launch_bounds__(QT, 1) qrcp_kernel(QrcpArgs a) {
                     }
                 }
             } else {
-                for (int r = c + 1 + tid; r < m; r += QT) {
+                for (int r = c + 1 + tid; r < nr; r += QT) {
                     const double tv = tau * (xs[r - c] * scale);
                     double* pa = At + (int64_t)r * ldm + ka;
                     double* pb = At + (int64_t)r * ldm + kb;
@@ -741,16 +930,22 @@ int pbi_gemm_nn_sub(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int
 
 namespace {
 constexpr int64_t RS_MAX = 1400;                 // rows of an inner panel staged per CTA (1400 x 18 doubles = 197 KB)
-int qr_leaf(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, double* R, int64_t ldr, int64_t rows_out);
+int qr_leaf(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, double* R, int64_t ldr, int64_t rows_out,
+            bool rr, int64_t* f_rows);
 }
 
-// R (m x m upper triangular, ld ldr, rows_out >= m rows written: zero below the triangle) of A (rows x m, lda).
+// Factor F of A (rows x m, lda): F^T F = A^T A to working accuracy, written to R (ld ldr, rows_out >= m rows
+// available, all of them written -- zero below the factor).
+//   rr == false: F = the m x m upper-triangular R of the blocked Householder QR (LAPACK dgeqrf's R up to row signs).
+//   rr == true:  rank-revealing (block pivoting + early termination, see above): *f_rows <= ceil64(m) rows, dense, in the
+//                input's column order.
 // Slabs whose working copy would exceed 16 GiB are cut into equal row blocks of at most sm_count x 1400 rows -- TSQR
-// leaves inside the GPU: R_i = qr(A_i), then the QR of the stacked factors.  The working copy is then one leaf, not the
+// leaves inside the GPU: F_i = qr(A_i), then the QR of the stacked factors.  The working copy is then one leaf, not the
 // whole slab (6.8 GB instead of 41 GB at C5), every leaf runs the shared-memory panel path, and the stack adds
 // n_leaves m / rows of the flops (2 % at 1.25 M x 4096).  Measured time-neutral at 1.25 M x 4096 (2.20 vs 2.24 s) and
 // 4 % slower at 250 000 x 4096 (two leaves), hence the memory criterion.
-int pbi_qr_r(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, double* R, int64_t ldr, int64_t rows_out) {
+int pbi_qr_factor(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, double* R, int64_t ldr, int64_t rows_out,
+                  bool rr, int64_t* f_rows) {
     if (rows <= 0 || m <= 0 || lda < m || ldr < m || rows_out < m) PB_FAIL(ctx, PB_ERR_SHAPE, "tsqr: bad shape");
     if (m > 8192) PB_FAIL(ctx, PB_ERR_SHAPE, "tsqr: %lld columns exceed 8192", (long long)m);
     const char* le = getenv("PB_QR_LEAVES");            // 0: never, 1 (default): by the memory criterion, 2: whenever possible
@@ -758,40 +953,112 @@ int pbi_qr_r(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda,
     const int64_t leaf_max = (int64_t)ctx->sm_count * RS_MAX;
     const int64_t n_leaves = (rows + leaf_max - 1) / leaf_max;
     const bool big = (double)rows * (double)((m + QIB - 1) / QIB * QIB) * 8. > 16. * 1073741824.;
-    if (!(leaves_env == 2 || (leaves_env == 1 && big)) || n_leaves < 2 || rows < 4 * m || n_leaves * m > leaf_max)
-        return qr_leaf(ctx, A, rows, m, lda, R, ldr, rows_out);
-    PB_TRY(pb_reserve(ctx, &ctx->qr_stack, &ctx->qr_stack_cap, (size_t)n_leaves * m * m));
+    int64_t fr = m;
+    if (!(leaves_env == 2 || (leaves_env == 1 && big)) || n_leaves < 2 || rows < 4 * m || n_leaves * m > leaf_max) {
+        PB_TRY(qr_leaf(ctx, A, rows, m, lda, R, ldr, rows_out, rr, &fr));
+        if (f_rows) *f_rows = fr;
+        return PB_OK;
+    }
+    // every leaf zero-fills m rows from its offset, so the stack needs one factor of slack
+    PB_TRY(pb_reserve(ctx, &ctx->qr_stack, &ctx->qr_stack_cap, (size_t)(n_leaves + 1) * m * m));
     const int64_t per = (rows + n_leaves - 1) / n_leaves;
+    int64_t off = 0;
     for (int64_t i = 0; i < n_leaves; ++i) {
         const int64_t r0 = i * per, nr = std::min(per, rows - r0);
-        PB_TRY(qr_leaf(ctx, A + r0 * lda, nr, m, lda, ctx->qr_stack + (size_t)i * m * m, m, m));
+        PB_TRY(qr_leaf(ctx, A + r0 * lda, nr, m, lda, ctx->qr_stack + (size_t)off * m, m, m, rr, &fr));
+        off += std::min(fr, m);
     }
-    return qr_leaf(ctx, ctx->qr_stack, n_leaves * m, m, m, R, ldr, rows_out);
+    PB_TRY(qr_leaf(ctx, ctx->qr_stack, off, m, m, R, ldr, rows_out, rr, &fr));
+    if (f_rows) *f_rows = fr;
+    return PB_OK;
+}
+
+int pbi_qr_r(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, double* R, int64_t ldr, int64_t rows_out) {
+    return pbi_qr_factor(ctx, A, rows, m, lda, R, ldr, rows_out, false, nullptr);
 }
 
 namespace {
-int qr_leaf(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, double* R, int64_t ldr, int64_t rows_out) {
+// exact residual norms^2 of the columns at positions >= J over the rows >= J
+int qr_exact_norms(pb_ctx* ctx, const double* W, int64_t ldw, int64_t rowsW, int J, int mp, double* part, double* cn2) {
+    const int ncols = mp - J;
+    const int ctile = (ncols + CN_COLS - 1) / CN_COLS;
+    int nrb = std::max(1, std::min<int>((ctx->sm_count * 8 + ctile - 1) / ctile, (int)((rowsW - J + 63) / 64)));
+    qr_colnorm_part_kernel<<<dim3(ctile, nrb), 128, 0, ctx->stream>>>(W, ldw, J, rowsW, J, ncols, part, mp);
+    PB_LAUNCH_CHECK(ctx);
+    qr_colnorm_reduce_kernel<<<(ncols + 255) / 256, 256, 0, ctx->stream>>>(part, nrb, mp, ncols, cn2 + J);
+    PB_LAUNCH_CHECK(ctx);
+    return PB_OK;
+}
+
+int qr_leaf(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, double* R, int64_t ldr, int64_t rows_out,
+            bool rr, int64_t* f_rows) {
     const int64_t mp = (m + QIB - 1) / QIB * QIB;            // padded column count (zero columns reflect to nothing)
     const int64_t ldw = mp;
     const int64_t rowsW = std::max(rows, mp);
     PB_TRY(pb_reserve(ctx, &ctx->qr_W, &ctx->qr_W_cap, (size_t)rowsW * ldw));
     const int Gmax = ctx->sm_count;
     // scratch: tau [mp] | part [2*G*16] | diag [32] | zpart [G*ZE] | zfin [ZE] | [S | Z] [64*mp] | T^T [64*64]
-    const size_t n_scr = (size_t)mp + 2 * (size_t)Gmax * QIB + 2 * QIB + (size_t)Gmax * ZE + ZE + (size_t)QNB * mp + QNB * QNB;
+    //          | rank-revealing mode: cn2 [mp] | first [8] | norm partials [8 sm_count x mp] | colperm (ints) [mp]
+    const int nrb_max = Gmax * 8;
+    const size_t n_scr = (size_t)mp + 2 * (size_t)Gmax * QIB + 2 * QIB + (size_t)Gmax * ZE + ZE + (size_t)QNB * mp + QNB * QNB
+                         + (rr ? (size_t)mp + 8 + (size_t)nrb_max * mp + (size_t)(mp + 1) / 2 + 8 : 0);
     PB_TRY(pb_reserve(ctx, &ctx->qr_scr, &ctx->qr_scr_cap, n_scr));
     double* tau = ctx->qr_scr; double* part = tau + mp; double* diag = part + 2 * (size_t)Gmax * QIB;
     double* zpart = diag + 2 * QIB; double* zfin = zpart + (size_t)Gmax * ZE; double* Zb = zfin + ZE;
     double* Tt = Zb + (size_t)QNB * mp;
+    double* cn2 = Tt + QNB * QNB; double* first = cn2 + mp; double* npart = first + 8;
+    int* colperm = rr ? reinterpret_cast<int*>(npart + (size_t)nrb_max * mp) : nullptr;
+    int* piv_out = ctx->d_int + 64; int* piv_host = ctx->h_int + 64;        // [0] stop [1] want exact [2] swaps [4..] pairs
     double* W = ctx->qr_W;
     PB_CUDA(ctx, cudaMemset2DAsync(R, ldr * sizeof(double), 0, m * sizeof(double), rows_out, ctx->stream));
     const int cp_grid = ctx->sm_count * 8;
     qr_copy_pad_kernel<<<cp_grid, 256, 0, ctx->stream>>>(A, lda, rows, m, W, ldw, rowsW);
     PB_LAUNCH_CHECK(ctx);
     static const int stage_env = getenv("PB_QR_STAGE") ? atoi(getenv("PB_QR_STAGE")) : 1;
+    static const int pivot_env = getenv("PB_QR_PIVOT") ? atoi(getenv("PB_QR_PIVOT")) : 1;
     const size_t tt_smem = sizeof(double) * 2 * QNB * (QNB + 1);
     PB_CUDA(ctx, cudaFuncSetAttribute(qr_tt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tt_smem));
+    if (rr) {
+        qr_iota_kernel<<<(unsigned)((mp + 255) / 256), 256, 0, ctx->stream>>>(colperm, (int)mp);
+        PB_LAUNCH_CHECK(ctx);
+        PB_CUDA(ctx, cudaFuncSetAttribute(qr_pivot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * mp)));
+    }
+    int64_t K = mp;                                                   // rows of the factor (panels actually run)
+    int panels = 0;
     for (int64_t J = 0; J < mp; J += QNB) {
         const int nbo = (int)std::min<int64_t>(QNB, mp - J);
+        if (rr) {
+            // residual must fall below the rounding noise the panels run so far have put into the kept rows
+            const double tol = 16. * DBL_EPSILON * sqrt((double)std::max(1, panels));
+            int exact = 0;
+            if (J == 0) { PB_TRY(qr_exact_norms(ctx, W, ldw, rowsW, 0, (int)mp, npart, cn2)); exact = 1; }
+            for (;;) {
+                QrPivArgs pa{cn2, colperm, (int)J, nbo, (int)mp, tol * tol, first, exact, pivot_env, piv_out};
+                qr_pivot_kernel<<<1, PIVT, sizeof(double) * (mp - J), ctx->stream>>>(pa);
+                PB_LAUNCH_CHECK(ctx);
+                PB_CUDA(ctx, cudaMemcpyAsync(piv_host, piv_out, sizeof(int) * (4 + 2 * QNB), cudaMemcpyDeviceToHost, ctx->stream));
+                PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                if (piv_host[1] && !exact) { PB_TRY(qr_exact_norms(ctx, W, ldw, rowsW, (int)J, (int)mp, npart, cn2)); exact = 1; continue; }
+                break;
+            }
+            static const int dbg = getenv("PB_QR_DEBUG") ? atoi(getenv("PB_QR_DEBUG")) : 0;
+            if (dbg) {
+                double hv[2] = {0., 0.};
+                std::vector<double> hc((size_t)(mp - J));
+                cudaMemcpy(hv, first, sizeof(double), cudaMemcpyDeviceToHost);
+                cudaMemcpy(hc.data(), cn2 + J, sizeof(double) * (mp - J), cudaMemcpyDeviceToHost);
+                double mxv = 0.; for (double v : hc) mxv = std::max(mxv, v);
+                fprintf(stderr, "[qr] rows %lld J %lld exact %d max/first %.3e (sqrt %.3e) tol %.3e stop %d swaps %d\n", (long long)rows,
+                        (long long)J, exact, mxv / hv[0], sqrt(mxv / hv[0]), tol, piv_host[0], piv_host[2]);
+            }
+            if (piv_host[0]) { K = J; break; }
+            if (piv_host[2] > 0) {
+                const int ns = piv_host[2];
+                qr_swap_cols_kernel<<<(unsigned)std::min<int64_t>(cp_grid * 4, (rowsW * ns + 255) / 256), 256, 0, ctx->stream>>>(
+                    W, ldw, rowsW, piv_out + 4, ns);
+                PB_LAUNCH_CHECK(ctx);
+            }
+        }
         int grid = std::max(1, std::min<int>((int)((rowsW - J + 127) / 128), ctx->sm_count));
         int64_t rpc = (rowsW - J + grid - 1) / grid; rpc = (rpc + 7) / 8 * 8;       // as the kernel computes it
         const int use_smem = (stage_env && rpc <= RS_MAX) ? 1 : 0;
@@ -802,8 +1069,13 @@ int qr_leaf(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, 
         void* args[] = {&pa};
         PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)qr_panel_kernel, dim3(grid), dim3(QT), args, smem, ctx->stream));
         ctx->launches++;
+        ++panels;
+        {   // Householder flop count of this panel (factorisation + trailing update), over the rows still active
+            const double ra = (double)std::max<int64_t>(0, rows - J), nt = (double)(mp - J - nbo);
+            ctx->qr_flops += 2. * ra * nbo * nbo + 4. * ra * nbo * nt;
+        }
         qr_save_r_make_y_kernel<<<(unsigned)std::min<int64_t>(cp_grid, ((J + nbo) * nbo + 255) / 256), 256, 0, ctx->stream>>>(
-            W, ldw, (int)J, nbo, m, R, ldr);
+            W, ldw, (int)J, nbo, m, R, ldr, colperm);
         PB_LAUNCH_CHECK(ctx);
         const int64_t ntrail = mp - J - nbo;
         if (ntrail <= 0) break;
@@ -815,7 +1087,18 @@ int qr_leaf(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, 
         qr_applyt_kernel<<<(unsigned)((ntrail + QAT - 1) / QAT), QT, 0, ctx->stream>>>(Zb + nbo, ldz, ntrail, Tt, nbo);   // -X = -T^T Z
         PB_LAUNCH_CHECK(ctx);
         PB_TRY(pbi_gemm_nn_sub(ctx, Y, ldw, rowsW, nbo, Zb + nbo, ldz, ntrail, W + J + nbo, ldw)); // C += Y (-X)
+        if (rr) {
+            qr_downdate_kernel<<<(unsigned)((ntrail + 127) / 128), 128, 0, ctx->stream>>>(W, ldw, (int)J, nbo, (int)mp, cn2);
+            PB_LAUNCH_CHECK(ctx);
+        }
     }
+    if (rr && K < mp && K > 0) {      // stopped early: the rows of R12 that belong to the columns never factored
+        qr_gather_tail_kernel<<<(unsigned)std::min<int64_t>(cp_grid, (K * (mp - K) + 255) / 256), 256, 0, ctx->stream>>>(
+            W, ldw, (int)K, (int)mp, m, colperm, R, ldr);
+        PB_LAUNCH_CHECK(ctx);
+    }
+    ctx->qr_panels += panels;
+    if (f_rows) *f_rows = std::min<int64_t>(K, m);
     return PB_OK;
 }
 }  // namespace
@@ -826,17 +1109,25 @@ int pbi_qr_load_factor(pb_ctx* ctx, const double* R, int64_t ldr, int64_t m, dou
     PB_LAUNCH_CHECK(ctx);
     return PB_OK;
 }
+// At (rows_total x ldm, zero padded) = the dense factor F (f_rows x m, ld ldf)
+int pbi_qr_load_dense(pb_ctx* ctx, const double* F, int64_t ldf, int64_t f_rows, int64_t m, double* At, int64_t ldm, int64_t rows_total) {
+    qr_copy_pad_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(F, ldf, f_rows, m, At, ldm, rows_total);
+    PB_LAUNCH_CHECK(ctx);
+    return PB_OK;
+}
 
-// Rank-revealing QR with column pivoting of the factor held in At (m rows x ldm, rows = vectors after the call).
+// Rank-revealing QR with column pivoting of the factor held in At (m rows x ldm, rows = vectors after the call; only the
+// first nrows rows can be non-zero -- nrows = m for a triangular R, fewer for a truncated factor).
 // tol_rel: stop when the largest remaining column norm <= tol_rel * the first pivot norm (0: all m steps).
 // The number of vectors r is left in ctx->d_int[0] / returned.
-int pbi_qrcp_factor(pb_ctx* ctx, double* At, int64_t m, int64_t ldm, int64_t rows_total, double tol_rel, int* r_out) {
+int pbi_qrcp_factor(pb_ctx* ctx, double* At, int64_t m, int64_t nrows, int64_t ldm, int64_t rows_total, double tol_rel, int* r_out) {
+    if (nrows <= 0 || nrows > m) nrows = m;
     const int Gmax = ctx->sm_count;
     const int ngroups = (int)(ldm / 8);
     int grid = std::min(Gmax, ngroups);
     const int mg_max = (ngroups + grid - 1) / grid;
     if (mg_max > 64) PB_FAIL(ctx, PB_ERR_SHAPE, "tsqr: %lld columns exceed the pivoted QR's limit", (long long)m);
-    const size_t smem = sizeof(double) * ((size_t)(m + 7) / 8 * 8 + (size_t)mg_max * 8);
+    const size_t smem = sizeof(double) * ((size_t)(nrows + 7) / 8 * 8 + (size_t)mg_max * 8);
     PB_CUDA(ctx, cudaFuncSetAttribute(qrcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PB_TRY(coop_grid(ctx, (const void*)qrcp_kernel, smem, grid, &grid));
     // scratch: cand_val [2*G] | diagval [m] | then ints: cand_idx [2*G] | done_step [ldm]
@@ -845,7 +1136,7 @@ int pbi_qrcp_factor(pb_ctx* ctx, double* At, int64_t m, int64_t ldm, int64_t row
     PB_TRY(pb_reserve(ctx, &ctx->qr_scr2, &ctx->qr_scr2_cap, n_dbl + (n_int + 1) / 2));
     double* cand_val = ctx->qr_scr2; double* diagval = cand_val + 2 * (size_t)Gmax;
     int* cand_idx = reinterpret_cast<int*>(diagval + m + 8); int* done_step = cand_idx + 2 * (size_t)Gmax;
-    QrcpArgs qa{At, ldm, (int)m, (int)m, tol_rel * tol_rel, cand_val, cand_idx, done_step, diagval, ctx->d_int + 0};
+    QrcpArgs qa{At, ldm, (int)m, (int)nrows, (int)nrows, tol_rel * tol_rel, cand_val, cand_idx, done_step, diagval, ctx->d_int + 0};
     void* args[] = {&qa};
     PB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)qrcp_kernel, dim3(grid), dim3(QT), args, smem, ctx->stream));
     ctx->launches++;

@@ -44,15 +44,38 @@ def _all_gather_stack(backend, R, group=None):
     return backend.all_gather_rows(R, group)
 
 
+def _max_over_ranks(backend, value, group=None):
+    """max of a host integer over the ranks (the row count of the truncated factors)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return int(value)
+    dev = getattr(backend, "dev", None) if dist.get_backend(group) == "nccl" else None
+    t = torch.tensor([int(value)], dtype=torch.int64, device=dev or "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return int(t.item())
+
+
 def pod_sharded_tsqr(backend, A_local, eps=0., n_L=0, group=None):
-    """TSQR mode: one leaf per rank.  R_p = qr(A_p).R locally (blocked Householder, Q not formed), all-gather, the QR
-    of the (P n_st x n_st) stack and the Jacobi SVD of its factor are replicated (same bits on every rank, hence the
-    same rank and factors), V_p = A_p Z / sigma locally (pod.py:42-45).  Returns (V_local, sigma, n_L)."""
-    R = backend.tsqr_r(A_local)
-    stack = _all_gather_stack(backend, R, group)
-    if stack is not R:
-        R = backend.tsqr_r(stack)
-    n_L_out = backend.pod_from_r(R, eps, n_L)
+    """TSQR mode: one leaf per rank.  F_p = the rank-revealing Householder factor of A_p (pb_tsqr_factor: block
+    pivoting, stops at the numerical rank; Q not formed), all-gather of the first max_p rows(F_p) rows, the factor of
+    the stack and its Jacobi SVD are replicated (same bits on every rank, hence the same rank and factors),
+    V_p = A_p Z / sigma locally (pod.py:42-45).  eps == 0 without n_L asks for every mode: nothing may be dropped, the
+    plain triangular R factors are used.  Returns (V_local, sigma, n_L)."""
+    if eps == 0. and n_L == 0:
+        R = backend.tsqr_r(A_local)
+        stack = _all_gather_stack(backend, R, group)
+        if stack is not R:
+            R = backend.tsqr_r(stack)
+        n_L_out = backend.pod_from_r(R, eps, n_L)
+    else:
+        F, rows = backend.tsqr_factor(A_local)
+        cap = _max_over_ranks(backend, rows, group)
+        Fc = F[:cap]
+        stack = _all_gather_stack(backend, Fc, group)
+        if stack is not Fc:
+            F, rows = backend.tsqr_factor(stack)
+        n_L_out = backend.pod_from_factor(F, rows, eps, n_L)
     V = backend.basis(A_local, None, n_L_out)
     return V, backend.sigma(), n_L_out
 
@@ -161,6 +184,22 @@ class CudaBackend:
         ptr, ld = (A.data_ptr(), A.stride(0)) if is_t else (A.ptr, A.ld)
         self.ctx.check(self.L.pb_tsqr_r(self.ctx.h, ptr, rows, m, ld, R.data_ptr()))
         return R
+
+    def tsqr_factor(self, A):
+        """Rank-revealing factor of a DeviceArray slab or of a torch (rows x m) stack: (F torch tensor m x m, rows used)."""
+        is_t = isinstance(A, self.torch.Tensor)
+        rows, m = A.shape
+        F = self._empty(m, m)
+        ptr, ld = (A.data_ptr(), A.stride(0)) if is_t else (A.ptr, A.ld)
+        fr = C.c_int64()
+        self.ctx.check(self.L.pb_tsqr_factor(self.ctx.h, ptr, rows, m, ld, F.data_ptr(), C.byref(fr)))
+        return F, fr.value
+
+    def pod_from_factor(self, F, rows, eps, n_L):
+        nl = C.c_int()
+        self.ctx.check(self.L.pb_pod_from_factor(self.ctx.h, F.data_ptr(), int(rows), F.shape[1], F.stride(0), float(eps),
+                                                 int(n_L), C.byref(nl)))
+        return nl.value
 
     def all_gather_rows(self, R, group=None):
         import torch.distributed as dist

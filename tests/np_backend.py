@@ -25,6 +25,21 @@ class NumpyBackend:
         A = A.numpy() if isinstance(A, torch.Tensor) else A
         return torch.from_numpy(np.linalg.qr(A, mode="r"))
 
+    def tsqr_factor(self, A):
+        """Double of pb_tsqr_factor: pivoted QR cut at the numerical rank, columns back in input order; (m x m buffer, rows)."""
+        import scipy.linalg as sl
+        A = A.numpy() if isinstance(A, torch.Tensor) else A
+        m = A.shape[1]
+        R, piv = sl.qr(A, mode="r", pivoting=True)
+        d = np.abs(np.diag(R))
+        k = max(1, int((d > 16 * np.finfo(float).eps * d[0]).sum()))
+        F = np.zeros((m, m))
+        F[:k, piv] = R[:k]
+        return torch.from_numpy(F), k
+
+    def pod_from_factor(self, F, rows, eps, n_L):
+        return self.pod_from_r(F[:rows], eps, n_L)
+
     def all_gather_rows(self, R, group=None):
         import torch.distributed as dist
         parts = [torch.empty_like(R) for _ in range(dist.get_world_size(group))]
@@ -32,7 +47,8 @@ class NumpyBackend:
         return torch.cat(parts, 0)
 
     def pod_from_r(self, R, eps, n_L):
-        _, s, Zt = np.linalg.svd(R.numpy())
+        _, s, Zt = np.linalg.svd(R.numpy(), full_matrices=True)
+        s = np.concatenate([s, np.zeros(Zt.shape[0] - len(s))])
         self._sig, self._W = s, Zt.T
         if n_L == 0:
             n_L = po.truncation_rank(s ** 2, eps, len(s))

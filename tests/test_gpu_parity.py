@@ -207,6 +207,74 @@ def test_tsqr_r_ill_conditioned_and_strided(ctx):
     assert np.abs(R[:, 17]).max() == 0.
 
 
+def _tsqr_factor(ctx, A, ld=None):
+    rows, m = A.shape
+    Ad, Fd = ctx.to_device(A), ctx.alloc(m, m)
+    fr = C.c_int64()
+    ctx.check(_lib.lib().pb_tsqr_factor(ctx.h, Ad.ptr, rows, m, Ad.ld, Fd.ptr, C.byref(fr)))
+    panels, frs, fl = C.c_int64(), C.c_int64(), C.c_double()
+    ctx.check(_lib.lib().pb_tsqr_stats(ctx.h, C.byref(panels), C.byref(frs), C.byref(fl)))
+    assert frs.value == fr.value
+    return Fd.download(), fr.value, panels.value
+
+
+@pytest.mark.parametrize("rows,m,rank", [(3000, 500, 20), (3000, 500, 100), (5000, 333, 333), (700, 130, 130),
+                                         (2000, 1000, 64), (100, 1, 1), (33, 70, 33), (4000, 256, 0)])
+def test_tsqr_factor_rank_revealing(ctx, rows, m, rank):
+    """pb_tsqr_factor: F^T F = A^T A relative to the largest column norm; a numerically low-rank matrix stops after
+    ceil(rank / 64) (+1) panels with that many rows instead of m; a full-rank one runs every panel; the rows below the
+    factor are zero; a zero matrix gives zero rows."""
+    rng = np.random.default_rng(rows + m + rank)
+    if rank == 0:
+        A = np.zeros((rows, m))
+    elif rank < min(rows, m):
+        A = rng.standard_normal((rows, rank)) @ rng.standard_normal((rank, m))
+    else:
+        A = rng.standard_normal((rows, m))
+    F, fr, panels = _tsqr_factor(ctx, A)
+    G = A.T @ A
+    assert np.abs(F.T @ F - G).max() <= 2e-13 * max(np.abs(G).max(), 1e-300)
+    assert np.abs(F[fr:]).max() == 0. if fr < m else True
+    if rank == 0:
+        assert fr == 0
+    elif rank < min(rows, m):
+        assert fr <= (rank + 63) // 64 * 64 + 64 and panels <= (rank + 63) // 64 + 1, (fr, panels)
+    else:
+        assert fr == min(m, (min(rows, m) + 63) // 64 * 64) or fr == m
+
+
+def test_tsqr_factor_adversarial_column_order(ctx):
+    """200 copies of one column first, the informative columns last, graded by 1e-12: block pivoting brings the
+    informative columns forward, so the factorisation still stops at the numerical rank, and the POD through the
+    factor matches the SVD."""
+    rng = np.random.default_rng(77)
+    B = rng.standard_normal((6000, 40)) @ np.diag(10. ** -np.linspace(0, 12, 40)) @ rng.standard_normal((40, 300))
+    A = np.hstack([np.tile(B[:, :1], (1, 200)), B])
+    F, fr, panels = _tsqr_factor(ctx, A)
+    assert fr <= 128 and panels <= 2, (fr, panels)
+    G = A.T @ A
+    assert np.abs(F.T @ F - G).max() <= 2e-13 * np.abs(G).max()
+    V, sig = perform_pod(A, 1e-12, 0, False, mode="tsqr", ctx=ctx, return_sigma=True)
+    Vr = po.perform_pod(A, 1e-12)
+    assert V.shape == Vr.shape
+    assert cmp.largest_principal_angle(V, Vr) <= cmp.TOL_ANGLE
+    D = np.linalg.svd(A, compute_uv=False)
+    assert cmp.sigma_error(sig[:len(D)], D) <= cmp.TOL_SIGMA_REL
+
+
+@pytest.mark.parametrize("name,field", POD_CASES)
+def test_tsqr_full_equals_rank_revealing(ctx, name, field):
+    """tsqr (early stop) against tsqr_full (every panel): same rank, same singular values, same subspace."""
+    g = load_golden(f"pod_{name}")
+    _, U, _, _ = regen(g, field)
+    V1, s1 = perform_pod(U, float(g["eps"]), 0, False, mode="tsqr", ctx=ctx, return_sigma=True)
+    V2, s2 = perform_pod(U, float(g["eps"]), 0, False, mode="tsqr_full", ctx=ctx, return_sigma=True)
+    assert V1.shape == V2.shape == g["V"].shape
+    assert cmp.sigma_error(s1, s2) <= 1e-13
+    assert cmp.largest_principal_angle(V1, V2) <= 1e-9
+    assert cmp.largest_principal_angle(V2, g["V"]) <= cmp.TOL_ANGLE
+
+
 def test_tsqr_logical_shards_equal_unsharded(ctx):
     """TSQR with one leaf per (logical) rank: R of the stacked slab factors gives the POD of the whole matrix."""
     g = load_golden("pod_ackley_64")
