@@ -309,6 +309,9 @@ int  pb_residual_gram(pb_ctx* ctx, const double* V_dev, int64_t ldv, int n_L, co
 int  pb_probe_fp64_peak(pb_ctx* ctx, int kind, double* tflops);
 /* device-to-device copy of `bytes` (read+write counted).  Returns GB/s. */
 int  pb_probe_hbm_copy(pb_ctx* ctx, size_t bytes, double* gbs);
+/* GB/s of the host-side pageable -> pinned staging copy (threads <= 0 / streaming < 0: the library's own settings:
+ * env PB_HOST_COPY_THREADS, PB_HOST_COPY_NT) */
+int  pb_probe_host_copy(size_t bytes, int threads, int streaming, double* gbs);
 /* write `bytes` of scratch to evict L2 between timed iterations */
 int  pb_flush_l2(pb_ctx* ctx);
 

@@ -87,6 +87,7 @@ SIGNATURES = {
     "pb_residual_gram": (_int, [_vp, _vp, _i64, _int, _vp, _i64, _int, _i64, _vp, _vp]),
     "pb_probe_fp64_peak": (_int, [_vp, _int, _pd]),
     "pb_probe_hbm_copy": (_int, [_vp, C.c_size_t, _pd]),
+    "pb_probe_host_copy": (_int, [C.c_size_t, _int, _int, _pd]),
     "pb_flush_l2": (_int, [_vp]),
 }
 

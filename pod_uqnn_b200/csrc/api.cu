@@ -5,6 +5,11 @@
 #include <cmath>
 #include <algorithm>
 #include <mutex>
+#include <condition_variable>
+#include <chrono>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <thread>
 #include <cstdlib>
 #include <vector>
@@ -165,7 +170,16 @@ int pb_download_async(pb_ctx* ctx, void* host, const void* dev, size_t bytes) {
     PB_ENTER(ctx); PB_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream)); return PB_OK;
 }
 int pb_upload(pb_ctx* ctx, void* dev, const void* host, size_t bytes) { PB_TRY(pb_upload_async(ctx, dev, host, bytes)); return pb_sync(ctx); }
-int pb_download(pb_ctx* ctx, void* host, const void* dev, size_t bytes) { PB_TRY(pb_download_async(ctx, host, dev, bytes)); return pb_sync(ctx); }
+namespace { int download_staged(pb_ctx* ctx, char* host, const char* dev, size_t bytes); bool host_is_pinned(const void* p); }
+// D2H + sync.  Large pageable destinations (an ordinary numpy array) go through the pinned staging ring: the copy engine
+// fills slot s + 1 while host threads move slot s into the destination (the driver's own pageable path is single-threaded).
+int pb_download(pb_ctx* ctx, void* host, const void* dev, size_t bytes) {
+    if (ctx && host && dev && bytes >= ((size_t)8 << 20) && !host_is_pinned(host)) {
+        PB_ENTER(ctx);
+        return download_staged(ctx, static_cast<char*>(host), static_cast<const char*>(dev), bytes);
+    }
+    PB_TRY(pb_download_async(ctx, host, dev, bytes)); return pb_sync(ctx);
+}
 int pb_slab(pb_ctx* ctx, size_t bytes, void** dev) {
     PB_ENTER(ctx); if (!dev) return PB_ERR_ARG;
     size_t elems = (bytes + 7) / 8; if (elems == 0) elems = 1;
@@ -609,24 +623,89 @@ int host_copy_threads() {
     static const int n = []{
         const char* e = getenv("PB_HOST_COPY_THREADS");
         int v = e ? atoi(e) : 0;
-        if (v <= 0) { v = (int)std::thread::hardware_concurrency() / 2; if (v > 16) v = 16; }
+        if (v <= 0) { v = (int)std::thread::hardware_concurrency(); if (v > 16) v = 16; }
         return v < 1 ? 1 : v;
     }();
     return n;
 }
+bool host_copy_streaming() {
+    static const bool nt = []{ const char* e = getenv("PB_HOST_COPY_NT"); return e ? atoi(e) != 0 : true; }();
+    return nt;
+}
+// one thread's share: non-temporal 16-byte stores keep the staging buffer out of the caches (it is read next by the
+// copy engine, never by the CPU) and spare the read-for-ownership of every destination line
+void copy_span(char* dst, const char* src, size_t bytes, bool nt) {
+#if defined(__SSE2__)
+    if (nt && bytes >= 4096 && ((uintptr_t)dst & 15) == 0) {
+        const size_t n16 = bytes / 64 * 4;
+        const __m128i* s = reinterpret_cast<const __m128i*>(src);
+        __m128i* d = reinterpret_cast<__m128i*>(dst);
+        for (size_t i = 0; i < n16; i += 4) {
+            __m128i a = _mm_loadu_si128(s + i), b = _mm_loadu_si128(s + i + 1), c = _mm_loadu_si128(s + i + 2), e = _mm_loadu_si128(s + i + 3);
+            _mm_stream_si128(d + i, a); _mm_stream_si128(d + i + 1, b); _mm_stream_si128(d + i + 2, c); _mm_stream_si128(d + i + 3, e);
+        }
+        _mm_sfence();
+        if (bytes > n16 * 16) memcpy(dst + n16 * 16, src + n16 * 16, bytes - n16 * 16);
+        return;
+    }
+#endif
+    memcpy(dst, src, bytes);
+}
+// persistent host threads (started on first use, shared by every context of the process): a job is a row range of a
+// pitched copy; the caller takes share 0 itself and waits for the others
+class HostCopyPool {
+public:
+    static HostCopyPool& get() { static HostCopyPool* p = new HostCopyPool(); return *p; }   // never destroyed: no join at exit
+    void copy(char* dst, const char* src, size_t rows, size_t row_bytes, size_t src_pitch, int T, bool nt) {
+        std::unique_lock<std::mutex> call(call_mu_);            // one copy at a time
+        T = std::max(1, std::min(T, kMax));
+        ensure(T - 1);
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            job_ = {dst, src, rows, row_bytes, src_pitch, T, nt}; pending_ = T - 1; ++gen_;
+        }
+        if (T > 1) cv_.notify_all();
+        run(job_, 0);
+        if (T > 1) { std::unique_lock<std::mutex> g(mu_); done_.wait(g, [&]{ return pending_ == 0; }); }
+    }
+private:
+    static constexpr int kMax = 64;
+    struct Job { char* dst; const char* src; size_t rows, row_bytes, pitch; int T; bool nt; };
+    static void run(const Job& j, int t) {
+        if (j.pitch == j.row_bytes) {            // contiguous: 64-byte aligned byte spans
+            const size_t total = j.rows * j.row_bytes, lines = total / 64;
+            const size_t b0 = lines * t / j.T * 64, b1 = (t + 1 == j.T) ? total : lines * (t + 1) / j.T * 64;
+            if (b1 > b0) copy_span(j.dst + b0, j.src + b0, b1 - b0, j.nt);
+            return;
+        }
+        const size_t r0 = j.rows * t / j.T, r1 = j.rows * (t + 1) / j.T;
+        for (size_t r = r0; r < r1; ++r) copy_span(j.dst + r * j.row_bytes, j.src + r * j.pitch, j.row_bytes, j.nt);
+    }
+    void ensure(int n) {
+        while ((int)workers_.size() < n) {
+            const int id = (int)workers_.size() + 1;
+            uint64_t seen; { std::lock_guard<std::mutex> g(mu_); seen = gen_; }
+            workers_.emplace_back([this, id, seen]() mutable {
+                for (;;) {
+                    Job j;
+                    { std::unique_lock<std::mutex> g(mu_); cv_.wait(g, [&]{ return gen_ != seen; }); seen = gen_; j = job_; }
+                    if (id < j.T) {
+                        run(j, id);
+                        std::lock_guard<std::mutex> g(mu_);
+                        if (--pending_ == 0) done_.notify_one();
+                    }
+                }
+            });
+            workers_.back().detach();
+        }
+    }
+    std::mutex call_mu_, mu_; std::condition_variable cv_, done_;
+    std::vector<std::thread> workers_; Job job_{}; int pending_ = 0; uint64_t gen_ = 0;
+};
 // dst (contiguous, row length `row_bytes`) <- src rows with pitch `src_pitch`, split over the host threads
 void parallel_host_copy(char* dst, const char* src, size_t rows, size_t row_bytes, size_t src_pitch) {
-    const int T = (int)std::min<size_t>((size_t)host_copy_threads(), std::max<size_t>(1, rows * row_bytes / (4u << 20)));
-    auto work = [=](int t) {
-        const size_t r0 = rows * t / T, r1 = rows * (t + 1) / T;
-        if (src_pitch == row_bytes) memcpy(dst + r0 * row_bytes, src + r0 * src_pitch, (r1 - r0) * row_bytes);
-        else for (size_t r = r0; r < r1; ++r) memcpy(dst + r * row_bytes, src + r * src_pitch, row_bytes);
-    };
-    if (T <= 1) { work(0); return; }
-    std::vector<std::thread> th;
-    for (int t = 1; t < T; ++t) th.emplace_back(work, t);
-    work(0);
-    for (auto& x : th) x.join();
+    const int T = (int)std::min<size_t>((size_t)host_copy_threads(), std::max<size_t>(1, rows * row_bytes / (1u << 20)));
+    HostCopyPool::get().copy(dst, src, rows, row_bytes, src_pitch, T, host_copy_streaming());
 }
 int stage_reserve(pb_ctx* ctx, size_t bytes) {
     if (ctx->stage_cap >= bytes && ctx->stage[0]) return PB_OK;
@@ -661,6 +740,27 @@ int upload_rows(pb_ctx* ctx, double* dev, const double* host, int64_t n_rows, in
                            (size_t)ld_host * sizeof(double));
         PB_CUDA(ctx, cudaMemcpyAsync(dev + r0 * n_cols, ctx->stage[s], nr * row_bytes, cudaMemcpyHostToDevice, stream));
         PB_CUDA(ctx, cudaEventRecord(ctx->stage_ev[s], stream));
+    }
+    return PB_OK;
+}
+int download_staged(pb_ctx* ctx, char* host, const char* dev, size_t bytes) {
+    PB_TRY(stage_reserve(ctx, (size_t)64 << 20));
+    const size_t piece = ctx->stage_cap;
+    const size_t n = (bytes + piece - 1) / piece;
+    for (int s = 0; s < PB_STAGE_SLOTS; ++s) PB_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[s]));   // ring idle (uploads done)
+    auto issue = [&](size_t i) -> cudaError_t {
+        const size_t off = i * piece, nb = std::min(piece, bytes - off);
+        const int s = (int)(i % PB_STAGE_SLOTS);
+        cudaError_t e = cudaMemcpyAsync(ctx->stage[s], dev + off, nb, cudaMemcpyDeviceToHost, ctx->stream);
+        return e != cudaSuccess ? e : cudaEventRecord(ctx->stage_ev[s], ctx->stream);
+    };
+    for (size_t i = 0; i < std::min<size_t>(n, PB_STAGE_SLOTS - 1); ++i) PB_CUDA(ctx, issue(i));
+    for (size_t i = 0; i < n; ++i) {
+        if (i + PB_STAGE_SLOTS - 1 < n) PB_CUDA(ctx, issue(i + PB_STAGE_SLOTS - 1));   // its slot was drained at step i - 1
+        const size_t off = i * piece, nb = std::min(piece, bytes - off);
+        const int s = (int)(i % PB_STAGE_SLOTS);
+        PB_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[s]));
+        parallel_host_copy(host + off, static_cast<const char*>(ctx->stage[s]), 1, nb, nb);
     }
     return PB_OK;
 }
@@ -732,6 +832,31 @@ int pb_upload_matrix(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_s
     PB_ENTER(ctx); if (!U_host || !U_dev) return PB_ERR_ARG;
     if (n_h <= 0 || n_st <= 0 || ldu_host < n_st) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_upload_matrix: bad shape");
     return upload_whole(ctx, U_dev, U_host, n_h, n_st, ldu_host);
+}
+
+// Host-side ceiling of the staged upload: GB/s of the pageable -> pinned copy alone (threads <= 0: the library's own
+// setting; streaming < 0: the library's own).  No GPU work.
+int pb_probe_host_copy(size_t bytes, int threads, int streaming, double* gbs) {
+    if (!gbs || bytes < (1u << 20)) return PB_ERR_ARG;
+    char* src = static_cast<char*>(malloc(bytes));
+    void* dst = nullptr;
+    if (!src) return PB_ERR_NOMEM;
+    const bool pinned = cudaMallocHost(&dst, bytes) == cudaSuccess;
+    if (!pinned) { cudaGetLastError(); dst = malloc(bytes); if (!dst) { free(src); return PB_ERR_NOMEM; } memset(dst, 0, bytes); }
+    memset(src, 1, bytes);
+    const int T = threads > 0 ? threads : host_copy_threads();
+    const bool nt = streaming < 0 ? host_copy_streaming() : streaming != 0;
+    double best = 0.;
+    for (int rep = 0; rep < 4; ++rep) {
+        auto t0 = std::chrono::steady_clock::now();
+        HostCopyPool::get().copy(static_cast<char*>(dst), src, bytes / 4096, 4096, 4096, T, nt);
+        double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (rep > 0) best = std::max(best, (double)(bytes / 4096 * 4096) / sec / 1e9);
+    }
+    if (pinned) cudaFreeHost(dst); else free(dst);
+    free(src);
+    *gbs = best;
+    return PB_OK;
 }
 
 int pb_gram_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, int64_t ldu_host, double* U_dev,
