@@ -623,7 +623,7 @@ int host_copy_threads() {
     static const int n = []{
         const char* e = getenv("PB_HOST_COPY_THREADS");
         int v = e ? atoi(e) : 0;
-        if (v <= 0) { v = (int)std::thread::hardware_concurrency(); if (v > 16) v = 16; }
+        if (v <= 0) { v = (int)std::thread::hardware_concurrency() / 2; if (v > 16) v = 16; }
         return v < 1 ? 1 : v;
     }();
     return n;
@@ -632,8 +632,10 @@ bool host_copy_streaming() {
     static const bool nt = []{ const char* e = getenv("PB_HOST_COPY_NT"); return e ? atoi(e) != 0 : true; }();
     return nt;
 }
-// one thread's share: non-temporal 16-byte stores keep the staging buffer out of the caches (it is read next by the
-// copy engine, never by the CPU) and spare the read-for-ownership of every destination line
+// one thread's share.  Non-temporal 16-byte stores (PB_HOST_COPY_NT=0 turns them off): no read-for-ownership of the
+// destination lines and the staging buffer stays out of the caches.  Alone the plain memcpy is faster on the B200 box's
+// host (8 threads: 76 vs 66 GB/s), but with the copy engine reading the ring at the same time the streaming stores win:
+// 1.28 GB pageable upload 24.4 ms (52.5 GB/s, the PCIe rate) vs 27.8 ms (profiles/r02_hostcopy.txt)
 void copy_span(char* dst, const char* src, size_t bytes, bool nt) {
 #if defined(__SSE2__)
     if (nt && bytes >= 4096 && ((uintptr_t)dst & 15) == 0) {

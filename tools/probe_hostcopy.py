@@ -25,10 +25,10 @@ def api_timing():
         tp, tj, tr = [], [], []
         for _ in range(3):
             t0 = time.perf_counter(); V = pod_mod.perform_pod(U, 1e-10, 0, False, mode=mode, ctx=ctx)
-            t1 = time.perf_counter(); v = pod_mod.project_to_v(V, U, ctx=ctx)
-            t2 = time.perf_counter(); v2 = pod_mod.project_to_v(V, U, ctx=ctx, reuse_slab=True)
+            t1 = time.perf_counter(); v2 = pod_mod.project_to_v(V, U, ctx=ctx, reuse_slab=True)
+            t2 = time.perf_counter(); v = pod_mod.project_to_v(V, U, ctx=ctx)
             t3 = time.perf_counter()
-            tp.append(t1 - t0); tj.append(t2 - t1); tr.append(t3 - t2)
+            tp.append(t1 - t0); tr.append(t2 - t1); tj.append(t3 - t2)
         out[mode] = {"perform_pod_ms": min(tp) * 1e3, "project_to_v_ms": min(tj) * 1e3, "project_reuse_ms": min(tr) * 1e3,
                      "n_L": V.shape[1]}
     Ud = ctx.to_device(U)
@@ -48,6 +48,6 @@ for T in (1, 2, 4, 8, 12, 16):
         g = C.c_double()
         L.pb_probe_host_copy(1 << 30, T, nt, C.byref(g))
         print(f"host copy pageable -> pinned: threads {T:2d} streaming {nt}: {g.value:6.1f} GB/s", flush=True)
-for T, nt in (("4", "1"), ("8", "1"), ("16", "1"), ("8", "0")):
+for T, nt in (("4", "0"), ("8", "0"), ("16", "0"), ("8", "1")):
     env = dict(os.environ, PB_HOST_COPY_THREADS=T, PB_HOST_COPY_NT=nt)
     subprocess.run([sys.executable, os.path.abspath(__file__), "api"], env=env, check=False)
