@@ -328,6 +328,8 @@ def run_gpu(args):
     clocks = sampler.stop() if sampler else None
     ms_step = max_over_ranks(ms_total / args.steps)
     value = algo_flops(n_h, N_S, n_L) / (ms_step * 1e-3) / 1e12
+    from pod_uqnn_b200.pod import pod_sigma
+    sig_resident = pod_sigma(ctx)
 
     # ---- end to end: host buffers in, host buffers out (pinned), copies inside the timed region
     hU, hV, hv = C.c_void_p(), C.c_void_p(), C.c_void_p()
@@ -411,28 +413,46 @@ def run_gpu(args):
     if world > 1:
         parity = parity_vs_single_gpu(ctx, be, sharded, snapshots_device, X, w["mu"], U, n_h, rank, state, pod_single, barrier)
 
-    # ---- the TSQR accuracy mode on the same resident slab(s): Householder QR per rank, all-gather of the R factors,
-    #      replicated QR of the stack + pivoted QR + Jacobi SVD, basis, projection
-    def step_tsqr():
-        if world == 1:
-            return pod_single(U, "tsqr", "t")[2]
-        V, _, nl = sharded.pod_sharded(be, U, EPS, 0, "tsqr")
-        sharded.project_sharded(be, V, U)
-        return nl
-    step_tsqr(); barrier()
-    t_best = 1e30
-    for _ in range(3):
-        barrier(); ctx.timer_start(); nl_t = step_tsqr(); t_best = min(t_best, ctx.timer_stop())
-    barrier()
-    t_tsqr = max_over_ranks(t_best)
-    qr_flops = world * (2 * n_h_loc * N_S ** 2 - 2 / 3 * N_S ** 3)
-    tsqr_line = {"workload": "same slabs, mode tsqr (blocked Householder QR of U, pivoted QR + Jacobi SVD of R), basis, projection",
-                 "ms_per_step": t_tsqr, "n_L": nl_t, "local_qr_ms": ctx.ms(_lib.T_QR),
-                 "householder_tflops": qr_flops / (t_tsqr * 1e-3) / 1e12,
-                 "frac_fp64_peak": qr_flops / (t_tsqr * 1e-3) / 1e12 / (peak_tf * world),
-                 "note": "flop count 2 n_h n_s^2 - (2/3) n_s^3 per slab (SURVEY 8d); at N > 1 T_QR is the replicated QR of the stacked R factors"}
-    for k in [k for k in state if k.startswith("t")]:
-        state.pop(k)
+    # ---- the TSQR accuracy mode on the same resident slab(s): rank-revealing Householder QR per rank (block pivoting,
+    #      stops at the numerical rank), all-gather of the truncated factors, replicated factor of the stack + pivoted QR
+    #      + Jacobi SVD, basis, projection.  "tsqr_full" = the same without the early stop (every 64-column panel).
+    def qr_stats():
+        if world > 1:
+            st = be.qr_stats
+            return {"panels_local": st["local"][0], "factor_rows_local": st["local"][1],
+                    "flops_executed": world * st["local"][2] + st.get("stack", (0, 0, 0.))[2]}
+        p_, f_, fl_ = C.c_int64(), C.c_int64(), C.c_double()
+        ctx.check(L.pb_tsqr_stats(ctx.h, C.byref(p_), C.byref(f_), C.byref(fl_)))
+        return {"panels_local": p_.value, "factor_rows_local": f_.value, "flops_executed": fl_.value}
+
+    tsqr_line = {"workload": "same slabs, TSQR accuracy mode (never forms U^T U): blocked Householder QR of U, pivoted QR + Jacobi "
+                             "SVD of the factor, basis, projection"}
+    qr_flops_full = world * (2 * n_h_loc * N_S ** 2 - 2 / 3 * N_S ** 3)
+    for tmode in ("tsqr", "tsqr_full"):
+        def step_tsqr():
+            if world == 1:
+                return pod_single(U, tmode, "t")[2]
+            V, _, nl = sharded.pod_sharded(be, U, EPS, 0, tmode)
+            sharded.project_sharded(be, V, U)
+            return nl
+        step_tsqr(); barrier()
+        t_best = 1e30
+        for _ in range(3):
+            barrier(); ctx.timer_start(); nl_t = step_tsqr(); t_best = min(t_best, ctx.timer_stop())
+        barrier()
+        t_tsqr = max_over_ranks(t_best)
+        st = qr_stats()
+        tsqr_line[tmode] = {"ms_per_step": t_tsqr, "n_L": nl_t, "qr_ms_last_factor": ctx.ms(_lib.T_QR), **st,
+                            "executed_tflops": st["flops_executed"] / (t_tsqr * 1e-3) / 1e12,
+                            "frac_fp64_peak_executed": st["flops_executed"] / (t_tsqr * 1e-3) / 1e12 / (peak_tf * world),
+                            "full_householder_equiv_tflops": qr_flops_full / (t_tsqr * 1e-3) / 1e12}
+        for k in [k for k in state if k.startswith("t")]:
+            state.pop(k)
+    tsqr_line["ms_per_step"] = tsqr_line["tsqr"]["ms_per_step"]
+    tsqr_line["n_L"] = tsqr_line["tsqr"]["n_L"]
+    tsqr_line["note"] = ("tsqr = the API default (rank-revealing: stops when every residual column is at the QR's rounding level); "
+                         "flops_executed = Householder count of the panels actually run (pb_tsqr_stats); full count 2 n_h n_s^2 - "
+                         "(2/3) n_s^3 per slab (SURVEY 8d)")
 
     ens_line = ensemble_bench(ctx, L, world, rank, max_over_ranks, peak_tf, with_cpu=(world == 1 and not args.no_cpu_baseline))
     train_lines = train_bench(ctx, world, rank, max_over_ranks, peak_tf, with_cpu=(world == 1 and not args.no_cpu_baseline))
@@ -444,6 +464,15 @@ def run_gpu(args):
         if be is not None:
             be._cache.clear()
         c5 = c5_leg(ctx, L, be, sharded, wl, world, rank, barrier, max_over_ranks, sum_over_ranks, peak_tf, pod_single, state)
+
+    # ---- N > 1: the same C2 step from ONE process (rank 0) driving all N GPUs through pb_multi_* (the library's own
+    #      peer-memory collectives, no torch / NCCL on the path); the other ranks idle at the barrier meanwhile
+    lib_multi = None
+    if world > 1 and not args.skip_lib_multi:
+        barrier()
+        if rank == 0:
+            lib_multi = lib_multi_leg(world, X, w["mu"], n_h_loc, n_L, sig_resident, ms_step, snapshots_device)
+        barrier()
 
     if rank != 0:
         if dist is not None:
@@ -481,7 +510,7 @@ def run_gpu(args):
                     "h2d_bytes_per_step": n_h * N_S * 8, "d2h_bytes_per_step": (n_h + N_S) * n_L * 8},
             "e2e_api": e2e_api, "h2d_probe": h2d,
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "stage_ms": {k: statistics.mean(v) for k, v in parts.items()}, "parity": parity, "tsqr_mode": tsqr_line, "c5": c5,
+            "stage_ms": {k: statistics.mean(v) for k, v in parts.items()}, "parity": parity, "tsqr_mode": tsqr_line, "c5": c5, "lib_multi": lib_multi,
             "ensemble_predict": ens_line, "ensemble_train": train_lines,
             "snapshot_kernel": {"ms": snap_ms, "gbs": n_h_loc * N_S * 8 / (snap_ms * 1e-3) / 1e9,
                                 "note": "Ackley field -> U slab in HBM (outside the timed step): table kernels + ackley_indexed_kernel, second call"}}
@@ -528,6 +557,52 @@ def parity_vs_single_gpu(ctx, be, sharded, snapshots_device, X, mu, U, n_h, rank
     return out or None
 
 
+def lib_multi_leg(world, X, mu, n_h_loc, n_L_ref, sig_ref, ms_torchrun, snapshots_device, steps=20):
+    """The weak-scaled C2 step (POD + basis + projection on resident slabs) driven by ONE process over all N GPUs:
+    pb_multi_pod / pb_multi_basis / pb_multi_project.  Checked against the torchrun + NCCL run of the same slabs
+    (equal n_L, sigma to 1e-10 sigma_max); device time = max over the GPUs of the events around the region."""
+    import ctypes as C
+    from pod_uqnn_b200 import _lib
+    L = _lib.lib()
+    m = _lib.MultiContext(world)
+    slabs = [snapshots_device(m.ctxs[p], "ackley", X, mu, row0=p * n_h_loc, n_rows=n_h_loc)[0] for p in range(world)]
+    n_h = n_h_loc * world
+    U_ptrs, rows, lds = _lib._ptr_array([s.ptr for s in slabs]), _lib._i64_array([n_h_loc] * world), _lib._i64_array([N_S] * world)
+    out = {"workload": f"the same {world} resident C2 slabs, one process, pb_multi_* (peer-memory all-reduce over NVLink)"}
+    for mode in (MODE, "tsqr"):
+        nl = C.c_int()
+        m.check(L.pb_multi_pod(m.h, U_ptrs, rows, N_S, lds, EPS, 0, _lib.POD_MODES[mode], C.byref(nl)))
+        V = [m.ctxs[p].alloc(n_h_loc, nl.value) for p in range(world)]
+        v = [m.ctxs[p].alloc(N_S, nl.value) for p in range(world)]
+        V_ptrs, v_ptrs = _lib._ptr_array([a.ptr for a in V]), _lib._ptr_array([a.ptr for a in v])
+
+        def step():
+            m.check(L.pb_multi_pod(m.h, U_ptrs, rows, N_S, lds, EPS, 0, _lib.POD_MODES[mode], C.byref(nl)))
+            m.check(L.pb_multi_basis(m.h, V_ptrs, None))
+            m.check(L.pb_multi_project(m.h, V_ptrs, None, nl.value, U_ptrs, lds, rows, N_S, v_ptrs))
+        for _ in range(3):
+            step()
+        m.sync()
+        m.timer_start()
+        for _ in range(steps):
+            step()
+        ms = m.timer_stop() / steps
+        sig = m.sigma()
+        line = {"ms_per_step": ms, "n_L": nl.value, "tflops": algo_flops(n_h, N_S, nl.value) / (ms * 1e-3) / 1e12}
+        if mode == MODE:
+            smax = float(sig_ref[0])
+            err = float(np.max(np.abs(sig[:n_L_ref] - sig_ref[:n_L_ref])) / smax)
+            line.update({"sigma_err_vs_torchrun": err, "n_L_torchrun": n_L_ref, "ms_per_step_torchrun": ms_torchrun,
+                         "status": "ok" if (nl.value == n_L_ref and err <= 1e-10) else "MISMATCH"})
+            if line["status"] != "ok":
+                raise SystemExit(f"bench.py: single-process multi-GPU result differs from the torchrun run: {json.dumps(line)}")
+        out[mode] = line
+        del V, v
+    del slabs
+    m.close()
+    return out
+
+
 def c5_leg(ctx, L, be, sharded, wl, world, rank, barrier, max_over_ranks, sum_over_ranks, peak_tf, pod_single, state):
     """BASELINE.json configs[4] at 1.25 M rows per GPU: U = sum_k s_k phi_k psi_k^T (DCT-II vectors) filled in
     HBM, POD (gram2 and tsqr) + projection.  ASSERTS the closed form (north_star tolerances): n_L, sigma_k = s_k to
@@ -545,7 +620,7 @@ def c5_leg(ctx, L, be, sharded, wl, world, rank, barrier, max_over_ranks, sum_ov
     out = {"workload": f"C5 DCT known-answer slab(s): n_h = {n_h} ({n_loc} rows per GPU) x n_s = {n_s}, fp64, eps = {EPS:g}, "
                        f"POD + projection, r = {r} exact singular values 2^(-k/4)", "n_L_closed_form": nL_closed}
     n_chk = 4096
-    for mode in ("gram2", "tsqr"):
+    for mode in ("gram2", "tsqr", "tsqr_full"):
         def step():
             if world == 1:
                 V, v, nl = pod_single(Uc, mode, "c")
@@ -561,8 +636,15 @@ def c5_leg(ctx, L, be, sharded, wl, world, rank, barrier, max_over_ranks, sum_ov
         ms = max_over_ranks(best)
         from pod_uqnn_b200.pod import pod_sigma
         sig = pod_sigma(ctx)
-        flops = algo_flops(n_h, n_s, nl) if mode != "tsqr" else \
-            world * (2 * n_loc * n_s ** 2 - (2 / 3) * n_s ** 3) + 4 * n_h * n_s * nl
+        full_qr = world * (2 * n_loc * n_s ** 2 - (2 / 3) * n_s ** 3) + 4 * n_h * n_s * nl
+        if mode == "gram2":
+            flops = algo_flops(n_h, n_s, nl)
+        elif mode == "tsqr_full" or be is None:
+            p_, f_, fl_ = C.c_int64(), C.c_int64(), C.c_double()
+            ctx.check(L.pb_tsqr_stats(ctx.h, C.byref(p_), C.byref(f_), C.byref(fl_)))
+            flops = (full_qr if mode == "tsqr_full" else fl_.value + 4 * n_h * n_s * nl)
+        else:
+            flops = world * be.qr_stats["local"][2] + be.qr_stats.get("stack", (0, 0, 0.))[2] + 4 * n_h * n_s * nl
         # closed-form checks (every rank checks its own rows of V; rank 0 reports)
         sig_err = float(np.max(np.abs(sig[:nL_closed] - s[:nL_closed])) / s[0]) if len(sig) >= nL_closed else float("inf")
         Vh = np.empty((n_chk, nl))
@@ -583,9 +665,11 @@ def c5_leg(ctx, L, be, sharded, wl, world, rank, barrier, max_over_ranks, sum_ov
         out[mode] = {"wall_s": ms * 1e-3, "n_L": nl, "tflops": flops / (ms * 1e-3) / 1e12,
                      "frac": flops / (ms * 1e-3) / 1e12 / (peak_tf * world),
                      "sigma_err_rel_sigma_max": sig_err, "subspace_angle": angle, "V_rows_err_rel": v_err,
-                     "flop_count": "n_h n_s (n_s+1) + 4 n_h n_s n_L" if mode != "tsqr" else
-                                   "Householder N (2 n_loc n_s^2 - 2/3 n_s^3) + 4 n_h n_s n_L",
-                     "stage_ms": {"gram_or_qr": ctx.ms(_lib.T_GRAM if mode != "tsqr" else _lib.T_QR), "eig": ctx.ms(_lib.T_EIG),
+                     "flop_count": {"gram2": "n_h n_s (n_s+1) + 4 n_h n_s n_L",
+                                    "tsqr": "Householder flops of the panels actually run (rank-revealing early stop, pb_tsqr_stats) + 4 n_h n_s n_L",
+                                    "tsqr_full": "Householder N (2 n_loc n_s^2 - 2/3 n_s^3) + 4 n_h n_s n_L"}[mode],
+                     "full_householder_equiv_tflops": None if mode == "gram2" else full_qr / (ms * 1e-3) / 1e12,
+                     "stage_ms": {"gram_or_qr": ctx.ms(_lib.T_GRAM if mode == "gram2" else _lib.T_QR), "eig": ctx.ms(_lib.T_EIG),
                                   "basis": ctx.ms(_lib.T_BASIS), "project": ctx.ms(_lib.T_PROJECT)},
                      "status": "ok" if ok else "MISMATCH"}
         if not ok:
@@ -693,6 +777,7 @@ def main():
     ap.add_argument("--impl", default="podb200", choices=["podb200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-c5", action="store_true", help="skip the C5 (1.25 M x 4096 per GPU) leg")
+    ap.add_argument("--skip-lib-multi", action="store_true", help="skip the single-process multi-GPU leg (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "podb200" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -245,6 +245,47 @@ int  pb_struct_to_matrix(pb_ctx* ctx, const double* Us_dev, int64_t n_h, int n_t
 int  pb_matrix_to_struct(pb_ctx* ctx, const double* U_dev, int64_t ldu, int64_t n_h, int n_t,
                          int64_t n_s, double* Us_dev);
 
+/* ---- single-process multi-GPU (csrc/multi.cu) ------------------------------
+ * "pb_create(n_gpus, device_ids) ... no MPI, no torchrun needed".  A pb_multi owns one context (stream +
+ * work buffers) and one host thread per GPU.  The snapshot matrix is row-sharded by dof (contiguous, balanced slabs:
+ * pb_multi_row_range); the exchange steps -- sum of the Gram / second-pass Gram / refinement / projection partials,
+ * gather of the TSQR factors -- run as the library's own peer-memory kernels and copies over NVLink (deterministic:
+ * every GPU ends with the same bits), the small eigensolve is replicated.  Stands behind the reference's
+ * single-process calls pod.perform_pod(U, eps, n_L) (pod.py:7-47) and (V.T.dot(U)).T (podnnmodel.py:435-437) when
+ * n_gpus > 1.  device_ids == NULL: GPUs 0..n_gpus-1.  Logical ranks may share a device (tests on a one-GPU box).
+ *   pb_multi_ctx:          the context of rank p (for pb_malloc / pb_upload / pb_snapshots ... on that GPU)
+ *   pb_multi_pod:          slabs already in HBM: U_dev[p] is rows[p] x n_st with pitch ldu[p] (NULL: n_st)
+ *   pb_multi_pod_host:     host matrix in (pinned or pageable), slabs uploaded concurrently (chunked, overlapped with
+ *                          the per-chunk Grams) and kept in each context's slab for the calls below
+ *   pb_multi_basis:        V_dev[p] (rows[p] x n_L, pitch ldv[p] or n_L) = rank p's rows of the modes
+ *   pb_multi_basis_host:   the same gathered into a host matrix (n_h x n_L, pitch ldv_host)
+ *   pb_multi_project:      v_dev[p] (n x n_L) = sum over ranks of (V_p^T U_p)^T, replicated on every GPU
+ *   pb_multi_project_host: projection of the matrix the last pb_multi_pod_host uploaded onto the basis the last
+ *                          pb_multi_basis_host formed (both still in HBM) -> v_host (n_st x n_L)
+ *   pb_multi_all_reduce:   in-place sum of bufs[p] (count doubles on GPU p) over the ranks
+ *   pb_multi_timer_*:      bracket a region on every GPU's stream; stop returns the MAX device time over the GPUs */
+typedef struct pb_multi pb_multi;
+int  pb_multi_create(int n_gpus, const int* device_ids, pb_multi** out);
+int  pb_multi_destroy(pb_multi* m);
+const char* pb_multi_last_error(const pb_multi* m);
+int  pb_multi_size(const pb_multi* m);
+pb_ctx* pb_multi_ctx(pb_multi* m, int rank);
+int  pb_multi_row_range(const pb_multi* m, int64_t n_rows, int rank, int64_t* lo, int64_t* hi);
+int  pb_multi_sync(pb_multi* m);
+int  pb_multi_pod(pb_multi* m, const double* const* U_dev, const int64_t* rows, int64_t n_st, const int64_t* ldu,
+                  double eps, int n_L_in, int mode, int* n_L);
+int  pb_multi_pod_host(pb_multi* m, const double* U_host, int64_t n_h, int64_t n_st, int64_t ldu_host,
+                       double eps, int n_L_in, int mode, int* n_L);
+int  pb_multi_basis(pb_multi* m, double* const* V_dev, const int64_t* ldv);
+int  pb_multi_basis_host(pb_multi* m, double* V_host, int64_t ldv_host);
+int  pb_multi_project(pb_multi* m, const double* const* V_dev, const int64_t* ldv, int n_L, const double* const* U_dev,
+                      const int64_t* ldu, const int64_t* rows, int64_t n, double* const* v_dev);
+int  pb_multi_project_host(pb_multi* m, double* v_host);
+int  pb_multi_sigma(pb_multi* m, double* sigma_host, int64_t capacity, int64_t* count);
+int  pb_multi_all_reduce(pb_multi* m, double* const* bufs, int64_t count);
+int  pb_multi_timer_start(pb_multi* m);
+int  pb_multi_timer_stop(pb_multi* m, double* ms);
+
 /* ---- projection / reconstruction ----------------------------------------
  * replaces podnnmodel.py:435-437 (project_to_v), :431-433 (project_to_U), :247-253.
  *   pb_project:      v (n x n_L, ld = n_L) = (V^T U)^T for the local slab; partial sums

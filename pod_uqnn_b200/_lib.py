@@ -87,6 +87,23 @@ SIGNATURES = {
     "pb_residual_gram": (_int, [_vp, _vp, _i64, _int, _vp, _i64, _int, _i64, _vp, _vp]),
     "pb_probe_fp64_peak": (_int, [_vp, _int, _pd]),
     "pb_probe_hbm_copy": (_int, [_vp, C.c_size_t, _pd]),
+    "pb_multi_create": (_int, [_int, _pi, _pvp]),
+    "pb_multi_destroy": (_int, [_vp]),
+    "pb_multi_last_error": (C.c_char_p, [_vp]),
+    "pb_multi_size": (_int, [_vp]),
+    "pb_multi_ctx": (_vp, [_vp, _int]),
+    "pb_multi_row_range": (_int, [_vp, _i64, _int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "pb_multi_sync": (_int, [_vp]),
+    "pb_multi_pod": (_int, [_vp, _pvp, C.POINTER(C.c_int64), _i64, C.POINTER(C.c_int64), _dbl, _int, _int, _pi]),
+    "pb_multi_pod_host": (_int, [_vp, _vp, _i64, _i64, _i64, _dbl, _int, _int, _pi]),
+    "pb_multi_basis": (_int, [_vp, _pvp, C.POINTER(C.c_int64)]),
+    "pb_multi_basis_host": (_int, [_vp, _vp, _i64]),
+    "pb_multi_project": (_int, [_vp, _pvp, C.POINTER(C.c_int64), _int, _pvp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _i64, _pvp]),
+    "pb_multi_project_host": (_int, [_vp, _vp]),
+    "pb_multi_sigma": (_int, [_vp, _pd, _i64, C.POINTER(C.c_int64)]),
+    "pb_multi_all_reduce": (_int, [_vp, _pvp, _i64]),
+    "pb_multi_timer_start": (_int, [_vp]),
+    "pb_multi_timer_stop": (_int, [_vp, _pd]),
     "pb_probe_host_copy": (_int, [C.c_size_t, _int, _int, _pd]),
     "pb_flush_l2": (_int, [_vp]),
 }
@@ -176,7 +193,11 @@ class DeviceArray:
 class Context:
     """One GPU, one stream (pb_ctx)."""
 
-    def __init__(self, device=None):
+    def __init__(self, device=None, _borrowed=None):
+        self._owner = _borrowed is None
+        if _borrowed is not None:                      # a context owned by a MultiContext
+            self.h, self.device = C.c_void_p(_borrowed), int(device)
+            return
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", "0"))
         h = C.c_void_p()
@@ -241,9 +262,9 @@ class Context:
         return dict(sm_count=sm.value, cc=(ma.value, mi.value), mem_bytes=mem.value)
 
     def close(self):
-        if self.h:
+        if self.h and self._owner:
             lib().pb_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -261,3 +282,120 @@ def default_context():
     if _default is None or _default.h is None:
         _default = Context()
     return _default
+
+
+def _ptr_array(ptrs):
+    return (C.c_void_p * len(ptrs))(*[C.c_void_p(int(p) if p else None) for p in ptrs])
+
+
+def _i64_array(vals):
+    return (C.c_int64 * len(vals))(*[int(v) for v in vals])
+
+
+class MultiContext:
+    """n_gpus GPUs driven from THIS process (pb_multi: one context + one host thread per GPU, the library's own
+    peer-memory collectives over NVLink; no torch, no torchrun, no NCCL).  `device_ids` may repeat a device: logical
+    ranks on one GPU (tests on a one-GPU box)."""
+
+    def __init__(self, n_gpus, device_ids=None):
+        ids = None if device_ids is None else (C.c_int * n_gpus)(*[int(d) for d in device_ids])
+        h = C.c_void_p()
+        rc = lib().pb_multi_create(int(n_gpus), ids, C.byref(h))
+        if rc != PB_OK:
+            raise PodB200Error(f"pb_multi_create({n_gpus}) failed ({rc}): {lib().pb_last_error(None).decode()}")
+        self.h, self.n_gpus = h, int(n_gpus)
+        devs = list(device_ids) if device_ids is not None else list(range(n_gpus))
+        self.ctxs = [Context(devs[p], _borrowed=lib().pb_multi_ctx(h, p)) for p in range(n_gpus)]
+
+    def check(self, rc):
+        if rc != PB_OK:
+            msg = lib().pb_multi_last_error(self.h).decode()
+            raise _EXC.get(rc, PodB200Error)(f"libpodb200 (multi-GPU) error {rc}: {msg}")
+
+    def row_range(self, n_rows, rank):
+        lo, hi = C.c_int64(), C.c_int64()
+        self.check(lib().pb_multi_row_range(self.h, int(n_rows), int(rank), C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def sync(self):
+        self.check(lib().pb_multi_sync(self.h))
+
+    # ---- slabs resident in HBM (DeviceArray per rank, each owned by self.ctxs[p])
+    def pod(self, slabs, eps=0., n_L=0, mode="tsqr"):
+        """Row-sharded POD of per-GPU slabs; returns (V slabs, sigma, n_L)."""
+        n_st = slabs[0].shape[1]
+        rows = [s.shape[0] for s in slabs]
+        nl = C.c_int()
+        self.check(lib().pb_multi_pod(self.h, _ptr_array([s.ptr for s in slabs]), _i64_array(rows), n_st,
+                                      _i64_array([s.ld for s in slabs]), float(eps), int(n_L), POD_MODES[mode], C.byref(nl)))
+        V = [self.ctxs[p].alloc(max(rows[p], 1), nl.value) for p in range(self.n_gpus)]
+        self.check(lib().pb_multi_basis(self.h, _ptr_array([v.ptr for v in V]), None))
+        for p, v in enumerate(V):
+            v.shape = (rows[p], nl.value)
+        return V, self.sigma(), nl.value
+
+    def project(self, V, slabs):
+        """v (n x n_L) = sum_p (V_p^T U_p)^T; returned as the host copy of rank 0's (replicated) result."""
+        n, n_L = slabs[0].shape[1], V[0].shape[1]
+        out = [self.ctxs[p].alloc(n, n_L) for p in range(self.n_gpus)]
+        self.check(lib().pb_multi_project(self.h, _ptr_array([v.ptr for v in V]), None, n_L, _ptr_array([s.ptr for s in slabs]),
+                                          _i64_array([s.ld for s in slabs]), _i64_array([s.shape[0] for s in slabs]), n,
+                                          _ptr_array([o.ptr for o in out])))
+        return out
+
+    def sigma(self):
+        cnt = C.c_int64()
+        self.check(lib().pb_multi_sigma(self.h, None, 0, C.byref(cnt)))
+        sig = np.zeros(cnt.value)
+        self.check(lib().pb_multi_sigma(self.h, sig.ctypes.data, cnt.value, C.byref(cnt)))
+        return sig
+
+    # ---- host matrices (what the reference's calls are handed)
+    def pod_host(self, U, eps=0., n_L=0, mode="tsqr"):
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        n_h, n_st = U.shape
+        nl = C.c_int()
+        self.check(lib().pb_multi_pod_host(self.h, U.ctypes.data, n_h, n_st, n_st, float(eps), int(n_L), POD_MODES[mode], C.byref(nl)))
+        V = np.empty((n_h, nl.value))
+        self.check(lib().pb_multi_basis_host(self.h, V.ctypes.data, nl.value))
+        self._held = (n_h, n_st, nl.value)
+        return V, self.sigma()
+
+    def project_held(self):
+        """v of the matrix / basis the last pod_host left in HBM."""
+        n_h, n_st, n_L = self._held
+        v = np.empty((n_st, n_L))
+        self.check(lib().pb_multi_project_host(self.h, v.ctypes.data))
+        return v
+
+    def timer_start(self):
+        self.check(lib().pb_multi_timer_start(self.h))
+
+    def timer_stop(self):
+        v = C.c_double()
+        self.check(lib().pb_multi_timer_stop(self.h, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if self.h:
+            for c in self.ctxs:
+                c.h = None
+            lib().pb_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+_multi = {}
+
+
+def multi_context(n_gpus):
+    """Process-wide MultiContext over GPUs 0..n_gpus-1 (created on first use)."""
+    m = _multi.get(n_gpus)
+    if m is None or m.h is None:
+        m = _multi[n_gpus] = MultiContext(n_gpus)
+    return m

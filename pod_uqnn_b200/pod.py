@@ -39,15 +39,21 @@ def pod_sigma(ctx):
     return sig
 
 
-def perform_pod(U, eps=0., n_L=0, verbose=True, *, mode=DEFAULT_MODE, ctx=None, return_sigma=False):
+def perform_pod(U, eps=0., n_L=0, verbose=True, *, mode=DEFAULT_MODE, ctx=None, return_sigma=False, n_gpus=1):
     """Reference signature (pod.py:7).  numpy in -> numpy V (n_h, n_L), C-contiguous float64.
 
     A DeviceArray input stays on the device and returns a DeviceArray.
+    n_gpus > 1: the rows of U are sharded over GPUs 0..n_gpus-1 of this box from THIS process (pb_multi_pod_host:
+    concurrent slab uploads, the library's own NVLink collectives); tall matrices only (n_h >= n_st), wide or small
+    ones run on one GPU.
     """
-    ctx = ctx or _lib.default_context()
     on_device = isinstance(U, DeviceArray)
     if verbose:
         print("Contructing the reduced bases V")     # pod.py:38 (sic)
+    if n_gpus > 1 and not on_device and U.shape[0] >= max(U.shape[1], 4096 * n_gpus):
+        V, sig = _lib.multi_context(n_gpus).pod_host(U, eps, n_L, mode)
+        return (V, sig) if return_sigma else V
+    ctx = ctx or _lib.default_context()
     if on_device:
         Vd, sig = pod_device(ctx, U, eps, n_L, mode)
         return (Vd, sig) if return_sigma else Vd
@@ -81,11 +87,23 @@ def pod_host(ctx, U, eps=0., n_L=0, mode=DEFAULT_MODE):
     return V, pod_sigma(ctx)
 
 
-def project_to_v(V, U, *, ctx=None, reuse_slab=False):
+def project_to_v(V, U, *, ctx=None, reuse_slab=False, n_gpus=1):
     """v = (V.T.dot(U)).T (podnnmodel.py:435-437) as a module-level call: numpy in, numpy (n, n_L) out.
 
     reuse_slab=True: `U` is the array the last perform_pod on this context was given and `V` what it returned; both
-    are still resident in HBM and are not uploaded again (the caller vouches that U has not been modified since)."""
+    are still resident in HBM and are not uploaded again (the caller vouches that U has not been modified since).
+    n_gpus > 1: row-sharded over the GPUs of this process' MultiContext (the partial products are summed over NVLink)."""
+    if n_gpus > 1 and U.shape[0] >= max(U.shape[1], 4096 * n_gpus):
+        m = _lib.multi_context(n_gpus)
+        if reuse_slab:
+            if getattr(m, "_held", None) != (U.shape[0], U.shape[1], V.shape[1]):
+                raise ValueError("project_to_v(reuse_slab=True): the multi-GPU context does not hold this matrix")
+            return m.project_held()
+        m._held = None
+        rng = [m.row_range(U.shape[0], p) for p in range(n_gpus)]
+        Us = [m.ctxs[p].to_device(U[lo:hi]) for p, (lo, hi) in enumerate(rng)]
+        Vs = [m.ctxs[p].to_device(V[lo:hi]) for p, (lo, hi) in enumerate(rng)]
+        return m.project(Vs, Us)[0].download()
     ctx = ctx or _lib.default_context()
     L = _lib.lib()
     n_h, n = U.shape

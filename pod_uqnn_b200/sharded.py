@@ -56,13 +56,13 @@ def _max_over_ranks(backend, value, group=None):
     return int(t.item())
 
 
-def pod_sharded_tsqr(backend, A_local, eps=0., n_L=0, group=None):
+def pod_sharded_tsqr(backend, A_local, eps=0., n_L=0, group=None, full=False):
     """TSQR mode: one leaf per rank.  F_p = the rank-revealing Householder factor of A_p (pb_tsqr_factor: block
     pivoting, stops at the numerical rank; Q not formed), all-gather of the first max_p rows(F_p) rows, the factor of
     the stack and its Jacobi SVD are replicated (same bits on every rank, hence the same rank and factors),
     V_p = A_p Z / sigma locally (pod.py:42-45).  eps == 0 without n_L asks for every mode: nothing may be dropped, the
-    plain triangular R factors are used.  Returns (V_local, sigma, n_L)."""
-    if eps == 0. and n_L == 0:
+    plain triangular R factors are used (also with full=True, the "tsqr_full" mode).  Returns (V_local, sigma, n_L)."""
+    if full or (eps == 0. and n_L == 0):
         R = backend.tsqr_r(A_local)
         stack = _all_gather_stack(backend, R, group)
         if stack is not R:
@@ -85,10 +85,10 @@ def pod_sharded(backend, A_local, eps=0., n_L=0, mode="gram", group=None, A_host
 
     `A_host` (address of this rank's slab in pinned host memory, same shape as `A_local`): the slab is uploaded into
     `A_local` in row chunks overlapped with the chunk Grams (pb_gram_host) instead of being read from HBM."""
-    if mode == "tsqr":
+    if mode in ("tsqr", "tsqr_full"):
         if A_host is not None:
             backend.upload(A_host, A_local)
-        return pod_sharded_tsqr(backend, A_local, eps, n_L, group)
+        return pod_sharded_tsqr(backend, A_local, eps, n_L, group, full=(mode == "tsqr_full"))
     G = backend.gram(A_local) if A_host is None else backend.gram_host(A_host, A_local)
     backend.reduce(G, group)
     n_L_out, keep = backend.pod_from_gram(G, eps, n_L, mode)
@@ -98,7 +98,7 @@ def pod_sharded(backend, A_local, eps=0., n_L=0, mode="gram", group=None, A_host
         backend.reduce(G2, group)
         n_L_out = backend.pass2_finish(G2, eps, n_L)
     V = backend.basis(A_local, Y, n_L_out)
-    if keep > 0 and backend.refine_steps() > 0:
+    if keep > 0 and _max_over_ranks(backend, backend.refine_steps(), group) > 0:     # one decision for all ranks
         # gram2 tolerance safety (csrc/api.cu, "subspace refinement"): one step of subspace iteration with the matrix
         # itself -- two more all-reduces (the n_st x n_L projection block and an n_L x n_L Gram)
         B = backend.project(V, A_local)
@@ -125,6 +125,7 @@ class CudaBackend:
         self.dev = torch.device("cuda", ctx.device)
         self.L = _lib.lib()
         self._cache = {}
+        self.qr_stats = {}
         # the library and NCCL share one torch stream: the all-reduces are ordered against the kernels on the
         # device (NCCL's stream waits on / is waited for by this stream through events), no host synchronisation.
         # It is made torch's CURRENT stream for the life of the backend (restored by close()): a `with
@@ -183,7 +184,14 @@ class CudaBackend:
         R = self._empty(m, m)
         ptr, ld = (A.data_ptr(), A.stride(0)) if is_t else (A.ptr, A.ld)
         self.ctx.check(self.L.pb_tsqr_r(self.ctx.h, ptr, rows, m, ld, R.data_ptr()))
+        self._note_qr(is_t)
         return R
+
+    def _note_qr(self, stacked):
+        """(panels, factor rows, Householder flops) of the factorisation just run, kept per stage for reporting."""
+        p, f, fl = C.c_int64(), C.c_int64(), C.c_double()
+        self.ctx.check(self.L.pb_tsqr_stats(self.ctx.h, C.byref(p), C.byref(f), C.byref(fl)))
+        self.qr_stats["stack" if stacked else "local"] = (p.value, f.value, fl.value)
 
     def tsqr_factor(self, A):
         """Rank-revealing factor of a DeviceArray slab or of a torch (rows x m) stack: (F torch tensor m x m, rows used)."""
@@ -193,6 +201,7 @@ class CudaBackend:
         ptr, ld = (A.data_ptr(), A.stride(0)) if is_t else (A.ptr, A.ld)
         fr = C.c_int64()
         self.ctx.check(self.L.pb_tsqr_factor(self.ctx.h, ptr, rows, m, ld, F.data_ptr(), C.byref(fr)))
+        self._note_qr(is_t)
         return F, fr.value
 
     def pod_from_factor(self, F, rows, eps, n_L):
