@@ -100,7 +100,7 @@ SIGNATURES = {
     "pb_multi_basis_host": (_int, [_vp, _vp, _i64]),
     "pb_multi_project": (_int, [_vp, _pvp, C.POINTER(C.c_int64), _int, _pvp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _i64, _pvp]),
     "pb_multi_project_host": (_int, [_vp, _vp]),
-    "pb_multi_sigma": (_int, [_vp, _pd, _i64, C.POINTER(C.c_int64)]),
+    "pb_multi_sigma": (_int, [_vp, _vp, _i64, C.POINTER(C.c_int64)]),
     "pb_multi_all_reduce": (_int, [_vp, _pvp, _i64]),
     "pb_multi_timer_start": (_int, [_vp]),
     "pb_multi_timer_stop": (_int, [_vp, _pd]),

@@ -82,7 +82,8 @@ def test_multi_pod_matches_reference(multi, ctx, name, field, mode):
     V = np.vstack([Vs[p].download() for p in range(P)])
     V1, sig1 = perform_pod(U, eps, 0, False, mode=mode, ctx=ctx, return_sigma=True)
     assert V.shape == V1.shape
-    assert cmp.sigma_error(sig[:n_L], sig1[:n_L]) <= 1e-12
+    # one Gram pass resolves small singular values only to eps sigma_1^2 / sigma_k: a different summation order shows there
+    assert cmp.sigma_error(sig[:n_L], sig1[:n_L]) <= (cmp.TOL_SIGMA_REL if mode == "gram" else 1e-12)
     assert cmp.largest_principal_angle(V, V1) <= (1e-6 if mode == "gram" else 1e-9)
     if mode != "gram":
         assert V.shape == g["V"].shape
