@@ -39,6 +39,25 @@ int pb_reserve_int(pb_ctx* ctx, int** p, size_t* cap, size_t elems) {
     return PB_OK;
 }
 
+int pbi_smem_optin(pb_ctx* ctx, const void* func, size_t need) {
+    static std::mutex mu;
+    static std::vector<std::pair<std::pair<const void*, int>, size_t>> done;    // ((function, device), limit)
+    std::lock_guard<std::mutex> g(mu);
+    size_t limit = 0;
+    for (auto& e : done) if (e.first.first == func && e.first.second == ctx->device) { limit = e.second; break; }
+    if (!limit) {
+        cudaFuncAttributes a;
+        PB_CUDA(ctx, cudaFuncGetAttributes(&a, func));
+        int optin = 0;
+        PB_CUDA(ctx, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+        limit = (size_t)optin - a.sharedSizeBytes;
+        PB_CUDA(ctx, cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+        done.push_back({{func, ctx->device}, limit});
+    }
+    if (need > limit) PB_FAIL(ctx, PB_ERR_SHAPE, "kernel needs %zu bytes of shared memory, the device offers %zu", need, limit);
+    return PB_OK;
+}
+
 namespace {
 // Stage timer: two events on the context stream, NO host synchronisation -- pb_last_ms() waits for the stop event when the
 // number is asked for.  (A synchronising timer cost one pipeline bubble per stage: 6 of the 16 host syncs of a C2 step.)

@@ -102,6 +102,11 @@ const char* pb_set_global_error(const std::string& s);
 #define PB_LAUNCH_CHECK(ctx) do { (ctx)->launches++; cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { \
     PB_FAIL(ctx, PB_ERR_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); } } while (0)
 
+// Opt `func` in to the device's maximal dynamic shared memory (once per function and device, cached) and check that
+// `need` fits.  The limit is raised to the maximum, never to `need`: an exact size set per launch is a race when two
+// contexts drive the same device from two threads (one lowers the limit between the other's attribute call and launch).
+int pbi_smem_optin(pb_ctx* ctx, const void* func, size_t need);
+
 // grow-on-demand device buffer
 int pb_reserve(pb_ctx* ctx, double** p, size_t* cap, size_t elems);
 

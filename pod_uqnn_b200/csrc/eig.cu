@@ -520,7 +520,7 @@ int pbi_jacobi_factor(pb_ctx* ctx, double* At, int64_t m, int r, const double* s
     const double tol = ctx->eig_jacobi_tol > 0. ? ctx->eig_jacobi_tol : std::max(4., sqrt((double)m)) * DBL_EPSILON;
     ctx->eig_jacobi_tol = 0.;
     size_t jac_smem = sizeof(double) * 2 * JP * JPX;
-    PB_CUDA(ctx, cudaFuncSetAttribute(jacobi_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jac_smem));
+    PB_TRY(pbi_smem_optin(ctx, (const void*)jacobi_pair_kernel, (size_t)(jac_smem)));
     int sweeps = 0; bool converged = false;
     const bool trust_single = ctx->eig_trust_single_pair && nb == 2;
     ctx->eig_trust_single_pair = false;
@@ -549,7 +549,7 @@ int pbi_jacobi_factor(pb_ctx* ctx, double* At, int64_t m, int r, const double* s
     PB_LAUNCH_CHECK(ctx);
     int npow2 = 1; while (npow2 < nvec) npow2 <<= 1;
     size_t sort_smem = (sizeof(double) + sizeof(int)) * (size_t)npow2;
-    PB_CUDA(ctx, cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+    PB_TRY(pbi_smem_optin(ctx, (const void*)sort_kernel, (size_t)(sort_smem)));
     sort_kernel<<<1, 1024, sort_smem, ctx->stream>>>(nrm2_scr, nvec, npow2, shift_dev, sig_dev, nrm_dev, (int)m, perm_dev, ctx->d_int + 3, 0, 0, 0);
     PB_LAUNCH_CHECK(ctx);
     if (sweeps_out) *sweeps_out = sweeps;
@@ -586,7 +586,7 @@ int pbi_eig_psd(pb_ctx* ctx, const double* G, int64_t m, double tol_rel, double 
     if (k_start >= 0) {
         int grid = (int)std::min<int64_t>(ctx->sm_count, (m + CHOL_ROWS - 1) / CHOL_ROWS);
         size_t chol_smem = sizeof(double) * (size_t)m;
-        PB_CUDA(ctx, cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
+        PB_TRY(pbi_smem_optin(ctx, (const void*)chol_kernel, (size_t)(chol_smem)));
         int occ = 0;
         PB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol_kernel, CHOL_THREADS, chol_smem));
         if (occ < 1) PB_FAIL(ctx, PB_ERR_CUDA, "eig_psd: Cholesky kernel does not fit an SM");
@@ -731,7 +731,7 @@ int pbi_eig_psd_batched(pb_ctx* ctx, const double* G_all, int64_t m, int batch, 
     const int nvec = (int)cap_rows;
     const double tol = std::max(4., sqrt((double)m)) * DBL_EPSILON;
     size_t jac_smem = sizeof(double) * 2 * JP * JPX;
-    PB_CUDA(ctx, cudaFuncSetAttribute(jacobi_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jac_smem));
+    PB_TRY(pbi_smem_optin(ctx, (const void*)jacobi_pair_kernel, (size_t)(jac_smem)));
     int sweeps = 0; bool converged = false;
     const bool trust_single = ctx->eig_trust_single_pair && nb == 2;
     ctx->eig_trust_single_pair = false;
@@ -753,7 +753,7 @@ int pbi_eig_psd_batched(pb_ctx* ctx, const double* G_all, int64_t m, int batch, 
     PB_LAUNCH_CHECK(ctx);
     int npow2 = 1; while (npow2 < nvec) npow2 <<= 1;
     size_t sort_smem = (sizeof(double) + sizeof(int)) * (size_t)npow2;
-    PB_CUDA(ctx, cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+    PB_TRY(pbi_smem_optin(ctx, (const void*)sort_kernel, (size_t)(sort_smem)));
     // r_eff is not needed for the batch: reuse the tail of the scratch as a dump (ints)
     int* r_eff = reinterpret_cast<int*>(shift + batch);
     sort_kernel<<<batch, 1024, sort_smem, ctx->stream>>>(nrm2, nvec, npow2, shift, sig_all, nrm_all, (int)m, perm_all, r_eff,

@@ -434,7 +434,7 @@ __global__ void transpose_kernel(const double* __restrict__ in, int64_t rows, in
 
 template <typename K>
 int set_smem(pb_ctx* ctx, K kernel, size_t bytes) {
-    PB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    PB_TRY(pbi_smem_optin(ctx, (const void*)kernel, (size_t)(bytes)));
     return PB_OK;
 }
 

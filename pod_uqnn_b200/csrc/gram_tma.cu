@@ -293,18 +293,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static const EncodeTiledFn fn = []() -> EncodeTiledFn {      // initialised once, thread-safe (several contexts may call at once)
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-        else
-            cudaGetLastError();
-    }
+            return reinterpret_cast<EncodeTiledFn>(p);
+        cudaGetLastError();
+        return nullptr;
+    }();
     return fn;
 }
 
@@ -337,7 +334,7 @@ int pbi_gram_tma(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int64_t 
     const int tiles_n = (int)((ka + 127) / 128);
     const int tiles = tiles_n * (tiles_n + 1) / 2;
     const size_t smem = (size_t)TSTAGES * STAGE_BYTES + 2 * TSTAGES * sizeof(uint64_t) + 1024;
-    PB_CUDA(ctx, cudaFuncSetAttribute(gram_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PB_TRY(pbi_smem_optin(ctx, (const void*)gram_tma_kernel, (size_t)(smem)));
     if (time_it) cudaEventRecord(ctx->evk0, ctx->stream);
     gram_tma_kernel<<<dim3(tiles, splits), TMA_THREADS, smem, ctx->stream>>>(map, (int)ka, rows, rows_per_split, ws, ka,
                                                                             split_stride, tiles_n);
@@ -484,7 +481,7 @@ int pbi_gram_streamk(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int6
     const int* d_tile_src = d_tile_off + (T + 1);
     PB_TRY(pb_reserve(ctx, &ctx->ws, &ctx->ws_bytes, (size_t)plan.nslots * 128 * 128));
     const size_t smem = (size_t)TSTAGES * STAGE_BYTES + 2 * TSTAGES * sizeof(uint64_t) + 1024;
-    PB_CUDA(ctx, cudaFuncSetAttribute(gram_streamk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PB_TRY(pbi_smem_optin(ctx, (const void*)gram_streamk_kernel, (size_t)(smem)));
     if (time_it) cudaEventRecord(ctx->evk0, ctx->stream);
     gram_streamk_kernel<<<P, TMA_THREADS, smem, ctx->stream>>>(map, d_segs, d_seg_begin, ctx->ws);
     PB_LAUNCH_CHECK(ctx);

@@ -443,7 +443,7 @@ extern "C" int pb_ensemble_predict(pb_ctx* ctx, int n_members, int n_layers, con
     pack_weights_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(weights_dev, pk, n_members, n_layers, a, src);
     PB_LAUNCH_CHECK(ctx);
     const size_t smem = sizeof(double) * (size_t)(MP * PACT + RING * CHUNK_DOUBLES) + 2 * RING * sizeof(uint64_t);
-    PB_CUDA(ctx, cudaFuncSetAttribute(ensemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PB_TRY(pbi_smem_optin(ctx, (const void*)ensemble_kernel, (size_t)(smem)));
     ensemble_kernel<<<grid, MLP_THREADS, smem, ctx->stream>>>(a);
     PB_LAUNCH_CHECK(ctx);
     cudaEventRecord(ctx->ev1, ctx->stream);

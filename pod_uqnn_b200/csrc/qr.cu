@@ -1017,11 +1017,11 @@ int qr_leaf(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, 
     static const int stage_env = getenv("PB_QR_STAGE") ? atoi(getenv("PB_QR_STAGE")) : 1;
     static const int pivot_env = getenv("PB_QR_PIVOT") ? atoi(getenv("PB_QR_PIVOT")) : 1;
     const size_t tt_smem = sizeof(double) * 2 * QNB * (QNB + 1);
-    PB_CUDA(ctx, cudaFuncSetAttribute(qr_tt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tt_smem));
+    PB_TRY(pbi_smem_optin(ctx, (const void*)qr_tt_kernel, (size_t)(tt_smem)));
     if (rr) {
         qr_iota_kernel<<<(unsigned)((mp + 255) / 256), 256, 0, ctx->stream>>>(colperm, (int)mp);
         PB_LAUNCH_CHECK(ctx);
-        PB_CUDA(ctx, cudaFuncSetAttribute(qr_pivot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * mp)));
+        PB_TRY(pbi_smem_optin(ctx, (const void*)qr_pivot_kernel, (size_t)((sizeof(double) * mp))));
     }
     int64_t K = mp;                                                   // rows of the factor (panels actually run)
     int panels = 0;
@@ -1063,7 +1063,7 @@ int qr_leaf(pb_ctx* ctx, const double* A, int64_t rows, int64_t m, int64_t lda, 
         int64_t rpc = (rowsW - J + grid - 1) / grid; rpc = (rpc + 7) / 8 * 8;       // as the kernel computes it
         const int use_smem = (stage_env && rpc <= RS_MAX) ? 1 : 0;
         const size_t smem = use_smem ? sizeof(double) * (size_t)rpc * QP : 0;
-        PB_CUDA(ctx, cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PB_TRY(pbi_smem_optin(ctx, (const void*)qr_panel_kernel, (size_t)(smem)));
         PB_TRY(coop_grid(ctx, (const void*)qr_panel_kernel, smem, grid, &grid));
         QrPanelArgs pa{W, ldw, rowsW, (int)J, nbo, tau + J, part, diag, zpart, zfin, use_smem};
         void* args[] = {&pa};
@@ -1128,7 +1128,7 @@ int pbi_qrcp_factor(pb_ctx* ctx, double* At, int64_t m, int64_t nrows, int64_t l
     const int mg_max = (ngroups + grid - 1) / grid;
     if (mg_max > 64) PB_FAIL(ctx, PB_ERR_SHAPE, "tsqr: %lld columns exceed the pivoted QR's limit", (long long)m);
     const size_t smem = sizeof(double) * ((size_t)(nrows + 7) / 8 * 8 + (size_t)mg_max * 8);
-    PB_CUDA(ctx, cudaFuncSetAttribute(qrcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PB_TRY(pbi_smem_optin(ctx, (const void*)qrcp_kernel, (size_t)(smem)));
     PB_TRY(coop_grid(ctx, (const void*)qrcp_kernel, smem, grid, &grid));
     // scratch: cand_val [2*G] | diagval [m] | then ints: cand_idx [2*G] | done_step [ldm]
     const size_t n_dbl = 2 * (size_t)Gmax + (size_t)m + 8;

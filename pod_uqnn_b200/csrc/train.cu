@@ -825,7 +825,7 @@ inline bool al16(const void* p, int64_t ld, int64_t stride) {
 
 template <typename K>
 int set_smem(pb_ctx* ctx, K kernel, size_t bytes) {
-    PB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    PB_TRY(pbi_smem_optin(ctx, (const void*)kernel, (size_t)(bytes)));
     return PB_OK;
 }
 
