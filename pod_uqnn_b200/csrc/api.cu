@@ -44,15 +44,17 @@ int pbi_smem_optin(pb_ctx* ctx, const void* func, size_t need) {
     static std::vector<std::pair<std::pair<const void*, int>, size_t>> done;    // ((function, device), limit)
     std::lock_guard<std::mutex> g(mu);
     size_t limit = 0;
-    for (auto& e : done) if (e.first.first == func && e.first.second == ctx->device) { limit = e.second; break; }
+    int device = 0;
+    if (ctx) device = ctx->device; else PB_CUDA(ctx, cudaGetDevice(&device));      // (configuration calls pass no context)
+    for (auto& e : done) if (e.first.first == func && e.first.second == device) { limit = e.second; break; }
     if (!limit) {
         cudaFuncAttributes a;
         PB_CUDA(ctx, cudaFuncGetAttributes(&a, func));
         int optin = 0;
-        PB_CUDA(ctx, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+        PB_CUDA(ctx, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         limit = (size_t)optin - a.sharedSizeBytes;
         PB_CUDA(ctx, cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
-        done.push_back({{func, ctx->device}, limit});
+        done.push_back({{func, device}, limit});
     }
     if (need > limit) PB_FAIL(ctx, PB_ERR_SHAPE, "kernel needs %zu bytes of shared memory, the device offers %zu", need, limit);
     return PB_OK;
