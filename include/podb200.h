@@ -276,6 +276,10 @@ int  pb_multi_pod(pb_multi* m, const double* const* U_dev, const int64_t* rows, 
                   double eps, int n_L_in, int mode, int* n_L);
 int  pb_multi_pod_host(pb_multi* m, const double* U_host, int64_t n_h, int64_t n_st, int64_t ldu_host,
                        double eps, int n_L_in, int mode, int* n_L);
+/* two-step POD (pod.py:51-68) of row-sharded slabs with sample-major columns (n_st = n_t n_s); needs rows[p] >= n_t and
+ * a tall packed basis (n_h >= sum r_k); pb_multi_basis afterwards */
+int  pb_multi_fast_pod(pb_multi* m, const double* const* U_dev, const int64_t* rows, int n_t, int64_t n_s, const int64_t* ldu,
+                       double eps, double eps_init, int mode, int* n_L, int* ranks_host);
 int  pb_multi_basis(pb_multi* m, double* const* V_dev, const int64_t* ldv);
 int  pb_multi_basis_host(pb_multi* m, double* V_host, int64_t ldv_host);
 int  pb_multi_project(pb_multi* m, const double* const* V_dev, const int64_t* ldv, int n_L, const double* const* U_dev,

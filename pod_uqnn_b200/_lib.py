@@ -96,6 +96,7 @@ SIGNATURES = {
     "pb_multi_sync": (_int, [_vp]),
     "pb_multi_pod": (_int, [_vp, _pvp, C.POINTER(C.c_int64), _i64, C.POINTER(C.c_int64), _dbl, _int, _int, _pi]),
     "pb_multi_pod_host": (_int, [_vp, _vp, _i64, _i64, _i64, _dbl, _int, _int, _pi]),
+    "pb_multi_fast_pod": (_int, [_vp, _pvp, C.POINTER(C.c_int64), _int, _i64, C.POINTER(C.c_int64), _dbl, _dbl, _int, _pi, _pi]),
     "pb_multi_basis": (_int, [_vp, _pvp, C.POINTER(C.c_int64)]),
     "pb_multi_basis_host": (_int, [_vp, _vp, _i64]),
     "pb_multi_project": (_int, [_vp, _pvp, C.POINTER(C.c_int64), _int, _pvp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _i64, _pvp]),
@@ -333,6 +334,19 @@ class MultiContext:
         for p, v in enumerate(V):
             v.shape = (rows[p], nl.value)
         return V, self.sigma(), nl.value
+
+    def fast_pod(self, slabs, n_t, n_s, eps, eps_init, mode="tsqr"):
+        """Two-step POD (pod.py:51-68) of row-sharded slabs with sample-major columns; returns (V slabs, ranks, n_L)."""
+        rows = [s.shape[0] for s in slabs]
+        nl, ranks = C.c_int(), (C.c_int * n_s)()
+        self.check(lib().pb_multi_fast_pod(self.h, _ptr_array([s.ptr for s in slabs]), _i64_array(rows), int(n_t), int(n_s),
+                                           _i64_array([s.ld for s in slabs]), float(eps), float(eps_init), POD_MODES[mode],
+                                           C.byref(nl), ranks))
+        V = [self.ctxs[p].alloc(max(rows[p], 1), nl.value) for p in range(self.n_gpus)]
+        self.check(lib().pb_multi_basis(self.h, _ptr_array([v.ptr for v in V]), None))
+        for p, v in enumerate(V):
+            v.shape = (rows[p], nl.value)
+        return V, np.array(ranks[:], dtype=np.int64), nl.value
 
     def project(self, V, slabs):
         """v (n x n_L) = sum_p (V_p^T U_p)^T; returned as the host copy of rank 0's (replicated) result."""

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <algorithm>
 #include <mutex>
+#include <functional>
 #include <condition_variable>
 #include <chrono>
 #if defined(__SSE2__)
@@ -968,7 +969,8 @@ __global__ void pack_bases_kernel(const double* __restrict__ T, int64_t rows, in
 
 // Stage 1 of the two-step POD as ONE batch: every kernel below is launched once for all samples.
 int fast_pod_stage1_batched(pb_ctx* ctx, const double* U, int64_t n_h, int n_t, int64_t n_s, int64_t ldu,
-                            double eps_init, int mode, int* ranks, int64_t ldf, int64_t* total) {
+                            double eps_init, int mode, int* ranks, int64_t ldf, int64_t* total,
+                            const std::function<int(double*, int64_t)>* reduce = nullptr) {
     const int64_t m = n_t; const int B = (int)n_s;
     const int64_t ldm = (m + 7) / 8 * 8, cap_rows = (m + 31) / 32 * 32;
     enum { G = 0, AT, SIG, NRM, SCR, BM, T1, T2 };
@@ -985,6 +987,7 @@ int fast_pod_stage1_batched(pb_ctx* ctx, const double* U, int64_t n_h, int n_t, 
     int *perm = ctx->fp_ibuf, *r_dev = perm + (size_t)B * cap_rows, *nl_dev = r_dev + B, *off_dev = nl_dev + B;
     const bool full = (mode == PB_POD_ACCURATE) || eps_init == 0.;
     PB_TRY(pbi_gram_batched(ctx, U, ldu, m, n_t, n_h, Gall, m * m, B));
+    if (reduce) PB_TRY((*reduce)(Gall, (int64_t)B * m * m));          // row-sharded: sum of the per-GPU partial Grams
     PB_TRY(pbi_eig_psd_batched(ctx, Gall, m, B, full ? 0. : 4. * DBL_EPSILON, full ? 2. * (double)m * DBL_EPSILON : 0.,
                                At, sig, nrm, perm, r_dev, scr, nullptr, 40));
     const double* basis_src = Tm;
@@ -999,6 +1002,7 @@ int fast_pod_stage1_batched(pb_ctx* ctx, const double* U, int64_t n_h, int n_t, 
         PB_TRY(pbi_factor_to_right_batched(ctx, At, m, (int)m, B, perm, nrm, nullptr, Bm, m * m));
         PB_TRY(pbi_gemm_nn_batched(ctx, U, ldu, n_t, n_h, m, Bm, m, m * m, m, Tm, m, n_h * m, B));       // Y
         PB_TRY(pbi_gram_batched(ctx, Tm, m, m, n_h * m, n_h, Gall, m * m, B));                            // G2
+        if (reduce) PB_TRY((*reduce)(Gall, (int64_t)B * m * m));
         PB_TRY(pbi_eig_psd_batched(ctx, Gall, m, B, 0., 0., At, sig, nrm, perm, r_dev, scr, nullptr, 40));
         PB_TRY(pbi_rank_batched(ctx, sig, m, B, eps_init, nl_dev));
         PB_TRY(pbi_factor_to_right_batched(ctx, At, m, (int)m, B, perm, nrm, sig, Bm, m * m));
@@ -1027,6 +1031,20 @@ int fast_pod_stage1_batched(pb_ctx* ctx, const double* U, int64_t n_h, int n_t, 
     return PB_OK;
 }
 }  // namespace
+
+}  // extern "C"
+// Row-sharded stage 1 (multi.cu): the local rows of every sample's basis, packed into ctx->Uf (n_h_loc x ldf, ldf =
+// n_t n_s); `reduce` sums the batched Gram partials over the GPUs, the per-sample eigensolves are replicated.
+int pbi_fast_pod_stage1(pb_ctx* ctx, const double* U, int64_t n_h_loc, int n_t, int64_t n_s, int64_t ldu, double eps_init,
+                        int mode, int* ranks_host, int64_t* total, const std::function<int(double*, int64_t)>& reduce) {
+    const int64_t ldf = (int64_t)n_t * n_s;
+    PB_TRY(pb_reserve(ctx, &ctx->Uf, &ctx->Uf_cap, (size_t)std::max<int64_t>(n_h_loc, 1) * ldf));
+    PB_TRY(fast_pod_stage1_batched(ctx, U, n_h_loc, n_t, n_s, ldu, eps_init, mode == PB_POD_TSQR ? PB_POD_ACCURATE : mode,
+                                   ranks_host, ldf, total, &reduce));
+    ctx->uf_rows = n_h_loc; ctx->uf_cols = *total; ctx->uf_ld = ldf;
+    return PB_OK;
+}
+extern "C" {
 
 int pb_fast_pod(pb_ctx* ctx, const double* U, int64_t n_h, int n_t, int64_t n_s, int64_t ldu,
                 double eps, double eps_init, int mode, int* n_L, int* ranks_host) {

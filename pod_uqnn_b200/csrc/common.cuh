@@ -6,6 +6,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <functional>
 #include "../../include/podb200.h"
 
 constexpr int PB_STAGE_SLOTS = 3;
@@ -149,6 +150,8 @@ int pbi_rank(pb_ctx* ctx, const double* sig_dev, int64_t count, double eps, int*
 int pbi_factor_to_right(pb_ctx* ctx, const double* At, int64_t m, int k, const int* perm_dev,
                         const double* nrm_dev, const double* sig_dev, double* B, int64_t ldb);
 int pb_reserve_int(pb_ctx* ctx, int** p, size_t* cap, size_t elems);
+int pbi_fast_pod_stage1(pb_ctx* ctx, const double* U, int64_t n_h_loc, int n_t, int64_t n_s, int64_t ldu, double eps_init,
+                        int mode, int* ranks_host, int64_t* total, const std::function<int(double*, int64_t)>& reduce);
 // batched variants (two-step POD)
 int pbi_gram_batched(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int64_t sA, int64_t rows,
                      double* C, int64_t sC, int count);

@@ -462,7 +462,7 @@ int pbi_gram_tma(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int64_t 
 int pbi_gram_streamk(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int64_t rows, double* C, int64_t ldc,
                      bool time_it);
 namespace {
-bool g_time_tn = false;   // set per call by pbi_gemm_tn (contexts are single-threaded)
+thread_local bool g_time_tn = false;   // set per call by pbi_gemm_tn; thread-local: several contexts may run in parallel threads (multi.cu)
 
 struct Batch { int count = 1; int64_t sA = 0, sB = 0, sC = 0; };
 

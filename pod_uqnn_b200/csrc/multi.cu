@@ -425,6 +425,51 @@ int pb_multi_pod_host(pb_multi* m, const double* U_host, int64_t n_h, int64_t n_
     return PB_OK;
 }
 
+// Two-step POD (pod.py:51-68), row-sharded: per-sample PODs with eps_init as ONE batch on every GPU's rows -- the batched
+// n_t x n_t Gram partials are summed over the GPUs (one all-reduce per pass), the small eigensolves are replicated --
+// then the global POD of the packed bases (n_h x sum r_k, tall) through the sharded path above.  ranks_host (nullable):
+// the per-sample ranks.  pb_multi_basis afterwards gives every GPU's rows of V.
+int pb_multi_fast_pod(pb_multi* m, const double* const* U_dev, const int64_t* rows, int n_t, int64_t n_s, const int64_t* ldu,
+                      double eps, double eps_init, int mode, int* n_L, int* ranks_host) {
+    if (!m || !U_dev || !rows || !n_L) return PB_ERR_ARG;
+    if (n_t <= 0 || n_s <= 0 || n_t > 1024 || n_s >= 65536) { m->err = "pb_multi_fast_pod: bad shape (n_t in [1, 1024], n_s < 65536)"; return PB_ERR_SHAPE; }
+    if (mode < PB_POD_GRAM || mode > PB_POD_TSQR) { m->err = "pb_multi_fast_pod: unknown mode"; return PB_ERR_ARG; }
+    int64_t n_h = 0;
+    for (int p = 0; p < m->P; ++p) {
+        if (rows[p] < n_t) { m->err = "pb_multi_fast_pod: every GPU needs at least n_t rows"; return PB_ERR_SHAPE; }
+        n_h += rows[p];
+    }
+    const int64_t n_st = (int64_t)n_t * n_s;
+    m->have = false; m->host_slabs = false;
+    std::vector<std::vector<int>> ranks(m->P, std::vector<int>((size_t)n_s, 0));
+    std::vector<int64_t> total(m->P, 0);
+    PB_TRY(run(m, [&, eps, eps_init, mode](int p) {
+        pb_ctx* c = m->ctx[p];
+        bool peer_abort = false;       // a peer failed before the collective: this rank has already taken part in that agreement
+        std::function<int(double*, int64_t)> reduce = [m, p, &peer_abort](double* buf, int64_t count) {
+            int rc = agree(m, p, PB_OK);
+            if (rc != PB_OK) { peer_abort = true; return rc; }
+            return all_reduce(m, p, buf, count);
+        };
+        {
+            int rc = pbi_fast_pod_stage1(c, U_dev[p], rows[p], n_t, n_s, ldu ? ldu[p] : n_st, eps_init, mode, ranks[p].data(), &total[p], reduce);
+            if (peer_abort) return rc;
+            MB_STEP(rc);
+        }
+        // stage 2 on the packed bases (identical column count on every rank: the eigensolves are replicated)
+        if (n_h < total[p]) { c->err = "pb_multi_fast_pod: the packed bases are wide (sum r_k > n_h): run the global stage on one GPU"; MB_STEP(PB_ERR_SHAPE); }
+        if (total[p] > 8192) { c->err = "pb_multi_fast_pod: sum r_k exceeds 8192"; MB_STEP(PB_ERR_SHAPE); }
+        m->U[p] = c->Uf; m->rows[p] = rows[p]; m->ldu[p] = n_st;
+        if (p == 0) { m->n_h = n_h; m->n_st = total[0]; m->mode = mode; }
+        MB_STEP(PB_OK);                                     // (publishes n_st before pod_rank reads it)
+        return pod_rank(m, p, nullptr, 0, 0, eps, 0, mode);
+    }));
+    m->have = true;
+    if (ranks_host) for (int64_t z = 0; z < n_s; ++z) ranks_host[z] = ranks[0][z];
+    *n_L = m->n_L;
+    return PB_OK;
+}
+
 int pb_multi_basis(pb_multi* m, double* const* V_dev, const int64_t* ldv) {
     if (!m || !V_dev) return PB_ERR_ARG;
     if (!m->have) { m->err = "pb_multi_basis: no decomposition (call pb_multi_pod first)"; return PB_ERR_ARG; }

@@ -57,7 +57,7 @@ def split_dataset(X_v, v, test_size):
 
 
 class PodnnModel:
-    def __init__(self, resdir, n_v, x_mesh, n_t, *, ctx=None, pod_mode=DEFAULT_MODE):
+    def __init__(self, resdir, n_v, x_mesh, n_t, *, ctx=None, pod_mode=DEFAULT_MODE, n_gpus=1, multi=None):
         self.n_v, self.x_mesh = n_v, x_mesh
         self.n_xyz = x_mesh.shape[0]
         self.n_h = self.n_v * x_mesh.shape[0]
@@ -74,7 +74,20 @@ class PodnnModel:
         self.pod_mode = pod_mode
         self._ctx = ctx
         self._V_dev = None
+        # n_gpus > 1: snapshots, POD, projection and pod_sig run row-sharded (by dof) over GPUs 0..n_gpus-1 from this
+        # process (pb_multi_*: the library's own NVLink collectives, no torchrun), predict_v splits the batch
+        # (`multi`: an existing _lib.MultiContext to use instead of the process-wide one over GPUs 0..n_gpus-1)
+        self._multi = multi
+        self.n_gpus = int(multi.n_gpus if multi is not None else n_gpus)
         self.save_setup_data()
+
+    @property
+    def multi(self):
+        return self._multi if self._multi is not None else _lib.multi_context(self.n_gpus)
+
+    def _sharded(self, n_cols):
+        """Row-shard when asked to and the matrix is tall enough for every GPU to hold a useful slab."""
+        return self.n_gpus > 1 and self.n_h >= max(n_cols, 4096 * self.n_gpus)
 
     @property
     def ctx(self):
@@ -109,6 +122,28 @@ class PodnnModel:
         self.n_L = self.V.shape[1]
         return self._finish_projection(U_train_d, U_val_d)
 
+    def _pod_project_sharded(self, Ut, Uv, eps, n_L):
+        """Row-sharded POD + projection + pod_sig on per-GPU slabs (lists of DeviceArray, one per rank): podnnmodel.py:239,
+        247-253 with the Gram / projection partials summed over NVLink.  U_pod is never materialised."""
+        m, L = self.multi, _lib.lib()
+        Vs, _, self.n_L = m.pod(Ut, eps, n_L, self.pod_mode)
+        self.V = np.vstack([v.download() for v in Vs])
+        self._V_dev = None
+        vt = m.project(Vs, Ut)                                  # replicated on every GPU
+        v_train = vt[0].download()
+        v_val = m.project(Vs, Uv)[0].download() if Uv is not None else np.zeros((0, self.n_L))
+        sigs = []
+        for p, c in enumerate(m.ctxs):
+            rows = Ut[p].shape[0]
+            sig = c.alloc(max(rows, 1))
+            if rows:
+                c.check(L.pb_reconstruct(c.h, Vs[p].ptr, Vs[p].ld, self.n_L, vt[p].ptr, v_train.shape[0], rows,
+                                         Ut[p].ptr, Ut[p].ld, None, 0, sig.ptr))
+            sigs.append((sig, rows))
+        self.pod_sig = np.concatenate([s.download()[:r] for s, r in sigs])
+        print(f"Mean pod sig: {self.pod_sig.mean()}")
+        return v_train, v_val
+
     def _project_dev(self, Ud):
         ctx = self.ctx
         n = Ud.shape[1]
@@ -139,10 +174,23 @@ class PodnnModel:
         n_st = n_s * (self.n_t if self.has_t else 1)
         print(f"Generating {n_st} corresponding snapshots")
         X = self.x_mesh[:, 1:].T
-        U_tr_d, X_v_train, _ = snapshots_device(self.ctx, u, X, mu_tr, self.n_t, t_min, t_max)
-        U_val_d, X_v_val, _ = snapshots_device(self.ctx, u, X, mu_val, self.n_t, t_min, t_max)
-        v_train, v_val = self._pod_project(U_tr_d, U_val_d, eps, eps_init, n_L, mu_tr.shape[0])
-        U_train, U_val = U_tr_d.download(), U_val_d.download()
+        two_step = eps_init is not None and self.has_t
+        if not two_step and self._sharded(mu_tr.shape[0] * (self.n_t if self.has_t else 1)):
+            m = self.multi
+            rr = [m.row_range(self.n_h, p) for p in range(m.n_gpus)]
+            tr = [snapshots_device(m.ctxs[p], u, X, mu_tr, self.n_t, t_min, t_max, row0=lo, n_rows=hi - lo)
+                  for p, (lo, hi) in enumerate(rr)]
+            va = [snapshots_device(m.ctxs[p], u, X, mu_val, self.n_t, t_min, t_max, row0=lo, n_rows=hi - lo)
+                  for p, (lo, hi) in enumerate(rr)]
+            X_v_train, X_v_val = tr[0][1], va[0][1]
+            Ut, Uv = [a[0] for a in tr], [a[0] for a in va]
+            v_train, v_val = self._pod_project_sharded(Ut, Uv, eps, n_L)
+            U_train, U_val = np.vstack([a.download() for a in Ut]), np.vstack([a.download() for a in Uv])
+        else:
+            U_tr_d, X_v_train, _ = snapshots_device(self.ctx, u, X, mu_tr, self.n_t, t_min, t_max)
+            U_val_d, X_v_val, _ = snapshots_device(self.ctx, u, X, mu_val, self.n_t, t_min, t_max)
+            v_train, v_val = self._pod_project(U_tr_d, U_val_d, eps, eps_init, n_L, mu_tr.shape[0])
+            U_train, U_val = U_tr_d.download(), U_val_d.download()
         if self.n_t > 0 and rm_init:        # podnnmodel.py:256-272
             idx = np.arange(mu_tr.shape[0]) * self.n_t
             init = [X_v_train[idx], v_train[idx], U_train[:, idx]]
@@ -172,6 +220,14 @@ class PodnnModel:
         U_train = self.destruct(U_struct[..., tr])
         U_val = self.destruct(U_struct[..., va])
         ctx = self.ctx
+        if not (eps_init is not None and self.has_t) and self._sharded(U_train.shape[1]):
+            m = self.multi
+            rr = [m.row_range(self.n_h, p) for p in range(m.n_gpus)]
+            Ut = [m.ctxs[p].to_device(U_train[lo:hi]) for p, (lo, hi) in enumerate(rr)]
+            Uv = [m.ctxs[p].to_device(U_val[lo:hi]) for p, (lo, hi) in enumerate(rr)] if len(va) else None
+            v_train, v_val = self._pod_project_sharded(Ut, Uv, eps, n_L)
+            self.save_train_data(X_v_train, v_train, U_train, X_v_val, v_val, U_val)
+            return X_v_train, v_train, X_v_val, v_val, U_val
         Ut, Uv = ctx.to_device(U_train), (ctx.to_device(U_val) if len(va) else None)
         if eps_init is not None and self.has_t:
             # the reference feeds ALL samples (incl. validation) to the two-step POD (:160)
@@ -272,6 +328,15 @@ class PodnnModel:
     def predict_v(self, X_v):
         """Gaussian-mixture moments over the members, podnnmodel.py:314-328 -> (v_pred, v_pred_sig)."""
         members, layers, soft_0, norm, nb = self._ensemble_args()
+        X_v = np.asarray(X_v, dtype=np.float64).reshape(-1, layers[0])
+        if self.n_gpus > 1 and X_v.shape[0] >= 4096 * self.n_gpus:
+            # the points are independent: contiguous batch slices, one per GPU, launched back to back (the kernels of
+            # the different GPUs run concurrently), gathered on the host
+            m = self.multi
+            rr = [m.row_range(X_v.shape[0], p) for p in range(m.n_gpus)]
+            parts = [ensemble_predict_device(m.ctxs[p], members, layers, X_v[lo:hi], soft_0, norm, nb)
+                     for p, (lo, hi) in enumerate(rr)]
+            return np.vstack([a.download() for a, _ in parts]), np.vstack([b.download() for _, b in parts])
         vm, vs = ensemble_predict_device(self.ctx, members, layers, X_v, soft_0, norm, nb)
         return vm.download(), vs.download()
 

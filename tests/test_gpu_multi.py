@@ -136,3 +136,71 @@ def test_multi_errors(multi):
     Vs, sig, n_L = multi.pod(slabs, 1e-10, 0, "tsqr")
     assert n_L == 8
     assert cmp.largest_principal_angle(Vs[0].download(), po.perform_pod(U, 1e-10)) <= cmp.TOL_ANGLE
+
+
+def test_podnnmodel_sharded_dataset_and_predict(multi, ctx, tmp_path):
+    """PodnnModel(..., n_gpus=P): generate_dataset / convert_multigpu_data / predict_v row- and batch-sharded from one
+    process against the single-GPU model (same V up to rounding, same coefficients, same pod_sig)."""
+    from pod_uqnn_b200 import workloads as wl
+    from pod_uqnn_b200.podnnmodel import PodnnModel
+    P = multi.n_gpus
+    w = wl.ackley(96, 48 * P, 70)                      # n_h = 4608 P rows >= 4096 P: sharded
+    kw = dict(eps=1e-9, mu_lhs=w["mu"])
+    outs = []
+    for tag, extra in (("one", dict(ctx=ctx)), ("multi", dict(multi=multi))):
+        d = tmp_path / tag
+        d.mkdir()
+        model = PodnnModel(str(d), 1, w["x_mesh"], 0, pod_mode="tsqr", **extra)
+        np.random.seed(9)
+        outs.append((model, model.generate_dataset("ackley", [-1.] * 3, [1.] * 3, 70, (0.8, 0.2), **kw)))
+    (m1, o1), (m2, o2) = outs
+    assert m2.n_gpus == P and m2._sharded(56)
+    assert m1.V.shape == m2.V.shape
+    assert cmp.largest_principal_angle(m1.V, m2.V) <= 1e-9
+    assert np.array_equal(o1[0], o2[0]) and np.array_equal(o1[2], o2[2]) and np.array_equal(o1[5], o2[5])
+    _, s = cmp.align_signs(m2.V, m1.V)
+    assert cmp.rel_err(o2[1] * s, o1[1]) <= 1e-9 and cmp.rel_err(o2[4] * s, o1[4]) <= 1e-9
+    assert np.allclose(m2.pod_sig, m1.pod_sig, rtol=1e-6, atol=1e-13 * np.abs(o1[2]).max())
+    # convert_multigpu_data on the same snapshots
+    U_struct = np.vstack([o2[2].T, o2[5].T]).T.reshape(1, m2.n_h, -1)
+    X_v = np.vstack([o2[0], o2[3]])
+    np.random.seed(4); a = m1.convert_multigpu_data(U_struct, X_v, (0.8, 0.2), 1e-9)
+    np.random.seed(4); b = m2.convert_multigpu_data(U_struct, X_v, (0.8, 0.2), 1e-9)
+    assert cmp.largest_principal_angle(m1.V, m2.V) <= 1e-9
+    assert cmp.rel_err(m2.V @ b[1].T, m1.V @ a[1].T) <= 1e-9
+    # batch-split predict_v: the same numbers as one GPU (the members and every point are independent)
+    for m in (m1, m2):
+        m.initVNNs(3, [40, 40], 0.01, 0.001, 0., soft_0=0.01, norm="meanstd", seed=31)
+        for net in m.regnn:
+            net.set_normalize_bounds(w["mu"])
+    for a_, b_ in zip(m1.regnn, m2.regnn):
+        b_.weights = [x.copy() for x in a_.weights]
+    X = np.random.default_rng(2).uniform(-1, 1, (4096 * P + 11, 3))
+    (vm1, vs1), (vm2, vs2) = m1.predict_v(X), m2.predict_v(X)
+    assert np.array_equal(vm1, vm2) and np.array_equal(vs1, vs2)
+
+
+def test_multi_fast_pod(multi, ctx):
+    """Two-step POD (pod.py:51-68) row-sharded: per-sample ranks identical to the single-GPU run, same subspace; a tall
+    Burgers mesh so that the packed bases stay tall."""
+    from pod_uqnn_b200 import workloads as wl
+    from pod_uqnn_b200.acceleration import snapshots_device
+    from pod_uqnn_b200.pod import fast_pod_device
+    P = multi.n_gpus
+    w = wl.burgers(700 * P + 5, 24, 9, eps=1e-6)
+    X = w["x_mesh"][:, 1:].T
+    n_h = X.shape[1]
+    Ud, _, _ = snapshots_device(ctx, "burgers", X, w["mu"], 24, w["t_min"], w["t_max"])
+    for mode in ("gram2", "tsqr"):
+        V1, r1 = fast_pod_device(ctx, Ud, 24, 9, 1e-6, 1e-6, mode)
+        rr = [multi.row_range(n_h, p) for p in range(P)]
+        slabs = [snapshots_device(multi.ctxs[p], "burgers", X, w["mu"], 24, w["t_min"], w["t_max"], row0=lo, n_rows=hi - lo)[0]
+                 for p, (lo, hi) in enumerate(rr)]
+        Vs, r2, n_L = multi.fast_pod(slabs, 24, 9, 1e-6, 1e-6, mode)
+        V2 = np.vstack([v.download() for v in Vs])
+        assert np.array_equal(r1, r2), (mode, r1, r2)
+        assert V2.shape == V1.shape
+        assert cmp.largest_principal_angle(V2, V1.download()) <= 1e-8
+        assert np.abs(V2.T @ V2 - np.eye(n_L)).max() <= 1e-10
+    with pytest.raises(ValueError, match="at least n_t rows"):
+        multi.fast_pod([multi.ctxs[p].alloc(8, 24 * 9) for p in range(P)], 24, 9, 1e-6, 1e-6, "gram2")
