@@ -175,3 +175,39 @@ def test_dct_generator_matches_host(ctx):
     Ud = ctx.alloc(1000, 200)
     ctx.check(L.pb_dct_lowrank(ctx.h, 3000, 200, 64, 0.25, 1500, 1000, Ud.ptr, Ud.ld))
     assert cmp.rel_err(Ud.download(), U[1500:2500]) <= 1e-12
+
+
+@pytest.mark.parametrize("mode", ["gram2", "tsqr"])
+def test_c3_full_two_step_pod_matches_reference(ctx, mode):
+    """BASELINE.json C3 at full size (256 nodes x 100 steps x 300 samples, eps = eps_init = 1e-4): all 300 per-sample
+    ranks, n_L and the subspace against the unmodified reference's perform_fast_pod (tests/golden, oracle/gen_golden.py)."""
+    from pod_uqnn_b200.pod import perform_fast_pod
+    g = load_golden("fastpod_burgers_c3_full")
+    _, _, U_struct, _ = po.create_snapshots(g["x_mesh"], 1, int(g["n_t"]), po.u_burgers, g["mu"], float(g["t_min"]),
+                                            float(g["t_max"]))
+    V, ranks = perform_fast_pod(U_struct, 1e-4, 1e-4, mode=mode, ctx=ctx, return_ranks=True)
+    assert np.array_equal(ranks, g["ranks"]) and int(ranks.sum()) == 3268        # SURVEY App. A
+    assert V.shape == g["V"].shape == (256, 36)
+    assert cmp.largest_principal_angle(V, g["V"]) <= cmp.TOL_ANGLE
+
+
+def test_c4_ensemble_predict_one_million_points(ctx):
+    """BASELINE.json C4 at full size: predict_v of M = 8 members [1,128,128,128,2*64] on 1e6 points, every point
+    compared with the oracle (evaluated in chunks of 50 000 on the host), tolerance 1e-6 relative (north_star)."""
+    from oracle import ensemble as ens
+    from pod_uqnn_b200.varneuralnetwork import ensemble_predict_device, glorot_normal
+    layers, M, N = [1, 128, 128, 128, 64], 8, 1_000_000
+    dims = layers[:-1] + [2 * layers[-1]]
+    members = []
+    for i in range(M):
+        rng = np.random.default_rng(4000 + i)
+        members.append([a for fi, fo in zip(dims[:-1], dims[1:]) for a in (glorot_normal(rng, fi, fo), 0.1 * rng.standard_normal(fo))])
+    X = np.linspace(800, 1200, N)[:, None]
+    nb = (X.mean(0), X.std(0))
+    vm, vs = ensemble_predict_device(ctx, members, layers, X, 0.01, "meanstd", nb)
+    vm, vs = vm.download(), vs.download()
+    worst = 0.
+    for lo in range(0, N, 50_000):
+        rm, rs = ens.predict_v(X[lo:lo + 50_000], members, layers[-1], 0.01, "meanstd", nb)
+        worst = max(worst, cmp.rel_err(vm[lo:lo + 50_000], rm), cmp.rel_err(vs[lo:lo + 50_000], rs))
+    assert worst <= cmp.TOL_ENSEMBLE_REL, worst

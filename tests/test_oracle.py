@@ -50,6 +50,16 @@ def test_fast_pod_restatement_matches_reference(eps):
     assert cmp.largest_principal_angle(V, g["V"]) < 1e-9
 
 
+def test_fast_pod_restatement_matches_reference_c3_full():
+    """C3 at full size: the restatement reproduces the 300 per-sample ranks and the subspace of the reference run."""
+    g = load_golden("fastpod_burgers_c3_full")
+    _, _, U_struct, _ = regen(g, "burgers")
+    V, ranks = po.perform_fast_pod(U_struct, 1e-4, 1e-4, return_ranks=True)
+    assert np.array_equal(ranks, g["ranks"]) and int(ranks.sum()) == 3268
+    assert V.shape == g["V"].shape == (256, 36)
+    assert cmp.largest_principal_angle(V, g["V"]) < 1e-9
+
+
 def test_truncation_rank_rule():
     lam = 2.0 ** (-np.arange(40))
     # smallest n with cumulative energy >= 1 - eps, monotone in eps
