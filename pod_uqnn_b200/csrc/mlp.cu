@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "tile_ops.cuh"
 #include <cstdlib>
+#include <algorithm>
 
 namespace {
 using namespace pbt;
@@ -404,6 +405,85 @@ __global__ void sqrt_inplace_kernel(double* __restrict__ x, int64_t rows, int64_
     x[r * ld + c] = sqrt(fmax(x[r * ld + c], 0.));
 }
 
+// ---- layer-by-layer path for nets with a layer wider than the fused kernel's 128-column activation tile (e.g. the
+//      reference's 1dt_shallowwater h_layers = [256, 256, 256]): Dense products on the generic DMMA NN kernel,
+//      bias / ReLU and the mixture moments as elementwise passes.  Same formulas as ensemble_kernel.
+__global__ void normalize_rows_kernel(const double* __restrict__ X, int64_t n, int d, int kind, const double* __restrict__ na,
+                                      const double* __restrict__ nb, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * d) return;
+    const int c = (int)(i % d);
+    double v = X[i];
+    if (kind == PB_NORM_MEANSTD) v = (v - na[c]) / nb[c];
+    else if (kind == PB_NORM_CENTER) v = (v - na[c]) - 0.5 * (nb[c] - na[c]);
+    out[i] = v;
+}
+__global__ void bias_act_kernel(double* __restrict__ H, int64_t n, int cols, const double* __restrict__ bias, int relu) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * cols) return;
+    const double v = H[i] + bias[i % cols];
+    H[i] = relu ? fmax(v, 0.) : v;
+}
+// T (n x 2 n_L): loc = T[:, :n_L], scale = softplus(soft0 T[:, n_L:]) + 1e-6 (varneuralnetwork.py:57-58)
+__global__ void mixture_accum_kernel(const double* __restrict__ T, int64_t n, int n_L, double soft0, int first,
+                                     double* __restrict__ s1, double* __restrict__ s2, double* __restrict__ var1) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * n_L) return;
+    const int64_t p = i / n_L; const int j = (int)(i % n_L);
+    const double mu = T[p * 2 * n_L + j];
+    const double sc = softplus(soft0 * T[p * 2 * n_L + n_L + j]) + 1e-6;
+    const double var = sc * sc;
+    s1[i] = (first ? 0. : s1[i]) + mu;
+    s2[i] = (first ? 0. : s2[i]) + (var + mu * mu);
+    var1[i] = var;
+}
+__global__ void mixture_final_kernel(double* __restrict__ s1, double* __restrict__ s2, const double* __restrict__ var1,
+                                     int64_t n, int M) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double mean = s1[i] / (double)M;
+    const double var = M == 1 ? var1[i] : s2[i] / (double)M - mean * mean;      // (podnnmodel.py:322-326)
+    s1[i] = mean; s2[i] = sqrt(var);
+}
+
+int ensemble_predict_layered(pb_ctx* ctx, int M, int n_layers, const int* dims, const double* w, int norm_kind,
+                             const double* na, const double* nb, double soft0, const double* X, int64_t N,
+                             double* v_mean, double* v_sig) {
+    const int n_L = dims[n_layers] / 2;
+    int maxw = 0; int64_t per_member = 0;
+    for (int l = 0; l <= n_layers; ++l) maxw = std::max(maxw, dims[l]);
+    for (int l = 0; l < n_layers; ++l) per_member += (int64_t)dims[l] * dims[l + 1] + dims[l + 1];
+    // row batches sized so that the two activation buffers stay within 1 GiB
+    const int64_t NB = std::max<int64_t>(1024, std::min<int64_t>(N, ((int64_t)1 << 30) / (16 * (int64_t)maxw)));
+    PB_TRY(pb_reserve(ctx, &ctx->ws, &ctx->ws_bytes, (size_t)(2 * NB * maxw + NB * n_L + 64)));
+    double* H[2] = {ctx->ws, ctx->ws + NB * maxw};
+    double* var1 = ctx->ws + 2 * NB * maxw;
+    auto blocks = [](int64_t n) { return (unsigned)((n + 255) / 256); };
+    for (int64_t r0 = 0; r0 < N; r0 += NB) {
+        const int64_t nr = std::min(NB, N - r0);
+        double* s1 = v_mean + r0 * n_L; double* s2 = v_sig + r0 * n_L;
+        for (int mem = 0; mem < M; ++mem) {
+            const double* wm = w + (int64_t)mem * per_member;
+            normalize_rows_kernel<<<blocks(nr * dims[0]), 256, 0, ctx->stream>>>(X + r0 * dims[0], nr, dims[0], norm_kind, na, nb, H[0]);
+            PB_LAUNCH_CHECK(ctx);
+            int cur = 0;
+            for (int l = 0; l < n_layers; ++l) {
+                const int in = dims[l], out = dims[l + 1];
+                PB_TRY(pbi_gemm_nn(ctx, H[cur], in, nr, in, wm, out, out, H[cur ^ 1], out, nullptr, 0, nullptr));
+                bias_act_kernel<<<blocks(nr * out), 256, 0, ctx->stream>>>(H[cur ^ 1], nr, out, wm + (int64_t)in * out, l + 1 < n_layers);
+                PB_LAUNCH_CHECK(ctx);
+                wm += (int64_t)in * out + out;
+                cur ^= 1;
+            }
+            mixture_accum_kernel<<<blocks(nr * n_L), 256, 0, ctx->stream>>>(H[cur], nr, n_L, soft0, mem == 0, s1, s2, var1);
+            PB_LAUNCH_CHECK(ctx);
+        }
+        mixture_final_kernel<<<blocks(nr * n_L), 256, 0, ctx->stream>>>(s1, s2, var1, nr * n_L, M);
+        PB_LAUNCH_CHECK(ctx);
+    }
+    return PB_OK;
+}
+
 }  // namespace
 
 extern "C" int pb_ensemble_predict(pb_ctx* ctx, int n_members, int n_layers, const int* dims,
@@ -415,10 +495,22 @@ extern "C" int pb_ensemble_predict(pb_ctx* ctx, int n_members, int n_layers, con
         PB_FAIL(ctx, PB_ERR_SHAPE, "pb_ensemble_predict: need 1..%d layers, >= 1 member, N > 0", MAX_LAYERS);
     const int out_last = dims[n_layers];
     if (out_last % 2) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_ensemble_predict: the head must have 2*n_L outputs");
-    for (int l = 0; l < n_layers; ++l)
-        if (dims[l] <= 0 || dims[l] > MAX_WIDTH)
-            PB_FAIL(ctx, PB_ERR_SHAPE, "pb_ensemble_predict: layer input width %d outside (0, %d]", dims[l], MAX_WIDTH);
+    bool wide = false;
+    for (int l = 0; l < n_layers; ++l) {
+        if (dims[l] <= 0 || dims[l] > 8192)
+            PB_FAIL(ctx, PB_ERR_SHAPE, "pb_ensemble_predict: layer input width %d outside (0, 8192]", dims[l]);
+        wide = wide || dims[l] > MAX_WIDTH;
+    }
     if (norm_kind != PB_NORM_NONE && (!norm_a_dev || !norm_b_dev)) PB_FAIL(ctx, PB_ERR_ARG, "pb_ensemble_predict: normalisation bounds missing");
+    if (wide) {     // a layer wider than the fused kernel's activation tile: layer-by-layer path (any h_layers, varneuralnetwork.py:47-50)
+        cudaEventRecord(ctx->ev0, ctx->stream);
+        PB_TRY(ensemble_predict_layered(ctx, n_members, n_layers, dims, weights_dev, norm_kind, norm_a_dev, norm_b_dev, soft_0,
+                                        X_dev, N, v_mean_dev, v_sig_dev));
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        PB_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+        float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->ms[PB_T_PREDICT] = ms;
+        return PB_OK;
+    }
     MlpArgs a{};
     a.n_members = n_members; a.n_layers = n_layers; a.n_L = out_last / 2; a.norm_kind = norm_kind;
     int64_t packed = 0, src = 0;

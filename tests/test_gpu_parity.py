@@ -471,7 +471,11 @@ def test_struct_matrix_roundtrip(ctx):
 # ------------------------------------------------------------------ ensemble
 @pytest.mark.parametrize("layers,M,N,norm", [([1, 128, 128, 128, 64], 8, 1000, "meanstd"), ([3, 40, 40, 14], 5, 300, "center"),
                                              ([11, 128, 128, 128, 71], 3, 257, "none"), ([2, 16, 5], 1, 100, "meanstd"),
-                                             ([1, 40, 40, 130], 2, 129, "meanstd")])
+                                             ([1, 40, 40, 130], 2, 129, "meanstd"),
+                                             # wider than the fused kernel's 128-column tile: the layer-by-layer path
+                                             # (1dt_shallowwater's h_layers = [256, 256, 256]; odd widths; one member)
+                                             ([2, 256, 256, 256, 20], 3, 1500, "meanstd"), ([3, 140, 301, 7], 2, 333, "center"),
+                                             ([1, 129, 3], 1, 64, "none")])
 def test_ensemble_predict_v(ctx, layers, M, N, norm):
     members = [ens.init_weights(layers, 4000 + i, bias_scale=0.1) for i in range(M)]
     X = np.random.default_rng(5).uniform(800, 1200, (N, layers[0]))
@@ -493,8 +497,9 @@ def test_var_neural_network_predict(ctx):
     mean_r, var_r = ens.member_predict(X, w, 6, 0.3, "meanstd", (X.mean(0), X.std(0)))
     assert cmp.rel_err(mean, mean_r) <= cmp.TOL_ENSEMBLE_REL
     assert np.max(np.abs(var - var_r) / var_r) <= cmp.TOL_ENSEMBLE_REL     # own variance, no cancellation
-    with pytest.raises(ValueError):                                         # hidden width > 128 is not built
-        ensemble_predict_device(ctx, [ens.init_weights([1, 256, 2], 1)], [1, 256, 2], X[:, :1])
+    deep = [1] + [8] * 9 + [2]
+    with pytest.raises(ValueError):                                         # more than 8 Dense layers
+        ensemble_predict_device(ctx, [ens.init_weights(deep, 1)], deep, X[:, :1])
 
 
 def test_predict_U_closed_form(ctx):
