@@ -596,7 +596,12 @@ int pbi_gemm_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const dou
             return launch_tn<64, 256, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);
     }
     if (!sym && ka > 32 && ka <= 64) return launch_tn<64, 128, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);
-    if (!sym && ka > 64 && ka <= 96) return launch_tn<96, 128, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);
+    // 64 < ka <= 96 (the projection V^T U with n_L = 67 at C5): tiles as narrow as ka rounded up to 8 -- the DMMA count
+    // follows the padded width (a 96-wide tile for 67 columns wastes 30 % of the pipe; 72-wide: 7 %)
+    if (!sym && ka > 64 && ka <= 72) return launch_tn<72, 128, 1, 8>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);
+    if (!sym && ka > 72 && ka <= 80) return launch_tn<80, 128, 1, 8>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);
+    if (!sym && ka > 80 && ka <= 88) return launch_tn<88, 128, 1, 8>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);
+    if (!sym && ka > 88 && ka <= 96) return launch_tn<96, 128, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);
     if (sym || ka > 32) return launch_tn<128, 128, 2, 4>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, sym);
     if (ka <= 16) return launch_tn<16, 128, 1, 8>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);   // n_L <= 16: HBM bound
     return launch_tn<32, 128, 1, 8>(ctx, A, lda, ka, B, ldb, kb, rows, C, ldc, 0);
@@ -627,7 +632,10 @@ int pbi_gemm_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t
         part = ctx->ws;
     }
     if (k > 96) PB_TRY((launch_nn<128, 2, 4>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
-    else if (k > 64) PB_TRY((launch_nn<96, 2, 4>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
+    else if (k > 88) PB_TRY((launch_nn<96, 2, 4>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
+    else if (k > 80) PB_TRY((launch_nn<88, 8, 1>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
+    else if (k > 72) PB_TRY((launch_nn<80, 8, 1>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
+    else if (k > 64) PB_TRY((launch_nn<72, 8, 1>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
     else if (wide) PB_TRY((launch_nn<64, 4, 2>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
     else if (k <= 16) PB_TRY((launch_nn<16, 8, 1>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
     else      PB_TRY((launch_nn<32, 8, 1>(ctx, A, lda, rows, m, B, ldb, k, Y, ldy, Uref, ldu, part)));
