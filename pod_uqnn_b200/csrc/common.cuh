@@ -150,6 +150,9 @@ int pbi_rank(pb_ctx* ctx, const double* sig_dev, int64_t count, double eps, int*
 int pbi_factor_to_right(pb_ctx* ctx, const double* At, int64_t m, int k, const int* perm_dev,
                         const double* nrm_dev, const double* sig_dev, double* B, int64_t ldb);
 int pb_reserve_int(pb_ctx* ctx, int** p, size_t* cap, size_t elems);
+// C (rows x n, ldc) += Y (rows x 64, ldy) B (64 x n, ldb) in place; 1 = outside the kernel's domain (qr_update.cu)
+int pbi_qr_update(pb_ctx* ctx, const double* Y, int64_t ldy, int64_t rows, int64_t K, const double* B, int64_t ldb, int64_t n,
+                  double* C, int64_t ldc);
 int pbi_fast_pod_stage1(pb_ctx* ctx, const double* U, int64_t n_h_loc, int n_t, int64_t n_s, int64_t ldu, double eps_init,
                         int mode, int* ranks_host, int64_t* total, const std::function<int(double*, int64_t)>& reduce);
 // batched variants (two-step POD)

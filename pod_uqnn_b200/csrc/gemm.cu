@@ -651,6 +651,10 @@ int pbi_gemm_nn(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t
 int pbi_gemm_nn_sub(pb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t m, const double* B, int64_t ldb,
                     int64_t k, double* Y, int64_t ldy) {
     if (rows <= 0 || m <= 0 || k <= 0) PB_FAIL(ctx, PB_ERR_SHAPE, "gemm_nn_sub: bad shape");
+    if (m == 64) {      // full 64-column panels: the TMA / mbarrier / register-resident-C kernel (qr_update.cu)
+        const int rc = pbi_qr_update(ctx, A, lda, rows, m, B, ldb, k, Y, ldy);
+        if (rc <= 0) return rc;
+    }
     // K <= 64 and a wide C: the strip kernel streams C through shared memory once (in place)
     static const int strip_env = getenv("PB_QR_STRIP") ? atoi(getenv("PB_QR_STRIP")) : 1;
     if (strip_env && m <= 64 && k >= 64) {

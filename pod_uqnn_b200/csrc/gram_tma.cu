@@ -307,6 +307,21 @@ EncodeTiledFn get_encode() {
 
 }  // namespace
 
+// 3-D fp64 tensor map for the other TMA kernels of the library (qr_update.cu); 0 on success
+int pbi_tma_encode_3d(CUtensorMap* map, const double* base, const uint64_t dims[3], const uint64_t strides_bytes[2],
+                      const uint32_t box[3], int swizzle64) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return 1;
+    const cuuint64_t gdim[3] = {dims[0], dims[1], dims[2]};
+    const cuuint64_t gstr[2] = {strides_bytes[0], strides_bytes[1]};
+    const cuuint32_t bx[3] = {box[0], box[1], box[2]};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), gdim, gstr, bx, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 1;
+}
+
 void pbi_gram_plan_free(pb_ctx* ctx) {
     if (!ctx->gram_plan) return;
     GramPlan* p = static_cast<GramPlan*>(ctx->gram_plan);
