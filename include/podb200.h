@@ -350,6 +350,12 @@ int  pb_dct_basis(pb_ctx* ctx, int64_t n_h, int r, int64_t row0, int64_t n_rows,
  * sqrt(lambda_max) of the sum over ranks = sin(largest principal angle between span V and span Phi). */
 int  pb_residual_gram(pb_ctx* ctx, const double* V_dev, int64_t ldv, int n_L, const double* Phi_dev, int64_t ldp, int k,
                       int64_t n_rows, const double* C_dev, double* G_out_dev);
+/* Host-only (no GPU needed): the warp work shapes of the Gram kernel's special tile kinds for a matrix whose last
+ * 128-column tile holds `valid_atom_cols` (1..16) groups of 8 columns.  out[kind - 1][warp] = {r0, c0, nt} for
+ * kind 1 = edge, 2 = diagonal, 3 = diagonal + edge: the warp accumulates the 8 x 8 atoms (r0 .. r0 + nt - 1) x
+ * (c0 .. c0 + 3) of the 16 x 16-atom tile (of its transpose when transposed[kind - 1]); weight[kind - 1] = atoms of
+ * the busiest SM sub-partition (a full tile: 64). */
+int  pb_gram_tile_shapes(int valid_atom_cols, int out[3][8][3], int transposed[3], int weight[3]);
 /* kind: 0 = DFMA register loop, 1 = DMMA m8n8k4 loop, 2 = both pipes mixed.  Returns TFLOP/s. */
 int  pb_probe_fp64_peak(pb_ctx* ctx, int kind, double* tflops);
 /* device-to-device copy of `bytes` (read+write counted).  Returns GB/s. */

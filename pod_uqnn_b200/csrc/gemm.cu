@@ -489,11 +489,7 @@ int launch_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const doubl
     if (sym && BM == 128 && BN == 128 && bt.count == 1) {     // stream-K TMA kernel: writes C itself
         int rc = pbi_gram_streamk(ctx, A, lda, ka, rows, C, ldc, g_time_tn);
         if (rc < 0) return rc;
-        if (rc == PB_OK) {
-            symmetrize_kernel<<<(unsigned)(((int64_t)ka * kb + 255) / 256), 256, 0, ctx->stream>>>(C, (int)ka, ldc, 0);
-            PB_LAUNCH_CHECK(ctx);
-            return PB_OK;
-        }
+        if (rc == PB_OK) return PB_OK;                         // its reduction mirrors the lower triangle itself
     }
     if (sym && BM == 128 && BN == 128 && bt.count == 1) {     // TMA + mbarrier pipeline when the layout allows it
         int rc = pbi_gram_tma(ctx, A, lda, ka, rows, splits, rps, ctx->ws, split_stride, g_time_tn);

@@ -152,19 +152,60 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ka, int64_t rows, 
 
 // ---------------------------------------------------------------------------
 // stream-K variant: one persistent CTA per SM owns a contiguous range of the linearised
-// (tile, k-iteration) space, weighted 4 per off-diagonal and 3 per diagonal iteration.
+// (tile, k-iteration) space, every iteration weighted by what it costs the busiest SM sub-partition.
 //   * no wave quantisation and no split heuristics: every SM gets the same weight;
-//   * diagonal tiles skip their strictly-lower 64 x 64 quadrant: warps 0-3 keep their 64 x 32 tiles of
-//     the upper half, warps 4-7 take 64 x 16 tiles of the lower-right quadrant, so each SM sub-partition
-//     issues 3/4 of the DMMAs of an off-diagonal tile (the consumer warps are decoupled, no barrier);
+//   * a tile is 16 x 16 "atoms" (one DMMA m8n8k4 accumulator each).  Off-diagonal interior tiles run the
+//     plain 2 x 4 warp layout (64 x 32 per warp = 8 x 4 atoms, 64 atoms per sub-partition and iteration).
+//     Diagonal tiles need only the atoms on or above the diagonal (136 of 256) and tiles of the last tile
+//     column only the columns below n_s (13 of 16 atom columns at n_s = 1000): for those three kinds the
+//     host cuts the needed 4 x 4-atom blocks into 8 chunks of nt <= 8 atom rows x 4 atom columns (nt A
+//     fragments, 4 B fragments; the k loop is instantiated per nt, so the DMMA stream stays free of
+//     predicates -- a per-atom mask measured 2 x slower) and pairs the chunks so that the four
+//     sub-partitions (warps w and w + 4 share one) carry the same number of atoms: 40 / 64 for a diagonal
+//     tile instead of the 48 / 64 of a quadrant skip, 52 / 64 for an edge tile (computed transposed, so
+//     that the short side is the one split over the warp rows) instead of 64 / 64;
+//   * the consumer warps are decoupled (no CTA barrier), so unequal chunks of the two warps of a
+//     sub-partition overlap;
 //   * the partition is static (host tables), so the partial tiles are summed in a fixed order.
-struct SegEntry { int ti, tj, k0, k1, slot; };
+enum { GK_FULL = 0, GK_EDGE = 1, GK_DIAG = 2, GK_DIAG_EDGE = 3 };
+struct SegEntry { int ti, tj, k0, k1, slot, kind; };
+struct WarpShape { int r0, c0, nt, pad; };      // nt atom rows from r0 x the 4 atom columns from c0
+struct GramShapes { WarpShape w[4][8]; int transposed[4]; int weight[4]; };
 struct GramPlan { int64_t ka = -1, rows = -1; int P = 0; int nslots = 0; std::vector<SegEntry> segs; std::vector<int> seg_begin,
-                  tile_off, tile_src; int* d_tab = nullptr; size_t d_cap = 0; };
+                  tile_off, tile_src; int* d_tab = nullptr; size_t d_cap = 0; GramShapes shapes; };
+
+// k loop of one (tile, k range) segment for a warp that owns NT atom rows x 4 atom columns
+template <int NT>
+__device__ __forceinline__ void consume_segment(double (&acc)[8][4][2], const double* panels, uint64_t* full, uint64_t* empty,
+                                                int a_off, int b_off, const int (&koff)[4], int k0, int k1, uint32_t& it, int lane) {
+    for (int k = k0; k < k1; ++k, ++it) {
+        const int s = it % TSTAGES; const uint32_t ph = (it / TSTAGES) & 1;
+        mbar_wait(full + s, ph);
+        if (NT > 0) {
+            const double* st = panels + (size_t)s * 2 * PANEL_DOUBLES;
+            const double* ap = st + a_off;
+            const double* bp = st + b_off;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                double a[NT > 0 ? NT : 1], b[4];
+#pragma unroll
+                for (int t = 0; t < NT; ++t) a[t] = ap[t * (TBK * 8) + koff[kk]];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) b[u] = bp[u * (TBK * 8) + koff[kk]];
+#pragma unroll
+                for (int t = 0; t < NT; ++t)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) dmma884(acc[t][u][0], acc[t][u][1], a[t], b[u]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+    }
+}
 
 __global__ void __launch_bounds__(TMA_THREADS, 1)
-gram_streamk_kernel(const __grid_constant__ CUtensorMap tmap, const SegEntry* __restrict__ segs,
-                    const int* __restrict__ seg_begin, double* __restrict__ ws) {
+gram_streamk_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ GramShapes shapes,
+                    const SegEntry* __restrict__ segs, const int* __restrict__ seg_begin, double* __restrict__ ws) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     double* panels = reinterpret_cast<double*>(smem_raw);
@@ -210,60 +251,40 @@ gram_streamk_kernel(const __grid_constant__ CUtensorMap tmap, const SegEntry* __
     for (int sg = sb; sg < se; ++sg) {
         const SegEntry e = segs[sg];
         const bool diag = (e.ti == e.tj);
-        const bool half = diag && wm == 1;                 // lower-right quadrant only, 16 columns per warp
-        const int col0 = half ? 64 + wn * 16 : wn * 32;   // first column of this warp inside the tile
+        // frame of this warp: nt atom rows from r0 (A fragments), 4 atom columns from c0 (B fragments)
+        int r0 = wm * 8, c0 = wn * 4, nt = 8; bool tr = false;
+        if (e.kind != GK_FULL) {
+            const WarpShape sh = shapes.w[e.kind][warp];
+            r0 = sh.r0; c0 = sh.c0; nt = sh.nt; tr = shapes.transposed[e.kind] != 0;
+        }
         double acc[8][4][2];
 #pragma unroll
         for (int t = 0; t < 8; ++t)
 #pragma unroll
             for (int u = 0; u < 4; ++u) { acc[t][u][0] = 0.; acc[t][u][1] = 0.; }
-        for (int k = e.k0; k < e.k1; ++k, ++it) {
-            const int s = it % TSTAGES; const uint32_t ph = (it / TSTAGES) & 1;
-            mbar_wait(full + s, ph);
-            const double* As = panels + (size_t)s * 2 * PANEL_DOUBLES;
-            const double* Bs = diag ? As : As + PANEL_DOUBLES;
-            const double* ap = As + (wm * 8) * (TBK * 8);
-            const double* bp = Bs + (col0 / 8) * (TBK * 8);
-            if (!half) {
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    double a[8], b[4];
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) a[t] = ap[t * (TBK * 8) + koff[kk]];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) b[u] = bp[u * (TBK * 8) + koff[kk]];
-#pragma unroll
-                    for (int t = 0; t < 8; ++t)
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) dmma884(acc[t][u][0], acc[t][u][1], a[t], b[u]);
-                }
-            } else {
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    double a[8], b[2];
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) a[t] = ap[t * (TBK * 8) + koff[kk]];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) b[u] = bp[u * (TBK * 8) + koff[kk]];
-#pragma unroll
-                    for (int t = 0; t < 8; ++t)
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) dmma884(acc[t][u][0], acc[t][u][1], a[t], b[u]);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + s);
+        const int a_off = ((tr && !diag) ? PANEL_DOUBLES : 0) + r0 * (TBK * 8);
+        const int b_off = ((tr || diag) ? 0 : PANEL_DOUBLES) + c0 * (TBK * 8);
+        // one straight-line k loop per row count: no predicates or branches between the DMMAs
+        switch (nt) {
+            case 8: consume_segment<8>(acc, panels, full, empty, a_off, b_off, koff, e.k0, e.k1, it, lane); break;
+            case 7: consume_segment<7>(acc, panels, full, empty, a_off, b_off, koff, e.k0, e.k1, it, lane); break;
+            case 6: consume_segment<6>(acc, panels, full, empty, a_off, b_off, koff, e.k0, e.k1, it, lane); break;
+            case 5: consume_segment<5>(acc, panels, full, empty, a_off, b_off, koff, e.k0, e.k1, it, lane); break;
+            case 4: consume_segment<4>(acc, panels, full, empty, a_off, b_off, koff, e.k0, e.k1, it, lane); break;
+            case 3: consume_segment<3>(acc, panels, full, empty, a_off, b_off, koff, e.k0, e.k1, it, lane); break;
+            case 2: consume_segment<2>(acc, panels, full, empty, a_off, b_off, koff, e.k0, e.k1, it, lane); break;
+            case 1: consume_segment<1>(acc, panels, full, empty, a_off, b_off, koff, e.k0, e.k1, it, lane); break;
+            default: consume_segment<0>(acc, panels, full, empty, a_off, b_off, koff, e.k0, e.k1, it, lane); break;
         }
-        // partial tile -> workspace slot (dense 128 x 128)
+        // partial tile -> workspace slot (dense 128 x 128; a transposed kind is stored transposed, the reduction knows)
         double* o = ws + (size_t)e.slot * (128 * 128);
-        const int nu = half ? 2 : 4;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-            const int i = wm * 64 + t * 8 + lg;
+            if (t < nt) {
+                const int i = (r0 + t) * 8 + lg;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (u < nu) {
-                    const int j = col0 + u * 8 + 2 * lk;
+                for (int u = 0; u < 4; ++u) {
+                    const int j = (c0 + u) * 8 + 2 * lk;
                     *reinterpret_cast<double2*>(o + i * 128 + j) = make_double2(acc[t][u][0], acc[t][u][1]);
                 }
             }
@@ -271,21 +292,110 @@ gram_streamk_kernel(const __grid_constant__ CUtensorMap tmap, const SegEntry* __
     }
 }
 
-// C[i][j] = sum over the slots of tile (ti, tj) in table order; lower tiles mirrored from the upper ones
+// C[i][j] = sum over the slots of tile (ti, tj) in table order.  Everything below the diagonal is the mirror of
+// the element above it (lower tiles do not exist, and diagonal tiles hold only their upper atoms), so C is exactly
+// symmetric.  edge_tr: off-diagonal tiles of the last tile column were stored transposed.
 __global__ void streamk_reduce_kernel(const double* __restrict__ ws, const int* __restrict__ tile_src_off,
-                                      const int* __restrict__ tile_src, int ka, int tiles_n,
+                                      const int* __restrict__ tile_src, int ka, int tiles_n, int edge_tr,
                                       double* __restrict__ C, int64_t ldc) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)ka * ka) return;
     const int i = (int)(idx / ka), j = (int)(idx % ka);
     int si = i, sj = j;
-    if (j / 128 < i / 128) { si = j; sj = i; }
+    if (j < i) { si = j; sj = i; }
     const int ti = si / 128, tj = sj / 128;
     const int t = ti * tiles_n - ti * (ti - 1) / 2 + (tj - ti);
-    const int li = si % 128, lj = sj % 128;
+    int li = si % 128, lj = sj % 128;
+    if (edge_tr && ti != tj && tj == tiles_n - 1) { const int x = li; li = lj; lj = x; }
     double s = 0.;
     for (int q = tile_src_off[t]; q < tile_src_off[t + 1]; ++q) s += ws[(size_t)tile_src[q] * (128 * 128) + li * 128 + lj];
     C[(int64_t)i * ldc + j] = s;
+}
+
+// ---- host: warp shapes of the three masked tile kinds
+// need[r][c]: atom (r, c) of the frame orientation is wanted.  Per column block (4 atom columns) the wanted rows are
+// cut into contiguous chunks of at most 8 rows; the number of chunks per block and the cuts minimise the atoms of
+// the busiest sub-partition after pairing the chunks largest-with-smallest.
+struct Chunk { int cb, ra, rb, atoms; };
+bool plan_chunks(const bool need[16][16], std::vector<Chunk>& best, int& best_load) {
+    int rlo[4], rhi[4], strip[4][16];
+    for (int cb = 0; cb < 4; ++cb) {
+        rlo[cb] = 16; rhi[cb] = 0;
+        for (int r = 0; r < 16; ++r) {
+            strip[cb][r] = 0;
+            for (int u = 0; u < 4; ++u) if (need[r][cb * 4 + u]) strip[cb][r] = 4;      // a warp row is 4 atoms wide, wanted or not
+            if (strip[cb][r]) { rlo[cb] = std::min(rlo[cb], r); rhi[cb] = std::max(rhi[cb], r + 1); }
+        }
+        if (rhi[cb] <= rlo[cb]) { rlo[cb] = rhi[cb] = 0; }
+    }
+    // split of rows [rlo, rhi) of block cb into n chunks (<= 8 rows each) minimising the largest chunk (DP over cut points)
+    auto split = [&](int cb, int n, std::vector<Chunk>& out) -> bool {
+        const int lo = rlo[cb], hi = rhi[cb], len = hi - lo;
+        if (len == 0) return n == 0;
+        if (n <= 0 || n * 8 < len || n > len) return false;
+        int pre[17]; pre[0] = 0;
+        for (int x = 0; x < len; ++x) pre[x + 1] = pre[x] + strip[cb][lo + x];
+        const int INF = 1 << 30;
+        std::vector<std::vector<int>> f(n + 1, std::vector<int>(len + 1, INF)), from(n + 1, std::vector<int>(len + 1, -1));
+        f[0][0] = 0;
+        for (int c = 1; c <= n; ++c)
+            for (int x = 1; x <= len; ++x)
+                for (int y = std::max(0, x - 8); y < x; ++y) {
+                    if (f[c - 1][y] == INF) continue;
+                    const int v = std::max(f[c - 1][y], pre[x] - pre[y]);
+                    if (v < f[c][x]) { f[c][x] = v; from[c][x] = y; }
+                }
+        if (f[n][len] == INF) return false;
+        std::vector<Chunk> tmp;
+        for (int c = n, x = len; c >= 1; --c) { const int y = from[c][x]; tmp.push_back({cb, lo + y, lo + x, pre[x] - pre[y]}); x = y; }
+        out.insert(out.end(), tmp.rbegin(), tmp.rend());
+        return true;
+    };
+    best_load = 1 << 30; int best_single = 1 << 30; best.clear();
+    int n[4];
+    for (n[0] = 0; n[0] <= 8; ++n[0]) for (n[1] = 0; n[0] + n[1] <= 8; ++n[1]) for (n[2] = 0; n[0] + n[1] + n[2] <= 8; ++n[2])
+        for (n[3] = 0; n[0] + n[1] + n[2] + n[3] <= 8; ++n[3]) {
+            std::vector<Chunk> ch; bool ok = true;
+            for (int cb = 0; cb < 4 && ok; ++cb) ok = split(cb, n[cb], ch);
+            if (!ok) continue;
+            while (ch.size() < 8) ch.push_back({0, 0, 0, 0});
+            std::sort(ch.begin(), ch.end(), [](const Chunk& a, const Chunk& b) { return a.atoms > b.atoms; });
+            int load = 0;
+            for (int q = 0; q < 4; ++q) load = std::max(load, ch[q].atoms + ch[7 - q].atoms);
+            if (load < best_load || (load == best_load && ch[0].atoms < best_single)) { best_load = load; best_single = ch[0].atoms; best = ch; }
+        }
+    return !best.empty();
+}
+
+// kinds for a matrix whose last tile column has cv valid atom columns (1 .. 16)
+bool build_shapes(int cv, GramShapes& gs) {
+    memset(&gs, 0, sizeof(gs));
+    gs.weight[GK_FULL] = 64;
+    for (int kind = 1; kind < 4; ++kind) {
+        int best_load = 1 << 30, best_tr = 0; std::vector<Chunk> best;
+        for (int tr = 0; tr < (kind == GK_EDGE ? 2 : 1); ++tr) {
+            bool need[16][16];
+            for (int r = 0; r < 16; ++r) for (int c = 0; c < 16; ++c) {
+                const int ar = tr ? c : r, ac = tr ? r : c;      // atom of the tile (row of panel ti, column of panel tj)
+                bool w = true;
+                if (kind == GK_DIAG || kind == GK_DIAG_EDGE) w = w && (ar <= ac);
+                if (kind == GK_EDGE || kind == GK_DIAG_EDGE) w = w && (ac < cv);
+                need[r][c] = w;
+            }
+            std::vector<Chunk> ch; int load;
+            if (!plan_chunks(need, ch, load)) continue;
+            if (load < best_load) { best_load = load; best_tr = tr; best = ch; }
+        }
+        if (best.empty()) return false;
+        gs.transposed[kind] = best_tr; gs.weight[kind] = std::max(best_load, 1);   // (the scheduler floors it: a stage is still 32 KB of TMA traffic)
+        // chunks are sorted by size: q and 7 - q share sub-partition q (warps q and q + 4)
+        for (int q = 0; q < 8; ++q) {
+            const Chunk& c = best[q < 4 ? q : 7 - (q - 4)];
+            WarpShape& w = gs.w[kind][q];
+            w.r0 = c.ra; w.c0 = c.cb * 4; w.nt = c.rb - c.ra;
+        }
+    }
+    return true;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -320,6 +430,17 @@ int pbi_tma_encode_3d(CUtensorMap* map, const double* base, const uint64_t dims[
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : 1;
+}
+
+extern "C" int pb_gram_tile_shapes(int valid_atom_cols, int out[3][8][3], int transposed[3], int weight[3]) {
+    if (valid_atom_cols < 1 || valid_atom_cols > 16 || !out || !transposed || !weight) return PB_ERR_ARG;
+    GramShapes gs;
+    if (!build_shapes(valid_atom_cols, gs)) return PB_ERR_ARG;
+    for (int k = 1; k < 4; ++k) {
+        for (int w = 0; w < 8; ++w) { out[k - 1][w][0] = gs.w[k][w].r0; out[k - 1][w][1] = gs.w[k][w].c0; out[k - 1][w][2] = gs.w[k][w].nt; }
+        transposed[k - 1] = gs.transposed[k]; weight[k - 1] = gs.weight[k];
+    }
+    return PB_OK;
 }
 
 void pbi_gram_plan_free(pb_ctx* ctx) {
@@ -359,7 +480,7 @@ int pbi_gram_tma(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int64_t 
 }
 
 
-// stream-K launcher: returns PB_OK when it produced C (upper part; the caller symmetrises), 1 to fall back
+// stream-K launcher: returns PB_OK when it produced C (both triangles, exactly symmetric), 1 to fall back
 int pbi_gram_streamk(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int64_t rows, double* C, int64_t ldc,
                      bool time_it) {
     static const bool enabled = []{ const char* e = getenv("PB_GRAM_STREAMK"); return !e || atoi(e) != 0; }();
@@ -386,7 +507,16 @@ int pbi_gram_streamk(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int6
     if (!ctx->gram_plan) ctx->gram_plan = new GramPlan();
     GramPlan& plan = *static_cast<GramPlan*>(ctx->gram_plan);
     if (plan.ka != ka || plan.rows != rows || plan.P != P) {
-        plan.ka = ka; plan.rows = rows; plan.P = P; plan.segs.clear(); plan.seg_begin.assign(P + 1, 0);
+        plan.ka = -1; plan.rows = rows; plan.P = P; plan.segs.clear(); plan.seg_begin.assign(P + 1, 0);
+        const int cv = (int)((ka - (int64_t)(tiles_n - 1) * 128) / 8);          // valid atom columns of the last tile column
+        if (!build_shapes(cv, plan.shapes)) return 1;
+        const GramShapes& gs = plan.shapes;
+        auto kind_of = [&](int ti, int tj) {
+            const bool edge = (cv < 16 && tj == tiles_n - 1);
+            return ti == tj ? (edge ? GK_DIAG_EDGE : GK_DIAG) : (edge ? GK_EDGE : GK_FULL);
+        };
+        auto wt = [&](int ti, int tj) { return (int64_t)std::max(gs.weight[kind_of(ti, tj)], 16); };
+        const double WF = (double)gs.weight[GK_FULL];
         // Static schedule.  Two parts:
         //  (1) ALIGNED part: equal-length pieces of OFF-DIAGONAL tiles that all start together, one per CTA
         //      and round -- pieces with the same row range run in lockstep on different SMs, so a panel
@@ -404,10 +534,12 @@ int pbi_gram_streamk(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int6
         std::vector<std::pair<int,int>> off, dia;
         for (int i = 0; i < tiles_n; ++i) for (int j = i; j < tiles_n; ++j) (i == j ? dia : off).push_back({i, j});
         const int n_off = (int)off.size();
-        const double Wtot = (double)nk * (4. * n_off + 3. * dia.size());
+        double Wtot = 0.;
+        for (auto& t : off) Wtot += (double)nk * wt(t.first, t.second);
+        for (auto& t : dia) Wtot += (double)nk * wt(t.first, t.second);
         const double D = Wtot / P;
-        if (n_off > 0 && 4. * nk >= D) {                       // pieces of tiles, one round
-            const int64_t L = std::max<int64_t>(1, (int64_t)(D / 4.));
+        if (n_off > 0 && WF * nk >= D) {                       // pieces of tiles, one round
+            const int64_t L = std::max<int64_t>(1, (int64_t)(D / WF));
             const int64_t q = nk / L;
             int cta = 0;
             bool diag_aligned = false;
@@ -435,7 +567,7 @@ int pbi_gram_streamk(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int6
         }
         for (auto& d : dia) tail.push_back({d.first, d.second, 0, nk});
         // weights
-        auto wof = [](const Item& it) { return (it.k1 - it.k0) * (it.ti == it.tj ? 3 : 4); };
+        auto wof = [&](const Item& it) { return (it.k1 - it.k0) * wt(it.ti, it.tj); };
         std::vector<int64_t> cum(tail.size() + 1, 0);
         for (size_t x = 0; x < tail.size(); ++x) cum[x + 1] = cum[x] + wof(tail[x]);
         const int64_t WT = cum.back();
@@ -447,7 +579,7 @@ int pbi_gram_streamk(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int6
         auto locate = [&](int64_t b, int& x, int64_t& k) {
             if (b >= WT) { x = (int)tail.size(); k = 0; return; }
             int lo = (int)(std::upper_bound(cum.begin(), cum.end(), b) - cum.begin()) - 1;
-            x = lo; k = (b - cum[lo]) / (tail[lo].ti == tail[lo].tj ? 3 : 4);
+            x = lo; k = (b - cum[lo]) / wt(tail[lo].ti, tail[lo].tj);
         };
         const int Tn = tiles_n;
         auto tile_id = [&](int ti, int tj) { return ti * Tn - ti * (ti - 1) / 2 + (tj - ti); };
@@ -457,7 +589,7 @@ int pbi_gram_streamk(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int6
         for (int sI = 0; sI < P; ++sI) {
             plan.seg_begin[sI] = (int)plan.segs.size();
             for (auto& it : own[sI]) {
-                plan.segs.push_back({it.ti, it.tj, (int)it.k0, (int)it.k1, slot});
+                plan.segs.push_back({it.ti, it.tj, (int)it.k0, (int)it.k1, slot, kind_of(it.ti, it.tj)});
                 src[tile_id(it.ti, it.tj)].push_back(slot); ++slot;
             }
             const int64_t b0 = need_sum > 0. ? (int64_t)((double)WT * (acc_need / need_sum)) : 0;
@@ -469,7 +601,7 @@ int pbi_gram_streamk(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int6
                 const int64_t ks = tail[x].k0 + (x == x0 ? k0 : 0);
                 const int64_t ke = (x == x1) ? tail[x].k0 + k1 : tail[x].k1;
                 if (ke > ks) {
-                    plan.segs.push_back({tail[x].ti, tail[x].tj, (int)ks, (int)ke, slot});
+                    plan.segs.push_back({tail[x].ti, tail[x].tj, (int)ks, (int)ke, slot, kind_of(tail[x].ti, tail[x].tj)});
                     src[tile_id(tail[x].ti, tail[x].tj)].push_back(slot); ++slot;
                 }
             }
@@ -479,30 +611,32 @@ int pbi_gram_streamk(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int6
         plan.tile_off.assign(T + 1, 0); plan.tile_src.clear();
         for (int tt = 0; tt < T; ++tt) { plan.tile_off[tt] = (int)plan.tile_src.size(); for (int v : src[tt]) plan.tile_src.push_back(v); }
         plan.tile_off[T] = (int)plan.tile_src.size();
-        // device tables: [segs (5 ints each)] [seg_begin (P+1)] [tile_off (T+1)] [tile_src]
-        const size_t n_int = plan.segs.size() * 5 + (P + 1) + (T + 1) + plan.tile_src.size();
+        // device tables: [segs (6 ints each)] [seg_begin (P+1)] [tile_off (T+1)] [tile_src]
+        const size_t n_int = plan.segs.size() * 6 + (P + 1) + (T + 1) + plan.tile_src.size();
         if (plan.d_cap < n_int) { if (plan.d_tab) cudaFree(plan.d_tab); PB_CUDA(ctx, cudaMalloc(&plan.d_tab, n_int * sizeof(int))); plan.d_cap = n_int; }
         std::vector<int> host(n_int); size_t o = 0;
-        memcpy(host.data(), plan.segs.data(), plan.segs.size() * 5 * sizeof(int)); o += plan.segs.size() * 5;
+        memcpy(host.data(), plan.segs.data(), plan.segs.size() * 6 * sizeof(int)); o += plan.segs.size() * 6;
         memcpy(host.data() + o, plan.seg_begin.data(), (P + 1) * sizeof(int)); o += P + 1;
         memcpy(host.data() + o, plan.tile_off.data(), (T + 1) * sizeof(int)); o += T + 1;
         memcpy(host.data() + o, plan.tile_src.data(), plan.tile_src.size() * sizeof(int));
         PB_CUDA(ctx, cudaMemcpyAsync(plan.d_tab, host.data(), n_int * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        plan.ka = ka;
     }
     const SegEntry* d_segs = reinterpret_cast<const SegEntry*>(plan.d_tab);
-    const int* d_seg_begin = plan.d_tab + plan.segs.size() * 5;
+    const int* d_seg_begin = plan.d_tab + plan.segs.size() * 6;
     const int* d_tile_off = d_seg_begin + (P + 1);
     const int* d_tile_src = d_tile_off + (T + 1);
     PB_TRY(pb_reserve(ctx, &ctx->ws, &ctx->ws_bytes, (size_t)plan.nslots * 128 * 128));
     const size_t smem = (size_t)TSTAGES * STAGE_BYTES + 2 * TSTAGES * sizeof(uint64_t) + 1024;
     PB_TRY(pbi_smem_optin(ctx, (const void*)gram_streamk_kernel, (size_t)(smem)));
     if (time_it) cudaEventRecord(ctx->evk0, ctx->stream);
-    gram_streamk_kernel<<<P, TMA_THREADS, smem, ctx->stream>>>(map, d_segs, d_seg_begin, ctx->ws);
+    gram_streamk_kernel<<<P, TMA_THREADS, smem, ctx->stream>>>(map, plan.shapes, d_segs, d_seg_begin, ctx->ws);
     PB_LAUNCH_CHECK(ctx);
     if (time_it) { cudaEventRecord(ctx->evk1, ctx->stream); ctx->tn_timing_pending = true; }
     const int64_t n = ka * ka;
-    streamk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->ws, d_tile_off, d_tile_src, (int)ka, tiles_n, C, ldc);
+    streamk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->ws, d_tile_off, d_tile_src, (int)ka, tiles_n,
+                                                                                         (ka % 128) ? plan.shapes.transposed[GK_EDGE] : 0, C, ldc);
     PB_LAUNCH_CHECK(ctx);
     return PB_OK;
 }

@@ -71,7 +71,9 @@ def test_snapshot_row_sharding(ctx):
 # ------------------------------------------------------------------ products
 @pytest.mark.parametrize("rows,ka,kb,sym", [(1000, 200, 200, True), (5000, 1000, 1000, True), (777, 71, 71, True),
                                             (3001, 14, 300, False), (4096, 71, 333, False), (40, 129, 129, True),
-                                            (9000, 33, 1001, False), (1, 5, 5, True), (100000, 256, 256, True)])
+                                            (9000, 33, 1001, False), (1, 5, 5, True), (100000, 256, 256, True),
+                                            (20000, 1000, 1000, True), (30000, 136, 136, True), (9000, 648, 648, True),
+                                            (4000, 1920, 1920, True), (60000, 8, 8, True), (25000, 376, 376, True)])
 def test_gemm_tn(ctx, rows, ka, kb, sym):
     rng = np.random.default_rng(rows + ka)
     A = rng.standard_normal((rows, ka))

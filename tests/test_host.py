@@ -163,3 +163,37 @@ def test_u_level_output_tiles():
         for j0, j1, Um, Us, t in tiles:
             assert Um.shape == Us.shape == (100, j1 - j0) and 0 < j1 - j0 <= max(1, cap // 800)
         assert [t[4] for t in tiles] == list(range(len(tiles)))
+
+
+@pytest.mark.parametrize("cv", list(range(1, 17)))
+def test_gram_tile_shapes_cover_needed_atoms_once(cv):
+    """The special tile kinds of the stream-K Gram kernel: every wanted 8 x 8 atom is computed by exactly one warp,
+    no atom twice, every frame inside the 16-group panel, and the weights are the busiest sub-partition's."""
+    out = (ctypes.c_int * (3 * 8 * 3))()
+    tr, wt = (ctypes.c_int * 3)(), (ctypes.c_int * 3)()
+    assert _lib.lib().pb_gram_tile_shapes(cv, out, tr, wt) == 0
+    sh = np.array(out[:]).reshape(3, 8, 3)
+    for k, kind in enumerate(("edge", "diag", "diag_edge")):
+        got = np.zeros((16, 16), int)
+        load = np.zeros(4, int)
+        for w in range(8):
+            r0, c0, nt = (int(x) for x in sh[k, w])
+            assert 0 <= nt <= 8 and 0 <= r0 and r0 + nt <= 16 and c0 in (0, 4, 8, 12)
+            for t in range(nt):
+                for u in range(4):
+                    r, c = (c0 + u, r0 + t) if tr[k] else (r0 + t, c0 + u)     # atom of the tile (panel ti, panel tj)
+                    got[r, c] += 1
+                    load[w % 4] += 1
+        want = np.ones((16, 16), int)
+        if kind != "edge":
+            want = np.triu(want)
+        if kind != "diag":
+            want[:, cv:] = 0
+        assert got.max() <= 1 and np.all(got >= want), (cv, kind)
+        assert load.max() == wt[k]
+        assert wt[k] <= 64
+        if kind == "diag":
+            assert wt[k] == 40                       # 10 blocks of 16 atoms over 4 sub-partitions
+        if kind == "edge" and cv == 13:
+            assert wt[k] == 52 and tr[k] == 1        # n_s = 1000: 13 atom rows x 16 atom columns, transposed
+    assert _lib.lib().pb_gram_tile_shapes(0, out, tr, wt) == _lib.PB_ERR_ARG
