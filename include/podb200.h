@@ -353,9 +353,13 @@ int  pb_residual_gram(pb_ctx* ctx, const double* V_dev, int64_t ldv, int n_L, co
 /* Host-only (no GPU needed): the warp work shapes of the Gram kernel's special tile kinds for a matrix whose last
  * 128-column tile holds `valid_atom_cols` (1..16) groups of 8 columns.  out[kind - 1][warp] = {r0, c0, nt} for
  * kind 1 = edge, 2 = diagonal, 3 = diagonal + edge: the warp accumulates the 8 x 8 atoms (r0 .. r0 + nt - 1) x
- * (c0 .. c0 + 3) of the 16 x 16-atom tile (of its transpose when transposed[kind - 1]); weight[kind - 1] = atoms of
- * the busiest SM sub-partition (a full tile: 64). */
+ * (c0 .. c0 + 3) of the 16 x 16-atom tile (of its transpose when transposed[kind - 1]); weight[kind - 1] = schedule
+ * weight of one iteration: tenths of an atom of the busiest SM sub-partition + measured overhead (a full tile: 640). */
 int  pb_gram_tile_shapes(int valid_atom_cols, int out[3][8][3], int transposed[3], int weight[3]);
+/* Calibration of the Gram kernel's static schedule.  enable = 1: later pb_gram calls of this context record the busy time
+ * of every persistent CTA.  With busy_us / iters (capacity >= the SM count) it returns, per CTA of the last Gram, that
+ * time and the 16-row iterations it ran of each tile kind (full, edge, diagonal, diagonal + edge); n_cta = CTAs. */
+int  pb_gram_profile(pb_ctx* ctx, int enable, int capacity, double* busy_us, int* iters, int* n_cta);
 /* kind: 0 = DFMA register loop, 1 = DMMA m8n8k4 loop, 2 = both pipes mixed.  Returns TFLOP/s. */
 int  pb_probe_fp64_peak(pb_ctx* ctx, int kind, double* tflops);
 /* device-to-device copy of `bytes` (read+write counted).  Returns GB/s. */

@@ -108,6 +108,7 @@ SIGNATURES = {
     "pb_probe_host_copy": (_int, [C.c_size_t, _int, _int, _pd]),
     "pb_flush_l2": (_int, [_vp]),
     "pb_gram_tile_shapes": (_int, [_int, _vp, _vp, _vp]),
+    "pb_gram_profile": (_int, [_vp, _int, _int, _vp, _vp, _vp]),
 }
 
 

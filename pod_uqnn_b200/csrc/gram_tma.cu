@@ -172,7 +172,7 @@ struct SegEntry { int ti, tj, k0, k1, slot, kind; };
 struct WarpShape { int r0, c0, nt, pad; };      // nt atom rows from r0 x the 4 atom columns from c0
 struct GramShapes { WarpShape w[4][8]; int transposed[4]; int weight[4]; };
 struct GramPlan { int64_t ka = -1, rows = -1; int P = 0; int nslots = 0; std::vector<SegEntry> segs; std::vector<int> seg_begin,
-                  tile_off, tile_src; int* d_tab = nullptr; size_t d_cap = 0; GramShapes shapes; };
+                  tile_off, tile_src; int* d_tab = nullptr; size_t d_cap = 0; GramShapes shapes; long long* d_prof = nullptr; };
 
 // k loop of one (tile, k range) segment for a warp that owns NT atom rows x 4 atom columns
 template <int NT>
@@ -205,7 +205,8 @@ __device__ __forceinline__ void consume_segment(double (&acc)[8][4][2], const do
 
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 gram_streamk_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ GramShapes shapes,
-                    const SegEntry* __restrict__ segs, const int* __restrict__ seg_begin, double* __restrict__ ws) {
+                    const SegEntry* __restrict__ segs, const int* __restrict__ seg_begin, double* __restrict__ ws,
+                    long long* __restrict__ prof) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     double* panels = reinterpret_cast<double*>(smem_raw);
@@ -219,6 +220,8 @@ gram_streamk_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     }
     __syncthreads();
     const int sb = seg_begin[blockIdx.x], se = seg_begin[blockIdx.x + 1];
+    long long t_begin = 0;
+    if (prof && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
 
     if (warp == 8) {
         if (lane == 0) {
@@ -289,6 +292,10 @@ gram_streamk_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                 }
             }
         }
+    }
+    if (prof && tid == 0) {                       // schedule calibration (pb_gram_profile): ns this CTA's first warp was busy
+        long long t_end; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        prof[blockIdx.x] = t_end - t_begin;
     }
 }
 
@@ -370,7 +377,7 @@ bool plan_chunks(const bool need[16][16], std::vector<Chunk>& best, int& best_lo
 // kinds for a matrix whose last tile column has cv valid atom columns (1 .. 16)
 bool build_shapes(int cv, GramShapes& gs) {
     memset(&gs, 0, sizeof(gs));
-    gs.weight[GK_FULL] = 64;
+    gs.weight[GK_FULL] = 640;
     for (int kind = 1; kind < 4; ++kind) {
         int best_load = 1 << 30, best_tr = 0; std::vector<Chunk> best;
         for (int tr = 0; tr < (kind == GK_EDGE ? 2 : 1); ++tr) {
@@ -387,7 +394,12 @@ bool build_shapes(int cv, GramShapes& gs) {
             if (load < best_load) { best_load = load; best_tr = tr; best = ch; }
         }
         if (best.empty()) return false;
-        gs.transposed[kind] = best_tr; gs.weight[kind] = std::max(best_load, 1);   // (the scheduler floors it: a stage is still 32 KB of TMA traffic)
+        gs.transposed[kind] = best_tr;
+        // schedule weight of one 16-row iteration, in tenths of an atom: the atoms of the busiest sub-partition plus what
+        // pb_gram_profile measured on top (per-stage hand-over and the unequal chunks of a sub-partition's two warps):
+        // C2 on B200: full 2.13 us, edge 1.76, diagonal 1.41, diagonal + edge 1.41 per iteration = 640 / 528 / 423 / 424 (edge: 535 balanced best)
+        gs.weight[kind] = 10 * std::max(best_load, 1) + (kind == GK_EDGE ? 15 : 23);
+        if (kind == GK_DIAG_EDGE) gs.weight[kind] = std::max(gs.weight[kind], std::min(gs.weight[GK_DIAG], 10 * best_load + 54));
         // chunks are sorted by size: q and 7 - q share sub-partition q (warps q and q + 4)
         for (int q = 0; q < 8; ++q) {
             const Chunk& c = best[q < 4 ? q : 7 - (q - 4)];
@@ -443,10 +455,34 @@ extern "C" int pb_gram_tile_shapes(int valid_atom_cols, int out[3][8][3], int tr
     return PB_OK;
 }
 
+// Schedule calibration: after pb_gram_profile(ctx, 1, ...) the stream-K kernel records the busy time of every CTA; a later
+// call returns, per CTA, that time and the k iterations it ran of each tile kind (full, edge, diagonal, diagonal + edge).
+extern "C" int pb_gram_profile(pb_ctx* ctx, int enable, int capacity, double* busy_us, int* iters /* [capacity][4] */, int* n_cta) {
+    PB_ENTER(ctx);
+    if (!ctx->gram_plan) ctx->gram_plan = new GramPlan();
+    GramPlan& plan = *static_cast<GramPlan*>(ctx->gram_plan);
+    if (enable && !plan.d_prof) { PB_CUDA(ctx, cudaMalloc(&plan.d_prof, sizeof(long long) * 1024)); PB_CUDA(ctx, cudaMemset(plan.d_prof, 0, sizeof(long long) * 1024)); }
+    if (!enable && plan.d_prof) { PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(plan.d_prof); plan.d_prof = nullptr; }
+    if (n_cta) *n_cta = plan.ka > 0 ? plan.P : 0;
+    if (busy_us && iters && plan.d_prof && plan.ka > 0) {
+        if (capacity < plan.P || plan.P > 1024) return PB_ERR_ARG;
+        std::vector<long long> t(plan.P);
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        PB_CUDA(ctx, cudaMemcpy(t.data(), plan.d_prof, sizeof(long long) * plan.P, cudaMemcpyDeviceToHost));
+        for (int c = 0; c < plan.P; ++c) {
+            busy_us[c] = (double)t[c] * 1e-3;
+            for (int k = 0; k < 4; ++k) iters[c * 4 + k] = 0;
+            for (int sg = plan.seg_begin[c]; sg < plan.seg_begin[c + 1]; ++sg) iters[c * 4 + plan.segs[sg].kind] += plan.segs[sg].k1 - plan.segs[sg].k0;
+        }
+    }
+    return PB_OK;
+}
+
 void pbi_gram_plan_free(pb_ctx* ctx) {
     if (!ctx->gram_plan) return;
     GramPlan* p = static_cast<GramPlan*>(ctx->gram_plan);
     if (p->d_tab) cudaFree(p->d_tab);
+    if (p->d_prof) cudaFree(p->d_prof);
     delete p; ctx->gram_plan = nullptr;
 }
 
@@ -510,12 +546,16 @@ int pbi_gram_streamk(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int6
         plan.ka = -1; plan.rows = rows; plan.P = P; plan.segs.clear(); plan.seg_begin.assign(P + 1, 0);
         const int cv = (int)((ka - (int64_t)(tiles_n - 1) * 128) / 8);          // valid atom columns of the last tile column
         if (!build_shapes(cv, plan.shapes)) return 1;
+        if (const char* e = getenv("PB_GRAM_WEIGHTS")) {          // experiment knob: "edge,diag,diag_edge" schedule weights (a full tile is 640)
+            int w1, w2, w3;
+            if (sscanf(e, "%d,%d,%d", &w1, &w2, &w3) == 3) { plan.shapes.weight[GK_EDGE] = w1; plan.shapes.weight[GK_DIAG] = w2; plan.shapes.weight[GK_DIAG_EDGE] = w3; }
+        }
         const GramShapes& gs = plan.shapes;
         auto kind_of = [&](int ti, int tj) {
             const bool edge = (cv < 16 && tj == tiles_n - 1);
             return ti == tj ? (edge ? GK_DIAG_EDGE : GK_DIAG) : (edge ? GK_EDGE : GK_FULL);
         };
-        auto wt = [&](int ti, int tj) { return (int64_t)std::max(gs.weight[kind_of(ti, tj)], 16); };
+        auto wt = [&](int ti, int tj) { return (int64_t)std::max(gs.weight[kind_of(ti, tj)], 160); };   // floor: a stage is still 16-32 KB of TMA traffic
         const double WF = (double)gs.weight[GK_FULL];
         // Static schedule.  Two parts:
         //  (1) ALIGNED part: equal-length pieces of OFF-DIAGONAL tiles that all start together, one per CTA
@@ -631,7 +671,7 @@ int pbi_gram_streamk(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int6
     const size_t smem = (size_t)TSTAGES * STAGE_BYTES + 2 * TSTAGES * sizeof(uint64_t) + 1024;
     PB_TRY(pbi_smem_optin(ctx, (const void*)gram_streamk_kernel, (size_t)(smem)));
     if (time_it) cudaEventRecord(ctx->evk0, ctx->stream);
-    gram_streamk_kernel<<<P, TMA_THREADS, smem, ctx->stream>>>(map, plan.shapes, d_segs, d_seg_begin, ctx->ws);
+    gram_streamk_kernel<<<P, TMA_THREADS, smem, ctx->stream>>>(map, plan.shapes, d_segs, d_seg_begin, ctx->ws, plan.d_prof);
     PB_LAUNCH_CHECK(ctx);
     if (time_it) { cudaEventRecord(ctx->evk1, ctx->stream); ctx->tn_timing_pending = true; }
     const int64_t n = ka * ka;

@@ -190,10 +190,10 @@ def test_gram_tile_shapes_cover_needed_atoms_once(cv):
         if kind != "diag":
             want[:, cv:] = 0
         assert got.max() <= 1 and np.all(got >= want), (cv, kind)
-        assert load.max() == wt[k]
-        assert wt[k] <= 64
+        # weight: tenths of an atom of the busiest sub-partition + the measured per-stage overhead
+        assert 10 * load.max() <= wt[k] <= 10 * load.max() + 60 and wt[k] < 640 + 60
         if kind == "diag":
-            assert wt[k] == 40                       # 10 blocks of 16 atoms over 4 sub-partitions
+            assert load.max() == 40                  # 10 blocks of 16 atoms over 4 sub-partitions
         if kind == "edge" and cv == 13:
-            assert wt[k] == 52 and tr[k] == 1        # n_s = 1000: 13 atom rows x 16 atom columns, transposed
+            assert load.max() == 52 and tr[k] == 1   # n_s = 1000: 13 atom rows x 16 atom columns, transposed
     assert _lib.lib().pb_gram_tile_shapes(0, out, tr, wt) == _lib.PB_ERR_ARG
