@@ -26,15 +26,14 @@
 namespace {
 using namespace pbt;
 
-constexpr int MP = 128;            // points per tile
 constexpr int PACT = 132;          // activation pitch (== 4 mod 16: conflict-free A fragments)
 constexpr int PW = 132;            // packed weight pitch
-constexpr int RING = 5;
+constexpr int RING = 7;             // weight ring slots (96-point tile: 101 KB activations + 118 KB ring)
 constexpr int CHUNK_DOUBLES = BK * PW;             // 2112 doubles = 16 896 B per K chunk
 constexpr int BIAS_DOUBLES = PW;                   // 132 doubles = 1 056 B
 constexpr int MAX_LAYERS = 8;
 constexpr int MAX_WIDTH = 128;     // hidden widths (inputs of every layer) must fit the tile
-constexpr int MLP_THREADS = 384;   // 8 consumer warps + one producer warpgroup (registers are re-balanced)
+constexpr int MLP_GROUPS = 3;      // consumer groups of 4 warps, 32 points each (tile = 96 points); see ensemble_kernel
 
 struct MlpArgs {
     int n_members, n_layers, n_L, norm_kind;
@@ -70,9 +69,12 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-// the two consumer groups (warps 0-3: points 0-63, warps 4-7: points 64-127 of the tile) only synchronise
-// internally, so one group's epilogue / mixture pass overlaps the other group's DMMA work
+// the consumer groups (4 warps = 32 points of the tile each) only synchronise internally, so one group's
+// epilogue / mixture pass overlaps the other groups' DMMA work
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;\n" :: "r"(1 + g) : "memory"); }
+
+// max(v, 0) on the integer pipe (sign bit of the high word): -0 and negative NaNs become +0
+__device__ __forceinline__ double relu_bits(double v) { return __double2hiint(v) < 0 ? 0. : v; }
 
 __device__ __forceinline__ double softplus(double x) {
     // np.logaddexp(0, x) == tf.math.softplus within 1 ulp.
@@ -95,7 +97,7 @@ __device__ __forceinline__ double softplus(double x) {
 }
 
 // Keras layout (per member: W0 (in x out) row-major, b0, W1, b1, ...) -> packed stream
-// (per member, per layer, per 128-wide output chunk: ceil(in/16) blocks [16][132], then bias [132])
+// (per member, per layer, per 128-wide output chunk: bias [132], then ceil(in/16) blocks [16][132])
 __global__ void pack_weights_kernel(const double* __restrict__ w, double* __restrict__ packed, int n_members,
                                     int n_layers, MlpArgs a, int64_t src_member_stride) {
     const int64_t total = (int64_t)n_members * a.member_stride;
@@ -112,12 +114,13 @@ __global__ void pack_weights_kernel(const double* __restrict__ w, double* __rest
             if (r < layer_sz) {
                 const int c = (int)(r / per_chunk); const int64_t q = r % per_chunk;
                 const double* W = w + (int64_t)mem * src_member_stride + src_off;
-                if (q < (int64_t)nk * CHUNK_DOUBLES) {
-                    const int kc = (int)(q / CHUNK_DOUBLES); const int e = (int)(q % CHUNK_DOUBLES);
+                if (q >= BIAS_DOUBLES) {
+                    const int64_t qq = q - BIAS_DOUBLES;
+                    const int kc = (int)(qq / CHUNK_DOUBLES); const int e = (int)(qq % CHUNK_DOUBLES);
                     const int row = kc * BK + e / PW, col = c * 128 + e % PW;
                     if (row < in && (e % PW) < 128 && col < out) v = W[(int64_t)row * out + col];
                 } else {
-                    const int e = (int)(q - (int64_t)nk * CHUNK_DOUBLES); const int col = c * 128 + e;
+                    const int e = (int)q; const int col = c * 128 + e;
                     if (e < 128 && col < out) v = W[(int64_t)in * out + col];
                 }
                 break;
@@ -129,25 +132,33 @@ __global__ void pack_weights_kernel(const double* __restrict__ w, double* __rest
     }
 }
 
-__global__ void __launch_bounds__(MLP_THREADS, 1) ensemble_kernel(MlpArgs a) {
+// NG consumer groups of 4 warps; a group owns 32 points of the tile (warp tile 32 points x 32 outputs).  Every SM
+// sub-partition hosts one warp of each group, so while one group is in a layer epilogue / the mixture pass / the input
+// stage the other groups' warps keep its DMMA pipe fed.  (Two groups of 64 points measured 72 % tensor-pipe activity:
+// a group spends ~30 % of its time outside the products, and ONE warp per sub-partition reaches only ~60 % of the pipe.)
+template <int NG>
+__global__ void __launch_bounds__((NG * 4 + 4) * 32, 1) ensemble_kernel(MlpArgs a) {
+    constexpr int MPT = 32 * NG;                          // points per tile
+    constexpr int NCW = NG * 4;                           // consumer warps
     extern __shared__ __align__(16) double smem[];
-    double* act = smem;                                   // [MP][PACT]
-    double* ring = smem + MP * PACT;                      // [RING][CHUNK_DOUBLES]
-    uint64_t* full = reinterpret_cast<uint64_t*>(ring + RING * CHUNK_DOUBLES);
+    double* act = smem;                                   // [MPT][PACT]
+    double* ring = smem + MPT * PACT;                     // [RING][CHUNK_DOUBLES]
+    double* xs = ring + RING * CHUNK_DOUBLES;             // [MPT][4]: normalised inputs of the tile when n_d <= 4
+    uint64_t* full = reinterpret_cast<uint64_t*>(xs + MPT * 4);
     uint64_t* empty = full + RING;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_L = a.n_L;
     if (tid == 0) {
-        for (int s = 0; s < RING; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 8); }
+        for (int s = 0; s < RING; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NCW); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     }
     __syncthreads();
 
-    if (warp >= 8) {
+    if (warp >= NCW) {
         // ------------------------------------------------ producer: streams the packed weights
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
-        if (warp == 8 && lane == 0) {
+        if (warp == NCW && lane == 0) {
             uint32_t it = 0;
             for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x)
                 for (int mem = 0; mem < a.n_members; ++mem) {
@@ -155,9 +166,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) ensemble_kernel(MlpArgs a) {
                     for (int l = 0; l < a.n_layers; ++l) {
                         const int nk = (a.dims[l] + BK - 1) / BK, nc = (a.dims[l + 1] + 127) / 128;
                         for (int c = 0; c < nc; ++c)
-                            for (int kc = 0; kc <= nk; ++kc, ++it) {       // kc == nk: the bias block
+                            for (int kc = -1; kc < nk; ++kc, ++it) {       // kc == -1: the bias block (it seeds the accumulators)
                                 const int s = it % RING; const uint32_t ph = (it / RING) & 1;
-                                const uint32_t bytes = (kc < nk ? CHUNK_DOUBLES : BIAS_DOUBLES) * 8;
+                                const uint32_t bytes = (kc >= 0 ? CHUNK_DOUBLES : BIAS_DOUBLES) * 8;
                                 mbar_wait(empty + s, ph ^ 1);
                                 mbar_expect_tx(full + s, bytes);
                                 bulk_load(ring + (size_t)s * CHUNK_DOUBLES, src, bytes, full + s);
@@ -169,123 +180,163 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) ensemble_kernel(MlpArgs a) {
         return;
     }
 
-    // ---------------------------------------------------- consumers: 2 x 4 warps, warp tile 64 x 32
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
-    const int wm = warp >> 2, wn = warp & 3;
+    // ---------------------------------------------------- consumers
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;\n");
+    const int g = warp >> 2, wn = warp & 3;               // group, 32-column slice of the layer output
+    const int gt = tid & 127;                             // thread inside the group
     const int lk = lane & 3, lg = lane >> 2;
     const int n_d = a.dims[0];
+    const bool small_in = (n_d <= 4);                     // first layer on plain FMAs from xs (no 16-column padding)
     const int out_head = 2 * n_L;
-    double* scr = a.scratch + (size_t)blockIdx.x * a.n_members * MP * out_head;
+    double* scr = a.scratch + (size_t)blockIdx.x * a.n_members * MPT * out_head;
     uint32_t it = 0;
-    // Skew the second group by a couple of weight chunks: it then runs its GEMM chunks while the first group
-    // is in a layer epilogue / mixture pass and vice versa, so the DMMA pipe is not idle in those phases
-    // (both groups consume the same weight ring, which bounds the skew to its depth).
-    if (wm == 1 && a.skew_ns > 0) __nanosleep(a.skew_ns);
+    // Skew the groups against each other so that their epilogues do not coincide (all groups consume the same weight
+    // ring, which bounds the skew to its depth).
+    if (g > 0 && a.skew_ns > 0) __nanosleep(a.skew_ns * g);
     for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const int64_t p0 = tile * MP;
-        for (int mem = 0; mem < a.n_members; ++mem) {
-            // ---- input tile, normalised (varneuralnetwork.py:75-86), zero padded to 16 columns
-            const int kin0 = (n_d + BK - 1) / BK * BK;
-            for (int e = (tid & 127); e < (MP / 2) * kin0; e += 128) {
-                const int p = wm * (MP / 2) + e / kin0, c = e % kin0;
+        const int64_t p0 = tile * MPT;
+        if (small_in) {
+            // ---- inputs of the tile, normalised once for all members (varneuralnetwork.py:75-86)
+            if (gt < 32 * 4) {
+                const int p = g * 32 + (gt >> 2), c = gt & 3;
                 double v = 0.;
                 if (c < n_d && p0 + p < a.N) {
                     v = a.X[(p0 + p) * n_d + c];
                     if (a.norm_kind == PB_NORM_MEANSTD) v = (v - a.norm_a[c]) / a.norm_b[c];
                     else if (a.norm_kind == PB_NORM_CENTER) v = (v - a.norm_a[c]) - 0.5 * (a.norm_b[c] - a.norm_a[c]);
                 }
-                act[p * PACT + c] = v;
+                xs[p * 4 + c] = v;
             }
-            group_sync(wm);
+            group_sync(g);
+        }
+        for (int mem = 0; mem < a.n_members; ++mem) {
+            if (!small_in) {
+                // ---- input tile, normalised, zero padded to a multiple of 16 columns
+                const int kin0 = (n_d + BK - 1) / BK * BK;
+                for (int e = gt; e < 32 * kin0; e += 128) {
+                    const int p = g * 32 + e / kin0, c = e % kin0;
+                    double v = 0.;
+                    if (c < n_d && p0 + p < a.N) {
+                        v = a.X[(p0 + p) * n_d + c];
+                        if (a.norm_kind == PB_NORM_MEANSTD) v = (v - a.norm_a[c]) / a.norm_b[c];
+                        else if (a.norm_kind == PB_NORM_CENTER) v = (v - a.norm_a[c]) - 0.5 * (a.norm_b[c] - a.norm_a[c]);
+                    }
+                    act[p * PACT + c] = v;
+                }
+                group_sync(g);
+            }
             for (int l = 0; l < a.n_layers; ++l) {
                 const int in = a.dims[l], out = a.dims[l + 1];
                 const bool head = (l == a.n_layers - 1);
                 const int nk = (in + BK - 1) / BK, nc = (out + 127) / 128;
                 for (int c = 0; c < nc; ++c) {                 // > 1 chunk only for a wide head
-                    double acc[8][4][2];
+                    // the bias block of this (layer, chunk) comes first and seeds the accumulators: the epilogue then has no
+                    // fp64-pipe instruction at all (a DADD queues behind the other groups' DMMAs for ~40 cycles each)
+                    double acc[4][4][2];
+                    {
+                        const int sb = it % RING; const uint32_t phb = (it / RING) & 1;
+                        ++it;
+                        mbar_wait(full + sb, phb);
+                        const double* bias = ring + (size_t)sb * CHUNK_DOUBLES + wn * 32 + 2 * lk;
 #pragma unroll
-                    for (int t = 0; t < 8; ++t)
+                        for (int u = 0; u < 4; ++u) {
+                            const double2 b2 = *reinterpret_cast<const double2*>(bias + u * 8);
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) { acc[t][u][0] = 0.; acc[t][u][1] = 0.; }
-#pragma unroll 1
-                    for (int kt = 0; kt < nk; ++kt, ++it) {
+                            for (int t = 0; t < 4; ++t) { acc[t][u][0] = b2.x; acc[t][u][1] = b2.y; }
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(empty + sb);
+                    }
+                    if (l == 0 && small_in) {
+                        // x W0 for 1..4 inputs: n_d FMAs per output from the one weight chunk (rows >= n_d are zero padding)
                         const int s = it % RING; const uint32_t ph = (it / RING) & 1;
+                        ++it;
                         mbar_wait(full + s, ph);
-                        const double* as = act + (wm * 64 + lg) * PACT + kt * BK + lk;
-                        const double* bs = ring + (size_t)s * CHUNK_DOUBLES + wn * 32 + lg;
+                        const double* w0 = ring + (size_t)s * CHUNK_DOUBLES + wn * 32 + 2 * lk;
+                        for (int ci = 0; ci < n_d; ++ci) {
+                            double xv[4];
 #pragma unroll
-                        for (int kk = 0; kk < BK / 4; ++kk) {
-                            double af[8], bf[4];
+                            for (int t = 0; t < 4; ++t) xv[t] = xs[(g * 32 + t * 8 + lg) * 4 + ci];
 #pragma unroll
-                            for (int t = 0; t < 8; ++t) af[t] = as[t * 8 * PACT + kk * 4];
+                            for (int u = 0; u < 4; ++u) {
+                                const double2 w = *reinterpret_cast<const double2*>(w0 + ci * PW + u * 8);
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) bf[u] = bs[(kk * 4 + lk) * PW + u * 8];
-#pragma unroll
-                            for (int t = 0; t < 8; ++t)
-#pragma unroll
-                                for (int u = 0; u < 4; ++u) dmma884(acc[t][u][0], acc[t][u][1], af[t], bf[u]);
+                                for (int t = 0; t < 4; ++t) { acc[t][u][0] = fma(xv[t], w.x, acc[t][u][0]); acc[t][u][1] = fma(xv[t], w.y, acc[t][u][1]); }
+                            }
                         }
                         __syncwarp();
                         if (lane == 0) mbar_arrive(empty + s);
+                    } else {
+#pragma unroll 1
+                        for (int kt = 0; kt < nk; ++kt, ++it) {
+                            const int s = it % RING; const uint32_t ph = (it / RING) & 1;
+                            mbar_wait(full + s, ph);
+                            const double* as = act + (g * 32 + lg) * PACT + kt * BK + lk;
+                            const double* bs = ring + (size_t)s * CHUNK_DOUBLES + wn * 32 + lg;
+#pragma unroll
+                            for (int kk = 0; kk < BK / 4; ++kk) {
+                                double af[4], bf[4];
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) af[t] = as[t * 8 * PACT + kk * 4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) bf[u] = bs[(kk * 4 + lk) * PW + u * 8];
+#pragma unroll
+                                for (int t = 0; t < 4; ++t)
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) dmma884(acc[t][u][0], acc[t][u][1], af[t], bf[u]);
+                            }
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(empty + s);
+                        }
                     }
-                    // bias block of this (layer, chunk)
-                    const int sb = it % RING; const uint32_t phb = (it / RING) & 1;
-                    ++it;
-                    mbar_wait(full + sb, phb);
-                    const double* bias = ring + (size_t)sb * CHUNK_DOUBLES;
                     if (!head) {
-                        group_sync(wm);            // every warp has finished reading act for this layer
+                        if (!(l == 0 && small_in)) group_sync(g);   // every warp of the group has finished reading act for this layer
                         // next activations: relu(acc + b), columns [out, ceil16(out)) zeroed
                         const int outp = (out + BK - 1) / BK * BK;
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) {
-                            const int p = wm * 64 + t * 8 + lg;
+                        for (int t = 0; t < 4; ++t) {
+                            const int p = g * 32 + t * 8 + lg;
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 const int n = wn * 32 + u * 8 + 2 * lk;
                                 double2 v;
-                                v.x = n < out ? fmax(acc[t][u][0] + bias[n], 0.) : 0.;
-                                v.y = n + 1 < out ? fmax(acc[t][u][1] + bias[n + 1], 0.) : 0.;
+                                v.x = n < out ? relu_bits(acc[t][u][0]) : 0.;
+                                v.y = n + 1 < out ? relu_bits(acc[t][u][1]) : 0.;
                                 if (n < outp) *reinterpret_cast<double2*>(act + p * PACT + n) = v;
                             }
                         }
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(empty + sb);
-                        group_sync(wm);            // activations of the next layer are complete
+                        group_sync(g);            // activations of the next layer are complete
                     } else {
                         // head: raw outputs t = h W + b go to the per-CTA scratch (L2); the Normal's
                         // parameters are formed in the mixture pass below
-                        double* sm = scr + (size_t)mem * MP * out_head;
+                        double* sm = scr + (size_t)mem * MPT * out_head;
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) {
-                            const int p = wm * 64 + t * 8 + lg;
+                        for (int t = 0; t < 4; ++t) {
+                            const int p = g * 32 + t * 8 + lg;
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 const int nl = wn * 32 + u * 8 + 2 * lk;          // column inside the chunk (even)
                                 const int n = c * 128 + nl;
                                 if (n + 1 < out)
-                                    *reinterpret_cast<double2*>(sm + (size_t)p * out_head + n) =
-                                        make_double2(acc[t][u][0] + bias[nl], acc[t][u][1] + bias[nl + 1]);
-                                else if (n < out) sm[(size_t)p * out_head + n] = acc[t][u][0] + bias[nl];
+                                    *reinterpret_cast<double2*>(sm + (size_t)p * out_head + n) = make_double2(acc[t][u][0], acc[t][u][1]);
+                                else if (n < out) sm[(size_t)p * out_head + n] = acc[t][u][0];
                             }
                         }
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(empty + sb);
                     }
                 }
             }
-            group_sync(wm);        // act may be overwritten by the next member's input tile
+            group_sync(g);        // act may be overwritten by the next member's input tile / first layer
         }
         // ---- mixture moments (podnnmodel.py:322-326): mean_i mu_i, sqrt(mean_i(var_i + mu_i^2) - mean^2)
         __threadfence_block();
-        group_sync(wm);
+        group_sync(g);
         const double invM = 1. / (double)a.n_members;
-        const int64_t pts = min((int64_t)(MP / 2), a.N - p0 - wm * (MP / 2));      // points of this group
+        const int64_t pts = min((int64_t)32, a.N - p0 - g * 32);      // points of this group
         // 4 members x 2 elements per pass: 16 independent loads, then 8 independent softplus chains (the fp64
         // exp / log1p sequences are latency bound one at a time; measured 30 % of the kernel before)
         const int64_t n_el = pts * n_L;
 #pragma unroll 1
-        for (int64_t e0 = (tid & 127); e0 < n_el; e0 += 256) {
+        for (int64_t e0 = gt; e0 < n_el; e0 += 256) {
             int64_t el[2] = {e0, e0 + 128};
             const bool ok1 = el[1] < n_el;
             if (!ok1) el[1] = e0;
@@ -293,7 +344,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) ensemble_kernel(MlpArgs a) {
             const double* base[2]; int jj[2];
 #pragma unroll
             for (int x = 0; x < 2; ++x) {
-                const int64_t e = (int64_t)wm * (MP / 2) * n_L + el[x];
+                const int64_t e = (int64_t)g * 32 * n_L + el[x];
                 const int p = (int)(e / n_L); jj[x] = (int)(e % n_L);
                 base[x] = scr + (size_t)p * out_head;
             }
@@ -305,7 +356,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) ensemble_kernel(MlpArgs a) {
                     const int mem = min(m0 + k, a.n_members - 1);
 #pragma unroll
                     for (int x = 0; x < 2; ++x) {
-                        const double* tm = base[x] + (size_t)mem * MP * out_head;
+                        const double* tm = base[x] + (size_t)mem * MPT * out_head;
                         mu4[x][k] = tm[jj[x]];                              // loc = t[:, :n_L]   (:57)
                         rw4[x][k] = tm[n_L + jj[x]];
                     }
@@ -332,12 +383,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) ensemble_kernel(MlpArgs a) {
                 const double mean = s1[x] * invM;
                 // one member: its own variance, exactly (VarNeuralNetwork.predict, varneuralnetwork.py:159)
                 const double var = a.n_members == 1 ? var1[x] : s2[x] * invM - mean * mean;
-                const int64_t o = (p0 + (int64_t)wm * (MP / 2)) * n_L + el[x];
+                const int64_t o = (p0 + (int64_t)g * 32) * n_L + el[x];
                 a.v_mean[o] = mean;
                 a.v_sig[o] = sqrt(var);
             }
         }
-        group_sync(wm);            // scratch is reused by the next tile
+        group_sync(g);            // scratch is reused by the next tile
     }
 }
 
@@ -523,20 +574,21 @@ extern "C" int pb_ensemble_predict(pb_ctx* ctx, int n_members, int n_layers, con
     a.member_stride = packed;
     a.norm_a = norm_a_dev; a.norm_b = norm_b_dev; a.soft0 = soft_0;
     a.X = X_dev; a.N = N; a.v_mean = v_mean_dev; a.v_sig = v_sig_dev;
-    a.n_tiles = (N + MP - 1) / MP;
-    { static const unsigned sk = []{ const char* e = getenv("PB_MLP_SKEW_NS"); return e ? (unsigned)atoi(e) : 5000u; }(); a.skew_ns = sk; }
+    constexpr int MPT = 32 * MLP_GROUPS;
+    a.n_tiles = (N + MPT - 1) / MPT;
+    { static const unsigned sk = []{ const char* e = getenv("PB_MLP_SKEW_NS"); return e ? (unsigned)atoi(e) : 3000u; }(); a.skew_ns = sk; }
     const int grid = (int)std::min<int64_t>(a.n_tiles, ctx->sm_count);
     cudaEventRecord(ctx->ev0, ctx->stream);
     // workspace: packed weights, then the per-CTA member scratch
-    const size_t scr = (size_t)grid * n_members * MP * 2 * a.n_L;
+    const size_t scr = (size_t)grid * n_members * MPT * 2 * a.n_L;
     PB_TRY(pb_reserve(ctx, &ctx->ws, &ctx->ws_bytes, (size_t)n_members * packed + scr + 16));
     double* pk = ctx->ws;
     a.packed = pk; a.scratch = pk + (((size_t)n_members * packed + 1) & ~(size_t)1);
     pack_weights_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(weights_dev, pk, n_members, n_layers, a, src);
     PB_LAUNCH_CHECK(ctx);
-    const size_t smem = sizeof(double) * (size_t)(MP * PACT + RING * CHUNK_DOUBLES) + 2 * RING * sizeof(uint64_t);
-    PB_TRY(pbi_smem_optin(ctx, (const void*)ensemble_kernel, (size_t)(smem)));
-    ensemble_kernel<<<grid, MLP_THREADS, smem, ctx->stream>>>(a);
+    const size_t smem = sizeof(double) * (size_t)(MPT * PACT + RING * CHUNK_DOUBLES + MPT * 4) + 2 * RING * sizeof(uint64_t);
+    PB_TRY(pbi_smem_optin(ctx, (const void*)ensemble_kernel<MLP_GROUPS>, (size_t)(smem)));
+    ensemble_kernel<MLP_GROUPS><<<grid, (MLP_GROUPS * 4 + 4) * 32, smem, ctx->stream>>>(a);
     PB_LAUNCH_CHECK(ctx);
     cudaEventRecord(ctx->ev1, ctx->stream);
     PB_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
