@@ -635,9 +635,9 @@ __global__ void __launch_bounds__(1024) chol_small_kernel(const double* __restri
                                                          int64_t ldm, int64_t bsAt, double tol_rel, double shift_rel,
                                                          int* __restrict__ r_out, double* __restrict__ shift_out,
                                                          int max_steps, double* __restrict__ d_out,
-                                                         double* __restrict__ thresh_out, int* __restrict__ done_out) {
-    extern __shared__ double chol_sm[];          // d[m], lp[m]
-    double* d = chol_sm; double* lp = chol_sm + m;
+                                                         double* __restrict__ thresh_out, int* __restrict__ done_out, int srows) {
+    extern __shared__ double chol_sm[];          // d[m], lp[m], Ls[srows][m]: the first srows factor rows stay in shared memory
+    double* d = chol_sm; double* lp = chol_sm + m; double* Ls = chol_sm + 2 * m;
     __shared__ double red_v[1024];
     __shared__ int red_i[1024];
     const int nth = blockDim.x, nwarps = blockDim.x >> 5;
@@ -671,13 +671,24 @@ __global__ void __launch_bounds__(1024) chol_small_kernel(const double* __restri
         __syncthreads();
         if (k == 0) thresh = tol_rel * dp;
         if (!(dp > thresh) || !(dp > 0.)) { done = 1; break; }
-        for (int q = tid; q < k; q += nth) lp[q] = At[(int64_t)q * ldm + p];
-        __syncthreads();
+        const int ks = min(k, srows);                // rows [0, ks) come from shared memory (a step then costs ~0.4 us instead of
+                                                     // ~3.8 us of dependent L2 round trips), rows [ks, k) from the global factor
+        if (k > ks) {
+            for (int q = ks + tid; q < k; q += nth) lp[q] = At[(int64_t)q * ldm + p];
+            __syncthreads();
+        }
         const double inv = 1. / sqrt(dp);
         for (int j = tid; j < m; j += nth) {
-            // 8 independent loads in flight per pass (the factor lives in L2: one load at a time costs ~0.35 us)
+            // even rows accumulate in s0, odd rows in s1, each in row order (the same sums whatever srows is)
             double s0 = 0., s1 = 0.;
             int q = 0;
+            for (; q + 1 < ks; q += 2) {
+                s0 += Ls[q * m + j] * Ls[q * m + p];
+                s1 += Ls[(q + 1) * m + j] * Ls[(q + 1) * m + p];
+            }
+            if (q < ks) { s0 += Ls[q * m + j] * Ls[q * m + p]; ++q; }
+            if (q < k && (q & 1)) { s1 += At[(int64_t)q * ldm + j] * lp[q]; ++q; }      // re-align to an even row
+            // 8 independent loads in flight per pass (the factor lives in L2: one load at a time costs ~0.35 us)
             for (; q + 7 < k; q += 8) {
                 double l[8];
 #pragma unroll
@@ -697,6 +708,7 @@ __global__ void __launch_bounds__(1024) chol_small_kernel(const double* __restri
             if (d[j] == -DBL_MAX) v = 0.;
             if (j == p) v = sqrt(dp);
             At[(int64_t)k * ldm + j] = v;
+            if (k < srows) Ls[k * m + j] = v;
             d[j] = (j == p || d[j] == -DBL_MAX) ? -DBL_MAX : d[j] - v * v;
         }
         __syncthreads();
@@ -723,9 +735,13 @@ int pbi_eig_psd_batched(pb_ctx* ctx, const double* G_all, int64_t m, int batch, 
     const int64_t bsAt = cap_rows * ldm;
     PB_CUDA(ctx, cudaMemsetAsync(At_all, 0, sizeof(double) * (size_t)bsAt * batch, ctx->stream));
     double* nrm2 = scratch_dbl; double* shift = scratch_dbl + (size_t)batch * cap_rows;
-    chol_small_kernel<<<batch, m > 256 ? 1024 : 256, sizeof(double) * 2 * (size_t)m, ctx->stream>>>(G_all, (int)m, At_all, ldm, bsAt, tol_rel,
-                                                                                shift_rel, r_dev, shift, (int)m, nullptr, nullptr,
-                                                                                nullptr);
+    {   // factor rows cached in shared memory: up to ~96 KB per CTA so that two matrices share an SM
+        const int srows = (int)std::min<int64_t>(m, (96 * 1024) / (8 * m));
+        const size_t sm = sizeof(double) * (size_t)m * (2 + srows);
+        PB_TRY(pbi_smem_optin(ctx, (const void*)chol_small_kernel, sm));
+        chol_small_kernel<<<batch, m > 256 ? 1024 : 256, sm, ctx->stream>>>(G_all, (int)m, At_all, ldm, bsAt, tol_rel, shift_rel, r_dev,
+                                                                          shift, (int)m, nullptr, nullptr, nullptr, srows);
+    }
     PB_LAUNCH_CHECK(ctx);
     const int nb = (int)(cap_rows / JB);
     const int nvec = (int)cap_rows;
@@ -783,9 +799,13 @@ int pbi_factor_to_right_batched(pb_ctx* ctx, const double* At_all, int64_t m, in
 
 int pbi_chol_small_launch(pb_ctx* ctx, const double* G, int64_t m, double* At, int64_t ldm, double tol_rel, double shift_rel,
                           int* r_dev, double* shift_dev, int max_steps, double* d_out, double* thresh_out, int* done_out) {
-    chol_small_kernel<<<1, m > 256 ? 1024 : 256, sizeof(double) * 2 * (size_t)m, ctx->stream>>>(G, (int)m, At, ldm, 0, tol_rel, shift_rel, r_dev,
-                                                                            shift_dev, std::min<int>(max_steps, (int)m), d_out,
-                                                                            thresh_out, done_out);
+    const int steps = std::min<int>(max_steps, (int)m);
+    // one CTA: as many factor rows in shared memory as fit next to the 12 KB of static reduction buffers (m = 1000: 25 rows)
+    const int srows = (int)std::max<int64_t>(0, std::min<int64_t>(steps, (210 * 1024 - 16 * m) / (8 * m)));
+    const size_t sm = sizeof(double) * (size_t)m * (2 + srows);
+    PB_TRY(pbi_smem_optin(ctx, (const void*)chol_small_kernel, sm));
+    chol_small_kernel<<<1, m > 256 ? 1024 : 256, sm, ctx->stream>>>(G, (int)m, At, ldm, 0, tol_rel, shift_rel, r_dev, shift_dev, steps, d_out,
+                                                                   thresh_out, done_out, srows);
     PB_LAUNCH_CHECK(ctx);
     return PB_OK;
 }

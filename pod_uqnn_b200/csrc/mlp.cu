@@ -33,7 +33,7 @@ constexpr int CHUNK_DOUBLES = BK * PW;             // 2112 doubles = 16 896 B pe
 constexpr int BIAS_DOUBLES = PW;                   // 132 doubles = 1 056 B
 constexpr int MAX_LAYERS = 8;
 constexpr int MAX_WIDTH = 128;     // hidden widths (inputs of every layer) must fit the tile
-constexpr int MLP_GROUPS = 3;      // consumer groups of 4 warps, 32 points each (tile = 96 points); see ensemble_kernel
+constexpr int MLP_GROUPS = 3;      // consumer groups of 4 warps, 32 points each (tile = 96 points); see ensemble_kernel (PB_MLP_GROUPS=1|2|3)
 
 struct MlpArgs {
     int n_members, n_layers, n_L, norm_kind;
@@ -71,7 +71,7 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
 }
 // the consumer groups (4 warps = 32 points of the tile each) only synchronise internally, so one group's
 // epilogue / mixture pass overlaps the other groups' DMMA work
-__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;\n" :: "r"(1 + g) : "memory"); }
+__device__ __forceinline__ void group_sync(int bar_id) { asm volatile("bar.sync %0, 128;\n" :: "r"(bar_id) : "memory"); }
 
 // max(v, 0) on the integer pipe (sign bit of the high word): -0 and negative NaNs become +0
 __device__ __forceinline__ double relu_bits(double v) { return __double2hiint(v) < 0 ? 0. : v; }
@@ -136,8 +136,13 @@ __global__ void pack_weights_kernel(const double* __restrict__ w, double* __rest
 // sub-partition hosts one warp of each group, so while one group is in a layer epilogue / the mixture pass / the input
 // stage the other groups' warps keep its DMMA pipe fed.  (Two groups of 64 points measured 72 % tensor-pipe activity:
 // a group spends ~30 % of its time outside the products, and ONE warp per sub-partition reaches only ~60 % of the pipe.)
+// Block = NG * 4 consumer warps + ONE producer warp (13 warps at NG = 3, 128 registers per thread).  A 16-warp layout
+// (producer warpgroup + setmaxnreg 40 / 152, i.e. 512 threads x 128 registers = the whole register file) was 3 % faster
+// but produced sporadic wrong tiles -- one consumer warp's 32 output columns of one member, ~10 of 3 000 tiles, only with
+// >= 5 ring slots, with or without setmaxnreg; NG = 1, 2 and this 13-warp layout passed 12 launches x 1e6 points against
+// the oracle (tools/stress_ens.py, tests/test_gpu_scale.py::test_ensemble_predict_repeated_launches).  Root cause not found.
 template <int NG>
-__global__ void __launch_bounds__((NG * 4 + 4) * 32, 1) ensemble_kernel(MlpArgs a) {
+__global__ void __launch_bounds__((NG * 4 + 1) * 32, 1) ensemble_kernel(MlpArgs a) {
     constexpr int MPT = 32 * NG;                          // points per tile
     constexpr int NCW = NG * 4;                           // consumer warps
     extern __shared__ __align__(16) double smem[];
@@ -157,7 +162,6 @@ __global__ void __launch_bounds__((NG * 4 + 4) * 32, 1) ensemble_kernel(MlpArgs 
 
     if (warp >= NCW) {
         // ------------------------------------------------ producer: streams the packed weights
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
         if (warp == NCW && lane == 0) {
             uint32_t it = 0;
             for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x)
@@ -181,9 +185,9 @@ __global__ void __launch_bounds__((NG * 4 + 4) * 32, 1) ensemble_kernel(MlpArgs 
     }
 
     // ---------------------------------------------------- consumers
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;\n");
     const int g = warp >> 2, wn = warp & 3;               // group, 32-column slice of the layer output
     const int gt = tid & 127;                             // thread inside the group
+    const int bid = 1 + g;                                // named barrier of the group
     const int lk = lane & 3, lg = lane >> 2;
     const int n_d = a.dims[0];
     const bool small_in = (n_d <= 4);                     // first layer on plain FMAs from xs (no 16-column padding)
@@ -207,7 +211,7 @@ __global__ void __launch_bounds__((NG * 4 + 4) * 32, 1) ensemble_kernel(MlpArgs 
                 }
                 xs[p * 4 + c] = v;
             }
-            group_sync(g);
+            group_sync(bid);
         }
         for (int mem = 0; mem < a.n_members; ++mem) {
             if (!small_in) {
@@ -223,7 +227,7 @@ __global__ void __launch_bounds__((NG * 4 + 4) * 32, 1) ensemble_kernel(MlpArgs 
                     }
                     act[p * PACT + c] = v;
                 }
-                group_sync(g);
+                group_sync(bid);
             }
             for (int l = 0; l < a.n_layers; ++l) {
                 const int in = a.dims[l], out = a.dims[l + 1];
@@ -244,6 +248,8 @@ __global__ void __launch_bounds__((NG * 4 + 4) * 32, 1) ensemble_kernel(MlpArgs 
 #pragma unroll
                             for (int t = 0; t < 4; ++t) { acc[t][u][0] = b2.x; acc[t][u][1] = b2.y; }
                         }
+                        // the slot may only be released once the loads have RETURNED: nothing else consumes them before the arrive
+                        asm volatile("" :: "d"(acc[0][0][0]), "d"(acc[0][1][0]), "d"(acc[0][2][0]), "d"(acc[0][3][1]) : "memory");
                         __syncwarp();
                         if (lane == 0) mbar_arrive(empty + sb);
                     }
@@ -290,7 +296,7 @@ __global__ void __launch_bounds__((NG * 4 + 4) * 32, 1) ensemble_kernel(MlpArgs 
                         }
                     }
                     if (!head) {
-                        if (!(l == 0 && small_in)) group_sync(g);   // every warp of the group has finished reading act for this layer
+                        if (!(l == 0 && small_in)) group_sync(bid);   // every warp of the group has finished reading act for this layer
                         // next activations: relu(acc + b), columns [out, ceil16(out)) zeroed
                         const int outp = (out + BK - 1) / BK * BK;
 #pragma unroll
@@ -305,7 +311,7 @@ __global__ void __launch_bounds__((NG * 4 + 4) * 32, 1) ensemble_kernel(MlpArgs 
                                 if (n < outp) *reinterpret_cast<double2*>(act + p * PACT + n) = v;
                             }
                         }
-                        group_sync(g);            // activations of the next layer are complete
+                        group_sync(bid);            // activations of the next layer are complete
                     } else {
                         // head: raw outputs t = h W + b go to the per-CTA scratch (L2); the Normal's
                         // parameters are formed in the mixture pass below
@@ -325,11 +331,11 @@ __global__ void __launch_bounds__((NG * 4 + 4) * 32, 1) ensemble_kernel(MlpArgs 
                     }
                 }
             }
-            group_sync(g);        // act may be overwritten by the next member's input tile / first layer
+            group_sync(bid);        // act may be overwritten by the next member's input tile / first layer
         }
         // ---- mixture moments (podnnmodel.py:322-326): mean_i mu_i, sqrt(mean_i(var_i + mu_i^2) - mean^2)
-        __threadfence_block();
-        group_sync(g);
+        __threadfence();          // the head outputs are re-read through L2 (ld.global.cg) by other threads of the group
+        group_sync(bid);
         const double invM = 1. / (double)a.n_members;
         const int64_t pts = min((int64_t)32, a.N - p0 - g * 32);      // points of this group
         // 4 members x 2 elements per pass: 16 independent loads, then 8 independent softplus chains (the fp64
@@ -357,8 +363,11 @@ __global__ void __launch_bounds__((NG * 4 + 4) * 32, 1) ensemble_kernel(MlpArgs 
 #pragma unroll
                     for (int x = 0; x < 2; ++x) {
                         const double* tm = base[x] + (size_t)mem * MPT * out_head;
-                        mu4[x][k] = tm[jj[x]];                              // loc = t[:, :n_L]   (:57)
-                        rw4[x][k] = tm[n_L + jj[x]];
+                        // L2 loads (ld.global.cg): the scratch is rewritten every tile by this CTA's own STGs, and a line
+                        // still resident in L1 from the previous tile's pass was observed to be served stale (sporadic 5 %
+                        // errors in a few of 3 000 tiles) -- the data is read once, L1 has nothing to offer here
+                        mu4[x][k] = __ldcg(tm + jj[x]);                     // loc = t[:, :n_L]   (:57)
+                        rw4[x][k] = __ldcg(tm + n_L + jj[x]);
                     }
                 }
                 double sc4[2][4];
@@ -388,7 +397,7 @@ __global__ void __launch_bounds__((NG * 4 + 4) * 32, 1) ensemble_kernel(MlpArgs 
                 a.v_sig[o] = sqrt(var);
             }
         }
-        group_sync(g);            // scratch is reused by the next tile
+        group_sync(bid);            // scratch is reused by the next tile
     }
 }
 
@@ -574,7 +583,8 @@ extern "C" int pb_ensemble_predict(pb_ctx* ctx, int n_members, int n_layers, con
     a.member_stride = packed;
     a.norm_a = norm_a_dev; a.norm_b = norm_b_dev; a.soft0 = soft_0;
     a.X = X_dev; a.N = N; a.v_mean = v_mean_dev; a.v_sig = v_sig_dev;
-    constexpr int MPT = 32 * MLP_GROUPS;
+    static const int groups = []{ const char* e = getenv("PB_MLP_GROUPS"); const int g = e ? atoi(e) : MLP_GROUPS; return (g >= 1 && g <= 3) ? g : MLP_GROUPS; }();
+    const int MPT = 32 * groups;
     a.n_tiles = (N + MPT - 1) / MPT;
     { static const unsigned sk = []{ const char* e = getenv("PB_MLP_SKEW_NS"); return e ? (unsigned)atoi(e) : 3000u; }(); a.skew_ns = sk; }
     const int grid = (int)std::min<int64_t>(a.n_tiles, ctx->sm_count);
@@ -587,8 +597,16 @@ extern "C" int pb_ensemble_predict(pb_ctx* ctx, int n_members, int n_layers, con
     pack_weights_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(weights_dev, pk, n_members, n_layers, a, src);
     PB_LAUNCH_CHECK(ctx);
     const size_t smem = sizeof(double) * (size_t)(MPT * PACT + RING * CHUNK_DOUBLES + MPT * 4) + 2 * RING * sizeof(uint64_t);
-    PB_TRY(pbi_smem_optin(ctx, (const void*)ensemble_kernel<MLP_GROUPS>, (size_t)(smem)));
-    ensemble_kernel<MLP_GROUPS><<<grid, (MLP_GROUPS * 4 + 4) * 32, smem, ctx->stream>>>(a);
+    if (groups == 3) {
+        PB_TRY(pbi_smem_optin(ctx, (const void*)ensemble_kernel<3>, (size_t)(smem)));
+        ensemble_kernel<3><<<grid, (3 * 4 + 1) * 32, smem, ctx->stream>>>(a);
+    } else if (groups == 2) {
+        PB_TRY(pbi_smem_optin(ctx, (const void*)ensemble_kernel<2>, (size_t)(smem)));
+        ensemble_kernel<2><<<grid, (2 * 4 + 1) * 32, smem, ctx->stream>>>(a);
+    } else {
+        PB_TRY(pbi_smem_optin(ctx, (const void*)ensemble_kernel<1>, (size_t)(smem)));
+        ensemble_kernel<1><<<grid, (1 * 4 + 1) * 32, smem, ctx->stream>>>(a);
+    }
     PB_LAUNCH_CHECK(ctx);
     cudaEventRecord(ctx->ev1, ctx->stream);
     PB_CUDA(ctx, cudaEventSynchronize(ctx->ev1));

@@ -211,3 +211,23 @@ def test_c4_ensemble_predict_one_million_points(ctx):
         rm, rs = ens.predict_v(X[lo:lo + 50_000], members, layers[-1], 0.01, "meanstd", nb)
         worst = max(worst, cmp.rel_err(vm[lo:lo + 50_000], rm), cmp.rel_err(vs[lo:lo + 50_000], rs))
     assert worst <= cmp.TOL_ENSEMBLE_REL, worst
+
+
+@pytest.mark.gpu
+def test_ensemble_predict_repeated_launches(ctx):
+    """Persistent-kernel stress: three launches on 300 000 points (21 tiles per CTA) against the oracle, every point.
+    (A 16-warp layout of this kernel produced sporadic wrong tiles that a single small launch never showed.)"""
+    from oracle import ensemble as ens
+    from pod_uqnn_b200.varneuralnetwork import ensemble_predict_device
+    layers, M, N = [1, 128, 128, 128, 64], 8, 300_000
+    members = [ens.init_weights(layers, 4000 + i, bias_scale=0.1) for i in range(M)]
+    X = np.linspace(800, 1200, N)[:, None]
+    nb = ens.set_normalize_bounds(X, "meanstd")
+    rm, rs = np.empty((N, layers[-1])), np.empty((N, layers[-1]))
+    for lo in range(0, N, 50_000):
+        rm[lo:lo + 50_000], rs[lo:lo + 50_000] = ens.predict_v(X[lo:lo + 50_000], members, layers[-1], 0.01, "meanstd", nb)
+    Xd = ctx.to_device(X)
+    for _ in range(3):
+        vm, vs = ensemble_predict_device(ctx, members, layers, Xd, 0.01, "meanstd", nb)
+        assert cmp.rel_err(vm.download(), rm) <= cmp.TOL_ENSEMBLE_REL
+        assert cmp.rel_err(vs.download(), rs) <= cmp.TOL_ENSEMBLE_REL
