@@ -209,7 +209,9 @@ __device__ int inner_jacobi(double (*S)[SP], double (*Q)[SP], double* cs, double
                 }
                 cs[tid] = c; sn[tid] = s;
             }
-            rot_sweep += __syncthreads_count(did);
+            const int rot_round = __syncthreads_count(did);
+            rot_sweep += rot_round;
+            if (rot_round == 0) continue;      // no pair of this round rotates (late sweeps): skip the apply pass and its barrier
             {
                 const int P = tid / (JP / 2), R = tid % (JP / 2);
                 int p1, q1, p2, q2; inner_pair(cross, round, P, p1, q1); inner_pair(cross, round, R, p2, q2);
@@ -630,6 +632,19 @@ int pbi_factor_to_right(pb_ctx* ctx, const double* At, int64_t m, int k, const i
 // batched variant (two-step POD, pod.py:51-68): `batch` independent small PSD matrices
 // ---------------------------------------------------------------------------
 namespace {
+// warp arg-max over (v, i) for v > 0 (anything else counts as 0): on return every lane holds the largest v and the
+// smallest index that carries it; (0., 0x7fffffff) when no lane has a positive value
+__device__ __forceinline__ void warp_argmax_pos(double& v, int& i) {
+    const unsigned long long key = v > 0. ? (unsigned long long)__double_as_longlong(v) : 0ull;
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    const bool win = (hi == mh) && (lo == ml) && key != 0ull;
+    const unsigned mi = __reduce_min_sync(0xffffffffu, win ? (unsigned)i : 0x7fffffffu);
+    v = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+    i = (int)mi;
+}
+
 // pivoted Cholesky of one matrix per CTA (m <= 1024); same arithmetic as chol_kernel
 __global__ void __launch_bounds__(1024) chol_small_kernel(const double* __restrict__ Gall, int m, double* __restrict__ Atall,
                                                          int64_t ldm, int64_t bsAt, double tol_rel, double shift_rel,
@@ -657,18 +672,15 @@ __global__ void __launch_bounds__(1024) chol_small_kernel(const double* __restri
     for (; k < max_steps; ++k) {
         double bv = -DBL_MAX; int bi = 0x7fffffff;
         for (int j = tid; j < m; j += nth) { double v = d[j]; if (v > bv || (v == bv && j < bi)) { bv = v; bi = j; } }
-        // arg-max: warp shuffles, then the 8 warp results through shared memory (2 barriers instead of 9)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
+        // arg-max (largest value, smallest index among equals) on order-preserving integer keys with three warp REDUX
+        // instructions per level instead of five rounds of 64-bit shuffles and fp64 compares; values <= 0 (exhausted
+        // pivots carry -DBL_MAX) map to key 0 = "no pivot left".  One barrier: every warp reduces the warp results itself.
+        warp_argmax_pos(bv, bi);
         if ((tid & 31) == 0) { red_v[tid >> 5] = bv; red_i[tid >> 5] = bi; }
         __syncthreads();
-        bv = red_v[0]; bi = red_i[0];
-        for (int w = 1; w < nwarps; ++w) { const double ov = red_v[w]; const int oi = red_i[w]; if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; } }
+        bv = (tid & 31) < nwarps ? red_v[tid & 31] : 0.; bi = (tid & 31) < nwarps ? red_i[tid & 31] : 0x7fffffff;
+        warp_argmax_pos(bv, bi);
         const double dp = bv; const int p = bi;
-        __syncthreads();
         if (k == 0) thresh = tol_rel * dp;
         if (!(dp > thresh) || !(dp > 0.)) { done = 1; break; }
         const int ks = min(k, srows);                // rows [0, ks) come from shared memory (a step then costs ~0.4 us instead of
