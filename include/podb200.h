@@ -129,6 +129,15 @@ int  pb_snapshots_ackley_indexed(pb_ctx* ctx, int64_t n_xyz, const double* X_dev
                                  int64_t n_s, const double* mu_dev, int64_t row0, int64_t n_rows,
                                  double* U_dev, int64_t ldu);
 
+/* Ackley field on radius-sorted nodes (symmetric meshes repeat r = sqrt(.5 (x^2 + y^2)); the first term
+ * -20 (1 + .1 mu_2) exp(-.2 (1 + .1 mu_1) r) of experiments/2d_ackley/hyperparams.py:51-57 only depends on (r, sample)):
+ * perm (int32, n_rows) = the node ids of [row0, row0 + n_rows) ordered by r, r_sorted (n_rows) = their radii.
+ * One exp per run of equal radii instead of one per element; bit-identical to pb_snapshots_ackley_indexed. */
+int  pb_snapshots_ackley_grouped(pb_ctx* ctx, int64_t n_xyz, int n_ux, const double* ux_dev, const int* ix_dev,
+                                 int n_uy, const double* uy_dev, const int* iy_dev, int64_t n_s,
+                                 const double* mu_dev, int64_t row0, int64_t n_rows, const int* perm_dev,
+                                 const double* r_sorted_dev, double* U_dev, int64_t ldu);
+
 /* Known-answer matrix U = sum_k s_k phi_k psi_k^T (DCT-II vectors, s_k = 2^(-decay k)),
  * rows [row0, row0+n_rows) of an n_h x n_s matrix, filled in HBM. */
 int  pb_dct_lowrank(pb_ctx* ctx, int64_t n_h, int64_t n_s, int r, double decay,

@@ -50,6 +50,7 @@ SIGNATURES = {
     "pb_host_free": (_int, [_vp]),
     "pb_snapshots": (_int, [_vp, _int, _int, _i64, _vp, _i64, _int, _vp, _int, _vp, _i64, _i64, _vp, _i64]),
     "pb_snapshots_ackley_indexed": (_int, [_vp, _i64, _vp, _int, _vp, _vp, _int, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _i64]),
+    "pb_snapshots_ackley_grouped": (_int, [_vp, _i64, _int, _vp, _vp, _int, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _i64]),
     "pb_dct_lowrank": (_int, [_vp, _i64, _i64, _int, _dbl, _i64, _i64, _vp, _i64]),
     "pb_gram": (_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
     "pb_gemm_tn": (_int, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _vp]),

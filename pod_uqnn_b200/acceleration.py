@@ -22,11 +22,12 @@ def time_grid(t_min, t_max, n_t):
     return t_min + (np.arange(n_t) * (float(t_max) - float(t_min))) / (n_t - 1)
 
 
-def snapshots_device(ctx, u, X, mu_lhs, n_t=0, t_min=0., t_max=0., row0=0, n_rows=None, out=None):
+def snapshots_device(ctx, u, X, mu_lhs, n_t=0, t_min=0., t_max=0., row0=0, n_rows=None, out=None, ackley_path=None):
     """Fill (and return) the device snapshot matrix for nodes [row0, row0+n_rows).
 
     X is (dim, n_xyz) as the reference passes it (x_mesh[:, 1:].T).  Returns
-    (U_dev (n_rows, n_st), X_v host (n_st, n_d), t host or None).
+    (U_dev (n_rows, n_st), X_v host (n_st, n_d), t host or None).  `ackley_path` forces one of the three Ackley
+    kernels ("plain" | "indexed" | "grouped"; None = pick by the mesh's repeated coordinates / radii).
     """
     f = resolve(u)
     X = np.ascontiguousarray(X, dtype=np.float64)
@@ -46,9 +47,22 @@ def snapshots_device(ctx, u, X, mu_lhs, n_t=0, t_min=0., t_max=0., row0=0, n_row
         # tensor grids repeat coordinates: tabulate the separable term per distinct x / y (fields.cu)
         ux, ix = np.unique(X[0], return_inverse=True)
         uy, iy = np.unique(X[1], return_inverse=True)
-        if 4 * (len(ux) + len(uy)) <= n_xyz:
+        if 4 * (len(ux) + len(uy)) <= n_xyz and ackley_path != "plain":
             uxd, uyd = ctx.to_device(ux), ctx.to_device(uy)
             ixd, iyd = ctx.to_device_i32(ix), ctx.to_device_i32(iy)
+            # symmetric meshes repeat the radius of the first term: order this call's nodes by r so that one exp
+            # serves a whole run of equal radii (fields.cu, ackley_grouped_kernel); same bits as the indexed kernel
+            xs, ys = X[0, row0:row0 + n_rows], X[1, row0:row0 + n_rows]
+            r = np.sqrt(.5 * (xs ** 2 + ys ** 2))
+            order = np.argsort(r, kind="stable")
+            rs = r[order]
+            n_runs = 1 + int(np.count_nonzero(rs[1:] != rs[:-1])) if n_rows > 0 else 0
+            if ackley_path == "grouped" or (ackley_path is None and 2 * n_runs <= n_rows):
+                permd, rsd = ctx.to_device_i32(order + row0), ctx.to_device(rs)
+                ctx.check(_lib.lib().pb_snapshots_ackley_grouped(ctx.h, n_xyz, len(ux), uxd.ptr, ixd.ptr, len(uy), uyd.ptr,
+                                                                 iyd.ptr, n_s, mud.ptr, row0, n_rows, permd.ptr, rsd.ptr,
+                                                                 U.ptr, U.ld))
+                return U, mu.copy(), None
             ctx.check(_lib.lib().pb_snapshots_ackley_indexed(ctx.h, n_xyz, Xd.ptr, len(ux), uxd.ptr, ixd.ptr, len(uy),
                                                              uyd.ptr, iyd.ptr, n_s, mud.ptr, row0, n_rows, U.ptr, U.ld))
             return U, mu.copy(), None

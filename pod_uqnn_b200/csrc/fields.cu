@@ -23,7 +23,7 @@ __device__ __forceinline__ double dvd(double a, double b) { return __ddiv_rn(a, 
 // Shekel, experiments/1d_shekel/hyperparams.py:55-67: sum_k 1 / (bet_k + (x - gam_k)^2)
 __global__ void shekel_kernel(const double* __restrict__ X, int64_t n_rows, int64_t row0,
                               const double* __restrict__ mu, int64_t n_s, int n_mu,
-                              double* __restrict__ U, int64_t ldu) {
+                              double* __restrict__ U, int64_t ldu, int npb) {
     extern __shared__ double smu[];           // [n_mu][COLS_PER_BLOCK]
     const int64_t c0 = (int64_t)blockIdx.y * COLS_PER_BLOCK;
     for (int e = threadIdx.x; e < n_mu * COLS_PER_BLOCK; e += blockDim.x) {
@@ -33,8 +33,8 @@ __global__ void shekel_kernel(const double* __restrict__ X, int64_t n_rows, int6
     __syncthreads();
     const int64_t col = c0 + threadIdx.x;
     const int half = n_mu / 2;
-    const int64_t r_begin = (int64_t)blockIdx.x * NODES_PER_BLOCK;
-    const int64_t r_end = min(n_rows, r_begin + NODES_PER_BLOCK);
+    const int64_t r_begin = (int64_t)blockIdx.x * npb;
+    const int64_t r_end = min(n_rows, r_begin + npb);
     if (col >= n_s) return;
     for (int64_t r = r_begin; r < r_end; ++r) {
         const double x = X[row0 + r];
@@ -85,13 +85,14 @@ __global__ void ackley_kernel(const double* __restrict__ X, int64_t n_xyz, int64
 // table entries: one exp per element instead of two exp + two cos, which moves the kernel from the fp64
 // issue limit to the HBM write roofline.  exp(a) exp(b) vs exp(a + b): <= 3 ulp of a term <= e, i.e.
 // ~1e-16 of max|U| (the parity tolerance is 1e-13).
-__global__ void ackley_table_kernel(const double* __restrict__ u, int n_u, const double* __restrict__ mu, int64_t n_s,
-                                    int n_mu, double* __restrict__ E) {
+// (E holds the x table followed by the y table: one launch for both)
+__global__ void ackley_table_kernel(const double* __restrict__ ux, int n_ux, const double* __restrict__ uy, int n_uy,
+                                    const double* __restrict__ mu, int64_t n_s, int n_mu, double* __restrict__ E) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)n_u * n_s) return;
+    if (idx >= (int64_t)(n_ux + n_uy) * n_s) return;
     const int iu = (int)(idx / n_s); const int64_t s = idx % n_s;
     const double w = mul(6.283185307179586, add(1., mul(.1, mu[s * n_mu + 0])));
-    E[idx] = exp(mul(.5, cos(mul(w, u[iu]))));
+    E[idx] = exp(mul(.5, cos(mul(w, iu < n_ux ? ux[iu] : uy[iu - n_ux]))));
 }
 
 __global__ void ackley_indexed_kernel(const double* __restrict__ X, int64_t n_xyz, int64_t n_rows, int64_t row0,
@@ -132,15 +133,77 @@ __global__ void ackley_indexed_kernel(const double* __restrict__ X, int64_t n_xy
     }
 }
 
+// Ackley on radius-sorted nodes.  The first term a2 exp(c1 r) only depends on (r, sample), and a symmetric mesh
+// repeats radii (the 400 x 400 grid of C2 has 31 965 distinct values of r for 160 000 nodes): the host sorts the
+// nodes of this call by r (perm = node ids, rs = their radii), a thread keeps the last exp and re-evaluates it
+// only when r changes -- a warp-uniform branch -- so ~1 exp per 5 elements is left and the kernel is bound by
+// the HBM writes.  A row is still written as one contiguous segment per CTA; bit-identical to ackley_indexed_kernel.
+template <int VEC>   // VEC = 2: two adjacent columns per thread (16-byte table loads and stores; n_s, ldu even)
+__global__ void ackley_grouped_kernel(const int* __restrict__ perm, const double* __restrict__ rs, int64_t n_sorted,
+                                      int64_t row0, const int* __restrict__ ix, const int* __restrict__ iy,
+                                      const double* __restrict__ Ex, const double* __restrict__ Ey,
+                                      const double* __restrict__ mu, int64_t n_s, int n_mu,
+                                      double* __restrict__ U, int64_t ldu) {
+    const int64_t col = ((int64_t)blockIdx.y * COLS_PER_BLOCK + threadIdx.x) * VEC;
+    const int64_t e_begin = (int64_t)blockIdx.x * NODES_PER_BLOCK;
+    const int n_here = (int)(min(n_sorted, e_begin + NODES_PER_BLOCK) - e_begin);
+    __shared__ double sr[NODES_PER_BLOCK];
+    __shared__ int4 sidx[NODES_PER_BLOCK];           // {ix, iy, local row, -}: one LDS.128 per node
+    for (int e = threadIdx.x; e < n_here; e += blockDim.x) {
+        const int node = perm[e_begin + e];
+        sr[e] = rs[e_begin + e];
+        sidx[e] = make_int4(ix[node], iy[node], (int)(node - row0), 0);
+    }
+    __syncthreads();
+    if (col >= n_s) return;
+    double a2[VEC], c1[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        const int64_t c = min(col + v, n_s - 1);
+        a2[v] = mul(-20., add(1., mul(.1, mu[c * n_mu + 2])));
+        c1[v] = mul(-.2, add(1., mul(.1, mu[c * n_mu + 1])));
+    }
+    const double e1 = 2.718281828459045;
+    const double* __restrict__ exc = Ex + col;
+    const double* __restrict__ eyc = Ey + col;
+    double* __restrict__ uc = U + col;
+    const int ns = (int)n_s, ld = (int)ldu;
+    double last_r = -1., t1[VEC] = {};
+#pragma unroll 4
+    for (int e = 0; e < n_here; ++e) {
+        const int4 id = sidx[e];
+        double ex[VEC], ey[VEC], out[VEC];
+        if (VEC == 2) {
+            const double2 a = *reinterpret_cast<const double2*>(exc + (int64_t)id.x * ns);
+            const double2 b = *reinterpret_cast<const double2*>(eyc + (int64_t)id.y * ns);
+            ex[0] = a.x; ex[VEC - 1] = a.y; ey[0] = b.x; ey[VEC - 1] = b.y;
+        } else {
+            ex[0] = exc[(int64_t)id.x * ns]; ey[0] = eyc[(int64_t)id.y * ns];
+        }
+        const double r = sr[e];
+        if (r != last_r) {
+            last_r = r;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) t1[v] = mul(a2[v], exp(mul(c1[v], r)));
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) out[v] = add(add(sub(t1[v], mul(ex[v], ey[v])), 20.), e1);
+        double* dst = uc + (int64_t)id.z * ld;
+        // streaming stores: U is written once and must not push the two tables out of L2
+        if (VEC == 2) __stcs(reinterpret_cast<double2*>(dst), make_double2(out[0], out[VEC - 1]));
+        else __stcs(dst, out[0]);
+    }
+}
+
 // Burgers, experiments/1dt_burger/hyperparams.py:45-55.  Column = i_sample * n_t + j_time.
 __global__ void burgers_kernel(const double* __restrict__ X, int64_t n_rows, int64_t row0,
                                const double* __restrict__ mu, int64_t n_s, int n_mu,
                                const double* __restrict__ t, int n_t,
-                               double* __restrict__ U, int64_t ldu) {
+                               double* __restrict__ U, int64_t ldu, int npb) {
     const int64_t n_st = n_s * n_t;
     const int64_t col = (int64_t)blockIdx.y * COLS_PER_BLOCK + threadIdx.x;
-    const int64_t r_begin = (int64_t)blockIdx.x * NODES_PER_BLOCK;
-    const int64_t r_end = min(n_rows, r_begin + NODES_PER_BLOCK);
+    const int64_t r_begin = (int64_t)blockIdx.x * npb;
+    const int64_t r_end = min(n_rows, r_begin + npb);
     if (col >= n_st) return;
     const int64_t i = col / n_t; const int j = (int)(col % n_t);
     const double m = mu[i * n_mu], tj = t[j];
@@ -194,11 +257,16 @@ extern "C" int pb_snapshots(pb_ctx* ctx, int field, int dim, int64_t n_xyz, cons
     dim3 grid((unsigned)((n_rows + NODES_PER_BLOCK - 1) / NODES_PER_BLOCK),
               (unsigned)((n_st + COLS_PER_BLOCK - 1) / COLS_PER_BLOCK));
     if (grid.y > 65535) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_snapshots: too many snapshot columns (%lld)", (long long)n_st);
+    // Shekel / Burgers are bound by fp64 issue (divisions, exp) on small meshes: fewer nodes per CTA until the grid
+    // holds >= 8 CTAs of 128 threads per SM (C1: 400 nodes x 1000 samples was 56 CTAs on 148 SMs)
+    int npb = NODES_PER_BLOCK;
+    while (npb > 2 && ((n_rows + npb - 1) / npb) * (int64_t)grid.y < 8 * (int64_t)ctx->sm_count) npb /= 2;
+    dim3 grid_small((unsigned)((n_rows + npb - 1) / npb), grid.y);
     switch (field) {
     case PB_FIELD_SHEKEL:
         if (dim != 1 || n_t > 0 || n_mu < 2 || (n_mu % 2)) PB_FAIL(ctx, PB_ERR_SHAPE, "shekel: dim=1, steady, even n_mu");
-        shekel_kernel<<<grid, COLS_PER_BLOCK, (size_t)n_mu * COLS_PER_BLOCK * sizeof(double), ctx->stream>>>(
-            X_dev, n_rows, row0, mu_dev, n_s, n_mu, U_dev, ldu);
+        shekel_kernel<<<grid_small, COLS_PER_BLOCK, (size_t)n_mu * COLS_PER_BLOCK * sizeof(double), ctx->stream>>>(
+            X_dev, n_rows, row0, mu_dev, n_s, n_mu, U_dev, ldu, npb);
         break;
     case PB_FIELD_ACKLEY:
         if (dim != 2 || n_t > 0 || n_mu != 3) PB_FAIL(ctx, PB_ERR_SHAPE, "ackley: dim=2, steady, n_mu=3");
@@ -206,7 +274,7 @@ extern "C" int pb_snapshots(pb_ctx* ctx, int field, int dim, int64_t n_xyz, cons
         break;
     case PB_FIELD_BURGERS:
         if (dim != 1 || n_t <= 0 || n_mu != 1 || !t_dev) PB_FAIL(ctx, PB_ERR_SHAPE, "burgers: dim=1, n_t>0, n_mu=1");
-        burgers_kernel<<<grid, COLS_PER_BLOCK, 0, ctx->stream>>>(X_dev, n_rows, row0, mu_dev, n_s, n_mu, t_dev, n_t, U_dev, ldu);
+        burgers_kernel<<<grid_small, COLS_PER_BLOCK, 0, ctx->stream>>>(X_dev, n_rows, row0, mu_dev, n_s, n_mu, t_dev, n_t, U_dev, ldu, npb);
         break;
     default:
         PB_FAIL(ctx, PB_ERR_UNSUPPORTED_FIELD, "pb_snapshots: field id %d is not registered (no CPU fallback)", field);
@@ -229,14 +297,46 @@ extern "C" int pb_snapshots_ackley_indexed(pb_ctx* ctx, int64_t n_xyz, const dou
     cudaEventRecord(ctx->ev0, ctx->stream);
     PB_TRY(pb_reserve(ctx, &ctx->ws, &ctx->ws_bytes, (size_t)(n_ux + n_uy) * n_s));
     double* Ex = ctx->ws; double* Ey = Ex + (size_t)n_ux * n_s;
-    ackley_table_kernel<<<(unsigned)(((int64_t)n_ux * n_s + 255) / 256), 256, 0, ctx->stream>>>(ux_dev, n_ux, mu_dev, n_s, 3, Ex);
-    PB_LAUNCH_CHECK(ctx);
-    ackley_table_kernel<<<(unsigned)(((int64_t)n_uy * n_s + 255) / 256), 256, 0, ctx->stream>>>(uy_dev, n_uy, mu_dev, n_s, 3, Ey);
+    ackley_table_kernel<<<(unsigned)(((int64_t)(n_ux + n_uy) * n_s + 255) / 256), 256, 0, ctx->stream>>>(ux_dev, n_ux, uy_dev, n_uy,
+                                                                                                        mu_dev, n_s, 3, Ex);
     PB_LAUNCH_CHECK(ctx);
     dim3 grid((unsigned)((n_rows + NODES_PER_BLOCK - 1) / NODES_PER_BLOCK), (unsigned)((n_s + COLS_PER_BLOCK - 1) / COLS_PER_BLOCK));
     if (grid.y > 65535) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_snapshots_ackley_indexed: too many snapshot columns");
     ackley_indexed_kernel<<<grid, COLS_PER_BLOCK, 0, ctx->stream>>>(X_dev, n_xyz, n_rows, row0, ix_dev, iy_dev, Ex, Ey, mu_dev, n_s, 3,
                                                                   U_dev, ldu);
+    PB_LAUNCH_CHECK(ctx);
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    PB_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->ms[PB_T_SNAPSHOTS] = ms;
+    return PB_OK;
+}
+
+extern "C" int pb_snapshots_ackley_grouped(pb_ctx* ctx, int64_t n_xyz, int n_ux, const double* ux_dev, const int* ix_dev,
+                                           int n_uy, const double* uy_dev, const int* iy_dev, int64_t n_s,
+                                           const double* mu_dev, int64_t row0, int64_t n_rows, const int* perm_dev,
+                                           const double* r_sorted_dev, double* U_dev, int64_t ldu) {
+    PB_ENTER(ctx);
+    if (n_xyz <= 0 || n_s <= 0 || n_rows < 0 || row0 < 0 || row0 + n_rows > n_xyz || n_ux <= 0 || n_uy <= 0 || ldu < n_s ||
+        n_xyz > INT32_MAX)
+        PB_FAIL(ctx, PB_ERR_SHAPE, "pb_snapshots_ackley_grouped: bad shape");
+    if (n_rows == 0) return PB_OK;
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    PB_TRY(pb_reserve(ctx, &ctx->ws, &ctx->ws_bytes, (size_t)(n_ux + n_uy) * n_s));
+    double* Ex = ctx->ws; double* Ey = Ex + (size_t)n_ux * n_s;
+    ackley_table_kernel<<<(unsigned)(((int64_t)(n_ux + n_uy) * n_s + 255) / 256), 256, 0, ctx->stream>>>(ux_dev, n_ux, uy_dev, n_uy,
+                                                                                                        mu_dev, n_s, 3, Ex);
+    PB_LAUNCH_CHECK(ctx);
+    const bool vec2 = n_s % 2 == 0 && ldu % 2 == 0 && ((uintptr_t)U_dev % 16) == 0 && ldu < INT32_MAX;
+    const int cols_per_block = COLS_PER_BLOCK * (vec2 ? 2 : 1);
+    dim3 grid((unsigned)((n_rows + NODES_PER_BLOCK - 1) / NODES_PER_BLOCK), (unsigned)((n_s + cols_per_block - 1) / cols_per_block));
+    if (grid.y > 65535 || (int64_t)(n_ux > n_uy ? n_ux : n_uy) * n_s > INT32_MAX || ldu > INT32_MAX)
+        PB_FAIL(ctx, PB_ERR_SHAPE, "pb_snapshots_ackley_grouped: too many snapshot columns");
+    if (vec2)
+        ackley_grouped_kernel<2><<<grid, COLS_PER_BLOCK, 0, ctx->stream>>>(perm_dev, r_sorted_dev, n_rows, row0, ix_dev, iy_dev, Ex, Ey,
+                                                                         mu_dev, n_s, 3, U_dev, ldu);
+    else
+        ackley_grouped_kernel<1><<<grid, COLS_PER_BLOCK, 0, ctx->stream>>>(perm_dev, r_sorted_dev, n_rows, row0, ix_dev, iy_dev, Ex, Ey,
+                                                                         mu_dev, n_s, 3, U_dev, ldu);
     PB_LAUNCH_CHECK(ctx);
     cudaEventRecord(ctx->ev1, ctx->stream);
     PB_CUDA(ctx, cudaEventSynchronize(ctx->ev1));

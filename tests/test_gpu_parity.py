@@ -68,6 +68,26 @@ def test_snapshot_row_sharding(ctx):
     assert np.array_equal(part.download(), full.download()[100:157])
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_s", [133, 70])          # odd: one column per thread, even: two (16-byte accesses)
+def test_ackley_kernel_variants_agree(ctx, n_s):
+    """Radius-grouped (sorted nodes, one exp per run of equal radii) == coordinate-indexed, bit for bit; both within
+    a few ulp of the plain per-element kernel; ragged node ranges and a non-symmetric mesh included."""
+    w = wl.ackley(50, 36, n_s)
+    X = w["x_mesh"][:, 1:].T
+    plain = snapshots_device(ctx, "ackley", X, w["mu"], ackley_path="plain")[0].download()
+    for row0, n_rows in ((0, None), (70, 1), (123, 1001)):
+        a = snapshots_device(ctx, "ackley", X, w["mu"], row0=row0, n_rows=n_rows, ackley_path="indexed")[0].download()
+        b = snapshots_device(ctx, "ackley", X, w["mu"], row0=row0, n_rows=n_rows, ackley_path="grouped")[0].download()
+        assert np.array_equal(a, b)
+        hi = X.shape[1] if n_rows is None else row0 + n_rows
+        assert np.abs(a - plain[row0:hi]).max() <= 1e-14 * np.abs(plain).max()
+    Xs = X.copy(); Xs[0] += .37                    # shifted: few repeated radii, the default picks the indexed kernel
+    c = snapshots_device(ctx, "ackley", Xs, w["mu"])[0].download()
+    d = snapshots_device(ctx, "ackley", Xs, w["mu"], ackley_path="grouped")[0].download()
+    assert np.array_equal(c, d)
+
+
 # ------------------------------------------------------------------ products
 @pytest.mark.parametrize("rows,ka,kb,sym", [(1000, 200, 200, True), (5000, 1000, 1000, True), (777, 71, 71, True),
                                             (3001, 14, 300, False), (4096, 71, 333, False), (40, 129, 129, True),
