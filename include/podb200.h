@@ -335,6 +335,15 @@ int  pb_predict_U(pb_ctx* ctx, const double* V_dev, int64_t ldv, int64_t n_rows,
                   const double* v_mean_dev, const double* v_sig_dev, int64_t N,
                   int samples, uint64_t seed, double* U_mean_dev, double* U_sig_dev, int64_t ldo);
 
+/* Mixture of the ensemble members at the U level, PodnnModel.predict_mc (podnnmodel.py:344-362), kept in HBM:
+ * accumulate: sum += U_mean_i, m2 += U_sig_i^2 + U_mean_i^2 (first != 0 overwrites instead of adding);
+ * finalize (in place): sum <- U_pred = sum / n_members, m2 <- sqrt(m2 / n_members - U_pred^2) (+ pod_sig[row] when
+ * pod_sig_dev is not NULL, :359-360).  All matrices n_rows x N with the given leading dimensions. */
+int  pb_mixture_accumulate(pb_ctx* ctx, const double* U_mean_dev, const double* U_sig_dev, int64_t ld_in,
+                           int64_t n_rows, int64_t N, double* sum_dev, double* m2_dev, int64_t ld_acc, int first);
+int  pb_mixture_finalize(pb_ctx* ctx, double* sum_dev, double* m2_dev, int64_t ld, int64_t n_rows, int64_t N,
+                         int n_members, const double* pod_sig_dev);
+
 /* Ensemble training, SURVEY.md section 8 row f4: `epochs` full-batch steps of VarNeuralNetwork.grad +
  * tf_optimization_step (varneuralnetwork.py:94-128; optimiser tf.keras.optimizers.Adam(lr) :24, L2 term :88-92)
  * for all members at once.  dims = [n_d, hidden..., 2 n_L] (n_layers + 1 entries).

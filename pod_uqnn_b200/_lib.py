@@ -82,6 +82,8 @@ SIGNATURES = {
     "pb_reconstruct": (_int, [_vp, _vp, _i64, _int, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp]),
     "pb_ensemble_predict": (_int, [_vp, _int, _int, _pi, _vp, _int, _vp, _vp, _dbl, _vp, _i64, _vp, _vp]),
     "pb_predict_U": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp, _i64, _int, C.c_uint64, _vp, _vp, _i64]),
+    "pb_mixture_accumulate": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _int]),
+    "pb_mixture_finalize": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
     "pb_ensemble_train": (_int, [_vp, _int, _int, _pi, _vp, _vp, _vp, _i64, _int, _dbl, _dbl, _int, _dbl, _dbl, _vp, _vp, _i64,
                           _vp, _int]),
     "pb_dct_basis": (_int, [_vp, _i64, _int, _i64, _i64, _vp, _i64]),

@@ -419,6 +419,8 @@ int pb_pod_pass2_gram(pb_ctx* ctx, const double* A, int64_t rows, int64_t lda, d
     PB_ENTER(ctx);
     const int keep = ctx->n_keep; const int64_t m = ctx->m;
     if (keep <= 0) PB_FAIL(ctx, PB_ERR_ARG, "pb_pod_pass2_gram: the last decomposition has no second pass (mode GRAM)");
+    Timer t2(ctx, PB_T_PASS2);       // stopped by pb_pod_pass2_finish (a sharded caller sums G2 over the GPUs in between)
+    ctx->pass2_t_started = true;
     PB_TRY(pb_reserve(ctx, &ctx->Wk, &ctx->Wk_cap, (size_t)m * keep));
     PB_TRY(pbi_factor_to_right(ctx, ctx->At, m, keep, ctx->perm, ctx->nrm, nullptr, ctx->Wk, keep));
     PB_TRY(pbi_gemm_nn(ctx, A, lda, rows, m, ctx->Wk, keep, keep, Y, keep, nullptr, 0, nullptr));
@@ -440,6 +442,10 @@ int pb_pod_pass2_finish(pb_ctx* ctx, const double* G2, double eps, int n_L_in, i
     PB_TRY(finish_rank(ctx, ctx->sig2, keep, ctx->r2, eps, n_L_in, n_L));
     ctx->pass2_done = true;
     ctx->refine_steps = refine_steps_needed(ctx);
+    if (ctx->pass2_t_started) {
+        cudaEventRecord(ctx->tev[PB_T_PASS2][1], ctx->stream);
+        ctx->t_pending[PB_T_PASS2] = true; ctx->pass2_t_started = false;
+    }
     return PB_OK;
 }
 
@@ -571,13 +577,11 @@ static int pod_after_gram(pb_ctx* ctx, const double* A, int64_t rows, int64_t m,
     int keep = 0;
     PB_TRY(pb_pod_from_gram(ctx, ctx->Gbuf, m, eps, n_L_in, mode, n_L, &keep));
     ctx->ms[PB_T_PASS2] = 0.; ctx->t_pending[PB_T_PASS2] = false;
-    if (keep > 0) {
-        Timer t2(ctx, PB_T_PASS2);
+    if (keep > 0) {      // (PB_T_PASS2 is armed by the two calls themselves: the sharded drivers issue them separately)
         PB_TRY(pb_reserve(ctx, &ctx->Ybuf, &ctx->Y_cap, (size_t)rows * keep));
         PB_TRY(pb_reserve(ctx, &ctx->G2buf, &ctx->G2_cap, (size_t)keep * keep));
         PB_TRY(pb_pod_pass2_gram(ctx, A, rows, lda, ctx->Ybuf, ctx->G2buf));
         PB_TRY(pb_pod_pass2_finish(ctx, ctx->G2buf, eps, n_L_in, n_L));
-        t2.stop();
     }
     return PB_OK;
 }

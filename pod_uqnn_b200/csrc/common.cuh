@@ -24,6 +24,7 @@ struct pb_ctx {
     cudaEvent_t evr0 = nullptr, evr1 = nullptr;     // user region timer
     cudaEvent_t tev[PB_T_COUNT][2] = {{nullptr}};   // stage timers: recorded on the stream, read lazily by pb_last_ms
     bool t_pending[PB_T_COUNT] = {false};           // (no host synchronisation inside the ops)
+    bool pass2_t_started = false;        // pb_pod_pass2_gram recorded the start event of PB_T_PASS2
     bool sigma_pending = false;                     // h_sig (pinned) is being filled by an async copy; pb_pod_sigma finishes it
     double* h_sig = nullptr; size_t h_sig_cap = 0; int64_t sig_count = 0, sig_total = 0;
     bool tn_timing_pending = false;

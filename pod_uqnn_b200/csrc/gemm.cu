@@ -461,6 +461,8 @@ int pbi_gram_tma(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int64_t 
                  int64_t rows_per_split, double* ws, int64_t split_stride, bool time_it);
 int pbi_gram_streamk(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, int64_t rows, double* C, int64_t ldc,
                      bool time_it);
+int pbi_qr_tn(pb_ctx* ctx, const double* W, int64_t ldw, int64_t n, int64_t rows, int splits, int64_t rows_per_split,
+              double* out, int64_t ldo, int64_t split_stride);
 namespace {
 thread_local bool g_time_tn = false;   // set per call by pbi_gemm_tn; thread-local: several contexts may run in parallel threads (multi.cu)
 
@@ -493,6 +495,12 @@ int launch_tn(pb_ctx* ctx, const double* A, int64_t lda, int64_t ka, const doubl
     }
     if (sym && BM == 128 && BN == 128 && bt.count == 1) {     // TMA + mbarrier pipeline when the layout allows it
         int rc = pbi_gram_tma(ctx, A, lda, ka, rows, splits, rps, ctx->ws, split_stride, g_time_tn);
+        if (rc < 0) return rc;
+        if (rc == PB_OK) goto reduce;
+    }
+    if (!sym && BM == 64 && BN == 256 && bt.count == 1 && A == B && lda == ldb && ka == 64) {
+        // the QR trailing product Y^T [Y | C]: TMA + mbarrier kernel (qr_tn.cu), same split layout
+        int rc = pbi_qr_tn(ctx, A, lda, kb, rows, splits, rps, out, ldo, split_stride);
         if (rc < 0) return rc;
         if (rc == PB_OK) goto reduce;
     }

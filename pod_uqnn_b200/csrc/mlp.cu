@@ -446,6 +446,31 @@ __global__ void mc_finalize_kernel(double* __restrict__ sum, double* __restrict_
     sq[o] = sqrt(fmax(S * b - a * a, 0.) / (S * (S - 1.)));
 }
 
+// Gaussian mixture of the members at the U level (podnnmodel.py:344-362): running sum of the member means and of
+// sig_i^2 + U_i^2, then U_pred = mean, U_sig = sqrt(mean(sig^2 + U^2) - U_pred^2) (+ pod_sig per row)
+__global__ void mixture_accumulate_kernel(const double* __restrict__ Um, const double* __restrict__ Us, int64_t ldi,
+                                          double* __restrict__ sum, double* __restrict__ m2, int64_t lda,
+                                          int64_t rows, int64_t cols, int first) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int64_t r = i / cols, c = i % cols;
+    const double u = Um[r * ldi + c], sg = Us[r * ldi + c];
+    const double q = sg * sg + u * u;
+    const int64_t o = r * lda + c;
+    sum[o] = first ? u : sum[o] + u;
+    m2[o] = first ? q : m2[o] + q;
+}
+__global__ void mixture_finalize_kernel(double* __restrict__ sum, double* __restrict__ m2, int64_t ld, int64_t rows,
+                                        int64_t cols, double n_members, const double* __restrict__ pod_sig) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int64_t r = i / cols, o = r * ld + i % cols;
+    const double mean = sum[o] / n_members;
+    double sg = sqrt(m2[o] / n_members - mean * mean);      // NaN for a negative rounding residue, as np.sqrt
+    if (pod_sig) sg += pod_sig[r];
+    sum[o] = mean; m2[o] = sg;
+}
+
 // closed-form U-level moments: U_mean = V v_mean^T ; U_sig = sqrt((V*V) (v_sig^2)^T)
 __global__ void square_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -668,5 +693,29 @@ extern "C" int pb_predict_U(pb_ctx* ctx, const double* V_dev, int64_t ldv, int64
         cudaFree(V2); cudaFree(s2);
         if (rc != PB_OK) return rc;
     }
+    return PB_OK;
+}
+
+extern "C" int pb_mixture_accumulate(pb_ctx* ctx, const double* U_mean_dev, const double* U_sig_dev, int64_t ld_in,
+                                     int64_t n_rows, int64_t N, double* sum_dev, double* m2_dev, int64_t ld_acc, int first) {
+    PB_ENTER(ctx);
+    if (n_rows <= 0 || N <= 0 || ld_in < N || ld_acc < N || !U_mean_dev || !U_sig_dev || !sum_dev || !m2_dev)
+        PB_FAIL(ctx, PB_ERR_SHAPE, "pb_mixture_accumulate: bad shape");
+    const int64_t n = n_rows * N;
+    mixture_accumulate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(U_mean_dev, U_sig_dev, ld_in, sum_dev, m2_dev,
+                                                                                   ld_acc, n_rows, N, first);
+    PB_LAUNCH_CHECK(ctx);
+    return PB_OK;
+}
+
+extern "C" int pb_mixture_finalize(pb_ctx* ctx, double* sum_dev, double* m2_dev, int64_t ld, int64_t n_rows, int64_t N,
+                                   int n_members, const double* pod_sig_dev) {
+    PB_ENTER(ctx);
+    if (n_rows <= 0 || N <= 0 || ld < N || n_members <= 0 || !sum_dev || !m2_dev)
+        PB_FAIL(ctx, PB_ERR_SHAPE, "pb_mixture_finalize: bad shape");
+    const int64_t n = n_rows * N;
+    mixture_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(sum_dev, m2_dev, ld, n_rows, N, (double)n_members,
+                                                                                 pod_sig_dev);
+    PB_LAUNCH_CHECK(ctx);
     return PB_OK;
 }

@@ -383,21 +383,28 @@ class PodnnModel:
         members, layers, soft_0, norm, nb = self._ensemble_args()
         Xd = ctx.to_device(np.asarray(X_v, dtype=np.float64).reshape(-1, layers[0]))
         N = Xd.shape[0]
-        U_sum, U_m2 = np.zeros((self.n_h, N)), np.zeros((self.n_h, N))
         print(f"Ensembling {len(members)} predictions...")
-        for i, w in enumerate(members):
-            vm, vs = ensemble_predict_device(ctx, [w], layers, Xd, soft_0, norm, nb)
-            for j0, j1, Um, Us, t in self._u_tiles(N):
-                ctx.check(_lib.lib().pb_predict_U(ctx.h, Vd.ptr, Vd.ld, self.n_h, self.n_L, vm.ptr + 8 * j0 * self.n_L,
-                                                  vs.ptr + 8 * j0 * self.n_L, j1 - j0, int(samples) if monte_carlo else 0,
-                                                  int(seed) + i + 7919 * t, Um.ptr, Us.ptr, Um.ld))
-                U_i, sig_i = Um.download(), Us.download()
-                U_sum[:, j0:j1] += U_i
-                U_m2[:, j0:j1] += sig_i ** 2 + U_i ** 2
-        U_pred = U_sum / len(members)
-        U_pred_sig = np.sqrt(U_m2 / len(members) - U_pred ** 2)
-        if self.pod_sig is not None:
-            U_pred_sig += self.pod_sig[:, np.newaxis]
+        L = _lib.lib()
+        v_members = [ensemble_predict_device(ctx, [w], layers, Xd, soft_0, norm, nb) for w in members]
+        sig_d = ctx.to_device(np.asarray(self.pod_sig, dtype=np.float64)) if self.pod_sig is not None else None
+        U_pred, U_pred_sig = np.empty((self.n_h, N)), np.empty((self.n_h, N))
+        acc = {}
+        # the member mixture stays in HBM: per column tile the member moments are accumulated on the device and only
+        # the finished U_pred / U_pred_sig tiles cross PCIe
+        for j0, j1, Um, Us, t in self._u_tiles(N):
+            if (j1 - j0) not in acc:
+                acc.clear()
+                acc[j1 - j0] = (ctx.alloc(self.n_h, j1 - j0), ctx.alloc(self.n_h, j1 - j0))
+            S1, S2 = acc[j1 - j0]
+            for i, (vm, vs) in enumerate(v_members):
+                ctx.check(L.pb_predict_U(ctx.h, Vd.ptr, Vd.ld, self.n_h, self.n_L, vm.ptr + 8 * j0 * self.n_L,
+                                         vs.ptr + 8 * j0 * self.n_L, j1 - j0, int(samples) if monte_carlo else 0,
+                                         int(seed) + i + 7919 * t, Um.ptr, Us.ptr, Um.ld))
+                ctx.check(L.pb_mixture_accumulate(ctx.h, Um.ptr, Us.ptr, Um.ld, self.n_h, j1 - j0, S1.ptr, S2.ptr, S1.ld,
+                                                  1 if i == 0 else 0))
+            ctx.check(L.pb_mixture_finalize(ctx.h, S1.ptr, S2.ptr, S1.ld, self.n_h, j1 - j0, len(members),
+                                            sig_d.ptr if sig_d is not None else None))
+            U_pred[:, j0:j1], U_pred_sig[:, j0:j1] = S1.download(), S2.download()
         return U_pred, U_pred_sig
 
     # ------------------------------------------------------------ layout helpers (host index maps)

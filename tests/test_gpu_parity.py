@@ -114,6 +114,21 @@ def test_gemm_tn(ctx, rows, ka, kb, sym):
         assert np.array_equal(Cd2.download(), Cg)          # deterministic (fixed-order split-K)
 
 
+@pytest.mark.parametrize("rows,n", [(3000, 512), (20011, 576), (70000, 1000), (9000, 4096), (1500, 328)])
+def test_gemm_tn_qr_trailing_product(ctx, rows, n):
+    """Y^T [Y | C] with Y = the first 64 columns of the same matrix: the TSQR trailing product (TMA kernel qr_tn.cu for
+    n >= 512, tile rows split over row ranges; narrower shapes take the cp.async kernels) against numpy."""
+    rng = np.random.default_rng(rows + n)
+    W = rng.standard_normal((rows, n))
+    Wd, Zd = ctx.to_device(W), ctx.alloc(64, n)
+    L = _lib.lib()
+    ctx.check(L.pb_gemm_tn(ctx.h, Wd.ptr, Wd.ld, 64, Wd.ptr, Wd.ld, n, rows, Zd.ptr))
+    Z = Zd.download()
+    assert cmp.rel_err(Z, W[:, :64].T @ W) < 1e-13
+    ctx.check(L.pb_gemm_tn(ctx.h, Wd.ptr, Wd.ld, 64, Wd.ptr, Wd.ld, n, rows, Zd.ptr))
+    assert np.array_equal(Zd.download(), Z)                # deterministic (fixed-order split sum)
+
+
 @pytest.mark.parametrize("rows,m,k", [(1000, 200, 14), (5000, 1000, 71), (777, 333, 333), (130, 14, 1000),
                                       (300, 71, 2), (999, 15, 33), (1, 3, 1)])
 def test_gemm_nn(ctx, rows, m, k):
