@@ -1056,7 +1056,7 @@ int pb_fast_pod(pb_ctx* ctx, const double* U, int64_t n_h, int n_t, int64_t n_s,
     if (n_t <= 0 || n_s <= 0 || ldu < n_s * n_t) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_fast_pod: bad shape");
     if (mode < PB_POD_GRAM || mode > PB_POD_TSQR) PB_FAIL(ctx, PB_ERR_ARG, "pb_fast_pod: unknown mode %d", mode);
     if (!(eps >= 0.) || eps >= 1. || !(eps_init >= 0.) || eps_init >= 1.) PB_FAIL(ctx, PB_ERR_ARG, "pb_fast_pod: eps in [0, 1)");
-    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEvent_t e0 = ctx->ev2, e1 = ctx->ev3;          // context-owned (the inner pb_pod calls use their own pairs)
     cudaEventRecord(e0, ctx->stream);
     // stage 1: per-sample bases T_k, packed side by side into U_f (n_h x sum r_k); r_k <= min(n_h, n_t)
     const int64_t cap_per = std::min<int64_t>(n_h, n_t);
@@ -1084,7 +1084,6 @@ int pb_fast_pod(pb_ctx* ctx, const double* U, int64_t n_h, int n_t, int64_t n_s,
     ctx->uf_rows = n_h; ctx->uf_cols = off; ctx->uf_ld = ldf;
     cudaEventRecord(e1, ctx->stream); cudaEventSynchronize(e1);
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ctx->ms[PB_T_POD_TOTAL] = ms; ctx->t_pending[PB_T_POD_TOTAL] = false;
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     return rc;
 }
 

@@ -448,7 +448,7 @@ __global__ void mc_finalize_kernel(double* __restrict__ sum, double* __restrict_
 
 // Gaussian mixture of the members at the U level (podnnmodel.py:344-362): running sum of the member means and of
 // sig_i^2 + U_i^2, then U_pred = mean, U_sig = sqrt(mean(sig^2 + U^2) - U_pred^2) (+ pod_sig per row)
-__global__ void mixture_accumulate_kernel(const double* __restrict__ Um, const double* __restrict__ Us, int64_t ldi,
+__global__ void u_mixture_accumulate_kernel(const double* __restrict__ Um, const double* __restrict__ Us, int64_t ldi,
                                           double* __restrict__ sum, double* __restrict__ m2, int64_t lda,
                                           int64_t rows, int64_t cols, int first) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -460,7 +460,7 @@ __global__ void mixture_accumulate_kernel(const double* __restrict__ Um, const d
     sum[o] = first ? u : sum[o] + u;
     m2[o] = first ? q : m2[o] + q;
 }
-__global__ void mixture_finalize_kernel(double* __restrict__ sum, double* __restrict__ m2, int64_t ld, int64_t rows,
+__global__ void u_mixture_finalize_kernel(double* __restrict__ sum, double* __restrict__ m2, int64_t ld, int64_t rows,
                                         int64_t cols, double n_members, const double* __restrict__ pod_sig) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * cols) return;
@@ -674,24 +674,19 @@ extern "C" int pb_predict_U(pb_ctx* ctx, const double* V_dev, int64_t ldv, int64
     }
     if (U_sig_dev) {
         // (V*V) (sig^2)^T, then sqrt
-        double* V2 = nullptr; double* s2 = nullptr;
-        PB_CUDA(ctx, cudaMalloc(&V2, sizeof(double) * (size_t)n_rows * n_L));
-        PB_CUDA(ctx, cudaMalloc(&s2, sizeof(double) * (size_t)N * n_L));
+        // transient workspace of the context (grown on demand, kept): V*V (n_rows x n_L) then sig^2 (N x n_L)
+        PB_TRY(pb_reserve(ctx, &ctx->ws, &ctx->ws_bytes, (size_t)n_rows * n_L + (size_t)N * n_L));
+        double* V2 = ctx->ws; double* s2 = V2 + (size_t)n_rows * n_L;
         int64_t nv = n_rows * n_L, ns = N * n_L;
         square_strided_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, ctx->stream>>>(V_dev, ldv, V2, n_rows, n_L);
         PB_LAUNCH_CHECK(ctx);
         square_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, ctx->stream>>>(v_sig_dev, s2, ns);
         PB_LAUNCH_CHECK(ctx);
-        int rc = pbi_transpose(ctx, s2, N, n_L, n_L, ctx->Bmat, ldb);
-        if (rc == PB_OK) rc = pbi_gemm_nn(ctx, V2, n_L, n_rows, n_L, ctx->Bmat, ldb, N, U_sig_dev, ldo, nullptr, 0, nullptr);
-        if (rc == PB_OK) {
-            int64_t n = n_rows * N;
-            sqrt_inplace_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(U_sig_dev, n_rows, N, ldo);
-            ctx->launches++;
-        }
-        cudaStreamSynchronize(ctx->stream);
-        cudaFree(V2); cudaFree(s2);
-        if (rc != PB_OK) return rc;
+        PB_TRY(pbi_transpose(ctx, s2, N, n_L, n_L, ctx->Bmat, ldb));
+        PB_TRY(pbi_gemm_nn(ctx, V2, n_L, n_rows, n_L, ctx->Bmat, ldb, N, U_sig_dev, ldo, nullptr, 0, nullptr));
+        int64_t n = n_rows * N;
+        sqrt_inplace_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(U_sig_dev, n_rows, N, ldo);
+        PB_LAUNCH_CHECK(ctx);
     }
     return PB_OK;
 }
@@ -702,7 +697,7 @@ extern "C" int pb_mixture_accumulate(pb_ctx* ctx, const double* U_mean_dev, cons
     if (n_rows <= 0 || N <= 0 || ld_in < N || ld_acc < N || !U_mean_dev || !U_sig_dev || !sum_dev || !m2_dev)
         PB_FAIL(ctx, PB_ERR_SHAPE, "pb_mixture_accumulate: bad shape");
     const int64_t n = n_rows * N;
-    mixture_accumulate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(U_mean_dev, U_sig_dev, ld_in, sum_dev, m2_dev,
+    u_mixture_accumulate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(U_mean_dev, U_sig_dev, ld_in, sum_dev, m2_dev,
                                                                                    ld_acc, n_rows, N, first);
     PB_LAUNCH_CHECK(ctx);
     return PB_OK;
@@ -714,7 +709,7 @@ extern "C" int pb_mixture_finalize(pb_ctx* ctx, double* sum_dev, double* m2_dev,
     if (n_rows <= 0 || N <= 0 || ld < N || n_members <= 0 || !sum_dev || !m2_dev)
         PB_FAIL(ctx, PB_ERR_SHAPE, "pb_mixture_finalize: bad shape");
     const int64_t n = n_rows * N;
-    mixture_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(sum_dev, m2_dev, ld, n_rows, N, (double)n_members,
+    u_mixture_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(sum_dev, m2_dev, ld, n_rows, N, (double)n_members,
                                                                                  pod_sig_dev);
     PB_LAUNCH_CHECK(ctx);
     return PB_OK;
