@@ -522,7 +522,7 @@ def run_gpu(args):
             "stage_ms": {k: statistics.mean(v) for k, v in parts.items()}, "parity": parity, "tsqr_mode": tsqr_line, "c5": c5, "lib_multi": lib_multi,
             "ensemble_predict": ens_line, "ensemble_train": train_lines,
             "snapshot_kernel": {"ms": snap_ms, "gbs": n_h_loc * N_S * 8 / (snap_ms * 1e-3) / 1e9,
-                                "note": "Ackley field -> U slab in HBM (outside the timed step): table kernel + ackley_grouped_kernel (radius-sorted nodes), second call"}}
+                                "note": "Ackley field -> U slab in HBM (outside the timed step): table kernel + radius-grouped kernel (or the coordinate-indexed one when a slab repeats few radii), second call"}}
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
