@@ -397,6 +397,13 @@ def run_gpu(args):
                    "reuse_slab": {"value": fl / sec_reuse / 1e12, "ms_per_step": sec_reuse * 1e3, "ratio_to_e2e": ms_e2e / (sec_reuse * 1e3),
                                   "call": "the same with project_to_v(..., reuse_slab=True): U and V stay in HBM between the two calls"},
                    "ratio_to_e2e": ms_e2e / (sec_api * 1e3), "v_shape": list(v_np.shape)}
+        # the API default (mode "tsqr"): leaf QRs of the row chunks overlap the upload; PB_TSQR_HOST_OVERLAP=0 = upload, then pb_pod
+        t_def = []
+        pod_mod.perform_pod(U_np, EPS, 0, False, ctx=ctx)
+        for _ in range(3):
+            t0 = time.perf_counter(); V_def = pod_mod.perform_pod(U_np, EPS, 0, False, ctx=ctx); t_def.append(time.perf_counter() - t0)
+        e2e_api["default_mode_tsqr"] = {"perform_pod_ms": min(t_def) * 1e3, "n_L": int(V_def.shape[1]),
+                                        "call": "V = pod.perform_pod(U_ndarray, eps): pageable numpy in, numpy out, best of 3"}
         del U_np
     # ---- the host -> device ceiling of this box with every rank copying at once (explains the e2e scaling)
     ctx.sync(); barrier()

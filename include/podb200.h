@@ -238,7 +238,10 @@ int  pb_gram_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, 
 /* Same from a HOST matrix: the upload into U_dev (n_h x n_st, ld = n_st, caller-allocated) is cut into row chunks on
  * a copy stream and overlapped with the Gram.  Pinned memory (pb_host_alloc) is copied directly; pageable memory
  * (an ordinary numpy array, what poduqnn/pod.py:7 is handed) goes through a ring of pinned staging buffers filled by
- * host threads (PB_HOST_COPY_THREADS, default half the cores, at most 16). */
+ * host threads (PB_HOST_COPY_THREADS, default half the cores, at most 16).
+ * Mode PB_POD_TSQR (rank-revealing): the leaf QR of row chunk c runs while chunks c + 1 .. cross PCIe (an uploader
+ * thread feeds the copy stream, the calling thread drives the leaf factorisations and their pivot decisions), then the
+ * QR of the stacked leaf factors; PB_POD_TSQR_FULL uploads first. */
 int  pb_pod_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, int64_t ldu_host, double* U_dev,
                  double eps, int n_L_in, int mode, int* n_L);
 

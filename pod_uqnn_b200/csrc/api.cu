@@ -12,6 +12,7 @@
 #include <emmintrin.h>
 #endif
 #include <thread>
+#include <atomic>
 #include <cstdlib>
 #include <vector>
 
@@ -838,6 +839,71 @@ int gram_host_chunked(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_
 }
 }  // namespace
 
+// Rank-revealing TSQR factor of a HOST matrix: the upload is cut into row chunks (an uploader thread fills the copy
+// stream: pinned sources directly, pageable ones through the staging ring) and the leaf QR of chunk c runs on the
+// compute stream as soon as chunk c has landed -- TSQR leaves in time instead of in space.  The leaf factors
+// (f_c x n_st rows each, f_c = a multiple of 64 >= the leaf's numerical rank) are stacked and factored once more, exactly
+// as the sharded path does with the factors of the GPUs (test_tsqr_logical_shards_equal_unsharded).  The leaf QR
+// synchronises with the host once per panel (pivot decisions), which is why the uploads need their own thread.
+// F_out (n_st x n_st) receives the factor, *f_rows its row count.  Returns 1 when the shape does not chunk (nothing done).
+namespace {
+int tsqr_host_chunked(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, int64_t ldu_host, double* U_dev,
+                      double* F_out, int64_t* f_rows) {
+    static const bool enabled = []{ const char* e = getenv("PB_TSQR_HOST_OVERLAP"); return !e || atoi(e) != 0; }();
+    const int64_t m = n_st;
+    const int nchunks = (int)std::min<int64_t>(8, n_h / std::max<int64_t>(8192, 8 * m));
+    if (!enabled || n_h < n_st || nchunks < 2 || n_st > 8192) return 1;
+    if (!ctx->copy_stream) {
+        PB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int c = 0; c < 16; ++c) PB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->chunk_ev[c], cudaEventDisableTiming));
+    }
+    // every leaf zero-fills m rows from its offset (pbi_qr_factor), so the stack keeps one factor of slack
+    PB_TRY(pb_reserve(ctx, &ctx->Gpart, &ctx->Gpart_cap, (size_t)(nchunks + 1) * m * m));
+    const bool pinned = host_is_pinned(U_host);
+    if (!pinned) PB_TRY(stage_reserve(ctx, (size_t)64 << 20));
+    int64_t rows_c = (n_h + nchunks - 1) / nchunks; rows_c = (rows_c + 15) / 16 * 16;
+    PB_CUDA(ctx, cudaEventRecord(ctx->chunk_ev[15], ctx->stream));      // U_dev may still be read by earlier work
+    PB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[15], 0));
+    Timer tq(ctx, PB_T_QR);
+    ctx->qr_panels = 0; ctx->qr_flops = 0.;
+    std::atomic<int> issued{0};
+    std::atomic<int> up_rc{PB_OK};
+    std::thread uploader([&] {
+        cudaSetDevice(ctx->device);
+        int slot = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            const int64_t r0 = (int64_t)c * rows_c, nr = std::min(rows_c, n_h - r0);
+            if (nr > 0) {
+                int rc = upload_rows(ctx, U_dev + r0 * n_st, U_host + r0 * ldu_host, nr, n_st, ldu_host, pinned, ctx->copy_stream, &slot);
+                if (rc == PB_OK && cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream) != cudaSuccess) rc = PB_ERR_CUDA;
+                if (rc != PB_OK) { up_rc.store(rc); issued.store(nchunks, std::memory_order_release); return; }
+            }
+            issued.store(c + 1, std::memory_order_release);
+        }
+    });
+    int rc = PB_OK;
+    int64_t off = 0;
+    for (int c = 0; c < nchunks && rc == PB_OK; ++c) {
+        const int64_t r0 = (int64_t)c * rows_c, nr = std::min(rows_c, n_h - r0);
+        if (nr <= 0) break;
+        while (issued.load(std::memory_order_acquire) <= c) std::this_thread::yield();
+        if (up_rc.load() != PB_OK) { rc = up_rc.load(); break; }
+        if (cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0) != cudaSuccess) { rc = PB_ERR_CUDA; break; }
+        int64_t fr = 0;
+        rc = pbi_qr_factor(ctx, U_dev + r0 * n_st, nr, m, n_st, ctx->Gpart + (size_t)off * m, m, m, true, &fr);
+        off += std::min(fr, m);
+    }
+    uploader.join();
+    if (rc == PB_OK && up_rc.load() != PB_OK) rc = up_rc.load();
+    if (rc != PB_OK) return rc < 0 ? rc : PB_ERR_CUDA;
+    int64_t fr = 0;
+    if (off > 0) PB_TRY(pbi_qr_factor(ctx, ctx->Gpart, off, m, m, F_out, m, m, true, &fr));
+    *f_rows = fr; ctx->qr_f_rows = fr;
+    tq.stop();
+    return PB_OK;
+}
+}  // namespace
+
 namespace {
 // whole-matrix upload on the compute stream (small / wide inputs and the TSQR mode)
 int upload_whole(pb_ctx* ctx, double* U_dev, const double* U_host, int64_t n_h, int64_t n_st, int64_t ldu_host) {
@@ -905,7 +971,21 @@ int pb_pod_host(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_st, in
     Timer t_total(ctx, PB_T_POD_TOTAL);
     const int64_t m = n_st;
     if (n_h >= n_st) PB_TRY(pb_reserve(ctx, &ctx->Gbuf, &ctx->G_cap, (size_t)m * m));
-    // the TSQR mode has no Gram to overlap with the upload: plain copy, then the device path
+    if (mode == PB_POD_TSQR && n_h >= n_st && !(eps == 0. && n_L_in == 0)) {
+        // rank-revealing TSQR: the leaf QR of a row chunk runs while the next chunks cross PCIe
+        int64_t f_rows = 0;
+        int rq = tsqr_host_chunked(ctx, U_host, n_h, n_st, ldu_host, U_dev, ctx->Gbuf, &f_rows);
+        if (rq < 0) return rq;
+        if (rq == PB_OK) {
+            ctx->wide = false;
+            ctx->ms[PB_T_GRAM] = 0.; ctx->ms[PB_T_PASS2] = 0.; ctx->t_pending[PB_T_GRAM] = ctx->t_pending[PB_T_PASS2] = false;
+            if (f_rows <= 0) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_pod_host: zero matrix");
+            PB_TRY(pb_pod_from_factor(ctx, ctx->Gbuf, f_rows, m, m, eps, n_L_in, n_L));
+            t_total.stop();
+            return PB_OK;
+        }
+    }
+    // tsqr_full (and shapes that do not chunk) have nothing to overlap with the upload: plain copy, then the device path
     int rc = (mode == PB_POD_TSQR || mode == PB_POD_TSQR_FULL) ? 1 : gram_host_chunked(ctx, U_host, n_h, n_st, ldu_host, U_dev, ctx->Gbuf);
     if (rc == 1) {        // small or wide, or the TSQR mode: upload (staged when pageable), then the device path
         PB_TRY(upload_whole(ctx, U_dev, U_host, n_h, n_st, ldu_host));

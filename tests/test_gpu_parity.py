@@ -595,6 +595,40 @@ def test_pod_host_pipelined_upload(ctx):
     assert nl.value == Vr.shape[1] and np.array_equal(Ud.download(), U)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("pinned", [False, True])
+def test_pod_host_tsqr_overlapped_upload(ctx, pinned):
+    """pb_pod_host in the default TSQR mode factors each row chunk while the next ones cross PCIe (leaf factors,
+    then the QR of the stack): same rank / sigma / modes as the device path and as the reference's SVD; the uploaded
+    slab is complete."""
+    rng = np.random.default_rng(22)
+    n_h, n_st = 70000, 200
+    U = (rng.standard_normal((n_h, 20)) * 2. ** -np.arange(20)) @ rng.standard_normal((20, n_st))
+    L = _lib.lib()
+    host = U
+    hp = None
+    if pinned:
+        hp = C.c_void_p(); assert L.pb_host_alloc(U.nbytes, C.byref(hp)) == 0
+        host = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_double)), shape=U.shape); host[...] = U
+    try:
+        Ud, nl = ctx.alloc(n_h, n_st), C.c_int()
+        ctx.check(L.pb_pod_host(ctx.h, host.ctypes.data, n_h, n_st, n_st, Ud.ptr, 1e-9, 0, _lib.POD_MODES["tsqr"], C.byref(nl)))
+        V1 = ctx.alloc(n_h, nl.value)
+        ctx.check(L.pb_pod_basis_full(ctx.h, Ud.ptr, n_h, n_st, Ud.ld, V1.ptr, V1.ld))
+        from pod_uqnn_b200.pod import pod_sigma
+        s1 = pod_sigma(ctx)
+        assert np.array_equal(Ud.download(), U)
+        V2d, s2 = pod_device(ctx, Ud, 1e-9, 0, "tsqr")
+        Vr = po.perform_pod(U, 1e-9)
+        assert nl.value == Vr.shape[1] == V2d.shape[1]
+        assert cmp.largest_principal_angle(V1.download(), Vr) <= cmp.TOL_ANGLE
+        assert cmp.largest_principal_angle(V1.download(), V2d.download()) <= 1e-10
+        assert cmp.sigma_error(s1[:nl.value], s2[:nl.value]) <= 1e-12
+    finally:
+        if hp is not None:
+            L.pb_host_free(hp)
+
+
 def test_predict_U_monte_carlo(ctx):
     """The reference's MC estimator on the GPU: reproducible per seed, converges to the closed form."""
     rng = np.random.default_rng(18)
