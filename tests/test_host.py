@@ -197,3 +197,27 @@ def test_gram_tile_shapes_cover_needed_atoms_once(cv):
         if kind == "edge" and cv == 13:
             assert load.max() == 52 and tr[k] == 1   # n_s = 1000: 13 atom rows x 16 atom columns, transposed
     assert _lib.lib().pb_gram_tile_shapes(0, out, tr, wt) == _lib.PB_ERR_ARG
+
+
+def test_bench_host_logic_and_no_gpu_failure():
+    """bench.py: the algorithmic flop count of SURVEY 8d, the workload description per N, and -- without a GPU -- a loud
+    failure of the product arm (no CPU fallback may stand in for the CUDA path)."""
+    import importlib.util, subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    argv = sys.argv
+    try:
+        sys.argv = ["bench.py"]
+        spec.loader.exec_module(b)
+    finally:
+        sys.argv = argv
+    assert b.algo_flops(160000, 1000, 14) == 160000 * 1000 * 1001 + 4 * 160000 * 1000 * 14
+    cfg = b.workload_config(8)
+    assert cfg["n_h_per_gpu"] == 160000 and "n_h = 1280000" in cfg["workload"] and cfg["parallelism"] == "row-sharded x8"
+    assert b.METRIC == "pod_fp64_tflops" and b.MODE == "gram2"
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "1"],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr and not r.stdout.strip().startswith("{")
