@@ -95,6 +95,16 @@ class PodnnModel:
             self._ctx = _lib.default_context()
         return self._ctx
 
+    def generate_hifi_inputs(self, n_s, mu_min, mu_max, t_min=0, t_max=0):
+        """podnnmodel.py:60-87: the (t, mu) regression inputs of a large prediction task (LHS over mu, every time step
+        per sample).  Rows s*n_t + j = [t_j, mu_s...] for time-dependent models, [mu_s...] otherwise."""
+        mu_min, mu_max = np.array(mu_min), np.array(mu_max)
+        mu_lhs = sample_mu(n_s, mu_min, mu_max)
+        if not self.has_t:
+            return mu_lhs.copy()
+        t = np.linspace(t_min, t_max, self.n_t)                 # podnnmodel.py:75
+        return np.hstack((np.tile(t, n_s)[:, None], np.repeat(mu_lhs, self.n_t, axis=0)))
+
     # ------------------------------------------------------------ snapshots
     def create_snapshots(self, n_d, n_h, u, mu_lhs, t_min=0, t_max=0, u_noise=0., x_noise=0.):
         """podnnmodel.py:89-116 -> (X_v, U, U_struct, U_no_noise), host arrays."""
@@ -374,6 +384,22 @@ class PodnnModel:
                 bufs[j1 - j0] = (self.ctx.alloc(self.n_h, j1 - j0), self.ctx.alloc(self.n_h, j1 - j0))
             Um, Us = bufs[j1 - j0]
             yield j0, j1, Um, Us, t
+
+    def predict_dist(self, X_v, model_i, samples=100, *, monte_carlo=False, seed=0):
+        """podnnmodel.py:330-342: the U-level distribution of ONE member, (U_pred, U_pred_sig).  As in `predict`: the
+        exact moments of the reference's Monte-Carlo loop by default, the loop itself (Philox draws) on request."""
+        ctx, Vd = self.ctx, self._ensure_V_dev()
+        members, layers, soft_0, norm, nb = self._ensemble_args()
+        Xd = ctx.to_device(np.asarray(X_v, dtype=np.float64).reshape(-1, layers[0]))
+        vm, vs = ensemble_predict_device(ctx, [members[model_i]], layers, Xd, soft_0, norm, nb)
+        N = Xd.shape[0]
+        U_pred, U_pred_sig = np.empty((self.n_h, N)), np.empty((self.n_h, N))
+        for j0, j1, Um, Us, t in self._u_tiles(N):
+            ctx.check(_lib.lib().pb_predict_U(ctx.h, Vd.ptr, Vd.ld, self.n_h, self.n_L, vm.ptr + 8 * j0 * self.n_L,
+                                              vs.ptr + 8 * j0 * self.n_L, j1 - j0, int(samples) if monte_carlo else 0,
+                                              int(seed) + int(model_i) + 7919 * t, Um.ptr, Us.ptr, Um.ld))
+            U_pred[:, j0:j1], U_pred_sig[:, j0:j1] = Um.download(), Us.download()
+        return U_pred, U_pred_sig
 
     def predict_mc(self, X_v, samples=100, *, monte_carlo=False, seed=0):
         """podnnmodel.py:344-364: per-member U-level prediction (predict_dist :330-342), Gaussian mixture

@@ -186,6 +186,24 @@ class VarNeuralNetwork:
         elif self.norm == NORM_MEANSTD:
             self.norm_bounds = (X.mean(0), X.std(0))
 
+    def normalize(self, X):
+        """varneuralnetwork.py:75-86 (host arrays; the fused kernels normalise on the device)."""
+        return normalize_host(X, self.norm, self.norm_bounds)
+
+    def summary(self):
+        """varneuralnetwork.py:167-169: the layer table Keras would print (Dense ... Dense(2 n_L), mean / softplus head)."""
+        dims = list(self.layers[:-1]) + [2 * self.layers[-1]]
+        lines, total = [f"{'Layer':<24}{'Output shape':<16}{'Param #':>10}"], 0
+        for i, (a, b) in enumerate(zip(dims[:-1], dims[1:])):
+            n = a * b + b
+            total += n
+            act = "relu" if i < len(dims) - 2 else "linear (mean | softplus var)"
+            lines.append(f"{'dense_' + str(i) + ' (' + act + ')':<24}{'(None, ' + str(b) + ')':<16}{n:>10}")
+        lines.append(f"Total params: {total}")
+        text = "\n".join(lines)
+        print(text)
+        return text
+
     # --- forward -------------------------------------------------------------
     def predict(self, X, *, ctx=None):
         """(mean, variance) of the predictive Normal, as the reference (:154-160)."""

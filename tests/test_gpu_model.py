@@ -71,8 +71,17 @@ def test_predict_path(ctx, tmp_path):
     U_pred, U_sig = model.predict(X)
     Ur, Usr = ens.predict_U_moments(model.V, vr, sr)
     assert cmp.rel_err(U_pred, Ur) <= cmp.TOL_ENSEMBLE_REL and cmp.rel_err(U_sig, Usr) <= cmp.TOL_ENSEMBLE_REL
+    # predict_dist: ONE member's U-level moments (podnnmodel.py:330-342); predict_mc mixes exactly these
+    per = [model.predict_dist(X, i) for i in range(4)]
+    for i, (Ui, Si) in enumerate(per):
+        vi, si = ens.predict_v(X, [members[i]], model.n_L, 0.01, "meanstd", nb)
+        Uir, Sir = ens.predict_U_moments(model.V, vi, si)
+        assert cmp.rel_err(Ui, Uir) <= cmp.TOL_ENSEMBLE_REL and cmp.rel_err(Si, Sir) <= cmp.TOL_ENSEMBLE_REL
+    Umix = np.mean([u for u, _ in per], axis=0)
+    Smix = np.sqrt(np.mean([sg ** 2 + u ** 2 for u, sg in per], axis=0) - Umix ** 2) + model.pod_sig[:, None]
     # predict_mc: per-member U-level moments, mixture at the U level, + pod_sig (podnnmodel.py:344-364)
     Um, Usm = model.predict_mc(X)
+    assert cmp.rel_err(Um, Umix) <= 1e-12 and cmp.rel_err(Usm, Smix) <= 1e-9
     Umr, Usmr = ens.predict_mc_moments(model.V, X, members, model.n_L, 0.01, "meanstd", nb, model.pod_sig)
     assert cmp.rel_err(Um, Umr) <= cmp.TOL_ENSEMBLE_REL and cmp.rel_err(Usm, Usmr) <= cmp.TOL_ENSEMBLE_REL
     U_mc, Us_mc = model.predict(X, samples=400, monte_carlo=True, seed=3)

@@ -221,3 +221,26 @@ def test_bench_host_logic_and_no_gpu_failure():
         r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "1"],
                            capture_output=True, text=True, timeout=300)
         assert r.returncode != 0 and "no CPU fallback" in r.stderr and not r.stdout.strip().startswith("{")
+
+
+def test_generate_hifi_inputs_and_summary():
+    """podnnmodel.py:60-87 (row layout of the large prediction inputs) and varneuralnetwork.py:167-169; host only."""
+    import numpy as np
+    from pod_uqnn_b200.podnnmodel import PodnnModel
+    from pod_uqnn_b200.varneuralnetwork import VarNeuralNetwork
+    x_mesh = np.column_stack((np.arange(5), np.linspace(0., 1., 5)))
+    m = PodnnModel.__new__(PodnnModel)
+    m.has_t, m.n_t = True, 4
+    np.random.seed(3)
+    X_v = m.generate_hifi_inputs(6, [0.1, 1.], [0.2, 2.], t_min=1., t_max=2.5)
+    assert X_v.shape == (24, 3)
+    assert np.array_equal(X_v[:4, 0], np.linspace(1., 2.5, 4)) and np.array_equal(X_v[4:8, 0], X_v[:4, 0])
+    assert np.all(X_v[:4, 1:] == X_v[0, 1:]) and not np.array_equal(X_v[0, 1:], X_v[4, 1:])
+    assert np.all((X_v[:, 1] >= 0.1) & (X_v[:, 1] <= 0.2) & (X_v[:, 2] >= 1.) & (X_v[:, 2] <= 2.))
+    m.has_t = False
+    assert m.generate_hifi_inputs(6, [0.1, 1.], [0.2, 2.]).shape == (6, 2)
+    net = VarNeuralNetwork([3, 8, 8, 5], 1e-3, 1e-3, norm="meanstd")
+    text = net.summary()
+    assert "Total params: " + str(3 * 8 + 8 + 8 * 8 + 8 + 8 * 10 + 10) in text
+    net.set_normalize_bounds(np.array([[0., 2.], [2., 6.]]))
+    assert np.allclose(net.normalize(np.array([[1., 4.]])), 0.)
