@@ -187,6 +187,10 @@ int  pb_pod_basis(pb_ctx* ctx, const double* A_dev, int64_t n_rows, int64_t lda,
  * all-reduce), pb_pod_refine_apply (V~ = A_local B Sigma^-2, G3 = V~^T V~ partial), all-reduce G3,
  * pb_pod_refine_finish (V = V~ R^-1, R^T R = G3).  pb_pod_basis_full does all of it on one GPU. */
 int  pb_pod_refine_steps(pb_ctx* ctx, int* steps);
+/* The row count the a-priori estimate uses instead of the rows of the last Gram (0 = those): row-sharded callers pass
+ * the LARGEST slab of the job once, so that every rank takes the same decision from replicated quantities only and no
+ * collective is needed for it. */
+int  pb_pod_set_refine_rows(pb_ctx* ctx, int64_t rows);
 int  pb_pod_refine_estimate(pb_ctx* ctx, double* est);   /* the a-priori angle estimate the decision was taken on */
 int  pb_pod_refine_apply(pb_ctx* ctx, const double* A_dev, int64_t n_rows, int64_t lda, double* B_dev, double* G3_dev);
 int  pb_pod_refine_finish(pb_ctx* ctx, const double* G3_dev, int64_t n_rows, double* V_dev, int64_t ldv);

@@ -60,6 +60,7 @@ SIGNATURES = {
     "pb_pod_pass2_finish": (_int, [_vp, _vp, _dbl, _int, _pi]),
     "pb_pod_basis": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _i64]),
     "pb_pod_refine_steps": (_int, [_vp, _pi]),
+    "pb_pod_set_refine_rows": (_int, [_vp, _i64]),
     "pb_pod_refine_estimate": (_int, [_vp, _pd]),
     "pb_pod_refine_apply": (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "pb_pod_refine_finish": (_int, [_vp, _vp, _i64, _vp, _i64]),

@@ -331,7 +331,8 @@ static int refine_steps_needed(pb_ctx* ctx) {
     const double s1 = ctx->sigma_host[0], sl = ctx->sigma_host[ctx->n_L - 1];
     if (!(sl > 0.) || !(s1 > 0.)) return 0;
     const double x = s1 / sl;
-    const double size_f = pow(std::max(1., (double)ctx->gram_rows / 65536.), 1.2) * pow(std::max(1., (double)ctx->m / 1024.), 0.8);
+    const int64_t est_rows = ctx->refine_rows_fixed > 0 ? ctx->refine_rows_fixed : ctx->gram_rows;
+    const double size_f = pow(std::max(1., (double)est_rows / 65536.), 1.2) * pow(std::max(1., (double)ctx->m / 1024.), 0.8);
     const double est = ctx->wide ? 0.4 * DBL_EPSILON * x * x
                                  : 0.54 * DBL_EPSILON * x * x * x * sqrt(4. * DBL_EPSILON) * size_f;
     ctx->refine_est = est;
@@ -373,6 +374,11 @@ __global__ void scale_cols_inv_sq_kernel(double* __restrict__ B, int64_t n, int 
 }
 }  // namespace
 
+int pb_pod_set_refine_rows(pb_ctx* ctx, int64_t rows) {
+    PB_ENTER(ctx); if (rows < 0) return PB_ERR_ARG;
+    ctx->refine_rows_fixed = rows;
+    return PB_OK;
+}
 int pb_pod_refine_steps(pb_ctx* ctx, int* steps) {
     PB_ENTER(ctx); if (!steps) return PB_ERR_ARG;
     *steps = ctx->pass2_done ? ctx->refine_steps : 0;

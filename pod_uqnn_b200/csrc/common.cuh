@@ -77,7 +77,7 @@ struct pb_ctx {
     // per-call knobs of the next eigensolve (set by the POD orchestration, consumed and cleared by eig.cu)
     bool eig_trust_single_pair = false;   // skip the confirming sweep of a single-pair problem (a second pass follows)
     double eig_jacobi_tol = 0.;           // > 0: rotation threshold of the next eig (first pass of the accurate mode)
-    int refine_steps = 0; double refine_est = 0.; int64_t gram_rows = 0;   // gram2: subspace-refinement decision of the last decomposition (api.cu)
+    int refine_steps = 0; double refine_est = 0.; int64_t gram_rows = 0; int64_t refine_rows_fixed = 0;   // gram2: subspace-refinement decision of the last decomposition (api.cu)
     double* Rbuf = nullptr; size_t R_cap = 0;       // refinement: V~ (rows x n_L)
     double* Pbuf = nullptr; size_t P_cap = 0;       // refinement: projection block + small Gram
     void* gram_plan = nullptr;            // stream-K schedule of the last Gram shape (gram_tma.cu), owned by the context

@@ -89,6 +89,13 @@ def pod_sharded(backend, A_local, eps=0., n_L=0, mode="gram", group=None, A_host
         if A_host is not None:
             backend.upload(A_host, A_local)
         return pod_sharded_tsqr(backend, A_local, eps, n_L, group, full=(mode == "tsqr_full"))
+    # the gram2 refinement decision depends on sigma (replicated), the column count and a row count: every rank uses the
+    # LARGEST slab of the job (one MAX all-reduce per shape, cached), so the decision needs no collective per call
+    key = (id(group), int(A_local.shape[0]), int(A_local.shape[1]))
+    cache = backend.__dict__.setdefault("_rows_max_cache", {})
+    if key not in cache:
+        cache[key] = _max_over_ranks(backend, A_local.shape[0], group)
+    backend.set_refine_rows(cache[key])
     G = backend.gram(A_local) if A_host is None else backend.gram_host(A_host, A_local)
     backend.reduce(G, group)
     n_L_out, keep = backend.pod_from_gram(G, eps, n_L, mode)
@@ -98,7 +105,7 @@ def pod_sharded(backend, A_local, eps=0., n_L=0, mode="gram", group=None, A_host
         backend.reduce(G2, group)
         n_L_out = backend.pass2_finish(G2, eps, n_L)
     V = backend.basis(A_local, Y, n_L_out)
-    if keep > 0 and _max_over_ranks(backend, backend.refine_steps(), group) > 0:     # one decision for all ranks
+    if keep > 0 and backend.refine_steps() > 0:     # the same on every rank (replicated inputs, see above)
         # gram2 tolerance safety (csrc/api.cu, "subspace refinement"): one step of subspace iteration with the matrix
         # itself -- two more all-reduces (the n_st x n_L projection block and an n_L x n_L Gram)
         B = backend.project(V, A_local)
@@ -244,6 +251,9 @@ class CudaBackend:
         self.ctx.check(self.L.pb_pod_basis(self.ctx.h, A.ptr, A.shape[0], A.ld, Y.ptr if Y is not None else None,
                                            V.ptr, V.ld))
         return V
+
+    def set_refine_rows(self, rows):
+        self.ctx.check(self.L.pb_pod_set_refine_rows(self.ctx.h, int(rows)))
 
     def refine_steps(self):
         st = C.c_int()

@@ -82,6 +82,9 @@ class NumpyBackend:
         return A @ self._W[:, :n_L] / self._sig[:n_L]
 
     # gram2 subspace refinement (always engaged here so that the gloo test walks the two extra all-reduces)
+    def set_refine_rows(self, rows):
+        self.refine_rows = int(rows)
+
     def refine_steps(self):
         return 1
 

@@ -31,6 +31,8 @@ def _worker(rank, world, port, mode, out):
     lo, hi = sharded.row_range(U.shape[0], rank, world)
     be = NumpyBackend()
     V_loc, sig, n_L = sharded.pod_sharded(be, U[lo:hi], 1e-8, 0, mode)
+    if mode != "tsqr":      # the refinement decision is taken from the largest slab on every rank (no collective per call)
+        assert be.refine_rows == max(b - a for a, b in (sharded.row_range(U.shape[0], p, world) for p in range(world)))
     v = sharded.project_sharded(be, V_loc, U[lo:hi]).numpy()
     gathered = [None] * world
     dist.all_gather_object(gathered, (lo, hi, V_loc))
