@@ -325,7 +325,6 @@ def run_gpu(args):
     ms_total = ctx.timer_stop()
     barrier()
     launches = ctx.launches() - launches0
-    clocks = sampler.stop() if sampler else None
     ms_step = max_over_ranks(ms_total / args.steps)
     value = algo_flops(n_h, N_S, n_L) / (ms_step * 1e-3) / 1e12
     from pod_uqnn_b200.pod import pod_sigma
@@ -368,6 +367,8 @@ def run_gpu(args):
     ms_e2e = max_over_ranks(ctx.timer_stop() / e2e_steps)
     barrier()
     e2e_value = algo_flops(n_h, N_S, n_L) / (ms_e2e * 1e-3) / 1e12
+    # the clock / throttle samples cover BOTH timed regions (device-resident steps and the e2e steps)
+    clocks = sampler.stop() if sampler else None
 
     # ---- e2e through the Python API a reference user calls: ordinary numpy arrays in, numpy arrays out
     e2e_api = None
