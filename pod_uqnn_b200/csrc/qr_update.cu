@@ -214,11 +214,15 @@ int pbi_qr_update(pb_ctx* ctx, const double* Y, int64_t ldy, int64_t rows, int64
     const int grid = std::min(n_pairs, ctx->sm_count);
     const int n_tiles = (int)((n + NTQ - 1) / NTQ);
     int csplit = 1; double best = 0.;
-    for (int c = 1; c <= 4 && n_tiles / c >= 6; ++c) {         // least idle time in the last wave (ties: fewer splits)
+    // column splits only when there are too few strip pairs to balance the persistent grid by rows alone: a split costs a
+    // second staging of the Y strip and a second pipeline fill per pair (measured: 250 000 x 4096 QR 354 -> 348 ms, C2
+    // tsqr_full 23.2 -> 23.0 ms without them)
+    for (int c = 1; c <= 4 && n_tiles / c >= 6 && (c == 1 || n_pairs < 2 * grid); ++c) {
         const int64_t units = (int64_t)n_pairs * c;
         const double eff = (double)units / (double)((units + grid - 1) / grid * grid);
         if (eff > best + 0.01) { best = eff; csplit = c; }
     }
+    { static const int cs_env = getenv("PB_QR_UPDATE_CSPLIT") ? atoi(getenv("PB_QR_UPDATE_CSPLIT")) : 0; if (cs_env > 0) csplit = cs_env; }
     const size_t smem = sizeof(double) * ((size_t)QSTAGES * BTILE_DOUBLES + 2 * 64 * PAQ) + 2 * QSTAGES * sizeof(uint64_t) + 1024;
     PB_TRY(pbi_smem_optin(ctx, (const void*)qr_update_kernel, smem));
     qr_update_kernel<<<grid, QTHREADS, smem, ctx->stream>>>(map, Y, ldy, rows, n, C, ldc, n_pairs, csplit);
