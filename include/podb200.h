@@ -187,9 +187,10 @@ int  pb_pod_basis(pb_ctx* ctx, const double* A_dev, int64_t n_rows, int64_t lda,
  * all-reduce), pb_pod_refine_apply (V~ = A_local B Sigma^-2, G3 = V~^T V~ partial), all-reduce G3,
  * pb_pod_refine_finish (V = V~ R^-1, R^T R = G3).  pb_pod_basis_full does all of it on one GPU. */
 int  pb_pod_refine_steps(pb_ctx* ctx, int* steps);
-/* The row count the a-priori estimate uses instead of the rows of the last Gram (0 = those): row-sharded callers pass
- * the LARGEST slab of the job once, so that every rank takes the same decision from replicated quantities only and no
- * collective is needed for it. */
+/* The row count the a-priori estimate of the decomposition in progress uses instead of the rows of its Gram (0 = those):
+ * row-sharded callers pass the LARGEST slab of the job between pb_gram / pb_gram_host and pb_pod_from_gram, so that every
+ * rank takes the same decision from replicated quantities only and no collective is needed for it.  Every new Gram
+ * clears the override. */
 int  pb_pod_set_refine_rows(pb_ctx* ctx, int64_t rows);
 int  pb_pod_refine_estimate(pb_ctx* ctx, double* est);   /* the a-priori angle estimate the decision was taken on */
 int  pb_pod_refine_apply(pb_ctx* ctx, const double* A_dev, int64_t n_rows, int64_t lda, double* B_dev, double* G3_dev);

@@ -223,7 +223,7 @@ int pb_gram(pb_ctx* ctx, const double* A, int64_t rows, int64_t cols, int64_t ld
     PB_ENTER(ctx);
     if (lda < cols) PB_FAIL(ctx, PB_ERR_SHAPE, "pb_gram: lda %lld < n_cols %lld", (long long)lda, (long long)cols);
     Timer t(ctx, PB_T_GRAM);
-    ctx->gram_rows = rows;
+    ctx->gram_rows = rows; ctx->refine_rows_fixed = 0;     // a new Gram: the override (pb_pod_set_refine_rows) must be renewed
     PB_TRY(pbi_gemm_tn(ctx, A, lda, cols, A, lda, cols, rows, G, cols, 3));   // sym | time the main kernel
     t.stop();
     return PB_OK;
@@ -824,7 +824,7 @@ int gram_host_chunked(pb_ctx* ctx, const double* U_host, int64_t n_h, int64_t n_
     PB_CUDA(ctx, cudaEventRecord(ctx->chunk_ev[0], ctx->stream));
     PB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[0], 0));
     int used = 0;
-    ctx->gram_rows = n_h;
+    ctx->gram_rows = n_h; ctx->refine_rows_fixed = 0;
     Timer tg(ctx, PB_T_GRAM);
     const bool pinned = host_is_pinned(U_host);
     if (!pinned) PB_TRY(stage_reserve(ctx, (size_t)64 << 20));

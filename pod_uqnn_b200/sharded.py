@@ -95,9 +95,9 @@ def pod_sharded(backend, A_local, eps=0., n_L=0, mode="gram", group=None, A_host
     cache = backend.__dict__.setdefault("_rows_max_cache", {})
     if key not in cache:
         cache[key] = _max_over_ranks(backend, A_local.shape[0], group)
-    backend.set_refine_rows(cache[key])
     G = backend.gram(A_local) if A_host is None else backend.gram_host(A_host, A_local)
     backend.reduce(G, group)
+    backend.set_refine_rows(cache[key])          # (every new Gram clears the override: it belongs to this decomposition)
     n_L_out, keep = backend.pod_from_gram(G, eps, n_L, mode)
     Y = None
     if keep > 0:

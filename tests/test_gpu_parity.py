@@ -629,6 +629,36 @@ def test_pod_host_tsqr_overlapped_upload(ctx, pinned):
             L.pb_host_free(hp)
 
 
+def test_refine_rows_override_is_scoped_to_one_decomposition(ctx):
+    """pb_pod_set_refine_rows (row-sharded callers: the largest slab of the job) changes the a-priori estimate of the
+    decomposition in progress only: every new Gram clears it, so a later single-GPU pb_pod on the same context is not
+    decided with another job's row count."""
+    rng = np.random.default_rng(33)
+    n_h, n_st = 300000, 64
+    U = (rng.standard_normal((n_h, 24)) * 2. ** (-1.3 * np.arange(24))) @ rng.standard_normal((24, n_st))
+    L, Ud = _lib.lib(), ctx.to_device(U)
+    est = C.c_double()
+
+    def estimate_after_pod():
+        pod_device(ctx, Ud, 1e-10, 0, "gram2")
+        ctx.check(L.pb_pod_refine_estimate(ctx.h, C.byref(est)))
+        return est.value
+
+    e_plain = estimate_after_pod()
+    ctx.check(L.pb_pod_set_refine_rows(ctx.h, 1000))            # stale override from "another job"
+    assert estimate_after_pod() == e_plain                       # pb_pod -> pb_gram cleared it
+    # set between the Gram and the eigensolve (what sharded.pod_sharded does): it is used
+    G, nl, keep = ctx.alloc(n_st, n_st), C.c_int(), C.c_int()
+    ctx.check(L.pb_gram(ctx.h, Ud.ptr, n_h, n_st, Ud.ld, G.ptr))
+    ctx.check(L.pb_pod_set_refine_rows(ctx.h, 1000))
+    ctx.check(L.pb_pod_from_gram(ctx.h, G.ptr, n_st, 1e-10, 0, _lib.POD_MODES["gram2"], C.byref(nl), C.byref(keep)))
+    Y, G2 = ctx.alloc(n_h, keep.value), ctx.alloc(keep.value, keep.value)
+    ctx.check(L.pb_pod_pass2_gram(ctx.h, Ud.ptr, n_h, Ud.ld, Y.ptr, G2.ptr))
+    ctx.check(L.pb_pod_pass2_finish(ctx.h, G2.ptr, 1e-10, 0, C.byref(nl)))
+    ctx.check(L.pb_pod_refine_estimate(ctx.h, C.byref(est)))
+    assert 0. < est.value < e_plain                              # 1000 rows instead of 300 000: a smaller estimate
+
+
 def test_predict_U_monte_carlo(ctx):
     """The reference's MC estimator on the GPU: reproducible per seed, converges to the closed form."""
     rng = np.random.default_rng(18)
