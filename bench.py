@@ -345,8 +345,11 @@ def run_gpu(args):
             nl = nl_c.value
             V, v = state["V"], state["v"]
             ctx.check(L.pb_pod_basis_full(ctx.h, U.ptr, n_h_loc, N_S, U.ld, V.ptr, V.ld))
+            ctx.check(L.pb_download_forked(ctx.h, hV, V.ptr, n_h_loc * nl * 8))      # V crosses PCIe while V^T U runs
             ctx.check(L.pb_project(ctx.h, V.ptr, V.ld, nl, U.ptr, U.ld, n_h_loc, N_S, v.ptr))
-            vptr = v.ptr
+            ctx.check(L.pb_download_async(ctx.h, hv, v.ptr, N_S * nl * 8))
+            ctx.sync()
+            return
         else:
             # row-sharded host call: each rank's chunked upload overlaps its Gram (pb_gram_host), then the same
             # all-reduces as the resident step

@@ -94,6 +94,9 @@ int  pb_upload(pb_ctx* ctx, void* dev, const void* host, size_t bytes);   /* H2D
 int  pb_download(pb_ctx* ctx, void* host, const void* dev, size_t bytes); /* D2H + sync */
 int  pb_upload_async(pb_ctx* ctx, void* dev, const void* host, size_t bytes);
 int  pb_download_async(pb_ctx* ctx, void* host, const void* dev, size_t bytes);
+/* D2H on the context's copy stream: ordered after everything queued so far, concurrent with what is queued next;
+ * pb_sync joins it.  (V travelling to the host while pb_project runs.) */
+int  pb_download_forked(pb_ctx* ctx, void* host, const void* dev, size_t bytes);
 /* Context-owned device slab for the host-facing calls (pb_pod_host / pb_gram_host receive the uploaded matrix in
  * it): grown on demand, reused across calls (a cudaMalloc / cudaFree pair of 1.28 GB per perform_pod call costs
  * milliseconds and synchronises the device).  Valid until a later pb_slab asks for more, or pb_destroy. */

@@ -44,6 +44,7 @@ SIGNATURES = {
     "pb_download": (_int, [_vp, _vp, _vp, C.c_size_t]),
     "pb_upload_async": (_int, [_vp, _vp, _vp, C.c_size_t]),
     "pb_download_async": (_int, [_vp, _vp, _vp, C.c_size_t]),
+    "pb_download_forked": (_int, [_vp, _vp, _vp, C.c_size_t]),
     "pb_slab": (_int, [_vp, C.c_size_t, _pvp]),
     "pb_upload_matrix": (_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
     "pb_host_alloc": (_int, [C.c_size_t, _pvp]),

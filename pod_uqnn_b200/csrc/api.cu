@@ -147,7 +147,12 @@ const char* pb_last_error(const pb_ctx* ctx) {
     std::lock_guard<std::mutex> l(g_err_mu); return g_err.c_str();
 }
 int pb_set_stream(pb_ctx* ctx, void* s) { PB_ENTER(ctx); ctx->stream = s ? (cudaStream_t)s : ctx->own_stream; return PB_OK; }
-int pb_sync(pb_ctx* ctx) { PB_ENTER(ctx); PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return PB_OK; }
+int pb_sync(pb_ctx* ctx) {
+    PB_ENTER(ctx);
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->fork_pending) { ctx->fork_pending = false; PB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream)); }
+    return PB_OK;
+}
 int pb_device_info(pb_ctx* ctx, int* sm, int* maj, int* min_, size_t* mem) {
     PB_ENTER(ctx);
     cudaDeviceProp p; PB_CUDA(ctx, cudaGetDeviceProperties(&p, ctx->device));
@@ -191,6 +196,21 @@ int pb_upload_async(pb_ctx* ctx, void* dev, const void* host, size_t bytes) {
 }
 int pb_download_async(pb_ctx* ctx, void* host, const void* dev, size_t bytes) {
     PB_ENTER(ctx); PB_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream)); return PB_OK;
+}
+// D2H of a finished result on the context's COPY stream: ordered after the work queued so far, overlapping what is
+// queued next (e.g. V on its way to the host while the projection V^T U runs).  pb_sync waits for it as well.  The
+// source buffer must not be rewritten before pb_sync.
+int pb_download_forked(pb_ctx* ctx, void* host, const void* dev, size_t bytes) {
+    PB_ENTER(ctx); if (!host || !dev) return PB_ERR_ARG;
+    if (!ctx->copy_stream) {
+        PB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int c = 0; c < 16; ++c) PB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->chunk_ev[c], cudaEventDisableTiming));
+    }
+    PB_CUDA(ctx, cudaEventRecord(ctx->chunk_ev[14], ctx->stream));
+    PB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[14], 0));
+    PB_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    ctx->fork_pending = true;
+    return PB_OK;
 }
 int pb_upload(pb_ctx* ctx, void* dev, const void* host, size_t bytes) { PB_TRY(pb_upload_async(ctx, dev, host, bytes)); return pb_sync(ctx); }
 namespace { int download_staged(pb_ctx* ctx, char* host, const char* dev, size_t bytes); bool host_is_pinned(const void* p); }

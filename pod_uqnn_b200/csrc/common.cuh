@@ -29,6 +29,7 @@ struct pb_ctx {
     double* h_sig = nullptr; size_t h_sig_cap = 0; int64_t sig_count = 0, sig_total = 0;
     bool tn_timing_pending = false;
     cudaStream_t copy_stream = nullptr;             // pb_pod_host: chunked upload overlapped with the Gram
+    bool fork_pending = false;                      // pb_download_forked: a D2H copy is in flight on copy_stream (pb_sync joins it)
     cudaEvent_t chunk_ev[16] = {nullptr};
     double* Gpart = nullptr; size_t Gpart_cap = 0;
     void* stage[PB_STAGE_SLOTS] = {nullptr};        // pinned staging ring for pageable host inputs (api.cu)

@@ -629,6 +629,24 @@ def test_pod_host_tsqr_overlapped_upload(ctx, pinned):
             L.pb_host_free(hp)
 
 
+def test_download_forked_overlaps_and_joins_at_sync(ctx):
+    """pb_download_forked: D2H on the copy stream, ordered after the producer, joined by pb_sync."""
+    rng = np.random.default_rng(44)
+    A = rng.standard_normal((200000, 16)); B = rng.standard_normal((16, 16))
+    L = _lib.lib()
+    Ad, Bd, Yd, Zd = ctx.to_device(A), ctx.to_device(B), ctx.alloc(200000, 16), ctx.alloc(200000, 16)
+    hp = C.c_void_p(); assert L.pb_host_alloc(Yd.nbytes, C.byref(hp)) == 0
+    try:
+        host = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_double)), shape=(200000, 16)); host[...] = 0.
+        ctx.check(L.pb_gemm_nn(ctx.h, Ad.ptr, Ad.ld, 200000, 16, Bd.ptr, Bd.ld, 16, Yd.ptr, Yd.ld))      # producer
+        ctx.check(L.pb_download_forked(ctx.h, hp, Yd.ptr, Yd.nbytes))
+        ctx.check(L.pb_gemm_nn(ctx.h, Yd.ptr, Yd.ld, 200000, 16, Bd.ptr, Bd.ld, 16, Zd.ptr, Zd.ld))      # runs beside the copy
+        ctx.sync()
+        assert cmp.rel_err(host, A @ B) < 1e-13 and cmp.rel_err(Zd.download(), A @ B @ B) < 1e-13
+    finally:
+        L.pb_host_free(hp)
+
+
 def test_refine_rows_override_is_scoped_to_one_decomposition(ctx):
     """pb_pod_set_refine_rows (row-sharded callers: the largest slab of the job) changes the a-priori estimate of the
     decomposition in progress only: every new Gram clears it, so a later single-GPU pb_pod on the same context is not
