@@ -168,10 +168,11 @@ int  pb_gemm_nn(pb_ctx* ctx, const double* A_dev, int64_t lda, int64_t n_rows, i
                 const double* B_dev, int64_t ldb, int64_t k, double* Y_dev, int64_t ldy);
 
 /* Eigen-decomposition of the (all-reduced) Gram + truncation rank (pod.py:22-32).
- * mode as above; eps / n_L_in as perform_pod(U, eps, n_L).  On return *n_L is the
- * rank and *n_keep the number of rotated columns the second pass needs (0 for
- * PB_POD_GRAM).  sigma_host (nullable) receives min(n_cols, capacity) singular
- * values, zero beyond the numerical rank. */
+ * mode as above; eps / n_L_in as perform_pod(U, eps, n_L).  On return *n_keep is the
+ * number of rotated columns the second pass needs (0 for PB_POD_GRAM) and *n_L the
+ * rank -- provisional (the numerical rank) when *n_keep > 0: the second pass
+ * (pb_pod_pass2_gram / pb_pod_pass2_finish) decides sigma and n_L from the rotated
+ * block, so the first pass spends no rank kernel / host round trip on them. */
 int  pb_pod_from_gram(pb_ctx* ctx, const double* G_dev, int64_t n_cols, double eps, int n_L_in,
                       int mode, int* n_L, int* n_keep);
 /* Second pass (modes GRAM2 / ACCURATE): Y = A W_keep on the local slab, G2 = Y^T Y.

@@ -321,8 +321,14 @@ int pb_pod_from_gram(pb_ctx* ctx, const double* G, int64_t m, double eps, int n_
                        &ctx->r, &ctx->sweeps1, 40));
     ctx->n_keep = (mode == PB_POD_GRAM) ? 0 : ctx->r;
     if (n_keep) *n_keep = ctx->n_keep;
-    PB_TRY(fetch_sigma(ctx, ctx->sig, m, m));
-    PB_TRY(finish_rank(ctx, ctx->sig, m, ctx->r, eps, n_L_in, n_L));
+    if (ctx->n_keep > 0) {
+        // a second pass follows and decides sigma and n_L from the rotated block: no rank kernel, no host round trip
+        // here.  *n_L is provisional (the numerical rank) until pb_pod_pass2_finish.
+        ctx->n_L = ctx->r; *n_L = ctx->r;
+    } else {
+        PB_TRY(fetch_sigma(ctx, ctx->sig, m, m));
+        PB_TRY(finish_rank(ctx, ctx->sig, m, ctx->r, eps, n_L_in, n_L));
+    }
     t.stop();
     return PB_OK;
 }
@@ -463,10 +469,32 @@ int pb_pod_pass2_finish(pb_ctx* ctx, const double* G2, double eps, int n_L_in, i
     PB_TRY(pb_reserve(ctx, &ctx->nrm2, &ctx->nrm2_cap, (size_t)keep + 32));
     PB_TRY(pb_reserve_int(ctx, &ctx->perm2, &ctx->perm2_cap, (size_t)keep + 64));
     // G2 = D (I + E) D is graded and nearly diagonal: no shift, no truncation (relative accuracy)
-    PB_TRY(pbi_eig_psd(ctx, G2, keep, 0., 0., &ctx->At2, &ctx->At2_cap, ctx->sig2, ctx->nrm2, ctx->perm2,
-                       &ctx->r2, &ctx->sweeps2, 40));
-    PB_TRY(fetch_sigma(ctx, ctx->sig2, keep, ctx->m));
-    PB_TRY(finish_rank(ctx, ctx->sig2, keep, ctx->r2, eps, n_L_in, n_L));
+    bool done = false;
+    static const bool queued_ok = []{ const char* e = getenv("PB_EIG_SMALL_QUEUED"); return !e || atoi(e) != 0; }();
+    if (queued_ok && keep <= 32 && n_L_in == 0) {
+        // one host round trip for the whole small decomposition (Cholesky, single-pair Jacobi, norms, sort, rank rule)
+        int rq = pbi_eig_psd_small_queued(ctx, G2, keep, &ctx->At2, &ctx->At2_cap, ctx->sig2, ctx->nrm2, ctx->perm2, eps);
+        if (rq < 0) return rq;
+        if (rq == PB_OK) {
+            PB_TRY(fetch_sigma(ctx, ctx->sig2, keep, ctx->m));
+            PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            const int r = ctx->h_int[0], nl = ctx->h_int[2];
+            if (ctx->h_int[5] == 1 && ctx->h_int[4] == 1 && r > 0 && nl > 0) {
+                ctx->r2 = r; ctx->sweeps2 = 1;
+                ctx->sigma_host.assign((size_t)ctx->sig_total, 0.);
+                memcpy(ctx->sigma_host.data(), ctx->h_sig, sizeof(double) * (size_t)std::min(ctx->sig_count, ctx->sig_total));
+                ctx->sigma_pending = false;
+                ctx->n_L = std::min(nl, r); *n_L = ctx->n_L;
+                done = true;
+            }
+        }
+    }
+    if (!done) {     // larger blocks, a fixed n_L, or a solve that did not end on a clean sweep: the general path
+        PB_TRY(pbi_eig_psd(ctx, G2, keep, 0., 0., &ctx->At2, &ctx->At2_cap, ctx->sig2, ctx->nrm2, ctx->perm2,
+                           &ctx->r2, &ctx->sweeps2, 40));
+        PB_TRY(fetch_sigma(ctx, ctx->sig2, keep, ctx->m));
+        PB_TRY(finish_rank(ctx, ctx->sig2, keep, ctx->r2, eps, n_L_in, n_L));
+    }
     ctx->pass2_done = true;
     ctx->refine_steps = refine_steps_needed(ctx);
     if (ctx->pass2_t_started) {

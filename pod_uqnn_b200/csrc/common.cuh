@@ -129,6 +129,8 @@ int pbi_transpose(pb_ctx* ctx, const double* in, int64_t rows, int64_t cols, int
 // eigen-decomposition of a PSD matrix G (m x m, ld m): factor vectors At (r x m) sorted by
 // descending norm, sig[0..m) (zero beyond r).  tol_rel: Cholesky truncation (relative to max diag),
 // shift_rel: diagonal shift relative to trace (full-rank mode), returns r.
+int pbi_eig_psd_small_queued(pb_ctx* ctx, const double* G, int64_t m, double** At_buf, size_t* At_cap, double* sig_dev,
+                             double* nrm_dev, int* perm_dev, double eps);
 int pbi_eig_psd(pb_ctx* ctx, const double* G, int64_t m, double tol_rel, double shift_rel,
                 double** At_buf, size_t* At_cap, double* sig_dev, double* nrm_dev, int* perm_dev,
                 int* r_out, int* sweeps_out, int max_sweeps);

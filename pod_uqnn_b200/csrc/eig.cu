@@ -609,6 +609,44 @@ int pbi_eig_psd(pb_ctx* ctx, const double* G, int64_t m, double tol_rel, double 
     return PB_OK;
 }
 
+// Orders <= 32 (the second-pass Gram of the rotated block, C2: 27): everything a decomposition needs -- pivoted Cholesky
+// in one CTA, the single-pair Jacobi solve iterated to a clean sweep inside its kernel, norms, sort, the rank rule --
+// is queued WITHOUT a host round trip; the caller synchronises once and reads h_int: [0] r, [2] n_L, [4] the Jacobi
+// solve ended on a clean sweep, [5] the Cholesky finished.  (pbi_eig_psd + pbi_rank take three round trips for the same
+// kernels: the factor rank, the convergence flag, the rank.)  If a flag is not as expected the caller repeats the
+// decomposition through pbi_eig_psd; G is not modified.
+int pbi_chol_small_launch(pb_ctx*, const double*, int64_t, double*, int64_t, double, double, int*, double*, int, double*, double*, int*);
+int pbi_eig_psd_small_queued(pb_ctx* ctx, const double* G, int64_t m, double** At_buf, size_t* At_cap, double* sig_dev,
+                             double* nrm_dev, int* perm_dev, double eps) {
+    if (m <= 0 || m > JP) return 1;
+    const int64_t ldm = (m + 7) / 8 * 8;
+    const int64_t cap_rows = JP;
+    PB_TRY(pb_reserve(ctx, At_buf, At_cap, (size_t)cap_rows * ldm));
+    double* At = *At_buf;
+    EigScratch sc; PB_TRY(get_scratch(ctx, m, &sc));
+    PB_CUDA(ctx, cudaMemsetAsync(At, 0, sizeof(double) * (size_t)cap_rows * ldm, ctx->stream));
+    PB_CUDA(ctx, cudaMemsetAsync(ctx->d_int, 0, 6 * sizeof(int), ctx->stream));
+    PB_TRY(pbi_chol_small_launch(ctx, G, m, At, ldm, 0., 0., ctx->d_int + 0, sc.shift, (int)m, sc.d, sc.shift + 1, ctx->d_int + 5));
+    const double tol = std::max(4., sqrt((double)m)) * DBL_EPSILON;
+    const size_t jac_smem = sizeof(double) * 2 * JP * JPX;
+    PB_TRY(pbi_smem_optin(ctx, (const void*)jacobi_pair_kernel, jac_smem));
+    JacArgs ja{At, ldm, 2, 0, tol, ctx->d_int + 1, 16, 0, 0, ctx->d_int + 4};
+    jacobi_pair_kernel<<<1, 256, jac_smem, ctx->stream>>>(ja);
+    PB_LAUNCH_CHECK(ctx);
+    const int nvec = JP;
+    norms_kernel<<<nvec, 256, 0, ctx->stream>>>(At, ldm, nvec, sc.nrm2, 0, 0);
+    PB_LAUNCH_CHECK(ctx);
+    const int npow2 = JP;
+    const size_t sort_smem = (sizeof(double) + sizeof(int)) * (size_t)npow2;
+    PB_TRY(pbi_smem_optin(ctx, (const void*)sort_kernel, sort_smem));
+    sort_kernel<<<1, 1024, sort_smem, ctx->stream>>>(sc.nrm2, nvec, npow2, sc.shift, sig_dev, nrm_dev, (int)m, perm_dev, ctx->d_int + 3, 0, 0, 0);
+    PB_LAUNCH_CHECK(ctx);
+    rank_kernel<<<1, 32, 0, ctx->stream>>>(sig_dev, (int)m, eps, ctx->d_int + 2, 0);
+    PB_LAUNCH_CHECK(ctx);
+    PB_CUDA(ctx, cudaMemcpyAsync(ctx->h_int, ctx->d_int, 6 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    return PB_OK;
+}
+
 int pbi_rank(pb_ctx* ctx, const double* sig_dev, int64_t count, double eps, int* n_L_out) {
     rank_kernel<<<1, 32, 0, ctx->stream>>>(sig_dev, (int)count, eps, ctx->d_int + 2, 0);
     PB_LAUNCH_CHECK(ctx);
