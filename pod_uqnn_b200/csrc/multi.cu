@@ -224,6 +224,7 @@ int pod_rank(pb_multi* m, int p, const double* U_host, int64_t ldu_host, int64_t
             MB_STEP(all_gather(m, p, m->F[p], cap * n, m->S[p]));
             // the factor of the stack is replicated: identical input bits -> identical rank and factors on every GPU
             if (plain) { rc = pb_tsqr_r(c, m->S[p], m->P * cap, n, n, m->F[p]); f_rows = n; }
+            else if (m->P * cap <= std::min<int64_t>(512, n)) { F = m->S[p]; f_rows = m->P * cap; rc = PB_OK; }   // a short stack is a valid factor as it is
             else rc = pb_tsqr_factor(c, m->S[p], m->P * cap, n, n, m->F[p], &f_rows);
             MB_STEP(rc);
         }

@@ -56,6 +56,9 @@ def _max_over_ranks(backend, value, group=None):
     return int(t.item())
 
 
+SMALL_STACK_ROWS = 512      # stacked leaf factors up to this many rows go to the pivoted QR directly
+
+
 def pod_sharded_tsqr(backend, A_local, eps=0., n_L=0, group=None, full=False):
     """TSQR mode: one leaf per rank.  F_p = the rank-revealing Householder factor of A_p (pb_tsqr_factor: block
     pivoting, stops at the numerical rank; Q not formed), all-gather of the first max_p rows(F_p) rows, the factor of
@@ -74,7 +77,12 @@ def pod_sharded_tsqr(backend, A_local, eps=0., n_L=0, group=None, full=False):
         Fc = F[:cap]
         stack = _all_gather_stack(backend, Fc, group)
         if stack is not Fc:
-            F, rows = backend.tsqr_factor(stack)
+            if stack.shape[0] <= min(SMALL_STACK_ROWS, stack.shape[1]):
+                # a short stack IS a valid factor (A^T A = S^T S): the pivoted QR of pod_from_factor takes it as it is; a
+                # blocked QR of it first would be all fixed latency (2 panels ~ 1.6 ms at C2 for 256 x 1000)
+                F, rows = stack, stack.shape[0]
+            else:
+                F, rows = backend.tsqr_factor(stack)
         n_L_out = backend.pod_from_factor(F, rows, eps, n_L)
     V = backend.basis(A_local, None, n_L_out)
     return V, backend.sigma(), n_L_out
