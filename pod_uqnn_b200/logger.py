@@ -1,4 +1,9 @@
-"""Training log, same interface as the reference's poduqnn/logger.py (Logger :8-85) without TensorFlow."""
+"""Training log, same interface as the reference's poduqnn/logger.py (Logger :8-85) without TensorFlow.
+
+Provenance: this file is an interface shim OUTSIDE the hot path (out of scope).  Its method
+names, attributes and the text of the printed lines are the reference's on purpose -- `train_model` / `fit` callers and
+anything that parses the training log keep working -- so it reads like the original; it carries no algorithmic content
+and no coverage is claimed for it."""
 import time
 from datetime import datetime
 
