@@ -130,7 +130,8 @@ def test_gemm_tn_qr_trailing_product(ctx, rows, n):
 
 
 @pytest.mark.parametrize("rows,m,k", [(1000, 200, 14), (5000, 1000, 71), (777, 333, 333), (130, 14, 1000),
-                                      (300, 71, 2), (999, 15, 33), (1, 3, 1)])
+                                      (300, 71, 2), (999, 15, 33), (1, 3, 1), (4001, 512, 100), (3000, 260, 111),
+                                      (2500, 96, 118), (2000, 300, 128)])
 def test_gemm_nn(ctx, rows, m, k):
     rng = np.random.default_rng(rows + m + k)
     A, B = rng.standard_normal((rows, m)), rng.standard_normal((m, k))
